@@ -1,0 +1,461 @@
+// api.cu — C ABI of include/dbgphmm_b200.h: handles, row export, and the bulk (read-set) entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "engine.h"
+
+static const double LN2 = 0.693147180559945309417232121458;
+
+// ------------------------------------------------------------------ reads / mappings handles
+extern "C" int dbgphmm_reads_create(uint64_t n_reads, const uint64_t* offsets, const uint8_t* bases, dbgphmm_reads** out) {
+    if (!out || !offsets || (n_reads && offsets[n_reads] && !bases)) { dbg_set_error("reads_create: bad argument"); return DBGPHMM_ERR_INVALID; }
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (offsets[r + 1] < offsets[r]) { dbg_set_error("reads_create: offsets not monotone"); return DBGPHMM_ERR_INVALID; }
+    const uint64_t total = offsets[n_reads];
+    for (uint64_t i = 0; i < total; i++) {
+        uint8_t b = bases[i];
+        if (b != 'A' && b != 'C' && b != 'G' && b != 'T') { dbg_set_error("reads_create: bases must be uppercase ACGT (collection.rs:236-249)"); return DBGPHMM_ERR_INVALID; }
+    }
+    dbgphmm_reads* r = new dbgphmm_reads();
+    r->n_reads = n_reads;
+    r->off.assign(offsets, offsets + n_reads + 1);
+    r->bases.assign(bases, bases + total);
+    *out = r;
+    return DBGPHMM_OK;
+}
+extern "C" void dbgphmm_reads_destroy(dbgphmm_reads* r) {
+    if (!r) return;
+    if (r->d_bases) { cudaSetDevice(r->device); cudaFree(r->d_bases); }
+    delete r;
+}
+extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) {
+    if (!m || !r) { dbg_set_error("reads_to_device: bad argument"); return DBGPHMM_ERR_INVALID; }
+    if (r->d_bases && r->device == m->device) return DBGPHMM_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (r->d_bases) { cudaFree(r->d_bases); r->d_bases = nullptr; }
+    CUDA_TRY(cudaMalloc((void**)&r->d_bases, std::max<size_t>(r->bases.size(), 1)));
+    if (!r->bases.empty()) CUDA_TRY(cudaMemcpy(r->d_bases, r->bases.data(), r->bases.size(), cudaMemcpyHostToDevice));
+    r->device = m->device;
+    return DBGPHMM_OK;
+}
+
+extern "C" int dbgphmm_mappings_create(uint64_t n_reads, const uint64_t* read_off, const uint64_t* row_off, const uint32_t* nodes,
+                                       const double* logp, dbgphmm_mappings** out) {
+    if (!out || !read_off || !row_off) { dbg_set_error("mappings_create: bad argument"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_mappings* mp = new dbgphmm_mappings();
+    mp->read_off.assign(read_off, read_off + n_reads + 1);
+    uint64_t n_rows = read_off[n_reads];
+    mp->row_off.assign(row_off, row_off + n_rows + 1);
+    uint64_t n_ent = row_off[n_rows];
+    if (n_ent) { mp->nodes.assign(nodes, nodes + n_ent); if (logp) mp->logp.assign(logp, logp + n_ent); else mp->logp.assign(n_ent, 0.0); }
+    *out = mp;
+    return DBGPHMM_OK;
+}
+extern "C" void dbgphmm_mappings_destroy(dbgphmm_mappings* mp) { delete mp; }
+extern "C" int dbgphmm_mappings_sizes(const dbgphmm_mappings* mp, uint64_t* n_reads, uint64_t* n_rows, uint64_t* n_entries) {
+    if (!mp) { dbg_set_error("mappings_sizes: null"); return DBGPHMM_ERR_INVALID; }
+    if (n_reads) *n_reads = mp->read_off.empty() ? 0 : mp->read_off.size() - 1;
+    if (n_rows) *n_rows = mp->row_off.empty() ? 0 : mp->row_off.size() - 1;
+    if (n_entries) *n_entries = mp->nodes.size();
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_mappings_export(const dbgphmm_mappings* mp, uint64_t* read_off, uint64_t* row_off, uint32_t* nodes, double* logp) {
+    if (!mp) { dbg_set_error("mappings_export: null"); return DBGPHMM_ERR_INVALID; }
+    std::memcpy(read_off, mp->read_off.data(), 8 * mp->read_off.size());
+    std::memcpy(row_off, mp->row_off.data(), 8 * mp->row_off.size());
+    if (!mp->nodes.empty()) { std::memcpy(nodes, mp->nodes.data(), 4 * mp->nodes.size()); std::memcpy(logp, mp->logp.data(), 8 * mp->logp.size()); }
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32_t n_nodes, double* freqs) {
+    if (!mp || !freqs) { dbg_set_error("mappings_to_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
+    // hint.rs:161-171 — a plain host-side scatter of exp(logp); not on the DP path, no device work involved
+    std::fill(freqs, freqs + n_nodes, 0.0);
+    for (size_t i = 0; i < mp->nodes.size(); i++) {
+        if (mp->nodes[i] >= n_nodes) { dbg_set_error("mapping node id out of range"); return DBGPHMM_ERR_INVALID; }
+        freqs[mp->nodes[i]] += std::exp(mp->logp[i]);
+    }
+    return DBGPHMM_OK;
+}
+
+// ------------------------------------------------------------------ PHMMTables of one read
+struct dbgphmm_tables {
+    dbgphmm_model* m = nullptr;
+    int dir = 0, kind = 0;
+    std::vector<uint8_t> bases;
+    uint8_t* d_bases = nullptr;
+    RowStore store;
+    std::vector<RowDesc> desc;  // host copy
+};
+
+static int tables_finish(dbgphmm_tables* t) {
+    t->desc.resize(t->store.n_desc);
+    if (t->store.n_desc) CUDA_TRY(cudaMemcpy(t->desc.data(), t->store.d_desc, sizeof(RowDesc) * t->store.n_desc, cudaMemcpyDeviceToHost));
+    return DBGPHMM_OK;
+}
+extern "C" void dbgphmm_tables_destroy(dbgphmm_tables* t) {
+    if (!t) return;
+    cudaSetDevice(t->m->device);
+    t->store.release();
+    cudaFree(t->d_bases);
+    delete t;
+}
+static int one_job(dbgphmm_model* m, const uint8_t* bases, uint64_t n, const dbgphmm_mappings* mp, uint64_t read_index, dbgphmm_tables* t,
+                   std::vector<HJob>* jobs, DevMappings* dmap, bool need_map) {
+    if (n == 0 || n > 0x7fffffffu) { dbg_set_error("read length must be in [1, 2^31)"); return DBGPHMM_ERR_INVALID; }
+    for (uint64_t i = 0; i < n; i++)
+        if (bases[i] != 'A' && bases[i] != 'C' && bases[i] != 'G' && bases[i] != 'T') { dbg_set_error("bases must be uppercase ACGT"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    t->m = m; t->bases.assign(bases, bases + n);
+    CUDA_TRY(cudaMalloc((void**)&t->d_bases, n));
+    CUDA_TRY(cudaMemcpy(t->d_bases, bases, n, cudaMemcpyHostToDevice));
+    HJob j{}; j.read = 0; j.x = 0; j.base_off = 0; j.len = (uint32_t)n; j.map_row0 = 0;
+    if (need_map) {
+        if (!mp || read_index + 1 >= mp->read_off.size()) { dbg_set_error("mapping kind needs a mappings handle and a valid read index"); return DBGPHMM_ERR_INVALID; }
+        if (mp->read_off[read_index + 1] - mp->read_off[read_index] != n) { dbg_set_error("mapping length differs from read length"); return DBGPHMM_ERR_INVALID; }
+        ST_TRY(upload_mappings(m, mp, dmap));
+        j.map_row0 = mp->read_off[read_index];
+    }
+    jobs->push_back(j);
+    return DBGPHMM_OK;
+}
+
+extern "C" int dbgphmm_forward(dbgphmm_model* m, const uint8_t* bases, uint64_t n, int kind, const dbgphmm_mappings* mapping,
+                               uint64_t read_index, dbgphmm_tables** out) {
+    if (!m || !bases || !out || kind < 0 || kind > 3) { dbg_set_error("forward: bad argument"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_tables* t = new dbgphmm_tables();
+    t->dir = 0; t->kind = kind;
+    std::vector<HJob> jobs; DevMappings dmap;
+    int st = one_job(m, bases, n, mapping, read_index, t, &jobs, &dmap, kind == DBGPHMM_FWD_MAPPING);
+    if (st == DBGPHMM_OK) st = run_forward(m, jobs, t->d_bases, kind, true, true, kind == DBGPHMM_FWD_MAPPING ? &dmap : nullptr, &t->store);
+    if (st == DBGPHMM_OK) st = tables_finish(t);
+    dmap.release();
+    if (st != DBGPHMM_OK) { if (t->m) dbgphmm_tables_destroy(t); else delete t; return st; }
+    *out = t;
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_backward(dbgphmm_model* m, const uint8_t* bases, uint64_t n, int kind, const dbgphmm_mappings* mapping,
+                                uint64_t read_index, const dbgphmm_tables* fwd, dbgphmm_tables** out) {
+    if (!m || !bases || !out || kind < 0 || kind > 3) { dbg_set_error("backward: bad argument"); return DBGPHMM_ERR_INVALID; }
+    if (kind == DBGPHMM_BWD_BY_FORWARD && (!fwd || fwd->dir != 0 || fwd->bases.size() != n)) { dbg_set_error("backward_by_forward needs the forward tables of the same read"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_tables* t = new dbgphmm_tables();
+    t->dir = 1; t->kind = kind;
+    std::vector<HJob> jobs; DevMappings dmap;
+    int st = one_job(m, bases, n, mapping, read_index, t, &jobs, &dmap, kind == DBGPHMM_BWD_MAPPING);
+    if (st == DBGPHMM_OK) st = run_backward(m, jobs, t->d_bases, kind, true, kind == DBGPHMM_BWD_MAPPING ? &dmap : nullptr, fwd ? &fwd->store : nullptr, &t->store);
+    if (st == DBGPHMM_OK) st = tables_finish(t);
+    dmap.release();
+    if (st != DBGPHMM_OK) { if (t->m) dbgphmm_tables_destroy(t); else delete t; return st; }
+    *out = t;
+    return DBGPHMM_OK;
+}
+extern "C" uint64_t dbgphmm_tables_len(const dbgphmm_tables* t) { return t ? t->desc.size() : 0; }
+extern "C" int dbgphmm_tables_full_prob(const dbgphmm_tables* t, double* logp) {
+    if (!t || !logp || t->desc.empty()) { dbg_set_error("tables_full_prob: empty tables (table.rs:380-393 panics)"); return DBGPHMM_ERR_INVALID; }
+    *logp = t->dir == 0 ? xlog(t->desc.back().e) : xlog(t->desc.front().mb);
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_tables_row_info(const dbgphmm_tables* t, int64_t row, uint64_t info[3], double sc[3]) {
+    if (!t || row < -1 || row >= (int64_t)t->desc.size()) { dbg_set_error("tables_row_info: row out of range"); return DBGPHMM_ERR_INVALID; }
+    if (row < 0) {  // init_table: f_init (forward.rs:255-266) / b_init (backward.rs:197-211), both dense
+        info[0] = 1; info[1] = t->m->N; info[2] = t->m->N;
+        sc[0] = t->dir == 0 ? 0.0 : -INFINITY; sc[1] = -INFINITY; sc[2] = -INFINITY;
+        return DBGPHMM_OK;
+    }
+    const RowDesc& r = t->desc[row];
+    info[0] = r.kind == ROW_DENSE; info[1] = r.kind == ROW_DENSE ? t->m->N : r.n_mi; info[2] = r.kind == ROW_DENSE ? t->m->N : r.n_d;
+    sc[0] = xlog(r.mb); sc[1] = xlog(r.ib); sc[2] = xlog(r.e);
+    return DBGPHMM_OK;
+}
+static inline double lg(double v, int e) { return v == 0.0 ? -INFINITY : std::log(v) + (double)e * LN2; }
+
+// raw copy of a stored row to the host
+struct HostRow { std::vector<double> m, i, d; std::vector<int> ex; std::vector<uint32_t> id; std::vector<uint16_t> dlist; };
+static int fetch_row(const dbgphmm_tables* t, const RowDesc& r, HostRow* h) {
+    const dbgphmm_model* m = t->m;
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (r.kind == ROW_DENSE) {
+        uint32_t N = m->N, Np = t->store.pool.Np;
+        const char* sl = t->store.pool.base + r.off * t->store.pool.slab_bytes;
+        h->m.resize(N); h->i.resize(N); h->d.resize(N); h->ex.resize(N);
+        CUDA_TRY(cudaMemcpy(h->m.data(), sl, 8ull * N, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h->i.data(), sl + 8ull * Np, 8ull * N, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h->d.data(), sl + 16ull * Np, 8ull * N, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h->ex.data(), sl + 24ull * Np, 4ull * N, cudaMemcpyDeviceToHost));
+    } else {
+        uint32_t n = r.n_ent;
+        const char* pay = t->store.arena.base + r.off;
+        h->m.resize(n); h->i.resize(n); h->d.resize(n); h->ex.resize(n); h->id.resize(n); h->dlist.resize(r.n_d);
+        if (n) {
+            CUDA_TRY(cudaMemcpy(h->m.data(), pay, 8ull * n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(h->i.data(), pay + 8ull * n, 8ull * n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(h->d.data(), pay + 16ull * n, 8ull * n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(h->id.data(), pay + 24ull * n, 4ull * n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(h->ex.data(), pay + 28ull * n, 4ull * n, cudaMemcpyDeviceToHost));
+        }
+        if (r.n_d) CUDA_TRY(cudaMemcpy(h->dlist.data(), pay + 32ull * n, 2ull * r.n_d, cudaMemcpyDeviceToHost));
+    }
+    return DBGPHMM_OK;
+}
+
+extern "C" int dbgphmm_tables_row_export(const dbgphmm_tables* t, int64_t row, uint32_t* ids_mi, double* om, double* oi, uint32_t* ids_d, double* od) {
+    if (!t || row < -1 || row >= (int64_t)t->desc.size()) { dbg_set_error("tables_row_export: row out of range"); return DBGPHMM_ERR_INVALID; }
+    const dbgphmm_model* m = t->m;
+    if (row < 0) {
+        double v = t->dir == 0 ? -INFINITY : m->params.p_end;
+        for (uint32_t k = 0; k < m->N; k++) { om[k] = v; oi[k] = v; od[k] = v; }
+        return DBGPHMM_OK;
+    }
+    const RowDesc& r = t->desc[row];
+    HostRow h;
+    ST_TRY(fetch_row(t, r, &h));
+    if (r.kind == ROW_DENSE) {
+        for (uint32_t p = 0; p < m->N; p++) {
+            uint32_t o = m->orig_of[p];
+            om[o] = lg(h.m[p], h.ex[p]); oi[o] = lg(h.i[p], h.ex[p]); od[o] = lg(h.d[p], h.ex[p]);
+        }
+    } else {
+        for (uint32_t e = 0; e < r.n_mi; e++) { ids_mi[e] = m->orig_of[h.id[e]]; om[e] = lg(h.m[e], h.ex[e]); oi[e] = lg(h.i[e], h.ex[e]); }
+        for (uint32_t a = 0; a < r.n_d; a++) { uint32_t e = h.dlist[a]; ids_d[a] = m->orig_of[h.id[e]]; od[a] = lg(h.d[e], h.ex[e]); }
+    }
+    return DBGPHMM_OK;
+}
+
+extern "C" int dbgphmm_tables_row_top_nodes(const dbgphmm_tables* t, int64_t row, int by_ratio, uint32_t k, double ratio, uint32_t* out, uint32_t* n_out) {
+    if (!t || !out || !n_out || row < 0 || row >= (int64_t)t->desc.size()) { dbg_set_error("tables_row_top_nodes: row out of range"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_model* m = t->m;
+    const RowDesc& r = t->desc[row];
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (r.kind == ROW_DENSE) {  // the device selection kernel used by the forward/backward drivers
+        DevBuf b_req, b_ids, b_cnt;
+        std::vector<SelectReq> rq(1);
+        rq[0].slab = r.off; rq[0].k = by_ratio ? MAX_ACTIVE : std::min<uint32_t>(k, MAX_ACTIVE); rq[0].by_ratio = by_ratio; rq[0].ratio = ratio; rq[0].active_idx = -1; rq[0].out = 0;
+        ST_TRY(dev_upload(b_req, rq, m->stream));
+        ST_TRY(b_ids.alloc(sizeof(uint32_t) * MAX_ACTIVE)); ST_TRY(b_cnt.alloc(sizeof(uint32_t)));
+        ST_TRY(dense_select(m, t->store.pool, b_req.as<SelectReq>(), 1, nullptr, b_ids.as<uint32_t>(), b_cnt.as<uint32_t>()));
+        uint32_t cnt = 0; std::vector<uint32_t> ids(MAX_ACTIVE);
+        CUDA_TRY(cudaMemcpyAsync(&cnt, b_cnt.p, 4, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(ids.data(), b_ids.p, 4 * MAX_ACTIVE, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        for (uint32_t a = 0; a < cnt; a++) out[a] = m->orig_of[ids[a]];
+        *n_out = cnt;
+        return DBGPHMM_OK;
+    }
+    // sparse row: same ordering rule as the device kernels (value desc, then entry position), evaluated on the row's cells
+    HostRow h;
+    ST_TRY(fetch_row(t, r, &h));
+    uint32_t n = r.n_ent;
+    std::vector<uint32_t> ord(n);
+    std::vector<XF> key(n);
+    for (uint32_t e = 0; e < n; e++) { ord[e] = e; key[e] = xnorm(xf(h.m[e] + h.i[e] + h.d[e], h.ex[e])); }
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+        if (key[a].e != key[b].e) return key[a].e > key[b].e;
+        return key[a].v > key[b].v;
+    });
+    uint32_t K = by_ratio ? MAX_ACTIVE : k, cnt = 0;
+    double L0 = n ? xlog(key[ord[0]]) : -INFINITY;
+    for (uint32_t a = 0; a < n && a < K; a++) {
+        if (by_ratio && !(L0 - xlog(key[ord[a]]) < ratio)) continue;
+        out[cnt++] = m->orig_of[h.id[ord[a]]];
+    }
+    *n_out = cnt;
+    return DBGPHMM_OK;
+}
+
+// ------------------------------------------------------------------ PHMMOutput of one read
+static int check_pair(const dbgphmm_model* m, const dbgphmm_tables* f, const dbgphmm_tables* b) {
+    if (!m || !f || !b || f->dir != 0 || b->dir != 1 || f->m != m || b->m != m || f->desc.size() != b->desc.size()) {
+        dbg_set_error("PHMMOutput::new: forward/backward tables do not match (table.rs:473-478 asserts)"); return DBGPHMM_ERR_INVALID;
+    }
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* freqs) {
+    ST_TRY(check_pair(m, fwd, bwd));
+    CUDA_TRY(cudaSetDevice(m->device));
+    DevBuf b_f;
+    ST_TRY(b_f.alloc(sizeof(double) * m->N));
+    CUDA_TRY(cudaMemsetAsync(b_f.p, 0, sizeof(double) * m->N, m->stream));
+    std::vector<HJob> jobs(1);
+    jobs[0] = HJob{0, 0, 0, (uint32_t)fwd->desc.size(), 0};
+    ST_TRY(run_products_freqs(m, jobs, fwd->store, bwd->store, b_f.as<double>()));
+    CUDA_TRY(cudaMemcpy(freqs, b_f.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, int by_ratio, uint32_t n_active,
+                                      double ratio, dbgphmm_mappings** out) {
+    ST_TRY(check_pair(m, fwd, bwd));
+    CUDA_TRY(cudaSetDevice(m->device));
+    std::vector<HJob> jobs(1);
+    jobs[0] = HJob{0, 0, 0, (uint32_t)fwd->desc.size(), 0};
+    dbgphmm_mappings* mp = new dbgphmm_mappings();
+    int st = run_products_mapping(m, jobs, fwd->store, bwd->store, by_ratio, n_active, ratio, mp);
+    if (st != DBGPHMM_OK) { delete mp; return st; }
+    *out = mp;
+    return DBGPHMM_OK;
+}
+
+// ------------------------------------------------------------------ bulk calls
+static void reset_times() { g_times = EngineTimes(); }
+extern "C" int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells) {
+    ms[0] = g_times.dense_ms; ms[1] = g_times.sparse_ms; ms[2] = g_times.product_ms; ms[3] = g_times.total_ms;
+    if (dense_cells) *dense_cells = g_times.dense_cells;
+    return DBGPHMM_OK;
+}
+
+static int check_reads_mappings(const dbgphmm_reads* reads, const dbgphmm_mappings* mp) {
+    if (!mp) return DBGPHMM_OK;
+    if (mp->read_off.size() != reads->n_reads + 1) { dbg_set_error("mappings / reads count mismatch"); return DBGPHMM_ERR_INVALID; }
+    for (uint64_t r = 0; r < reads->n_reads; r++)
+        if (mp->read_off[r + 1] - mp->read_off[r] != reads->off[r + 1] - reads->off[r]) { dbg_set_error("mapping length differs from read length"); return DBGPHMM_ERR_INVALID; }
+    return DBGPHMM_OK;
+}
+
+// split job indices [0, n) into batches whose estimated device footprint fits the budget
+static std::vector<std::pair<size_t, size_t>> plan_batches(const std::vector<uint64_t>& bytes, uint64_t budget, size_t max_jobs) {
+    std::vector<std::pair<size_t, size_t>> out;
+    size_t i = 0;
+    while (i < bytes.size()) {
+        uint64_t acc = 0; size_t j = i;
+        while (j < bytes.size() && j - i < max_jobs && (j == i || acc + bytes[j] <= budget)) { acc += bytes[j]; j++; }
+        out.push_back({i, j});
+        i = j;
+    }
+    return out;
+}
+
+extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads* reads, const dbgphmm_mappings* mappings, int use_max_ratio,
+                                          double* out_logp, double* out_per_read) {
+    if (!m || !reads || !out_logp) { dbg_set_error("to_full_prob_reads: bad argument"); return DBGPHMM_ERR_INVALID; }
+    ST_TRY(check_reads_mappings(reads, mappings));
+    CUDA_TRY(cudaSetDevice(m->device));
+    ST_TRY(dbgphmm_reads_to_device(m, const_cast<dbgphmm_reads*>(reads)));
+    reset_times();
+    EvTimer total(m->stream, &g_times.total_ms);
+    const uint64_t R = reads->n_reads; const uint32_t X = m->n_batch;
+    const int kind = mappings ? DBGPHMM_FWD_MAPPING : (use_max_ratio ? DBGPHMM_FWD_SPARSE_RATIO : DBGPHMM_FWD_SPARSE);
+    DevMappings dmap;
+    if (mappings) ST_TRY(upload_mappings(m, mappings, &dmap));
+    std::vector<HJob> all; all.reserve(R * X);
+    std::vector<uint64_t> bytes; bytes.reserve(R * X);
+    const uint64_t slab = dense_slab_bytes(m->N);
+    for (uint32_t x = 0; x < X; x++)
+        for (uint64_t r = 0; r < R; r++) {
+            uint64_t len = reads->off[r + 1] - reads->off[r];
+            if (len == 0 || len > 0x7fffffffu) { dmap.release(); dbg_set_error("read length must be in [1, 2^31)"); return DBGPHMM_ERR_INVALID; }
+            HJob j{(uint32_t)r, x, reads->off[r], (uint32_t)len, mappings ? mappings->read_off[r] : 0};
+            all.push_back(j);
+            bytes.push_back((mappings ? 0 : 2 * slab) + len * sizeof(RowDesc) + 65536);
+        }
+    std::vector<double> per(all.size());
+    int st = DBGPHMM_OK;
+    for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535)) {
+        std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
+        RowStore F;
+        st = run_forward(m, jobs, reads->d_bases, kind, false, false, mappings ? &dmap : nullptr, &F);
+        if (st == DBGPHMM_OK) for (size_t i = 0; i < jobs.size(); i++) per[bt.first + i] = xlog(F.h_final[i]);
+        F.release();
+        if (st != DBGPHMM_OK) break;
+    }
+    dmap.release();
+    if (st != DBGPHMM_OK) return st;
+    for (uint32_t x = 0; x < X; x++) {
+        double s = 0.0;  // Product over reads = sum of logs, fixed read order (prob.rs:245-249)
+        for (uint64_t r = 0; r < R; r++) { s += per[(size_t)x * R + r]; if (out_per_read) out_per_read[(size_t)x * R + r] = per[(size_t)x * R + r]; }
+        out_logp[x] = s;
+    }
+    return DBGPHMM_OK;
+}
+
+static void run_kinds(int mode, int use_max_ratio, int* fk, int* bk) {
+    switch (mode) {
+        case DBGPHMM_RUN_DENSE: *fk = DBGPHMM_FWD_DENSE; *bk = DBGPHMM_BWD_DENSE; break;
+        case DBGPHMM_RUN_SPARSE: *fk = DBGPHMM_FWD_SPARSE; *bk = DBGPHMM_BWD_SPARSE; break;
+        case DBGPHMM_RUN_SPARSE_ADAPTIVE: *fk = use_max_ratio ? DBGPHMM_FWD_SPARSE_RATIO : DBGPHMM_FWD_SPARSE; *bk = DBGPHMM_BWD_BY_FORWARD; break;
+        default: *fk = DBGPHMM_FWD_MAPPING; *bk = DBGPHMM_BWD_MAPPING; break;
+    }
+}
+// device bytes one read needs when both directions keep their rows
+static uint64_t job_bytes_keep(const dbgphmm_model* m, int fk, int bk, uint64_t len) {
+    const uint64_t slab = dense_slab_bytes(m->N), W = m->params.n_warmup;
+    uint64_t fd = fk == DBGPHMM_FWD_DENSE ? len : (fk == DBGPHMM_FWD_MAPPING ? 0 : std::min(len, W));
+    uint64_t bd = bk == DBGPHMM_BWD_DENSE ? len : (bk == DBGPHMM_BWD_SPARSE ? std::min(len, W) : (bk == DBGPHMM_BWD_BY_FORWARD ? std::min(len, W) + 2 : 0));
+    uint64_t per_row = (uint64_t)m->params.n_active_nodes * 3 * 34 + 256 + 2 * sizeof(RowDesc);
+    return (fd + bd) * slab + 2 * len * per_row + ((uint64_t)1 << 20);
+}
+
+static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int use_max_ratio, const dbgphmm_mappings* mappings,
+                    double* d_freqs, double* h_logp_fwd, double* h_logp_bwd, uint64_t cells[2], dbgphmm_mappings* map_out, int map_by_ratio) {
+    ST_TRY(check_reads_mappings(reads, mappings));
+    if (mode == DBGPHMM_RUN_WITH_MAPPING && !mappings) { dbg_set_error("run_with_mapping needs mappings"); return DBGPHMM_ERR_INVALID; }
+    ST_TRY(dbgphmm_reads_to_device(m, const_cast<dbgphmm_reads*>(reads)));
+    reset_times();
+    EvTimer total(m->stream, &g_times.total_ms);
+    int fk, bk;
+    run_kinds(mode, use_max_ratio, &fk, &bk);
+    const bool with_map = mode == DBGPHMM_RUN_WITH_MAPPING;
+    DevMappings dmap;
+    if (with_map) ST_TRY(upload_mappings(m, mappings, &dmap));
+    const uint64_t R = reads->n_reads;
+    std::vector<HJob> all; std::vector<uint64_t> bytes;
+    for (uint64_t r = 0; r < R; r++) {
+        uint64_t len = reads->off[r + 1] - reads->off[r];
+        if (len == 0 || len > 0x7fffffffu) { dmap.release(); dbg_set_error("read length must be in [1, 2^31)"); return DBGPHMM_ERR_INVALID; }
+        all.push_back(HJob{(uint32_t)r, 0, reads->off[r], (uint32_t)len, with_map ? mappings->read_off[r] : 0});
+        bytes.push_back(job_bytes_keep(m, fk, bk, len));
+    }
+    if (cells) cells[0] = cells[1] = 0;
+    int st = DBGPHMM_OK;
+    for (auto& bt : plan_batches(bytes, m->mem_budget, 65535)) {
+        std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
+        RowStore F, B;
+        st = run_forward(m, jobs, reads->d_bases, fk, true, true, with_map ? &dmap : nullptr, &F);
+        if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, true, with_map ? &dmap : nullptr, &F, &B);
+        if (st == DBGPHMM_OK && d_freqs) st = run_products_freqs(m, jobs, F, B, d_freqs);
+        if (st == DBGPHMM_OK && map_out) st = run_products_mapping(m, jobs, F, B, map_by_ratio, m->params.n_active_nodes, m->params.active_node_max_ratio, map_out);
+        if (st == DBGPHMM_OK) {
+            for (size_t i = 0; i < jobs.size(); i++) {
+                if (h_logp_fwd) h_logp_fwd[bt.first + i] = xlog(F.h_final[i]);
+                if (h_logp_bwd) h_logp_bwd[bt.first + i] = xlog(B.h_final[i]);
+            }
+            if (cells) { cells[0] += F.cells; cells[1] += B.cells; }
+        }
+        F.release(); B.release();
+        if (st != DBGPHMM_OK) break;
+    }
+    dmap.release();
+    return st;
+}
+
+extern "C" int dbgphmm_run_node_freqs_dev(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int use_max_ratio,
+                                          const dbgphmm_mappings* mappings, double* node_freqs_dev, double* logp_fwd_dev, double* logp_bwd_dev,
+                                          uint64_t cells[2]) {
+    if (!m || !reads || mode < 0 || mode > 3) { dbg_set_error("run_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    std::vector<double> lf(reads->n_reads), lb(reads->n_reads);
+    ST_TRY(run_impl(m, reads, mode, use_max_ratio, mappings, node_freqs_dev, lf.data(), lb.data(), cells, nullptr, 0));
+    if (logp_fwd_dev && !lf.empty()) CUDA_TRY(cudaMemcpy(logp_fwd_dev, lf.data(), 8 * lf.size(), cudaMemcpyHostToDevice));
+    if (logp_bwd_dev && !lb.empty()) CUDA_TRY(cudaMemcpy(logp_bwd_dev, lb.data(), 8 * lb.size(), cudaMemcpyHostToDevice));
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_run_node_freqs(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int use_max_ratio, const dbgphmm_mappings* mappings,
+                                      double* node_freqs, double* logp_fwd, double* logp_bwd, uint64_t cells[2]) {
+    if (!m || !reads || mode < 0 || mode > 3) { dbg_set_error("run_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    DevBuf b_f;
+    if (node_freqs) { ST_TRY(b_f.alloc(sizeof(double) * m->N)); CUDA_TRY(cudaMemsetAsync(b_f.p, 0, sizeof(double) * m->N, m->stream)); }
+    ST_TRY(run_impl(m, reads, mode, use_max_ratio, mappings, node_freqs ? b_f.as<double>() : nullptr, logp_fwd, logp_bwd, cells, nullptr, 0));
+    if (node_freqs) CUDA_TRY(cudaMemcpy(node_freqs, b_f.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_generate_mappings(dbgphmm_model* m, const dbgphmm_reads* reads, const dbgphmm_mappings* mappings, int use_max_ratio,
+                                         dbgphmm_mappings** out) {
+    if (!m || !reads || !out) { dbg_set_error("generate_mappings: bad argument"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    dbgphmm_mappings* mp = new dbgphmm_mappings();
+    mp->read_off.push_back(0); mp->row_off.push_back(0);
+    // hint.rs:205-217: run_with_mapping if hints exist, else run_sparse_adaptive(use_max_ratio)
+    int st = run_impl(m, reads, mappings ? DBGPHMM_RUN_WITH_MAPPING : DBGPHMM_RUN_SPARSE_ADAPTIVE, use_max_ratio, mappings, nullptr, nullptr, nullptr,
+                      nullptr, mp, use_max_ratio ? 1 : 0);
+    if (st != DBGPHMM_OK) { delete mp; return st; }
+    *out = mp;
+    return DBGPHMM_OK;
+}

@@ -1,0 +1,586 @@
+// dense.cu — dense DP rows over all N node states.
+//
+// One CTA computes one DP row of one chunk (DENSE_CORE consecutive relabelled nodes) for one read:
+// the previous row of the chunk and of its 6-hop upstream halo is staged in shared memory, Match/Ins are
+// computed for every local node within 5 hops, and the bounded Del chain (fd0 + 4 x fdt, forward.rs:423-466;
+// bd0 + 4 x bdt, backward.rs:299-343) is propagated through shared memory with the valid region shrinking by
+// one hop per round, so a row costs one read and one write of the 28 B cell per node.
+// f_step: forward.rs:276-306 (fm :337, fi :378, fd0 :480, fdt :510, fib :541, fe :554)
+// b_step: backward.rs:216-261 (bd0 :354, bdt :387, bm :423, bi :462, bmb :499, bib :535)
+#include <algorithm>
+#include "dense.h"
+
+struct PlanView {
+    const uint32_t *chunk_start, *loc_base, *loc_node, *nle, *le_off, *le_eid;
+    const uint16_t* le_idx;
+};
+struct GraphView {
+    uint32_t N, E;
+    const uint8_t* emission;
+    const double *init, *trans;
+    const uint32_t* orig_of;
+};
+static PlanView plan_view(const DevPlan& p) { return PlanView{p.chunk_start, p.loc_base, p.loc_node, p.nle, p.le_off, p.le_eid, p.le_idx}; }
+static GraphView graph_view(const dbgphmm_model* m) { return GraphView{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_orig_of}; }
+
+__device__ __forceinline__ uint64_t slab_of(const DJob& jb, uint32_t s) { return jb.slab0 + (jb.slab_mod ? (s % jb.slab_mod) : s); }
+
+__device__ __forceinline__ XF warp_xsum(XF a) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        XF b;
+        b.v = __shfl_down_sync(0xffffffffu, a.v, o);
+        b.e = __shfl_down_sync(0xffffffffu, a.e, o);
+        a = xadd(a, b);
+    }
+    return a;
+}
+__device__ __forceinline__ XF warp_xmax(XF a) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        XF b;
+        b.v = __shfl_down_sync(0xffffffffu, a.v, o);
+        b.e = __shfl_down_sync(0xffffffffu, a.e, o);
+        if (xgt(b, a)) a = b;
+    }
+    return a;
+}
+
+#define SMEM_CARVE()                                                   \
+    extern __shared__ __align__(16) unsigned char smem_raw[];          \
+    double* pm = (double*)smem_raw;                                    \
+    double* pi = pm + DENSE_LMAX;                                      \
+    double* pd = pi + DENSE_LMAX;                                      \
+    double* cm = pd + DENSE_LMAX;                                      \
+    double* ci = cm + DENSE_LMAX;                                      \
+    double* dv0 = ci + DENSE_LMAX;                                     \
+    double* dv1 = dv0 + DENSE_LMAX;                                    \
+    int* pex = (int*)(dv1 + DENSE_LMAX);                               \
+    int* cex = pex + DENSE_LMAX;                                       \
+    int* de0 = cex + DENSE_LMAX;                                       \
+    int* de1 = de0 + DENSE_LMAX;
+#define DENSE_SMEM_BYTES (DENSE_LMAX * (7 * 8 + 4 * 4))
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(DENSE_THREADS, 2)
+k_dense_fwd(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs, uint32_t s, const uint8_t* __restrict__ bases,
+            const RowDesc* __restrict__ desc, const int* __restrict__ active, char* __restrict__ pool, uint64_t slab_bytes,
+            uint32_t Np, XF* __restrict__ partials, uint32_t n_chunks) {
+    const DJob jb = jobs[blockIdx.y];
+    if (s >= jb.n_steps) return;
+    if (jb.active_idx >= 0 && !active[jb.active_idx]) return;
+    SMEM_CARVE();
+    const int tid = threadIdx.x;
+    const uint32_t c = blockIdx.x;
+    const int row = jb.first_row + (int)s;
+    const uint8_t x = bases[jb.base_off + row];
+    const uint32_t lb = P.loc_base[c], lo = lb + c;
+    const uint32_t* nle = P.nle + (size_t)c * 8;
+    const int n0 = nle[0], n4 = nle[4], n5 = nle[5], nL = nle[6];
+    const double* init = G.init + (size_t)jb.x * G.N;
+    const double* trans = G.trans + (size_t)jb.x * G.E;
+    // begin-state scalars of the previous row (f_init: mb = 1, forward.rs:255-266)
+    XF mbp, ibp;
+    if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
+    else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
+    const XF ib_cur = xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random);  // fib, forward.rs:541-545
+    const XF fb0 = xadd(xmul(mbp, lp.p_MM), xmul(ibp, lp.p_IM));                        // begin part of fm
+    // ---- stage the previous row of the local set
+    const int pk = (s == 0) ? jb.prev0_kind : PREV_SLAB;
+    if (pk == PREV_SLAB) {
+        const char* sl = pool + (s == 0 ? jb.prev0_slab : slab_of(jb, s - 1)) * slab_bytes;
+        const double* gm = (const double*)sl; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
+        for (int j = tid; j < nL; j += DENSE_THREADS) {
+            uint32_t g = P.loc_node[lb + j];
+            pm[j] = gm[g]; pi[j] = gi[g]; pd[j] = gd[g]; pex[j] = ge[g];
+        }
+    } else {
+        for (int j = tid; j < nL; j += DENSE_THREADS) { pm[j] = 0.0; pi[j] = 0.0; pd[j] = 0.0; pex[j] = 0; }
+    }
+    __syncthreads();
+    // ---- round A: Match / Ins of the current row (fm, fi)
+    for (int j = tid; j < n5; j += DENSE_THREADS) {
+        uint32_t g = P.loc_node[lb + j];
+        XF acc = xf_zero();
+        for (uint32_t a = P.le_off[lo + j], ae = P.le_off[lo + j + 1]; a < ae; a++) {
+            int l = P.le_idx[a];
+            double t = trans[P.le_eid[a]];
+            acc = xadd(acc, xf(t * (lp.p_MM * pm[l] + lp.p_IM * pi[l] + lp.p_DM * pd[l]), pex[l]));
+        }
+        acc = xadd(acc, xmul(fb0, init[g]));
+        XF m = xmul(acc, G.emission[g] == x ? lp.p_match : lp.p_mismatch);
+        XF i = xf(lp.p_random * (lp.p_MI * pm[j] + lp.p_II * pi[j] + lp.p_DI * pd[j]), pex[j]);
+        int Em = xexp(m), Ei = xexp(i), Ec = Em > Ei ? Em : Ei;
+        if (Ec == XF_ZERO_E) { cm[j] = 0.0; ci[j] = 0.0; cex[j] = 0; }
+        else {
+            cm[j] = m.v == 0.0 ? 0.0 : m.v * pow2i(m.e - Ec);
+            ci[j] = i.v == 0.0 ? 0.0 : i.v * pow2i(i.e - Ec);
+            cex[j] = Ec;
+        }
+    }
+    __syncthreads();
+    // ---- round B: fd0 ; rounds C1..C4: fdt.  d accumulates in registers (slot q of this thread).
+    XF dacc[DENSE_SLOTS];
+#pragma unroll
+    for (int q = 0; q < DENSE_SLOTS; q++) {
+        dacc[q] = xf_zero();
+        int j = tid + q * DENSE_THREADS;
+        if (j < n4) {
+            uint32_t g = P.loc_node[lb + j];
+            XF acc = xf_zero();
+            for (uint32_t a = P.le_off[lo + j], ae = P.le_off[lo + j + 1]; a < ae; a++) {
+                int l = P.le_idx[a];
+                double t = trans[P.le_eid[a]];
+                acc = xadd(acc, xf(t * (lp.p_MD * cm[l] + lp.p_ID * ci[l]), cex[l]));
+            }
+            acc = xadd(acc, xmul(ib_cur, lp.p_ID * init[g]));  // mb of the current row is 0 (fmb, forward.rs:531-533)
+            dv0[j] = acc.v; de0[j] = acc.e;
+            dacc[q] = acc;
+        }
+    }
+    __syncthreads();
+    double* dprev = dv0; int* eprev = de0; double* dcur = dv1; int* ecur = de1;
+#pragma unroll 1
+    for (int t = 1; t < N_DEL_ROUNDS; t++) {
+        const int nb = nle[4 - t];
+#pragma unroll
+        for (int q = 0; q < DENSE_SLOTS; q++) {
+            int j = tid + q * DENSE_THREADS;
+            if (j < nb) {
+                XF acc = xf_zero();
+                for (uint32_t a = P.le_off[lo + j], ae = P.le_off[lo + j + 1]; a < ae; a++) {
+                    int l = P.le_idx[a];
+                    double tr = trans[P.le_eid[a]];
+                    acc = xadd(acc, xf(tr * lp.p_DD * dprev[l], eprev[l]));
+                }
+                dcur[j] = acc.v; ecur[j] = acc.e;
+                dacc[q] = xadd(dacc[q], acc);
+            }
+        }
+        __syncthreads();
+        double* tv = dprev; dprev = dcur; dcur = tv;
+        int* te = eprev; eprev = ecur; ecur = te;
+    }
+    // ---- store the chunk's cells, reduce sum(m+i+d) for fe (forward.rs:554-558)
+    char* so = pool + slab_of(jb, s) * slab_bytes;
+    double* om = (double*)so; double* oi = om + Np; double* od = oi + Np; int* oe = (int*)(od + Np);
+    const uint32_t g0 = P.chunk_start[c];
+    XF part = xf_zero();
+#pragma unroll
+    for (int q = 0; q < DENSE_SLOTS; q++) {
+        int j = tid + q * DENSE_THREADS;
+        if (j < n0) {
+            Cell cl = cell_pack(xf(cm[j], cex[j]), xf(ci[j], cex[j]), dacc[q]);
+            om[g0 + j] = cl.m; oi[g0 + j] = cl.i; od[g0 + j] = cl.d; oe[g0 + j] = cl.e;
+            part = xadd(part, xf(cl.m + cl.i + cl.d, cl.e));
+        }
+    }
+    part = warp_xsum(part);
+    __shared__ XF wsum[DENSE_THREADS / 32];
+    if ((tid & 31) == 0) wsum[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        XF tot = xf_zero();
+        for (int w = 0; w < DENSE_THREADS / 32; w++) tot = xadd(tot, wsum[w]);
+        partials[(size_t)blockIdx.y * n_chunks + c] = tot;
+    }
+}
+
+// row reduction of the forward step: e = p_end * sum ; ib ; mb = 0
+__global__ void k_dense_fwd_finish(LinParams lp, const DJob* __restrict__ jobs, uint32_t s, RowDesc* __restrict__ desc,
+                                   const int* __restrict__ active, const XF* __restrict__ partials, uint32_t n_chunks) {
+    const DJob jb = jobs[blockIdx.x];
+    if (s >= jb.n_steps) return;
+    if (jb.active_idx >= 0 && !active[jb.active_idx]) return;
+    __shared__ XF sh[256];
+    XF acc = xf_zero();
+    for (uint32_t c = threadIdx.x; c < n_chunks; c += blockDim.x) acc = xadd(acc, partials[(size_t)blockIdx.x * n_chunks + c]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XF tot = xf_zero();
+        for (int t = 0; t < (int)blockDim.x; t++) tot = xadd(tot, sh[t]);
+        int row = jb.first_row + (int)s;
+        XF mbp, ibp;
+        if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
+        else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
+        RowDesc r;
+        r.kind = ROW_DENSE; r.n_ent = 0; r.n_mi = 0; r.n_d = 0;
+        r.off = jb.slab0 + (jb.slab_mod ? (s % jb.slab_mod) : s);
+        r.mb = xf_zero();
+        r.ib = xnorm(xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random));
+        r.e = xnorm(xmul(tot, lp.p_end));
+        desc[jb.desc0 + row] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(DENSE_THREADS, 2)
+k_dense_bwd(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs, uint32_t s, const uint8_t* __restrict__ bases,
+            const int* __restrict__ active, char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np, XF* __restrict__ partials,
+            uint32_t n_chunks) {
+    const DJob jb = jobs[blockIdx.y];
+    if (s >= jb.n_steps) return;
+    if (jb.active_idx >= 0 && !active[jb.active_idx]) return;
+    SMEM_CARVE();
+    (void)pd; (void)ci;
+    const int tid = threadIdx.x;
+    const uint32_t c = blockIdx.x;
+    const int row = jb.first_row - (int)s;
+    const uint8_t x = bases[jb.base_off + row];
+    const uint32_t lb = P.loc_base[c], lo = lb + c;
+    const uint32_t* nle = P.nle + (size_t)c * 8;
+    const int n0 = nle[0], n1 = nle[1], n5 = nle[5], nL = nle[6];
+    const double* init = G.init + (size_t)jb.x * G.N;
+    const double* trans = G.trans + (size_t)jb.x * G.E;
+    // ---- stage the next row (i+1): m'', i'' pre-multiplied views are formed on the fly
+    const int pk = (s == 0) ? jb.prev0_kind : PREV_SLAB;
+    if (pk == PREV_SLAB) {
+        const char* sl = pool + (s == 0 ? jb.prev0_slab : slab_of(jb, s - 1)) * slab_bytes;
+        const double* gm = (const double*)sl; const double* gi = gm + Np; const int* ge = (const int*)(gi + 2 * (size_t)Np);
+        for (int j = tid; j < nL; j += DENSE_THREADS) {
+            uint32_t g = P.loc_node[lb + j];
+            // cm holds e_l(x) * m''[l] (the emission of the child is what every use multiplies by)
+            double em = G.emission[g] == x ? lp.p_match : lp.p_mismatch;
+            pm[j] = gm[g] * em; pi[j] = gi[g]; pex[j] = ge[g];
+        }
+    } else {  // b_init: m = i = d = p_end (backward.rs:197-211)
+        for (int j = tid; j < nL; j += DENSE_THREADS) {
+            uint32_t g = P.loc_node[lb + j];
+            double em = G.emission[g] == x ? lp.p_match : lp.p_mismatch;
+            pm[j] = lp.p_end * em; pi[j] = lp.p_end; pex[j] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- bd0 for depth <= 5, then bdt with the valid region shrinking; d of depth <= 1 ends in (cm, cex)
+    XF dacc[DENSE_SLOTS];
+#pragma unroll
+    for (int q = 0; q < DENSE_SLOTS; q++) {
+        dacc[q] = xf_zero();
+        int j = tid + q * DENSE_THREADS;
+        if (j < n5) {
+            XF acc = xf_zero();
+            for (uint32_t a = P.le_off[lo + j], ae = P.le_off[lo + j + 1]; a < ae; a++) {
+                int l = P.le_idx[a];
+                double t = trans[P.le_eid[a]];
+                acc = xadd(acc, xf(t * lp.p_DM * pm[l], pex[l]));
+            }
+            acc = xadd(acc, xf(lp.p_DI * lp.p_random * pi[j], pex[j]));
+            dv0[j] = acc.v; de0[j] = acc.e;
+            dacc[q] = acc;
+        }
+    }
+    __syncthreads();
+    double* dprev = dv0; int* eprev = de0; double* dcur = dv1; int* ecur = de1;
+#pragma unroll 1
+    for (int t = 1; t < N_DEL_ROUNDS; t++) {
+        const int nb = nle[5 - t];
+#pragma unroll
+        for (int q = 0; q < DENSE_SLOTS; q++) {
+            int j = tid + q * DENSE_THREADS;
+            if (j < nb) {
+                XF acc = xf_zero();
+                for (uint32_t a = P.le_off[lo + j], ae = P.le_off[lo + j + 1]; a < ae; a++) {
+                    int l = P.le_idx[a];
+                    double tr = trans[P.le_eid[a]];
+                    acc = xadd(acc, xf(tr * lp.p_DD * dprev[l], eprev[l]));
+                }
+                dcur[j] = acc.v; ecur[j] = acc.e;
+                dacc[q] = xadd(dacc[q], acc);
+            }
+        }
+        __syncthreads();
+        double* tv = dprev; dprev = dcur; dcur = tv;
+        int* te = eprev; eprev = ecur; ecur = te;
+    }
+#pragma unroll
+    for (int q = 0; q < DENSE_SLOTS; q++) {
+        int j = tid + q * DENSE_THREADS;
+        if (j < n1) { cm[j] = dacc[q].v; cex[j] = dacc[q].e; }
+    }
+    __syncthreads();
+    // ---- bm, bi of the chunk; partial sums of bmb / bib over the chunk's nodes
+    char* so = pool + slab_of(jb, s) * slab_bytes;
+    double* om = (double*)so; double* oi = om + Np; double* od = oi + Np; int* oe = (int*)(od + Np);
+    const uint32_t g0 = P.chunk_start[c];
+    XF pmb = xf_zero(), pib = xf_zero();
+#pragma unroll
+    for (int q = 0; q < DENSE_SLOTS; q++) {
+        int j = tid + q * DENSE_THREADS;
+        if (j < n0) {
+            XF am = xf_zero(), ai = xf_zero();
+            for (uint32_t a = P.le_off[lo + j], ae = P.le_off[lo + j + 1]; a < ae; a++) {
+                int l = P.le_idx[a];
+                double t = trans[P.le_eid[a]];
+                XF tm = xf(t * pm[l], pex[l]);        // t * e_l(x) * m''[l]
+                XF td = xf(t * cm[l], cex[l]);        // t * d[l]
+                am = xadd(am, xadd(xmul(tm, lp.p_MM), xmul(td, lp.p_MD)));
+                ai = xadd(ai, xadd(xmul(tm, lp.p_IM), xmul(td, lp.p_ID)));
+            }
+            am = xadd(am, xf(lp.p_MI * lp.p_random * pi[j], pex[j]));
+            ai = xadd(ai, xf(lp.p_II * lp.p_random * pi[j], pex[j]));
+            Cell cl = cell_pack(am, ai, dacc[q]);
+            uint32_t g = g0 + j;
+            om[g] = cl.m; oi[g] = cl.i; od[g] = cl.d; oe[g] = cl.e;
+            // bmb / bib terms of this node (backward.rs:499-555)
+            double in = init[g];
+            XF um = xf(pm[j], pex[j]);
+            pmb = xadd(pmb, xmul(xadd(xmul(um, lp.p_MM), xmul(dacc[q], lp.p_MD)), in));
+            pib = xadd(pib, xmul(xadd(xmul(um, lp.p_IM), xmul(dacc[q], lp.p_ID)), in));
+        }
+    }
+    pmb = warp_xsum(pmb); pib = warp_xsum(pib);
+    __shared__ XF wsum[2][DENSE_THREADS / 32];
+    if ((tid & 31) == 0) { wsum[0][tid >> 5] = pmb; wsum[1][tid >> 5] = pib; }
+    __syncthreads();
+    if (tid == 0) {
+        XF a = xf_zero(), b = xf_zero();
+        for (int w = 0; w < DENSE_THREADS / 32; w++) { a = xadd(a, wsum[0][w]); b = xadd(b, wsum[1][w]); }
+        partials[((size_t)blockIdx.y * n_chunks + c) * 2] = a;
+        partials[((size_t)blockIdx.y * n_chunks + c) * 2 + 1] = b;
+    }
+}
+
+__global__ void k_dense_bwd_finish(LinParams lp, const DJob* __restrict__ jobs, uint32_t s, RowDesc* __restrict__ desc,
+                                   const int* __restrict__ active, const XF* __restrict__ partials, uint32_t n_chunks) {
+    const DJob jb = jobs[blockIdx.x];
+    if (s >= jb.n_steps) return;
+    if (jb.active_idx >= 0 && !active[jb.active_idx]) return;
+    __shared__ XF sh[2][256];
+    XF a = xf_zero(), b = xf_zero();
+    for (uint32_t c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+        a = xadd(a, partials[((size_t)blockIdx.x * n_chunks + c) * 2]);
+        b = xadd(b, partials[((size_t)blockIdx.x * n_chunks + c) * 2 + 1]);
+    }
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XF ta = xf_zero(), tb = xf_zero();
+        for (int t = 0; t < (int)blockDim.x; t++) { ta = xadd(ta, sh[0][t]); tb = xadd(tb, sh[1][t]); }
+        int row = jb.first_row - (int)s;
+        XF ibn = (row == (int)jb.len - 1) ? xf_zero() : desc[jb.desc0 + row + 1].ib;  // b_init: ib = 0
+        RowDesc r;
+        r.kind = ROW_DENSE; r.n_ent = 0; r.n_mi = 0; r.n_d = 0;
+        r.off = jb.slab0 + (jb.slab_mod ? (s % jb.slab_mod) : s);
+        r.mb = xnorm(xadd(ta, xmul(ibn, lp.p_MI * lp.p_random)));
+        r.ib = xnorm(xadd(tb, xmul(ibn, lp.p_II * lp.p_random)));
+        r.e = xf_zero();
+        desc[jb.desc0 + row] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ top-k selection
+// Key of a cell: (T, mantissa, ~original id) with merged value v = (m+i+d) * 2^ex = mant * 2^T, mant in [1,2).
+// Exact ordering of the linear values; ties -> lower ORIGINAL node index first (the dense SparseVec iterates in
+// node-index order; UNPINNED in the reference, see oracle header).  Multi-level radix select over the digits
+// [T window | 5 mantissa digits | 3 id digits]; as soon as the boundary bin holds <= SELECT_CAP cells the rest is
+// resolved in shared memory.
+struct SKey { int T; unsigned long long mant; uint32_t inv_id; };
+__device__ __forceinline__ bool skey_gt(const SKey& a, const SKey& b) {
+    if (a.T != b.T) return a.T > b.T;
+    if (a.mant != b.mant) return a.mant > b.mant;
+    return a.inv_id > b.inv_id;
+}
+__device__ __forceinline__ SKey cell_key(double m, double i, double d, int ex, uint32_t orig) {
+    double v = m + i + d;
+    SKey k;
+    k.inv_id = ~orig;
+    if (v == 0.0) { k.T = XF_ZERO_E; k.mant = 0; return k; }
+    long long b = __double_as_longlong(v);
+    k.T = ex + (int)((b >> 52) & 0x7ff) - 1023;
+    k.mant = (unsigned long long)b & 0xfffffffffffffull;
+    return k;
+}
+// digit `lvl` (0..8) of a key relative to window top Ttop: 11 bits each, larger = better
+#define SEL_BINS 2048
+__device__ __forceinline__ int skey_digit(const SKey& k, int lvl, int Ttop) {
+    if (lvl == 0) { long long dlt = (long long)Ttop - k.T; return dlt >= SEL_BINS - 1 ? 0 : (int)(SEL_BINS - 1 - dlt); }  // bin 0 = everything far below
+    if (lvl <= 4) return (int)((k.mant >> (52 - 11 * lvl)) & 0x7ff);
+    if (lvl == 5) return (int)(k.mant & 0xff);
+    if (lvl == 6) return (int)((k.inv_id >> 21) & 0x7ff);
+    if (lvl == 7) return (int)((k.inv_id >> 10) & 0x7ff);
+    return (int)(k.inv_id & 0x3ff);
+}
+
+#define SELECT_SMEM_BYTES (SELECT_CAP * (8 + 4 + 4 + 4))
+__global__ void __launch_bounds__(SELECT_THREADS, 1)
+k_dense_select(GraphView G, const SelectReq* __restrict__ reqs, const int* __restrict__ active, const char* __restrict__ pool,
+               uint64_t slab_bytes, uint32_t Np, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_cnt) {
+    const SelectReq rq = reqs[blockIdx.x];
+    if (rq.active_idx >= 0 && !active[rq.active_idx]) return;
+    const char* sl = pool + rq.slab * slab_bytes;
+    const double* gm = (const double*)sl; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
+    const uint32_t N = G.N;
+    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long* c_mant = (unsigned long long*)sel_smem;
+    int* c_T = (int*)(c_mant + SELECT_CAP);
+    uint32_t* c_inv = (uint32_t*)(c_T + SELECT_CAP);
+    uint32_t* c_node = c_inv + SELECT_CAP;
+    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ int sh_T[SELECT_THREADS / 32];
+    __shared__ int prefix[9];  // chosen digit per level
+    __shared__ int s_Ttop;
+    __shared__ unsigned int s_need, s_ncand, s_done, s_shift;
+    __shared__ double s_L0;
+    const uint32_t K = rq.k < N ? rq.k : N;
+    if (tid == 0) { s_need = K; s_ncand = 0; s_Ttop = 0x7fffffff; }
+    __syncthreads();
+    int nlev = 0;
+    // ---- level 0: exponent window [Ttop-2046, Ttop]; shift the window down while fewer than `need` cells are in it
+    for (;;) {
+        const int Tcap = s_Ttop;  // only cells with T <= Tcap (strictly below the previous window) remain
+        int tmax = XF_ZERO_E;
+        for (uint32_t g = tid; g < N; g += SELECT_THREADS) {
+            SKey k = cell_key(gm[g], gi[g], gd[g], ge[g], 0);
+            if (k.T <= Tcap || Tcap == 0x7fffffff) tmax = k.T > tmax ? k.T : tmax;
+        }
+        for (int o = 16; o; o >>= 1) { int t = __shfl_down_sync(0xffffffffu, tmax, o); tmax = t > tmax ? t : tmax; }
+        if ((tid & 31) == 0) sh_T[tid >> 5] = tmax;
+        for (int b = tid; b < SEL_BINS; b += SELECT_THREADS) hist[b] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            int t = XF_ZERO_E;
+            for (int w = 0; w < SELECT_THREADS / 32; w++) t = sh_T[w] > t ? sh_T[w] : t;
+            s_Ttop = t;
+        }
+        __syncthreads();
+        const int Ttop = s_Ttop;
+        for (uint32_t g = tid; g < N; g += SELECT_THREADS) {
+            SKey k = cell_key(gm[g], gi[g], gd[g], ge[g], 0);
+            if (k.T <= Ttop) atomicAdd(&hist[skey_digit(k, 0, Ttop)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int need = s_need, cum = 0;
+            int b = SEL_BINS - 1;
+            for (; b > 0; b--) { if (cum + hist[b] >= need) break; cum += hist[b]; }
+            s_shift = 0;
+            if (b == 0 && Ttop != XF_ZERO_E) {  // not enough cells in this window: all of bins >= 1 win, look further down
+                s_need = need - cum;
+                s_Ttop = Ttop - (SEL_BINS - 1);
+                s_shift = 1;
+            } else {
+                prefix[0] = b;
+                s_need = need - cum;
+                s_done = (hist[b] + (K - s_need) <= SELECT_CAP) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        if (!s_shift) break;
+    }
+    const int Ttop = s_Ttop;
+    nlev = 1;
+    // ---- levels 1..8: mantissa digits, then inverted original id digits
+    for (int lvl = 1; lvl < 9 && !s_done; lvl++) {
+        for (int b = tid; b < SEL_BINS; b += SELECT_THREADS) hist[b] = 0;
+        __syncthreads();
+        for (uint32_t g = tid; g < N; g += SELECT_THREADS) {
+            SKey k = cell_key(gm[g], gi[g], gd[g], ge[g], G.orig_of[g]);
+            bool match = k.T <= Ttop;
+            for (int l2 = 0; l2 < lvl; l2++) match = match && (skey_digit(k, l2, Ttop) == prefix[l2]);
+            if (match) atomicAdd(&hist[skey_digit(k, lvl, Ttop)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int need = s_need, cum = 0;
+            int b = SEL_BINS - 1;
+            for (; b > 0; b--) { if (cum + hist[b] >= need) break; cum += hist[b]; }
+            prefix[lvl] = b;
+            s_need = need - cum;
+            s_done = (hist[b] + (K - s_need) <= SELECT_CAP) ? 1u : 0u;
+        }
+        nlev = lvl + 1;
+        __syncthreads();
+    }
+    // ---- collect every cell whose key is >= the boundary prefix (sure winners + boundary bin)
+    for (uint32_t g = tid; g < N; g += SELECT_THREADS) {
+        SKey k = cell_key(gm[g], gi[g], gd[g], ge[g], G.orig_of[g]);
+        bool take = true;
+        if (k.T <= Ttop) {
+            for (int l2 = 0; l2 < nlev; l2++) {
+                int dg = skey_digit(k, l2, Ttop);
+                if (dg > prefix[l2]) { take = true; break; }
+                if (dg < prefix[l2]) { take = false; break; }
+            }
+        }
+        if (take) {
+            unsigned int slot = atomicAdd(&s_ncand, 1u);
+            if (slot < SELECT_CAP) { c_mant[slot] = k.mant; c_T[slot] = k.T; c_inv[slot] = k.inv_id; c_node[slot] = g; }
+        }
+    }
+    __syncthreads();
+    const unsigned int nc = s_ncand < SELECT_CAP ? s_ncand : SELECT_CAP;
+    // ---- rank by counting (nc <= SELECT_CAP), emit in descending order
+    for (unsigned int a = tid; a < nc; a += SELECT_THREADS) {
+        SKey ka; ka.T = c_T[a]; ka.mant = c_mant[a]; ka.inv_id = c_inv[a];
+        unsigned int rank = 0;
+        for (unsigned int b = 0; b < nc; b++) {
+            SKey kb; kb.T = c_T[b]; kb.mant = c_mant[b]; kb.inv_id = c_inv[b];
+            rank += skey_gt(kb, ka) ? 1u : 0u;
+        }
+        if (rank < K) out_ids[(size_t)rq.out * MAX_ACTIVE + rank] = c_node[a];
+        if (rank == 0) {
+            uint32_t g = c_node[a];
+            s_L0 = xlog(xf(gm[g] + gi[g] + gd[g], ge[g]));
+        }
+    }
+    __syncthreads();
+    const unsigned int kk = K < nc ? K : nc;
+    if (!rq.by_ratio) { if (tid == 0) out_cnt[rq.out] = kk; return; }
+    // ratio filter on the sorted list: keep while ln v0 - ln v < ratio (table.rs:134-149); NaN compares false
+    __shared__ unsigned int s_keep;
+    if (tid == 0) s_keep = 0;
+    __syncthreads();
+    for (unsigned int r = tid; r < kk; r += SELECT_THREADS) {
+        uint32_t g = out_ids[(size_t)rq.out * MAX_ACTIVE + r];
+        double L = xlog(xf(gm[g] + gi[g] + gd[g], ge[g]));
+        if (s_L0 - L < rq.ratio) atomicAdd(&s_keep, 1u);  // sorted descending => the kept ones are a prefix
+    }
+    __syncthreads();
+    if (tid == 0) out_cnt[rq.out] = s_keep;
+}
+
+// ------------------------------------------------------------------------------------------------ host wrappers
+int dense_configure(dbgphmm_model* m) {
+    (void)m;
+    CUDA_TRY(cudaFuncSetAttribute(k_dense_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_dense_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_dense_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SELECT_SMEM_BYTES));
+    return DBGPHMM_OK;
+}
+
+int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
+                       const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, XF* d_rowmax) {
+    (void)d_rowmax;
+    dim3 grid(m->fwd.n_chunks, n_jobs);
+    k_dense_fwd<<<grid, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
+                                                                      d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks);
+    COUNT_LAUNCH();
+    k_dense_fwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->fwd.n_chunks);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}
+
+int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
+                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, XF* d_rowmax) {
+    (void)d_rowmax;
+    dim3 grid(m->bwd.n_chunks, n_jobs);
+    k_dense_bwd<<<grid, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_active,
+                                                                      pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks);
+    COUNT_LAUNCH();
+    k_dense_bwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->bwd.n_chunks);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}
+
+int dense_select(dbgphmm_model* m, const DensePool& pool, const SelectReq* d_reqs, uint32_t n_reqs, const int* d_active,
+                 uint32_t* d_out_ids, uint32_t* d_out_cnt) {
+    if (n_reqs == 0) return DBGPHMM_OK;
+    k_dense_select<<<n_reqs, SELECT_THREADS, SELECT_SMEM_BYTES, m->stream>>>(graph_view(m), d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, d_out_ids, d_out_cnt);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}

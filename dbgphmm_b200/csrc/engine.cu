@@ -1,0 +1,381 @@
+// engine.cu — drives the dense and sparse phases of forward / backward for a batch of (read, X) jobs.
+//
+// forward  drivers: forward.rs:24-45 (dense), :51-75 (mapping), :93-154 (sparse top-n / max-ratio)
+// backward drivers: backward.rs:24-53 (dense), :59-93 (mapping), :101-142 (by forward), :146-185 (sparse)
+#include <algorithm>
+#include <cstring>
+#include "engine.h"
+
+EngineTimes g_times;
+
+void RowStore::release() {
+    cudaFree(d_desc); d_desc = nullptr;
+    cudaFree(pool.base); pool = DensePool();
+    cudaFree(arena.base); cudaFree(arena.cursor); arena = SparseArena();
+    cudaFree(d_final); d_final = nullptr;
+}
+void DevMappings::release() { cudaFree(row_off); cudaFree(nodes); row_off = nullptr; nodes = nullptr; }
+
+int upload_mappings(dbgphmm_model* m, const dbgphmm_mappings* mp, DevMappings* out) {
+    std::vector<uint32_t> nodes(mp->nodes.size());
+    for (size_t i = 0; i < nodes.size(); i++) {
+        if (mp->nodes[i] >= m->N) { dbg_set_error("mapping node id out of range"); return DBGPHMM_ERR_INVALID; }
+        nodes[i] = m->pos_of[mp->nodes[i]];
+    }
+    CUDA_TRY(cudaMalloc((void**)&out->row_off, sizeof(uint64_t) * std::max<size_t>(mp->row_off.size(), 1)));
+    CUDA_TRY(cudaMalloc((void**)&out->nodes, sizeof(uint32_t) * std::max<size_t>(nodes.size(), 1)));
+    CUDA_TRY(cudaMemcpy(out->row_off, mp->row_off.data(), sizeof(uint64_t) * mp->row_off.size(), cudaMemcpyHostToDevice));
+    if (!nodes.empty()) CUDA_TRY(cudaMemcpy(out->nodes, nodes.data(), sizeof(uint32_t) * nodes.size(), cudaMemcpyHostToDevice));
+    out->read_off = mp->read_off;
+    return DBGPHMM_OK;
+}
+
+// ------------------------------------------------------------------ small control kernels
+// forward_sparse(use_max_ratio = true): decide after dense row s whether row s+1 stays dense (forward.rs:119-133)
+__global__ void k_ratio_decide(uint32_t n_jobs, uint32_t s, uint32_t W, uint32_t thr, const uint32_t* __restrict__ len,
+                               const uint32_t* __restrict__ top_cnt, int* __restrict__ active, uint32_t* __restrict__ nd) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs || !active[j]) return;
+    if (s + 1 >= len[j]) { active[j] = 0; nd[j] = len[j]; return; }
+    bool use_dense = (s + 1 < W) && (top_cnt[j] > thr);
+    if (!use_dense) { active[j] = 0; nd[j] = s + 1; }
+}
+__global__ void k_final_from_desc(uint32_t n_jobs, const RowDesc* __restrict__ desc, const uint64_t* __restrict__ desc0,
+                                  const uint32_t* __restrict__ len, const uint8_t* __restrict__ take, int dir, XF* __restrict__ out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs || !take[j]) return;
+    out[j] = dir == 0 ? desc[desc0[j] + len[j] - 1].e : desc[desc0[j]].mb;
+}
+// scatter a stored sparse row into a zeroed dense slab (backward_by_forward: dense step after sparse rows)
+__global__ void k_scatter_row(uint32_t n, const uint64_t* __restrict__ desc_idx, const uint64_t* __restrict__ slab, const RowDesc* __restrict__ desc,
+                              const char* __restrict__ arena, char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np, uint32_t N) {
+    uint32_t r = blockIdx.y;
+    if (r >= n) return;
+    char* sl = pool + slab[r] * slab_bytes;
+    double* gm = (double*)sl; double* gi = gm + Np; double* gd = gi + Np; int* ge = (int*)(gd + Np);
+    const RowDesc d = desc[desc_idx[r]];
+    // phase split by blockIdx.x parity is not possible without a grid sync: zero here, scatter in a second launch
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) { gm[g] = 0.0; gi[g] = 0.0; gd[g] = 0.0; ge[g] = 0; }
+    (void)d; (void)arena;
+}
+__global__ void k_scatter_row2(uint32_t n, const uint64_t* __restrict__ desc_idx, const uint64_t* __restrict__ slab, const RowDesc* __restrict__ desc,
+                               const char* __restrict__ arena, char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np) {
+    uint32_t r = blockIdx.x;
+    if (r >= n) return;
+    char* sl = pool + slab[r] * slab_bytes;
+    double* gm = (double*)sl; double* gi = gm + Np; double* gd = gi + Np; int* ge = (int*)(gd + Np);
+    const RowDesc d = desc[desc_idx[r]];
+    const char* pay = arena + d.off;
+    const double* fm = (const double*)pay; const double* fi = fm + d.n_ent; const double* fd = fi + d.n_ent;
+    const uint32_t* fid = (const uint32_t*)(fd + d.n_ent); const int* fex = (const int*)(fid + d.n_ent);
+    for (uint32_t e = threadIdx.x; e < d.n_ent; e += blockDim.x) { uint32_t g = fid[e]; gm[g] = fm[e]; gi[g] = fi[e]; gd[g] = fd[e]; ge[g] = fex[e]; }
+}
+
+static int alloc_pool(DensePool& pool, uint32_t N, uint64_t n_slabs) {
+    pool.Np = (N + 1) & ~1u;
+    pool.slab_bytes = dense_slab_bytes(N);
+    pool.n_slabs = n_slabs;
+    if (n_slabs == 0) { pool.base = nullptr; return DBGPHMM_OK; }
+    if (cudaMalloc((void**)&pool.base, pool.slab_bytes * n_slabs) != cudaSuccess) {
+        cudaGetLastError(); pool.base = nullptr;
+        dbg_set_error("out of device memory for dense rows"); return DBGPHMM_ERR_OOM;
+    }
+    return DBGPHMM_OK;
+}
+static int alloc_arena(SparseArena& a, uint64_t bytes, cudaStream_t st) {
+    a.bytes = bytes;
+    if (cudaMalloc((void**)&a.base, bytes ? bytes : 256) != cudaSuccess) { cudaGetLastError(); a.base = nullptr; dbg_set_error("out of device memory for sparse rows"); return DBGPHMM_ERR_OOM; }
+    CUDA_TRY(cudaMalloc((void**)&a.cursor, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), st));
+    return DBGPHMM_OK;
+}
+
+// Run a set of sparse jobs, re-running the ones that overflowed the small shared-memory capacity with the big one.
+static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io, RowStore* store, uint32_t small_cap) {
+    if (sj.empty()) return DBGPHMM_OK;
+    cudaStream_t st = m->stream;
+    const uint32_t n = (uint32_t)sj.size();
+    DevBuf b_jobs, b_status, b_final, b_cells;
+    ST_TRY(dev_upload(b_jobs, sj, st));
+    ST_TRY(b_status.alloc(sizeof(int) * n)); ST_TRY(b_final.alloc(sizeof(XF) * n)); ST_TRY(b_cells.alloc(sizeof(unsigned long long) * n));
+    io.status = b_status.as<int>(); io.final_scalar = b_final.as<XF>(); io.cells = b_cells.as<unsigned long long>();
+    std::vector<int> status(n);
+    std::vector<XF> fin(n);
+    std::vector<unsigned long long> cells(n);
+    std::vector<uint32_t> todo(n);
+    for (uint32_t i = 0; i < n; i++) todo[i] = i;
+    uint32_t caps[2] = {small_cap, 832};
+    for (int pass = 0; pass < 2 && !todo.empty(); pass++) {
+        if (pass == 1 && caps[1] <= caps[0]) break;
+        std::vector<SJob> cur(todo.size());
+        for (size_t i = 0; i < todo.size(); i++) cur[i] = sj[todo[i]];
+        CUDA_TRY(cudaMemcpyAsync(b_jobs.p, cur.data(), sizeof(SJob) * cur.size(), cudaMemcpyHostToDevice, st));
+        ST_TRY(sparse_run(m, b_jobs.as<SJob>(), (uint32_t)cur.size(), io, caps[pass]));
+        CUDA_TRY(cudaMemcpyAsync(status.data(), io.status, sizeof(int) * cur.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(fin.data(), io.final_scalar, sizeof(XF) * cur.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(cells.data(), io.cells, sizeof(unsigned long long) * cur.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        std::vector<uint32_t> next;
+        for (size_t i = 0; i < cur.size(); i++) {
+            if (status[i] == SJ_OK) {
+                store->h_final[cur[i].out_idx] = fin[i];
+                store->cells += cells[i];
+            } else if (status[i] == SJ_NEED_BIG && pass == 0) next.push_back(todo[i]);
+            else if (status[i] == SJ_OOM) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
+            else { dbg_set_error("a sparse row exceeded MAX_ACTIVE_NODES entries (the reference panics: insufficient capacity)"); return DBGPHMM_ERR_CAPACITY; }
+        }
+        todo.swap(next);
+    }
+    return DBGPHMM_OK;
+}
+
+static uint64_t arena_estimate(uint64_t n_rows, uint32_t n_active, bool ratio) {
+    uint64_t per_row = ratio ? 2048 : (uint64_t)n_active * 3 * 34 + 256;
+    uint64_t b = n_rows * per_row + (uint64_t)8 * SPARSE_PAGE_BYTES;
+    return (b + 255) & ~(uint64_t)255;
+}
+
+// ================================================================================================ forward
+int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, bool keep_rows, bool store_sparse,
+                const DevMappings* dmap, RowStore* out) {
+    cudaStream_t st = m->stream;
+    const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup;
+    out->dir = 0;
+    out->desc0.resize(J); out->len.resize(J); out->nd.assign(J, 0); out->h_final.assign(J, xf_zero());
+    uint64_t tot_rows = 0;
+    for (uint32_t j = 0; j < J; j++) { out->desc0[j] = tot_rows; out->len[j] = jobs[j].len; tot_rows += jobs[j].len; }
+    out->n_desc = tot_rows;
+    CUDA_TRY(cudaMalloc((void**)&out->d_desc, sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1)));
+    CUDA_TRY(cudaMalloc((void**)&out->d_final, sizeof(XF) * std::max<uint32_t>(J, 1)));
+    // ---- dense phase layout
+    std::vector<uint32_t> nd_max(J);
+    std::vector<DJob> dj(J);
+    uint64_t n_slabs = 0; uint32_t steps = 0;
+    for (uint32_t j = 0; j < J; j++) {
+        uint32_t n = jobs[j].len;
+        nd_max[j] = kind == DBGPHMM_FWD_DENSE ? n : (kind == DBGPHMM_FWD_MAPPING ? 0 : std::min(n, W));
+        DJob& d = dj[j];
+        d.x = jobs[j].x; d.len = n; d.base_off = jobs[j].base_off; d.n_steps = nd_max[j]; d.first_row = 0;
+        d.prev0_kind = PREV_F_INIT; d.prev0_slab = 0; d.slab0 = n_slabs; d.slab_mod = keep_rows ? 0 : 2; d.desc0 = out->desc0[j];
+        d.active_idx = kind == DBGPHMM_FWD_SPARSE_RATIO ? (int32_t)j : -1;
+        n_slabs += keep_rows ? nd_max[j] : std::min<uint32_t>(nd_max[j], 2);
+        steps = std::max(steps, nd_max[j]);
+    }
+    out->slab0.resize(J);
+    for (uint32_t j = 0; j < J; j++) out->slab0[j] = dj[j].slab0;
+    ST_TRY(alloc_pool(out->pool, N, n_slabs));
+    DevBuf b_dj, b_active, b_nd, b_len, b_part, b_top_ids, b_top_cnt, b_reqs;
+    ST_TRY(dev_upload(b_dj, dj, st));
+    std::vector<int> h_active(J, 1);
+    ST_TRY(dev_upload(b_active, h_active, st));
+    ST_TRY(dev_upload(b_nd, nd_max, st));
+    ST_TRY(dev_upload(b_len, out->len, st));
+    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * m->fwd.n_chunks));
+    ST_TRY(b_top_ids.alloc(sizeof(uint32_t) * (size_t)J * MAX_ACTIVE));
+    ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
+    CUDA_TRY(cudaMemsetAsync(b_top_cnt.p, 0, sizeof(uint32_t) * J, st));
+    const int* d_active = kind == DBGPHMM_FWD_SPARSE_RATIO ? b_active.as<int>() : nullptr;
+    std::vector<SelectReq> reqs(J);
+    ST_TRY(b_reqs.alloc(sizeof(SelectReq) * J));
+    auto slab_of_h = [&](uint32_t j, uint32_t s) { return dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    {
+        EvTimer tm(st, &g_times.dense_ms);
+        for (uint32_t s = 0; s < steps; s++) {
+            ST_TRY(dense_forward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), nullptr));
+            if (kind == DBGPHMM_FWD_SPARSE_RATIO) {
+                // top_nodes_by_score_ratio of row s for every job still dense (forward.rs:112-116)
+                uint32_t nr = 0;
+                for (uint32_t j = 0; j < J; j++)
+                    if (s < nd_max[j]) { SelectReq& r = reqs[nr++]; r.slab = slab_of_h(j, s); r.k = MAX_ACTIVE; r.by_ratio = 1; r.ratio = m->params.active_node_max_ratio; r.active_idx = (int32_t)j; r.out = j; }
+                CUDA_TRY(cudaMemcpyAsync(b_reqs.p, reqs.data(), sizeof(SelectReq) * nr, cudaMemcpyHostToDevice, st));
+                ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), nr, d_active, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
+                k_ratio_decide<<<(J + 127) / 128, 128, 0, st>>>(J, s, W, m->params.warmup_threshold, b_len.as<uint32_t>(), b_top_cnt.as<uint32_t>(),
+                                                                 b_active.as<int>(), b_nd.as<uint32_t>());
+                COUNT_LAUNCH();
+                CUDA_TRY(cudaStreamSynchronize(st));  // reqs is reused next step
+            }
+        }
+        if (kind == DBGPHMM_FWD_SPARSE_RATIO) {
+            CUDA_TRY(cudaMemcpyAsync(out->nd.data(), b_nd.p, sizeof(uint32_t) * J, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else out->nd = nd_max;
+        if (kind == DBGPHMM_FWD_SPARSE) {  // top_nodes(n_active) of the last dense row (forward.rs:115)
+            uint32_t nr = 0;
+            for (uint32_t j = 0; j < J; j++)
+                if (jobs[j].len > out->nd[j]) { SelectReq& r = reqs[nr++]; r.slab = slab_of_h(j, out->nd[j] - 1); r.k = m->params.n_active_nodes; r.by_ratio = 0; r.ratio = 0; r.active_idx = -1; r.out = j; }
+            CUDA_TRY(cudaMemcpyAsync(b_reqs.p, reqs.data(), sizeof(SelectReq) * nr, cudaMemcpyHostToDevice, st));
+            ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), nr, nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
+    // ---- sparse phase
+    std::vector<SJob> sj;
+    uint64_t sparse_rows = 0;
+    std::vector<uint8_t> dense_final(J, 0);
+    for (uint32_t j = 0; j < J; j++) {
+        uint32_t n = jobs[j].len, nd = out->nd[j];
+        if (nd >= n) { dense_final[j] = n > 0; continue; }
+        SJob s{};
+        s.x = jobs[j].x; s.len = n; s.base_off = jobs[j].base_off; s.dir = 0;
+        s.mode = kind == DBGPHMM_FWD_SPARSE ? SP_TOPN : (kind == DBGPHMM_FWD_SPARSE_RATIO ? SP_RATIO : SP_MAPPING);
+        s.row_begin = (int32_t)nd; s.n_rows = n - nd;
+        s.prev0_kind = nd == 0 ? SPREV_F_INIT : SPREV_DENSE;
+        s.prev0_slab = nd == 0 ? 0 : slab_of_h(j, nd - 1);
+        s.top0 = j; s.desc0 = out->desc0[j]; s.fdesc0 = 0; s.map_row0 = jobs[j].map_row0;
+        s.store = store_sparse ? 1 : 0; s.active_idx = -1; s.out_idx = j;
+        sj.push_back(s); sparse_rows += s.n_rows;
+    }
+    {
+        EvTimer tm(st, &g_times.sparse_ms);
+        ST_TRY(alloc_arena(out->arena, store_sparse ? arena_estimate(sparse_rows, m->params.n_active_nodes, kind == DBGPHMM_FWD_SPARSE_RATIO) : 256, st));
+        SparseIO io{};
+        io.bases = d_bases; io.desc = out->d_desc; io.fdesc = nullptr; io.farena = nullptr;
+        io.top_ids = b_top_ids.as<uint32_t>(); io.top_cnt = b_top_cnt.as<uint32_t>();
+        io.map_row_off = dmap ? dmap->row_off : nullptr; io.map_nodes = dmap ? dmap->nodes : nullptr;
+        io.pool = out->pool.base; io.slab_bytes = out->pool.slab_bytes; io.Np = out->pool.Np;
+        io.arena = out->arena.base; io.arena_bytes = out->arena.bytes; io.arena_cursor = out->arena.cursor; io.active = nullptr;
+        ST_TRY(run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_FWD_MAPPING ? 64 : 256));
+    }
+    // final e of jobs whose last row is dense
+    DevBuf b_take, b_desc0;
+    ST_TRY(dev_upload(b_take, dense_final, st)); ST_TRY(dev_upload(b_desc0, out->desc0, st));
+    CUDA_TRY(cudaMemcpyAsync(out->d_final, out->h_final.data(), sizeof(XF) * J, cudaMemcpyHostToDevice, st));
+    k_final_from_desc<<<(J + 127) / 128, 128, 0, st>>>(J, out->d_desc, b_desc0.as<uint64_t>(), b_len.as<uint32_t>(), b_take.as<uint8_t>(), 0, out->d_final);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out->h_final.data(), out->d_final, sizeof(XF) * J, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}
+
+// ================================================================================================ backward
+int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, bool keep_rows,
+                 const DevMappings* dmap, const RowStore* fwd, RowStore* out) {
+    cudaStream_t st = m->stream;
+    const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup;
+    out->dir = 1;
+    out->desc0.resize(J); out->len.resize(J); out->nd.assign(J, 0); out->h_final.assign(J, xf_zero());
+    out->bdense_lo.assign(J, -1); out->bdense_hi.assign(J, -1);
+    uint64_t tot_rows = 0;
+    for (uint32_t j = 0; j < J; j++) { out->desc0[j] = tot_rows; out->len[j] = jobs[j].len; tot_rows += jobs[j].len; }
+    out->n_desc = tot_rows;
+    CUDA_TRY(cudaMalloc((void**)&out->d_desc, sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1)));
+    CUDA_TRY(cudaMalloc((void**)&out->d_final, sizeof(XF) * std::max<uint32_t>(J, 1)));
+    // dense rows of job j: [lo, hi]; they are computed from hi down to lo
+    std::vector<DJob> dj(J);
+    uint64_t n_slabs = 0; uint32_t steps = 0;
+    const bool sparse_first = kind == DBGPHMM_BWD_BY_FORWARD;
+    for (uint32_t j = 0; j < J; j++) {
+        int n = (int)jobs[j].len;
+        int lo = -1, hi = -1;
+        if (n > 0) {
+            if (kind == DBGPHMM_BWD_DENSE) { lo = 0; hi = n - 1; }
+            else if (kind == DBGPHMM_BWD_SPARSE) { hi = n - 1; lo = std::max(0, n - (int)W); }
+            else if (kind == DBGPHMM_BWD_BY_FORWARD) { lo = 0; hi = std::min<int>((int)fwd->nd[j], n - 1); }  // row r dense iff r == 0 or F row r-1 dense
+        }
+        out->bdense_lo[j] = lo; out->bdense_hi[j] = hi;
+        uint32_t nd = hi >= 0 ? (uint32_t)(hi - lo + 1) : 0;
+        out->nd[j] = nd;
+        DJob& d = dj[j];
+        d.x = jobs[j].x; d.len = n; d.base_off = jobs[j].base_off; d.n_steps = nd; d.first_row = hi;
+        d.prev0_kind = PREV_B_INIT; d.prev0_slab = 0; d.slab0 = n_slabs; d.slab_mod = keep_rows ? 0 : 2; d.desc0 = out->desc0[j]; d.active_idx = -1;
+        uint64_t need = keep_rows ? nd : std::min<uint32_t>(nd, 2);
+        if (sparse_first && nd > 0 && hi < n - 1) { d.prev0_kind = PREV_SLAB; d.prev0_slab = n_slabs + need; need += 1; }  // scattered sparse row hi+1
+        n_slabs += need;
+        steps = std::max(steps, nd);
+    }
+    out->slab0.resize(J);
+    for (uint32_t j = 0; j < J; j++) out->slab0[j] = dj[j].slab0;
+    ST_TRY(alloc_pool(out->pool, N, n_slabs));
+    DevBuf b_dj, b_len, b_part, b_top_ids, b_top_cnt, b_reqs;
+    ST_TRY(dev_upload(b_dj, dj, st));
+    ST_TRY(dev_upload(b_len, out->len, st));
+    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * m->bwd.n_chunks));
+    ST_TRY(b_top_ids.alloc(sizeof(uint32_t) * (size_t)J * MAX_ACTIVE));
+    ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
+    CUDA_TRY(cudaMemsetAsync(b_top_cnt.p, 0, sizeof(uint32_t) * J, st));
+    auto slab_of_h = [&](uint32_t j, uint32_t s) { return dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+
+    auto dense_phase = [&]() -> int {
+        EvTimer tm(st, &g_times.dense_ms);
+        for (uint32_t s = 0; s < steps; s++)
+            ST_TRY(dense_backward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), nullptr));
+        for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
+        return DBGPHMM_OK;
+    };
+    auto sparse_phase = [&]() -> int {
+        EvTimer tm(st, &g_times.sparse_ms);
+        std::vector<SJob> sj;
+        uint64_t sparse_rows = 0;
+        for (uint32_t j = 0; j < J; j++) {
+            int n = (int)jobs[j].len, lo = out->bdense_lo[j], hi = out->bdense_hi[j];
+            if (n == 0) continue;
+            SJob s{};
+            s.x = jobs[j].x; s.len = n; s.base_off = jobs[j].base_off; s.dir = 1;
+            s.desc0 = out->desc0[j]; s.fdesc0 = fwd ? fwd->desc0[j] : 0; s.map_row0 = jobs[j].map_row0;
+            s.store = 1; s.active_idx = -1; s.out_idx = j; s.top0 = j;
+            if (kind == DBGPHMM_BWD_SPARSE) {
+                if (lo <= 0) continue;  // all rows dense
+                s.mode = SP_TOPN; s.row_begin = lo - 1; s.n_rows = (uint32_t)lo; s.prev0_kind = SPREV_DENSE; s.prev0_slab = slab_of_h(j, out->nd[j] - 1);
+            } else if (kind == DBGPHMM_BWD_MAPPING) {
+                s.mode = SP_MAPPING; s.row_begin = n - 1; s.n_rows = (uint32_t)n; s.prev0_kind = SPREV_B_INIT;
+            } else if (kind == DBGPHMM_BWD_BY_FORWARD) {
+                if (hi >= n - 1) continue;  // every row dense
+                s.mode = SP_BYFWD; s.row_begin = n - 1; s.n_rows = (uint32_t)(n - 1 - hi); s.prev0_kind = SPREV_B_INIT;
+            } else continue;
+            sj.push_back(s); sparse_rows += s.n_rows;
+        }
+        ST_TRY(alloc_arena(out->arena, arena_estimate(sparse_rows, m->params.n_active_nodes, kind == DBGPHMM_BWD_BY_FORWARD), st));
+        SparseIO io{};
+        io.bases = d_bases; io.desc = out->d_desc; io.fdesc = fwd ? fwd->d_desc : nullptr; io.farena = fwd ? fwd->arena.base : nullptr;
+        io.top_ids = b_top_ids.as<uint32_t>(); io.top_cnt = b_top_cnt.as<uint32_t>();
+        io.map_row_off = dmap ? dmap->row_off : nullptr; io.map_nodes = dmap ? dmap->nodes : nullptr;
+        io.pool = out->pool.base; io.slab_bytes = out->pool.slab_bytes; io.Np = out->pool.Np;
+        io.arena = out->arena.base; io.arena_bytes = out->arena.bytes; io.arena_cursor = out->arena.cursor; io.active = nullptr;
+        return run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_BWD_MAPPING ? 64 : 256);
+    };
+
+    if (!sparse_first) {
+        ST_TRY(dense_phase());
+        if (kind == DBGPHMM_BWD_SPARSE) {  // top_nodes(n_active) of the last dense row (backward.rs:174)
+            std::vector<SelectReq> reqs;
+            for (uint32_t j = 0; j < J; j++)
+                if (out->bdense_lo[j] > 0) { SelectReq r{}; r.slab = slab_of_h(j, out->nd[j] - 1); r.k = m->params.n_active_nodes; r.by_ratio = 0; r.active_idx = -1; r.out = j; reqs.push_back(r); }
+            ST_TRY(dev_upload(b_reqs, reqs, st));
+            ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), (uint32_t)reqs.size(), nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
+        }
+        ST_TRY(sparse_phase());
+    } else {
+        ST_TRY(sparse_phase());
+        // scatter sparse row hi+1 into the spare slab, then the dense tail hi..0
+        std::vector<uint64_t> didx, slabs;
+        for (uint32_t j = 0; j < J; j++)
+            if (dj[j].prev0_kind == PREV_SLAB) { didx.push_back(out->desc0[j] + out->bdense_hi[j] + 1); slabs.push_back(dj[j].prev0_slab); }
+        if (!didx.empty()) {
+            DevBuf b_didx, b_slabs;
+            ST_TRY(dev_upload(b_didx, didx, st)); ST_TRY(dev_upload(b_slabs, slabs, st));
+            dim3 g(std::min<uint32_t>((N + 255) / 256, 256), (uint32_t)didx.size());
+            k_scatter_row<<<g, 256, 0, st>>>((uint32_t)didx.size(), b_didx.as<uint64_t>(), b_slabs.as<uint64_t>(), out->d_desc, out->arena.base,
+                                             out->pool.base, out->pool.slab_bytes, out->pool.Np, N);
+            COUNT_LAUNCH();
+            k_scatter_row2<<<(uint32_t)didx.size(), 256, 0, st>>>((uint32_t)didx.size(), b_didx.as<uint64_t>(), b_slabs.as<uint64_t>(), out->d_desc,
+                                                                  out->arena.base, out->pool.base, out->pool.slab_bytes, out->pool.Np);
+            COUNT_LAUNCH();
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        ST_TRY(dense_phase());
+    }
+    // final mb: row 0 is dense whenever dense rows reach row 0
+    std::vector<uint8_t> dense_final(J, 0);
+    for (uint32_t j = 0; j < J; j++) dense_final[j] = (out->bdense_lo[j] == 0);
+    DevBuf b_take, b_desc0;
+    ST_TRY(dev_upload(b_take, dense_final, st)); ST_TRY(dev_upload(b_desc0, out->desc0, st));
+    CUDA_TRY(cudaMemcpyAsync(out->d_final, out->h_final.data(), sizeof(XF) * J, cudaMemcpyHostToDevice, st));
+    k_final_from_desc<<<(J + 127) / 128, 128, 0, st>>>(J, out->d_desc, b_desc0.as<uint64_t>(), b_len.as<uint32_t>(), b_take.as<uint8_t>(), 1, out->d_final);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out->h_final.data(), out->d_final, sizeof(XF) * J, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}

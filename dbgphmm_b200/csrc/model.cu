@@ -1,0 +1,369 @@
+// model.cu — device graph layout: relabelling, CSR adjacency, dense tiling plans, parameter sets.
+//
+// Replaces the petgraph DiGraph<PNode,PEdge> behind PHMMModel (hmmv2/common.rs:61-67,202-261) and the
+// per-candidate rebuild of it in SeqGraph::to_phmm (graph/seq_graph.rs:160-223).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "model.h"
+#include "dense.h"
+#include "sparse.h"
+
+static thread_local std::string g_error;
+unsigned long long g_launch_count = 0;
+void dbg_set_error(const std::string& s) { g_error = s; }
+
+extern "C" const char* dbgphmm_last_error(void) { return g_error.c_str(); }
+extern "C" uint64_t dbgphmm_launch_count(int reset) {
+    uint64_t c = g_launch_count;
+    if (reset) g_launch_count = 0;
+    return c;
+}
+extern "C" int dbgphmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major >= 10) ok++;
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------ params (hmmv2/params.rs:73-124)
+extern "C" void dbgphmm_params_new(double p_mismatch, double p_gap_open, double p_gap_ext, double p_end,
+                                   uint32_t n_active_nodes, uint32_t n_warmup, dbgphmm_params* q) {
+    // Prob::from_prob(v) = ln v ; Prob::to_value() = exp(ln v)   (prob.rs:58-72)
+    double l_mis = std::log(p_mismatch), l_open = std::log(p_gap_open), l_ext = std::log(p_gap_ext), l_end = std::log(p_end);
+    q->p_mismatch = l_mis; q->p_gap_open = l_open; q->p_gap_ext = l_ext; q->p_end = l_end;
+    q->p_DD = l_ext; q->p_II = l_ext; q->p_MI = l_open; q->p_MD = l_open; q->p_ID = l_open; q->p_DI = l_open;
+    q->p_MM = std::log(1.0 - 2.0 * std::exp(l_open) - std::exp(l_end));
+    q->p_DM = std::log(1.0 - std::exp(l_open) - std::exp(l_ext) - std::exp(l_end));
+    q->p_IM = q->p_DM;
+    q->p_match = std::log(1.0 - std::exp(l_mis));
+    q->p_random = std::log(0.25);
+    q->n_active_nodes = n_active_nodes;
+    q->n_warmup = n_warmup;
+    q->warmup_threshold = DBGPHMM_MAX_ACTIVE_NODES / 2;
+    q->n_max_gaps = 4;
+    q->active_node_max_ratio = 30.0;
+}
+extern "C" void dbgphmm_params_uniform(double p, dbgphmm_params* q) { dbgphmm_params_new(p, p, p, 0.00001, 40, 50, q); }
+
+LinParams to_lin(const dbgphmm_params& p) {
+    LinParams l;
+    l.p_mismatch = std::exp(p.p_mismatch); l.p_match = std::exp(p.p_match); l.p_random = std::exp(p.p_random);
+    l.p_end = std::exp(p.p_end);
+    l.p_MM = std::exp(p.p_MM); l.p_IM = std::exp(p.p_IM); l.p_DM = std::exp(p.p_DM);
+    l.p_MI = std::exp(p.p_MI); l.p_II = std::exp(p.p_II); l.p_DI = std::exp(p.p_DI);
+    l.p_MD = std::exp(p.p_MD); l.p_ID = std::exp(p.p_ID); l.p_DD = std::exp(p.p_DD);
+    l.n_active_nodes = p.n_active_nodes; l.n_warmup = p.n_warmup; l.warmup_threshold = p.warmup_threshold;
+    l.n_max_gaps = p.n_max_gaps; l.active_node_max_ratio = p.active_node_max_ratio;
+    return l;
+}
+
+template <class T>
+static int upload(T** dptr, const std::vector<T>& h) {
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc((void**)dptr, bytes));
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return DBGPHMM_OK;
+}
+
+// ------------------------------------------------------------------ dense tiling plan
+// up_off/up_node/up_eid: CSR of the upstream direction (parents for forward, children for backward).
+static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_off, const std::vector<uint32_t>& up_node,
+                      const std::vector<uint32_t>& up_eid) {
+    std::vector<uint32_t> chunk_start, loc_base, loc_node, nle, le_off, le_eid;
+    std::vector<uint16_t> le_idx;
+    std::vector<uint32_t> stamp(N, 0xffffffffu), lidx(N, 0);
+    std::vector<uint32_t> local, depth_cnt(8);
+    uint32_t start = 0, cidx = 0, max_local = 0;
+    chunk_start.push_back(0);
+    loc_base.push_back(0);
+    while (start < N) {
+        uint32_t size = std::min<uint32_t>(DENSE_CORE, N - start);
+        for (;;) {
+            // closure of [start, start+size) over HALO_HOPS upstream hops
+            local.clear();
+            std::fill(depth_cnt.begin(), depth_cnt.end(), 0);
+            for (uint32_t v = start; v < start + size; v++) { stamp[v] = cidx; lidx[v] = (uint32_t)local.size(); local.push_back(v); }
+            depth_cnt[0] = size;
+            size_t fb = 0, fe = local.size();
+            bool ok = true;
+            for (int h = 1; h <= HALO_HOPS && ok; h++) {
+                for (size_t q = fb; q < fe; q++) {
+                    uint32_t v = local[q];
+                    for (uint32_t a = up_off[v]; a < up_off[v + 1]; a++) {
+                        uint32_t u = up_node[a];
+                        if (stamp[u] != cidx) {
+                            stamp[u] = cidx; lidx[u] = (uint32_t)local.size(); local.push_back(u);
+                            depth_cnt[h]++;
+                        }
+                    }
+                    if (local.size() > DENSE_LMAX) { ok = false; break; }
+                }
+                fb = fe; fe = local.size();
+            }
+            if (ok) break;
+            // undo stamps and retry with a smaller chunk
+            for (uint32_t v : local) stamp[v] = 0xffffffffu;
+            if (size == 1) { dbg_set_error("graph too dense: the 6-hop neighbourhood of one node exceeds the tile capacity"); return DBGPHMM_ERR_INVALID; }
+            size = std::max<uint32_t>(1, size / 2);
+        }
+        // emit chunk
+        uint32_t base = (uint32_t)loc_node.size();
+        uint32_t cum = 0;
+        for (int h = 0; h < 8; h++) { cum += (h <= HALO_HOPS ? depth_cnt[h] : 0); nle.push_back(cum); }
+        uint32_t n_need_edges = nle[nle.size() - 8 + (HALO_HOPS - 1)];  // depth <= 5 gather from upstream
+        for (size_t j = 0; j < local.size(); j++) {
+            uint32_t v = local[j];
+            loc_node.push_back(v);
+            le_off.push_back((uint32_t)le_idx.size());
+            if (j < n_need_edges)
+                for (uint32_t a = up_off[v]; a < up_off[v + 1]; a++) { le_idx.push_back((uint16_t)lidx[up_node[a]]); le_eid.push_back(up_eid[a]); }
+        }
+        le_off.push_back((uint32_t)le_idx.size());  // sentinel of this chunk
+        max_local = std::max<uint32_t>(max_local, (uint32_t)local.size());
+        for (uint32_t v : local) stamp[v] = 0xffffffffu;  // a node may be halo of several chunks
+        start += size;
+        cidx++;
+        chunk_start.push_back(start);
+        loc_base.push_back(base + (uint32_t)local.size());
+        (void)base;
+    }
+    P.n_chunks = cidx;
+    P.max_local = max_local;
+    P.h_chunk_start = chunk_start;
+    ST_TRY(upload(&P.chunk_start, chunk_start));
+    ST_TRY(upload(&P.loc_base, loc_base));
+    ST_TRY(upload(&P.loc_node, loc_node));
+    ST_TRY(upload(&P.nle, nle));
+    ST_TRY(upload(&P.le_off, le_off));
+    ST_TRY(upload(&P.le_idx, le_idx));
+    ST_TRY(upload(&P.le_eid, le_eid));
+    return DBGPHMM_OK;
+}
+
+static void free_plan(DevPlan& P) {
+    cudaFree(P.chunk_start); cudaFree(P.loc_base); cudaFree(P.loc_node); cudaFree(P.nle);
+    cudaFree(P.le_off); cudaFree(P.le_idx); cudaFree(P.le_eid);
+    P = DevPlan();
+}
+
+// ------------------------------------------------------------------ graph build
+int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* src, const uint32_t* dst, const uint8_t* emission) {
+    m->N = N; m->E = E;
+    for (uint32_t e = 0; e < E; e++)
+        if (src[e] >= N || dst[e] >= N) { dbg_set_error("edge endpoint out of range"); return DBGPHMM_ERR_INVALID; }
+    m->e_src.assign(src, src + E); m->e_dst.assign(dst, dst + E);
+    // adjacency in ORIGINAL ids, newest edge first (petgraph 0.6 linked lists)
+    std::vector<uint32_t> ooff(N + 1, 0), ioff(N + 1, 0);
+    for (uint32_t e = 0; e < E; e++) { ooff[src[e] + 1]++; ioff[dst[e] + 1]++; }
+    for (uint32_t v = 0; v < N; v++) { ooff[v + 1] += ooff[v]; ioff[v + 1] += ioff[v]; }
+    std::vector<uint32_t> oe(E), ie(E), ofill(ooff.begin(), ooff.end() - 1), ifill(ioff.begin(), ioff.end() - 1);
+    for (uint32_t e = E; e-- > 0;) { oe[ofill[src[e]]++] = e; ie[ifill[dst[e]]++] = e; }
+    auto indeg = [&](uint32_t v) { return ioff[v + 1] - ioff[v]; };
+    auto outdeg = [&](uint32_t v) { return ooff[v + 1] - ooff[v]; };
+    // ---- relabel: depth-first over maximal simple chains so that a node's parent is usually its predecessor
+    std::vector<uint32_t> orig_of; orig_of.reserve(N);
+    std::vector<uint8_t> visited(N, 0);
+    auto is_head = [&](uint32_t v) {
+        if (indeg(v) != 1) return true;
+        uint32_t p = src[ie[ioff[v]]];
+        return outdeg(p) != 1 || p == v;
+    };
+    std::vector<uint32_t> stack;
+    auto run_from = [&](uint32_t s) {
+        stack.push_back(s);
+        while (!stack.empty()) {
+            uint32_t v = stack.back(); stack.pop_back();
+            if (visited[v]) continue;
+            // walk the chain
+            for (;;) {
+                visited[v] = 1; orig_of.push_back(v);
+                if (outdeg(v) == 1) {
+                    uint32_t c = dst[oe[ooff[v]]];
+                    if (!visited[c] && !is_head(c)) { v = c; continue; }
+                }
+                break;
+            }
+            // children of the tail, pushed so that the newest-first first child is visited first
+            for (uint32_t a = ooff[v + 1]; a-- > ooff[v];) { uint32_t c = dst[oe[a]]; if (!visited[c]) stack.push_back(c); }
+        }
+    };
+    for (uint32_t v = 0; v < N; v++) if (!visited[v] && indeg(v) == 0) run_from(v);
+    for (uint32_t v = 0; v < N; v++) if (!visited[v] && is_head(v)) run_from(v);
+    for (uint32_t v = 0; v < N; v++) if (!visited[v]) run_from(v);
+    m->orig_of = orig_of;
+    m->pos_of.assign(N, 0);
+    for (uint32_t p = 0; p < N; p++) m->pos_of[orig_of[p]] = p;
+    m->emission.resize(N);
+    for (uint32_t p = 0; p < N; p++) m->emission[p] = emission[orig_of[p]];
+    // ---- CSR in relabelled ids, per-node order = newest edge first
+    m->par_off.assign(N + 1, 0); m->chi_off.assign(N + 1, 0);
+    m->par_node.resize(E); m->par_eid.resize(E); m->chi_node.resize(E); m->chi_eid.resize(E);
+    for (uint32_t p = 0; p < N; p++) {
+        uint32_t v = orig_of[p];
+        m->par_off[p + 1] = m->par_off[p] + indeg(v);
+        m->chi_off[p + 1] = m->chi_off[p] + outdeg(v);
+        for (uint32_t a = 0; a < indeg(v); a++) { uint32_t e = ie[ioff[v] + a]; m->par_node[m->par_off[p] + a] = m->pos_of[src[e]]; m->par_eid[m->par_off[p] + a] = e; }
+        for (uint32_t a = 0; a < outdeg(v); a++) { uint32_t e = oe[ooff[v] + a]; m->chi_node[m->chi_off[p] + a] = m->pos_of[dst[e]]; m->chi_eid[m->chi_off[p] + a] = e; }
+    }
+    ST_TRY(upload(&m->d_pos_of, m->pos_of)); ST_TRY(upload(&m->d_orig_of, m->orig_of)); ST_TRY(upload(&m->d_emission, m->emission));
+    ST_TRY(upload(&m->d_par_off, m->par_off)); ST_TRY(upload(&m->d_par_node, m->par_node)); ST_TRY(upload(&m->d_par_eid, m->par_eid));
+    ST_TRY(upload(&m->d_chi_off, m->chi_off)); ST_TRY(upload(&m->d_chi_node, m->chi_node)); ST_TRY(upload(&m->d_chi_eid, m->chi_eid));
+    ST_TRY(build_plan(m->fwd, N, m->par_off, m->par_node, m->par_eid));
+    ST_TRY(build_plan(m->bwd, N, m->chi_off, m->chi_node, m->chi_eid));
+    return DBGPHMM_OK;
+}
+
+int model_upload_probs(dbgphmm_model* m, const double* log_init, const double* log_trans) {
+    std::vector<double> init(m->N), trans(std::max<uint32_t>(m->E, 1));
+    for (uint32_t p = 0; p < m->N; p++) init[p] = std::exp(log_init[m->orig_of[p]]);
+    for (uint32_t e = 0; e < m->E; e++) trans[e] = std::exp(log_trans[e]);
+    if (m->n_batch != 1 || !m->d_init) {
+        cudaFree(m->d_init); cudaFree(m->d_trans); m->d_init = m->d_trans = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&m->d_init, sizeof(double) * std::max<uint32_t>(m->N, 1)));
+        CUDA_TRY(cudaMalloc((void**)&m->d_trans, sizeof(double) * std::max<uint32_t>(m->E, 1)));
+        m->n_batch = 1;
+    }
+    CUDA_TRY(cudaMemcpy(m->d_init, init.data(), sizeof(double) * m->N, cudaMemcpyHostToDevice));
+    if (m->E) CUDA_TRY(cudaMemcpy(m->d_trans, trans.data(), sizeof(double) * m->E, cudaMemcpyHostToDevice));
+    return DBGPHMM_OK;
+}
+
+void model_free(dbgphmm_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_pos_of); cudaFree(m->d_orig_of); cudaFree(m->d_emission);
+    cudaFree(m->d_par_off); cudaFree(m->d_par_node); cudaFree(m->d_par_eid);
+    cudaFree(m->d_chi_off); cudaFree(m->d_chi_node); cudaFree(m->d_chi_eid);
+    cudaFree(m->d_init); cudaFree(m->d_trans);
+    free_plan(m->fwd); free_plan(m->bwd);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+// ------------------------------------------------------------------ copy numbers -> parameters on the device
+// graph/seq_graph.rs:110-135,160-273 with edge copy numbers None (multi_dbg.rs:1386-1387,1434-1437).
+__global__ void k_copy_total(const uint32_t* __restrict__ cn, const uint8_t* __restrict__ emission, const uint32_t* __restrict__ orig_of,
+                             uint32_t N, int mode, unsigned long long* __restrict__ total) {
+    uint32_t x = blockIdx.y;
+    unsigned long long s = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        if (emission[p] != 'n') {
+            unsigned long long c = cn[(size_t)x * N + orig_of[p]];
+            if (mode == 1 && c < 1) c = 1;
+            if (mode == 2) c = 1;
+            s += c;
+        }
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&total[x], s);
+}
+__global__ void k_copy_to_probs(const uint32_t* __restrict__ cn, const uint8_t* __restrict__ emission, const uint32_t* __restrict__ orig_of,
+                                const uint32_t* __restrict__ chi_off, const uint32_t* __restrict__ chi_node, const uint32_t* __restrict__ chi_eid,
+                                uint32_t N, uint32_t E, int mode, const unsigned long long* __restrict__ total,
+                                double* __restrict__ init, double* __restrict__ trans) {
+    uint32_t x = blockIdx.y;
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    auto eff = [&](uint32_t q) -> unsigned long long {
+        if (emission[q] == 'n') return 0ull;
+        unsigned long long c = cn[(size_t)x * N + orig_of[q]];
+        if (mode == 1 && c < 1) c = 1;
+        if (mode == 2) c = 1;
+        return c;
+    };
+    unsigned long long c = eff(p);
+    init[(size_t)x * N + p] = (emission[p] != 'n' && total[x] > 0) ? (double)c / (double)total[x] : 0.0;
+    unsigned long long ct = 0;
+    for (uint32_t a = chi_off[p]; a < chi_off[p + 1]; a++) ct += eff(chi_node[a]);
+    for (uint32_t a = chi_off[p]; a < chi_off[p + 1]; a++) {
+        uint32_t q = chi_node[a];
+        unsigned long long cq = eff(q);
+        trans[(size_t)x * E + chi_eid[a]] = (emission[q] != 'n' && ct > 0) ? (double)cq / (double)ct : 0.0;
+    }
+}
+
+extern "C" int dbgphmm_model_set_copy_nums_batch(dbgphmm_model* m, uint32_t n_batch, const uint32_t* copy_nums, int mode) {
+    if (!m || !copy_nums || n_batch == 0 || mode < 0 || mode > 2) { dbg_set_error("set_copy_nums_batch: bad argument"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    uint32_t N = m->N, E = m->E;
+    uint32_t* d_cn = nullptr; unsigned long long* d_total = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_cn, sizeof(uint32_t) * (size_t)n_batch * N));
+    CUDA_TRY(cudaMalloc((void**)&d_total, sizeof(unsigned long long) * n_batch));
+    CUDA_TRY(cudaMemcpyAsync(d_cn, copy_nums, sizeof(uint32_t) * (size_t)n_batch * N, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long) * n_batch, m->stream));
+    cudaFree(m->d_init); cudaFree(m->d_trans); m->d_init = m->d_trans = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&m->d_init, sizeof(double) * (size_t)n_batch * std::max<uint32_t>(N, 1)));
+    CUDA_TRY(cudaMalloc((void**)&m->d_trans, sizeof(double) * (size_t)n_batch * std::max<uint32_t>(E, 1)));
+    m->n_batch = n_batch;
+    dim3 g1(std::min<uint32_t>((N + 255) / 256, 1024), n_batch), g2((N + 255) / 256, n_batch);
+    k_copy_total<<<g1, 256, 0, m->stream>>>(d_cn, m->d_emission, m->d_orig_of, N, mode, d_total); COUNT_LAUNCH();
+    k_copy_to_probs<<<g2, 256, 0, m->stream>>>(d_cn, m->d_emission, m->d_orig_of, m->d_chi_off, m->d_chi_node, m->d_chi_eid, N, E, mode,
+                                                d_total, m->d_init, m->d_trans); COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    cudaFree(d_cn); cudaFree(d_total);
+    return DBGPHMM_OK;
+}
+
+extern "C" int dbgphmm_model_get_probs(const dbgphmm_model* m, uint32_t x, double* log_init, double* log_trans) {
+    if (!m || x >= m->n_batch) { dbg_set_error("get_probs: bad argument"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    std::vector<double> init(m->N), trans(m->E);
+    CUDA_TRY(cudaMemcpy(init.data(), m->d_init + (size_t)x * m->N, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
+    if (m->E) CUDA_TRY(cudaMemcpy(trans.data(), m->d_trans + (size_t)x * m->E, sizeof(double) * m->E, cudaMemcpyDeviceToHost));
+    for (uint32_t p = 0; p < m->N; p++) log_init[m->orig_of[p]] = std::log(init[p]);
+    for (uint32_t e = 0; e < m->E; e++) log_trans[e] = std::log(trans[e]);
+    return DBGPHMM_OK;
+}
+
+extern "C" int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const uint32_t* edge_src, const uint32_t* edge_dst,
+                                    const uint8_t* emission, const double* log_init, const double* log_trans,
+                                    const dbgphmm_params* params, int device, uint64_t mem_budget_bytes, dbgphmm_model** out) {
+    if (!out || !params || !emission || !log_init || (n_edges && (!edge_src || !edge_dst || !log_trans)) || n_nodes == 0) {
+        dbg_set_error("model_create: bad argument"); return DBGPHMM_ERR_INVALID;
+    }
+    if (params->n_max_gaps != 4) { dbg_set_error("model_create: n_max_gaps must be 4 (table.rs:17)"); return DBGPHMM_ERR_INVALID; }
+    if (params->n_active_nodes == 0 || params->n_active_nodes >= DBGPHMM_MAX_ACTIVE_NODES || params->n_warmup == 0) {
+        dbg_set_error("model_create: need 0 < n_active_nodes < 400 and n_warmup > 0 (params.rs:81-83)"); return DBGPHMM_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        dbg_set_error("model_create: no CUDA device (this library has no CPU path)"); return DBGPHMM_ERR_CUDA;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    dbgphmm_model* m = new dbgphmm_model();
+    m->device = device; m->params = *params; m->lin = to_lin(*params);
+    int st = DBGPHMM_OK;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { dbg_set_error("stream create failed"); st = DBGPHMM_ERR_CUDA; }
+    if (st == DBGPHMM_OK) st = model_build_graph(m, n_nodes, n_edges, edge_src, edge_dst, emission);
+    if (st == DBGPHMM_OK) st = model_upload_probs(m, log_init, log_trans);
+    if (st == DBGPHMM_OK) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        m->mem_budget = mem_budget_bytes ? mem_budget_bytes : (uint64_t)(fr * 0.7);
+        st = dense_configure(m);
+        if (st == DBGPHMM_OK) st = sparse_configure(m);
+    }
+    if (st != DBGPHMM_OK) { model_free(m); return st; }
+    *out = m;
+    return DBGPHMM_OK;
+}
+extern "C" void dbgphmm_model_destroy(dbgphmm_model* m) { model_free(m); }
+extern "C" int dbgphmm_model_set_params(dbgphmm_model* m, const dbgphmm_params* p) {
+    if (!m || !p || p->n_max_gaps != 4) { dbg_set_error("set_params: bad argument"); return DBGPHMM_ERR_INVALID; }
+    m->params = *p; m->lin = to_lin(*p);
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_model_set_probs(dbgphmm_model* m, const double* log_init, const double* log_trans) {
+    if (!m || !log_init) { dbg_set_error("set_probs: bad argument"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    return model_upload_probs(m, log_init, log_trans);
+}
+extern "C" uint32_t dbgphmm_model_n_nodes(const dbgphmm_model* m) { return m ? m->N : 0; }
+extern "C" uint32_t dbgphmm_model_n_batch(const dbgphmm_model* m) { return m ? m->n_batch : 0; }

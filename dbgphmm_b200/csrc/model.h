@@ -1,0 +1,89 @@
+// model.h — host-side structures of the device graph (internal; the public surface is include/dbgphmm_b200.h)
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "../../include/dbgphmm_b200.h"
+
+// thread-local error string + status helpers
+void dbg_set_error(const std::string& s);
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            dbg_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+            return DBGPHMM_ERR_CUDA;                                                           \
+        }                                                                                      \
+    } while (0)
+#define ST_TRY(expr)                 \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != DBGPHMM_OK) return _s; \
+    } while (0)
+
+extern unsigned long long g_launch_count;
+#define COUNT_LAUNCH() (++g_launch_count)
+
+// Tiling plan of the dense DP for one direction.  A chunk is a run of consecutive (relabelled) nodes; its
+// local set adds every node within HALO_HOPS hops upstream (forward: ancestors, backward: descendants), sorted
+// by hop depth, so that one CTA can compute a whole DP row of the chunk from the previous row alone.
+struct DevPlan {
+    uint32_t n_chunks = 0;
+    uint32_t max_local = 0;
+    uint32_t* chunk_start = nullptr;  // [n_chunks+1] first relabelled node of each chunk
+    uint32_t* loc_base = nullptr;     // [n_chunks+1] offset of the chunk's local node list
+    uint32_t* loc_node = nullptr;     // [loc_total] relabelled node id of each local slot (core nodes first)
+    uint32_t* nle = nullptr;          // [n_chunks][8] number of local slots with depth <= h (h = 0..6)
+    uint32_t* le_off = nullptr;       // [loc_total + n_chunks] per-slot offset into le_idx/le_eid (chunk c uses base loc_base[c]+c)
+    uint16_t* le_idx = nullptr;       // local slot of the upstream neighbour
+    uint32_t* le_eid = nullptr;       // original EdgeIndex of that edge (indexes trans)
+    std::vector<uint32_t> h_chunk_start;
+};
+
+struct dbgphmm_model {
+    int device = 0;
+    uint32_t N = 0, E = 0;
+    uint32_t n_batch = 1;
+    dbgphmm_params params;  // logs, as given
+    LinParams lin;          // linear
+    uint64_t mem_budget = 0;
+    cudaStream_t stream = nullptr;
+
+    // host copies (relabelled ids unless noted)
+    std::vector<uint32_t> pos_of;   // [N] original id -> relabelled
+    std::vector<uint32_t> orig_of;  // [N] relabelled -> original id
+    std::vector<uint8_t> emission;  // [N] relabelled
+    std::vector<uint32_t> par_off, par_node, par_eid;  // parents CSR, newest-edge-first (graph/iterators.rs:133-155)
+    std::vector<uint32_t> chi_off, chi_node, chi_eid;  // children CSR, newest-edge-first (graph/iterators.rs:104-131)
+    std::vector<uint32_t> e_src, e_dst;                // original edge list, ORIGINAL node ids
+
+    // device graph
+    uint32_t *d_pos_of = nullptr, *d_orig_of = nullptr;
+    uint8_t* d_emission = nullptr;
+    uint32_t *d_par_off = nullptr, *d_par_node = nullptr, *d_par_eid = nullptr;
+    uint32_t *d_chi_off = nullptr, *d_chi_node = nullptr, *d_chi_eid = nullptr;
+    double* d_init = nullptr;   // [n_batch][N] linear, relabelled node order
+    double* d_trans = nullptr;  // [n_batch][E] linear, original EdgeIndex order
+    DevPlan fwd, bwd;
+};
+
+struct dbgphmm_reads {
+    uint64_t n_reads = 0;
+    std::vector<uint64_t> off;
+    std::vector<uint8_t> bases;
+    uint8_t* d_bases = nullptr;  // device copy (lazy)
+    int device = -1;
+};
+
+struct dbgphmm_mappings {
+    std::vector<uint64_t> read_off, row_off;
+    std::vector<uint32_t> nodes;  // ORIGINAL node ids
+    std::vector<double> logp;
+};
+
+int model_build_graph(dbgphmm_model* m, uint32_t n_nodes, uint32_t n_edges, const uint32_t* src, const uint32_t* dst,
+                      const uint8_t* emission);
+int model_upload_probs(dbgphmm_model* m, const double* log_init, const double* log_trans);
+void model_free(dbgphmm_model* m);
+LinParams to_lin(const dbgphmm_params& p);

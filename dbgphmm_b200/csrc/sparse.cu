@@ -1,0 +1,658 @@
+// sparse.cu — sparse DP rows: per-row active-node selection + f_step / b_step over <= MAX_ACTIVE nodes.
+//
+// One CTA owns one (read, candidate X) job and walks its rows sequentially; the previous and the current row
+// (SparseVec-like entry tables with a hash index) live in shared memory.  Reproduces, index-for-index:
+//   PHMMTable::to_nodevec / top_nodes / top_nodes_by_score_ratio / filled_nodes   table.rs:117-149,199-211
+//   to_childs, to_childs_and_us, to_parents_and_us (first-seen unique, cap 400)    active_nodes.rs:15-56
+//   f_step with adaptive Del sets                                                  forward.rs:276-306,423-466
+//   b_step with adaptive Del sets                                                  backward.rs:216-261,299-343
+// Entry order of a row = insertion order of the reference's SparseVec: the step's `nodes` first (they hold m, i),
+// then nodes that only ever received a Del value, in the order the Del rounds first touched them.
+#include <algorithm>
+#include "sparse.h"
+
+#define SP_TENT 0x80000000u
+#define SP_ABSENT 0xffffffffu
+
+struct SGraph {
+    uint32_t N, E;
+    const uint8_t* emission;
+    const double *init, *trans;
+    const uint32_t *par_off, *par_node, *par_eid, *chi_off, *chi_node, *chi_eid;
+    const uint32_t* pos_of;
+};
+
+struct SS {  // shared-memory view of one job
+    uint32_t cap, hmask;
+    int hshift;
+    // previous row (packed cells)
+    uint32_t* p_id; double *p_m, *p_i, *p_d; int* p_ex;
+    uint32_t *ph_key, *ph_val;
+    // current row under construction
+    uint32_t* c_id; double *c_m, *c_i; int* c_mie; double* c_dv; int* c_de;
+    double* dval[2]; int* dexp[2]; uint32_t* dstamp[2];
+    uint32_t* firstpos; uint32_t* d_seen;
+    uint32_t *ch_key, *ch_val;
+    // lists
+    uint32_t* top_id;                    // [MAX_ACTIVE]
+    uint32_t* la_id[2]; uint16_t* la_slot[2];  // ping-pong node lists (ids + slots), [cap] each
+    uint32_t* act_id; uint16_t* act_slot;      // the step's `nodes` (m/i entries)
+    uint16_t* dlist;                     // [cap] slots in d insertion order
+    uint32_t* scan;                      // [cap + 1] scratch
+    // ranking scratch
+    int* k_T; unsigned long long* k_mant;
+};
+
+__device__ __forceinline__ uint32_t sp_hash(uint32_t id, int shift) { return (id * 2654435761u) >> shift; }
+__device__ __forceinline__ int sp_find(const uint32_t* key, const uint32_t* val, uint32_t hmask, int hshift, uint32_t id) {
+    uint32_t h = sp_hash(id, hshift);
+    for (;;) {
+        uint32_t k = key[h];
+        if (k == id + 1) { uint32_t v = val[h]; return v < SP_TENT ? (int)v : -1; }
+        if (k == 0) return -1;
+        h = (h + 1) & hmask;
+    }
+}
+// returns the cell holding `id`, inserting the key (value untouched = SP_ABSENT) if new
+__device__ __forceinline__ uint32_t sp_cell(uint32_t* key, uint32_t hmask, int hshift, uint32_t id) {
+    uint32_t h = sp_hash(id, hshift);
+    for (;;) {
+        uint32_t k = key[h];
+        if (k == id + 1) return h;
+        if (k == 0) {
+            uint32_t old = atomicCAS(&key[h], 0u, id + 1);
+            if (old == 0u || old == id + 1) return h;
+        } else h = (h + 1) & hmask;
+    }
+}
+
+// in-place exclusive scan of arr[0..n) ; arr[n] = total.  All threads must call.
+__device__ uint32_t block_exscan(uint32_t* arr, int n) {
+    __shared__ uint32_t wtot[32];
+    __shared__ uint32_t carry_s;
+    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, w = tid >> 5, nw = (B + 31) >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += B) {
+        int idx = base + tid;
+        uint32_t v = idx < n ? arr[idx] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wtot[w] = x;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int k = 0; k < w; k++) woff += wtot[k];
+        uint32_t carry = carry_s;
+        if (idx < n) arr[idx] = carry + woff + x - v;
+        __syncthreads();
+        if (tid == B - 1) carry_s = carry + woff + x;
+        (void)nw;
+        __syncthreads();
+    }
+    uint32_t tot = carry_s;
+    if (tid == 0) arr[n] = tot;
+    __syncthreads();
+    return tot;
+}
+
+__device__ __forceinline__ XF block_xsum(XF a) {  // deterministic block reduction; result valid in every thread
+    __shared__ XF wv[32];
+    __shared__ XF res;
+    for (int o = 16; o; o >>= 1) {
+        XF b; b.v = __shfl_down_sync(0xffffffffu, a.v, o); b.e = __shfl_down_sync(0xffffffffu, a.e, o);
+        a = xadd(a, b);
+    }
+    if ((threadIdx.x & 31) == 0) wv[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XF t = xf_zero();
+        for (int k = 0; k < (int)((blockDim.x + 31) >> 5); k++) t = xadd(t, wv[k]);
+        res = t;
+    }
+    __syncthreads();
+    XF r = res;
+    __syncthreads();
+    return r;
+}
+
+// Unique, first-occurrence-ordered expansion of `src` (node ids) over an adjacency CSR (active_nodes.rs:15-56).
+// and_us: the sources themselves come first.  with_nbrs: append their neighbours (in CSR = newest-edge-first order).
+// Nodes without a current-row entry get one appended (zeroed).  Output: out_id/out_slot, *n_out (<= max_out).
+// Returns false if the entry table would overflow `cap`.
+__device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t* off, const uint32_t* nbr, bool and_us, bool with_nbrs,
+                          uint32_t* out_id, uint16_t* out_slot, int max_out, uint32_t* n_ent_io, int* n_out) {
+    __shared__ uint32_t s_nent, s_nout;
+    __shared__ int s_ovf;
+    const int tid = threadIdx.x, B = blockDim.x;
+    const uint32_t n_ent0 = *n_ent_io;
+    const bool cap_limited = (int)S.cap < max_out;  // the table cannot hold the reference's 400-entry list
+    if (cap_limited) max_out = (int)S.cap;
+    for (int q = tid; q < n_src; q += B) S.scan[q] = with_nbrs ? (off[src[q] + 1] - off[src[q]]) : 0u;
+    for (uint32_t e = tid; e < n_ent0; e += B) S.firstpos[e] = SP_ABSENT;
+    if (tid == 0) s_ovf = 0;
+    __syncthreads();
+    const uint32_t n_nb = block_exscan(S.scan, n_src);
+    const uint32_t n_self = and_us ? (uint32_t)n_src : 0u;
+    const uint32_t C = n_self + n_nb;
+    auto cand = [&](uint32_t p) -> uint32_t {
+        if (p < n_self) return src[p];
+        uint32_t pp = p - n_self;
+        int lo = 0, hi = n_src;  // last q with scan[q] <= pp
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.scan[mid] <= pp) lo = mid; else hi = mid; }
+        return nbr[off[src[lo]] + (pp - S.scan[lo])];
+    };
+    // phase 1: first position of every id
+    for (uint32_t p = tid; p < C; p += B) {
+        uint32_t id = cand(p);
+        uint32_t cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
+        uint32_t v = S.ch_val[cell];
+        if (v < SP_TENT) atomicMin(&S.firstpos[v], p);
+        else atomicMin(&S.ch_val[cell], SP_TENT | p);
+    }
+    __syncthreads();
+    // phase 2: order-preserving compaction (kept count in the low half, new-entry count in the high half)
+    __shared__ uint32_t wtot[32];
+    __shared__ uint32_t carry_s;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = tid & 31, w = tid >> 5;
+    for (uint32_t base = 0; base < C; base += B) {
+        uint32_t p = base + tid;
+        uint32_t id = 0, cell = 0, v = SP_ABSENT;
+        bool kept = false, isnew = false;
+        if (p < C) {
+            id = cand(p);
+            cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
+            v = S.ch_val[cell];
+            if (v < SP_TENT) kept = (S.firstpos[v] == p);
+            else if (v == (SP_TENT | p)) { kept = true; isnew = true; }
+        }
+        uint32_t val = (kept ? 1u : 0u) | (isnew ? 0x10000u : 0u), x = val;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wtot[w] = x;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int k = 0; k < w; k++) woff += wtot[k];
+        uint32_t carry = carry_s;
+        uint32_t excl = carry + woff + x - val;
+        if (kept) {
+            uint32_t oi = excl & 0xffffu, ni = excl >> 16;
+            if ((int)oi < max_out) {
+                uint32_t slot = isnew ? n_ent0 + ni : v;
+                if (slot >= S.cap) s_ovf = 1;
+                else {
+                    if (isnew) {
+                        S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
+                        S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
+                        S.ch_val[cell] = slot;
+                    }
+                    out_id[oi] = id; out_slot[oi] = (uint16_t)slot;
+                }
+            } else if (isnew) S.ch_val[cell] = SP_ABSENT;
+        }
+        __syncthreads();
+        if (tid == B - 1) carry_s = carry + woff + x;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint32_t tot = carry_s;
+        uint32_t kept_tot = tot & 0xffffu;
+        // new entries among the first max_out kept ones: recount is not needed when nothing was truncated
+        s_nout = kept_tot < (uint32_t)max_out ? kept_tot : (uint32_t)max_out;
+        if (cap_limited && kept_tot > (uint32_t)max_out) s_ovf = 1;
+        s_nent = n_ent0;  // fixed below
+    }
+    __syncthreads();
+    // number of new entries actually appended = max slot + 1 among outputs (slots are appended in order)
+    {
+        uint32_t mx = n_ent0;
+        for (uint32_t o = tid; o < s_nout; o += B) { uint32_t sl = out_slot[o]; if (sl + 1 > mx) mx = sl + 1; }
+        for (int o = 16; o; o >>= 1) { uint32_t y = __shfl_down_sync(0xffffffffu, mx, o); mx = y > mx ? y : mx; }
+        if (lane == 0) atomicMax(&s_nent, mx);
+    }
+    __syncthreads();
+    *n_out = (int)s_nout;
+    *n_ent_io = s_nent;
+    bool ok = !s_ovf;
+    __syncthreads();
+    return ok;
+}
+
+// merged value key of packed entry e of the previous row
+__device__ __forceinline__ void sp_key(const SS& S, uint32_t e, int* T, unsigned long long* mant) {
+    double v = S.p_m[e] + S.p_i[e] + S.p_d[e];
+    if (v == 0.0) { *T = XF_ZERO_E; *mant = 0; return; }
+    long long b = __double_as_longlong(v);
+    *T = S.p_ex[e] + (int)((b >> 52) & 0x7ff) - 1023;
+    *mant = (unsigned long long)b & 0xfffffffffffffull;
+}
+
+// top-K ids of the previous (packed) row in descending merged value, ties by entry position (UNPINNED in the
+// reference); by_ratio keeps the prefix with ln v0 - ln v < ratio of the top-400 list (table.rs:134-149).
+__device__ int sp_top_of_prev(SS& S, uint32_t n_prev, uint32_t K, bool by_ratio, double ratio, uint32_t* out_id) {
+    __shared__ double s_L0;
+    __shared__ uint32_t s_cnt;
+    const int tid = threadIdx.x, B = blockDim.x;
+    for (uint32_t e = tid; e < n_prev; e += B) sp_key(S, e, &S.k_T[e], &S.k_mant[e]);
+    if (tid == 0) { s_cnt = 0; s_L0 = -INFINITY; }
+    __syncthreads();
+    const uint32_t KK = K < n_prev ? K : n_prev;
+    for (uint32_t e = tid; e < n_prev; e += B) {
+        int T = S.k_T[e]; unsigned long long mt = S.k_mant[e];
+        uint32_t rank = 0;
+        for (uint32_t f = 0; f < n_prev; f++) {
+            int Tf = S.k_T[f]; unsigned long long mf = S.k_mant[f];
+            bool gt = (Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)));
+            rank += gt ? 1u : 0u;
+        }
+        if (rank < KK) out_id[rank] = S.p_id[e];
+        S.scan[e] = rank;  // remember for the ratio filter
+        if (rank == 0) s_L0 = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
+    }
+    __syncthreads();
+    if (!by_ratio) return (int)KK;
+    for (uint32_t e = tid; e < n_prev; e += B) {
+        if (S.scan[e] < KK) {
+            double L = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
+            if (s_L0 - L < ratio) atomicAdd(&s_cnt, 1u);
+        }
+    }
+    __syncthreads();
+    int r = (int)s_cnt;
+    __syncthreads();
+    return r;
+}
+
+struct PrevAcc {  // accessor of the row before the current one
+    int kind;     // 0 sparse (shared memory), 1 dense slab, 2 B-init, 3 F-init
+    const double *gm, *gi, *gd; const int* ge;
+    double p_end;
+};
+__device__ __forceinline__ void prev_get(const SS& S, const PrevAcc& P, uint32_t id, double* m, double* i, double* d, int* ex) {
+    if (P.kind == 0) {
+        int sl = sp_find(S.ph_key, S.ph_val, S.hmask, S.hshift, id);
+        if (sl < 0) { *m = *i = *d = 0.0; *ex = 0; } else { *m = S.p_m[sl]; *i = S.p_i[sl]; *d = S.p_d[sl]; *ex = S.p_ex[sl]; }
+    } else if (P.kind == 1) { *m = P.gm[id]; *i = P.gi[id]; *d = P.gd[id]; *ex = P.ge[id]; }
+    else if (P.kind == 2) { *m = *i = *d = P.p_end; *ex = 0; }
+    else { *m = *i = *d = 0.0; *ex = 0; }
+}
+
+extern __shared__ __align__(16) unsigned char sp_smem[];
+
+__global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, SparseIO io, uint32_t cap, uint32_t hcap) {
+    const SJob jb = jobs[blockIdx.x];
+    if (jb.active_idx >= 0 && !io.active[jb.active_idx]) return;
+    if (jb.n_rows == 0) return;
+    const int tid = threadIdx.x, B = blockDim.x;
+    // ---- carve shared memory
+    SS S;
+    S.cap = cap; S.hmask = hcap - 1; S.hshift = 32 - (31 - __clz(hcap));
+    unsigned char* q = sp_smem;
+    auto take = [&](size_t bytes) { unsigned char* r = q; q += (bytes + 15) & ~(size_t)15; return r; };
+    S.p_m = (double*)take(8 * cap); S.p_i = (double*)take(8 * cap); S.p_d = (double*)take(8 * cap);
+    S.c_m = (double*)take(8 * cap); S.c_i = (double*)take(8 * cap); S.c_dv = (double*)take(8 * cap);
+    S.dval[0] = (double*)take(8 * cap); S.dval[1] = (double*)take(8 * cap);
+    S.k_mant = (unsigned long long*)take(8 * cap);
+    S.p_id = (uint32_t*)take(4 * cap); S.p_ex = (int*)take(4 * cap);
+    S.c_id = (uint32_t*)take(4 * cap); S.c_mie = (int*)take(4 * cap); S.c_de = (int*)take(4 * cap);
+    S.dexp[0] = (int*)take(4 * cap); S.dexp[1] = (int*)take(4 * cap);
+    S.dstamp[0] = (uint32_t*)take(4 * cap); S.dstamp[1] = (uint32_t*)take(4 * cap);
+    S.firstpos = (uint32_t*)take(4 * cap); S.d_seen = (uint32_t*)take(4 * cap);
+    S.k_T = (int*)take(4 * cap);
+    S.scan = (uint32_t*)take(4 * (cap + 1));
+    S.ph_key = (uint32_t*)take(4 * hcap); S.ph_val = (uint32_t*)take(4 * hcap);
+    S.ch_key = (uint32_t*)take(4 * hcap); S.ch_val = (uint32_t*)take(4 * hcap);
+    S.top_id = (uint32_t*)take(4 * MAX_ACTIVE);
+    S.la_id[0] = (uint32_t*)take(4 * cap); S.la_id[1] = (uint32_t*)take(4 * cap); S.act_id = (uint32_t*)take(4 * cap);
+    S.la_slot[0] = (uint16_t*)take(2 * cap); S.la_slot[1] = (uint16_t*)take(2 * cap); S.act_slot = (uint16_t*)take(2 * cap);
+    S.dlist = (uint16_t*)take(2 * cap);
+
+    __shared__ XF s_mb, s_ib;          // begin scalars of the previous row (forward) / ib of the next row (backward)
+    __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
+    __shared__ int s_fail;
+    __shared__ unsigned long long s_cells;
+    const double* init = G.init + (size_t)jb.x * G.N;
+    const double* trans = G.trans + (size_t)jb.x * G.E;
+    const bool fwd = jb.dir == 0;
+    const bool adaptive = (jb.mode == SP_TOPN || jb.mode == SP_RATIO);
+    if (tid == 0) {
+        s_page_left = 0; s_page_off = 0; s_fail = SJ_OK; s_cells = 0;
+        if (fwd) {
+            if (jb.row_begin == 0) { s_mb = xf(1.0, 0); s_ib = xf_zero(); }
+            else { s_mb = io.desc[jb.desc0 + jb.row_begin - 1].mb; s_ib = io.desc[jb.desc0 + jb.row_begin - 1].ib; }
+        } else {
+            s_mb = xf_zero();
+            s_ib = (jb.row_begin == (int)jb.len - 1) ? xf_zero() : io.desc[jb.desc0 + jb.row_begin + 1].ib;
+        }
+    }
+    uint32_t n_prev = 0;   // packed entries of the previous row (sparse prev only)
+    XF last_scalar = xf_zero();
+    __syncthreads();
+
+    for (uint32_t s = 0; s < jb.n_rows; s++) {
+        const int row = fwd ? jb.row_begin + (int)s : jb.row_begin - (int)s;
+        const uint8_t x = io.bases[jb.base_off + row];
+        PrevAcc PA;
+        PA.p_end = lp.p_end; PA.gm = PA.gi = PA.gd = nullptr; PA.ge = nullptr;
+        if (s > 0) PA.kind = 0;
+        else if (jb.prev0_kind == SPREV_DENSE) {
+            PA.kind = 1;
+            const char* sl = io.pool + jb.prev0_slab * io.slab_bytes;
+            PA.gm = (const double*)sl; PA.gi = PA.gm + io.Np; PA.gd = PA.gi + io.Np; PA.ge = (const int*)(PA.gd + io.Np);
+        } else PA.kind = jb.prev0_kind == SPREV_B_INIT ? 2 : 3;
+
+        // ---------------- 1. node list of this step
+        int n_top = 0;
+        if (jb.mode == SP_TOPN || jb.mode == SP_RATIO) {
+            if (s == 0) {
+                n_top = (int)io.top_cnt[jb.top0];
+                for (int t = tid; t < n_top; t += B) S.top_id[t] = io.top_ids[(size_t)jb.top0 * MAX_ACTIVE + t];
+            } else {
+                n_top = sp_top_of_prev(S, n_prev, jb.mode == SP_RATIO ? MAX_ACTIVE : lp.n_active_nodes, jb.mode == SP_RATIO,
+                                       lp.active_node_max_ratio, S.top_id);
+            }
+        } else if (jb.mode == SP_MAPPING) {
+            uint64_t a = io.map_row_off[jb.map_row0 + row], b = io.map_row_off[jb.map_row0 + row + 1];
+            n_top = (int)(b - a);
+            if (n_top > MAX_ACTIVE) n_top = MAX_ACTIVE;
+            for (int t = tid; t < n_top; t += B) S.top_id[t] = io.map_nodes[a + t];
+        } else {  // SP_BYFWD: filled_nodes() of forward row (row-1): top-|m entries| of its merged vector
+            const RowDesc fr = io.fdesc[jb.fdesc0 + row - 1];
+            const char* pay = io.farena + fr.off;
+            const double* fm = (const double*)pay; const double* fi = fm + fr.n_ent; const double* fd = fi + fr.n_ent;
+            const uint32_t* fid = (const uint32_t*)(fd + fr.n_ent); const int* fex = (const int*)(fid + fr.n_ent);
+            if (fr.n_ent > cap) { if (tid == 0) s_fail = SJ_NEED_BIG; }
+            else {
+                // stage into the *current* arrays (not yet in use) and rank there
+                for (uint32_t e = tid; e < fr.n_ent; e += B) {
+                    double v = fm[e] + fi[e] + fd[e];
+                    if (v == 0.0) { S.k_T[e] = XF_ZERO_E; S.k_mant[e] = 0; }
+                    else { long long bb = __double_as_longlong(v); S.k_T[e] = fex[e] + (int)((bb >> 52) & 0x7ff) - 1023; S.k_mant[e] = (unsigned long long)bb & 0xfffffffffffffull; }
+                    S.c_id[e] = fid[e];
+                }
+                __syncthreads();
+                for (uint32_t e = tid; e < fr.n_ent; e += B) {
+                    int T = S.k_T[e]; unsigned long long mt = S.k_mant[e];
+                    uint32_t rank = 0;
+                    for (uint32_t f = 0; f < fr.n_ent; f++) {
+                        int Tf = S.k_T[f]; unsigned long long mf = S.k_mant[f];
+                        rank += ((Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)))) ? 1u : 0u;
+                    }
+                    if (rank < fr.n_mi) S.top_id[rank] = S.c_id[e];
+                }
+                n_top = (int)fr.n_mi;
+            }
+        }
+        __syncthreads();
+        if (s_fail) break;
+
+        // ---------------- 2. reset the current row
+        uint32_t n_ent = 0;
+        for (uint32_t h = tid; h < hcap; h += B) { S.ch_key[h] = 0; S.ch_val[h] = SP_ABSENT; }
+        __syncthreads();
+
+        // ---------------- 3. the step's `nodes` (they hold m, i)
+        int n_act = 0;
+        bool ok = true;
+        if (fwd) {
+            // forward sparse: nodes = to_childs_and_us(top) (forward.rs:148) ; mapping: nodes = mapping.nodes(i)
+            ok = sp_expand(S, S.top_id, n_top, G.chi_off, G.chi_node, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
+        } else {
+            // backward sparse: M/I over to_parents_and_us(nodes) (backward.rs:243-259) ; non-adaptive: nodes themselves
+            ok = sp_expand(S, S.top_id, n_top, G.par_off, G.par_node, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
+        }
+        if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
+        const uint32_t n_mi = (uint32_t)n_act;
+        const uint32_t stamp0 = s * 8 + 1;
+        uint32_t n_d = 0;
+
+        if (fwd) {
+            // ---------------- 4f. fm, fi over nodes (forward.rs:337-388)
+            const XF fb0 = xadd(xmul(s_mb, lp.p_MM), xmul(s_ib, lp.p_IM));
+            const XF ib_cur = xmul(xadd(xmul(s_mb, lp.p_MI), xmul(s_ib, lp.p_II)), lp.p_random);
+            for (uint32_t a = tid; a < n_mi; a += B) {
+                uint32_t id = S.act_id[a], sl = S.act_slot[a];
+                XF acc = xf_zero();
+                for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
+                    double pm, pi, pd; int pe;
+                    prev_get(S, PA, G.par_node[e], &pm, &pi, &pd, &pe);
+                    acc = xadd(acc, xf(trans[G.par_eid[e]] * (lp.p_MM * pm + lp.p_IM * pi + lp.p_DM * pd), pe));
+                }
+                acc = xadd(acc, xmul(fb0, init[id]));
+                XF m = xmul(acc, G.emission[id] == x ? lp.p_match : lp.p_mismatch);
+                double pm, pi, pd; int pe;
+                prev_get(S, PA, id, &pm, &pi, &pd, &pe);
+                XF i = xf(lp.p_random * (lp.p_MI * pm + lp.p_II * pi + lp.p_DI * pd), pe);
+                int Em = xexp(m), Ei = xexp(i), Ec = Em > Ei ? Em : Ei;
+                if (Ec == XF_ZERO_E) { S.c_m[sl] = 0.0; S.c_i[sl] = 0.0; S.c_mie[sl] = 0; }
+                else { S.c_m[sl] = m.v == 0.0 ? 0.0 : m.v * pow2i(m.e - Ec); S.c_i[sl] = i.v == 0.0 ? 0.0 : i.v * pow2i(i.e - Ec); S.c_mie[sl] = Ec; }
+            }
+            __syncthreads();
+            // ---------------- 5f. fd: fd0 + 4 x fdt (forward.rs:423-466)
+            const uint32_t* src_id = S.act_id; int n_src = n_act;
+            for (int t = 0; t < N_DEL_ROUNDS; t++) {
+                uint32_t* l_id = S.la_id[t & 1]; uint16_t* l_slot = S.la_slot[t & 1];
+                int n_l = 0;
+                if (adaptive) {
+                    ok = sp_expand(S, src_id, n_src, G.chi_off, G.chi_node, false, true, l_id, l_slot, MAX_ACTIVE, &n_ent, &n_l);
+                    if (!ok) break;
+                } else {
+                    n_l = n_act;
+                    for (int a = tid; a < n_l; a += B) { l_id[a] = S.act_id[a]; l_slot[a] = S.act_slot[a]; }
+                    __syncthreads();
+                }
+                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint32_t* st = S.dstamp[t & 1];
+                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint32_t* stp = S.dstamp[(t & 1) ^ 1];
+                for (int a = tid; a < n_l; a += B) {
+                    uint32_t id = l_id[a], sl = l_slot[a];
+                    XF acc = xf_zero();
+                    for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
+                        int ps = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, G.par_node[e]);
+                        if (ps < 0) continue;
+                        double tr = trans[G.par_eid[e]];
+                        if (t == 0) { if ((uint32_t)ps < n_mi) acc = xadd(acc, xf(tr * (lp.p_MD * S.c_m[ps] + lp.p_ID * S.c_i[ps]), S.c_mie[ps])); }
+                        else if (stp[ps] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[ps], dep[ps]));
+                    }
+                    if (t == 0) acc = xadd(acc, xmul(ib_cur, lp.p_ID * init[id]));
+                    dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
+                    XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
+                    S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
+                }
+                // d insertion order: first time a slot receives a Del value
+                for (int a = tid; a < n_l; a += B) { uint32_t sl = l_slot[a]; S.scan[a] = S.d_seen[sl] ? 0u : 1u; }
+                __syncthreads();
+                uint32_t n_new = block_exscan(S.scan, n_l);
+                for (int a = tid; a < n_l; a += B) {
+                    uint32_t sl = l_slot[a];
+                    if (!S.d_seen[sl]) { uint32_t o = n_d + S.scan[a]; if (o < cap) S.dlist[o] = (uint16_t)sl; }
+                }
+                __syncthreads();
+                for (int a = tid; a < n_l; a += B) S.d_seen[l_slot[a]] = 1;
+                n_d += n_new;
+                __syncthreads();
+                src_id = l_id; n_src = n_l;
+            }
+            if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
+            // ---------------- 6f. fe over nodes (forward.rs:554-558), begin scalars
+            XF part = xf_zero();
+            for (uint32_t a = tid; a < n_mi; a += B) {
+                uint32_t sl = S.act_slot[a];
+                part = xadd(part, xadd(xf(S.c_m[sl] + S.c_i[sl], S.c_mie[sl]), xf(S.c_dv[sl], S.c_de[sl])));
+            }
+            XF esum = block_xsum(part);
+            last_scalar = xnorm(xmul(esum, lp.p_end));
+            if (tid == 0) { s_mb = xf_zero(); s_ib = xnorm(ib_cur); }
+        } else {
+            // ---------------- 4b. bd: bd0 + 4 x bdt over iterated to_parents_and_us (backward.rs:299-343)
+            const uint32_t* src_id = S.act_id; int n_src = n_act;
+            for (int t = 0; t < N_DEL_ROUNDS; t++) {
+                const uint32_t* l_id; const uint16_t* l_slot; int n_l;
+                if (t == 0 || !adaptive) { l_id = S.act_id; l_slot = S.act_slot; n_l = n_act; }  // A0 == to_parents_and_us(nodes)
+                else {
+                    int nn = 0;
+                    ok = sp_expand(S, src_id, n_src, G.par_off, G.par_node, true, true, S.la_id[t & 1], S.la_slot[t & 1], MAX_ACTIVE, &n_ent, &nn);
+                    if (!ok) break;
+                    l_id = S.la_id[t & 1]; l_slot = S.la_slot[t & 1]; n_l = nn;
+                }
+                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint32_t* st = S.dstamp[t & 1];
+                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint32_t* stp = S.dstamp[(t & 1) ^ 1];
+                for (int a = tid; a < n_l; a += B) {
+                    uint32_t id = l_id[a], sl = l_slot[a];
+                    XF acc = xf_zero();
+                    for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) {
+                        uint32_t ch = G.chi_node[e];
+                        double tr = trans[G.chi_eid[e]];
+                        if (t == 0) {
+                            double pm, pi, pd; int pe;
+                            prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
+                            acc = xadd(acc, xf(tr * lp.p_DM * (G.emission[ch] == x ? lp.p_match : lp.p_mismatch) * pm, pe));
+                        } else {
+                            int cs = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, ch);
+                            if (cs >= 0 && stp[cs] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[cs], dep[cs]));
+                        }
+                    }
+                    if (t == 0) {
+                        double pm, pi, pd; int pe;
+                        prev_get(S, PA, id, &pm, &pi, &pd, &pe);
+                        acc = xadd(acc, xf(lp.p_DI * lp.p_random * pi, pe));
+                    }
+                    dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
+                    XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
+                    S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
+                }
+                for (int a = tid; a < n_l; a += B) { uint32_t sl = l_slot[a]; S.scan[a] = S.d_seen[sl] ? 0u : 1u; }
+                __syncthreads();
+                uint32_t n_new = block_exscan(S.scan, n_l);
+                for (int a = tid; a < n_l; a += B) {
+                    uint32_t sl = l_slot[a];
+                    if (!S.d_seen[sl]) { uint32_t o = n_d + S.scan[a]; if (o < cap) S.dlist[o] = (uint16_t)sl; }
+                }
+                __syncthreads();
+                for (int a = tid; a < n_l; a += B) S.d_seen[l_slot[a]] = 1;
+                n_d += n_new;
+                __syncthreads();
+                src_id = l_id; n_src = n_l;
+            }
+            if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
+            // ---------------- 5b. bm, bi over nodes ; bmb, bib sums (backward.rs:423-555)
+            XF pmb = xf_zero(), pib = xf_zero();
+            for (uint32_t a = tid; a < n_mi; a += B) {
+                uint32_t id = S.act_id[a], sl = S.act_slot[a];
+                XF am = xf_zero(), ai = xf_zero();
+                for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) {
+                    uint32_t ch = G.chi_node[e];
+                    double tr = trans[G.chi_eid[e]];
+                    double pm, pi, pd; int pe;
+                    prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
+                    XF tm = xf(tr * (G.emission[ch] == x ? lp.p_match : lp.p_mismatch) * pm, pe);
+                    int cs = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, ch);
+                    XF td = cs >= 0 ? xf(tr * S.c_dv[cs], S.c_de[cs]) : xf_zero();
+                    am = xadd(am, xadd(xmul(tm, lp.p_MM), xmul(td, lp.p_MD)));
+                    ai = xadd(ai, xadd(xmul(tm, lp.p_IM), xmul(td, lp.p_ID)));
+                }
+                double pm, pi, pd; int pe;
+                prev_get(S, PA, id, &pm, &pi, &pd, &pe);
+                am = xadd(am, xf(lp.p_MI * lp.p_random * pi, pe));
+                ai = xadd(ai, xf(lp.p_II * lp.p_random * pi, pe));
+                int Em = xexp(am), Ei = xexp(ai), Ec = Em > Ei ? Em : Ei;
+                if (Ec == XF_ZERO_E) { S.c_m[sl] = 0.0; S.c_i[sl] = 0.0; S.c_mie[sl] = 0; }
+                else { S.c_m[sl] = am.v == 0.0 ? 0.0 : am.v * pow2i(am.e - Ec); S.c_i[sl] = ai.v == 0.0 ? 0.0 : ai.v * pow2i(ai.e - Ec); S.c_mie[sl] = Ec; }
+                // begin sums: init_l * (p_XM e_l(x) m''[l] + p_XD d[l])
+                XF um = xf((G.emission[id] == x ? lp.p_match : lp.p_mismatch) * pm, pe);
+                XF ud = xf(S.c_dv[sl], S.c_de[sl]);
+                double in = init[id];
+                pmb = xadd(pmb, xmul(xadd(xmul(um, lp.p_MM), xmul(ud, lp.p_MD)), in));
+                pib = xadd(pib, xmul(xadd(xmul(um, lp.p_IM), xmul(ud, lp.p_ID)), in));
+            }
+            XF smb = block_xsum(pmb);
+            XF sib = block_xsum(pib);
+            XF ibn = s_ib;
+            __syncthreads();
+            XF nmb = xnorm(xadd(smb, xmul(ibn, lp.p_MI * lp.p_random)));
+            XF nib = xnorm(xadd(sib, xmul(ibn, lp.p_II * lp.p_random)));
+            last_scalar = nmb;
+            if (tid == 0) { s_mb = nmb; s_ib = nib; }
+        }
+        __syncthreads();
+        if (n_d > MAX_ACTIVE) { if (tid == 0) s_fail = SJ_CAPACITY; __syncthreads(); break; }
+
+        // ---------------- 7. pack the row into the "previous" arrays, swap hash tables
+        for (uint32_t e = tid; e < n_ent; e += B) {
+            Cell cl = cell_pack(xf(S.c_m[e], S.c_mie[e]), xf(S.c_i[e], S.c_mie[e]), xf(S.c_dv[e], S.c_de[e]));
+            S.p_id[e] = S.c_id[e]; S.p_m[e] = cl.m; S.p_i[e] = cl.i; S.p_d[e] = cl.d; S.p_ex[e] = cl.e;
+        }
+        { uint32_t* t1 = S.ph_key; S.ph_key = S.ch_key; S.ch_key = t1; uint32_t* t2 = S.ph_val; S.ph_val = S.ch_val; S.ch_val = t2; }
+        n_prev = n_ent;
+        if (tid == 0) s_cells += n_mi;
+        __syncthreads();
+
+        // ---------------- 8. store
+        if (jb.store) {
+            uint64_t bytes = sparse_row_bytes(n_ent, n_d);
+            if (tid == 0) {
+                if (bytes > s_page_left) {
+                    uint64_t pg = bytes > SPARSE_PAGE_BYTES ? ((bytes + 255) & ~(uint64_t)255) : SPARSE_PAGE_BYTES;
+                    unsigned long long o = atomicAdd(io.arena_cursor, (unsigned long long)pg);
+                    if (o + pg > io.arena_bytes) s_fail = SJ_OOM;
+                    s_page_off = o; s_page_left = (uint32_t)pg;
+                }
+            }
+            __syncthreads();
+            if (s_fail) break;
+            const uint64_t off = s_page_off;
+            char* pay = io.arena + off;
+            double* om = (double*)pay; double* oi = om + n_ent; double* od = oi + n_ent;
+            uint32_t* oid = (uint32_t*)(od + n_ent); int* oex = (int*)(oid + n_ent); uint16_t* odl = (uint16_t*)(oex + n_ent);
+            for (uint32_t e = tid; e < n_ent; e += B) { om[e] = S.p_m[e]; oi[e] = S.p_i[e]; od[e] = S.p_d[e]; oid[e] = S.p_id[e]; oex[e] = S.p_ex[e]; }
+            for (uint32_t e = tid; e < n_d; e += B) odl[e] = S.dlist[e];
+            if (tid == 0) {
+                RowDesc r;
+                r.kind = ROW_SPARSE; r.n_ent = n_ent; r.n_mi = n_mi; r.n_d = n_d; r.off = off;
+                if (fwd) { r.mb = xf_zero(); r.ib = s_ib; r.e = last_scalar; }
+                else { r.mb = s_mb; r.ib = s_ib; r.e = xf_zero(); }
+                io.desc[jb.desc0 + row] = r;
+                s_page_off = off + bytes; s_page_left -= (uint32_t)bytes;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        io.status[blockIdx.x] = s_fail;
+        io.final_scalar[blockIdx.x] = last_scalar;
+        io.cells[blockIdx.x] = s_cells;
+    }
+}
+
+static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) {
+    auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    size_t s = 0;
+    s += 9 * r16(8 * (size_t)cap);
+    s += 12 * r16(4 * (size_t)cap);
+    s += r16(4 * ((size_t)cap + 1));
+    s += 4 * r16(4 * (size_t)hcap);
+    s += r16(4 * MAX_ACTIVE);
+    s += 3 * r16(4 * (size_t)cap);
+    s += 4 * r16(2 * (size_t)cap);
+    return s;
+}
+
+int sparse_configure(dbgphmm_model* m) {
+    (void)m;
+    CUDA_TRY(cudaFuncSetAttribute(k_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return DBGPHMM_OK;
+}
+
+int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap) {
+    if (n_jobs == 0) return DBGPHMM_OK;
+    uint32_t hcap = 1;
+    while (hcap < 2 * cap) hcap <<= 1;
+    size_t smem = sparse_smem_bytes(cap, hcap);
+    if (smem > 200 * 1024) { dbg_set_error("sparse_run: capacity too large for shared memory"); return DBGPHMM_ERR_INVALID; }
+    SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
+             m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
+    int threads = cap <= 64 ? 32 : (cap <= 256 ? 128 : 256);
+    k_sparse<<<n_jobs, threads, smem, m->stream>>>(G, m->lin, d_jobs, io, cap, hcap);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}

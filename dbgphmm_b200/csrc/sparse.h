@@ -1,0 +1,59 @@
+// sparse.h — sparse DP rows (<= MAX_ACTIVE active nodes): one CTA per (read, candidate X), rows in shared memory.
+#pragma once
+#include "model.h"
+
+enum {  // node-list source of a sparse step
+    SP_TOPN = 0,     // top_nodes(n_active) of the previous row, adaptive Del sets   (forward.rs:112-150, backward.rs:166-176)
+    SP_RATIO = 1,    // top_nodes_by_score_ratio(max_ratio), adaptive (forward only)  (forward.rs:112-150)
+    SP_MAPPING = 2,  // mapping.nodes(i), non-adaptive                                (forward.rs:71, backward.rs:84)
+    SP_BYFWD = 3     // filled_nodes() of forward row i-1, non-adaptive (backward)    (backward.rs:128-133)
+};
+enum { SPREV_F_INIT = 0, SPREV_B_INIT = 1, SPREV_DENSE = 2 };
+enum { SJ_OK = 0, SJ_NEED_BIG = 1, SJ_CAPACITY = 2, SJ_OOM = 3 };
+
+struct SJob {
+    uint32_t x;           // parameter set
+    uint32_t len;         // read length
+    uint64_t base_off;    // first base of the read in the device base array
+    int dir;              // 0 forward, 1 backward
+    int mode;             // SP_*
+    int32_t row_begin;    // row of step 0 ; row(s) = row_begin + s (forward) / row_begin - s (backward)
+    uint32_t n_rows;      // rows to compute
+    int prev0_kind;       // SPREV_* : what the row before step 0 is
+    uint64_t prev0_slab;  // dense slab of that row (SPREV_DENSE)
+    uint32_t top0;        // request slot of the dense top list for step 0 (SP_TOPN / SP_RATIO)
+    uint64_t desc0;       // RowDesc index of row 0 of this job (own direction)
+    uint64_t fdesc0;      // SP_BYFWD: RowDesc index of row 0 of the forward tables
+    uint64_t map_row0;    // SP_MAPPING: first row of this read in the mapping CSR
+    int store;            // 1: write rows to the arena, 0: score only
+    int32_t active_idx;   // skip unless active flag (or -1)
+    uint32_t out_idx;     // job index in the caller's batch
+};
+
+struct SparseArena {
+    char* base = nullptr;
+    uint64_t bytes = 0;
+    unsigned long long* cursor = nullptr;  // device bump pointer
+};
+#define SPARSE_PAGE_BYTES (256 * 1024)
+
+struct SparseIO {
+    const uint8_t* bases;
+    RowDesc* desc;             // own direction
+    const RowDesc* fdesc;      // forward tables (SP_BYFWD)
+    const char* farena;        // arena holding the forward sparse rows (SP_BYFWD)
+    const uint32_t* top_ids;   // dense_select output [slot][MAX_ACTIVE]
+    const uint32_t* top_cnt;
+    const uint64_t* map_row_off;  // mapping CSR (device): row -> entries
+    const uint32_t* map_nodes;    // relabelled node ids
+    const char* pool; uint64_t slab_bytes; uint32_t Np;  // dense pool (SPREV_DENSE)
+    char* arena; uint64_t arena_bytes; unsigned long long* arena_cursor;
+    int* status;               // per job SJ_*
+    XF* final_scalar;          // per job: forward -> e of the last row ; backward -> mb of row 0
+    unsigned long long* cells; // per job: sum over rows of |nodes| (GCUPS numerator)
+    const int* active;
+};
+
+int sparse_configure(dbgphmm_model* m);
+// cap: entry capacity per job in shared memory (256 normal, 832 big); threads per CTA chosen from cap
+int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap);

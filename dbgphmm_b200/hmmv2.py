@@ -1,0 +1,474 @@
+"""Host-side mirror of the reference's `impl PHMMModel` / `impl PHMMOutput` surface (src/hmmv2) over the C ABI.
+
+Same method names, argument meaning and error behaviour as the reference (forward.rs, backward.rs, freq.rs,
+hint.rs, table.rs); where the reference panics this raises DbgphmmError.  All compute goes through
+lib/libdbgphmm_b200.so (hand-written sm_100a CUDA); there is no CPU path — without the library or without a
+GPU every compute call raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdbgphmm_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_ZERO_PROB, ERR_OOM = range(6)
+MAX_ACTIVE_NODES = 400  # hmmv2/table.rs:22
+
+
+class DbgphmmError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"dbgphmm_b200 status {status}: {msg}")
+        self.status = status
+
+
+class Params(C.Structure):
+    """PHMMParams (hmmv2/params.rs:16-66); p_* are natural logs.  Layout == struct dbgphmm_params."""
+    _fields_ = [(n, C.c_double) for n in (
+        "p_mismatch", "p_match", "p_random", "p_gap_open", "p_gap_ext", "p_end",
+        "p_MM", "p_IM", "p_DM", "p_MI", "p_II", "p_DI", "p_MD", "p_ID", "p_DD")] + [
+        ("n_active_nodes", C.c_uint32), ("n_warmup", C.c_uint32),
+        ("warmup_threshold", C.c_uint32), ("n_max_gaps", C.c_uint32),
+        ("active_node_max_ratio", C.c_double)]
+
+    def copy(self):
+        q = Params()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(Params))
+        return q
+
+
+# every symbol include/dbgphmm_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "dbgphmm_last_error", "dbgphmm_device_count", "dbgphmm_params_new", "dbgphmm_params_uniform",
+    "dbgphmm_model_create", "dbgphmm_model_destroy", "dbgphmm_model_set_params", "dbgphmm_model_set_probs",
+    "dbgphmm_model_set_copy_nums_batch", "dbgphmm_model_get_probs", "dbgphmm_model_n_nodes", "dbgphmm_model_n_batch",
+    "dbgphmm_reads_create", "dbgphmm_reads_destroy", "dbgphmm_mappings_create", "dbgphmm_mappings_destroy",
+    "dbgphmm_mappings_sizes", "dbgphmm_mappings_export", "dbgphmm_mappings_to_node_freqs",
+    "dbgphmm_forward", "dbgphmm_backward", "dbgphmm_tables_destroy", "dbgphmm_tables_len", "dbgphmm_tables_full_prob",
+    "dbgphmm_tables_row_info", "dbgphmm_tables_row_export", "dbgphmm_tables_row_top_nodes",
+    "dbgphmm_output_node_freqs", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
+    "dbgphmm_run_node_freqs_dev", "dbgphmm_generate_mappings", "dbgphmm_launch_count", "dbgphmm_last_timing",
+    "dbgphmm_reads_to_device",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built (python -m dbgphmm_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DbgphmmError(ERR_CUDA, f"{LIB_PATH} is missing: build it with `python -m dbgphmm_b200.build` "
+                                     "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i64, dbl, ci = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_double, C.c_int
+    PP = C.POINTER(Params)
+    L.dbgphmm_last_error.restype = C.c_char_p
+    L.dbgphmm_device_count.restype = ci
+    L.dbgphmm_params_new.argtypes = [dbl, dbl, dbl, dbl, u32, u32, PP]
+    L.dbgphmm_params_uniform.argtypes = [dbl, PP]
+    L.dbgphmm_model_create.argtypes = [u32, u32, vp, vp, vp, vp, vp, PP, ci, u64, C.POINTER(vp)]
+    L.dbgphmm_model_destroy.argtypes = [vp]
+    L.dbgphmm_model_set_params.argtypes = [vp, PP]
+    L.dbgphmm_model_set_probs.argtypes = [vp, vp, vp]
+    L.dbgphmm_model_set_copy_nums_batch.argtypes = [vp, u32, vp, ci]
+    L.dbgphmm_model_get_probs.argtypes = [vp, u32, vp, vp]
+    L.dbgphmm_model_n_nodes.argtypes = [vp]; L.dbgphmm_model_n_nodes.restype = u32
+    L.dbgphmm_model_n_batch.argtypes = [vp]; L.dbgphmm_model_n_batch.restype = u32
+    L.dbgphmm_reads_create.argtypes = [u64, vp, vp, C.POINTER(vp)]
+    L.dbgphmm_reads_destroy.argtypes = [vp]
+    L.dbgphmm_reads_to_device.argtypes = [vp, vp]
+    L.dbgphmm_mappings_create.argtypes = [u64, vp, vp, vp, vp, C.POINTER(vp)]
+    L.dbgphmm_mappings_destroy.argtypes = [vp]
+    L.dbgphmm_mappings_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.dbgphmm_mappings_export.argtypes = [vp, vp, vp, vp, vp]
+    L.dbgphmm_mappings_to_node_freqs.argtypes = [vp, u32, vp]
+    L.dbgphmm_forward.argtypes = [vp, vp, u64, ci, vp, u64, C.POINTER(vp)]
+    L.dbgphmm_backward.argtypes = [vp, vp, u64, ci, vp, u64, vp, C.POINTER(vp)]
+    L.dbgphmm_tables_destroy.argtypes = [vp]
+    L.dbgphmm_tables_len.argtypes = [vp]; L.dbgphmm_tables_len.restype = u64
+    L.dbgphmm_tables_full_prob.argtypes = [vp, C.POINTER(dbl)]
+    L.dbgphmm_tables_row_info.argtypes = [vp, i64, vp, vp]
+    L.dbgphmm_tables_row_export.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.dbgphmm_tables_row_top_nodes.argtypes = [vp, i64, ci, u32, dbl, vp, C.POINTER(u32)]
+    L.dbgphmm_output_node_freqs.argtypes = [vp, vp, vp, vp]
+    L.dbgphmm_output_mapping.argtypes = [vp, vp, vp, ci, u32, dbl, C.POINTER(vp)]
+    L.dbgphmm_to_full_prob_reads.argtypes = [vp, vp, vp, ci, vp, vp]
+    L.dbgphmm_run_node_freqs.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+    L.dbgphmm_run_node_freqs_dev.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+    L.dbgphmm_generate_mappings.argtypes = [vp, vp, vp, ci, C.POINTER(vp)]
+    L.dbgphmm_launch_count.argtypes = [ci]; L.dbgphmm_launch_count.restype = u64
+    L.dbgphmm_last_timing.argtypes = [vp, C.POINTER(u64)]
+    for s in SYMBOLS:
+        getattr(L, s)  # fail loudly if the library does not export a declared symbol
+    _lib = L
+    return L
+
+
+def _check(st):
+    if st != OK:
+        raise DbgphmmError(st, lib().dbgphmm_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return int(lib().dbgphmm_device_count())
+
+
+def launch_count(reset=False):
+    return int(lib().dbgphmm_launch_count(1 if reset else 0))
+
+
+def last_timing():
+    """(dense_ms, sparse_ms, product_ms, total_ms, dense_cells) of the last bulk call, from CUDA events."""
+    ms = (C.c_double * 4)()
+    cells = C.c_uint64(0)
+    lib().dbgphmm_last_timing(ms, C.byref(cells))
+    return ms[0], ms[1], ms[2], ms[3], int(cells.value)
+
+
+def params_uniform(p):
+    """PHMMParams::uniform (params.rs:116-124)."""
+    q = Params()
+    lib().dbgphmm_params_uniform(float(p), C.byref(q))
+    return q
+
+
+def params_new(p_mismatch, p_gap_open, p_gap_ext, p_end, n_active_nodes, n_warmup):
+    """PHMMParams::new (params.rs:73-112)."""
+    q = Params()
+    lib().dbgphmm_params_new(p_mismatch, p_gap_open, p_gap_ext, p_end, n_active_nodes, n_warmup, C.byref(q))
+    return q
+
+
+def _bases(x):
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), np.uint8).copy()
+    return np.ascontiguousarray(x, np.uint8)
+
+
+class Reads:
+    """ReadCollection (common/collection.rs:131): CSR of uppercase ACGT reads."""
+
+    def __init__(self, seqs):
+        seqs = [_bases(s) for s in seqs]
+        self.offsets = np.zeros(len(seqs) + 1, np.uint64)
+        self.offsets[1:] = np.cumsum([len(s) for s in seqs])
+        self.bases = np.ascontiguousarray(np.concatenate(seqs)) if seqs else np.zeros(0, np.uint8)
+        h = C.c_void_p()
+        _check(lib().dbgphmm_reads_create(len(seqs), _p(self.offsets), _p(self.bases), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dbgphmm_reads_destroy(self._h)
+            self._h = None
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, r):
+        return self.bases[int(self.offsets[r]):int(self.offsets[r + 1])]
+
+    def total_bases(self):
+        return int(self.offsets[-1])
+
+
+class Mapping:
+    """hint.rs:27-30 for one read: per-base node lists and their ln probabilities."""
+
+    def __init__(self, nodes, probs):
+        self.nodes, self.probs = nodes, probs
+
+    def __len__(self):
+        return len(self.nodes)
+
+
+class Mappings:
+    """hint.rs:150-152 : CSR over reads -> bases -> (node, ln prob); owns a C handle."""
+
+    def __init__(self, read_off, row_off, nodes, probs, handle=None):
+        self.read_off = np.ascontiguousarray(read_off, np.uint64)
+        self.row_off = np.ascontiguousarray(row_off, np.uint64)
+        self.nodes = np.ascontiguousarray(nodes, np.uint32)
+        self.probs = np.ascontiguousarray(probs, np.float64)
+        if handle is None:
+            handle = C.c_void_p()
+            _check(lib().dbgphmm_mappings_create(len(self.read_off) - 1, _p(self.read_off), _p(self.row_off), _p(self.nodes),
+                                                 _p(self.probs), C.byref(handle)))
+        self._h = handle
+
+    @staticmethod
+    def _from_handle(h):
+        nr, nrow, nent = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().dbgphmm_mappings_sizes(h, C.byref(nr), C.byref(nrow), C.byref(nent)))
+        ro = np.zeros(nr.value + 1, np.uint64); rw = np.zeros(nrow.value + 1, np.uint64)
+        nd = np.zeros(nent.value, np.uint32); pr = np.zeros(nent.value, np.float64)
+        _check(lib().dbgphmm_mappings_export(h, _p(ro), _p(rw), _p(nd), _p(pr)))
+        return Mappings(ro, rw, nd, pr, handle=h)
+
+    @staticmethod
+    def from_list(maps):
+        read_off = [0]; row_off = [0]; nodes = []; probs = []
+        for m in maps:
+            for ns, ps in zip(m.nodes, m.probs):
+                nodes.append(np.asarray(ns, np.uint32)); probs.append(np.asarray(ps, np.float64))
+                row_off.append(row_off[-1] + len(ns))
+            read_off.append(read_off[-1] + len(m.nodes))
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+        return Mappings(np.array(read_off, np.uint64), np.array(row_off, np.uint64), cat(nodes, np.uint32), cat(probs, np.float64))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dbgphmm_mappings_destroy(self._h)
+            self._h = None
+
+    def n_reads(self):
+        return len(self.read_off) - 1
+
+    def __getitem__(self, r):
+        a, b = int(self.read_off[r]), int(self.read_off[r + 1])
+        ns = [self.nodes[int(self.row_off[i]):int(self.row_off[i + 1])] for i in range(a, b)]
+        ps = [self.probs[int(self.row_off[i]):int(self.row_off[i + 1])] for i in range(a, b)]
+        return Mapping(ns, ps)
+
+    def to_node_freqs(self, n_nodes):
+        """Mappings::to_node_freqs (hint.rs:161-171) == MultiDbg::mappings_to_freqs (multi_dbg/draft.rs:201-212)."""
+        f = np.zeros(n_nodes)
+        _check(lib().dbgphmm_mappings_to_node_freqs(self._h, n_nodes, _p(f)))
+        return f
+
+
+class Row:
+    """One PHMMTable (table.rs:42-73), natural logs."""
+    __slots__ = ("is_dense", "ids", "m", "i", "ids_d", "d", "mb", "ib", "e")
+
+
+class PHMMTables:
+    """PHMMTables (table.rs:365-435) of one read, resident on the GPU."""
+
+    def __init__(self, model, handle):
+        self._model, self._h = model, handle
+        self.n_nodes = model.n_nodes
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dbgphmm_tables_destroy(self._h)
+            self._h = None
+
+    def __len__(self):
+        return int(lib().dbgphmm_tables_len(self._h))
+
+    def n_emissions(self):
+        return len(self)
+
+    def full_prob(self):
+        v = C.c_double()
+        _check(lib().dbgphmm_tables_full_prob(self._h, C.byref(v)))
+        return v.value
+
+    def row(self, i):
+        """tables[i]; i = -1 is init_table."""
+        info = np.zeros(3, np.uint64); sc = np.zeros(3, np.float64)
+        _check(lib().dbgphmm_tables_row_info(self._h, i, _p(info), _p(sc)))
+        r = Row()
+        r.is_dense = bool(info[0]); r.mb, r.ib, r.e = (float(v) for v in sc)
+        if r.is_dense:
+            N = self.n_nodes
+            r.ids = r.ids_d = None
+            r.m = np.empty(N); r.i = np.empty(N); r.d = np.empty(N)
+            _check(lib().dbgphmm_tables_row_export(self._h, i, None, _p(r.m), _p(r.i), None, _p(r.d)))
+        else:
+            nm, nd = int(info[1]), int(info[2])
+            r.ids = np.empty(nm, np.uint32); r.m = np.empty(nm); r.i = np.empty(nm)
+            r.ids_d = np.empty(nd, np.uint32); r.d = np.empty(nd)
+            _check(lib().dbgphmm_tables_row_export(self._h, i, _p(r.ids), _p(r.m), _p(r.i), _p(r.ids_d), _p(r.d)))
+        return r
+
+    def top_nodes(self, i, k):
+        out = np.empty(MAX_ACTIVE_NODES, np.uint32); n = C.c_uint32()
+        _check(lib().dbgphmm_tables_row_top_nodes(self._h, i, 0, k, 0.0, _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def top_nodes_by_score_ratio(self, i, ratio):
+        out = np.empty(MAX_ACTIVE_NODES, np.uint32); n = C.c_uint32()
+        _check(lib().dbgphmm_tables_row_top_nodes(self._h, i, 1, 0, ratio, _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+
+class PHMMOutput:
+    """PHMMOutput (table.rs:450-517)."""
+
+    def __init__(self, model, forward, backward):
+        self._model, self.forward, self.backward = model, forward, backward
+
+    def n_emissions(self):
+        return len(self.forward)
+
+    def to_full_prob_forward(self):
+        return self.forward.full_prob()
+
+    def to_full_prob_backward(self):
+        return self.backward.full_prob()
+
+    def to_node_freqs(self):
+        f = np.empty(self._model.n_nodes)
+        _check(lib().dbgphmm_output_node_freqs(self._model._h, self.forward._h, self.backward._h, _p(f)))
+        return f
+
+    def _mapping(self, by_ratio, n_active, ratio):
+        h = C.c_void_p()
+        _check(lib().dbgphmm_output_mapping(self._model._h, self.forward._h, self.backward._h, by_ratio, n_active, ratio, C.byref(h)))
+        return Mappings._from_handle(h)[0]
+
+    def to_mapping(self, n_active_nodes):
+        return self._mapping(0, n_active_nodes, 0.0)
+
+    def to_mapping_by_score_ratio(self, max_ratio):
+        return self._mapping(1, 0, max_ratio)
+
+
+FWD_DENSE, FWD_SPARSE, FWD_SPARSE_RATIO, FWD_MAPPING = range(4)
+BWD_DENSE, BWD_SPARSE, BWD_MAPPING, BWD_BY_FORWARD = range(4)
+RUN_MODES = {"dense": 0, "sparse": 1, "sparse_adaptive": 2, "with_mapping": 3}
+
+
+class PHMMModel:
+    """PHMMModel<PNode,PEdge> (hmmv2/common.rs:61-67) resident on one B200.
+
+    edge_src/edge_dst in EdgeIndex order, emission bytes ('A','C','G','T','n'), log_init/log_trans as natural logs."""
+
+    def __init__(self, edge_src, edge_dst, emission, log_init, log_trans, param, device=0, mem_budget_bytes=0):
+        self.src = np.ascontiguousarray(edge_src, np.uint32)
+        self.dst = np.ascontiguousarray(edge_dst, np.uint32)
+        self.emission = _bases(emission)
+        li = np.ascontiguousarray(log_init, np.float64); lt = np.ascontiguousarray(log_trans, np.float64)
+        self.param = param.copy()
+        self.n_nodes = len(self.emission)
+        self.device = device
+        h = C.c_void_p()
+        _check(lib().dbgphmm_model_create(self.n_nodes, len(self.src), _p(self.src), _p(self.dst), _p(self.emission), _p(li), _p(lt),
+                                          C.byref(self.param), device, mem_budget_bytes, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dbgphmm_model_destroy(self._h)
+            self._h = None
+
+    def n_edges(self):
+        return len(self.src)
+
+    def set_params(self, param):
+        self.param = param.copy()
+        _check(lib().dbgphmm_model_set_params(self._h, C.byref(self.param)))
+
+    def set_probs(self, log_init, log_trans):
+        li = np.ascontiguousarray(log_init, np.float64); lt = np.ascontiguousarray(log_trans, np.float64)
+        _check(lib().dbgphmm_model_set_probs(self._h, _p(li), _p(lt)))
+
+    def set_copy_nums_batch(self, copy_nums, mode="normal"):
+        """Candidate copy-number assignments X [B][N] -> B parameter sets on the device (seq_graph.rs:160-273)."""
+        cn = np.ascontiguousarray(copy_nums, np.uint32)
+        if cn.ndim == 1:
+            cn = cn[None, :]
+        assert cn.shape[1] == self.n_nodes
+        _check(lib().dbgphmm_model_set_copy_nums_batch(self._h, cn.shape[0], _p(cn), {"normal": 0, "non_zero": 1, "uniform": 2}[mode]))
+
+    def get_probs(self, x=0):
+        li = np.empty(self.n_nodes); lt = np.empty(len(self.src))
+        with np.errstate(divide="ignore"):
+            _check(lib().dbgphmm_model_get_probs(self._h, x, _p(li), _p(lt)))
+        return li, lt
+
+    def n_batch(self):
+        return int(lib().dbgphmm_model_n_batch(self._h))
+
+    # ---- forward.rs
+    def _fwd(self, x, kind, mappings=None, read_index=0):
+        x = _bases(x)
+        h = C.c_void_p()
+        _check(lib().dbgphmm_forward(self._h, _p(x), len(x), kind, mappings._h if mappings is not None else None, read_index, C.byref(h)))
+        return PHMMTables(self, h)
+
+    def forward(self, x):
+        return self._fwd(x, FWD_DENSE)
+
+    def forward_sparse(self, x, use_max_ratio):
+        return self._fwd(x, FWD_SPARSE_RATIO if use_max_ratio else FWD_SPARSE)
+
+    def forward_with_mapping(self, x, mappings, read_index=0):
+        return self._fwd(x, FWD_MAPPING, mappings, read_index)
+
+    # ---- backward.rs
+    def _bwd(self, x, kind, mappings=None, read_index=0, fwd=None):
+        x = _bases(x)
+        h = C.c_void_p()
+        _check(lib().dbgphmm_backward(self._h, _p(x), len(x), kind, mappings._h if mappings is not None else None, read_index,
+                                      fwd._h if fwd is not None else None, C.byref(h)))
+        return PHMMTables(self, h)
+
+    def backward(self, x):
+        return self._bwd(x, BWD_DENSE)
+
+    def backward_sparse(self, x):
+        return self._bwd(x, BWD_SPARSE)
+
+    def backward_with_mapping(self, x, mappings, read_index=0):
+        return self._bwd(x, BWD_MAPPING, mappings, read_index)
+
+    def backward_by_forward(self, x, forward):
+        return self._bwd(x, BWD_BY_FORWARD, fwd=forward)
+
+    # ---- freq.rs:42-76
+    def run(self, x):
+        return PHMMOutput(self, self.forward(x), self.backward(x))
+
+    def run_sparse(self, x):
+        return PHMMOutput(self, self.forward_sparse(x, False), self.backward_sparse(x))
+
+    def run_sparse_adaptive(self, x, use_max_ratio):
+        f = self.forward_sparse(x, use_max_ratio)
+        return PHMMOutput(self, f, self.backward_by_forward(x, f))
+
+    def run_with_mapping(self, x, mappings, read_index=0):
+        return PHMMOutput(self, self.forward_with_mapping(x, mappings, read_index), self.backward_with_mapping(x, mappings, read_index))
+
+    # ---- bulk calls (freq.rs:87-192, hint.rs:193-220)
+    def to_full_prob_reads(self, reads, mappings=None, use_max_ratio=True):
+        """-> (ln P(R|X) [n_batch], per-read ln P [n_batch][n_reads]) — freq.rs:175-192 for every candidate X."""
+        B = self.n_batch()
+        tot = np.empty(B); per = np.empty((B, len(reads)))
+        _check(lib().dbgphmm_to_full_prob_reads(self._h, reads._h, mappings._h if mappings is not None else None, int(use_max_ratio),
+                                                _p(tot), _p(per)))
+        return tot, per
+
+    def run_node_freqs(self, reads, mode, use_max_ratio=True, mappings=None, want_freqs=True):
+        """-> (node_freqs[N] summed over reads, ln P forward [R], ln P backward [R], (cells_fwd, cells_bwd))."""
+        fr = np.zeros(self.n_nodes) if want_freqs else None
+        lf = np.empty(len(reads)); lb = np.empty(len(reads)); cells = np.zeros(2, np.uint64)
+        _check(lib().dbgphmm_run_node_freqs(self._h, reads._h, RUN_MODES[mode], int(use_max_ratio),
+                                            mappings._h if mappings is not None else None, _p(fr), _p(lf), _p(lb), _p(cells)))
+        return fr, lf, lb, (int(cells[0]), int(cells[1]))
+
+    def run_node_freqs_dev(self, reads, mode, node_freqs_ptr, use_max_ratio=True, mappings=None, logp_fwd_ptr=None, logp_bwd_ptr=None):
+        """Device-pointer variant: node_freqs_ptr (f64[N] on this model's device) is accumulated into."""
+        cells = np.zeros(2, np.uint64)
+        _check(lib().dbgphmm_run_node_freqs_dev(self._h, reads._h, RUN_MODES[mode], int(use_max_ratio),
+                                                mappings._h if mappings is not None else None, C.c_void_p(node_freqs_ptr),
+                                                C.c_void_p(logp_fwd_ptr) if logp_fwd_ptr else None,
+                                                C.c_void_p(logp_bwd_ptr) if logp_bwd_ptr else None, _p(cells)))
+        return int(cells[0]), int(cells[1])
+
+    def generate_mappings(self, reads, mappings=None, use_max_ratio=True):
+        h = C.c_void_p()
+        _check(lib().dbgphmm_generate_mappings(self._h, reads._h, mappings._h if mappings is not None else None, int(use_max_ratio), C.byref(h)))
+        return Mappings._from_handle(h)
+
+    def reads_to_device(self, reads):
+        _check(lib().dbgphmm_reads_to_device(self._h, reads._h))

@@ -1,0 +1,188 @@
+/* dbgphmm_b200.h — C ABI of the B200-native hmmv2 PHMM path.
+ *
+ * Drop-in boundary for ryought/dbgphmm `src/hmmv2`: the reference has no FFI layer, the seam is the
+ * inherent-method set `impl PHMMModel<N,E>` + `impl PHMMOutput`.  Each entry point below
+ * names the reference method it replaces (paths relative to the reference's src/).  A Rust shim that
+ * re-exposes these under the original method names lives in rust/ (source only).
+ *
+ * Conventions
+ *   - every call returns an int status (0 = DBGPHMM_OK); the reference panics instead (no Result).
+ *     dbgphmm_last_error() returns a thread-local message for the last non-zero status.
+ *   - probabilities cross the ABI as natural-log f64, exactly `Prob.0` (prob.rs:13,74-76);
+ *     zero probability is -INFINITY.
+ *   - node ids are the caller's petgraph NodeIndex values (u32); edges are given in EdgeIndex order,
+ *     which fixes the parent/child iteration order (graph/iterators.rs:104-155).
+ *   - host pointers in, host pointers out, unless the name ends in _dev.
+ *   - handles are immutable after creation except where stated; a handle may be used from one host
+ *     thread at a time.  All GPU work of a call is finished when it returns.
+ *   - there is NO CPU fallback: every call fails with DBGPHMM_ERR_CUDA if no sm_100-class device exists.
+ */
+#ifndef DBGPHMM_B200_H
+#define DBGPHMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBGPHMM_OK 0
+#define DBGPHMM_ERR_INVALID 1   /* bad argument (the reference would panic on an assert / index) */
+#define DBGPHMM_ERR_CUDA 2      /* CUDA runtime failure or no device */
+#define DBGPHMM_ERR_CAPACITY 3  /* a sparse row needed more than MAX_ACTIVE_NODES entries (table.rs:22; the
+                                   reference's ArrayVec-backed SparseVec panics with "insufficient capacity") */
+#define DBGPHMM_ERR_ZERO_PROB 4 /* P(read) == 0 where the reference would produce NaN and panic in Ord
+                                   (table.rs:500-505 with prob.rs:296-300) */
+#define DBGPHMM_ERR_OOM 5       /* device memory budget too small for one read */
+
+#define DBGPHMM_MAX_ACTIVE_NODES 400 /* hmmv2/table.rs:22 */
+
+/* PHMMParams (hmmv2/params.rs:16-66).  All p_* are natural logs. */
+typedef struct dbgphmm_params {
+    double p_mismatch, p_match, p_random, p_gap_open, p_gap_ext, p_end;
+    double p_MM, p_IM, p_DM, p_MI, p_II, p_DI, p_MD, p_ID, p_DD;
+    uint32_t n_active_nodes;   /* params.rs:28-38 */
+    uint32_t n_warmup;         /* params.rs:43-50 ; MultiDbg::to_phmm overrides it with k (multi_dbg.rs:1395) */
+    uint32_t warmup_threshold; /* params.rs:51-58 */
+    uint32_t n_max_gaps;       /* params.rs:59-62 ; must be 4 (table.rs:17 MAX_DEL) */
+    double active_node_max_ratio; /* params.rs:39-42 */
+} dbgphmm_params;
+
+typedef struct dbgphmm_model dbgphmm_model;       /* PHMMModel<PNode,PEdge>   hmmv2/common.rs:61-67 */
+typedef struct dbgphmm_reads dbgphmm_reads;       /* ReadCollection<S>         common/collection.rs:131 */
+typedef struct dbgphmm_mappings dbgphmm_mappings; /* Mappings                  hmmv2/hint.rs:150-152 */
+typedef struct dbgphmm_tables dbgphmm_tables;     /* PHMMTables of one read    hmmv2/table.rs:365-435 */
+
+const char* dbgphmm_last_error(void);
+/* number of usable sm_100-class devices (0 => every compute call fails; no CPU path exists) */
+int dbgphmm_device_count(void);
+
+/* PHMMParams::new / uniform (params.rs:73-124) */
+void dbgphmm_params_new(double p_mismatch, double p_gap_open, double p_gap_ext, double p_end,
+                        uint32_t n_active_nodes, uint32_t n_warmup, dbgphmm_params* out);
+void dbgphmm_params_uniform(double p, dbgphmm_params* out);
+
+/* ---- model ------------------------------------------------------------------------------------------- */
+/* Build the device graph from a node-centric PHMM (common.rs:61-67,202-261).
+ * edge_src/edge_dst: EdgeIndex order.  emission: 'A','C','G','T' or 'n' (NULL_BASE, common.rs:21).
+ * log_init[n_nodes], log_trans[n_edges]: PNode.init_prob / PEdge.trans_prob as natural logs.
+ * device: CUDA ordinal.  mem_budget_bytes: device memory the handle may use for DP rows (0 = 70% of free). */
+int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const uint32_t* edge_src, const uint32_t* edge_dst,
+                         const uint8_t* emission, const double* log_init, const double* log_trans,
+                         const dbgphmm_params* params, int device, uint64_t mem_budget_bytes, dbgphmm_model** out);
+void dbgphmm_model_destroy(dbgphmm_model* m);
+int dbgphmm_model_set_params(dbgphmm_model* m, const dbgphmm_params* params);
+/* Replace init/trans of parameter set 0 (a rebuilt PModel with the same graph). */
+int dbgphmm_model_set_probs(dbgphmm_model* m, const double* log_init, const double* log_trans);
+/* Derive n_batch parameter sets on the device from node copy numbers: SeqGraph::to_phmm (mode 0),
+ * to_non_zero_phmm (mode 1), to_uniform_phmm (mode 2)  — graph/seq_graph.rs:160-273 with edge copy numbers
+ * None (the branch MultiDbg uses, multi_dbg.rs:1386-1387).  copy_nums is [n_batch][n_nodes].  After this call
+ * dbgphmm_to_full_prob_reads evaluates all n_batch candidates X in one launch (posterior.rs:504-515). */
+int dbgphmm_model_set_copy_nums_batch(dbgphmm_model* m, uint32_t n_batch, const uint32_t* copy_nums, int mode);
+/* Read back parameter set `x` (natural logs), for tests. */
+int dbgphmm_model_get_probs(const dbgphmm_model* m, uint32_t x, double* log_init, double* log_trans);
+uint32_t dbgphmm_model_n_nodes(const dbgphmm_model* m);
+uint32_t dbgphmm_model_n_batch(const dbgphmm_model* m);
+
+/* ---- reads / mappings --------------------------------------------------------------------------------- */
+/* offsets[n_reads+1] into bases; bases are uppercase ACGT (collection.rs:236-249 panics otherwise). */
+int dbgphmm_reads_create(uint64_t n_reads, const uint64_t* offsets, const uint8_t* bases, dbgphmm_reads** out);
+void dbgphmm_reads_destroy(dbgphmm_reads* r);
+/* Mappings as CSR: read_off[n_reads+1] (rows = bases), row_off[n_rows+1] (entries), nodes[], logp[]
+ * (hint.rs:27-30: Mapping.nodes / Mapping.probs). */
+int dbgphmm_mappings_create(uint64_t n_reads, const uint64_t* read_off, const uint64_t* row_off,
+                            const uint32_t* nodes, const double* logp, dbgphmm_mappings** out);
+void dbgphmm_mappings_destroy(dbgphmm_mappings* mp);
+int dbgphmm_mappings_sizes(const dbgphmm_mappings* mp, uint64_t* n_reads, uint64_t* n_rows, uint64_t* n_entries);
+int dbgphmm_mappings_export(const dbgphmm_mappings* mp, uint64_t* read_off, uint64_t* row_off, uint32_t* nodes, double* logp);
+/* Mappings::to_node_freqs (hint.rs:161-171) == MultiDbg::mappings_to_freqs (multi_dbg/draft.rs:201-212) */
+int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32_t n_nodes, double* freqs);
+
+/* ---- PHMMTables of one read (forward.rs / backward.rs drivers) ---------------------------------------- */
+enum {
+    DBGPHMM_FWD_DENSE = 0,        /* forward               forward.rs:24  */
+    DBGPHMM_FWD_SPARSE = 1,       /* forward_sparse(false) forward.rs:93  */
+    DBGPHMM_FWD_SPARSE_RATIO = 2, /* forward_sparse(true)  forward.rs:93  */
+    DBGPHMM_FWD_MAPPING = 3       /* forward_with_mapping  forward.rs:51  */
+};
+enum {
+    DBGPHMM_BWD_DENSE = 0,     /* backward              backward.rs:24  */
+    DBGPHMM_BWD_SPARSE = 1,    /* backward_sparse       backward.rs:146 */
+    DBGPHMM_BWD_MAPPING = 2,   /* backward_with_mapping backward.rs:59  */
+    DBGPHMM_BWD_BY_FORWARD = 3 /* backward_by_forward   backward.rs:101 */
+};
+/* mapping / read_index are used by the *_MAPPING kinds only; fwd is used by BWD_BY_FORWARD only. */
+int dbgphmm_forward(dbgphmm_model* m, const uint8_t* bases, uint64_t n, int kind,
+                    const dbgphmm_mappings* mapping, uint64_t read_index, dbgphmm_tables** out);
+int dbgphmm_backward(dbgphmm_model* m, const uint8_t* bases, uint64_t n, int kind,
+                     const dbgphmm_mappings* mapping, uint64_t read_index, const dbgphmm_tables* fwd,
+                     dbgphmm_tables** out);
+void dbgphmm_tables_destroy(dbgphmm_tables* t);
+uint64_t dbgphmm_tables_len(const dbgphmm_tables* t);
+/* PHMMTables::full_prob (table.rs:395-401): last e (forward) or first mb (backward) */
+int dbgphmm_tables_full_prob(const dbgphmm_tables* t, double* logp);
+/* row = -1 is init_table.  info = {is_dense, n_mi, n_d}; scalars = {mb, ib, e} (natural logs). */
+int dbgphmm_tables_row_info(const dbgphmm_tables* t, int64_t row, uint64_t info[3], double scalars[3]);
+/* dense row: m,i,d each n_nodes (ids unused).  sparse row: ids_mi[n_mi], m[n_mi], i[n_mi], ids_d[n_d], d[n_d]
+ * in the insertion order of the reference's SparseVec. */
+int dbgphmm_tables_row_export(const dbgphmm_tables* t, int64_t row, uint32_t* ids_mi, double* m, double* i,
+                              uint32_t* ids_d, double* d);
+/* PHMMTable::top_nodes(k) (by_ratio = 0, table.rs:127) / top_nodes_by_score_ratio(ratio) (table.rs:134);
+ * out has room for DBGPHMM_MAX_ACTIVE_NODES ids. */
+int dbgphmm_tables_row_top_nodes(const dbgphmm_tables* t, int64_t row, int by_ratio, uint32_t k, double ratio,
+                                 uint32_t* out, uint32_t* n_out);
+
+/* ---- PHMMOutput of one read (table.rs:450-517, freq.rs:198-255, hint.rs:120-142) ---------------------- */
+/* to_node_freqs (freq.rs:245-255): freqs[n_nodes] */
+int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* freqs);
+/* to_mapping(n_active) (by_ratio = 0) / to_mapping_by_score_ratio(ratio): a 1-read Mappings handle */
+int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, int by_ratio,
+                           uint32_t n_active, double ratio, dbgphmm_mappings** out);
+
+/* ---- bulk calls over a read set (the rayon-parallel entry points) ------------------------------------- */
+/* PHMMModel::to_full_prob_reads (freq.rs:175-192) evaluated for every parameter set X of the model:
+ * mappings != NULL -> forward_with_mapping_score_only (forward.rs:79), else forward_sparse_score_only
+ * (forward.rs:158) with use_max_ratio.  out_logp[n_batch] = sum over reads in read order (fixed order, unlike
+ * rayon's); out_logp_per_read (nullable) is [n_batch][n_reads].  This is MultiDbg::to_likelihood
+ * (multi_dbg/posterior.rs:247-255) for each candidate of sample_posterior_once (:504-515). */
+int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads* reads, const dbgphmm_mappings* mappings,
+                               int use_max_ratio, double* out_logp, double* out_logp_per_read);
+
+enum {
+    DBGPHMM_RUN_DENSE = 0,           /* run                  freq.rs:42 */
+    DBGPHMM_RUN_SPARSE = 1,          /* run_sparse           freq.rs:51 */
+    DBGPHMM_RUN_SPARSE_ADAPTIVE = 2, /* run_sparse_adaptive  freq.rs:60 */
+    DBGPHMM_RUN_WITH_MAPPING = 3     /* run_with_mapping     freq.rs:72 */
+};
+/* For every read: run*() then PHMMOutput::to_node_freqs, summed over reads (PHMMModel::to_node_freqs,
+ * freq.rs:87-102, generalised to the four run modes).  node_freqs[n_nodes] (nullable), logp_fwd[n_reads] =
+ * to_full_prob_forward, logp_bwd[n_reads] = to_full_prob_backward (nullable).  cells (nullable) receives the
+ * number of (base, node) cells evaluated by f_step/b_step {forward, backward} — the GCUPS numerator. */
+int dbgphmm_run_node_freqs(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int use_max_ratio,
+                           const dbgphmm_mappings* mappings, double* node_freqs, double* logp_fwd, double* logp_bwd,
+                           uint64_t cells[2]);
+/* Same, but accumulating into / writing device buffers (f64 node_freqs_dev[n_nodes] is ADDED to, so that a
+ * caller can all-reduce it with NCCL without a host round trip; logp_*_dev are [n_reads], nullable). */
+int dbgphmm_run_node_freqs_dev(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int use_max_ratio,
+                               const dbgphmm_mappings* mappings, double* node_freqs_dev, double* logp_fwd_dev,
+                               double* logp_bwd_dev, uint64_t cells[2]);
+/* PHMMModel::generate_mappings (hint.rs:193-220): run_with_mapping if mappings != NULL else
+ * run_sparse_adaptive(use_max_ratio); then to_mapping_by_score_ratio(active_node_max_ratio) if use_max_ratio
+ * else to_mapping(n_active_nodes). */
+int dbgphmm_generate_mappings(dbgphmm_model* m, const dbgphmm_reads* reads, const dbgphmm_mappings* mappings,
+                              int use_max_ratio, dbgphmm_mappings** out);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------- */
+/* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
+uint64_t dbgphmm_launch_count(int reset);
+/* Milliseconds of the last bulk call spent in {dense kernels, sparse kernels, product kernels, total},
+ * measured with CUDA events on the library's stream; and the algorithmic cell count of the dense kernels. */
+int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells);
+/* Upload-free variant for benchmarking: move a reads handle's bases to the device once (idempotent). */
+int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBGPHMM_B200_H */

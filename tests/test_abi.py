@@ -1,0 +1,63 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads, exports every declared symbol, and refuses to
+compute without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dbgphmm_b200 import build as B
+from dbgphmm_b200 import graphs
+from dbgphmm_b200 import hmmv2 as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build()
+    return H.lib()
+
+
+def test_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "dbgphmm_b200.h")).read()
+    declared = set(re.findall(r"\b(dbgphmm_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(H.SYMBOLS), declared ^ set(H.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s)
+
+
+def test_params_match_reference_formula(lib):
+    q = H.params_uniform(0.001)  # params.rs:116-124
+    assert q.n_active_nodes == 40 and q.n_warmup == 50 and q.warmup_threshold == 200 and q.n_max_gaps == 4
+    assert abs(np.exp(q.p_MM) - (1 - 0.002 - 1e-5)) < 1e-15 and q.p_random == np.log(0.25)
+    from oracle import oracle as O
+    o = O.params_uniform(0.001)
+    for name, _ in H.Params._fields_:
+        assert getattr(q, name) == getattr(o, name), name
+
+
+def test_reads_validation(lib):
+    with pytest.raises(H.DbgphmmError):
+        H.Reads([b"ACGN"])  # collection.rs:236-249 panics on non-ACGT
+    r = H.Reads([b"ACGT", b"GG"])
+    assert len(r) == 2 and r.total_bases() == 6
+
+
+def test_mappings_roundtrip_and_freqs(lib):
+    m = H.Mappings.from_list([H.Mapping([[1, 2], [3]], [[np.log(0.75), np.log(0.25)], [0.0]])])
+    assert m.n_reads() == 1 and len(m[0]) == 2
+    f = m.to_node_freqs(5)  # hint.rs:161-171
+    assert np.allclose(f, [0, 0.75, 0.25, 1.0, 0])
+
+
+def test_no_gpu_means_loud_failure(lib):
+    if H.device_count() > 0:
+        pytest.skip("a GPU is present")
+    sg = graphs.mock_linear()
+    li, lt = sg.to_probs()
+    with pytest.raises(H.DbgphmmError) as ei:
+        H.PHMMModel(sg.src, sg.dst, sg.base, li, lt, H.params_uniform(0.01))
+    assert ei.value.status == H.ERR_CUDA

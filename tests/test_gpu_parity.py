@@ -1,0 +1,253 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): active-node sets and selected indices identical; ln P(R|X) and node frequencies within
+1e-9 relative (f64).  The reference's own known-answer values (tests/golden/reference_kat.json) are also asserted
+directly on the GPU results."""
+import numpy as np
+import pytest
+
+from dbgphmm_b200 import graphs, synth
+from oracle import oracle as O
+from tests.common import (REL_TOL, assert_rows_match, assert_tables_match, close_log, gpu_model, kat, oracle_model,
+                          oracle_params, random_linear_graph)
+
+pytestmark = pytest.mark.gpu
+K = kat()
+
+
+@pytest.fixture(scope="module")
+def H():
+    from dbgphmm_b200 import hmmv2
+    assert hmmv2.device_count() > 0, "no B200 visible"
+    return hmmv2
+
+
+def both(sg, param, mode="normal"):
+    return gpu_model(sg, param, mode), oracle_model(sg, param, mode)
+
+
+# ---------------------------------------------------------------- reference KATs straight on the GPU
+@pytest.mark.parametrize("case", ["forward_zero_error", "forward_high_error"])
+def test_kat_forward(H, case):
+    c = K[case]
+    g, _ = both(graphs.mock_linear(), oracle_params(c["p"]))
+    f = g.forward(c["read"].encode())
+    assert len(f) == 5
+    for row, node, val in c.get("m", []):
+        assert abs(f.row(row).m[node] - val) < c["eps"]
+    for row, val in c["e"]:
+        assert abs(f.row(row).e - val) < c["eps"]
+    if c.get("all_i_d_zero"):
+        for r in range(5):
+            assert np.isneginf(f.row(r).i).all() and np.isneginf(f.row(r).d).all()
+        assert np.isneginf(g.forward(c["impossible_read"].encode()).row(4).e)
+    if "read2" in c:
+        f2 = g.forward(c["read2"].encode())
+        for row, val in c["e2"]:
+            assert abs(f2.row(row).e - val) < c["eps"]
+
+
+@pytest.mark.parametrize("case", ["backward_zero_error", "backward_high_error"])
+def test_kat_backward(H, case):
+    c = K[case]
+    g, _ = both(graphs.mock_linear(), oracle_params(c["p"]))
+    b = g.backward(c["read"].encode())
+    for row, node, val in c.get("m", []):
+        assert abs(b.row(row).m[node] - val) < c["eps"]
+    for row, val in c["mb"]:
+        assert abs(b.row(row).mb - val) < c["eps"]
+    if "read2" in c:
+        b2 = g.backward(c["read2"].encode())
+        for row, val in c["mb2"]:
+            assert abs(b2.row(row).mb - val) < c["eps"]
+
+
+def test_kat_mapping_node_lists(H):
+    c = K["hint_mock_linear_high_error"]
+    g, _ = both(graphs.mock_linear(), oracle_params(c["p"]))
+    o = g.run(c["read"].encode())
+    hint = o.to_mapping(c["n_active"])
+    assert [list(map(int, x)) for x in hint.nodes] == c["nodes"]
+    maps = H.Mappings.from_list([hint])
+    p1 = g.forward(c["read"].encode()).full_prob()
+    p2 = g.forward_with_mapping(c["read"].encode(), maps, 0).full_prob()
+    assert abs(p1 - p2) < c["max_log_diff_dense_vs_hint"]
+
+
+def test_kat_hint_for_toy(H):
+    c = K["hint_for_toy"]
+    sg, k = graphs.toy_repeat()
+    par = oracle_params(c["p"], n_warmup=k)
+    g = gpu_model(sg, par, "non_zero")
+    for case in c["cases"]:
+        mp = g.generate_mappings(H.Reads([case["read"].encode()]), None, True)[0]
+        assert [int(x[0]) for x in mp.nodes] == case["top1"]
+
+
+# ---------------------------------------------------------------- row-by-row parity with the oracle
+def _dbg_case(seed, glen=600, k=12, ploidy=2, het=0.02, p_err=0.01, read_len=150, n_reads=4):
+    w = synth.make_workload("t", glen, k, 4, read_len, p_err, ploidy=ploidy, het=het, seed=seed, n_reads=n_reads)
+    return w
+
+
+@pytest.mark.parametrize("p", [0.0, 0.001, 0.1])
+def test_dense_rows_linear(H, p):
+    sg, seq = random_linear_graph(300, 1)
+    g, o = both(sg, oracle_params(p))
+    read = seq[100:160]
+    assert_tables_match(g.forward(read), o.forward(read), sg.n_nodes, f"fwd p={p}")
+    assert_tables_match(g.backward(read), o.backward(read), sg.n_nodes, f"bwd p={p}")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_dense_rows_dbg(H, seed):
+    w = _dbg_case(seed)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(w.graph, par)
+    for read in w.reads[:2]:
+        assert_tables_match(g.forward(read), o.forward(read), w.graph.n_nodes, "fwd")
+        assert_tables_match(g.backward(read), o.backward(read), w.graph.n_nodes, "bwd")
+
+
+def test_dense_multi_chunk_graph(H):
+    # more nodes than one tile (DENSE_CORE = 1024) so halos between chunks are exercised
+    w = _dbg_case(7, glen=3000, k=16, read_len=60, n_reads=2)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(w.graph, par)
+    assert w.graph.n_nodes > 2048
+    for read in w.reads:
+        assert_tables_match(g.forward(read), o.forward(read), w.graph.n_nodes, "fwd")
+        assert_tables_match(g.backward(read), o.backward(read), w.graph.n_nodes, "bwd")
+
+
+@pytest.mark.parametrize("seed,n_active", [(0, 40), (1, 10), (3, 80)])
+def test_sparse_topn_rows_bit_exact_sets(H, seed, n_active):
+    w = _dbg_case(seed)
+    par = oracle_params(0.01, n_warmup=w.k, n_active=n_active)
+    g, o = both(w.graph, par)
+    for read in w.reads[:3]:
+        assert_tables_match(g.forward_sparse(read, False), o.forward_sparse(read, False), w.graph.n_nodes, "fwd_sparse")
+        assert_tables_match(g.backward_sparse(read), o.backward_sparse(read), w.graph.n_nodes, "bwd_sparse")
+
+
+@pytest.mark.parametrize("seed", [0, 4])
+def test_sparse_ratio_and_by_forward(H, seed):
+    w = _dbg_case(seed, k=16, p_err=0.003)
+    par = oracle_params(0.001, n_warmup=w.k, warmup_threshold=30)
+    g, o = both(w.graph, par, "non_zero")
+    for read in w.reads[:3]:
+        gf, of = g.forward_sparse(read, True), o.forward_sparse(read, True)
+        assert_tables_match(gf, of, w.graph.n_nodes, "fwd_ratio")
+        assert_tables_match(g.backward_by_forward(read, gf), o.backward_by_forward(read, of), w.graph.n_nodes, "bwd_by_fwd")
+
+
+def test_top_nodes_of_rows(H):
+    w = _dbg_case(2)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(w.graph, par)
+    read = w.reads[0]
+    gf, of = g.forward_sparse(read, False), o.forward_sparse(read, False)
+    for r in (0, 3, w.k - 1, w.k, len(read) - 1):
+        assert list(gf.top_nodes(r, 40)) == list(of.top_nodes(r, 40)), r
+        assert list(gf.top_nodes_by_score_ratio(r, 30.0)) == list(of.top_nodes_by_score_ratio(r, 30.0)), r
+
+
+def test_mapping_tables_and_generate_mappings(H):
+    w = _dbg_case(5, k=16, p_err=0.003)
+    par = oracle_params(0.001, n_warmup=w.k, warmup_threshold=30)
+    g, o = both(w.graph, par, "non_zero")
+    reads = w.reads[:3]
+    gm = g.generate_mappings(H.Reads(reads), None, True)
+    om = o.generate_mappings(O.Reads(reads), None, True)
+    assert np.array_equal(gm.read_off, om.read_off)
+    assert np.array_equal(gm.row_off, om.row_off), "per-base candidate counts differ"
+    assert np.array_equal(gm.nodes, om.nodes), "mapping node ids differ"
+    assert close_log(gm.probs, om.probs).all()
+    # forward / backward restricted to the mapping (forward.rs:51, backward.rs:59)
+    for r, read in enumerate(reads):
+        assert_tables_match(g.forward_with_mapping(read, gm, r), o.forward_with_mapping(read, om[r]), w.graph.n_nodes, "fwd_map")
+        assert_tables_match(g.backward_with_mapping(read, gm, r), o.backward_with_mapping(read, om[r]), w.graph.n_nodes, "bwd_map")
+    # Mappings::to_node_freqs
+    assert np.allclose(gm.to_node_freqs(w.graph.n_nodes), om.to_node_freqs(w.graph.n_nodes), rtol=1e-9, atol=1e-12)
+    # top-n mapping mode (use_max_ratio = false)
+    gm2 = g.generate_mappings(H.Reads(reads), None, False)
+    om2 = o.generate_mappings(O.Reads(reads), None, False)
+    assert np.array_equal(gm2.row_off, om2.row_off) and np.array_equal(gm2.nodes, om2.nodes)
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse", "sparse_adaptive", "with_mapping"])
+def test_run_node_freqs_and_logp(H, mode):
+    w = _dbg_case(6, n_reads=6, k=16, p_err=0.003)
+    par = oracle_params(0.001, n_warmup=w.k, warmup_threshold=30)
+    g, o = both(w.graph, par, "non_zero")
+    reads = w.reads
+    gmaps = omaps = None
+    if mode == "with_mapping":
+        omaps = o.generate_mappings(O.Reads(reads), None, True)
+        gmaps = H.Mappings(omaps.read_off, omaps.row_off, omaps.nodes, omaps.probs)
+    gf, glf, glb, cells = g.run_node_freqs(H.Reads(reads), mode, True, gmaps)
+    of, olf, olb = o.run_node_freqs(O.Reads(reads), mode, True, omaps)
+    assert close_log(glf, olf).all(), (glf, olf)
+    assert close_log(glb, olb).all(), (glb, olb)
+    assert np.allclose(gf, of, rtol=REL_TOL, atol=1e-12), np.abs(gf - of).max()
+    if mode != "with_mapping":
+        ref_cells = [sum(o.count_cells(r, mode, True, d) for r in reads) for d in (1, 2)]
+        assert list(cells) == ref_cells
+
+
+def test_full_prob_reads_batched_over_candidates(H):
+    """to_full_prob_reads for a batch of candidate copy-number vectors X (posterior.rs:504-515)."""
+    w = _dbg_case(8, n_reads=5, k=16, p_err=0.003)
+    sg = w.graph
+    par = oracle_params(0.001, n_warmup=w.k, warmup_threshold=30)
+    g = gpu_model(sg, par, "non_zero")
+    o = oracle_model(sg, par, "non_zero")
+    reads = w.reads
+    omaps = o.generate_mappings(O.Reads(reads), None, True)
+    gmaps = H.Mappings(omaps.read_off, omaps.row_off, omaps.nodes, omaps.probs)
+    rng = np.random.default_rng(0)
+    X = np.stack([sg.node_copy_num] + [np.maximum(0, sg.node_copy_num + rng.integers(-1, 2, sg.n_nodes)) for _ in range(5)])
+    g.set_copy_nums_batch(X, "normal")
+    tot, per = g.to_full_prob_reads(H.Reads(reads), gmaps)
+    tot2, per2 = g.to_full_prob_reads(H.Reads(reads), None, True)
+    for x in range(len(X)):
+        li, lt = sg.to_probs("normal", X[x])
+        gl, gt = g.get_probs(x)
+        assert close_log(gl, li, rel=1e-14).all() and close_log(gt, lt, rel=1e-14).all()
+        o.set_probs(li, lt)
+        s, p = o.to_full_prob_reads(O.Reads(reads), omaps)
+        assert close_log(per[x], p).all(), (x, per[x], p)
+        assert close_log(tot[x], s).all()
+        s2, p2 = o.to_full_prob_reads(O.Reads(reads), None, True)
+        assert close_log(per2[x], p2).all(), (x, per2[x], p2)
+
+
+def test_capacity_overflow_is_an_error_like_the_reference_panic(H):
+    # ratio mode leaving warm-up with > 200 candidates overflows the 400-entry SparseVec (params.rs:37-38)
+    w = _dbg_case(0)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(w.graph, par, "non_zero")
+    with pytest.raises(RuntimeError):
+        o.forward_sparse(w.reads[0], True)
+    with pytest.raises(H.DbgphmmError) as ei:
+        g.forward_sparse(w.reads[0], True)
+    assert ei.value.status == H.ERR_CAPACITY
+
+
+def test_zero_probability_read_is_an_error(H):
+    g, _ = both(graphs.mock_linear(), oracle_params(0.0))
+    with pytest.raises(H.DbgphmmError) as ei:
+        g.run(b"CGATT").to_node_freqs()  # the reference divides by P = 0 and panics on NaN ordering
+    assert ei.value.status == H.ERR_ZERO_PROB
+
+
+def test_read_shorter_than_warmup_and_single_base(H):
+    sg, seq = random_linear_graph(120, 3)
+    par = oracle_params(0.01, n_warmup=40)
+    g, o = both(sg, par)
+    for read in (seq[5:6], seq[10:25]):
+        assert_tables_match(g.forward_sparse(read, False), o.forward_sparse(read, False), sg.n_nodes, "fwd")
+        assert_tables_match(g.backward_sparse(read), o.backward_sparse(read), sg.n_nodes, "bwd")
+        gf, of = g.forward_sparse(read, True), o.forward_sparse(read, True)
+        assert_tables_match(gf, of, sg.n_nodes, "fwd ratio")
+        assert_tables_match(g.backward_by_forward(read, gf), o.backward_by_forward(read, of), sg.n_nodes, "bwd by fwd")
