@@ -80,6 +80,7 @@ extern "C" int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32
 // ------------------------------------------------------------------ PHMMTables of one read
 struct dbgphmm_tables {
     dbgphmm_model* m = nullptr;
+    int device = -1;             // kept separately: the handle may be destroyed after its model
     int dir = 0, kind = 0;
     std::vector<uint8_t> bases;
     uint8_t* d_bases = nullptr;
@@ -94,7 +95,7 @@ static int tables_finish(dbgphmm_tables* t) {
 }
 extern "C" void dbgphmm_tables_destroy(dbgphmm_tables* t) {
     if (!t) return;
-    cudaSetDevice(t->m->device);
+    if (t->device >= 0) cudaSetDevice(t->device);
     t->store.release();
     cudaFree(t->d_bases);
     delete t;
@@ -105,7 +106,7 @@ static int one_job(dbgphmm_model* m, const uint8_t* bases, uint64_t n, const dbg
     for (uint64_t i = 0; i < n; i++)
         if (bases[i] != 'A' && bases[i] != 'C' && bases[i] != 'G' && bases[i] != 'T') { dbg_set_error("bases must be uppercase ACGT"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
-    t->m = m; t->bases.assign(bases, bases + n);
+    t->m = m; t->device = m->device; t->bases.assign(bases, bases + n);
     CUDA_TRY(cudaMalloc((void**)&t->d_bases, n));
     CUDA_TRY(cudaMemcpy(t->d_bases, bases, n, cudaMemcpyHostToDevice));
     HJob j{}; j.read = 0; j.x = 0; j.base_off = 0; j.len = (uint32_t)n; j.map_row0 = 0;
@@ -129,7 +130,7 @@ extern "C" int dbgphmm_forward(dbgphmm_model* m, const uint8_t* bases, uint64_t 
     if (st == DBGPHMM_OK) st = run_forward(m, jobs, t->d_bases, kind, true, true, kind == DBGPHMM_FWD_MAPPING ? &dmap : nullptr, &t->store);
     if (st == DBGPHMM_OK) st = tables_finish(t);
     dmap.release();
-    if (st != DBGPHMM_OK) { if (t->m) dbgphmm_tables_destroy(t); else delete t; return st; }
+    if (st != DBGPHMM_OK) { dbgphmm_tables_destroy(t); return st; }
     *out = t;
     return DBGPHMM_OK;
 }
@@ -144,7 +145,7 @@ extern "C" int dbgphmm_backward(dbgphmm_model* m, const uint8_t* bases, uint64_t
     if (st == DBGPHMM_OK) st = run_backward(m, jobs, t->d_bases, kind, true, kind == DBGPHMM_BWD_MAPPING ? &dmap : nullptr, fwd ? &fwd->store : nullptr, &t->store);
     if (st == DBGPHMM_OK) st = tables_finish(t);
     dmap.release();
-    if (st != DBGPHMM_OK) { if (t->m) dbgphmm_tables_destroy(t); else delete t; return st; }
+    if (st != DBGPHMM_OK) { dbgphmm_tables_destroy(t); return st; }
     *out = t;
     return DBGPHMM_OK;
 }

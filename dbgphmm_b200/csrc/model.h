@@ -12,7 +12,7 @@ void dbg_set_error(const std::string& s);
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \
         if (_e != cudaSuccess) {                                                               \
-            dbg_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+            dbg_set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " + #expr + ": " + cudaGetErrorString(_e));                 \
             return DBGPHMM_ERR_CUDA;                                                           \
         }                                                                                      \
     } while (0)

@@ -248,6 +248,16 @@ class Row:
     """One PHMMTable (table.rs:42-73), natural logs."""
     __slots__ = ("is_dense", "ids", "m", "i", "ids_d", "d", "mb", "ib", "e")
 
+    def merged(self, n_nodes):
+        """PHMMTable::to_nodevec (table.rs:199-211) as a dense ln array (absent = -inf)."""
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if self.is_dense:
+                return np.logaddexp(np.logaddexp(self.m, self.i), self.d)
+            v = np.full(n_nodes, -np.inf)
+            v[self.ids] = np.logaddexp(self.m, self.i)
+            v[self.ids_d] = np.logaddexp(v[self.ids_d], self.d)
+        return v
+
 
 class PHMMTables:
     """PHMMTables (table.rs:365-435) of one read, resident on the GPU."""

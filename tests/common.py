@@ -70,16 +70,64 @@ def assert_rows_match(g, o, n_nodes, what=""):
             ok = close_log(a, b) | (np.isneginf(a) & (b < cellmax - 700.0))
             assert ok.all(), f"{what}: dense {name} mismatch at {np.nonzero(~ok)[0][:5]}: {a[~ok][:5]} vs {b[~ok][:5]}"
     else:
-        assert list(g.ids) == list(o.ids), f"{what}: m/i node list differs\n gpu {list(g.ids)}\n ref {list(o.ids)}"
-        assert list(g.ids_d) == list(o.ids_d), f"{what}: d node list differs\n gpu {list(g.ids_d)}\n ref {list(o.ids_d)}"
-        assert close_log(g.m, o.m).all(), f"{what}: sparse m {g.m} vs {o.m}"
-        assert close_log(g.i, o.i).all(), f"{what}: sparse i {g.i} vs {o.i}"
-        # d of a node is compared against the max state of that node
-        ok = close_log(g.d, o.d)
-        if not ok.all():
-            mi = {int(k): max(a, b) for k, a, b in zip(o.ids, o.m, o.i)}
+        # Index SETS must be identical.  The order inside a row follows the order of the selected top nodes, which
+        # is only reproducible up to values that tie within rounding (log-space f64 on the CPU vs exponent-extended
+        # linear f64 on the GPU round differently) — see same_up_to_ties for the check on the selections themselves.
+        assert sorted(g.ids) == sorted(o.ids), f"{what}: m/i node set differs\n gpu {sorted(map(int, g.ids))}\n ref {sorted(map(int, o.ids))}"
+        assert sorted(g.ids_d) == sorted(o.ids_d), f"{what}: d node set differs\n gpu {sorted(map(int, g.ids_d))}\n ref {sorted(map(int, o.ids_d))}"
+        g = _reorder_like(g, o)
+        # largest state of each node in this row (the GPU cell exponent follows it)
+        cmax = {}
+        for k, a_, b_ in zip(o.ids, o.m, o.i):
+            cmax[int(k)] = max(a_, b_)
+        for k, d_ in zip(o.ids_d, o.d):
+            cmax[int(k)] = max(cmax.get(int(k), -np.inf), d_)
+        for name, ids in (("m", o.ids), ("i", o.ids), ("d", o.ids_d)):
+            a_, b_ = getattr(g, name), getattr(o, name)
+            ok = close_log(a_, b_)
             for j in np.nonzero(~ok)[0]:
-                assert np.isneginf(g.d[j]) and o.d[j] < mi.get(int(o.ids_d[j]), -np.inf) - 700.0, f"{what}: sparse d {g.d[j]} vs {o.d[j]}"
+                assert np.isneginf(a_[j]) and b_[j] < cmax[int(ids[j])] - 700.0, \
+                    f"{what}: sparse {name}[{j}] node {ids[j]}: {a_[j]} vs {b_[j]}"
+
+
+class _R:
+    pass
+
+
+def _reorder_like(g, o):
+    """view of sparse row g with its entries permuted into o's order"""
+    r = _R()
+    pos = {int(k): j for j, k in enumerate(g.ids)}
+    idx = [pos[int(k)] for k in o.ids]
+    r.ids = o.ids; r.m = g.m[idx]; r.i = g.i[idx]
+    posd = {int(k): j for j, k in enumerate(g.ids_d)}
+    idxd = [posd[int(k)] for k in o.ids_d]
+    r.ids_d = o.ids_d; r.d = g.d[idxd]
+    r.is_dense = False; r.mb, r.ib, r.e = g.mb, g.ib, g.e
+    return r
+
+
+def same_up_to_ties(a_ids, b_ids, b_vals, rel=1e-9):
+    """Two descending selections are equal up to permutations inside groups of values that tie within `rel`."""
+    a_ids = [int(x) for x in a_ids]; b_ids = [int(x) for x in b_ids]
+    if len(a_ids) != len(b_ids):
+        return False
+    n = len(b_ids)
+    start = 0
+    for i in range(1, n + 1):
+        tie = False
+        if i < n:
+            x, y = b_vals[i - 1], b_vals[i]
+            tie = (np.isneginf(x) and np.isneginf(y)) or abs(x - y) <= rel * max(1.0, abs(x))
+        if not tie:
+            if sorted(a_ids[start:i]) != sorted(b_ids[start:i]):
+                return False
+            start = i
+    return True
+
+
+def row_order_exact(g, o):
+    return o.is_dense or (list(g.ids) == list(o.ids) and list(g.ids_d) == list(o.ids_d))
 
 
 def assert_tables_match(gt, ot, n_nodes, what=""):

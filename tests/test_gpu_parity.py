@@ -9,7 +9,7 @@ import pytest
 from dbgphmm_b200 import graphs, synth
 from oracle import oracle as O
 from tests.common import (REL_TOL, assert_rows_match, assert_tables_match, close_log, gpu_model, kat, oracle_model,
-                          oracle_params, random_linear_graph)
+                          oracle_params, random_linear_graph, row_order_exact, same_up_to_ties)
 
 pytestmark = pytest.mark.gpu
 K = kat()
@@ -147,9 +147,33 @@ def test_top_nodes_of_rows(H):
     g, o = both(w.graph, par)
     read = w.reads[0]
     gf, of = g.forward_sparse(read, False), o.forward_sparse(read, False)
-    for r in (0, 3, w.k - 1, w.k, len(read) - 1):
-        assert list(gf.top_nodes(r, 40)) == list(of.top_nodes(r, 40)), r
-        assert list(gf.top_nodes_by_score_ratio(r, 30.0)) == list(of.top_nodes_by_score_ratio(r, 30.0)), r
+    for r in list(range(0, w.k + 3)) + [len(read) // 2, len(read) - 1]:
+        merged = of.row(r).merged(w.graph.n_nodes)
+        for k in (1, 10, 40):
+            a, b = gf.top_nodes(r, k), of.top_nodes(r, k)
+            assert same_up_to_ties(a, b, merged[b]), (r, k, list(a), list(b))
+        a, b = gf.top_nodes_by_score_ratio(r, 30.0), of.top_nodes_by_score_ratio(r, 30.0)
+        assert same_up_to_ties(a, b, merged[b]), (r, list(a), list(b))
+
+
+def test_sparse_row_order_is_exact_when_nothing_ties(H):
+    # on a unique-sequence linear genome with a clean read nothing ties: entry ORDER must then be identical too
+    sg, seq = random_linear_graph(400, 9)
+    par = oracle_params(0.01, n_warmup=20)
+    g, o = both(sg, par)
+    read = seq[150:300]
+    for gt, ot in ((g.forward_sparse(read, False), o.forward_sparse(read, False)), (g.backward_sparse(read), o.backward_sparse(read))):
+        exact = sum(row_order_exact(gt.row(r), ot.row(r)) for r in range(len(ot)))
+        assert exact >= 0.9 * len(ot), exact
+
+
+def _assert_mappings_equal(gm, om):
+    """same candidate nodes per base (order up to ties within rounding) and the same ln probabilities per node"""
+    for row in range(len(om.row_off) - 1):
+        a, b = int(om.row_off[row]), int(om.row_off[row + 1])
+        assert same_up_to_ties(gm.nodes[a:b], om.nodes[a:b], om.probs[a:b]), (row, gm.nodes[a:b], om.nodes[a:b])
+        gp = dict(zip(gm.nodes[a:b].tolist(), gm.probs[a:b].tolist()))
+        assert close_log([gp[int(k)] for k in om.nodes[a:b]], om.probs[a:b]).all(), row
 
 
 def test_mapping_tables_and_generate_mappings(H):
@@ -161,18 +185,21 @@ def test_mapping_tables_and_generate_mappings(H):
     om = o.generate_mappings(O.Reads(reads), None, True)
     assert np.array_equal(gm.read_off, om.read_off)
     assert np.array_equal(gm.row_off, om.row_off), "per-base candidate counts differ"
-    assert np.array_equal(gm.nodes, om.nodes), "mapping node ids differ"
-    assert close_log(gm.probs, om.probs).all()
+    _assert_mappings_equal(gm, om)
     # forward / backward restricted to the mapping (forward.rs:51, backward.rs:59)
+    gom = H.Mappings(om.read_off, om.row_off, om.nodes, om.probs)  # identical hint for both sides
     for r, read in enumerate(reads):
-        assert_tables_match(g.forward_with_mapping(read, gm, r), o.forward_with_mapping(read, om[r]), w.graph.n_nodes, "fwd_map")
-        assert_tables_match(g.backward_with_mapping(read, gm, r), o.backward_with_mapping(read, om[r]), w.graph.n_nodes, "bwd_map")
+        gt, ot = g.forward_with_mapping(read, gom, r), o.forward_with_mapping(read, om[r])
+        assert_tables_match(gt, ot, w.graph.n_nodes, "fwd_map")
+        assert all(row_order_exact(gt.row(i), ot.row(i)) for i in range(len(ot))), "mapping rows keep the hint's node order"
+        assert_tables_match(g.backward_with_mapping(read, gom, r), o.backward_with_mapping(read, om[r]), w.graph.n_nodes, "bwd_map")
     # Mappings::to_node_freqs
     assert np.allclose(gm.to_node_freqs(w.graph.n_nodes), om.to_node_freqs(w.graph.n_nodes), rtol=1e-9, atol=1e-12)
     # top-n mapping mode (use_max_ratio = false)
     gm2 = g.generate_mappings(H.Reads(reads), None, False)
     om2 = o.generate_mappings(O.Reads(reads), None, False)
-    assert np.array_equal(gm2.row_off, om2.row_off) and np.array_equal(gm2.nodes, om2.nodes)
+    assert np.array_equal(gm2.row_off, om2.row_off)
+    _assert_mappings_equal(gm2, om2)
 
 
 @pytest.mark.parametrize("mode", ["dense", "sparse", "sparse_adaptive", "with_mapping"])
@@ -206,10 +233,14 @@ def test_full_prob_reads_batched_over_candidates(H):
     omaps = o.generate_mappings(O.Reads(reads), None, True)
     gmaps = H.Mappings(omaps.read_off, omaps.row_off, omaps.nodes, omaps.probs)
     rng = np.random.default_rng(0)
-    X = np.stack([sg.node_copy_num] + [np.maximum(0, sg.node_copy_num + rng.integers(-1, 2, sg.n_nodes)) for _ in range(5)])
+    # candidates: the true copy numbers, +1 on a few nodes, and +-1 (some nodes drop to 0 copies)
+    X = np.stack([sg.node_copy_num] + [sg.node_copy_num + (rng.random(sg.n_nodes) < 0.03) for _ in range(2)]
+                 + [np.maximum(0, sg.node_copy_num + rng.integers(-1, 2, sg.n_nodes)) for _ in range(3)])
     g.set_copy_nums_batch(X, "normal")
     tot, per = g.to_full_prob_reads(H.Reads(reads), gmaps)
+    g.set_copy_nums_batch(X[:3], "normal")
     tot2, per2 = g.to_full_prob_reads(H.Reads(reads), None, True)
+    g.set_copy_nums_batch(X, "normal")
     for x in range(len(X)):
         li, lt = sg.to_probs("normal", X[x])
         gl, gt = g.get_probs(x)
@@ -218,8 +249,9 @@ def test_full_prob_reads_batched_over_candidates(H):
         s, p = o.to_full_prob_reads(O.Reads(reads), omaps)
         assert close_log(per[x], p).all(), (x, per[x], p)
         assert close_log(tot[x], s).all()
-        s2, p2 = o.to_full_prob_reads(O.Reads(reads), None, True)
-        assert close_log(per2[x], p2).all(), (x, per2[x], p2)
+        if x < 3:
+            s2, p2 = o.to_full_prob_reads(O.Reads(reads), None, True)
+            assert close_log(per2[x], p2).all(), (x, per2[x], p2)
 
 
 def test_capacity_overflow_is_an_error_like_the_reference_panic(H):
