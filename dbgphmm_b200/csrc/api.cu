@@ -301,6 +301,12 @@ extern "C" int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells) {
     if (dense_cells) *dense_cells = g_times.dense_cells;
     return DBGPHMM_OK;
 }
+extern "C" int dbgphmm_last_dense_kernel(double* ms, uint64_t* launches, uint64_t* cells) {
+    if (ms) *ms = g_times.dense_kernel_ms;
+    if (launches) *launches = g_times.dense_kernel_launches;
+    if (cells) *cells = g_times.dense_kernel_cells;
+    return DBGPHMM_OK;
+}
 
 static int check_reads_mappings(const dbgphmm_reads* reads, const dbgphmm_mappings* mp) {
     if (!mp) return DBGPHMM_OK;

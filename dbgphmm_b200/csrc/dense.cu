@@ -9,6 +9,7 @@
 // b_step: backward.rs:216-261 (bd0 :354, bdt :387, bm :423, bi :462, bmb :499, bib :535)
 #include <algorithm>
 #include "dense.h"
+#include "engine.h"
 
 struct PlanView {
     const uint32_t *chunk_start, *loc_base, *loc_node, *nle, *le_off, *le_eid;
@@ -551,11 +552,12 @@ int dense_configure(dbgphmm_model* m) {
 }
 
 int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
-                       const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, XF* d_rowmax) {
-    (void)d_rowmax;
+                       const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, uint64_t step_cells) {
     dim3 grid(m->fwd.n_chunks, n_jobs);
+    launch_timer_begin(m->stream);
     k_dense_fwd<<<grid, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
                                                                       d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks);
+    launch_timer_end(m->stream, step_cells);
     COUNT_LAUNCH();
     k_dense_fwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->fwd.n_chunks);
     COUNT_LAUNCH();
@@ -564,11 +566,12 @@ int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jo
 }
 
 int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
-                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, XF* d_rowmax) {
-    (void)d_rowmax;
+                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, uint64_t step_cells) {
     dim3 grid(m->bwd.n_chunks, n_jobs);
+    launch_timer_begin(m->stream);
     k_dense_bwd<<<grid, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_active,
                                                                       pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks);
+    launch_timer_end(m->stream, step_cells);
     COUNT_LAUNCH();
     k_dense_bwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->bwd.n_chunks);
     COUNT_LAUNCH();

@@ -40,9 +40,9 @@ static inline uint64_t dense_slab_bytes(uint32_t N) {
 int dense_configure(dbgphmm_model* m);
 // one forward / backward step `s` for all jobs (grid = chunks x jobs) followed by the row reduction.
 int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
-                       const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, XF* d_rowmax);
+                       const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, uint64_t step_cells);
 int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
-                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, XF* d_rowmax);
+                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, uint64_t step_cells);
 
 // Top-k of merged (m+i+d) values of dense rows (PHMMTable::top_nodes / top_nodes_by_score_ratio on a dense
 // table, table.rs:127-149).  One CTA per request.

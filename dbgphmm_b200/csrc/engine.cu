@@ -8,6 +8,30 @@
 
 EngineTimes g_times;
 
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_free, g_ev_busy;
+static std::vector<uint64_t> g_ev_cells;
+void launch_timer_begin(cudaStream_t st) {
+    std::pair<cudaEvent_t, cudaEvent_t> p;
+    if (!g_ev_free.empty()) { p = g_ev_free.back(); g_ev_free.pop_back(); }
+    else { cudaEventCreate(&p.first); cudaEventCreate(&p.second); }
+    cudaEventRecord(p.first, st);
+    g_ev_busy.push_back(p);
+}
+void launch_timer_end(cudaStream_t st, uint64_t cells) {
+    cudaEventRecord(g_ev_busy.back().second, st);
+    g_ev_cells.push_back(cells);
+}
+void launch_timer_flush() {
+    for (size_t i = 0; i < g_ev_busy.size(); i++) {
+        cudaEventSynchronize(g_ev_busy[i].second);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_ev_busy[i].first, g_ev_busy[i].second);
+        g_times.dense_kernel_ms += ms; g_times.dense_kernel_launches++; g_times.dense_kernel_cells += g_ev_cells[i];
+        g_ev_free.push_back(g_ev_busy[i]);
+    }
+    g_ev_busy.clear(); g_ev_cells.clear();
+}
+
 void RowStore::release() {
     cudaFree(d_desc); d_desc = nullptr;
     cudaFree(pool.base); pool = DensePool();
@@ -181,7 +205,9 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     {
         EvTimer tm(st, &g_times.dense_ms);
         for (uint32_t s = 0; s < steps; s++) {
-            ST_TRY(dense_forward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), nullptr));
+            uint64_t live = 0;  // jobs that (may) compute row s: the algorithmic cells of this launch
+            for (uint32_t j = 0; j < J; j++) live += s < nd_max[j];
+            ST_TRY(dense_forward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), live * N));
             if (kind == DBGPHMM_FWD_SPARSE_RATIO) {
                 // top_nodes_by_score_ratio of row s for every job still dense (forward.rs:112-116)
                 uint32_t nr = 0;
@@ -195,6 +221,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
                 CUDA_TRY(cudaStreamSynchronize(st));  // reqs is reused next step
             }
         }
+        launch_timer_flush();
         if (kind == DBGPHMM_FWD_SPARSE_RATIO) {
             CUDA_TRY(cudaMemcpyAsync(out->nd.data(), b_nd.p, sizeof(uint32_t) * J, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -299,8 +326,12 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
 
     auto dense_phase = [&]() -> int {
         EvTimer tm(st, &g_times.dense_ms);
-        for (uint32_t s = 0; s < steps; s++)
-            ST_TRY(dense_backward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), nullptr));
+        for (uint32_t s = 0; s < steps; s++) {
+            uint64_t live = 0;
+            for (uint32_t j = 0; j < J; j++) live += s < out->nd[j];
+            ST_TRY(dense_backward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), live * N));
+        }
+        launch_timer_flush();
         for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
         return DBGPHMM_OK;
     };

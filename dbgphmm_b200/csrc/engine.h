@@ -66,7 +66,17 @@ struct EvTimer {  // accumulates the device time between construction and destru
     }
 };
 
-struct EngineTimes { double dense_ms = 0, sparse_ms = 0, product_ms = 0, total_ms = 0; uint64_t dense_cells = 0; };
+struct EngineTimes {
+    double dense_ms = 0, sparse_ms = 0, product_ms = 0, total_ms = 0;
+    uint64_t dense_cells = 0;
+    double dense_kernel_ms = 0;        // sum of the k_dense_fwd / k_dense_bwd launch durations (CUDA events around each launch)
+    uint64_t dense_kernel_launches = 0;
+    uint64_t dense_kernel_cells = 0;   // cells those launches computed
+};
+// Event pairs around individual launches, resolved lazily (no sync per launch).
+void launch_timer_begin(cudaStream_t st);
+void launch_timer_end(cudaStream_t st, uint64_t cells);
+void launch_timer_flush();
 extern EngineTimes g_times;
 
 int upload_mappings(dbgphmm_model* m, const dbgphmm_mappings* mp, DevMappings* out);

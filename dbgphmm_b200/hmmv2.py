@@ -48,7 +48,7 @@ SYMBOLS = [
     "dbgphmm_tables_row_info", "dbgphmm_tables_row_export", "dbgphmm_tables_row_top_nodes",
     "dbgphmm_output_node_freqs", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
     "dbgphmm_run_node_freqs_dev", "dbgphmm_generate_mappings", "dbgphmm_launch_count", "dbgphmm_last_timing",
-    "dbgphmm_reads_to_device",
+    "dbgphmm_reads_to_device", "dbgphmm_last_dense_kernel",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def lib():
     L.dbgphmm_generate_mappings.argtypes = [vp, vp, vp, ci, C.POINTER(vp)]
     L.dbgphmm_launch_count.argtypes = [ci]; L.dbgphmm_launch_count.restype = u64
     L.dbgphmm_last_timing.argtypes = [vp, C.POINTER(u64)]
+    L.dbgphmm_last_dense_kernel.argtypes = [C.POINTER(dbl), C.POINTER(u64), C.POINTER(u64)]
     for s in SYMBOLS:
         getattr(L, s)  # fail loudly if the library does not export a declared symbol
     _lib = L
@@ -130,6 +131,13 @@ def last_timing():
     cells = C.c_uint64(0)
     lib().dbgphmm_last_timing(ms, C.byref(cells))
     return ms[0], ms[1], ms[2], ms[3], int(cells.value)
+
+
+def last_dense_kernel():
+    """(summed ms, launches, cells) of the dense row-step kernel launches of the last bulk call."""
+    ms = C.c_double(0); n = C.c_uint64(0); cells = C.c_uint64(0)
+    lib().dbgphmm_last_dense_kernel(C.byref(ms), C.byref(n), C.byref(cells))
+    return ms.value, int(n.value), int(cells.value)
 
 
 def params_uniform(p):

@@ -179,6 +179,9 @@ uint64_t dbgphmm_launch_count(int reset);
 /* Milliseconds of the last bulk call spent in {dense kernels, sparse kernels, product kernels, total},
  * measured with CUDA events on the library's stream; and the algorithmic cell count of the dense kernels. */
 int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells);
+/* The dominant kernel (dense forward/backward row step) of the last bulk call: summed launch durations from CUDA
+ * events recorded around every launch on the library's stream, number of launches, and the cells they computed. */
+int dbgphmm_last_dense_kernel(double* ms, uint64_t* launches, uint64_t* cells);
 /* Upload-free variant for benchmarking: move a reads handle's bases to the device once (idempotent). */
 int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r);
 
