@@ -127,7 +127,7 @@ extern "C" int dbgphmm_forward(dbgphmm_model* m, const uint8_t* bases, uint64_t 
     t->dir = 0; t->kind = kind;
     std::vector<HJob> jobs; DevMappings dmap;
     int st = one_job(m, bases, n, mapping, read_index, t, &jobs, &dmap, kind == DBGPHMM_FWD_MAPPING);
-    if (st == DBGPHMM_OK) st = run_forward(m, jobs, t->d_bases, kind, true, true, kind == DBGPHMM_FWD_MAPPING ? &dmap : nullptr, &t->store);
+    if (st == DBGPHMM_OK) st = run_forward(m, jobs, t->d_bases, kind, PhaseOpts(), kind == DBGPHMM_FWD_MAPPING ? &dmap : nullptr, &t->store);
     if (st == DBGPHMM_OK) st = tables_finish(t);
     dmap.release();
     if (st != DBGPHMM_OK) { dbgphmm_tables_destroy(t); return st; }
@@ -142,7 +142,7 @@ extern "C" int dbgphmm_backward(dbgphmm_model* m, const uint8_t* bases, uint64_t
     t->dir = 1; t->kind = kind;
     std::vector<HJob> jobs; DevMappings dmap;
     int st = one_job(m, bases, n, mapping, read_index, t, &jobs, &dmap, kind == DBGPHMM_BWD_MAPPING);
-    if (st == DBGPHMM_OK) st = run_backward(m, jobs, t->d_bases, kind, true, kind == DBGPHMM_BWD_MAPPING ? &dmap : nullptr, fwd ? &fwd->store : nullptr, &t->store);
+    if (st == DBGPHMM_OK) st = run_backward(m, jobs, t->d_bases, kind, PhaseOpts(), kind == DBGPHMM_BWD_MAPPING ? &dmap : nullptr, fwd ? &fwd->store : nullptr, &t->store);
     if (st == DBGPHMM_OK) st = tables_finish(t);
     dmap.release();
     if (st != DBGPHMM_OK) { dbgphmm_tables_destroy(t); return st; }
@@ -357,7 +357,8 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
     for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535)) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         RowStore F;
-        st = run_forward(m, jobs, reads->d_bases, kind, false, false, mappings ? &dmap : nullptr, &F);
+        PhaseOpts so; so.keep_rows = false; so.store_sparse = false;
+        st = run_forward(m, jobs, reads->d_bases, kind, so, mappings ? &dmap : nullptr, &F);
         if (st == DBGPHMM_OK) for (size_t i = 0; i < jobs.size(); i++) per[bt.first + i] = xlog(F.h_final[i]);
         F.release();
         if (st != DBGPHMM_OK) break;
@@ -411,13 +412,50 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
     }
     if (cells) cells[0] = cells[1] = 0;
     int st = DBGPHMM_OK;
+    // Strategy.  "store": both directions keep every row of a batch, products afterwards (any mode, any read length).
+    // "stream" (run_sparse on graphs whose dense rows do not fit): dense rows live in two ping-pong slabs per read; the
+    // pairs (dense row, sparse row of the other direction) are taken on the fly, which costs one recomputation of the
+    // forward warm-up rows but decouples the batch size from the 28 B x N x 2W bytes a read's dense rows would need.
+    const uint64_t W = m->params.n_warmup;
+    bool can_stream = (mode == DBGPHMM_RUN_SPARSE) && !map_out && d_freqs;
+    uint64_t store_total = 0;
+    for (uint64_t r = 0; r < R; r++) { store_total += bytes[r]; if (all[r].len < 2 * W + 2) can_stream = false; }
+    bool stream = can_stream && store_total > m->mem_budget;
+    if (const char* e = getenv("DBGPHMM_STRATEGY")) { if (!strcmp(e, "stream")) stream = can_stream; else if (!strcmp(e, "store")) stream = false; }
+    if (stream) {
+        const uint64_t slab = dense_slab_bytes(m->N);
+        const uint64_t per_row = (uint64_t)m->params.n_active_nodes * 3 * 34 + 256 + 3 * sizeof(RowDesc);
+        for (uint64_t r = 0; r < R; r++) bytes[r] = 2 * slab + 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20);
+    }
     for (auto& bt : plan_batches(bytes, m->mem_budget, 65535)) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
+        HostTrace tr_b("batch");
         RowStore F, B;
-        st = run_forward(m, jobs, reads->d_bases, fk, true, true, with_map ? &dmap : nullptr, &F);
-        if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, true, with_map ? &dmap : nullptr, &F, &B);
-        if (st == DBGPHMM_OK && d_freqs) st = run_products_freqs(m, jobs, F, B, d_freqs);
-        if (st == DBGPHMM_OK && map_out) st = run_products_mapping(m, jobs, F, B, map_by_ratio, m->params.n_active_nodes, m->params.active_node_max_ratio, map_out);
+        if (!stream) {
+            PhaseOpts po;
+            st = run_forward(m, jobs, reads->d_bases, fk, po, with_map ? &dmap : nullptr, &F);
+            if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, po, with_map ? &dmap : nullptr, &F, &B);
+            if (st == DBGPHMM_OK && d_freqs) st = run_products_freqs(m, jobs, F, B, d_freqs);
+            if (st == DBGPHMM_OK && map_out) st = run_products_mapping(m, jobs, F, B, map_by_ratio, m->params.n_active_nodes, m->params.active_node_max_ratio, map_out);
+        } else {
+            DevBuf b_err;
+            st = b_err.alloc(sizeof(int));
+            if (st == DBGPHMM_OK && cudaMemsetAsync(b_err.p, 0, sizeof(int), m->stream) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
+            PhaseOpts pf; pf.keep_rows = false; pf.store_sparse = true;
+            if (st == DBGPHMM_OK) st = run_forward(m, jobs, reads->d_bases, fk, pf, nullptr, &F);                    // F: sparse rows stored
+            StepProducts spb; spb.other = &F; spb.P = F.d_final; spb.d_freqs = d_freqs; spb.d_err = b_err.as<int>();
+            PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = &spb;
+            if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);               // B dense x F sparse on the fly
+            if (st == DBGPHMM_OK) st = run_products_freqs(m, jobs, F, B, d_freqs);                                    // sparse x sparse, F sparse x b_init
+            RowStore F2;
+            StepProducts spf; spf.other = &B; spf.P = F.d_final; spf.d_freqs = d_freqs; spf.d_err = b_err.as<int>();
+            PhaseOpts p2; p2.keep_rows = false; p2.store_sparse = false; p2.dense_only = true; p2.step = &spf;
+            if (st == DBGPHMM_OK) st = run_forward(m, jobs, reads->d_bases, fk, p2, nullptr, &F2);                   // F dense (recomputed) x B sparse
+            F2.release();
+            int err = 0;
+            if (st == DBGPHMM_OK && cudaMemcpy(&err, b_err.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
+            if (st == DBGPHMM_OK && err) { dbg_set_error("P(read) == 0: emit probabilities are NaN in the reference (table.rs:500-505)"); st = DBGPHMM_ERR_ZERO_PROB; }
+        }
         if (st == DBGPHMM_OK) {
             for (size_t i = 0; i < jobs.size(); i++) {
                 if (h_logp_fwd) h_logp_fwd[bt.first + i] = xlog(F.h_final[i]);
@@ -425,7 +463,7 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
             }
             if (cells) { cells[0] += F.cells; cells[1] += B.cells; }
         }
-        F.release(); B.release();
+        { HostTrace tr_r("release"); F.release(); B.release(); }
         if (st != DBGPHMM_OK) break;
     }
     dmap.release();

@@ -2,10 +2,17 @@
 #pragma once
 #include "model.h"
 
-#define DENSE_CORE 1024     // nodes of a chunk owned by one CTA
-#define DENSE_LMAX 1280     // chunk + 6-hop halo capacity (shared memory: 84 B per local slot)
-#define DENSE_THREADS 256
-#define DENSE_SLOTS (DENSE_LMAX / DENSE_THREADS)
+#define DENSE_CORE 128      // nodes of a tile (owned by one warp of the common-frame kernel)
+#define DENSE_LMAX 160      // tile + 6-hop halo capacity
+#define DENSE_EMAX 256      // local upstream edges of one tile
+#define DENSE_XMAX 64       // of which beyond the first of each node ("extras")
+#define DENSE_THREADS 64    // exact (per-value exponent) kernel: one CTA per tile
+#define DENSE_SLOTS ((DENSE_LMAX + DENSE_THREADS - 1) / DENSE_THREADS)
+#define WT_WARPS 8          // common-frame kernel: warps (= tiles) per CTA
+#define WT_SLOTS (DENSE_LMAX / 32)
+#ifndef WT_MIN_CTAS
+#define WT_MIN_CTAS 2
+#endif
 #define SELECT_THREADS 1024
 #define SELECT_CAP 4096     // candidates resolved in shared memory by the top-k selection
 
@@ -40,9 +47,11 @@ static inline uint64_t dense_slab_bytes(uint32_t N) {
 int dense_configure(dbgphmm_model* m);
 // one forward / backward step `s` for all jobs (grid = chunks x jobs) followed by the row reduction.
 int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
-                       const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, uint64_t step_cells);
+                       const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, unsigned long long* d_worklist,
+                       uint64_t step_cells);
 int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
-                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, uint64_t step_cells);
+                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, unsigned long long* d_worklist,
+                       uint64_t step_cells);
 
 // Top-k of merged (m+i+d) values of dense rows (PHMMTable::top_nodes / top_nodes_by_score_ratio on a dense
 // table, table.rs:127-149).  One CTA per request.

@@ -32,11 +32,49 @@ void launch_timer_flush() {
     g_ev_busy.clear(); g_ev_cells.clear();
 }
 
+struct CacheBlock { void* p; size_t bytes; int device; bool used; };
+static std::vector<CacheBlock> g_cache;
+void* cache_alloc(size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    if (bytes < (1u << 20)) { size_t c = 256; while (c < bytes) c <<= 1; bytes = c; }  // small blocks in power-of-two classes
+    int dev = 0; cudaGetDevice(&dev);
+    int best = -1;
+    for (size_t i = 0; i < g_cache.size(); i++) {
+        const CacheBlock& b = g_cache[i];
+        if (!b.used && b.device == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 + (1 << 20))
+            if (best < 0 || b.bytes < g_cache[best].bytes) best = (int)i;
+    }
+    if (best >= 0) { g_cache[best].used = true; return g_cache[best].p; }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        cache_trim();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    g_cache.push_back(CacheBlock{p, bytes, dev, true});
+    return p;
+}
+void cache_free(void* p) {
+    if (!p) return;
+    for (auto& b : g_cache) if (b.p == p) { b.used = false; return; }
+    cudaFree(p);
+}
+void cache_trim() {
+    int dev = 0; cudaGetDevice(&dev);
+    std::vector<CacheBlock> keep;
+    for (auto& b : g_cache) {
+        if (!b.used && b.device == dev) cudaFree(b.p);
+        else keep.push_back(b);
+    }
+    g_cache.swap(keep);
+}
+
 void RowStore::release() {
-    cudaFree(d_desc); d_desc = nullptr;
-    cudaFree(pool.base); pool = DensePool();
-    cudaFree(arena.base); cudaFree(arena.cursor); arena = SparseArena();
-    cudaFree(d_final); d_final = nullptr;
+    cache_free(d_desc); d_desc = nullptr;
+    cache_free(d_desc0); d_desc0 = nullptr;
+    cache_free(pool.base); pool = DensePool();
+    cache_free(arena.base); cache_free(arena.cursor); arena = SparseArena();
+    cache_free(d_final); d_final = nullptr;
 }
 void DevMappings::release() { cudaFree(row_off); cudaFree(nodes); row_off = nullptr; nodes = nullptr; }
 
@@ -100,16 +138,18 @@ static int alloc_pool(DensePool& pool, uint32_t N, uint64_t n_slabs) {
     pool.slab_bytes = dense_slab_bytes(N);
     pool.n_slabs = n_slabs;
     if (n_slabs == 0) { pool.base = nullptr; return DBGPHMM_OK; }
-    if (cudaMalloc((void**)&pool.base, pool.slab_bytes * n_slabs) != cudaSuccess) {
-        cudaGetLastError(); pool.base = nullptr;
+    pool.base = (char*)cache_alloc(pool.slab_bytes * n_slabs);
+    if (!pool.base) {
         dbg_set_error("out of device memory for dense rows"); return DBGPHMM_ERR_OOM;
     }
     return DBGPHMM_OK;
 }
 static int alloc_arena(SparseArena& a, uint64_t bytes, cudaStream_t st) {
     a.bytes = bytes;
-    if (cudaMalloc((void**)&a.base, bytes ? bytes : 256) != cudaSuccess) { cudaGetLastError(); a.base = nullptr; dbg_set_error("out of device memory for sparse rows"); return DBGPHMM_ERR_OOM; }
-    CUDA_TRY(cudaMalloc((void**)&a.cursor, sizeof(unsigned long long)));
+    a.base = (char*)cache_alloc(bytes ? bytes : 256);
+    if (!a.base) { dbg_set_error("out of device memory for sparse rows"); return DBGPHMM_ERR_OOM; }
+    a.cursor = (unsigned long long*)cache_alloc(sizeof(unsigned long long));
+    if (!a.cursor) { dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
     CUDA_TRY(cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), st));
     return DBGPHMM_OK;
 }
@@ -160,17 +200,24 @@ static uint64_t arena_estimate(uint64_t n_rows, uint32_t n_active, bool ratio) {
 }
 
 // ================================================================================================ forward
-int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, bool keep_rows, bool store_sparse,
+int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,
                 const DevMappings* dmap, RowStore* out) {
+    const bool keep_rows = opt.keep_rows, store_sparse = opt.store_sparse;
+    HostTrace tr_all("run_forward");
+    HostTrace* tr_setup = new HostTrace("  fwd setup");
     cudaStream_t st = m->stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup;
-    out->dir = 0;
+    out->dir = 0; out->dense_kept = keep_rows;
     out->desc0.resize(J); out->len.resize(J); out->nd.assign(J, 0); out->h_final.assign(J, xf_zero());
     uint64_t tot_rows = 0;
     for (uint32_t j = 0; j < J; j++) { out->desc0[j] = tot_rows; out->len[j] = jobs[j].len; tot_rows += jobs[j].len; }
     out->n_desc = tot_rows;
-    CUDA_TRY(cudaMalloc((void**)&out->d_desc, sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1)));
-    CUDA_TRY(cudaMalloc((void**)&out->d_final, sizeof(XF) * std::max<uint32_t>(J, 1)));
+    out->d_desc = (RowDesc*)cache_alloc(sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1));
+    if (!out->d_desc) { dbg_set_error("out of device memory for row descriptors"); return DBGPHMM_ERR_OOM; }
+    out->d_final = (XF*)cache_alloc(sizeof(XF) * std::max<uint32_t>(J, 1));
+    out->d_desc0 = (uint64_t*)cache_alloc(sizeof(uint64_t) * std::max<uint32_t>(J, 1));
+    if (!out->d_final || !out->d_desc0) { dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
+    CUDA_TRY(cudaMemcpyAsync(out->d_desc0, out->desc0.data(), sizeof(uint64_t) * J, cudaMemcpyHostToDevice, st));
     // ---- dense phase layout
     std::vector<uint32_t> nd_max(J);
     std::vector<DJob> dj(J);
@@ -187,7 +234,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     }
     out->slab0.resize(J);
     for (uint32_t j = 0; j < J; j++) out->slab0[j] = dj[j].slab0;
-    ST_TRY(alloc_pool(out->pool, N, n_slabs));
+    { HostTrace t("  fwd alloc_pool"); ST_TRY(alloc_pool(out->pool, N, n_slabs)); }
     DevBuf b_dj, b_active, b_nd, b_len, b_part, b_top_ids, b_top_cnt, b_reqs;
     ST_TRY(dev_upload(b_dj, dj, st));
     std::vector<int> h_active(J, 1);
@@ -195,6 +242,8 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     ST_TRY(dev_upload(b_nd, nd_max, st));
     ST_TRY(dev_upload(b_len, out->len, st));
     ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * m->fwd.n_chunks));
+    DevBuf b_wl;
+    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * m->fwd.n_chunks + 1)));
     ST_TRY(b_top_ids.alloc(sizeof(uint32_t) * (size_t)J * MAX_ACTIVE));
     ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
     CUDA_TRY(cudaMemsetAsync(b_top_cnt.p, 0, sizeof(uint32_t) * J, st));
@@ -202,12 +251,15 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     std::vector<SelectReq> reqs(J);
     ST_TRY(b_reqs.alloc(sizeof(SelectReq) * J));
     auto slab_of_h = [&](uint32_t j, uint32_t s) { return dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    delete tr_setup;
     {
+        HostTrace t("  fwd dense phase");
         EvTimer tm(st, &g_times.dense_ms);
         for (uint32_t s = 0; s < steps; s++) {
             uint64_t live = 0;  // jobs that (may) compute row s: the algorithmic cells of this launch
             for (uint32_t j = 0; j < J; j++) live += s < nd_max[j];
-            ST_TRY(dense_forward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), live * N));
+            ST_TRY(dense_forward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));
+            if (opt.step) ST_TRY(step_products(m, *opt.step, out->pool, b_dj.as<DJob>(), J, s, 0));
             if (kind == DBGPHMM_FWD_SPARSE_RATIO) {
                 // top_nodes_by_score_ratio of row s for every job still dense (forward.rs:112-116)
                 uint32_t nr = 0;
@@ -226,6 +278,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
             CUDA_TRY(cudaMemcpyAsync(out->nd.data(), b_nd.p, sizeof(uint32_t) * J, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         } else out->nd = nd_max;
+        if (opt.dense_only) { HostTrace t2("  fwd dense_only tail"); CUDA_TRY(cudaStreamSynchronize(st)); cache_free(out->pool.base); out->pool.base = nullptr; return DBGPHMM_OK; }
         if (kind == DBGPHMM_FWD_SPARSE) {  // top_nodes(n_active) of the last dense row (forward.rs:115)
             uint32_t nr = 0;
             for (uint32_t j = 0; j < J; j++)
@@ -254,6 +307,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
         sj.push_back(s); sparse_rows += s.n_rows;
     }
     {
+        HostTrace t("  fwd sparse phase");
         EvTimer tm(st, &g_times.sparse_ms);
         ST_TRY(alloc_arena(out->arena, store_sparse ? arena_estimate(sparse_rows, m->params.n_active_nodes, kind == DBGPHMM_FWD_SPARSE_RATIO) : 256, st));
         SparseIO io{};
@@ -264,6 +318,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
         io.arena = out->arena.base; io.arena_bytes = out->arena.bytes; io.arena_cursor = out->arena.cursor; io.active = nullptr;
         ST_TRY(run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_FWD_MAPPING ? 64 : 256));
     }
+    if (!keep_rows) { cache_free(out->pool.base); out->pool.base = nullptr; }  // ping-pong slabs are dead now
     // final e of jobs whose last row is dense
     DevBuf b_take, b_desc0;
     ST_TRY(dev_upload(b_take, dense_final, st)); ST_TRY(dev_upload(b_desc0, out->desc0, st));
@@ -277,18 +332,24 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
 }
 
 // ================================================================================================ backward
-int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, bool keep_rows,
+int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,
                  const DevMappings* dmap, const RowStore* fwd, RowStore* out) {
+    const bool keep_rows = opt.keep_rows;
+    HostTrace tr_all("run_backward");
     cudaStream_t st = m->stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup;
-    out->dir = 1;
+    out->dir = 1; out->dense_kept = keep_rows;
     out->desc0.resize(J); out->len.resize(J); out->nd.assign(J, 0); out->h_final.assign(J, xf_zero());
     out->bdense_lo.assign(J, -1); out->bdense_hi.assign(J, -1);
     uint64_t tot_rows = 0;
     for (uint32_t j = 0; j < J; j++) { out->desc0[j] = tot_rows; out->len[j] = jobs[j].len; tot_rows += jobs[j].len; }
     out->n_desc = tot_rows;
-    CUDA_TRY(cudaMalloc((void**)&out->d_desc, sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1)));
-    CUDA_TRY(cudaMalloc((void**)&out->d_final, sizeof(XF) * std::max<uint32_t>(J, 1)));
+    out->d_desc = (RowDesc*)cache_alloc(sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1));
+    if (!out->d_desc) { dbg_set_error("out of device memory for row descriptors"); return DBGPHMM_ERR_OOM; }
+    out->d_final = (XF*)cache_alloc(sizeof(XF) * std::max<uint32_t>(J, 1));
+    out->d_desc0 = (uint64_t*)cache_alloc(sizeof(uint64_t) * std::max<uint32_t>(J, 1));
+    if (!out->d_final || !out->d_desc0) { dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
+    CUDA_TRY(cudaMemcpyAsync(out->d_desc0, out->desc0.data(), sizeof(uint64_t) * J, cudaMemcpyHostToDevice, st));
     // dense rows of job j: [lo, hi]; they are computed from hi down to lo
     std::vector<DJob> dj(J);
     uint64_t n_slabs = 0; uint32_t steps = 0;
@@ -314,28 +375,33 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     }
     out->slab0.resize(J);
     for (uint32_t j = 0; j < J; j++) out->slab0[j] = dj[j].slab0;
-    ST_TRY(alloc_pool(out->pool, N, n_slabs));
+    { HostTrace t("  bwd alloc_pool"); ST_TRY(alloc_pool(out->pool, N, n_slabs)); }
     DevBuf b_dj, b_len, b_part, b_top_ids, b_top_cnt, b_reqs;
     ST_TRY(dev_upload(b_dj, dj, st));
     ST_TRY(dev_upload(b_len, out->len, st));
     ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * m->bwd.n_chunks));
+    DevBuf b_wl;
+    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * m->bwd.n_chunks + 1)));
     ST_TRY(b_top_ids.alloc(sizeof(uint32_t) * (size_t)J * MAX_ACTIVE));
     ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
     CUDA_TRY(cudaMemsetAsync(b_top_cnt.p, 0, sizeof(uint32_t) * J, st));
     auto slab_of_h = [&](uint32_t j, uint32_t s) { return dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
 
     auto dense_phase = [&]() -> int {
+        HostTrace t("  bwd dense phase");
         EvTimer tm(st, &g_times.dense_ms);
         for (uint32_t s = 0; s < steps; s++) {
             uint64_t live = 0;
             for (uint32_t j = 0; j < J; j++) live += s < out->nd[j];
-            ST_TRY(dense_backward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), live * N));
+            ST_TRY(dense_backward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));
+            if (opt.step) ST_TRY(step_products(m, *opt.step, out->pool, b_dj.as<DJob>(), J, s, 1));
         }
         launch_timer_flush();
         for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
         return DBGPHMM_OK;
     };
     auto sparse_phase = [&]() -> int {
+        HostTrace t("  bwd sparse phase");
         EvTimer tm(st, &g_times.sparse_ms);
         std::vector<SJob> sj;
         uint64_t sparse_rows = 0;
@@ -397,6 +463,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
         }
         ST_TRY(dense_phase());
     }
+    if (!keep_rows) { cache_free(out->pool.base); out->pool.base = nullptr; }
     // final mb: row 0 is dense whenever dense rows reach row 0
     std::vector<uint8_t> dense_final(J, 0);
     for (uint32_t j = 0; j < J; j++) dense_final[j] = (out->bdense_lo[j] == 0);

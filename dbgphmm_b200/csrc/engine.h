@@ -25,27 +25,35 @@ struct RowStore {
     RowDesc* d_desc = nullptr;       // [sum len]
     uint64_t n_desc = 0;
     std::vector<uint64_t> desc0;     // per job
+    uint64_t* d_desc0 = nullptr;     // device copy of desc0
     std::vector<uint32_t> len;       // per job
     std::vector<uint32_t> nd;        // per job: number of dense rows (forward: rows [0,nd) ; backward: see engine.cu)
     std::vector<uint64_t> slab0;     // per job: first slab (forward row r -> slab0 + r ; backward row t -> slab0 + (hi - t)), kept rows only
     std::vector<int32_t> bdense_lo, bdense_hi;  // backward: dense rows are [lo, hi] (inclusive), -1/-1 if none
     DensePool pool;
     SparseArena arena;
+    bool dense_kept = true;          // false: dense rows were computed in ping-pong slabs and are gone
     XF* d_final = nullptr;           // per job: forward e(last) / backward mb(first)
     std::vector<XF> h_final;
     uint64_t cells = 0;
     void release();
 };
 
+// Caching allocator for the large row buffers (cudaMalloc / cudaFree of tens of GB cost ~100 ms each).
+void* cache_alloc(size_t bytes);   // nullptr on failure
+void cache_free(void* p);
+void cache_trim();                 // give every unused block back to the driver
+
 struct DevBuf {  // scoped device allocation
     void* p = nullptr;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) cache_free(p); }
     int alloc(size_t bytes) {
-        if (p) { cudaFree(p); p = nullptr; }
-        if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { p = nullptr; cudaGetLastError(); dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
+        if (p) { cache_free(p); p = nullptr; }
+        p = cache_alloc(bytes);
+        if (!p) { dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
         return DBGPHMM_OK;
     }
     template <class T> T* as() { return (T*)p; }
@@ -66,6 +74,14 @@ struct EvTimer {  // accumulates the device time between construction and destru
     }
 };
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+struct HostTrace {  // DBGPHMM_TRACE=1: wall-clock trace of host-side phases on stderr
+    const char* name; std::chrono::steady_clock::time_point t0; bool on;
+    HostTrace(const char* n) : name(n), t0(std::chrono::steady_clock::now()) { const char* e = getenv("DBGPHMM_TRACE"); on = e && e[0] == '1'; }
+    ~HostTrace() { if (on) fprintf(stderr, "[trace] %-28s %8.2f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
 struct EngineTimes {
     double dense_ms = 0, sparse_ms = 0, product_ms = 0, total_ms = 0;
     uint64_t dense_cells = 0;
@@ -79,11 +95,27 @@ void launch_timer_end(cudaStream_t st, uint64_t cells);
 void launch_timer_flush();
 extern EngineTimes g_times;
 
+// Products taken on the fly, right after a dense row has been computed, against the OTHER direction's stored sparse
+// row (forward row r pairs with backward row r+1, table.rs:500-505).  Lets the dense rows live in two ping-pong slabs.
+struct StepProducts {
+    const RowStore* other = nullptr;  // stored rows of the other direction
+    const XF* P = nullptr;            // device, per job: forward full probability
+    double* d_freqs = nullptr;        // device, ORIGINAL node order, added to
+    int* d_err = nullptr;             // device flag: some P == 0
+};
+struct PhaseOpts {
+    bool keep_rows = true;      // dense rows kept (true) or ping-pong (false)
+    bool store_sparse = true;   // sparse rows written to the arena
+    bool dense_only = false;    // forward: stop after the dense rows (recompute pass)
+    const StepProducts* step = nullptr;
+};
+
 int upload_mappings(dbgphmm_model* m, const dbgphmm_mappings* mp, DevMappings* out);
-int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, bool keep_rows, bool store_sparse,
+int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,
                 const DevMappings* dmap, RowStore* out);
-int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, bool keep_rows,
+int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,
                  const DevMappings* dmap, const RowStore* fwd, RowStore* out);
+int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir);
 // sum over rows of F (x) B / P into d_freqs (device, ORIGINAL node order, added to); status ZERO_PROB if some P == 0
 int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, double* d_freqs);
 // per-base top nodes of the emit probabilities (hint.rs:124-142) appended to `out` (host Mappings, ORIGINAL ids)

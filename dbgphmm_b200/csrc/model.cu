@@ -8,6 +8,7 @@
 #include "model.h"
 #include "dense.h"
 #include "sparse.h"
+#include "engine.h"
 
 static thread_local std::string g_error;
 unsigned long long g_launch_count = 0;
@@ -74,8 +75,8 @@ static int upload(T** dptr, const std::vector<T>& h) {
 // up_off/up_node/up_eid: CSR of the upstream direction (parents for forward, children for backward).
 static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_off, const std::vector<uint32_t>& up_node,
                       const std::vector<uint32_t>& up_eid) {
-    std::vector<uint32_t> chunk_start, loc_base, loc_node, nle, le_off, le_eid;
-    std::vector<uint16_t> le_idx;
+    std::vector<uint32_t> chunk_start, loc_base, loc_node, nle, le_off, le_eid, fp_eid, fx_off, fx_eid;
+    std::vector<uint16_t> le_idx, fp_idx, fx_idx;
     std::vector<uint32_t> stamp(N, 0xffffffffu), lidx(N, 0);
     std::vector<uint32_t> local, depth_cnt(8);
     uint32_t start = 0, cidx = 0, max_local = 0;
@@ -105,6 +106,15 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
                 }
                 fb = fe; fe = local.size();
             }
+            if (ok) {  // the tile's edge list must fit as well
+                size_t n_edges_local = 0, n_need = 0;
+                for (int h = 0; h < HALO_HOPS; h++) n_need += depth_cnt[h];
+                for (size_t q = 0; q < n_need && q < local.size(); q++) n_edges_local += up_off[local[q] + 1] - up_off[local[q]];
+                if (n_edges_local > DENSE_EMAX) ok = false;
+                size_t n_extra = 0;
+                for (size_t q = 0; q < n_need && q < local.size(); q++) { uint32_t dg = up_off[local[q] + 1] - up_off[local[q]]; if (dg > 1) n_extra += dg - 1; }
+                if (n_extra > DENSE_XMAX) ok = false;
+            }
             if (ok) break;
             // undo stamps and retry with a smaller chunk
             for (uint32_t v : local) stamp[v] = 0xffffffffu;
@@ -120,10 +130,19 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
             uint32_t v = local[j];
             loc_node.push_back(v);
             le_off.push_back((uint32_t)le_idx.size());
-            if (j < n_need_edges)
-                for (uint32_t a = up_off[v]; a < up_off[v + 1]; a++) { le_idx.push_back((uint16_t)lidx[up_node[a]]); le_eid.push_back(up_eid[a]); }
+            fx_off.push_back((uint32_t)fx_idx.size());
+            uint16_t p0 = (uint16_t)j; uint32_t e0 = 0xffffffffu;
+            if (j < n_need_edges) {
+                for (uint32_t a = up_off[v]; a < up_off[v + 1]; a++) {
+                    le_idx.push_back((uint16_t)lidx[up_node[a]]); le_eid.push_back(up_eid[a]);
+                    if (a == up_off[v]) { p0 = (uint16_t)lidx[up_node[a]]; e0 = up_eid[a]; }
+                    else { fx_idx.push_back((uint16_t)lidx[up_node[a]]); fx_eid.push_back(up_eid[a]); }
+                }
+            }
+            fp_idx.push_back(p0); fp_eid.push_back(e0);
         }
         le_off.push_back((uint32_t)le_idx.size());  // sentinel of this chunk
+        fx_off.push_back((uint32_t)fx_idx.size());
         max_local = std::max<uint32_t>(max_local, (uint32_t)local.size());
         for (uint32_t v : local) stamp[v] = 0xffffffffu;  // a node may be halo of several chunks
         start += size;
@@ -142,12 +161,15 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
     ST_TRY(upload(&P.le_off, le_off));
     ST_TRY(upload(&P.le_idx, le_idx));
     ST_TRY(upload(&P.le_eid, le_eid));
+    ST_TRY(upload(&P.fp_idx, fp_idx)); ST_TRY(upload(&P.fp_eid, fp_eid));
+    ST_TRY(upload(&P.fx_off, fx_off)); ST_TRY(upload(&P.fx_idx, fx_idx)); ST_TRY(upload(&P.fx_eid, fx_eid));
     return DBGPHMM_OK;
 }
 
 static void free_plan(DevPlan& P) {
     cudaFree(P.chunk_start); cudaFree(P.loc_base); cudaFree(P.loc_node); cudaFree(P.nle);
     cudaFree(P.le_off); cudaFree(P.le_idx); cudaFree(P.le_eid);
+    cudaFree(P.fp_idx); cudaFree(P.fp_eid); cudaFree(P.fx_off); cudaFree(P.fx_idx); cudaFree(P.fx_eid);
     P = DevPlan();
 }
 
@@ -241,6 +263,7 @@ void model_free(dbgphmm_model* m) {
     cudaFree(m->d_chi_off); cudaFree(m->d_chi_node); cudaFree(m->d_chi_eid);
     cudaFree(m->d_init); cudaFree(m->d_trans);
     free_plan(m->fwd); free_plan(m->bwd);
+    cache_trim();
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }

@@ -38,6 +38,12 @@ struct DevPlan {
     uint32_t* le_off = nullptr;       // [loc_total + n_chunks] per-slot offset into le_idx/le_eid (chunk c uses base loc_base[c]+c)
     uint16_t* le_idx = nullptr;       // local slot of the upstream neighbour
     uint32_t* le_eid = nullptr;       // original EdgeIndex of that edge (indexes trans)
+    // the same adjacency split for the common-frame kernel: first upstream neighbour inline, the rest ("extras") in a CSR
+    uint16_t* fp_idx = nullptr;       // [loc_total] local slot of the first upstream neighbour (own slot if none)
+    uint32_t* fp_eid = nullptr;       // [loc_total] its EdgeIndex, 0xffffffff if none
+    uint32_t* fx_off = nullptr;       // [loc_total + n_chunks] offsets of the extra upstream edges (chunk c uses base loc_base[c]+c)
+    uint16_t* fx_idx = nullptr;
+    uint32_t* fx_eid = nullptr;
     std::vector<uint32_t> h_chunk_start;
 };
 
@@ -48,6 +54,7 @@ struct dbgphmm_model {
     dbgphmm_params params;  // logs, as given
     LinParams lin;          // linear
     uint64_t mem_budget = 0;
+    int n_sm = 148;
     cudaStream_t stream = nullptr;
 
     // host copies (relabelled ids unless noted)

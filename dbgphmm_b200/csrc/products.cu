@@ -15,6 +15,7 @@ struct ProdCtx {
     uint64_t fslab_bytes, bslab_bytes;
     uint32_t fNp, bNp;
     const XF* P;  // per job: forward full prob
+    int f_dense_ok, b_dense_ok;  // 0: the dense rows of that direction were not kept (their pairs are taken on the fly)
     const uint32_t* orig_of;
     double p_end;
     uint32_t N;
@@ -57,6 +58,7 @@ __global__ void k_prod_rows_freq(ProdCtx C, double* __restrict__ freq, int* __re
     RowDesc br;
     if (r + 1 < C.len[j]) br = C.bdesc[C.bdesc0[j] + r + 1]; else { br.kind = 3; br.n_ent = 0; br.n_mi = 0; br.n_d = 0; br.off = 0; }
     if (fr.kind == ROW_DENSE && br.kind != ROW_SPARSE) return;  // dense x dense: k_prod_dense_freq
+    if ((fr.kind == ROW_DENSE && !C.f_dense_ok) || (br.kind == ROW_DENSE && !C.b_dense_ok)) return;  // taken by step_products
     const RowView F = view_row(fr, C.farena, C.fpool, C.fslab_bytes, C.fNp);
     const RowView B = view_row(br, C.barena, C.bpool, C.bslab_bytes, C.bNp);
     __shared__ uint32_t sh_ids[PROD_MAXE];
@@ -113,6 +115,7 @@ __global__ void k_map_rows(ProdCtx C, int by_ratio, uint32_t n_active, double ra
     RowDesc br;
     if (r + 1 < C.len[j]) br = C.bdesc[C.bdesc0[j] + r + 1]; else { br.kind = 3; br.n_ent = 0; br.n_mi = 0; br.n_d = 0; br.off = 0; }
     if (fr.kind == ROW_DENSE && br.kind != ROW_SPARSE) return;  // dense x dense handled through dense_select
+    if ((fr.kind == ROW_DENSE && !C.f_dense_ok) || (br.kind == ROW_DENSE && !C.b_dense_ok)) return;
     const RowView F = view_row(fr, C.farena, C.fpool, C.fslab_bytes, C.fNp);
     const RowView B = view_row(br, C.barena, C.bpool, C.bslab_bytes, C.bNp);
     __shared__ uint32_t sh_ids[PROD_MAXE];
@@ -204,6 +207,42 @@ __global__ void k_map_dense_emit(ProdCtx C, const DensePair* __restrict__ pairs,
     }
 }
 
+// ---- on-the-fly products of a dense row that lives in a ping-pong slab with the other direction's stored sparse row
+__global__ void k_prod_step(const DJob* __restrict__ jobs, uint32_t s, int dir, const char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np,
+                            const RowDesc* __restrict__ odesc, const uint64_t* __restrict__ odesc0, const char* __restrict__ oarena,
+                            const XF* __restrict__ Pj, const uint32_t* __restrict__ orig_of, double* __restrict__ freq, int* __restrict__ err) {
+    const DJob jb = jobs[blockIdx.x];
+    if (s >= jb.n_steps) return;
+    const int row = dir == 0 ? jb.first_row + (int)s : jb.first_row - (int)s;
+    const int orow = dir == 0 ? row + 1 : row - 1;       // forward row r <-> backward row r+1
+    if (orow < 0 || orow >= (int)jb.len) return;
+    const RowDesc orr = odesc[odesc0[blockIdx.x] + orow];
+    if (orr.kind != ROW_SPARSE) return;
+    const XF P = Pj[blockIdx.x];
+    if (P.v == 0.0) { if (threadIdx.x == 0) *err = 1; return; }
+    const uint64_t slab = jb.slab0 + (jb.slab_mod ? (s % jb.slab_mod) : s);
+    const char* sl = pool + slab * slab_bytes;
+    const double* gm = (const double*)sl; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
+    const char* pay = oarena + orr.off;
+    const double* sm = (const double*)pay; const double* si = sm + orr.n_ent; const double* sd = si + orr.n_ent;
+    const uint32_t* sid = (const uint32_t*)(sd + orr.n_ent); const int* sex = (const int*)(sid + orr.n_ent);
+    for (uint32_t e = threadIdx.x; e < orr.n_ent; e += blockDim.x) {
+        uint32_t id = sid[e];
+        double v = sm[e] * gm[id] + si[e] * gi[id] + sd[e] * gd[id];
+        if (v > 0.0) {
+            double w = (v / P.v) * pow2i(sex[e] + ge[id] - P.e);
+            if (w > 0.0) atomicAdd(&freq[orig_of[id]], w);
+        }
+    }
+}
+int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir) {
+    if (!sp.other->d_desc0) { dbg_set_error("step_products: the other direction has no device row index"); return DBGPHMM_ERR_INVALID; }
+    k_prod_step<<<n_jobs, 128, 0, m->stream>>>(d_jobs, s, dir, pool.base, pool.slab_bytes, pool.Np, sp.other->d_desc, sp.other->d_desc0,
+                                               sp.other->arena.base, sp.P, m->d_orig_of, sp.d_freqs, sp.d_err);
+    COUNT_LAUNCH();
+    return DBGPHMM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ProdBufs { DevBuf fdesc0, bdesc0, len, pairs, err; };
 
@@ -215,12 +254,13 @@ static int make_ctx(dbgphmm_model* m, const RowStore& F, const RowStore& B, Prod
     C->fdesc = F.d_desc; C->bdesc = B.d_desc; C->fdesc0 = pb.fdesc0.as<uint64_t>(); C->bdesc0 = pb.bdesc0.as<uint64_t>(); C->len = pb.len.as<uint32_t>();
     C->farena = F.arena.base; C->barena = B.arena.base; C->fpool = F.pool.base; C->bpool = B.pool.base;
     C->fslab_bytes = F.pool.slab_bytes; C->bslab_bytes = B.pool.slab_bytes; C->fNp = F.pool.Np; C->bNp = B.pool.Np;
-    C->P = F.d_final; C->orig_of = m->d_orig_of; C->p_end = m->lin.p_end; C->N = m->N;
+    C->P = F.d_final; C->f_dense_ok = F.dense_kept; C->b_dense_ok = B.dense_kept; C->orig_of = m->d_orig_of; C->p_end = m->lin.p_end; C->N = m->N;
     return DBGPHMM_OK;
 }
 
 // (job, forward row r) pairs whose forward row r and backward row r+1 are both dense (or b_init)
 static void dense_pairs(const RowStore& F, const RowStore& B, std::vector<DensePair>& pairs, std::vector<uint64_t>* lin, const std::vector<uint64_t>& lin0) {
+    if (!F.dense_kept || !B.dense_kept) return;
     for (size_t j = 0; j < F.len.size(); j++) {
         uint32_t n = F.len[j], ndf = F.nd[j];
         int lo = B.bdense_lo[j], hi = B.bdense_hi[j];
@@ -237,6 +277,7 @@ static void dense_pairs(const RowStore& F, const RowStore& B, std::vector<DenseP
 }
 
 int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, double* d_freqs) {
+    HostTrace tr("run_products_freqs");
     cudaStream_t st = m->stream;
     EvTimer tm(st, &g_times.product_ms);
     const uint32_t J = (uint32_t)jobs.size();

@@ -222,6 +222,24 @@ def test_run_node_freqs_and_logp(H, mode):
         assert list(cells) == ref_cells
 
 
+def test_stream_strategy_matches_store_and_oracle(H, monkeypatch):
+    """run_sparse with dense rows in ping-pong slabs + on-the-fly products (the strategy used when N is large)."""
+    w = _dbg_case(9, n_reads=6)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(w.graph, par)
+    reads = w.reads
+    of, olf, olb = o.run_node_freqs(O.Reads(reads), "sparse", True, None)
+    res = {}
+    for strat in ("store", "stream"):
+        monkeypatch.setenv("DBGPHMM_STRATEGY", strat)
+        res[strat] = g.run_node_freqs(H.Reads(reads), "sparse", True, None)
+        gf, glf, glb, cells = res[strat]
+        assert close_log(glf, olf).all() and close_log(glb, olb).all()
+        assert np.allclose(gf, of, rtol=REL_TOL, atol=1e-12), (strat, np.abs(gf - of).max())
+    assert res["store"][3] == res["stream"][3]
+    assert np.allclose(res["store"][0], res["stream"][0], rtol=1e-12, atol=1e-15)
+
+
 def test_full_prob_reads_batched_over_candidates(H):
     """to_full_prob_reads for a batch of candidate copy-number vectors X (posterior.rs:504-515)."""
     w = _dbg_case(8, n_reads=5, k=16, p_err=0.003)

@@ -12,6 +12,7 @@ ap.add_argument("--read-len", type=int, default=10_000)
 ap.add_argument("--k", type=int, default=40)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--mode", default="sparse")
+ap.add_argument("--budget-gb", type=float, default=0)
 a = ap.parse_args()
 a.reads_per_gpu = a.reads
 t0 = time.time()
@@ -19,7 +20,7 @@ g, li, lt, reads = bench.make_inputs(a, 0, a.reads)
 print(f"inputs: N={g.n_nodes} E={g.n_edges} reads={len(reads)} built in {time.time()-t0:.1f}s", flush=True)
 par = H.params_uniform(0.001); par.n_warmup = a.k
 t0 = time.time()
-m = H.PHMMModel(g.src, g.dst, g.base, li, lt, par)
+m = H.PHMMModel(g.src, g.dst, g.base, li, lt, par, mem_budget_bytes=int(a.budget_gb * 2**30))
 print(f"model_create {time.time()-t0:.2f}s", flush=True)
 rd = H.Reads(reads)
 for rep in range(a.reps):
