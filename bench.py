@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-gpu", type=int, default=128)
+    ap.add_argument("--reads-per-gpu", type=int, default=512)
     ap.add_argument("--genome-len", type=int, default=1_000_000)
     ap.add_argument("--read-len", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=40)
@@ -150,6 +150,7 @@ def main():
     import torch
     import torch.distributed as dist
     from dbgphmm_b200 import hmmv2 as H
+    from dbgphmm_b200.dist import allreduce_results
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -160,7 +161,8 @@ def main():
     model = H.PHMMModel(g.src, g.dst, g.base, li, lt, par, device=local)
     N = g.n_nodes
     freqs = torch.zeros(N, dtype=torch.float64, device="cuda")
-    logp = torch.zeros(2, dtype=torch.float64, device="cuda")
+    logp = torch.zeros(1, dtype=torch.float64, device="cuda")
+    lp_dev = torch.zeros(R, dtype=torch.float64, device="cuda")
     rd = H.Reads(reads)
     model.reads_to_device(rd)
     h2d = int(rd.total_bases() + rd.offsets.nbytes); d2h = int(N * 8 + 2 * R * 8)
@@ -173,13 +175,12 @@ def main():
     def step_resident():
         """inputs resident in HBM; device outputs; one all-reduce of node freqs + summed ln P."""
         freqs.zero_()
-        cells = model.run_node_freqs_dev(rd, "sparse", freqs.data_ptr())
+        cells = model.run_node_freqs_dev(rd, "sparse", freqs.data_ptr(), logp_fwd_ptr=lp_dev.data_ptr())
+        logp[0] = lp_dev.sum()
         ms = H.last_timing()[3]
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-        if world > 1:
-            dist.all_reduce(freqs)
-            dist.all_reduce(logp)
+        allreduce_results(freqs, logp, dist if world > 1 else None)   # one NCCL all-reduce of [N] freqs + summed ln P
         ev1.record(); torch.cuda.synchronize()
         return sum(cells), ms + ev0.elapsed_time(ev1)
 

@@ -1,0 +1,121 @@
+// dbgphmm_b200.hpp — C++ host-side mirror of the reference's `impl PHMMModel` / `impl PHMMOutput` (src/hmmv2) over the
+// C ABI of dbgphmm_b200.h.  Header only; same method names and argument meaning as the Rust methods; where the reference
+// panics this throws dbgphmm::Error.  The reference is compiled Rust and no Rust toolchain exists in this image, so this
+// is the compiled-language host layer (see INTEGRATION.md for the Rust shim a maintainer would add).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "dbgphmm_b200.h"
+
+namespace dbgphmm {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int st) : std::runtime_error(dbgphmm_last_error()), status(st) {}
+};
+inline void check(int st) { if (st != DBGPHMM_OK) throw Error(st); }
+
+using PHMMParams = dbgphmm_params;
+inline PHMMParams uniform(double p) { PHMMParams q; dbgphmm_params_uniform(p, &q); return q; }   // params.rs:116
+
+class Reads {  // ReadCollection (common/collection.rs:131)
+public:
+    explicit Reads(const std::vector<std::string>& seqs) {
+        std::vector<uint64_t> off(1, 0); std::string all;
+        for (auto& s : seqs) { all += s; off.push_back(all.size()); }
+        check(dbgphmm_reads_create(seqs.size(), off.data(), (const uint8_t*)all.data(), &h_));
+    }
+    ~Reads() { dbgphmm_reads_destroy(h_); }
+    Reads(const Reads&) = delete; Reads& operator=(const Reads&) = delete;
+    dbgphmm_reads* handle() const { return h_; }
+private:
+    dbgphmm_reads* h_ = nullptr;
+};
+
+class Mappings {  // hint.rs:150-152
+public:
+    explicit Mappings(dbgphmm_mappings* h) : h_(h) {}
+    ~Mappings() { dbgphmm_mappings_destroy(h_); }
+    Mappings(const Mappings&) = delete; Mappings& operator=(const Mappings&) = delete;
+    dbgphmm_mappings* handle() const { return h_; }
+    std::vector<double> to_node_freqs(uint32_t n_nodes) const {  // hint.rs:161
+        std::vector<double> f(n_nodes); check(dbgphmm_mappings_to_node_freqs(h_, n_nodes, f.data())); return f;
+    }
+private:
+    dbgphmm_mappings* h_;
+};
+
+class PHMMTables {  // table.rs:365-435
+public:
+    explicit PHMMTables(dbgphmm_tables* h) : h_(h) {}
+    ~PHMMTables() { dbgphmm_tables_destroy(h_); }
+    PHMMTables(const PHMMTables&) = delete; PHMMTables& operator=(const PHMMTables&) = delete;
+    uint64_t n_emissions() const { return dbgphmm_tables_len(h_); }
+    double full_prob() const { double v; check(dbgphmm_tables_full_prob(h_, &v)); return v; }   // table.rs:395
+    dbgphmm_tables* handle() const { return h_; }
+private:
+    dbgphmm_tables* h_;
+};
+
+class PHMMModel {  // hmmv2/common.rs:61-67
+public:
+    PHMMModel(const std::vector<uint32_t>& edge_src, const std::vector<uint32_t>& edge_dst, const std::vector<uint8_t>& emission,
+              const std::vector<double>& log_init, const std::vector<double>& log_trans, const PHMMParams& param, int device = 0,
+              uint64_t mem_budget = 0) : n_nodes_((uint32_t)emission.size()) {
+        check(dbgphmm_model_create(n_nodes_, (uint32_t)edge_src.size(), edge_src.data(), edge_dst.data(), emission.data(), log_init.data(),
+                                   log_trans.data(), &param, device, mem_budget, &h_));
+    }
+    ~PHMMModel() { dbgphmm_model_destroy(h_); }
+    PHMMModel(const PHMMModel&) = delete; PHMMModel& operator=(const PHMMModel&) = delete;
+    uint32_t n_nodes() const { return n_nodes_; }
+    // candidate copy-number assignments X -> parameter sets on the device (seq_graph.rs:160-273)
+    void set_copy_nums_batch(uint32_t n_batch, const uint32_t* copy_nums, int mode = 0) { check(dbgphmm_model_set_copy_nums_batch(h_, n_batch, copy_nums, mode)); }
+
+    std::unique_ptr<PHMMTables> forward(const std::string& x) { return fwd(x, DBGPHMM_FWD_DENSE); }                           // forward.rs:24
+    std::unique_ptr<PHMMTables> forward_sparse(const std::string& x, bool use_max_ratio) { return fwd(x, use_max_ratio ? DBGPHMM_FWD_SPARSE_RATIO : DBGPHMM_FWD_SPARSE); }  // :93
+    std::unique_ptr<PHMMTables> forward_with_mapping(const std::string& x, const Mappings& m, uint64_t i) { return fwd(x, DBGPHMM_FWD_MAPPING, &m, i); }  // :51
+    std::unique_ptr<PHMMTables> backward(const std::string& x) { return bwd(x, DBGPHMM_BWD_DENSE); }                          // backward.rs:24
+    std::unique_ptr<PHMMTables> backward_sparse(const std::string& x) { return bwd(x, DBGPHMM_BWD_SPARSE); }                  // :146
+    std::unique_ptr<PHMMTables> backward_with_mapping(const std::string& x, const Mappings& m, uint64_t i) { return bwd(x, DBGPHMM_BWD_MAPPING, &m, i); }  // :59
+    std::unique_ptr<PHMMTables> backward_by_forward(const std::string& x, const PHMMTables& f) { return bwd(x, DBGPHMM_BWD_BY_FORWARD, nullptr, 0, &f); }  // :101
+
+    // freq.rs:175-192 for every candidate X: returns ln P(R|X) [n_batch]
+    std::vector<double> to_full_prob_reads(const Reads& reads, const Mappings* mappings, bool use_max_ratio) {
+        std::vector<double> out(dbgphmm_model_n_batch(h_));
+        check(dbgphmm_to_full_prob_reads(h_, reads.handle(), mappings ? mappings->handle() : nullptr, use_max_ratio, out.data(), nullptr));
+        return out;
+    }
+    // run / run_sparse / run_sparse_adaptive / run_with_mapping (freq.rs:42-76) + to_node_freqs (freq.rs:245), summed over reads
+    std::vector<double> to_node_freqs(const Reads& reads, int run_mode, bool use_max_ratio = true, const Mappings* mappings = nullptr,
+                                      std::vector<double>* logp_fwd = nullptr) {
+        std::vector<double> f(n_nodes_);
+        if (logp_fwd) logp_fwd->resize(0);
+        check(dbgphmm_run_node_freqs(h_, reads.handle(), run_mode, use_max_ratio, mappings ? mappings->handle() : nullptr, f.data(), nullptr, nullptr, nullptr));
+        return f;
+    }
+    std::unique_ptr<Mappings> generate_mappings(const Reads& reads, const Mappings* mappings, bool use_max_ratio) {  // hint.rs:193
+        dbgphmm_mappings* out = nullptr;
+        check(dbgphmm_generate_mappings(h_, reads.handle(), mappings ? mappings->handle() : nullptr, use_max_ratio, &out));
+        return std::make_unique<Mappings>(out);
+    }
+    dbgphmm_model* handle() const { return h_; }
+
+private:
+    std::unique_ptr<PHMMTables> fwd(const std::string& x, int kind, const Mappings* m = nullptr, uint64_t i = 0) {
+        dbgphmm_tables* t = nullptr;
+        check(dbgphmm_forward(h_, (const uint8_t*)x.data(), x.size(), kind, m ? m->handle() : nullptr, i, &t));
+        return std::make_unique<PHMMTables>(t);
+    }
+    std::unique_ptr<PHMMTables> bwd(const std::string& x, int kind, const Mappings* m = nullptr, uint64_t i = 0, const PHMMTables* f = nullptr) {
+        dbgphmm_tables* t = nullptr;
+        check(dbgphmm_backward(h_, (const uint8_t*)x.data(), x.size(), kind, m ? m->handle() : nullptr, i, f ? f->handle() : nullptr, &t));
+        return std::make_unique<PHMMTables>(t);
+    }
+    dbgphmm_model* h_ = nullptr;
+    uint32_t n_nodes_;
+};
+
+}  // namespace dbgphmm
