@@ -447,11 +447,8 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
             PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = &spb;
             if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);               // B dense x F sparse on the fly
             if (st == DBGPHMM_OK) st = run_products_freqs(m, jobs, F, B, d_freqs);                                    // sparse x sparse, F sparse x b_init
-            RowStore F2;
             StepProducts spf; spf.other = &B; spf.P = F.d_final; spf.d_freqs = d_freqs; spf.d_err = b_err.as<int>();
-            PhaseOpts p2; p2.keep_rows = false; p2.store_sparse = false; p2.dense_only = true; p2.step = &spf;
-            if (st == DBGPHMM_OK) st = run_forward(m, jobs, reads->d_bases, fk, p2, nullptr, &F2);                   // F dense (recomputed) x B sparse
-            F2.release();
+            if (st == DBGPHMM_OK) st = run_forward_recompute(m, jobs, reads->d_bases, F, B, spf);                    // F dense (cone only) x B sparse
             int err = 0;
             if (st == DBGPHMM_OK && cudaMemcpy(&err, b_err.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
             if (st == DBGPHMM_OK && err) { dbg_set_error("P(read) == 0: emit probabilities are NaN in the reference (table.rs:500-505)"); st = DBGPHMM_ERR_ZERO_PROB; }

@@ -903,6 +903,15 @@ int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jo
     return DBGPHMM_OK;
 }
 
+int dense_forward_step_list(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t s, const uint8_t* d_bases,
+                            const RowDesc* d_desc, XF* d_partials, const unsigned long long* d_worklist) {
+    k_dense_fwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
+                                                                             nullptr, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks, d_worklist);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}
+
 int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
                         const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, unsigned long long* d_worklist,
                         uint64_t step_cells) {

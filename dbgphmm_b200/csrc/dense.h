@@ -53,6 +53,11 @@ int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
                         const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, unsigned long long* d_worklist,
                        uint64_t step_cells);
 
+// forward step restricted to the (job, tile) pairs of a prebuilt worklist (recompute pass of the stream strategy);
+// no row reduction: the rows' scalars are taken from the descriptors written by the first pass.
+int dense_forward_step_list(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t s, const uint8_t* d_bases,
+                            const RowDesc* d_desc, XF* d_partials, const unsigned long long* d_worklist);
+
 // Top-k of merged (m+i+d) values of dense rows (PHMMTable::top_nodes / top_nodes_by_score_ratio on a dense
 // table, table.rs:127-149).  One CTA per request.
 struct SelectReq {

@@ -477,3 +477,68 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;
 }
+
+// ================================================================================================ ROI recompute
+// mark[j][tile] = 1 for every tile in the dependency cone of the node sets of backward rows 1..W of job j
+__global__ void k_roi_mark(uint32_t W, const RowDesc* __restrict__ bdesc, const uint64_t* __restrict__ bdesc0, const uint32_t* __restrict__ len,
+                           const char* __restrict__ barena, const uint32_t* __restrict__ tile_of, const uint32_t* __restrict__ roi_off,
+                           const uint32_t* __restrict__ roi_tile, uint32_t n_tiles, unsigned char* __restrict__ mark) {
+    const uint32_t j = blockIdx.y, t = blockIdx.x + 1;   // backward row t pairs with forward row t-1 < W
+    if (t > W || t >= len[j]) return;
+    const RowDesc r = bdesc[bdesc0[j] + t];
+    if (r.kind != ROW_SPARSE) return;
+    const uint32_t* id = (const uint32_t*)(barena + r.off + 24ull * r.n_ent);
+    for (uint32_t e = threadIdx.x; e < r.n_ent; e += blockDim.x) {
+        uint32_t tl = tile_of[id[e]];
+        for (uint32_t a = roi_off[tl]; a < roi_off[tl + 1]; a++) mark[(size_t)j * n_tiles + roi_tile[a]] = 1;
+    }
+}
+__global__ void k_roi_compact(uint32_t n_jobs, uint32_t n_tiles, const unsigned char* __restrict__ mark, unsigned long long* __restrict__ worklist) {
+    const size_t total = (size_t)n_jobs * n_tiles;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        if (mark[i]) {
+            unsigned long long w = atomicAdd(worklist, 1ull);
+            worklist[1 + w] = ((unsigned long long)(i / n_tiles) << 32) | (unsigned long long)(i % n_tiles);
+        }
+}
+
+int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
+                          const StepProducts& sp) {
+    HostTrace tr("run_forward_recompute");
+    cudaStream_t st = m->stream;
+    const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup, T = m->fwd.n_chunks;
+    ST_TRY(model_ensure_roi(m));
+    EvTimer tm(st, &g_times.dense_ms);
+    std::vector<DJob> dj(J);
+    for (uint32_t j = 0; j < J; j++) {
+        DJob& d = dj[j];
+        d.x = jobs[j].x; d.len = jobs[j].len; d.base_off = jobs[j].base_off; d.n_steps = std::min<uint32_t>(jobs[j].len, W); d.first_row = 0;
+        d.prev0_kind = PREV_F_INIT; d.prev0_slab = 0; d.slab0 = 2ull * j; d.slab_mod = 2; d.desc0 = F.desc0[j]; d.active_idx = -1;
+    }
+    DensePool pool;
+    pool.Np = (N + 1) & ~1u; pool.slab_bytes = dense_slab_bytes(N); pool.n_slabs = 2ull * J;
+    DevBuf b_pool, b_dj, b_len, b_mark, b_wl, b_part;
+    ST_TRY(b_pool.alloc(pool.slab_bytes * pool.n_slabs)); pool.base = b_pool.as<char>();
+    ST_TRY(dev_upload(b_dj, dj, st)); ST_TRY(dev_upload(b_len, F.len, st));
+    ST_TRY(b_mark.alloc((size_t)J * T));
+    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * T + 1)));
+    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * T));
+    CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)J * T, st));
+    CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * pool.n_slabs, st));   // cells outside the cone read as zero
+    {
+        dim3 g(W, J);
+        k_roi_mark<<<g, 128, 0, st>>>(W, B.d_desc, B.d_desc0, b_len.as<uint32_t>(), B.arena.base, m->d_tile_of, m->d_roi_off, m->d_roi_tile, T,
+                                      b_mark.as<unsigned char>());
+        COUNT_LAUNCH();
+        k_roi_compact<<<4 * m->n_sm, 256, 0, st>>>(J, T, b_mark.as<unsigned char>(), b_wl.as<unsigned long long>());
+        COUNT_LAUNCH();
+    }
+    for (uint32_t s = 0; s < W; s++) {
+        ST_TRY(dense_forward_step_list(m, pool, b_dj.as<DJob>(), s, d_bases, F.d_desc, b_part.as<XF>(), b_wl.as<unsigned long long>()));
+        ST_TRY(step_products(m, sp, pool, b_dj.as<DJob>(), J, s, 0));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}

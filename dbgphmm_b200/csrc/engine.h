@@ -115,6 +115,10 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
                 const DevMappings* dmap, RowStore* out);
 int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,
                  const DevMappings* dmap, const RowStore* fwd, RowStore* out);
+// Recompute the forward warm-up rows only inside the dependency cone of the backward rows' sparse node sets and take the
+// (forward dense row, backward sparse row) products there.  F supplies the row scalars of the first pass.
+int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
+                          const StepProducts& sp);
 int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir);
 // sum over rows of F (x) B / P into d_freqs (device, ORIGINAL node order, added to); status ZERO_PROB if some P == 0
 int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, double* d_freqs);

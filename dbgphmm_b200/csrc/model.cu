@@ -255,9 +255,45 @@ int model_upload_probs(dbgphmm_model* m, const double* log_init, const double* l
     return DBGPHMM_OK;
 }
 
+int model_ensure_roi(dbgphmm_model* m) {
+    const uint32_t W = m->params.n_warmup;
+    if (m->d_roi_off && m->roi_warmup == W) return DBGPHMM_OK;
+    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of);
+    m->d_roi_off = m->d_roi_tile = m->d_tile_of = nullptr;
+    const std::vector<uint32_t>& cs = m->fwd.h_chunk_start;
+    const uint32_t T = m->fwd.n_chunks, N = m->N;
+    std::vector<uint32_t> tile_of(N);
+    for (uint32_t t = 0; t < T; t++) for (uint32_t v = cs[t]; v < cs[t + 1]; v++) tile_of[v] = t;
+    const uint32_t hops = HALO_HOPS * W;
+    std::vector<uint32_t> roi_off(1, 0), roi_tile, stamp(N, 0xffffffffu), tstamp(T, 0xffffffffu), frontier, next;
+    for (uint32_t t = 0; t < T; t++) {
+        frontier.clear();
+        for (uint32_t v = cs[t]; v < cs[t + 1]; v++) { stamp[v] = t; frontier.push_back(v); }
+        tstamp[t] = t; roi_tile.push_back(t);
+        for (uint32_t h = 0; h < hops && !frontier.empty(); h++) {
+            next.clear();
+            for (uint32_t v : frontier)
+                for (uint32_t a = m->par_off[v]; a < m->par_off[v + 1]; a++) {
+                    uint32_t u = m->par_node[a];
+                    if (stamp[u] != t) {
+                        stamp[u] = t; next.push_back(u);
+                        uint32_t tu = tile_of[u];
+                        if (tstamp[tu] != t) { tstamp[tu] = t; roi_tile.push_back(tu); }
+                    }
+                }
+            frontier.swap(next);
+        }
+        roi_off.push_back((uint32_t)roi_tile.size());
+    }
+    ST_TRY(upload(&m->d_roi_off, roi_off)); ST_TRY(upload(&m->d_roi_tile, roi_tile)); ST_TRY(upload(&m->d_tile_of, tile_of));
+    m->roi_warmup = W;
+    return DBGPHMM_OK;
+}
+
 void model_free(dbgphmm_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of);
     cudaFree(m->d_pos_of); cudaFree(m->d_orig_of); cudaFree(m->d_emission);
     cudaFree(m->d_par_off); cudaFree(m->d_par_node); cudaFree(m->d_par_eid);
     cudaFree(m->d_chi_off); cudaFree(m->d_chi_node); cudaFree(m->d_chi_eid);

@@ -73,7 +73,12 @@ struct dbgphmm_model {
     double* d_init = nullptr;   // [n_batch][N] linear, relabelled node order
     double* d_trans = nullptr;  // [n_batch][E] linear, original EdgeIndex order
     DevPlan fwd, bwd;
+    // Recompute support for the stream strategy: for every forward tile the tiles that intersect the upstream closure of
+    // its nodes within HALO_HOPS * n_warmup hops (the dependency cone of n_warmup dense rows), built lazily.
+    uint32_t roi_warmup = 0;
+    uint32_t *d_roi_off = nullptr, *d_roi_tile = nullptr, *d_tile_of = nullptr;
 };
+int model_ensure_roi(dbgphmm_model* m);
 
 struct dbgphmm_reads {
     uint64_t n_reads = 0;
