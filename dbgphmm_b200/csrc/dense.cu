@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include "dense.h"
 #include "engine.h"
 
@@ -17,6 +18,8 @@ struct PlanView {
     const uint32_t *chunk_start, *loc_base, *loc_node, *nle, *le_off, *le_eid;
     const uint16_t* le_idx;
     const uint16_t* fp_idx; const uint32_t* fp_eid; const uint32_t* fx_off; const uint16_t* fx_idx; const uint32_t* fx_eid;
+    const uint32_t* rl_node; const uint16_t* rl_par; const uint32_t* rl_eid; const uint8_t* rl_flag; const uint16_t* rl_core;
+    const uint32_t* rx_off; const uint16_t* rx_idx; const uint32_t* rx_eid;
 };
 struct GraphView {
     uint32_t N, E;
@@ -24,7 +27,8 @@ struct GraphView {
     const double *init, *trans;
     const uint32_t* orig_of;
 };
-static PlanView plan_view(const DevPlan& p) { return PlanView{p.chunk_start, p.loc_base, p.loc_node, p.nle, p.le_off, p.le_eid, p.le_idx, p.fp_idx, p.fp_eid, p.fx_off, p.fx_idx, p.fx_eid}; }
+static PlanView plan_view(const DevPlan& p) { return PlanView{p.chunk_start, p.loc_base, p.loc_node, p.nle, p.le_off, p.le_eid, p.le_idx, p.fp_idx, p.fp_eid, p.fx_off, p.fx_idx, p.fx_eid,
+                                                                   p.rl_node, p.rl_par, p.rl_eid, p.rl_flag, p.rl_core, p.rx_off, p.rx_idx, p.rx_eid}; }
 static GraphView graph_view(const dbgphmm_model* m) { return GraphView{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_orig_of}; }
 
 __device__ __forceinline__ uint64_t slab_of(const DJob& jb, uint32_t s) { return jb.slab0 + (jb.slab_mod ? (s % jb.slab_mod) : s); }
@@ -675,6 +679,383 @@ k_dense_warp(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ job
     }
 }
 
+// ------------------------------------------------------------------------------------------------ register-stencil kernel
+// Same step as k_dense_warp (one warp per tile, one exponent frame per tile, exact scalings), but every lane OWNS
+// RS_PER_LANE consecutive positions of the tile's register layout (model.cu: [chain above the tile head | core | rest of
+// the halo in chains]).  For almost every node the first upstream neighbour is the previous position, i.e. the lane's own
+// previous register or one shuffle from the lane below, so Match/Ins/Del need no shared-memory gathers; nodes whose
+// neighbour is elsewhere (bit 0 of rl_flag) or that have further upstream edges (bit 1) take an out-of-line path through
+// the position-indexed copies kept in shared memory.  All positions are computed in every round: cells whose inputs lie
+// outside the tile become garbage-but-finite and can reach the core only after more than 6 hops, i.e. never.
+#define RS_PER_LANE (DENSE_LMAX / 32)
+#define RS_SMEM_PER_WARP (DENSE_LMAX * (3 * 8 + 4))
+#define RS_SMEM_BYTES (WT_WARPS * RS_SMEM_PER_WARP)
+
+// (rs_slow is kept for reference; the kernel uses the inline irregular path + rs_extras)
+// full upstream sum of one position through shared memory: first neighbour (if in the tile) + extras
+__device__ __noinline__ double rs_slow(const uint16_t* __restrict__ rl_par, const uint32_t* __restrict__ rx_off, const uint16_t* __restrict__ rx_idx,
+                                       const uint32_t* __restrict__ rx_eid, const double* __restrict__ trans, uint32_t pidx, uint32_t xidx, double tr_first,
+                                       const double* a, const double* b, const double* c, double ca, double cb, double cc) {
+    double acc = 0.0;
+    const uint32_t p = rl_par[pidx];
+    if (p != 0xffffu) acc = tr_first * (ca * a[p] + cb * b[p] + cc * c[p]);
+    for (uint32_t e = rx_off[xidx], ee = rx_off[xidx + 1]; e < ee; e++) {
+        const int l = rx_idx[e];
+        acc += trans[rx_eid[e]] * (ca * a[l] + cb * b[l] + cc * c[l]);
+    }
+    return acc;
+}
+__device__ __noinline__ double rs_extras(const uint32_t* __restrict__ rx_off, const uint16_t* __restrict__ rx_idx, const uint32_t* __restrict__ rx_eid,
+                                         const double* __restrict__ trans, uint32_t xidx, const double* a, const double* b, const double* c,
+                                         double ca, double cb, double cc) {
+    double acc = 0.0;
+    for (uint32_t e = rx_off[xidx], ee = rx_off[xidx + 1]; e < ee; e++) {
+        const int l = rx_idx[e];
+        acc += trans[rx_eid[e]] * (ca * a[l] + cb * b[l] + cc * c[l]);
+    }
+    return acc;
+}
+#define RS_EXTRAS(k, A, B, C, ca, cb, cc) rs_extras(P.rx_off, P.rx_idx, P.rx_eid, trans, (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane + (k), (A), (B), (C), (ca), (cb), (cc))
+// add the lane's register-held extra contribution `xc` to slot k of arr (compile-time unrolled select)
+#define RS_ADD_X(arr, xc) do { if (tile_has_x) { _Pragma("unroll") for (int k_ = 0; k_ < RS_PER_LANE; k_++) arr[k_] += (k_ == xk) ? (xc) : 0.0; } } while (0)
+#define RS_IRR(k) ((flg >> (2 * (k))) & 1)
+#define RS_EXT(k) ((flg >> (2 * (k) + 1)) & 1)
+#define RS_SLOW(k, A, B, C, ca, cb, cc) rs_slow(P.rl_par, P.rx_off, P.rx_idx, P.rx_eid, trans, tbase + RS_PER_LANE * lane + (k), \
+                                               (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane + (k), tr[k], (A), (B), (C), (ca), (cb), (cc))
+// value of the first upstream neighbour when it is the previous position: own previous register, or lane-1's last one
+#define RS_UP(arr, k, fromlow) ((k) == 0 ? (fromlow) : arr[(k) > 0 ? (k) - 1 : 0])
+
+template <bool FWD>
+__global__ void __launch_bounds__(WT_WARPS * 32, WT_MIN_CTAS)
+k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs, uint32_t n_jobs, uint32_t s, const uint8_t* __restrict__ bases,
+            const RowDesc* __restrict__ desc, const int* __restrict__ active, char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np,
+            XF* __restrict__ partials, uint32_t n_tiles, int span, unsigned long long* __restrict__ worklist, uint32_t jpc) {
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c = blockIdx.x * WT_WARPS + warp;
+    if (c >= n_tiles) return;   // no block-wide barrier anywhere in this kernel
+    double* sa = (double*)(rs_raw + (size_t)warp * RS_SMEM_PER_WARP);
+    double* sb = sa + DENSE_LMAX; double* sc = sb + DENSE_LMAX; int* se = (int*)(sc + DENSE_LMAX);
+    const uint32_t tbase = c * DENSE_LMAX;
+    const int core0 = P.rl_core[2 * c], ncore = P.rl_core[2 * c + 1];
+    const uint32_t g0 = P.chunk_start[c];
+    // ---- tile structure: slot-major node ids for global IO, owned positions for the recurrences
+    uint32_t ion[RS_PER_LANE];
+    uint32_t own_node[RS_PER_LANE], own_eid[RS_PER_LANE];
+    unsigned int emc = 0, flg = 0;   // 3-bit base codes and 2-bit flags of the owned positions
+    int ppos[RS_PER_LANE];           // position of the first upstream neighbour (used when it is not the previous position)
+#pragma unroll
+    for (int q = 0; q < RS_PER_LANE; q++) ion[q] = P.rl_node[tbase + 32 * q + lane];
+#pragma unroll
+    for (int k = 0; k < RS_PER_LANE; k++) {
+        const uint32_t pi_ = tbase + RS_PER_LANE * lane + k;
+        own_node[k] = P.rl_node[pi_]; own_eid[k] = P.rl_eid[pi_];
+        unsigned int code = 4;
+        if (own_node[k] != 0xffffffffu) { unsigned char ch = G.emission[own_node[k]]; code = ch == 'n' ? 4 : ((ch >> 1) & 3); }
+        emc |= code << (3 * k);
+        flg |= (unsigned int)(P.rl_flag[pi_] & 3) << (2 * k);
+        { const uint32_t pp = P.rl_par[pi_]; ppos[k] = pp == 0xffffu ? 0 : (int)pp; }
+    }
+    double tr[RS_PER_LANE], init_[RS_PER_LANE];
+#pragma unroll
+    for (int k = 0; k < RS_PER_LANE; k++) { tr[k] = 0.0; init_[k] = 0.0; }
+    // Extra upstream edges (merge nodes).  A lane whose owned positions carry exactly ONE extra edge keeps it in registers
+    // (slot xk, source position xp, edge id xe -> transition xt); lanes with more fall back to the out-of-line loop.
+    int xk = -1, xp = 0; uint32_t xe = 0xffffffffu; double xt = 0.0;
+    {
+        int n_x = 0;
+#pragma unroll
+        for (int k = 0; k < RS_PER_LANE; k++) {
+            if (RS_EXT(k)) {
+                const size_t xi = (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane + k;
+                const uint32_t a0 = P.rx_off[xi], a1 = P.rx_off[xi + 1];
+                n_x += (int)(a1 - a0);
+                if (a1 - a0 == 1 && xk < 0) { xk = k; xp = P.rx_idx[a0]; xe = P.rx_eid[a0]; }
+            }
+        }
+        if (n_x == 1) flg &= ~0xAAAu;          // the single extra lives in registers: clear the out-of-line flags
+        else { xk = -1; xe = 0xffffffffu; }    // none, or several: keep the generic path
+    }
+    const bool tile_has_x = __any_sync(0xffffffffu, xk >= 0);
+    int staged_x = -1;
+    const double* trans = G.trans;
+    const uint32_t job0 = blockIdx.y * jpc;
+    for (uint32_t jj = 0; jj < jpc; jj++) {
+        const uint32_t job_idx = job0 + jj;
+        if (job_idx >= n_jobs) break;
+        // ---- per-tile scalars: lane 0 prepares them, the warp receives them by shuffle
+        int valid = 0, hx = 0, pk = 0, row = 0; unsigned int xbase = 0;
+        unsigned long long prev_ptr = 0, out_ptr = 0;
+        XF fb0 = xf_zero(), ib_cur = xf_zero();
+        if (lane == 0) {
+            const DJob jb = jobs[job_idx];
+            if (s < jb.n_steps && !(jb.active_idx >= 0 && !active[jb.active_idx])) {
+                valid = 1; hx = (int)jb.x;
+                row = FWD ? jb.first_row + (int)s : jb.first_row - (int)s;
+                xbase = bases[jb.base_off + row];
+                pk = (s == 0) ? jb.prev0_kind : PREV_SLAB;
+                prev_ptr = (unsigned long long)(pool + (s == 0 ? jb.prev0_slab : slab_of(jb, s - 1)) * slab_bytes);
+                out_ptr = (unsigned long long)(pool + slab_of(jb, s) * slab_bytes);
+                if (FWD) {
+                    XF mbp, ibp;
+                    if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
+                    else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
+                    ib_cur = xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random);   // fib, forward.rs:541-545
+                    fb0 = xadd(xmul(mbp, lp.p_MM), xmul(ibp, lp.p_IM));                         // begin part of fm
+                }
+            }
+        }
+        valid = __shfl_sync(0xffffffffu, valid, 0);
+        if (!valid) continue;
+        hx = __shfl_sync(0xffffffffu, hx, 0); pk = __shfl_sync(0xffffffffu, pk, 0); xbase = __shfl_sync(0xffffffffu, xbase, 0);
+        prev_ptr = __shfl_sync(0xffffffffu, prev_ptr, 0); out_ptr = __shfl_sync(0xffffffffu, out_ptr, 0);
+        if (FWD) {
+            fb0.v = __shfl_sync(0xffffffffu, fb0.v, 0); fb0.e = __shfl_sync(0xffffffffu, fb0.e, 0);
+            ib_cur.v = __shfl_sync(0xffffffffu, ib_cur.v, 0); ib_cur.e = __shfl_sync(0xffffffffu, ib_cur.e, 0);
+        }
+        const unsigned int x = (xbase >> 1) & 3;   // base code of the read base
+        if (hx != staged_x) {
+            const double* init = G.init + (size_t)hx * G.N;
+            trans = G.trans + (size_t)hx * G.E;
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) {
+                init_[k] = own_node[k] == 0xffffffffu ? 0.0 : init[own_node[k]];
+                tr[k] = own_eid[k] == 0xffffffffu ? 0.0 : trans[own_eid[k]];
+            }
+            xt = xe == 0xffffffffu ? 0.0 : trans[xe];
+            staged_x = hx;
+        }
+        // ---- previous row: coalesced slot-major loads, exponent range by warp reductions
+        double vm[RS_PER_LANE], vi[RS_PER_LANE], vd[RS_PER_LANE]; int ve[RS_PER_LANE];
+        int elo = EXP_NONE_LO_, ehi = EXP_NONE_HI_;
+        if (pk == PREV_SLAB) {
+            const double* gm = (const double*)prev_ptr; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
+#pragma unroll
+            for (int q = 0; q < RS_PER_LANE; q++) {
+                vm[q] = 0.0; vi[q] = 0.0; vd[q] = 0.0; ve[q] = 0;
+                if (ion[q] != 0xffffffffu) { const uint32_t g = ion[q]; vm[q] = gm[g]; vi[q] = gi[g]; vd[q] = FWD ? gd[g] : 0.0; ve[q] = ge[g]; }
+            }
+#pragma unroll
+            for (int q = 0; q < RS_PER_LANE; q++)
+                if (vm[q] + vi[q] + vd[q] != 0.0) { elo = ve[q] < elo ? ve[q] : elo; ehi = ve[q] > ehi ? ve[q] : ehi; }
+        } else {
+            const double v0 = pk == PREV_B_INIT ? lp.p_end : 0.0;
+#pragma unroll
+            for (int q = 0; q < RS_PER_LANE; q++) { vm[q] = ion[q] != 0xffffffffu ? v0 : 0.0; vi[q] = vm[q]; vd[q] = 0.0; ve[q] = 0; }
+            if (v0 != 0.0) { elo = 0; ehi = 0; }
+        }
+        if (FWD) {
+            if (fb0.v != 0.0) { int e = xexp(fb0); elo = e < elo ? e : elo; ehi = e > ehi ? e : ehi; }
+            if (ib_cur.v != 0.0) { int e = xexp(ib_cur); elo = e < elo ? e : elo; ehi = e > ehi ? e : ehi; }
+        }
+        elo = __reduce_min_sync(0xffffffffu, elo); ehi = __reduce_max_sync(0xffffffffu, ehi);
+        double* om = (double*)out_ptr; double* oi = om + Np; double* od = oi + Np; int* oe = (int*)(od + Np);
+        if (ehi == EXP_NONE_HI_) {  // nothing but zeros flows into this tile: the row is zero here
+            for (int j = lane; j < ncore; j += 32) { om[g0 + j] = 0.0; oi[g0 + j] = 0.0; od[g0 + j] = 0.0; oe[g0 + j] = 0; }
+            if (lane == 0) {
+                if (FWD) partials[(size_t)job_idx * n_tiles + c] = xf_zero();
+                else { partials[((size_t)job_idx * n_tiles + c) * 2] = xf_zero(); partials[((size_t)job_idx * n_tiles + c) * 2 + 1] = xf_zero(); }
+            }
+            continue;
+        }
+        if (ehi - elo > span) {    // exponent range too wide for one frame: the exact kernel takes this tile
+            if (lane == 0) { unsigned long long w = atomicAdd(worklist, 1ull); worklist[1 + w] = ((unsigned long long)job_idx << 32) | c; }
+            continue;
+        }
+        const int Eref = ehi;
+        __syncwarp();   // shared-memory reads of the previous tile are done
+        // ---- scale into the frame, stage position-indexed, pick up the owned positions
+#pragma unroll
+        for (int q = 0; q < RS_PER_LANE; q++) {
+            const double sc_ = pow2i(ve[q] - Eref);
+            const int pos = 32 * q + lane;
+            sa[pos] = vm[q] * sc_; sb[pos] = vi[q] * sc_; if (FWD) sc[pos] = vd[q] * sc_;
+        }
+        __syncwarp();
+        double pm[RS_PER_LANE], pi[RS_PER_LANE], pd[RS_PER_LANE];
+#pragma unroll
+        for (int k = 0; k < RS_PER_LANE; k++) {
+            const int pos = RS_PER_LANE * lane + k;
+            pm[k] = sa[pos]; pi[k] = sb[pos]; pd[k] = FWD ? sc[pos] : 0.0;
+        }
+        double cm[RS_PER_LANE], ci[RS_PER_LANE], dacc[RS_PER_LANE], dcur[RS_PER_LANE];
+        if (FWD) {
+            const double fbv = fb0.v == 0.0 ? 0.0 : fb0.v * pow2i(fb0.e - Eref);
+            const double ibv = ib_cur.v == 0.0 ? 0.0 : ib_cur.v * pow2i(ib_cur.e - Eref);
+            // round A: fm, fi (forward.rs:337-388)
+            {
+                const double lm = __shfl_up_sync(0xffffffffu, pm[RS_PER_LANE - 1], 1), li = __shfl_up_sync(0xffffffffu, pi[RS_PER_LANE - 1], 1),
+                             ld = __shfl_up_sync(0xffffffffu, pd[RS_PER_LANE - 1], 1);
+                double xc = 0.0;
+                if (tile_has_x && xk >= 0) xc = xt * (lp.p_MM * sa[xp] + lp.p_IM * sb[xp] + lp.p_DM * sc[xp]);
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    double um = RS_UP(pm, k, lm), ui = RS_UP(pi, k, li), ud = RS_UP(pd, k, ld);
+                    if (RS_IRR(k)) { um = sa[ppos[k]]; ui = sb[ppos[k]]; ud = sc[ppos[k]]; }
+                    double acc = tr[k] * (lp.p_MM * um + lp.p_IM * ui + lp.p_DM * ud);
+                    if (RS_EXT(k)) acc += RS_EXTRAS(k, sa, sb, sc, lp.p_MM, lp.p_IM, lp.p_DM);
+                    if (tile_has_x) acc += (k == xk) ? xc : 0.0;
+                    acc += fbv * init_[k];
+                    cm[k] = acc * (((emc >> (3 * k)) & 7) == x ? lp.p_match : lp.p_mismatch);
+                    ci[k] = lp.p_random * (lp.p_MI * pm[k] + lp.p_II * pi[k] + lp.p_DI * pd[k]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) { const int pos = RS_PER_LANE * lane + k; sa[pos] = cm[k]; sb[pos] = ci[k]; }
+            __syncwarp();
+            // round B: fd0 (forward.rs:480-501)
+            {
+                const double lm = __shfl_up_sync(0xffffffffu, cm[RS_PER_LANE - 1], 1), li = __shfl_up_sync(0xffffffffu, ci[RS_PER_LANE - 1], 1);
+                double xc = 0.0;
+                if (tile_has_x && xk >= 0) xc = xt * (lp.p_MD * sa[xp] + lp.p_ID * sb[xp]);
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    double um = RS_UP(cm, k, lm), ui = RS_UP(ci, k, li);
+                    if (RS_IRR(k)) { um = sa[ppos[k]]; ui = sb[ppos[k]]; }
+                    double acc = tr[k] * (lp.p_MD * um + lp.p_ID * ui);
+                    if (RS_EXT(k)) acc += RS_EXTRAS(k, sa, sb, sb, lp.p_MD, lp.p_ID, 0.0);
+                    if (tile_has_x) acc += (k == xk) ? xc : 0.0;
+                    acc += ibv * (lp.p_ID * init_[k]);
+                    dcur[k] = acc; dacc[k] = acc;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) sc[RS_PER_LANE * lane + k] = dcur[k];
+            __syncwarp();
+            // fdt x 4 (forward.rs:510-524): previous round in registers, its copy in sc / sa alternately
+#pragma unroll
+            for (int t = 1; t < N_DEL_ROUNDS; t++) {
+                double* prevbuf = (t & 1) ? sc : sa; double* curbuf = (t & 1) ? sa : sc;
+                const double ld = __shfl_up_sync(0xffffffffu, dcur[RS_PER_LANE - 1], 1);
+                double nxt[RS_PER_LANE];
+                double xc = 0.0;
+                if (tile_has_x && xk >= 0) xc = xt * lp.p_DD * prevbuf[xp];
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    double up = RS_UP(dcur, k, ld);
+                    if (RS_IRR(k)) up = prevbuf[ppos[k]];
+                    double v = tr[k] * lp.p_DD * up;
+                    if (RS_EXT(k)) v += RS_EXTRAS(k, prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
+                    if (tile_has_x) v += (k == xk) ? xc : 0.0;
+                    nxt[k] = v;
+                }
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) { dcur[k] = nxt[k]; dacc[k] += nxt[k]; }
+                if (t < N_DEL_ROUNDS - 1) {
+#pragma unroll
+                    for (int k = 0; k < RS_PER_LANE; k++) curbuf[RS_PER_LANE * lane + k] = dcur[k];
+                }
+                __syncwarp();
+            }
+        } else {
+            // previous (= next base) row: pm := e_l(x) m''[l]  (every use of m'' is multiplied by the emission of that node)
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) pm[k] *= (((emc >> (3 * k)) & 7) == x ? lp.p_match : lp.p_mismatch);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) sa[RS_PER_LANE * lane + k] = pm[k];
+            __syncwarp();
+            // bd0 (backward.rs:354-377)
+            {
+                const double lm = __shfl_up_sync(0xffffffffu, pm[RS_PER_LANE - 1], 1);
+                double xc = 0.0;
+                if (tile_has_x && xk >= 0) xc = xt * lp.p_DM * sa[xp];
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    double um = RS_UP(pm, k, lm);
+                    if (RS_IRR(k)) um = sa[ppos[k]];
+                    double acc = tr[k] * lp.p_DM * um;
+                    if (RS_EXT(k)) acc += RS_EXTRAS(k, sa, sa, sa, lp.p_DM, 0.0, 0.0);
+                    if (tile_has_x) acc += (k == xk) ? xc : 0.0;
+                    acc += lp.p_DI * lp.p_random * pi[k];
+                    dcur[k] = acc; dacc[k] = acc;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) sc[RS_PER_LANE * lane + k] = dcur[k];
+            __syncwarp();
+            // bdt x 4 (backward.rs:387-404): copies alternate between sc and sb (sa keeps e m'' for bm / bi)
+#pragma unroll
+            for (int t = 1; t < N_DEL_ROUNDS; t++) {
+                double* prevbuf = (t & 1) ? sc : sb; double* curbuf = (t & 1) ? sb : sc;
+                const double ld = __shfl_up_sync(0xffffffffu, dcur[RS_PER_LANE - 1], 1);
+                double nxt[RS_PER_LANE];
+                double xc = 0.0;
+                if (tile_has_x && xk >= 0) xc = xt * lp.p_DD * prevbuf[xp];
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    double up = RS_UP(dcur, k, ld);
+                    if (RS_IRR(k)) up = prevbuf[ppos[k]];
+                    double v = tr[k] * lp.p_DD * up;
+                    if (RS_EXT(k)) v += RS_EXTRAS(k, prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
+                    if (tile_has_x) v += (k == xk) ? xc : 0.0;
+                    nxt[k] = v;
+                }
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) { dcur[k] = nxt[k]; dacc[k] += nxt[k]; }
+                if (t < N_DEL_ROUNDS - 1) {
+#pragma unroll
+                    for (int k = 0; k < RS_PER_LANE; k++) curbuf[RS_PER_LANE * lane + k] = dcur[k];
+                }
+                __syncwarp();
+            }
+            // d of every position into sc, then bm / bi (backward.rs:423-483)
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) sc[RS_PER_LANE * lane + k] = dacc[k];
+            __syncwarp();
+            {
+                const double lm = __shfl_up_sync(0xffffffffu, pm[RS_PER_LANE - 1], 1), ld = __shfl_up_sync(0xffffffffu, dacc[RS_PER_LANE - 1], 1);
+                double xcm = 0.0, xci = 0.0;
+                if (tile_has_x && xk >= 0) { xcm = xt * (lp.p_MM * sa[xp] + lp.p_MD * sc[xp]); xci = xt * (lp.p_IM * sa[xp] + lp.p_ID * sc[xp]); }
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    double um = RS_UP(pm, k, lm), ud = RS_UP(dacc, k, ld);
+                    if (RS_IRR(k)) { um = sa[ppos[k]]; ud = sc[ppos[k]]; }
+                    double am = tr[k] * (lp.p_MM * um + lp.p_MD * ud), ai = tr[k] * (lp.p_IM * um + lp.p_ID * ud);
+                    if (tile_has_x) { am += (k == xk) ? xcm : 0.0; ai += (k == xk) ? xci : 0.0; }
+                    if (RS_EXT(k)) {
+                        am += RS_EXTRAS(k, sa, sc, sc, lp.p_MM, lp.p_MD, 0.0);
+                        ai += RS_EXTRAS(k, sa, sc, sc, lp.p_IM, lp.p_ID, 0.0);
+                    }
+                    cm[k] = am + lp.p_MI * lp.p_random * pi[k];
+                    ci[k] = ai + lp.p_II * lp.p_random * pi[k];
+                }
+            }
+            __syncwarp();
+        }
+        // ---- pack the owned cells, stage position-indexed, store the core coalesced; partial sums over the core
+        double part = 0.0, part2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < RS_PER_LANE; k++) {
+            const int pos = RS_PER_LANE * lane + k;
+            const double m = cm[k], i = ci[k], d = dacc[k];
+            const double mx = fmax(m, fmax(i, d));
+            int qx = 0; double scl = 0.0;
+            if (mx != 0.0) { qx = ilogb_pos(mx); scl = pow2i(-qx); }
+            sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = mx != 0.0 ? Eref + qx : 0;
+            if (pos >= core0 && pos < core0 + ncore) {
+                if (FWD) part += m + i + d;
+                else { part += (pm[k] * lp.p_MM + d * lp.p_MD) * init_[k]; part2 += (pm[k] * lp.p_IM + d * lp.p_ID) * init_[k]; }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < RS_PER_LANE; q++) {
+            const int pos = 32 * q + lane;
+            if (pos >= core0 && pos < core0 + ncore) {
+                const uint32_t g = g0 + (uint32_t)(pos - core0);
+                om[g] = sa[pos]; oi[g] = sb[pos]; od[g] = sc[pos]; oe[g] = se[pos];
+            }
+        }
+        for (int o = 16; o; o >>= 1) { part += __shfl_down_sync(0xffffffffu, part, o); if (!FWD) part2 += __shfl_down_sync(0xffffffffu, part2, o); }
+        if (lane == 0) {
+            if (FWD) partials[(size_t)job_idx * n_tiles + c] = xf(part, Eref);
+            else { partials[((size_t)job_idx * n_tiles + c) * 2] = xf(part, Eref); partials[((size_t)job_idx * n_tiles + c) * 2 + 1] = xf(part2, Eref); }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ top-k selection
 // Key of a cell: (T, mantissa, ~original id) with merged value v = (m+i+d) * 2^ex = mant * 2^T, mant in [1,2).
 // Exact ordering of the linear values; ties -> lower ORIGINAL node index first (the dense SparseVec iterates in
@@ -862,6 +1243,7 @@ static int fast_span(const LinParams& lp) {
 }
 
 // reads handled by one CTA: the tile structure is staged once per CTA, so as many as still leave ~6 waves of CTAs
+static bool use_reg_kernel() { const char* e = getenv("DBGPHMM_DENSE_KERNEL"); return !(e && !strcmp(e, "warp")); }
 static uint32_t fast_jobs_per_cta(const dbgphmm_model* m, uint32_t n_chunks, uint32_t n_jobs) {
     uint32_t target = 8u * 3u * (uint32_t)m->n_sm;
     uint32_t n_ctas = (n_chunks + WT_WARPS - 1) / WT_WARPS;
@@ -872,6 +1254,8 @@ static uint32_t fast_jobs_per_cta(const dbgphmm_model* m, uint32_t n_chunks, uin
 int dense_configure(dbgphmm_model* m) {
     CUDA_TRY(cudaFuncSetAttribute(k_dense_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_dense_reg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_dense_reg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SELECT_SMEM_BYTES));
@@ -889,9 +1273,14 @@ int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jo
     const uint32_t jpc = fast_jobs_per_cta(m, m->fwd.n_chunks, n_jobs);
     dim3 grid((m->fwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
     launch_timer_begin(m->stream);
-    k_dense_warp<true><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
-                                                                           d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks,
-                                                                           fast_span(m->lin), d_worklist, jpc);
+    if (use_reg_kernel())
+        k_dense_reg<true><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
+                                                                              d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks,
+                                                                              fast_span(m->lin), d_worklist, jpc);
+    else
+        k_dense_warp<true><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
+                                                                               d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks,
+                                                                               fast_span(m->lin), d_worklist, jpc);
     COUNT_LAUNCH();
     k_dense_fwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
                                                                              d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks, d_worklist);
@@ -919,9 +1308,14 @@ int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
     const uint32_t jpc = fast_jobs_per_cta(m, m->bwd.n_chunks, n_jobs);
     dim3 grid((m->bwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
     launch_timer_begin(m->stream);
-    k_dense_warp<false><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
-                                                                            d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks,
-                                                                            fast_span(m->lin), d_worklist, jpc);
+    if (use_reg_kernel())
+        k_dense_reg<false><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
+                                                                               d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks,
+                                                                               fast_span(m->lin), d_worklist, jpc);
+    else
+        k_dense_warp<false><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
+                                                                                d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks,
+                                                                                fast_span(m->lin), d_worklist, jpc);
     COUNT_LAUNCH();
     k_dense_bwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_active,
                                                                              pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks, d_worklist);

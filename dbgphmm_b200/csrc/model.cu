@@ -77,6 +77,10 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
                       const std::vector<uint32_t>& up_eid) {
     std::vector<uint32_t> chunk_start, loc_base, loc_node, nle, le_off, le_eid, fp_eid, fx_off, fx_eid;
     std::vector<uint16_t> le_idx, fp_idx, fx_idx;
+    std::vector<uint32_t> rl_node, rl_eid, rx_off, rx_eid;
+    std::vector<uint16_t> rl_par, rl_core, rx_idx;
+    std::vector<uint8_t> rl_flag;
+    std::vector<uint32_t> rpos(N, 0xffffffffu);  // node -> position in the register layout of the current tile
     std::vector<uint32_t> stamp(N, 0xffffffffu), lidx(N, 0);
     std::vector<uint32_t> local, depth_cnt(8);
     uint32_t start = 0, cidx = 0, max_local = 0;
@@ -143,6 +147,66 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
         }
         le_off.push_back((uint32_t)le_idx.size());  // sentinel of this chunk
         fx_off.push_back((uint32_t)fx_idx.size());
+        // ---- register-stencil layout of this tile
+        {
+            std::vector<uint32_t> order; order.reserve(DENSE_LMAX);
+            std::vector<uint8_t> placed(local.size(), 0);
+            auto in_tile = [&](uint32_t u) { return stamp[u] == cidx; };
+            // chain of first upstream neighbours above the tile head, deepest first
+            std::vector<uint32_t> head;
+            uint32_t v = local[0];
+            for (int h = 0; h < HALO_HOPS; h++) {
+                if (up_off[v + 1] == up_off[v]) break;
+                uint32_t u = up_node[up_off[v]];
+                if (!in_tile(u) || lidx[u] < size || placed[lidx[u]]) break;
+                placed[lidx[u]] = 1; head.push_back(u); v = u;
+            }
+            for (size_t q = head.size(); q-- > 0;) order.push_back(head[q]);
+            const uint32_t core0 = (uint32_t)order.size();
+            for (uint32_t q = 0; q < size; q++) { order.push_back(local[q]); placed[q] = 1; }
+            // remaining halo nodes: chains following "x is the first upstream neighbour of the next", deepest first
+            for (size_t q = local.size(); q-- > size;) {   // local is depth-sorted: start from the deepest
+                if (placed[q]) continue;
+                uint32_t x = local[q];
+                // climb to the top of x's unplaced first-neighbour chain
+                for (;;) {
+                    if (up_off[x + 1] == up_off[x]) break;
+                    uint32_t u = up_node[up_off[x]];
+                    if (!in_tile(u) || placed[lidx[u]]) break;
+                    x = u;
+                }
+                // walk down: append x, then an unplaced halo node whose first neighbour is x
+                for (;;) {
+                    placed[lidx[x]] = 1; order.push_back(x);
+                    uint32_t nxt = 0xffffffffu;
+                    for (size_t r = size; r < local.size(); r++) {
+                        uint32_t y = local[r];
+                        if (!placed[r] && up_off[y + 1] > up_off[y] && up_node[up_off[y]] == x) { nxt = y; break; }
+                    }
+                    if (nxt == 0xffffffffu) break;
+                    x = nxt;
+                }
+            }
+            for (size_t q = 0; q < order.size(); q++) rpos[order[q]] = (uint32_t)q;
+            rl_core.push_back((uint16_t)core0); rl_core.push_back((uint16_t)size);
+            for (uint32_t q = 0; q < DENSE_LMAX; q++) {
+                rx_off.push_back((uint32_t)rx_idx.size());
+                if (q >= order.size()) { rl_node.push_back(0xffffffffu); rl_par.push_back(0xffff); rl_eid.push_back(0xffffffffu); rl_flag.push_back(0); continue; }
+                uint32_t x = order[q];
+                uint16_t p0 = 0xffff; uint32_t e0 = 0xffffffffu; uint8_t fl = 0;
+                bool first = true;
+                for (uint32_t a = up_off[x]; a < up_off[x + 1]; a++) {
+                    uint32_t u = up_node[a];
+                    bool here = in_tile(u);
+                    if (first) { first = false; if (here) { p0 = (uint16_t)rpos[u]; e0 = up_eid[a]; } }
+                    else if (here) { rx_idx.push_back((uint16_t)rpos[u]); rx_eid.push_back(up_eid[a]); fl |= 2; }
+                }
+                if (p0 != 0xffff && !(q > 0 && p0 == q - 1)) fl |= 1;   // in-tile first neighbour that is not the previous position
+                rl_node.push_back(x); rl_par.push_back(p0); rl_eid.push_back(e0); rl_flag.push_back(fl);
+            }
+            rx_off.push_back((uint32_t)rx_idx.size());
+            for (uint32_t x : order) rpos[x] = 0xffffffffu;
+        }
         max_local = std::max<uint32_t>(max_local, (uint32_t)local.size());
         for (uint32_t v : local) stamp[v] = 0xffffffffu;  // a node may be halo of several chunks
         start += size;
@@ -163,6 +227,8 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
     ST_TRY(upload(&P.le_eid, le_eid));
     ST_TRY(upload(&P.fp_idx, fp_idx)); ST_TRY(upload(&P.fp_eid, fp_eid));
     ST_TRY(upload(&P.fx_off, fx_off)); ST_TRY(upload(&P.fx_idx, fx_idx)); ST_TRY(upload(&P.fx_eid, fx_eid));
+    ST_TRY(upload(&P.rl_node, rl_node)); ST_TRY(upload(&P.rl_par, rl_par)); ST_TRY(upload(&P.rl_eid, rl_eid)); ST_TRY(upload(&P.rl_flag, rl_flag));
+    ST_TRY(upload(&P.rl_core, rl_core)); ST_TRY(upload(&P.rx_off, rx_off)); ST_TRY(upload(&P.rx_idx, rx_idx)); ST_TRY(upload(&P.rx_eid, rx_eid));
     return DBGPHMM_OK;
 }
 
@@ -170,6 +236,7 @@ static void free_plan(DevPlan& P) {
     cudaFree(P.chunk_start); cudaFree(P.loc_base); cudaFree(P.loc_node); cudaFree(P.nle);
     cudaFree(P.le_off); cudaFree(P.le_idx); cudaFree(P.le_eid);
     cudaFree(P.fp_idx); cudaFree(P.fp_eid); cudaFree(P.fx_off); cudaFree(P.fx_idx); cudaFree(P.fx_eid);
+    cudaFree(P.rl_node); cudaFree(P.rl_par); cudaFree(P.rl_eid); cudaFree(P.rl_flag); cudaFree(P.rl_core); cudaFree(P.rx_off); cudaFree(P.rx_idx); cudaFree(P.rx_eid);
     P = DevPlan();
 }
 

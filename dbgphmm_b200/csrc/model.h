@@ -44,6 +44,17 @@ struct DevPlan {
     uint32_t* fx_off = nullptr;       // [loc_total + n_chunks] offsets of the extra upstream edges (chunk c uses base loc_base[c]+c)
     uint16_t* fx_idx = nullptr;
     uint32_t* fx_eid = nullptr;
+    // Register-stencil layout of the same tiles (k_dense_reg): DENSE_LMAX positions per tile ordered
+    // [upstream chain of the tile head, deepest first | core nodes | remaining halo nodes in first-parent chains], so that
+    // "first upstream neighbour == previous position" holds for almost every node.  Fixed stride DENSE_LMAX per tile.
+    uint32_t* rl_node = nullptr;      // [n_chunks * LMAX] relabelled node id, 0xffffffff = padding
+    uint16_t* rl_par = nullptr;       // [n_chunks * LMAX] position of the first upstream neighbour, 0xffff = not in the tile
+    uint32_t* rl_eid = nullptr;       // [n_chunks * LMAX] its EdgeIndex (0xffffffff if none)
+    uint8_t* rl_flag = nullptr;       // [n_chunks * LMAX] bit0: first neighbour is NOT the previous position, bit1: has extra edges
+    uint16_t* rl_core = nullptr;      // [n_chunks * 2] position of the first core node, number of core nodes
+    uint32_t* rx_off = nullptr;       // [n_chunks * (LMAX + 1)] offsets into rx_idx / rx_eid (absolute)
+    uint16_t* rx_idx = nullptr;       // extra upstream neighbours as positions
+    uint32_t* rx_eid = nullptr;
     std::vector<uint32_t> h_chunk_start;
 };
 

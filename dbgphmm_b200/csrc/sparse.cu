@@ -9,6 +9,7 @@
 // Entry order of a row = insertion order of the reference's SparseVec: the step's `nodes` first (they hold m, i),
 // then nodes that only ever received a Del value, in the order the Del rounds first touched them.
 #include <algorithm>
+#include <cstdlib>
 #include "sparse.h"
 
 #define SP_TENT 0x80000000u
@@ -41,6 +42,8 @@ struct SS {  // shared-memory view of one job
     uint32_t* scan;                      // [cap + 1] scratch
     // ranking scratch
     int* k_T; unsigned long long* k_mant;
+    // expansion scratch: hash cell and ordered prefix of every candidate
+    uint32_t ccap; unsigned short* ccell; uint32_t* cpre;
 };
 
 __device__ __forceinline__ uint32_t sp_hash(uint32_t id, int shift) { return (id * 2654435761u) >> shift; }
@@ -66,32 +69,23 @@ __device__ __forceinline__ uint32_t sp_cell(uint32_t* key, uint32_t hmask, int h
     }
 }
 
-// in-place exclusive scan of arr[0..n) ; arr[n] = total.  All threads must call.
+// in-place exclusive scan of arr[0..n) ; arr[n] = total.  All threads must call.  The scan itself is done by warp 0
+// (each lane sums a contiguous chunk, one shuffle scan over the lane totals): two barriers instead of three per tile.
 __device__ uint32_t block_exscan(uint32_t* arr, int n) {
-    __shared__ uint32_t wtot[32];
-    __shared__ uint32_t carry_s;
-    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, w = tid >> 5, nw = (B + 31) >> 5;
-    if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += B) {
-        int idx = base + tid;
-        uint32_t v = idx < n ? arr[idx] : 0u, x = v;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int k = (n + 31) >> 5, lo = lane * k, hi = min(lo + k, n);
+        uint32_t sum = 0;
+        for (int i = lo; i < hi; i++) sum += arr[i];
+        uint32_t x = sum;
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) wtot[w] = x;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (int k = 0; k < w; k++) woff += wtot[k];
-        uint32_t carry = carry_s;
-        if (idx < n) arr[idx] = carry + woff + x - v;
-        __syncthreads();
-        if (tid == B - 1) carry_s = carry + woff + x;
-        (void)nw;
-        __syncthreads();
+        uint32_t run = x - sum;
+        for (int i = lo; i < hi; i++) { uint32_t v = arr[i]; arr[i] = run; run += v; }
+        if (lane == 31) arr[n] = x;
     }
-    uint32_t tot = carry_s;
-    if (tid == 0) arr[n] = tot;
     __syncthreads();
-    return tot;
+    return arr[n];
 }
 
 __device__ __forceinline__ XF block_xsum(XF a) {  // deterministic block reduction; result valid in every thread
@@ -140,74 +134,66 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.scan[mid] <= pp) lo = mid; else hi = mid; }
         return nbr[off[src[lo]] + (pp - S.scan[lo])];
     };
-    // phase 1: first position of every id
+    if (C > S.ccap) { if (tid == 0) s_ovf = 1; __syncthreads(); *n_out = 0; return false; }
+    // phase 1: first position of every id ; remember the hash cell of every candidate
     for (uint32_t p = tid; p < C; p += B) {
         uint32_t id = cand(p);
         uint32_t cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
+        S.ccell[p] = (unsigned short)cell;
         uint32_t v = S.ch_val[cell];
         if (v < SP_TENT) atomicMin(&S.firstpos[v], p);
         else atomicMin(&S.ch_val[cell], SP_TENT | p);
     }
     __syncthreads();
-    // phase 2: order-preserving compaction (kept count in the low half, new-entry count in the high half)
-    __shared__ uint32_t wtot[32];
-    __shared__ uint32_t carry_s;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = tid & 31, w = tid >> 5;
-    for (uint32_t base = 0; base < C; base += B) {
-        uint32_t p = base + tid;
-        uint32_t id = 0, cell = 0, v = SP_ABSENT;
-        bool kept = false, isnew = false;
-        if (p < C) {
-            id = cand(p);
-            cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
-            v = S.ch_val[cell];
-            if (v < SP_TENT) kept = (S.firstpos[v] == p);
-            else if (v == (SP_TENT | p)) { kept = true; isnew = true; }
-        }
-        uint32_t val = (kept ? 1u : 0u) | (isnew ? 0x10000u : 0u), x = val;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) wtot[w] = x;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (int k = 0; k < w; k++) woff += wtot[k];
-        uint32_t carry = carry_s;
-        uint32_t excl = carry + woff + x - val;
-        if (kept) {
-            uint32_t oi = excl & 0xffffu, ni = excl >> 16;
-            if ((int)oi < max_out) {
-                uint32_t slot = isnew ? n_ent0 + ni : v;
-                if (slot >= S.cap) s_ovf = 1;
-                else {
-                    if (isnew) {
-                        S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
-                        S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
-                        S.ch_val[cell] = slot;
-                    }
-                    out_id[oi] = id; out_slot[oi] = (uint16_t)slot;
+    // phase 2a: kept / new flags (kept count in the low half, new-entry count in the high half)
+    for (uint32_t p = tid; p < C; p += B) {
+        uint32_t v = S.ch_val[S.ccell[p]];
+        uint32_t f = 0;
+        if (v < SP_TENT) f = (S.firstpos[v] == p) ? 1u : 0u;
+        else if (v == (SP_TENT | p)) f = 0x10001u;
+        S.cpre[p] = f;
+    }
+    const uint32_t tot = block_exscan(S.cpre, (int)C);   // ordered prefix by warp 0
+    // phase 2b: emit in first-occurrence order
+    for (uint32_t p = tid; p < C; p += B) {
+        uint32_t excl = S.cpre[p], nxt = S.cpre[p + 1];
+        if (nxt == excl) continue;   // not kept
+        bool isnew = (nxt - excl) >> 16;
+        uint32_t oi = excl & 0xffffu, ni = excl >> 16;
+        uint32_t cell = S.ccell[p];
+        if ((int)oi < max_out) {
+            uint32_t slot = isnew ? n_ent0 + ni : S.ch_val[cell];
+            if (slot >= S.cap) s_ovf = 1;
+            else {
+                uint32_t id = S.ch_key[cell] - 1;
+                if (isnew) {
+                    S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
+                    S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
                 }
-            } else if (isnew) S.ch_val[cell] = SP_ABSENT;
+                out_id[oi] = id; out_slot[oi] = (unsigned short)slot;
+            }
         }
-        __syncthreads();
-        if (tid == B - 1) carry_s = carry + woff + x;
-        __syncthreads();
+    }
+    __syncthreads();
+    // publish slots of the new entries (after every thread has read the tentative values above)
+    for (uint32_t p = tid; p < C; p += B) {
+        uint32_t excl = S.cpre[p], nxt = S.cpre[p + 1];
+        if ((nxt - excl) >> 16) {
+            uint32_t oi = excl & 0xffffu, ni = excl >> 16;
+            S.ch_val[S.ccell[p]] = ((int)oi < max_out && n_ent0 + ni < S.cap) ? n_ent0 + ni : SP_ABSENT;
+        }
     }
     if (tid == 0) {
-        uint32_t tot = carry_s;
         uint32_t kept_tot = tot & 0xffffu;
-        // new entries among the first max_out kept ones: recount is not needed when nothing was truncated
         s_nout = kept_tot < (uint32_t)max_out ? kept_tot : (uint32_t)max_out;
         if (cap_limited && kept_tot > (uint32_t)max_out) s_ovf = 1;
-        s_nent = n_ent0;  // fixed below
-    }
-    __syncthreads();
-    // number of new entries actually appended = max slot + 1 among outputs (slots are appended in order)
-    {
-        uint32_t mx = n_ent0;
-        for (uint32_t o = tid; o < s_nout; o += B) { uint32_t sl = out_slot[o]; if (sl + 1 > mx) mx = sl + 1; }
-        for (int o = 16; o; o >>= 1) { uint32_t y = __shfl_down_sync(0xffffffffu, mx, o); mx = y > mx ? y : mx; }
-        if (lane == 0) atomicMax(&s_nent, mx);
+        // new entries among the emitted ones = new-count prefix at the first candidate that was not emitted
+        uint32_t new_emitted = tot >> 16;
+        if (kept_tot > (uint32_t)max_out) {
+            new_emitted = 0;
+            for (uint32_t p = 0; p < C; p++) if ((S.cpre[p] & 0xffffu) == (uint32_t)max_out) { new_emitted = S.cpre[p] >> 16; break; }
+        }
+        s_nent = n_ent0 + new_emitted;
     }
     __syncthreads();
     *n_out = (int)s_nout;
@@ -305,6 +291,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     S.la_id[0] = (uint32_t*)take(4 * cap); S.la_id[1] = (uint32_t*)take(4 * cap); S.act_id = (uint32_t*)take(4 * cap);
     S.la_slot[0] = (uint16_t*)take(2 * cap); S.la_slot[1] = (uint16_t*)take(2 * cap); S.act_slot = (uint16_t*)take(2 * cap);
     S.dlist = (uint16_t*)take(2 * cap);
+    S.ccap = 4 * cap; S.ccell = (unsigned short*)take(2 * (size_t)S.ccap); S.cpre = (uint32_t*)take(4 * ((size_t)S.ccap + 1));
 
     __shared__ XF s_mb, s_ib;          // begin scalars of the previous row (forward) / ib of the next row (backward)
     __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
@@ -633,6 +620,7 @@ static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) {
     s += r16(4 * MAX_ACTIVE);
     s += 3 * r16(4 * (size_t)cap);
     s += 4 * r16(2 * (size_t)cap);
+    s += r16(2 * 4 * (size_t)cap) + r16(4 * (4 * (size_t)cap + 1));
     return s;
 }
 
@@ -651,6 +639,7 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
     int threads = cap <= 64 ? 32 : (cap <= 256 ? 128 : 256);
+    if (const char* e = getenv("DBGPHMM_SPARSE_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) threads = t; }
     k_sparse<<<n_jobs, threads, smem, m->stream>>>(G, m->lin, d_jobs, io, cap, hcap);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
