@@ -168,9 +168,10 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
     std::vector<unsigned long long> cells(n);
     std::vector<uint32_t> todo(n);
     for (uint32_t i = 0; i < n; i++) todo[i] = i;
-    uint32_t caps[2] = {small_cap, 832};
-    for (int pass = 0; pass < 2 && !todo.empty(); pass++) {
-        if (pass == 1 && caps[1] <= caps[0]) break;
+    uint32_t caps[3] = {small_cap, 256, 832};
+    if (const char* e = getenv("DBGPHMM_SPARSE_CAP")) { int c0 = atoi(e); if (c0 >= 32 && c0 <= 832) caps[0] = (uint32_t)c0; }
+    for (int pass = 0; pass < 3 && !todo.empty(); pass++) {
+        if (pass > 0 && caps[pass] <= caps[pass - 1]) continue;
         std::vector<SJob> cur(todo.size());
         for (size_t i = 0; i < todo.size(); i++) cur[i] = sj[todo[i]];
         CUDA_TRY(cudaMemcpyAsync(b_jobs.p, cur.data(), sizeof(SJob) * cur.size(), cudaMemcpyHostToDevice, st));
@@ -184,7 +185,7 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
             if (status[i] == SJ_OK) {
                 store->h_final[cur[i].out_idx] = fin[i];
                 store->cells += cells[i];
-            } else if (status[i] == SJ_NEED_BIG && pass == 0) next.push_back(todo[i]);
+            } else if (status[i] == SJ_NEED_BIG && pass < 2) next.push_back(todo[i]);
             else if (status[i] == SJ_OOM) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
             else { dbg_set_error("a sparse row exceeded MAX_ACTIVE_NODES entries (the reference panics: insufficient capacity)"); return DBGPHMM_ERR_CAPACITY; }
         }

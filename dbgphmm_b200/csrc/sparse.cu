@@ -640,6 +640,12 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
     int threads = cap <= 64 ? 32 : (cap <= 256 ? 128 : 256);
     if (const char* e = getenv("DBGPHMM_SPARSE_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) threads = t; }
+    {   // leave the rest of the unified L1/shared array to L1: the CSR walks of a job re-read the same few lines every row
+        int carve = (int)((smem * 4 + 8192) * 100 / (228 * 1024)) + 1;
+        if (const char* e = getenv("DBGPHMM_SPARSE_CARVEOUT")) carve = atoi(e);
+        if (carve < 10) carve = 10; if (carve > 100) carve = 100;
+        cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
     k_sparse<<<n_jobs, threads, smem, m->stream>>>(G, m->lin, d_jobs, io, cap, hcap);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
