@@ -44,28 +44,8 @@ struct SS {  // shared-memory view of one job
     int* k_T; unsigned long long* k_mant;
     // expansion scratch: hash cell and ordered prefix of every candidate
     uint32_t ccap; unsigned short* ccell; uint32_t* cpre;
-    // per-job cache of graph neighbourhoods (nodes with <= 2 parents and <= 2 children), persistent across rows:
-    // the active set moves by a node or two per base, so almost every CSR / trans / init read of a row hits it.
-    uint32_t gcap, ghmask; int ghshift;
-    uint32_t* g_key; uint16_t* g_val;       // [2 gcap] open addressing, key = id + 1
-    uint32_t* g_cnt;                        // [0] slots used, [1] full flag, [2] keys used
-    uint32_t* g_meta;                       // n_par | n_chi << 4 | emission << 8 | emission(child k) << (16 + 8k)
-    double* g_init; double *g_pt, *g_ct;    // init ; trans of the parent / child edges [2 per slot]
-    uint32_t *g_pn, *g_cn;                  // parents / children [2 per slot], CSR order
-    uint16_t* gsrc;                         // [MAX_ACTIVE] cache slot of every expansion source
+    uint32_t* wt; uint32_t tog, ecall;   // block_prefix scratch [2][32] + call parities
 };
-#define GC_NONE 0xffffu
-
-__device__ __forceinline__ int gc_find(const SS& S, uint32_t id) {
-    if (!S.gcap) return -1;
-    uint32_t h = (id * 2654435761u) >> S.ghshift;
-    for (;;) {
-        uint32_t k = S.g_key[h];
-        if (k == id + 1) { uint32_t v = S.g_val[h]; return v == GC_NONE ? -1 : (int)v; }
-        if (k == 0) return -1;
-        h = (h + 1) & S.ghmask;
-    }
-}
 
 __device__ __forceinline__ uint32_t sp_hash(uint32_t id, int shift) { return (id * 2654435761u) >> shift; }
 __device__ __forceinline__ int sp_find(const uint32_t* key, const uint32_t* val, uint32_t hmask, int hshift, uint32_t id) {
@@ -90,63 +70,22 @@ __device__ __forceinline__ uint32_t sp_cell(uint32_t* key, uint32_t hmask, int h
     }
 }
 
-// Make sure every node of `list` has been looked at by the cache: the thread that inserts a key loads the node's
-// neighbourhood (3 dependent global round trips) — in the steady state nothing is missing and this is one probe per node.
-// Nodes of degree > 2 and nodes met while the cache is full stay uncached (readers then use the global arrays).
-__device__ void gc_ensure(SS& S, const SGraph& G, const double* __restrict__ trans, const double* __restrict__ init,
-                          const uint32_t* list, int n) {
-    if (!S.gcap) return;
-    for (int a = threadIdx.x; a < n; a += blockDim.x) {
-        const uint32_t id = list[a];
-        uint32_t h = (id * 2654435761u) >> S.ghshift;
-        bool mine = false;
-        for (;;) {
-            uint32_t k = S.g_key[h];
-            if (k == id + 1) break;
-            if (k == 0) {
-                if (S.g_cnt[1]) break;                                  // full: leave it uncached
-                if (atomicAdd(&S.g_cnt[2], 1u) >= S.gcap) { S.g_cnt[1] = 1; break; }
-                uint32_t old = atomicCAS(&S.g_key[h], 0u, id + 1);
-                if (old == 0u) { mine = true; break; }
-                if (old == id + 1) break;
-            } else h = (h + 1) & S.ghmask;
-        }
-        if (!mine) continue;
-        const uint32_t po = G.par_off[id], np = G.par_off[id + 1] - po, co = G.chi_off[id], nc = G.chi_off[id + 1] - co;
-        uint32_t slot = GC_NONE;
-        if (np <= 2 && nc <= 2) {
-            slot = atomicAdd(&S.g_cnt[0], 1u);
-            uint32_t meta = np | (nc << 4) | ((uint32_t)G.emission[id] << 8);
-            for (uint32_t k = 0; k < np; k++) { S.g_pn[2 * slot + k] = G.par_node[po + k]; S.g_pt[2 * slot + k] = trans[G.par_eid[po + k]]; }
-            for (uint32_t k = 0; k < nc; k++) {
-                const uint32_t ch = G.chi_node[co + k];
-                S.g_cn[2 * slot + k] = ch; S.g_ct[2 * slot + k] = trans[G.chi_eid[co + k]];
-                meta |= (uint32_t)G.emission[ch] << (16 + 8 * k);
-            }
-            S.g_meta[slot] = meta; S.g_init[slot] = init[id];
-        }
-        S.g_val[h] = (uint16_t)slot;
-    }
+// Ordered exclusive prefix of one small value per thread over the block (thread order) ; *total = block sum.
+// One barrier: warp shuffles + per-warp totals in shared memory (double-buffered, so back-to-back calls need no
+// second barrier).  All threads must call.  Two 16-bit counters may be packed into v.
+__device__ __forceinline__ uint32_t block_prefix(SS& S, uint32_t v, uint32_t* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    uint32_t* wt = S.wt + 32 * (S.tog & 1);
+    S.tog++;
+    if (lane == 31) wt[w] = x;
     __syncthreads();
-}
-
-// in-place exclusive scan of arr[0..n) ; arr[n] = total.  All threads must call.  The scan itself is done by warp 0
-// (each lane sums a contiguous chunk, one shuffle scan over the lane totals): two barriers instead of three per tile.
-__device__ uint32_t block_exscan(uint32_t* arr, int n) {
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const int k = (n + 31) >> 5, lo = lane * k, hi = min(lo + k, n);
-        uint32_t sum = 0;
-        for (int i = lo; i < hi; i++) sum += arr[i];
-        uint32_t x = sum;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        uint32_t run = x - sum;
-        for (int i = lo; i < hi; i++) { uint32_t v = arr[i]; arr[i] = run; run += v; }
-        if (lane == 31) arr[n] = x;
-    }
-    __syncthreads();
-    return arr[n];
+    uint32_t base = 0, tot = 0;
+    for (int k = 0; k < nw; k++) { uint32_t t = wt[k]; base += k < w ? t : 0u; tot += t; }
+    *total = tot;
+    return base + x - v;
 }
 
 __device__ __forceinline__ XF block_xsum(XF a) {  // deterministic block reduction; result valid in every thread
@@ -173,106 +112,85 @@ __device__ __forceinline__ XF block_xsum(XF a) {  // deterministic block reducti
 // and_us: the sources themselves come first.  with_nbrs: append their neighbours (in CSR = newest-edge-first order).
 // Nodes without a current-row entry get one appended (zeroed).  Output: out_id/out_slot, *n_out (<= max_out).
 // Returns false if the entry table would overflow `cap`.
-__device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t* off, const uint32_t* nbr, bool children, bool and_us,
-                          bool with_nbrs, uint32_t* out_id, uint16_t* out_slot, int max_out, uint32_t* n_ent_io, int* n_out) {
-    __shared__ uint32_t s_nent, s_nout;
-    __shared__ int s_ovf;
+//   phase 0  candidate list = [sources] ++ neighbours of source 0, 1, ... (ordered scatter through a block prefix)
+//   phase 1  every candidate finds / inserts its hash cell and min-reduces its position into it
+//   phase 2  a candidate is kept iff it holds the first position of its id ; ordered compaction by a second prefix
+__device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t* off, const uint32_t* nbr, bool and_us, bool with_nbrs,
+                          uint32_t* out_id, uint16_t* out_slot, int max_out, uint32_t* n_ent_io, int* n_out) {
+    __shared__ uint32_t s_flags[2][2];   // [call parity][0: overflow, 1: new entries not emitted]
     const int tid = threadIdx.x, B = blockDim.x;
     const uint32_t n_ent0 = *n_ent_io;
     const bool cap_limited = (int)S.cap < max_out;  // the table cannot hold the reference's 400-entry list
     if (cap_limited) max_out = (int)S.cap;
-    const uint32_t* g_nb = children ? S.g_cn : S.g_pn;
-    for (int q = tid; q < n_src; q += B) {
-        uint32_t cnt = 0;
-        if (with_nbrs) {
-            const uint32_t id = src[q];
-            const int cs = gc_find(S, id);
-            S.gsrc[q] = cs < 0 ? (uint16_t)GC_NONE : (uint16_t)cs;
-            cnt = cs >= 0 ? ((S.g_meta[cs] >> (children ? 4 : 0)) & 15u) : (off[id + 1] - off[id]);
-        }
-        S.scan[q] = cnt;
-    }
+    uint32_t* fl = s_flags[S.ecall & 1];
+    S.ecall++;
     for (uint32_t e = tid; e < n_ent0; e += B) S.firstpos[e] = SP_ABSENT;
-    if (tid == 0) s_ovf = 0;
+    if (tid == 0) { fl[0] = 0; fl[1] = 0; }
+    uint32_t* cid = S.cpre;   // candidate ids
+    uint32_t C = and_us ? (uint32_t)n_src : 0u;
+    if (and_us) for (int q = tid; q < n_src; q += B) if ((uint32_t)q < S.ccap) cid[q] = src[q];
+    if (with_nbrs) {
+        for (int q0 = 0; q0 < n_src; q0 += B) {
+            const int q = q0 + tid;
+            uint32_t o0 = 0, cnt = 0;
+            if (q < n_src) { const uint32_t id = src[q]; o0 = off[id]; cnt = off[id + 1] - o0; }
+            uint32_t tot;
+            const uint32_t pre = C + block_prefix(S, cnt, &tot);
+            for (uint32_t k = 0; k < cnt; k++) if (pre + k < S.ccap) cid[pre + k] = nbr[o0 + k];
+            C += tot;
+        }
+    }
     __syncthreads();
-    const uint32_t n_nb = block_exscan(S.scan, n_src);
-    const uint32_t n_self = and_us ? (uint32_t)n_src : 0u;
-    const uint32_t C = n_self + n_nb;
-    auto cand = [&](uint32_t p) -> uint32_t {
-        if (p < n_self) return src[p];
-        uint32_t pp = p - n_self;
-        int lo = 0, hi = n_src;  // last q with scan[q] <= pp
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (S.scan[mid] <= pp) lo = mid; else hi = mid; }
-        const uint32_t k = pp - S.scan[lo], cs = S.gsrc[lo];
-        return cs != GC_NONE ? g_nb[2 * cs + k] : nbr[off[src[lo]] + k];
-    };
-    if (C > S.ccap) { if (tid == 0) s_ovf = 1; __syncthreads(); *n_out = 0; return false; }
-    // phase 1: first position of every id ; remember the hash cell of every candidate
+    if (C > S.ccap) { *n_out = 0; return false; }
     for (uint32_t p = tid; p < C; p += B) {
-        uint32_t id = cand(p);
-        uint32_t cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
+        const uint32_t id = cid[p];
+        const uint32_t cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
         S.ccell[p] = (unsigned short)cell;
-        uint32_t v = S.ch_val[cell];
+        const uint32_t v = S.ch_val[cell];
         if (v < SP_TENT) atomicMin(&S.firstpos[v], p);
         else atomicMin(&S.ch_val[cell], SP_TENT | p);
     }
     __syncthreads();
-    // phase 2a: kept / new flags (kept count in the low half, new-entry count in the high half)
-    for (uint32_t p = tid; p < C; p += B) {
-        uint32_t v = S.ch_val[S.ccell[p]];
-        uint32_t f = 0;
-        if (v < SP_TENT) f = (S.firstpos[v] == p) ? 1u : 0u;
-        else if (v == (SP_TENT | p)) f = 0x10001u;
-        S.cpre[p] = f;
-    }
-    const uint32_t tot = block_exscan(S.cpre, (int)C);   // ordered prefix by warp 0
-    // phase 2b: emit in first-occurrence order
-    for (uint32_t p = tid; p < C; p += B) {
-        uint32_t excl = S.cpre[p], nxt = S.cpre[p + 1];
-        if (nxt == excl) continue;   // not kept
-        bool isnew = (nxt - excl) >> 16;
-        uint32_t oi = excl & 0xffffu, ni = excl >> 16;
-        uint32_t cell = S.ccell[p];
-        if ((int)oi < max_out) {
-            uint32_t slot = isnew ? n_ent0 + ni : S.ch_val[cell];
-            if (slot >= S.cap) s_ovf = 1;
-            else {
-                uint32_t id = S.ch_key[cell] - 1;
-                if (isnew) {
-                    S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
-                    S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
+    uint32_t run = 0;   // kept count in the low half, new-entry count in the high half
+    for (uint32_t p0 = 0; p0 < C; p0 += B) {
+        const uint32_t p = p0 + tid;
+        uint32_t f = 0, cell = 0, v = 0;
+        if (p < C) {
+            cell = S.ccell[p]; v = S.ch_val[cell];
+            if (v < SP_TENT) f = (S.firstpos[v] == p) ? 1u : 0u;
+            else if (v == (SP_TENT | p)) f = 0x10001u;
+        }
+        uint32_t tot;
+        const uint32_t excl = run + block_prefix(S, f, &tot);   // (barrier: every tentative value of this chunk has been read)
+        if (f) {
+            const bool isnew = f >> 16;
+            const uint32_t oi = excl & 0xffffu, ni = excl >> 16;
+            const uint32_t slot = isnew ? n_ent0 + ni : v;
+            const bool emit = (int)oi < max_out;
+            if (emit) {
+                if (slot >= S.cap) fl[0] = 1;
+                else {
+                    const uint32_t id = S.ch_key[cell] - 1;
+                    if (isnew) {
+                        S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
+                        S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
+                    }
+                    out_id[oi] = id; out_slot[oi] = (unsigned short)slot;
                 }
-                out_id[oi] = id; out_slot[oi] = (unsigned short)slot;
+            }
+            if (isnew) {
+                S.ch_val[cell] = (emit && slot < S.cap) ? slot : SP_ABSENT;
+                if (!emit) atomicAdd(&fl[1], 1u);
             }
         }
+        run += tot;
+        if (p0 + B < C) __syncthreads();   // later chunks must see the slots published by this one
     }
     __syncthreads();
-    // publish slots of the new entries (after every thread has read the tentative values above)
-    for (uint32_t p = tid; p < C; p += B) {
-        uint32_t excl = S.cpre[p], nxt = S.cpre[p + 1];
-        if ((nxt - excl) >> 16) {
-            uint32_t oi = excl & 0xffffu, ni = excl >> 16;
-            S.ch_val[S.ccell[p]] = ((int)oi < max_out && n_ent0 + ni < S.cap) ? n_ent0 + ni : SP_ABSENT;
-        }
-    }
-    if (tid == 0) {
-        uint32_t kept_tot = tot & 0xffffu;
-        s_nout = kept_tot < (uint32_t)max_out ? kept_tot : (uint32_t)max_out;
-        if (cap_limited && kept_tot > (uint32_t)max_out) s_ovf = 1;
-        // new entries among the emitted ones = new-count prefix at the first candidate that was not emitted
-        uint32_t new_emitted = tot >> 16;
-        if (kept_tot > (uint32_t)max_out) {
-            new_emitted = 0;
-            for (uint32_t p = 0; p < C; p++) if ((S.cpre[p] & 0xffffu) == (uint32_t)max_out) { new_emitted = S.cpre[p] >> 16; break; }
-        }
-        s_nent = n_ent0 + new_emitted;
-    }
-    __syncthreads();
-    *n_out = (int)s_nout;
-    *n_ent_io = s_nent;
-    bool ok = !s_ovf;
-    __syncthreads();
-    return ok;
+    const uint32_t kept_tot = run & 0xffffu, new_tot = run >> 16;
+    *n_out = (int)(kept_tot < (uint32_t)max_out ? kept_tot : (uint32_t)max_out);
+    *n_ent_io = n_ent0 + new_tot - fl[1];
+    return !fl[0] && !(cap_limited && kept_tot > (uint32_t)max_out);
 }
 
 // merged value key of packed entry e of the previous row
@@ -336,7 +254,7 @@ __device__ __forceinline__ void prev_get(const SS& S, const PrevAcc& P, uint32_t
 
 extern __shared__ __align__(16) unsigned char sp_smem[];
 
-__global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, SparseIO io, uint32_t cap, uint32_t hcap, uint32_t gcap) {
+__global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, SparseIO io, uint32_t cap, uint32_t hcap) {
     const SJob jb = jobs[blockIdx.x];
     if (jb.active_idx >= 0 && !io.active[jb.active_idx]) return;
     if (jb.n_rows == 0) return;
@@ -364,14 +282,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     S.la_slot[0] = (uint16_t*)take(2 * cap); S.la_slot[1] = (uint16_t*)take(2 * cap); S.act_slot = (uint16_t*)take(2 * cap);
     S.dlist = (uint16_t*)take(2 * cap);
     S.ccap = 4 * cap; S.ccell = (unsigned short*)take(2 * (size_t)S.ccap); S.cpre = (uint32_t*)take(4 * ((size_t)S.ccap + 1));
-    S.gsrc = (uint16_t*)take(2 * MAX_ACTIVE);
-    S.gcap = gcap; S.ghmask = 2 * gcap - 1; S.ghshift = gcap ? 32 - (31 - __clz(2 * gcap)) : 0;
-    S.g_cnt = (uint32_t*)take(16);
-    S.g_init = (double*)take(8 * (size_t)gcap); S.g_pt = (double*)take(16 * (size_t)gcap); S.g_ct = (double*)take(16 * (size_t)gcap);
-    S.g_pn = (uint32_t*)take(8 * (size_t)gcap); S.g_cn = (uint32_t*)take(8 * (size_t)gcap);
-    S.g_key = (uint32_t*)take(8 * (size_t)gcap); S.g_meta = (uint32_t*)take(4 * (size_t)gcap); S.g_val = (uint16_t*)take(4 * (size_t)gcap);
-    for (uint32_t h = threadIdx.x; h < 2 * gcap; h += blockDim.x) S.g_key[h] = 0;
-    if (threadIdx.x < 4) S.g_cnt[threadIdx.x] = 0;
+    S.wt = (uint32_t*)take(4 * 64); S.tog = 0; S.ecall = 0;
 
     __shared__ XF s_mb, s_ib;          // begin scalars of the previous row (forward) / ib of the next row (backward)
     __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
@@ -381,23 +292,6 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     const double* trans = G.trans + (size_t)jb.x * G.E;
     const bool fwd = jb.dir == 0;
     const bool adaptive = (jb.mode == SP_TOPN || jb.mode == SP_RATIO);
-    // neighbourhood walks in CSR order, from the job's cache when the node is in it
-    auto for_parents = [&](uint32_t id, int cs, auto&& f) {
-        if (cs >= 0) {
-            const uint32_t np = S.g_meta[cs] & 15u;
-            for (uint32_t k = 0; k < np; k++) f(S.g_pn[2 * cs + k], S.g_pt[2 * cs + k]);
-        } else {
-            for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) f(G.par_node[e], trans[G.par_eid[e]]);
-        }
-    };
-    auto for_children = [&](uint32_t id, int cs, auto&& f) {
-        if (cs >= 0) {
-            const uint32_t meta = S.g_meta[cs], nc = (meta >> 4) & 15u;
-            for (uint32_t k = 0; k < nc; k++) f(S.g_cn[2 * cs + k], S.g_ct[2 * cs + k], (uint8_t)(meta >> (16 + 8 * k)));
-        } else {
-            for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) { const uint32_t ch = G.chi_node[e]; f(ch, trans[G.chi_eid[e]], G.emission[ch]); }
-        }
-    };
     if (tid == 0) {
         s_page_left = 0; s_page_off = 0; s_fail = SJ_OK; s_cells = 0;
         if (fwd) {
@@ -466,33 +360,26 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 n_top = (int)fr.n_mi;
             }
         }
-        if (n_top > (int)cap && tid == 0) s_fail = SJ_NEED_BIG;
+        if (n_top > (int)cap && tid == 0) s_fail = SJ_NEED_BIG;   // list scratch is sized by cap
         __syncthreads();
         if (s_fail) break;
 
-        // ---------------- 2. reset the current row ; flush the graph cache when it filled up during the last row
+        // ---------------- 2. reset the current row
         uint32_t n_ent = 0;
         for (uint32_t h = tid; h < hcap; h += B) { S.ch_key[h] = 0; S.ch_val[h] = SP_ABSENT; }
-        if (gcap && S.g_cnt[1]) {
-            __syncthreads();
-            for (uint32_t h = tid; h < 2 * gcap; h += B) S.g_key[h] = 0;
-            if (tid < 4) S.g_cnt[tid] = 0;
-        }
         __syncthreads();
-        if (adaptive) gc_ensure(S, G, trans, init, S.top_id, n_top);
 
         // ---------------- 3. the step's `nodes` (they hold m, i)
         int n_act = 0;
         bool ok = true;
         if (fwd) {
             // forward sparse: nodes = to_childs_and_us(top) (forward.rs:148) ; mapping: nodes = mapping.nodes(i)
-            ok = sp_expand(S, S.top_id, n_top, G.chi_off, G.chi_node, true, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
+            ok = sp_expand(S, S.top_id, n_top, G.chi_off, G.chi_node, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
         } else {
             // backward sparse: M/I over to_parents_and_us(nodes) (backward.rs:243-259) ; non-adaptive: nodes themselves
-            ok = sp_expand(S, S.top_id, n_top, G.par_off, G.par_node, false, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
+            ok = sp_expand(S, S.top_id, n_top, G.par_off, G.par_node, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
         }
         if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
-        gc_ensure(S, G, trans, init, S.act_id, n_act);
         const uint32_t n_mi = (uint32_t)n_act;
         const uint32_t stamp0 = s * 8 + 1;
         uint32_t n_d = 0;
@@ -503,16 +390,14 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             const XF ib_cur = xmul(xadd(xmul(s_mb, lp.p_MI), xmul(s_ib, lp.p_II)), lp.p_random);
             for (uint32_t a = tid; a < n_mi; a += B) {
                 uint32_t id = S.act_id[a], sl = S.act_slot[a];
-                const int cs = gc_find(S, id);
                 XF acc = xf_zero();
-                for_parents(id, cs, [&](uint32_t pn, double tr) {
+                for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
                     double pm, pi, pd; int pe;
-                    prev_get(S, PA, pn, &pm, &pi, &pd, &pe);
-                    acc = xadd(acc, xf(tr * (lp.p_MM * pm + lp.p_IM * pi + lp.p_DM * pd), pe));
-                });
-                acc = xadd(acc, xmul(fb0, cs >= 0 ? S.g_init[cs] : init[id]));
-                const uint8_t em = cs >= 0 ? (uint8_t)(S.g_meta[cs] >> 8) : G.emission[id];
-                XF m = xmul(acc, em == x ? lp.p_match : lp.p_mismatch);
+                    prev_get(S, PA, G.par_node[e], &pm, &pi, &pd, &pe);
+                    acc = xadd(acc, xf(trans[G.par_eid[e]] * (lp.p_MM * pm + lp.p_IM * pi + lp.p_DM * pd), pe));
+                }
+                acc = xadd(acc, xmul(fb0, init[id]));
+                XF m = xmul(acc, G.emission[id] == x ? lp.p_match : lp.p_mismatch);
                 double pm, pi, pd; int pe;
                 prev_get(S, PA, id, &pm, &pi, &pd, &pe);
                 XF i = xf(lp.p_random * (lp.p_MI * pm + lp.p_II * pi + lp.p_DI * pd), pe);
@@ -527,9 +412,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 uint32_t* l_id = S.la_id[t & 1]; uint16_t* l_slot = S.la_slot[t & 1];
                 int n_l = 0;
                 if (adaptive) {
-                    ok = sp_expand(S, src_id, n_src, G.chi_off, G.chi_node, true, false, true, l_id, l_slot, MAX_ACTIVE, &n_ent, &n_l);
+                    ok = sp_expand(S, src_id, n_src, G.chi_off, G.chi_node, false, true, l_id, l_slot, MAX_ACTIVE, &n_ent, &n_l);
                     if (!ok) break;
-                    gc_ensure(S, G, trans, init, l_id, n_l);
                 } else {
                     n_l = n_act;
                     for (int a = tid; a < n_l; a += B) { l_id[a] = S.act_id[a]; l_slot[a] = S.act_slot[a]; }
@@ -537,32 +421,32 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 }
                 double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint32_t* st = S.dstamp[t & 1];
                 const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint32_t* stp = S.dstamp[(t & 1) ^ 1];
-                for (int a = tid; a < n_l; a += B) {
-                    uint32_t id = l_id[a], sl = l_slot[a];
-                    const int cs = gc_find(S, id);
-                    XF acc = xf_zero();
-                    for_parents(id, cs, [&](uint32_t pn, double tr) {
-                        int ps = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, pn);
-                        if (ps < 0) return;
-                        if (t == 0) { if ((uint32_t)ps < n_mi) acc = xadd(acc, xf(tr * (lp.p_MD * S.c_m[ps] + lp.p_ID * S.c_i[ps]), S.c_mie[ps])); }
-                        else if (stp[ps] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[ps], dep[ps]));
-                    });
-                    if (t == 0) acc = xadd(acc, xmul(ib_cur, lp.p_ID * (cs >= 0 ? S.g_init[cs] : init[id])));
-                    dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
-                    XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
-                    S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
+                for (int a0 = 0; a0 < n_l; a0 += B) {
+                    const int a = a0 + tid;
+                    uint32_t sl = 0, fresh = 0;
+                    if (a < n_l) {
+                        const uint32_t id = l_id[a];
+                        sl = l_slot[a];
+                        XF acc = xf_zero();
+                        for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
+                            int ps = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, G.par_node[e]);
+                            if (ps < 0) continue;
+                            double tr = trans[G.par_eid[e]];
+                            if (t == 0) { if ((uint32_t)ps < n_mi) acc = xadd(acc, xf(tr * (lp.p_MD * S.c_m[ps] + lp.p_ID * S.c_i[ps]), S.c_mie[ps])); }
+                            else if (stp[ps] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[ps], dep[ps]));
+                        }
+                        if (t == 0) acc = xadd(acc, xmul(ib_cur, lp.p_ID * init[id]));
+                        dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
+                        XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
+                        S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
+                        fresh = S.d_seen[sl] ? 0u : 1u;
+                    }
+                    // d insertion order: first time a slot receives a Del value
+                    uint32_t n_new;
+                    const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
+                    if (fresh) { if (o < cap) S.dlist[o] = (uint16_t)sl; S.d_seen[sl] = 1; }
+                    n_d += n_new;
                 }
-                // d insertion order: first time a slot receives a Del value
-                for (int a = tid; a < n_l; a += B) { uint32_t sl = l_slot[a]; S.scan[a] = S.d_seen[sl] ? 0u : 1u; }
-                __syncthreads();
-                uint32_t n_new = block_exscan(S.scan, n_l);
-                for (int a = tid; a < n_l; a += B) {
-                    uint32_t sl = l_slot[a];
-                    if (!S.d_seen[sl]) { uint32_t o = n_d + S.scan[a]; if (o < cap) S.dlist[o] = (uint16_t)sl; }
-                }
-                __syncthreads();
-                for (int a = tid; a < n_l; a += B) S.d_seen[l_slot[a]] = 1;
-                n_d += n_new;
                 __syncthreads();
                 src_id = l_id; n_src = n_l;
             }
@@ -584,45 +468,46 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 if (t == 0 || !adaptive) { l_id = S.act_id; l_slot = S.act_slot; n_l = n_act; }  // A0 == to_parents_and_us(nodes)
                 else {
                     int nn = 0;
-                    ok = sp_expand(S, src_id, n_src, G.par_off, G.par_node, false, true, true, S.la_id[t & 1], S.la_slot[t & 1], MAX_ACTIVE, &n_ent, &nn);
+                    ok = sp_expand(S, src_id, n_src, G.par_off, G.par_node, true, true, S.la_id[t & 1], S.la_slot[t & 1], MAX_ACTIVE, &n_ent, &nn);
                     if (!ok) break;
-                    gc_ensure(S, G, trans, init, S.la_id[t & 1], nn);
                     l_id = S.la_id[t & 1]; l_slot = S.la_slot[t & 1]; n_l = nn;
                 }
                 double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint32_t* st = S.dstamp[t & 1];
                 const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint32_t* stp = S.dstamp[(t & 1) ^ 1];
-                for (int a = tid; a < n_l; a += B) {
-                    uint32_t id = l_id[a], sl = l_slot[a];
-                    XF acc = xf_zero();
-                    for_children(id, gc_find(S, id), [&](uint32_t ch, double tr, uint8_t em) {
+                for (int a0 = 0; a0 < n_l; a0 += B) {
+                    const int a = a0 + tid;
+                    uint32_t sl = 0, fresh = 0;
+                    if (a < n_l) {
+                        const uint32_t id = l_id[a];
+                        sl = l_slot[a];
+                        XF acc = xf_zero();
+                        for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) {
+                            uint32_t ch = G.chi_node[e];
+                            double tr = trans[G.chi_eid[e]];
+                            if (t == 0) {
+                                double pm, pi, pd; int pe;
+                                prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
+                                acc = xadd(acc, xf(tr * lp.p_DM * (G.emission[ch] == x ? lp.p_match : lp.p_mismatch) * pm, pe));
+                            } else {
+                                int cs = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, ch);
+                                if (cs >= 0 && stp[cs] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[cs], dep[cs]));
+                            }
+                        }
                         if (t == 0) {
                             double pm, pi, pd; int pe;
-                            prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
-                            acc = xadd(acc, xf(tr * lp.p_DM * (em == x ? lp.p_match : lp.p_mismatch) * pm, pe));
-                        } else {
-                            int cs = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, ch);
-                            if (cs >= 0 && stp[cs] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[cs], dep[cs]));
+                            prev_get(S, PA, id, &pm, &pi, &pd, &pe);
+                            acc = xadd(acc, xf(lp.p_DI * lp.p_random * pi, pe));
                         }
-                    });
-                    if (t == 0) {
-                        double pm, pi, pd; int pe;
-                        prev_get(S, PA, id, &pm, &pi, &pd, &pe);
-                        acc = xadd(acc, xf(lp.p_DI * lp.p_random * pi, pe));
+                        dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
+                        XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
+                        S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
+                        fresh = S.d_seen[sl] ? 0u : 1u;
                     }
-                    dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
-                    XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
-                    S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
+                    uint32_t n_new;
+                    const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
+                    if (fresh) { if (o < cap) S.dlist[o] = (uint16_t)sl; S.d_seen[sl] = 1; }
+                    n_d += n_new;
                 }
-                for (int a = tid; a < n_l; a += B) { uint32_t sl = l_slot[a]; S.scan[a] = S.d_seen[sl] ? 0u : 1u; }
-                __syncthreads();
-                uint32_t n_new = block_exscan(S.scan, n_l);
-                for (int a = tid; a < n_l; a += B) {
-                    uint32_t sl = l_slot[a];
-                    if (!S.d_seen[sl]) { uint32_t o = n_d + S.scan[a]; if (o < cap) S.dlist[o] = (uint16_t)sl; }
-                }
-                __syncthreads();
-                for (int a = tid; a < n_l; a += B) S.d_seen[l_slot[a]] = 1;
-                n_d += n_new;
                 __syncthreads();
                 src_id = l_id; n_src = n_l;
             }
@@ -631,17 +516,18 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             XF pmb = xf_zero(), pib = xf_zero();
             for (uint32_t a = tid; a < n_mi; a += B) {
                 uint32_t id = S.act_id[a], sl = S.act_slot[a];
-                const int gs = gc_find(S, id);
                 XF am = xf_zero(), ai = xf_zero();
-                for_children(id, gs, [&](uint32_t ch, double tr, uint8_t em) {
+                for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) {
+                    uint32_t ch = G.chi_node[e];
+                    double tr = trans[G.chi_eid[e]];
                     double pm, pi, pd; int pe;
                     prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
-                    XF tm = xf(tr * (em == x ? lp.p_match : lp.p_mismatch) * pm, pe);
+                    XF tm = xf(tr * (G.emission[ch] == x ? lp.p_match : lp.p_mismatch) * pm, pe);
                     int cs = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, ch);
                     XF td = cs >= 0 ? xf(tr * S.c_dv[cs], S.c_de[cs]) : xf_zero();
                     am = xadd(am, xadd(xmul(tm, lp.p_MM), xmul(td, lp.p_MD)));
                     ai = xadd(ai, xadd(xmul(tm, lp.p_IM), xmul(td, lp.p_ID)));
-                });
+                }
                 double pm, pi, pd; int pe;
                 prev_get(S, PA, id, &pm, &pi, &pd, &pe);
                 am = xadd(am, xf(lp.p_MI * lp.p_random * pi, pe));
@@ -650,10 +536,9 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 if (Ec == XF_ZERO_E) { S.c_m[sl] = 0.0; S.c_i[sl] = 0.0; S.c_mie[sl] = 0; }
                 else { S.c_m[sl] = am.v == 0.0 ? 0.0 : am.v * pow2i(am.e - Ec); S.c_i[sl] = ai.v == 0.0 ? 0.0 : ai.v * pow2i(ai.e - Ec); S.c_mie[sl] = Ec; }
                 // begin sums: init_l * (p_XM e_l(x) m''[l] + p_XD d[l])
-                const uint8_t em_own = gs >= 0 ? (uint8_t)(S.g_meta[gs] >> 8) : G.emission[id];
-                XF um = xf((em_own == x ? lp.p_match : lp.p_mismatch) * pm, pe);
+                XF um = xf((G.emission[id] == x ? lp.p_match : lp.p_mismatch) * pm, pe);
                 XF ud = xf(S.c_dv[sl], S.c_de[sl]);
-                double in = gs >= 0 ? S.g_init[gs] : init[id];
+                double in = init[id];
                 pmb = xadd(pmb, xmul(xadd(xmul(um, lp.p_MM), xmul(ud, lp.p_MD)), in));
                 pib = xadd(pib, xmul(xadd(xmul(um, lp.p_IM), xmul(ud, lp.p_ID)), in));
             }
@@ -717,7 +602,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     }
 }
 
-static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap, uint32_t gcap) {
+static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) {
     auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t s = 0;
     s += 9 * r16(8 * (size_t)cap);
@@ -728,7 +613,7 @@ static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap, uint32_t gcap) {
     s += 3 * r16(4 * (size_t)cap);
     s += 4 * r16(2 * (size_t)cap);
     s += r16(2 * 4 * (size_t)cap) + r16(4 * (4 * (size_t)cap + 1));
-    s += r16(2 * MAX_ACTIVE) + 16 + r16(8 * (size_t)gcap) * 4 + r16(16 * (size_t)gcap) * 2 + r16(4 * (size_t)gcap) * 2;
+    s += 4 * 64;
     return s;
 }
 
@@ -742,11 +627,7 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
     if (n_jobs == 0) return DBGPHMM_OK;
     uint32_t hcap = 1;
     while (hcap < 2 * cap) hcap <<= 1;
-    uint32_t gcap = cap <= 256 ? 256 : 0;   // graph-neighbourhood cache slots (power of two ; 0 = off)
-    if (const char* e = getenv("DBGPHMM_SPARSE_GCACHE")) { int g = atoi(e); gcap = 0; while (g > 1 && gcap == 0) { if ((g & (g - 1)) == 0) gcap = (uint32_t)g; else g &= g - 1; } }
-    if (gcap > 4096) gcap = 4096;
-    size_t smem = sparse_smem_bytes(cap, hcap, gcap);
-    if (smem > 200 * 1024 && gcap) { gcap = 0; smem = sparse_smem_bytes(cap, hcap, 0); }
+    size_t smem = sparse_smem_bytes(cap, hcap);
     if (smem > 200 * 1024) { dbg_set_error("sparse_run: capacity too large for shared memory"); return DBGPHMM_ERR_INVALID; }
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
@@ -758,7 +639,7 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
         if (carve < 10) carve = 10; if (carve > 100) carve = 100;
         cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
-    k_sparse<<<n_jobs, threads, smem, m->stream>>>(G, m->lin, d_jobs, io, cap, hcap, gcap);
+    k_sparse<<<n_jobs, threads, smem, m->stream>>>(G, m->lin, d_jobs, io, cap, hcap);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;
