@@ -691,20 +691,6 @@ k_dense_warp(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ job
 #define RS_SMEM_PER_WARP (DENSE_LMAX * (3 * 8 + 4))
 #define RS_SMEM_BYTES (WT_WARPS * RS_SMEM_PER_WARP)
 
-// (rs_slow is kept for reference; the kernel uses the inline irregular path + rs_extras)
-// full upstream sum of one position through shared memory: first neighbour (if in the tile) + extras
-__device__ __noinline__ double rs_slow(const uint16_t* __restrict__ rl_par, const uint32_t* __restrict__ rx_off, const uint16_t* __restrict__ rx_idx,
-                                       const uint32_t* __restrict__ rx_eid, const double* __restrict__ trans, uint32_t pidx, uint32_t xidx, double tr_first,
-                                       const double* a, const double* b, const double* c, double ca, double cb, double cc) {
-    double acc = 0.0;
-    const uint32_t p = rl_par[pidx];
-    if (p != 0xffffu) acc = tr_first * (ca * a[p] + cb * b[p] + cc * c[p]);
-    for (uint32_t e = rx_off[xidx], ee = rx_off[xidx + 1]; e < ee; e++) {
-        const int l = rx_idx[e];
-        acc += trans[rx_eid[e]] * (ca * a[l] + cb * b[l] + cc * c[l]);
-    }
-    return acc;
-}
 __device__ __noinline__ double rs_extras(const uint32_t* __restrict__ rx_off, const uint16_t* __restrict__ rx_idx, const uint32_t* __restrict__ rx_eid,
                                          const double* __restrict__ trans, uint32_t xidx, const double* a, const double* b, const double* c,
                                          double ca, double cb, double cc) {
@@ -715,15 +701,10 @@ __device__ __noinline__ double rs_extras(const uint32_t* __restrict__ rx_off, co
     }
     return acc;
 }
-#define RS_EXTRAS(k, A, B, C, ca, cb, cc) rs_extras(P.rx_off, P.rx_idx, P.rx_eid, trans, (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane + (k), (A), (B), (C), (ca), (cb), (cc))
-// add the lane's register-held extra contribution `xc` to slot k of arr (compile-time unrolled select)
-#define RS_ADD_X(arr, xc) do { if (tile_has_x) { _Pragma("unroll") for (int k_ = 0; k_ < RS_PER_LANE; k_++) arr[k_] += (k_ == xk) ? (xc) : 0.0; } } while (0)
-#define RS_IRR(k) ((flg >> (2 * (k))) & 1)
-#define RS_EXT(k) ((flg >> (2 * (k) + 1)) & 1)
-#define RS_SLOW(k, A, B, C, ca, cb, cc) rs_slow(P.rl_par, P.rx_off, P.rx_idx, P.rx_eid, trans, tbase + RS_PER_LANE * lane + (k), \
-                                               (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane + (k), tr[k], (A), (B), (C), (ca), (cb), (cc))
-// value of the first upstream neighbour when it is the previous position: own previous register, or lane-1's last one
-#define RS_UP(arr, k, fromlow) ((k) == 0 ? (fromlow) : arr[(k) > 0 ? (k) - 1 : 0])
+// slot 0 of a lane with several extra upstream edges: out-of-line loop (rare)
+#define RS_EXTRAS0(A, B, C, ca, cb, cc) rs_extras(P.rx_off, P.rx_idx, P.rx_eid, trans, (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane, (A), (B), (C), (ca), (cb), (cc))
+// first upstream neighbour of slot k: slot 0 reads the staged copy at pp0, the others the previous register
+#define RS_UP(arr, buf, k) ((k) == 0 ? (buf)[pp0] : arr[(k) > 0 ? (k) - 1 : 0])
 
 template <bool FWD>
 __global__ void __launch_bounds__(WT_WARPS * 32, WT_MIN_CTAS)
@@ -737,46 +718,36 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
     double* sa = (double*)(rs_raw + (size_t)warp * RS_SMEM_PER_WARP);
     double* sb = sa + DENSE_LMAX; double* sc = sb + DENSE_LMAX; int* se = (int*)(sc + DENSE_LMAX);
     const uint32_t tbase = c * DENSE_LMAX;
-    const int core0 = P.rl_core[2 * c], ncore = P.rl_core[2 * c + 1];
-    const uint32_t g0 = P.chunk_start[c];
+    const uint32_t g0 = P.chunk_start[c], ncore = P.chunk_start[c + 1] - g0;
     // ---- tile structure: slot-major node ids for global IO, owned positions for the recurrences
     uint32_t ion[RS_PER_LANE];
-    uint32_t own_node[RS_PER_LANE], own_eid[RS_PER_LANE];
-    unsigned int emc = 0, flg = 0;   // 3-bit base codes and 2-bit flags of the owned positions
-    int ppos[RS_PER_LANE];           // position of the first upstream neighbour (used when it is not the previous position)
+    unsigned int emc = 0;     // 3-bit base codes of the owned positions
+    unsigned int cmask = 0;   // bit k: owned position k is a core node ; bit 8 + q: IO position 32 q + lane is a core node
 #pragma unroll
-    for (int q = 0; q < RS_PER_LANE; q++) ion[q] = P.rl_node[tbase + 32 * q + lane];
+    for (int q = 0; q < RS_PER_LANE; q++) { ion[q] = P.rl_node[tbase + 32 * q + lane]; cmask |= (ion[q] - g0 < ncore ? 1u : 0u) << (8 + q); }
 #pragma unroll
     for (int k = 0; k < RS_PER_LANE; k++) {
-        const uint32_t pi_ = tbase + RS_PER_LANE * lane + k;
-        own_node[k] = P.rl_node[pi_]; own_eid[k] = P.rl_eid[pi_];
+        const uint32_t nd = P.rl_node[tbase + RS_PER_LANE * lane + k];
         unsigned int code = 4;
-        if (own_node[k] != 0xffffffffu) { unsigned char ch = G.emission[own_node[k]]; code = ch == 'n' ? 4 : ((ch >> 1) & 3); }
+        if (nd != 0xffffffffu) { unsigned char ch = G.emission[nd]; code = ch == 'n' ? 4 : ((ch >> 1) & 3); }
         emc |= code << (3 * k);
-        flg |= (unsigned int)(P.rl_flag[pi_] & 3) << (2 * k);
-        { const uint32_t pp = P.rl_par[pi_]; ppos[k] = pp == 0xffffu ? 0 : (int)pp; }
+        cmask |= (nd - g0 < ncore ? 1u : 0u) << k;
     }
+    // Slot 0 of the lane: position of its first upstream neighbour (the layout puts every node whose neighbour is not the
+    // previous position, or that has further upstream edges, on a slot 0).  ONE extra edge is kept in registers
+    // (source position xp, edge id xe -> transition xt); more take the out-of-line loop.
+    const int pp0 = P.rl_par[tbase + RS_PER_LANE * lane];
+    int xp = 0; uint32_t xe = 0xffffffffu; double xt = 0.0; bool ext0 = false;
+    if (P.rl_flag[tbase + RS_PER_LANE * lane] & 2) {
+        const size_t xi = (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane;
+        const uint32_t a0 = P.rx_off[xi], a1 = P.rx_off[xi + 1];
+        if (a1 - a0 == 1) { xp = P.rx_idx[a0]; xe = P.rx_eid[a0]; } else ext0 = true;
+    }
+    const bool tile_has_x = __any_sync(0xffffffffu, xe != 0xffffffffu);
+    const bool tile_has_xx = __any_sync(0xffffffffu, ext0);
     double tr[RS_PER_LANE], init_[RS_PER_LANE];
 #pragma unroll
     for (int k = 0; k < RS_PER_LANE; k++) { tr[k] = 0.0; init_[k] = 0.0; }
-    // Extra upstream edges (merge nodes).  A lane whose owned positions carry exactly ONE extra edge keeps it in registers
-    // (slot xk, source position xp, edge id xe -> transition xt); lanes with more fall back to the out-of-line loop.
-    int xk = -1, xp = 0; uint32_t xe = 0xffffffffu; double xt = 0.0;
-    {
-        int n_x = 0;
-#pragma unroll
-        for (int k = 0; k < RS_PER_LANE; k++) {
-            if (RS_EXT(k)) {
-                const size_t xi = (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane + k;
-                const uint32_t a0 = P.rx_off[xi], a1 = P.rx_off[xi + 1];
-                n_x += (int)(a1 - a0);
-                if (a1 - a0 == 1 && xk < 0) { xk = k; xp = P.rx_idx[a0]; xe = P.rx_eid[a0]; }
-            }
-        }
-        if (n_x == 1) flg &= ~0xAAAu;          // the single extra lives in registers: clear the out-of-line flags
-        else { xk = -1; xe = 0xffffffffu; }    // none, or several: keep the generic path
-    }
-    const bool tile_has_x = __any_sync(0xffffffffu, xk >= 0);
     int staged_x = -1;
     const double* trans = G.trans;
     const uint32_t job0 = blockIdx.y * jpc;
@@ -819,8 +790,9 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             trans = G.trans + (size_t)hx * G.E;
 #pragma unroll
             for (int k = 0; k < RS_PER_LANE; k++) {
-                init_[k] = own_node[k] == 0xffffffffu ? 0.0 : init[own_node[k]];
-                tr[k] = own_eid[k] == 0xffffffffu ? 0.0 : trans[own_eid[k]];
+                const uint32_t nd = P.rl_node[tbase + RS_PER_LANE * lane + k], ed = P.rl_eid[tbase + RS_PER_LANE * lane + k];
+                init_[k] = nd == 0xffffffffu ? 0.0 : init[nd];
+                tr[k] = ed == 0xffffffffu ? 0.0 : trans[ed];
             }
             xt = xe == 0xffffffffu ? 0.0 : trans[xe];
             staged_x = hx;
@@ -851,7 +823,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
         elo = __reduce_min_sync(0xffffffffu, elo); ehi = __reduce_max_sync(0xffffffffu, ehi);
         double* om = (double*)out_ptr; double* oi = om + Np; double* od = oi + Np; int* oe = (int*)(od + Np);
         if (ehi == EXP_NONE_HI_) {  // nothing but zeros flows into this tile: the row is zero here
-            for (int j = lane; j < ncore; j += 32) { om[g0 + j] = 0.0; oi[g0 + j] = 0.0; od[g0 + j] = 0.0; oe[g0 + j] = 0; }
+            for (uint32_t j = lane; j < ncore; j += 32) { om[g0 + j] = 0.0; oi[g0 + j] = 0.0; od[g0 + j] = 0.0; oe[g0 + j] = 0; }
             if (lane == 0) {
                 if (FWD) partials[(size_t)job_idx * n_tiles + c] = xf_zero();
                 else { partials[((size_t)job_idx * n_tiles + c) * 2] = xf_zero(); partials[((size_t)job_idx * n_tiles + c) * 2 + 1] = xf_zero(); }
@@ -884,17 +856,14 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             const double ibv = ib_cur.v == 0.0 ? 0.0 : ib_cur.v * pow2i(ib_cur.e - Eref);
             // round A: fm, fi (forward.rs:337-388)
             {
-                const double lm = __shfl_up_sync(0xffffffffu, pm[RS_PER_LANE - 1], 1), li = __shfl_up_sync(0xffffffffu, pi[RS_PER_LANE - 1], 1),
-                             ld = __shfl_up_sync(0xffffffffu, pd[RS_PER_LANE - 1], 1);
-                double xc = 0.0;
-                if (tile_has_x && xk >= 0) xc = xt * (lp.p_MM * sa[xp] + lp.p_IM * sb[xp] + lp.p_DM * sc[xp]);
+                double x0 = 0.0;
+                if (tile_has_x) x0 = xt * (lp.p_MM * sa[xp] + lp.p_IM * sb[xp] + lp.p_DM * sc[xp]);
+                if (tile_has_xx && ext0) x0 += RS_EXTRAS0(sa, sb, sc, lp.p_MM, lp.p_IM, lp.p_DM);
 #pragma unroll
                 for (int k = 0; k < RS_PER_LANE; k++) {
-                    double um = RS_UP(pm, k, lm), ui = RS_UP(pi, k, li), ud = RS_UP(pd, k, ld);
-                    if (RS_IRR(k)) { um = sa[ppos[k]]; ui = sb[ppos[k]]; ud = sc[ppos[k]]; }
+                    const double um = RS_UP(pm, sa, k), ui = RS_UP(pi, sb, k), ud = RS_UP(pd, sc, k);
                     double acc = tr[k] * (lp.p_MM * um + lp.p_IM * ui + lp.p_DM * ud);
-                    if (RS_EXT(k)) acc += RS_EXTRAS(k, sa, sb, sc, lp.p_MM, lp.p_IM, lp.p_DM);
-                    if (tile_has_x) acc += (k == xk) ? xc : 0.0;
+                    if (k == 0) acc += x0;
                     acc += fbv * init_[k];
                     cm[k] = acc * (((emc >> (3 * k)) & 7) == x ? lp.p_match : lp.p_mismatch);
                     ci[k] = lp.p_random * (lp.p_MI * pm[k] + lp.p_II * pi[k] + lp.p_DI * pd[k]);
@@ -906,16 +875,14 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             __syncwarp();
             // round B: fd0 (forward.rs:480-501)
             {
-                const double lm = __shfl_up_sync(0xffffffffu, cm[RS_PER_LANE - 1], 1), li = __shfl_up_sync(0xffffffffu, ci[RS_PER_LANE - 1], 1);
-                double xc = 0.0;
-                if (tile_has_x && xk >= 0) xc = xt * (lp.p_MD * sa[xp] + lp.p_ID * sb[xp]);
+                double x0 = 0.0;
+                if (tile_has_x) x0 = xt * (lp.p_MD * sa[xp] + lp.p_ID * sb[xp]);
+                if (tile_has_xx && ext0) x0 += RS_EXTRAS0(sa, sb, sb, lp.p_MD, lp.p_ID, 0.0);
 #pragma unroll
                 for (int k = 0; k < RS_PER_LANE; k++) {
-                    double um = RS_UP(cm, k, lm), ui = RS_UP(ci, k, li);
-                    if (RS_IRR(k)) { um = sa[ppos[k]]; ui = sb[ppos[k]]; }
+                    const double um = RS_UP(cm, sa, k), ui = RS_UP(ci, sb, k);
                     double acc = tr[k] * (lp.p_MD * um + lp.p_ID * ui);
-                    if (RS_EXT(k)) acc += RS_EXTRAS(k, sa, sb, sb, lp.p_MD, lp.p_ID, 0.0);
-                    if (tile_has_x) acc += (k == xk) ? xc : 0.0;
+                    if (k == 0) acc += x0;
                     acc += ibv * (lp.p_ID * init_[k]);
                     dcur[k] = acc; dacc[k] = acc;
                 }
@@ -927,17 +894,14 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
 #pragma unroll
             for (int t = 1; t < N_DEL_ROUNDS; t++) {
                 double* prevbuf = (t & 1) ? sc : sa; double* curbuf = (t & 1) ? sa : sc;
-                const double ld = __shfl_up_sync(0xffffffffu, dcur[RS_PER_LANE - 1], 1);
+                double x0 = 0.0;
+                if (tile_has_x) x0 = xt * lp.p_DD * prevbuf[xp];
+                if (tile_has_xx && ext0) x0 += RS_EXTRAS0(prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
                 double nxt[RS_PER_LANE];
-                double xc = 0.0;
-                if (tile_has_x && xk >= 0) xc = xt * lp.p_DD * prevbuf[xp];
 #pragma unroll
                 for (int k = 0; k < RS_PER_LANE; k++) {
-                    double up = RS_UP(dcur, k, ld);
-                    if (RS_IRR(k)) up = prevbuf[ppos[k]];
-                    double v = tr[k] * lp.p_DD * up;
-                    if (RS_EXT(k)) v += RS_EXTRAS(k, prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
-                    if (tile_has_x) v += (k == xk) ? xc : 0.0;
+                    double v = tr[k] * lp.p_DD * RS_UP(dcur, prevbuf, k);
+                    if (k == 0) v += x0;
                     nxt[k] = v;
                 }
 #pragma unroll
@@ -958,16 +922,13 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             __syncwarp();
             // bd0 (backward.rs:354-377)
             {
-                const double lm = __shfl_up_sync(0xffffffffu, pm[RS_PER_LANE - 1], 1);
-                double xc = 0.0;
-                if (tile_has_x && xk >= 0) xc = xt * lp.p_DM * sa[xp];
+                double x0 = 0.0;
+                if (tile_has_x) x0 = xt * lp.p_DM * sa[xp];
+                if (tile_has_xx && ext0) x0 += RS_EXTRAS0(sa, sa, sa, lp.p_DM, 0.0, 0.0);
 #pragma unroll
                 for (int k = 0; k < RS_PER_LANE; k++) {
-                    double um = RS_UP(pm, k, lm);
-                    if (RS_IRR(k)) um = sa[ppos[k]];
-                    double acc = tr[k] * lp.p_DM * um;
-                    if (RS_EXT(k)) acc += RS_EXTRAS(k, sa, sa, sa, lp.p_DM, 0.0, 0.0);
-                    if (tile_has_x) acc += (k == xk) ? xc : 0.0;
+                    double acc = tr[k] * lp.p_DM * RS_UP(pm, sa, k);
+                    if (k == 0) acc += x0;
                     acc += lp.p_DI * lp.p_random * pi[k];
                     dcur[k] = acc; dacc[k] = acc;
                 }
@@ -979,17 +940,14 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
 #pragma unroll
             for (int t = 1; t < N_DEL_ROUNDS; t++) {
                 double* prevbuf = (t & 1) ? sc : sb; double* curbuf = (t & 1) ? sb : sc;
-                const double ld = __shfl_up_sync(0xffffffffu, dcur[RS_PER_LANE - 1], 1);
+                double x0 = 0.0;
+                if (tile_has_x) x0 = xt * lp.p_DD * prevbuf[xp];
+                if (tile_has_xx && ext0) x0 += RS_EXTRAS0(prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
                 double nxt[RS_PER_LANE];
-                double xc = 0.0;
-                if (tile_has_x && xk >= 0) xc = xt * lp.p_DD * prevbuf[xp];
 #pragma unroll
                 for (int k = 0; k < RS_PER_LANE; k++) {
-                    double up = RS_UP(dcur, k, ld);
-                    if (RS_IRR(k)) up = prevbuf[ppos[k]];
-                    double v = tr[k] * lp.p_DD * up;
-                    if (RS_EXT(k)) v += RS_EXTRAS(k, prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
-                    if (tile_has_x) v += (k == xk) ? xc : 0.0;
+                    double v = tr[k] * lp.p_DD * RS_UP(dcur, prevbuf, k);
+                    if (k == 0) v += x0;
                     nxt[k] = v;
                 }
 #pragma unroll
@@ -1005,19 +963,17 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             for (int k = 0; k < RS_PER_LANE; k++) sc[RS_PER_LANE * lane + k] = dacc[k];
             __syncwarp();
             {
-                const double lm = __shfl_up_sync(0xffffffffu, pm[RS_PER_LANE - 1], 1), ld = __shfl_up_sync(0xffffffffu, dacc[RS_PER_LANE - 1], 1);
-                double xcm = 0.0, xci = 0.0;
-                if (tile_has_x && xk >= 0) { xcm = xt * (lp.p_MM * sa[xp] + lp.p_MD * sc[xp]); xci = xt * (lp.p_IM * sa[xp] + lp.p_ID * sc[xp]); }
+                double xm = 0.0, xi_ = 0.0;
+                if (tile_has_x) { xm = xt * (lp.p_MM * sa[xp] + lp.p_MD * sc[xp]); xi_ = xt * (lp.p_IM * sa[xp] + lp.p_ID * sc[xp]); }
+                if (tile_has_xx && ext0) {
+                    xm += RS_EXTRAS0(sa, sc, sc, lp.p_MM, lp.p_MD, 0.0);
+                    xi_ += RS_EXTRAS0(sa, sc, sc, lp.p_IM, lp.p_ID, 0.0);
+                }
 #pragma unroll
                 for (int k = 0; k < RS_PER_LANE; k++) {
-                    double um = RS_UP(pm, k, lm), ud = RS_UP(dacc, k, ld);
-                    if (RS_IRR(k)) { um = sa[ppos[k]]; ud = sc[ppos[k]]; }
+                    const double um = RS_UP(pm, sa, k), ud = RS_UP(dacc, sc, k);
                     double am = tr[k] * (lp.p_MM * um + lp.p_MD * ud), ai = tr[k] * (lp.p_IM * um + lp.p_ID * ud);
-                    if (tile_has_x) { am += (k == xk) ? xcm : 0.0; ai += (k == xk) ? xci : 0.0; }
-                    if (RS_EXT(k)) {
-                        am += RS_EXTRAS(k, sa, sc, sc, lp.p_MM, lp.p_MD, 0.0);
-                        ai += RS_EXTRAS(k, sa, sc, sc, lp.p_IM, lp.p_ID, 0.0);
-                    }
+                    if (k == 0) { am += xm; ai += xi_; }
                     cm[k] = am + lp.p_MI * lp.p_random * pi[k];
                     ci[k] = ai + lp.p_II * lp.p_random * pi[k];
                 }
@@ -1034,7 +990,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             int qx = 0; double scl = 0.0;
             if (mx != 0.0) { qx = ilogb_pos(mx); scl = pow2i(-qx); }
             sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = mx != 0.0 ? Eref + qx : 0;
-            if (pos >= core0 && pos < core0 + ncore) {
+            if ((cmask >> k) & 1) {
                 if (FWD) part += m + i + d;
                 else { part += (pm[k] * lp.p_MM + d * lp.p_MD) * init_[k]; part2 += (pm[k] * lp.p_IM + d * lp.p_ID) * init_[k]; }
             }
@@ -1043,8 +999,8 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
 #pragma unroll
         for (int q = 0; q < RS_PER_LANE; q++) {
             const int pos = 32 * q + lane;
-            if (pos >= core0 && pos < core0 + ncore) {
-                const uint32_t g = g0 + (uint32_t)(pos - core0);
+            if ((cmask >> (8 + q)) & 1) {
+                const uint32_t g = ion[q];
                 om[g] = sa[pos]; oi[g] = sb[pos]; od[g] = sc[pos]; oe[g] = se[pos];
             }
         }

@@ -4,6 +4,7 @@
 
 #define DENSE_CORE 128      // nodes of a tile (owned by one warp of the common-frame kernel)
 #define DENSE_LMAX 160      // tile + 6-hop halo capacity
+#define DENSE_PER_LANE (DENSE_LMAX / 32)   // register-stencil kernel: consecutive positions owned by one lane
 #define DENSE_EMAX 256      // local upstream edges of one tile
 #define DENSE_XMAX 64       // of which beyond the first of each node ("extras")
 #define DENSE_THREADS 64    // exact (per-value exponent) kernel: one CTA per tile

@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include "model.h"
 #include "dense.h"
 #include "sparse.h"
@@ -86,8 +88,73 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
     uint32_t start = 0, cidx = 0, max_local = 0;
     chunk_start.push_back(0);
     loc_base.push_back(0);
+    std::vector<uint32_t> lay;   // register-stencil layout of the current tile: node per position, 0xffffffff = pad
     while (start < N) {
         uint32_t size = std::min<uint32_t>(DENSE_CORE, N - start);
+        // Order the tile's nodes as [chain above the tile head | core | remaining halo chains] so that a node's first upstream
+        // neighbour is usually the previous position, then pad so that every node whose first neighbour is elsewhere or
+        // that has further upstream edges in the tile sits on slot 0 of a lane (position % DENSE_PER_LANE == 0): the kernel
+        // specialises slot 0 and keeps the other slots a pure register stencil.  false = does not fit DENSE_LMAX.
+        auto build_layout = [&]() -> bool {
+            std::vector<uint32_t> order; order.reserve(DENSE_LMAX);
+            std::vector<uint8_t> placed(local.size(), 0);
+            auto in_tile = [&](uint32_t u) { return stamp[u] == cidx; };
+            // core in ascending node order when the first upstream neighbour of v is usually v - 1 (forward: the relabelling
+            // makes a parent the predecessor), descending when it is v + 1 (backward: upstream = children)
+            uint32_t n_prev = 0, n_next = 0;
+            for (uint32_t q = 0; q < size; q++) {
+                const uint32_t x = local[q];
+                if (up_off[x + 1] == up_off[x]) continue;
+                const uint32_t u = up_node[up_off[x]];
+                if (u + 1 == x) n_prev++; else if (u == x + 1) n_next++;
+            }
+            const bool descending = n_next > n_prev;
+            std::vector<uint32_t> head;
+            uint32_t v = descending ? local[size - 1] : local[0];
+            for (int h = 0; h < HALO_HOPS; h++) {   // chain of first upstream neighbours above the tile head, deepest first
+                if (up_off[v + 1] == up_off[v]) break;
+                uint32_t u = up_node[up_off[v]];
+                if (!in_tile(u) || lidx[u] < size || placed[lidx[u]]) break;
+                placed[lidx[u]] = 1; head.push_back(u); v = u;
+            }
+            for (size_t q = head.size(); q-- > 0;) order.push_back(head[q]);
+            for (uint32_t q = 0; q < size; q++) { order.push_back(local[descending ? size - 1 - q : q]); placed[q] = 1; }
+            // remaining halo nodes: chains following "x is the first upstream neighbour of the next", deepest first
+            for (size_t q = local.size(); q-- > size;) {   // local is depth-sorted: start from the deepest
+                if (placed[q]) continue;
+                uint32_t x = local[q];
+                for (;;) {   // climb to the top of x's unplaced first-neighbour chain
+                    if (up_off[x + 1] == up_off[x]) break;
+                    uint32_t u = up_node[up_off[x]];
+                    if (!in_tile(u) || placed[lidx[u]]) break;
+                    x = u;
+                }
+                for (;;) {   // walk down: append x, then an unplaced halo node whose first neighbour is x
+                    placed[lidx[x]] = 1; order.push_back(x);
+                    uint32_t nxt = 0xffffffffu;
+                    for (size_t r = size; r < local.size(); r++) {
+                        uint32_t y = local[r];
+                        if (!placed[r] && up_off[y + 1] > up_off[y] && up_node[up_off[y]] == x) { nxt = y; break; }
+                    }
+                    if (nxt == 0xffffffffu) break;
+                    x = nxt;
+                }
+            }
+            lay.clear();
+            for (size_t q = 0; q < order.size(); q++) {
+                const uint32_t x = order[q];
+                bool special = false, first = true;
+                for (uint32_t a = up_off[x]; a < up_off[x + 1]; a++) {
+                    const uint32_t u = up_node[a];
+                    if (first) { first = false; if (in_tile(u) && !(q > 0 && order[q - 1] == u)) special = true; }
+                    else if (in_tile(u)) special = true;
+                }
+                if (special) while (lay.size() % DENSE_PER_LANE) lay.push_back(0xffffffffu);
+                lay.push_back(x);
+                if (lay.size() > DENSE_LMAX) return false;
+            }
+            return true;
+        };
         for (;;) {
             // closure of [start, start+size) over HALO_HOPS upstream hops
             local.clear();
@@ -119,11 +186,12 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
                 for (size_t q = 0; q < n_need && q < local.size(); q++) { uint32_t dg = up_off[local[q] + 1] - up_off[local[q]]; if (dg > 1) n_extra += dg - 1; }
                 if (n_extra > DENSE_XMAX) ok = false;
             }
+            if (ok) ok = build_layout();
             if (ok) break;
             // undo stamps and retry with a smaller chunk
             for (uint32_t v : local) stamp[v] = 0xffffffffu;
             if (size == 1) { dbg_set_error("graph too dense: the 6-hop neighbourhood of one node exceeds the tile capacity"); return DBGPHMM_ERR_INVALID; }
-            size = std::max<uint32_t>(1, size / 2);
+            size = size > 16 ? size - 8 : std::max<uint32_t>(1, size / 2);
         }
         // emit chunk
         uint32_t base = (uint32_t)loc_node.size();
@@ -147,65 +215,30 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
         }
         le_off.push_back((uint32_t)le_idx.size());  // sentinel of this chunk
         fx_off.push_back((uint32_t)fx_idx.size());
-        // ---- register-stencil layout of this tile
+        // ---- register-stencil layout of this tile (positions computed by build_layout inside the sizing loop)
         {
-            std::vector<uint32_t> order; order.reserve(DENSE_LMAX);
-            std::vector<uint8_t> placed(local.size(), 0);
-            auto in_tile = [&](uint32_t u) { return stamp[u] == cidx; };
-            // chain of first upstream neighbours above the tile head, deepest first
-            std::vector<uint32_t> head;
-            uint32_t v = local[0];
-            for (int h = 0; h < HALO_HOPS; h++) {
-                if (up_off[v + 1] == up_off[v]) break;
-                uint32_t u = up_node[up_off[v]];
-                if (!in_tile(u) || lidx[u] < size || placed[lidx[u]]) break;
-                placed[lidx[u]] = 1; head.push_back(u); v = u;
-            }
-            for (size_t q = head.size(); q-- > 0;) order.push_back(head[q]);
-            const uint32_t core0 = (uint32_t)order.size();
-            for (uint32_t q = 0; q < size; q++) { order.push_back(local[q]); placed[q] = 1; }
-            // remaining halo nodes: chains following "x is the first upstream neighbour of the next", deepest first
-            for (size_t q = local.size(); q-- > size;) {   // local is depth-sorted: start from the deepest
-                if (placed[q]) continue;
-                uint32_t x = local[q];
-                // climb to the top of x's unplaced first-neighbour chain
-                for (;;) {
-                    if (up_off[x + 1] == up_off[x]) break;
-                    uint32_t u = up_node[up_off[x]];
-                    if (!in_tile(u) || placed[lidx[u]]) break;
-                    x = u;
-                }
-                // walk down: append x, then an unplaced halo node whose first neighbour is x
-                for (;;) {
-                    placed[lidx[x]] = 1; order.push_back(x);
-                    uint32_t nxt = 0xffffffffu;
-                    for (size_t r = size; r < local.size(); r++) {
-                        uint32_t y = local[r];
-                        if (!placed[r] && up_off[y + 1] > up_off[y] && up_node[up_off[y]] == x) { nxt = y; break; }
-                    }
-                    if (nxt == 0xffffffffu) break;
-                    x = nxt;
-                }
-            }
-            for (size_t q = 0; q < order.size(); q++) rpos[order[q]] = (uint32_t)q;
-            rl_core.push_back((uint16_t)core0); rl_core.push_back((uint16_t)size);
+            for (size_t q = 0; q < lay.size(); q++) if (lay[q] != 0xffffffffu) rpos[lay[q]] = (uint32_t)q;
+            rl_core.push_back(0); rl_core.push_back((uint16_t)size);
             for (uint32_t q = 0; q < DENSE_LMAX; q++) {
                 rx_off.push_back((uint32_t)rx_idx.size());
-                if (q >= order.size()) { rl_node.push_back(0xffffffffu); rl_par.push_back(0xffff); rl_eid.push_back(0xffffffffu); rl_flag.push_back(0); continue; }
-                uint32_t x = order[q];
-                uint16_t p0 = 0xffff; uint32_t e0 = 0xffffffffu; uint8_t fl = 0;
+                const uint16_t prevpos = (uint16_t)(q > 0 ? q - 1 : 0);
+                if (q >= lay.size() || lay[q] == 0xffffffffu) { rl_node.push_back(0xffffffffu); rl_par.push_back(prevpos); rl_eid.push_back(0xffffffffu); rl_flag.push_back(0); continue; }
+                uint32_t x = lay[q];
+                uint16_t p0 = prevpos; uint32_t e0 = 0xffffffffu; uint8_t fl = 0;
                 bool first = true;
                 for (uint32_t a = up_off[x]; a < up_off[x + 1]; a++) {
                     uint32_t u = up_node[a];
-                    bool here = in_tile(u);
-                    if (first) { first = false; if (here) { p0 = (uint16_t)rpos[u]; e0 = up_eid[a]; } }
+                    bool here = stamp[u] == cidx;
+                    if (first) { first = false; if (here) { p0 = (uint16_t)rpos[u]; e0 = up_eid[a]; if (p0 != prevpos || q == 0) fl |= 1; } }
                     else if (here) { rx_idx.push_back((uint16_t)rpos[u]); rx_eid.push_back(up_eid[a]); fl |= 2; }
                 }
-                if (p0 != 0xffff && !(q > 0 && p0 == q - 1)) fl |= 1;   // in-tile first neighbour that is not the previous position
+                // the kernel reads the first neighbour of slot 0 of a lane from rl_par and of the other slots from the previous
+                // register: build_layout put every node with fl != 0 on a slot 0
+                if (fl && q % DENSE_PER_LANE) { dbg_set_error("internal: register layout misaligned"); return DBGPHMM_ERR_INVALID; }
                 rl_node.push_back(x); rl_par.push_back(p0); rl_eid.push_back(e0); rl_flag.push_back(fl);
             }
             rx_off.push_back((uint32_t)rx_idx.size());
-            for (uint32_t x : order) rpos[x] = 0xffffffffu;
+            for (uint32_t x : lay) if (x != 0xffffffffu) rpos[x] = 0xffffffffu;
         }
         max_local = std::max<uint32_t>(max_local, (uint32_t)local.size());
         for (uint32_t v : local) stamp[v] = 0xffffffffu;  // a node may be halo of several chunks
@@ -217,6 +250,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
     }
     P.n_chunks = cidx;
     P.max_local = max_local;
+    if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] plan: %u tiles for %u nodes (%.1f core nodes per tile, capacity %d)\n", cidx, N, (double)N / cidx, DENSE_CORE);
     P.h_chunk_start = chunk_start;
     ST_TRY(upload(&P.chunk_start, chunk_start));
     ST_TRY(upload(&P.loc_base, loc_base));
