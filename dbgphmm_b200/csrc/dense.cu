@@ -687,8 +687,55 @@ k_dense_warp(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ job
 // neighbour is elsewhere (bit 0 of rl_flag) or that have further upstream edges (bit 1) take an out-of-line path through
 // the position-indexed copies kept in shared memory.  All positions are computed in every round: cells whose inputs lie
 // outside the tile become garbage-but-finite and can reach the core only after more than 6 hops, i.e. never.
+// Per-(job, step) scalars of the fast kernel, written by k_dense_prep before every step so that the tile warps get them
+// (and the address of the previous row, which the row prefetch needs one job ahead) with one 64-byte asynchronous copy.
+struct __align__(16) JStep {
+    unsigned long long prev_ptr, out_ptr;   // slab of the previous row / of this row
+    XF fb0, ib_cur;                         // forward: begin part of fm, fib (forward.rs:541-545)
+    int valid, x, pk; unsigned int base;    // 0 = skip ; parameter set ; PREV_* ; read base
+};
+static_assert(sizeof(JStep) == 64, "JStep is copied as four 16-byte pieces");
+
+template <bool FWD>
+__global__ void k_dense_prep(LinParams lp, const DJob* __restrict__ jobs, uint32_t n_jobs, uint32_t s, const uint8_t* __restrict__ bases,
+                             const RowDesc* __restrict__ desc, const int* __restrict__ active, char* __restrict__ pool, uint64_t slab_bytes,
+                             JStep* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const DJob jb = jobs[j];
+    JStep js;
+    js.prev_ptr = 0; js.out_ptr = 0; js.fb0 = xf_zero(); js.ib_cur = xf_zero(); js.valid = 0; js.x = 0; js.pk = 0; js.base = 0;
+    if (s < jb.n_steps && !(jb.active_idx >= 0 && !active[jb.active_idx])) {
+        const int row = FWD ? jb.first_row + (int)s : jb.first_row - (int)s;
+        js.valid = 1; js.x = (int)jb.x; js.base = bases[jb.base_off + row];
+        js.pk = (s == 0) ? jb.prev0_kind : PREV_SLAB;
+        js.prev_ptr = (unsigned long long)(pool + (s == 0 ? jb.prev0_slab : slab_of(jb, s - 1)) * slab_bytes);
+        js.out_ptr = (unsigned long long)(pool + slab_of(jb, s) * slab_bytes);
+        if (FWD) {
+            XF mbp, ibp;
+            if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
+            else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
+            js.ib_cur = xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random);
+            js.fb0 = xadd(xmul(mbp, lp.p_MM), xmul(ibp, lp.p_IM));
+        }
+    }
+    out[j] = js;
+}
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 #define RS_PER_LANE (DENSE_LMAX / 32)
-#define RS_SMEM_PER_WARP (DENSE_LMAX * (3 * 8 + 4))
+// per warp: frame-scaled copies sa, sb, sc + se ; raw prefetched previous row rm, ri, rd + re ; two JStep slots
+#define RS_SMEM_PER_WARP (2 * DENSE_LMAX * (3 * 8 + 4) + 2 * 64)
 #define RS_SMEM_BYTES (WT_WARPS * RS_SMEM_PER_WARP)
 
 __device__ __noinline__ double rs_extras(const uint32_t* __restrict__ rx_off, const uint16_t* __restrict__ rx_idx, const uint32_t* __restrict__ rx_eid,
@@ -708,8 +755,7 @@ __device__ __noinline__ double rs_extras(const uint32_t* __restrict__ rx_off, co
 
 template <bool FWD>
 __global__ void __launch_bounds__(WT_WARPS * 32, WT_MIN_CTAS)
-k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs, uint32_t n_jobs, uint32_t s, const uint8_t* __restrict__ bases,
-            const RowDesc* __restrict__ desc, const int* __restrict__ active, char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np,
+k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jstep, uint32_t n_jobs, uint32_t Np,
             XF* __restrict__ partials, uint32_t n_tiles, int span, unsigned long long* __restrict__ worklist, uint32_t jpc) {
     extern __shared__ __align__(16) unsigned char rs_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -717,6 +763,8 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
     if (c >= n_tiles) return;   // no block-wide barrier anywhere in this kernel
     double* sa = (double*)(rs_raw + (size_t)warp * RS_SMEM_PER_WARP);
     double* sb = sa + DENSE_LMAX; double* sc = sb + DENSE_LMAX; int* se = (int*)(sc + DENSE_LMAX);
+    double* rm = (double*)(se + DENSE_LMAX); double* ri = rm + DENSE_LMAX; double* rd = ri + DENSE_LMAX; int* re = (int*)(rd + DENSE_LMAX);
+    JStep* sj = (JStep*)(re + DENSE_LMAX);
     const uint32_t tbase = c * DENSE_LMAX;
     const uint32_t g0 = P.chunk_start[c], ncore = P.chunk_start[c + 1] - g0;
     // ---- tile structure: slot-major node ids for global IO, owned positions for the recurrences
@@ -751,39 +799,49 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
     int staged_x = -1;
     const double* trans = G.trans;
     const uint32_t job0 = blockIdx.y * jpc;
-    for (uint32_t jj = 0; jj < jpc; jj++) {
-        const uint32_t job_idx = job0 + jj;
-        if (job_idx >= n_jobs) break;
-        // ---- per-tile scalars: lane 0 prepares them, the warp receives them by shuffle
-        int valid = 0, hx = 0, pk = 0, row = 0; unsigned int xbase = 0;
-        unsigned long long prev_ptr = 0, out_ptr = 0;
-        XF fb0 = xf_zero(), ib_cur = xf_zero();
-        if (lane == 0) {
-            const DJob jb = jobs[job_idx];
-            if (s < jb.n_steps && !(jb.active_idx >= 0 && !active[jb.active_idx])) {
-                valid = 1; hx = (int)jb.x;
-                row = FWD ? jb.first_row + (int)s : jb.first_row - (int)s;
-                xbase = bases[jb.base_off + row];
-                pk = (s == 0) ? jb.prev0_kind : PREV_SLAB;
-                prev_ptr = (unsigned long long)(pool + (s == 0 ? jb.prev0_slab : slab_of(jb, s - 1)) * slab_bytes);
-                out_ptr = (unsigned long long)(pool + slab_of(jb, s) * slab_bytes);
-                if (FWD) {
-                    XF mbp, ibp;
-                    if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
-                    else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
-                    ib_cur = xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random);   // fib, forward.rs:541-545
-                    fb0 = xadd(xmul(mbp, lp.p_MM), xmul(ibp, lp.p_IM));                         // begin part of fm
-                }
+    const uint32_t n_here = job0 < n_jobs ? min(jpc, n_jobs - job0) : 0u;
+    // Software pipeline over the jobs of this warp: the scalars of job j + 2 and the previous-row tile of job j + 1 are
+    // in flight (cp.async into shared memory, no registers held) while job j is computed.
+    auto fetch_js = [&](uint32_t jj, int slot) {
+        if (lane < 4) cp_async16((char*)&sj[slot] + 16 * lane, (const char*)&jstep[job0 + jj] + 16 * lane);
+    };
+    auto fetch_rows = [&](const JStep& js) {
+        if (!js.valid || js.pk != PREV_SLAB) return;
+        const double* gm = (const double*)js.prev_ptr; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
+#pragma unroll
+        for (int q = 0; q < RS_PER_LANE; q++) {
+            if (ion[q] != 0xffffffffu) {
+                const uint32_t g = ion[q]; const int pos = 32 * q + lane;
+                cp_async8(&rm[pos], &gm[g]); cp_async8(&ri[pos], &gi[g]); if (FWD) cp_async8(&rd[pos], &gd[g]); cp_async4(&re[pos], &ge[g]);
             }
         }
-        valid = __shfl_sync(0xffffffffu, valid, 0);
-        if (!valid) continue;
-        hx = __shfl_sync(0xffffffffu, hx, 0); pk = __shfl_sync(0xffffffffu, pk, 0); xbase = __shfl_sync(0xffffffffu, xbase, 0);
-        prev_ptr = __shfl_sync(0xffffffffu, prev_ptr, 0); out_ptr = __shfl_sync(0xffffffffu, out_ptr, 0);
-        if (FWD) {
-            fb0.v = __shfl_sync(0xffffffffu, fb0.v, 0); fb0.e = __shfl_sync(0xffffffffu, fb0.e, 0);
-            ib_cur.v = __shfl_sync(0xffffffffu, ib_cur.v, 0); ib_cur.e = __shfl_sync(0xffffffffu, ib_cur.e, 0);
-        }
+    };
+    if (n_here == 0) return;
+#pragma unroll
+    for (int q = 0; q < RS_PER_LANE; q++) { const int pos = 32 * q + lane; rm[pos] = 0.0; ri[pos] = 0.0; rd[pos] = 0.0; re[pos] = 0; }   // pads stay zero
+    fetch_js(0, 0);
+    if (n_here > 1) fetch_js(1, 1);
+    cp_async_wait_all();
+    __syncwarp();
+    fetch_rows(sj[0]);
+    for (uint32_t jj = 0; jj < n_here; jj++) {
+        const uint32_t job_idx = job0 + jj;
+        const int slot = jj & 1;
+        cp_async_wait_all();
+        __syncwarp();
+        // refill the raw row and this JStep slot for the jobs ahead ; call once every lane is done reading them
+        auto prefetch_next = [&]() {
+            __syncwarp();
+            if (jj + 1 < n_here) fetch_rows(sj[slot ^ 1]);
+            if (jj + 2 < n_here) fetch_js(jj + 2, slot);
+        };
+        // ---- per-job scalars and the prefetched previous row
+        const int valid = sj[slot].valid, hx = sj[slot].x, pk = sj[slot].pk;
+        const unsigned int xbase = sj[slot].base;
+        const unsigned long long out_ptr = sj[slot].out_ptr;
+        XF fb0 = xf_zero(), ib_cur = xf_zero();
+        if (FWD) { fb0 = sj[slot].fb0; ib_cur = sj[slot].ib_cur; }
+        if (!valid) { prefetch_next(); continue; }
         const unsigned int x = (xbase >> 1) & 3;   // base code of the read base
         if (hx != staged_x) {
             const double* init = G.init + (size_t)hx * G.N;
@@ -797,19 +855,16 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             xt = xe == 0xffffffffu ? 0.0 : trans[xe];
             staged_x = hx;
         }
-        // ---- previous row: coalesced slot-major loads, exponent range by warp reductions
+        // ---- previous row from the prefetch buffer (slot-major), exponent range of the tile by warp reductions
         double vm[RS_PER_LANE], vi[RS_PER_LANE], vd[RS_PER_LANE]; int ve[RS_PER_LANE];
         int elo = EXP_NONE_LO_, ehi = EXP_NONE_HI_;
         if (pk == PREV_SLAB) {
-            const double* gm = (const double*)prev_ptr; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
 #pragma unroll
             for (int q = 0; q < RS_PER_LANE; q++) {
-                vm[q] = 0.0; vi[q] = 0.0; vd[q] = 0.0; ve[q] = 0;
-                if (ion[q] != 0xffffffffu) { const uint32_t g = ion[q]; vm[q] = gm[g]; vi[q] = gi[g]; vd[q] = FWD ? gd[g] : 0.0; ve[q] = ge[g]; }
-            }
-#pragma unroll
-            for (int q = 0; q < RS_PER_LANE; q++)
+                const int pos = 32 * q + lane;
+                vm[q] = rm[pos]; vi[q] = ri[pos]; vd[q] = FWD ? rd[pos] : 0.0; ve[q] = re[pos];
                 if (vm[q] + vi[q] + vd[q] != 0.0) { elo = ve[q] < elo ? ve[q] : elo; ehi = ve[q] > ehi ? ve[q] : ehi; }
+            }
         } else {
             const double v0 = pk == PREV_B_INIT ? lp.p_end : 0.0;
 #pragma unroll
@@ -823,6 +878,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
         elo = __reduce_min_sync(0xffffffffu, elo); ehi = __reduce_max_sync(0xffffffffu, ehi);
         double* om = (double*)out_ptr; double* oi = om + Np; double* od = oi + Np; int* oe = (int*)(od + Np);
         if (ehi == EXP_NONE_HI_) {  // nothing but zeros flows into this tile: the row is zero here
+            prefetch_next();
             for (uint32_t j = lane; j < ncore; j += 32) { om[g0 + j] = 0.0; oi[g0 + j] = 0.0; od[g0 + j] = 0.0; oe[g0 + j] = 0; }
             if (lane == 0) {
                 if (FWD) partials[(size_t)job_idx * n_tiles + c] = xf_zero();
@@ -831,19 +887,20 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
             continue;
         }
         if (ehi - elo > span) {    // exponent range too wide for one frame: the exact kernel takes this tile
+            prefetch_next();
             if (lane == 0) { unsigned long long w = atomicAdd(worklist, 1ull); worklist[1 + w] = ((unsigned long long)job_idx << 32) | c; }
             continue;
         }
         const int Eref = ehi;
-        __syncwarp();   // shared-memory reads of the previous tile are done
-        // ---- scale into the frame, stage position-indexed, pick up the owned positions
+        // ---- scale into the frame, stage position-indexed (the staged copies of the previous job were last read before
+        // the barrier at the top of this iteration), then start the prefetch for the next job while few registers are live
 #pragma unroll
         for (int q = 0; q < RS_PER_LANE; q++) {
             const double sc_ = pow2i(ve[q] - Eref);
             const int pos = 32 * q + lane;
             sa[pos] = vm[q] * sc_; sb[pos] = vi[q] * sc_; if (FWD) sc[pos] = vd[q] * sc_;
         }
-        __syncwarp();
+        prefetch_next();
         double pm[RS_PER_LANE], pi[RS_PER_LANE], pd[RS_PER_LANE];
 #pragma unroll
         for (int k = 0; k < RS_PER_LANE; k++) {
@@ -1221,6 +1278,16 @@ int dense_configure(dbgphmm_model* m) {
     return DBGPHMM_OK;
 }
 
+static int ensure_jstep(dbgphmm_model* m, uint32_t n_jobs) {
+    if (n_jobs <= m->jstep_cap) return DBGPHMM_OK;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    cudaFree(m->d_jstep); m->d_jstep = nullptr; m->jstep_cap = 0;
+    const uint32_t cap = std::max<uint32_t>(1024, n_jobs + n_jobs / 2);
+    CUDA_TRY(cudaMalloc(&m->d_jstep, (size_t)cap * sizeof(JStep)));
+    m->jstep_cap = cap;
+    return DBGPHMM_OK;
+}
+
 // worklist: [0] = number of tiles left to the exact kernel, [1..] = (job << 32 | chunk)
 int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, unsigned long long* d_worklist,
@@ -1228,11 +1295,15 @@ int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jo
     CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), m->stream));
     const uint32_t jpc = fast_jobs_per_cta(m, m->fwd.n_chunks, n_jobs);
     dim3 grid((m->fwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
+    if (use_reg_kernel()) {
+        ST_TRY(ensure_jstep(m, n_jobs));
+        k_dense_prep<true><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+        COUNT_LAUNCH();
+    }
     launch_timer_begin(m->stream);
     if (use_reg_kernel())
-        k_dense_reg<true><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
-                                                                              d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks,
-                                                                              fast_span(m->lin), d_worklist, jpc);
+        k_dense_reg<true><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+                                                                              d_partials, m->fwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
     else
         k_dense_warp<true><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
                                                                                d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks,
@@ -1263,11 +1334,15 @@ int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
     CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), m->stream));
     const uint32_t jpc = fast_jobs_per_cta(m, m->bwd.n_chunks, n_jobs);
     dim3 grid((m->bwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
+    if (use_reg_kernel()) {
+        ST_TRY(ensure_jstep(m, n_jobs));
+        k_dense_prep<false><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+        COUNT_LAUNCH();
+    }
     launch_timer_begin(m->stream);
     if (use_reg_kernel())
-        k_dense_reg<false><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
-                                                                               d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks,
-                                                                               fast_span(m->lin), d_worklist, jpc);
+        k_dense_reg<false><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+                                                                               d_partials, m->bwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
     else
         k_dense_warp<false><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
                                                                                 d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks,

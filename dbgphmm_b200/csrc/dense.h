@@ -9,7 +9,9 @@
 #define DENSE_XMAX 64       // of which beyond the first of each node ("extras")
 #define DENSE_THREADS 64    // exact (per-value exponent) kernel: one CTA per tile
 #define DENSE_SLOTS ((DENSE_LMAX + DENSE_THREADS - 1) / DENSE_THREADS)
+#ifndef WT_WARPS
 #define WT_WARPS 8          // common-frame kernel: warps (= tiles) per CTA
+#endif
 #define WT_SLOTS (DENSE_LMAX / 32)
 #ifndef WT_MIN_CTAS
 #define WT_MIN_CTAS 2

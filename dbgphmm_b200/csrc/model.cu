@@ -394,7 +394,7 @@ int model_ensure_roi(dbgphmm_model* m) {
 void model_free(dbgphmm_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of);
+    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of); cudaFree(m->d_jstep);
     cudaFree(m->d_pos_of); cudaFree(m->d_orig_of); cudaFree(m->d_emission);
     cudaFree(m->d_par_off); cudaFree(m->d_par_node); cudaFree(m->d_par_eid);
     cudaFree(m->d_chi_off); cudaFree(m->d_chi_node); cudaFree(m->d_chi_eid);

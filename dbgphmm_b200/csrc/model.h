@@ -88,6 +88,7 @@ struct dbgphmm_model {
     // its nodes within HALO_HOPS * n_warmup hops (the dependency cone of n_warmup dense rows), built lazily.
     uint32_t roi_warmup = 0;
     uint32_t *d_roi_off = nullptr, *d_roi_tile = nullptr, *d_tile_of = nullptr;
+    void* d_jstep = nullptr; uint32_t jstep_cap = 0;   // per-(job, step) scalars of the dense fast kernel (dense.cu: JStep)
 };
 int model_ensure_roi(dbgphmm_model* m);
 

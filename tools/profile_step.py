@@ -3,6 +3,8 @@ import argparse, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dbgphmm_b200 import hmmv2 as H
+if os.environ.get("DBGPHMM_LIB_PATH"):   # tuning sweeps: a library built by tools/build_variant.py
+    H.LIB_PATH = os.environ["DBGPHMM_LIB_PATH"]
 import bench
 
 ap = argparse.ArgumentParser()
