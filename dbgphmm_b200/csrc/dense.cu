@@ -734,11 +734,12 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 #define RS_PER_LANE (DENSE_LMAX / 32)
-// per warp: frame-scaled copies sa, sb, sc + se ; raw prefetched previous row rm, ri, rd + re ; two JStep slots
-#define RS_SMEM_PER_WARP (2 * DENSE_LMAX * (3 * 8 + 4) + 2 * 64)
+// per warp: frame-scaled copies sa, sb, sc + se ; raw prefetched previous row rm, ri, rd + re ; two JStep slots ;
+// init of the owned positions and node ids of the IO positions (lane-private, kept out of the register file)
+#define RS_SMEM_PER_WARP (2 * DENSE_LMAX * (3 * 8 + 4) + 2 * 64 + DENSE_LMAX * (8 + 4))
 #define RS_SMEM_BYTES (WT_WARPS * RS_SMEM_PER_WARP)
 
-__device__ __noinline__ double rs_extras(const uint32_t* __restrict__ rx_off, const uint16_t* __restrict__ rx_idx, const uint32_t* __restrict__ rx_eid,
+__device__ __forceinline__ double rs_extras(const uint32_t* __restrict__ rx_off, const uint16_t* __restrict__ rx_idx, const uint32_t* __restrict__ rx_eid,
                                          const double* __restrict__ trans, uint32_t xidx, const double* a, const double* b, const double* c,
                                          double ca, double cb, double cc) {
     double acc = 0.0;
@@ -765,14 +766,20 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
     double* sb = sa + DENSE_LMAX; double* sc = sb + DENSE_LMAX; int* se = (int*)(sc + DENSE_LMAX);
     double* rm = (double*)(se + DENSE_LMAX); double* ri = rm + DENSE_LMAX; double* rd = ri + DENSE_LMAX; int* re = (int*)(rd + DENSE_LMAX);
     JStep* sj = (JStep*)(re + DENSE_LMAX);
+    double* sinit = (double*)(sj + 2);               // init of the owned positions, [slot][lane] (lane-private, conflict-free)
+    uint32_t* sion = (uint32_t*)(sinit + DENSE_LMAX); // node of IO position 32 q + lane, [q][lane] (lane-private)
     const uint32_t tbase = c * DENSE_LMAX;
     const uint32_t g0 = P.chunk_start[c], ncore = P.chunk_start[c + 1] - g0;
     // ---- tile structure: slot-major node ids for global IO, owned positions for the recurrences
-    uint32_t ion[RS_PER_LANE];
     unsigned int emc = 0;     // 3-bit base codes of the owned positions
     unsigned int cmask = 0;   // bit k: owned position k is a core node ; bit 8 + q: IO position 32 q + lane is a core node
 #pragma unroll
-    for (int q = 0; q < RS_PER_LANE; q++) { ion[q] = P.rl_node[tbase + 32 * q + lane]; cmask |= (ion[q] - g0 < ncore ? 1u : 0u) << (8 + q); }
+    for (int q = 0; q < RS_PER_LANE; q++) {
+        const uint32_t nd = P.rl_node[tbase + 32 * q + lane];
+        sion[32 * q + lane] = nd;
+        cmask |= (nd - g0 < ncore ? 1u : 0u) << (8 + q);
+        if (nd != 0xffffffffu) cmask |= 1u << (16 + q);   // bit 16 + q: IO position holds a node
+    }
 #pragma unroll
     for (int k = 0; k < RS_PER_LANE; k++) {
         const uint32_t nd = P.rl_node[tbase + RS_PER_LANE * lane + k];
@@ -793,9 +800,9 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
     }
     const bool tile_has_x = __any_sync(0xffffffffu, xe != 0xffffffffu);
     const bool tile_has_xx = __any_sync(0xffffffffu, ext0);
-    double tr[RS_PER_LANE], init_[RS_PER_LANE];
+    double tr[RS_PER_LANE];
 #pragma unroll
-    for (int k = 0; k < RS_PER_LANE; k++) { tr[k] = 0.0; init_[k] = 0.0; }
+    for (int k = 0; k < RS_PER_LANE; k++) tr[k] = 0.0;
     int staged_x = -1;
     const double* trans = G.trans;
     const uint32_t job0 = blockIdx.y * jpc;
@@ -810,8 +817,8 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
         const double* gm = (const double*)js.prev_ptr; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
 #pragma unroll
         for (int q = 0; q < RS_PER_LANE; q++) {
-            if (ion[q] != 0xffffffffu) {
-                const uint32_t g = ion[q]; const int pos = 32 * q + lane;
+            if ((cmask >> (16 + q)) & 1) {
+                const int pos = 32 * q + lane; const uint32_t g = sion[pos];
                 cp_async8(&rm[pos], &gm[g]); cp_async8(&ri[pos], &gi[g]); if (FWD) cp_async8(&rd[pos], &gd[g]); cp_async4(&re[pos], &ge[g]);
             }
         }
@@ -849,7 +856,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
 #pragma unroll
             for (int k = 0; k < RS_PER_LANE; k++) {
                 const uint32_t nd = P.rl_node[tbase + RS_PER_LANE * lane + k], ed = P.rl_eid[tbase + RS_PER_LANE * lane + k];
-                init_[k] = nd == 0xffffffffu ? 0.0 : init[nd];
+                sinit[32 * k + lane] = nd == 0xffffffffu ? 0.0 : init[nd];
                 tr[k] = ed == 0xffffffffu ? 0.0 : trans[ed];
             }
             xt = xe == 0xffffffffu ? 0.0 : trans[xe];
@@ -868,7 +875,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
         } else {
             const double v0 = pk == PREV_B_INIT ? lp.p_end : 0.0;
 #pragma unroll
-            for (int q = 0; q < RS_PER_LANE; q++) { vm[q] = ion[q] != 0xffffffffu ? v0 : 0.0; vi[q] = vm[q]; vd[q] = 0.0; ve[q] = 0; }
+            for (int q = 0; q < RS_PER_LANE; q++) { vm[q] = ((cmask >> (16 + q)) & 1) ? v0 : 0.0; vi[q] = vm[q]; vd[q] = 0.0; ve[q] = 0; }
             if (v0 != 0.0) { elo = 0; ehi = 0; }
         }
         if (FWD) {
@@ -921,7 +928,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                     const double um = RS_UP(pm, sa, k), ui = RS_UP(pi, sb, k), ud = RS_UP(pd, sc, k);
                     double acc = tr[k] * (lp.p_MM * um + lp.p_IM * ui + lp.p_DM * ud);
                     if (k == 0) acc += x0;
-                    acc += fbv * init_[k];
+                    acc += fbv * sinit[32 * k + lane];
                     cm[k] = acc * (((emc >> (3 * k)) & 7) == x ? lp.p_match : lp.p_mismatch);
                     ci[k] = lp.p_random * (lp.p_MI * pm[k] + lp.p_II * pi[k] + lp.p_DI * pd[k]);
                 }
@@ -940,7 +947,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                     const double um = RS_UP(cm, sa, k), ui = RS_UP(ci, sb, k);
                     double acc = tr[k] * (lp.p_MD * um + lp.p_ID * ui);
                     if (k == 0) acc += x0;
-                    acc += ibv * (lp.p_ID * init_[k]);
+                    acc += ibv * (lp.p_ID * sinit[32 * k + lane]);
                     dcur[k] = acc; dacc[k] = acc;
                 }
             }
@@ -954,15 +961,13 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                 double x0 = 0.0;
                 if (tile_has_x) x0 = xt * lp.p_DD * prevbuf[xp];
                 if (tile_has_xx && ext0) x0 += RS_EXTRAS0(prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
-                double nxt[RS_PER_LANE];
+                // in place, highest slot first: slot k reads the previous round's value of slot k - 1
 #pragma unroll
-                for (int k = 0; k < RS_PER_LANE; k++) {
+                for (int k = RS_PER_LANE - 1; k >= 0; k--) {
                     double v = tr[k] * lp.p_DD * RS_UP(dcur, prevbuf, k);
                     if (k == 0) v += x0;
-                    nxt[k] = v;
+                    dcur[k] = v; dacc[k] += v;
                 }
-#pragma unroll
-                for (int k = 0; k < RS_PER_LANE; k++) { dcur[k] = nxt[k]; dacc[k] += nxt[k]; }
                 if (t < N_DEL_ROUNDS - 1) {
 #pragma unroll
                     for (int k = 0; k < RS_PER_LANE; k++) curbuf[RS_PER_LANE * lane + k] = dcur[k];
@@ -1000,15 +1005,13 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                 double x0 = 0.0;
                 if (tile_has_x) x0 = xt * lp.p_DD * prevbuf[xp];
                 if (tile_has_xx && ext0) x0 += RS_EXTRAS0(prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
-                double nxt[RS_PER_LANE];
+                // in place, highest slot first: slot k reads the previous round's value of slot k - 1
 #pragma unroll
-                for (int k = 0; k < RS_PER_LANE; k++) {
+                for (int k = RS_PER_LANE - 1; k >= 0; k--) {
                     double v = tr[k] * lp.p_DD * RS_UP(dcur, prevbuf, k);
                     if (k == 0) v += x0;
-                    nxt[k] = v;
+                    dcur[k] = v; dacc[k] += v;
                 }
-#pragma unroll
-                for (int k = 0; k < RS_PER_LANE; k++) { dcur[k] = nxt[k]; dacc[k] += nxt[k]; }
                 if (t < N_DEL_ROUNDS - 1) {
 #pragma unroll
                     for (int k = 0; k < RS_PER_LANE; k++) curbuf[RS_PER_LANE * lane + k] = dcur[k];
@@ -1049,7 +1052,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
             sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = mx != 0.0 ? Eref + qx : 0;
             if ((cmask >> k) & 1) {
                 if (FWD) part += m + i + d;
-                else { part += (pm[k] * lp.p_MM + d * lp.p_MD) * init_[k]; part2 += (pm[k] * lp.p_IM + d * lp.p_ID) * init_[k]; }
+                else { const double in = sinit[32 * k + lane]; part += (pm[k] * lp.p_MM + d * lp.p_MD) * in; part2 += (pm[k] * lp.p_IM + d * lp.p_ID) * in; }
             }
         }
         __syncwarp();
@@ -1057,7 +1060,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
         for (int q = 0; q < RS_PER_LANE; q++) {
             const int pos = 32 * q + lane;
             if ((cmask >> (8 + q)) & 1) {
-                const uint32_t g = ion[q];
+                const uint32_t g = sion[pos];
                 om[g] = sa[pos]; oi[g] = sb[pos]; od[g] = sc[pos]; oe[g] = se[pos];
             }
         }
