@@ -753,6 +753,11 @@ __device__ __forceinline__ double rs_extras(const uint32_t* __restrict__ rx_off,
 #define RS_EXTRAS0(A, B, C, ca, cb, cc) rs_extras(P.rx_off, P.rx_idx, P.rx_eid, trans, (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane, (A), (B), (C), (ca), (cb), (cc))
 // first upstream neighbour of slot k: slot 0 reads the staged copy at pp0, the others the previous register
 #define RS_UP(arr, buf, k) ((k) == 0 ? (buf)[pp0] : arr[(k) > 0 ? (k) - 1 : 0])
+// publish the owned values other lanes read (first-neighbour / extra sources): normally just the last slot
+#define RS_STAGE(buf, arr) do {                                                                                   \
+        if (tile_plain) (buf)[RS_PER_LANE * lane + RS_PER_LANE - 1] = arr[RS_PER_LANE - 1];                      \
+        else { _Pragma("unroll") for (int k_ = 0; k_ < RS_PER_LANE; k_++) if ((srcm >> k_) & 1) (buf)[RS_PER_LANE * lane + k_] = arr[k_]; } \
+    } while (0)
 
 template <bool FWD>
 __global__ void __launch_bounds__(WT_WARPS * 32, WT_MIN_CTAS)
@@ -773,6 +778,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
     // ---- tile structure: slot-major node ids for global IO, owned positions for the recurrences
     unsigned int emc = 0;     // 3-bit base codes of the owned positions
     unsigned int cmask = 0;   // bit k: owned position k is a core node ; bit 8 + q: IO position 32 q + lane is a core node
+    unsigned int srcm = 0;    // bit k: owned position k is read by another position's slot 0 or as an extra source
 #pragma unroll
     for (int q = 0; q < RS_PER_LANE; q++) {
         const uint32_t nd = P.rl_node[tbase + 32 * q + lane];
@@ -787,12 +793,14 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
         if (nd != 0xffffffffu) { unsigned char ch = G.emission[nd]; code = ch == 'n' ? 4 : ((ch >> 1) & 3); }
         emc |= code << (3 * k);
         cmask |= (nd - g0 < ncore ? 1u : 0u) << k;
+        srcm |= (unsigned int)((P.rl_flag[tbase + RS_PER_LANE * lane + k] >> 2) & 1) << k;
     }
+    const bool tile_plain = !__any_sync(0xffffffffu, (srcm & ((1u << (RS_PER_LANE - 1)) - 1)) != 0);
     // Slot 0 of the lane: position of its first upstream neighbour (the layout puts every node whose neighbour is not the
     // previous position, or that has further upstream edges, on a slot 0).  ONE extra edge is kept in registers
     // (source position xp, edge id xe -> transition xt); more take the out-of-line loop.
     const int pp0 = P.rl_par[tbase + RS_PER_LANE * lane];
-    int xp = 0; uint32_t xe = 0xffffffffu; double xt = 0.0; bool ext0 = false;
+    int xp = pp0; uint32_t xe = 0xffffffffu; double xt = 0.0; bool ext0 = false;   // (lanes without an extra read a published, finite value times 0)
     if (P.rl_flag[tbase + RS_PER_LANE * lane] & 2) {
         const size_t xi = (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane;
         const uint32_t a0 = P.rx_off[xi], a1 = P.rx_off[xi + 1];
@@ -862,21 +870,22 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
             xt = xe == 0xffffffffu ? 0.0 : trans[xe];
             staged_x = hx;
         }
-        // ---- previous row from the prefetch buffer (slot-major), exponent range of the tile by warp reductions
-        double vm[RS_PER_LANE], vi[RS_PER_LANE], vd[RS_PER_LANE]; int ve[RS_PER_LANE];
-        int elo = EXP_NONE_LO_, ehi = EXP_NONE_HI_;
-        if (pk == PREV_SLAB) {
-#pragma unroll
-            for (int q = 0; q < RS_PER_LANE; q++) {
-                const int pos = 32 * q + lane;
-                vm[q] = rm[pos]; vi[q] = ri[pos]; vd[q] = FWD ? rd[pos] : 0.0; ve[q] = re[pos];
-                if (vm[q] + vi[q] + vd[q] != 0.0) { elo = ve[q] < elo ? ve[q] : elo; ehi = ve[q] > ehi ? ve[q] : ehi; }
-            }
-        } else {
+        // ---- previous row: the prefetch buffer (filled slot-major by cp.async) is read position-major, so it doubles as
+        // the transpose buffer; the first row of a read (constant previous row) is materialised in it
+        if (pk != PREV_SLAB) {
             const double v0 = pk == PREV_B_INIT ? lp.p_end : 0.0;
 #pragma unroll
-            for (int q = 0; q < RS_PER_LANE; q++) { vm[q] = ((cmask >> (16 + q)) & 1) ? v0 : 0.0; vi[q] = vm[q]; vd[q] = 0.0; ve[q] = 0; }
-            if (v0 != 0.0) { elo = 0; ehi = 0; }
+            for (int q = 0; q < RS_PER_LANE; q++)
+                if ((cmask >> (16 + q)) & 1) { const int pos = 32 * q + lane; rm[pos] = v0; ri[pos] = v0; rd[pos] = 0.0; re[pos] = 0; }
+            __syncwarp();
+        }
+        double pm[RS_PER_LANE], pi[RS_PER_LANE], pd[RS_PER_LANE]; int pe[RS_PER_LANE];
+        int elo = EXP_NONE_LO_, ehi = EXP_NONE_HI_;
+#pragma unroll
+        for (int k = 0; k < RS_PER_LANE; k++) {
+            const int pos = RS_PER_LANE * lane + k;
+            pm[k] = rm[pos]; pi[k] = ri[pos]; pd[k] = FWD ? rd[pos] : 0.0; pe[k] = re[pos];
+            if (pm[k] + pi[k] + pd[k] != 0.0) { elo = pe[k] < elo ? pe[k] : elo; ehi = pe[k] > ehi ? pe[k] : ehi; }
         }
         if (FWD) {
             if (fb0.v != 0.0) { int e = xexp(fb0); elo = e < elo ? e : elo; ehi = e > ehi ? e : ehi; }
@@ -899,21 +908,17 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
             continue;
         }
         const int Eref = ehi;
-        // ---- scale into the frame, stage position-indexed (the staged copies of the previous job were last read before
-        // the barrier at the top of this iteration), then start the prefetch for the next job while few registers are live
+        // ---- into the frame: the owned cells, the first upstream neighbour of slot 0 and the source of the register-held extra
+        double u0m, u0i, u0d, x0m = 0.0, x0i = 0.0, x0d = 0.0;
+        { const double s0 = pow2i(re[pp0] - Eref); u0m = rm[pp0] * s0; u0i = ri[pp0] * s0; u0d = FWD ? rd[pp0] * s0 : 0.0; }
+        if (tile_has_x) { const double sx = pow2i(re[xp] - Eref); x0m = rm[xp] * sx; x0i = ri[xp] * sx; x0d = FWD ? rd[xp] * sx : 0.0; }
 #pragma unroll
-        for (int q = 0; q < RS_PER_LANE; q++) {
-            const double sc_ = pow2i(ve[q] - Eref);
-            const int pos = 32 * q + lane;
-            sa[pos] = vm[q] * sc_; sb[pos] = vi[q] * sc_; if (FWD) sc[pos] = vd[q] * sc_;
-        }
-        prefetch_next();
-        double pm[RS_PER_LANE], pi[RS_PER_LANE], pd[RS_PER_LANE];
+        for (int k = 0; k < RS_PER_LANE; k++) { const double sc_ = pow2i(pe[k] - Eref); pm[k] *= sc_; pi[k] *= sc_; pd[k] *= sc_; }
+        if (FWD && tile_has_xx) {   // several extras on one node (rare): the out-of-register loop reads position-indexed copies
 #pragma unroll
-        for (int k = 0; k < RS_PER_LANE; k++) {
-            const int pos = RS_PER_LANE * lane + k;
-            pm[k] = sa[pos]; pi[k] = sb[pos]; pd[k] = FWD ? sc[pos] : 0.0;
+            for (int k = 0; k < RS_PER_LANE; k++) { const int pos = RS_PER_LANE * lane + k; sa[pos] = pm[k]; sb[pos] = pi[k]; sc[pos] = pd[k]; }
         }
+        prefetch_next();   // (barrier inside) every lane is done with the raw row: refill it for the next job
         double cm[RS_PER_LANE], ci[RS_PER_LANE], dacc[RS_PER_LANE], dcur[RS_PER_LANE];
         if (FWD) {
             const double fbv = fb0.v == 0.0 ? 0.0 : fb0.v * pow2i(fb0.e - Eref);
@@ -921,11 +926,11 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
             // round A: fm, fi (forward.rs:337-388)
             {
                 double x0 = 0.0;
-                if (tile_has_x) x0 = xt * (lp.p_MM * sa[xp] + lp.p_IM * sb[xp] + lp.p_DM * sc[xp]);
+                if (tile_has_x) x0 = xt * (lp.p_MM * x0m + lp.p_IM * x0i + lp.p_DM * x0d);
                 if (tile_has_xx && ext0) x0 += RS_EXTRAS0(sa, sb, sc, lp.p_MM, lp.p_IM, lp.p_DM);
 #pragma unroll
                 for (int k = 0; k < RS_PER_LANE; k++) {
-                    const double um = RS_UP(pm, sa, k), ui = RS_UP(pi, sb, k), ud = RS_UP(pd, sc, k);
+                    const double um = k == 0 ? u0m : pm[k > 0 ? k - 1 : 0], ui = k == 0 ? u0i : pi[k > 0 ? k - 1 : 0], ud = k == 0 ? u0d : pd[k > 0 ? k - 1 : 0];
                     double acc = tr[k] * (lp.p_MM * um + lp.p_IM * ui + lp.p_DM * ud);
                     if (k == 0) acc += x0;
                     acc += fbv * sinit[32 * k + lane];
@@ -933,9 +938,8 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                     ci[k] = lp.p_random * (lp.p_MI * pm[k] + lp.p_II * pi[k] + lp.p_DI * pd[k]);
                 }
             }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < RS_PER_LANE; k++) { const int pos = RS_PER_LANE * lane + k; sa[pos] = cm[k]; sb[pos] = ci[k]; }
+            if (tile_has_xx) __syncwarp();   // the position-indexed copies of the previous row have been read
+            RS_STAGE(sa, cm); RS_STAGE(sb, ci);
             __syncwarp();
             // round B: fd0 (forward.rs:480-501)
             {
@@ -951,10 +955,9 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                     dcur[k] = acc; dacc[k] = acc;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < RS_PER_LANE; k++) sc[RS_PER_LANE * lane + k] = dcur[k];
+            RS_STAGE(sc, dcur);
             __syncwarp();
-            // fdt x 4 (forward.rs:510-524): previous round in registers, its copy in sc / sa alternately
+            // fdt x 4 (forward.rs:510-524): previous round in registers, its sources' copies in sc / sa alternately
 #pragma unroll
             for (int t = 1; t < N_DEL_ROUNDS; t++) {
                 double* prevbuf = (t & 1) ? sc : sa; double* curbuf = (t & 1) ? sa : sc;
@@ -968,19 +971,14 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                     if (k == 0) v += x0;
                     dcur[k] = v; dacc[k] += v;
                 }
-                if (t < N_DEL_ROUNDS - 1) {
-#pragma unroll
-                    for (int k = 0; k < RS_PER_LANE; k++) curbuf[RS_PER_LANE * lane + k] = dcur[k];
-                }
+                if (t < N_DEL_ROUNDS - 1) RS_STAGE(curbuf, dcur);
                 __syncwarp();
             }
         } else {
             // previous (= next base) row: pm := e_l(x) m''[l]  (every use of m'' is multiplied by the emission of that node)
 #pragma unroll
             for (int k = 0; k < RS_PER_LANE; k++) pm[k] *= (((emc >> (3 * k)) & 7) == x ? lp.p_match : lp.p_mismatch);
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < RS_PER_LANE; k++) sa[RS_PER_LANE * lane + k] = pm[k];
+            RS_STAGE(sa, pm);
             __syncwarp();
             // bd0 (backward.rs:354-377)
             {
@@ -995,8 +993,7 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                     dcur[k] = acc; dacc[k] = acc;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < RS_PER_LANE; k++) sc[RS_PER_LANE * lane + k] = dcur[k];
+            RS_STAGE(sc, dcur);
             __syncwarp();
             // bdt x 4 (backward.rs:387-404): copies alternate between sc and sb (sa keeps e m'' for bm / bi)
 #pragma unroll
@@ -1005,22 +1002,17 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
                 double x0 = 0.0;
                 if (tile_has_x) x0 = xt * lp.p_DD * prevbuf[xp];
                 if (tile_has_xx && ext0) x0 += RS_EXTRAS0(prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
-                // in place, highest slot first: slot k reads the previous round's value of slot k - 1
 #pragma unroll
                 for (int k = RS_PER_LANE - 1; k >= 0; k--) {
                     double v = tr[k] * lp.p_DD * RS_UP(dcur, prevbuf, k);
                     if (k == 0) v += x0;
                     dcur[k] = v; dacc[k] += v;
                 }
-                if (t < N_DEL_ROUNDS - 1) {
-#pragma unroll
-                    for (int k = 0; k < RS_PER_LANE; k++) curbuf[RS_PER_LANE * lane + k] = dcur[k];
-                }
+                if (t < N_DEL_ROUNDS - 1) RS_STAGE(curbuf, dcur);
                 __syncwarp();
             }
-            // d of every position into sc, then bm / bi (backward.rs:423-483)
-#pragma unroll
-            for (int k = 0; k < RS_PER_LANE; k++) sc[RS_PER_LANE * lane + k] = dacc[k];
+            // d of the source positions into sc, then bm / bi (backward.rs:423-483)
+            RS_STAGE(sc, dacc);
             __syncwarp();
             {
                 double xm = 0.0, xi_ = 0.0;

@@ -238,6 +238,14 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
                 rl_node.push_back(x); rl_par.push_back(p0); rl_eid.push_back(e0); rl_flag.push_back(fl);
             }
             rx_off.push_back((uint32_t)rx_idx.size());
+            {   // bit 2: the position is read by another one (slot-0 first neighbour, extra source): the kernel publishes only those
+                const size_t fbase = rl_flag.size() - DENSE_LMAX;
+                const size_t xbase = rx_off.size() - (DENSE_LMAX + 1);
+                for (uint32_t q = 0; q < DENSE_LMAX; q++) {
+                    if (q % DENSE_PER_LANE == 0) rl_flag[fbase + rl_par[fbase + q]] |= 4;
+                    for (uint32_t e = rx_off[xbase + q]; e < rx_off[xbase + q + 1]; e++) rl_flag[fbase + rx_idx[e]] |= 4;
+                }
+            }
             for (uint32_t x : lay) if (x != 0xffffffffu) rpos[x] = 0xffffffffu;
         }
         max_local = std::max<uint32_t>(max_local, (uint32_t)local.size());

@@ -98,3 +98,28 @@ def test_c4_batched_candidates_on_a_tandem_repeat(H):
         s, p = o.to_full_prob_reads(O.Reads(reads), omaps)
         assert close_log(per[x], p).all(), (x, per[x], p)
         assert close_log(tot[x], s).all()
+
+
+def test_fast_and_exact_dense_kernels_agree_on_a_large_graph(H, monkeypatch):
+    """The common-frame register-stencil kernel against the per-value-exponent kernel (which the small cases pin to the oracle)
+    on a graph large enough to contain every tile shape: merge nodes, irregular chains, padded layouts, halo-only tiles."""
+    w = synth.make_workload("C3m", 200_000, 40, 1, 1_500, 0.001, ploidy=2, het=0.01, seed=5, n_reads=6)
+    par = oracle_params(0.001, n_warmup=w.k)
+    g = gpu_model(w.graph, par)
+    read = w.reads[0][:8]
+    N = w.graph.n_nodes
+    rows, runs = {}, {}
+    for exact in ("1", "0"):
+        monkeypatch.setenv("DBGPHMM_FORCE_EXACT", exact)
+        tf, tb = g.forward(read), g.backward(read)
+        rows[exact] = [tf.row(i).merged(N) for i in range(len(read))] + [tb.row(i).merged(N) for i in range(len(read))]
+        runs[exact] = g.run_node_freqs(H.Reads(w.reads), "sparse")
+    for a, b in zip(rows["1"], rows["0"]):
+        assert not np.isnan(b).any()
+        fin = np.isfinite(a)
+        assert np.array_equal(fin, np.isfinite(b))
+        assert np.allclose(a[fin], b[fin], rtol=REL_TOL, atol=0)
+    fa, lfa, lba, ca = runs["1"]
+    fb, lfb, lbb, cb = runs["0"]
+    assert ca == cb and close_log(lfa, lfb).all() and close_log(lba, lbb).all()
+    assert np.allclose(fa, fb, rtol=REL_TOL, atol=1e-12)
