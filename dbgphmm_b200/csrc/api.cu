@@ -317,12 +317,15 @@ static int check_reads_mappings(const dbgphmm_reads* reads, const dbgphmm_mappin
 }
 
 // split job indices [0, n) into batches whose estimated device footprint fits the budget
-static std::vector<std::pair<size_t, size_t>> plan_batches(const std::vector<uint64_t>& bytes, uint64_t budget, size_t max_jobs) {
+// Batches of consecutive jobs within the memory budget.  quantum > 0: a batch that is not the last one is cut down to a
+// multiple of `quantum` jobs (the sparse kernel runs one CTA per job and is latency-bound: a partial wave costs a full one).
+static std::vector<std::pair<size_t, size_t>> plan_batches(const std::vector<uint64_t>& bytes, uint64_t budget, size_t max_jobs, size_t quantum = 0) {
     std::vector<std::pair<size_t, size_t>> out;
     size_t i = 0;
     while (i < bytes.size()) {
         uint64_t acc = 0; size_t j = i;
         while (j < bytes.size() && j - i < max_jobs && (j == i || acc + bytes[j] <= budget)) { acc += bytes[j]; j++; }
+        if (quantum && j < bytes.size() && j - i > quantum) j = i + (j - i) / quantum * quantum;
         out.push_back({i, j});
         i = j;
     }
@@ -354,7 +357,7 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
         }
     std::vector<double> per(all.size());
     int st = DBGPHMM_OK;
-    for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535)) {
+    for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535, sparse_wave_jobs(m, 256))) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         RowStore F;
         PhaseOpts so; so.keep_rows = false; so.store_sparse = false;
@@ -427,7 +430,7 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
         const uint64_t per_row = (uint64_t)m->params.n_active_nodes * 3 * 34 + 256 + 3 * sizeof(RowDesc);
         for (uint64_t r = 0; r < R; r++) bytes[r] = 2 * slab + 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20);
     }
-    for (auto& bt : plan_batches(bytes, m->mem_budget, 65535)) {
+    for (auto& bt : plan_batches(bytes, m->mem_budget, 65535, mode == DBGPHMM_RUN_DENSE ? 0 : sparse_wave_jobs(m, 256))) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         HostTrace tr_b("batch");
         RowStore F, B;

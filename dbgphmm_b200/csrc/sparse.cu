@@ -31,8 +31,8 @@ struct SS {  // shared-memory view of one job
     uint32_t *ph_key, *ph_val;
     // current row under construction
     uint32_t* c_id; double *c_m, *c_i; int* c_mie; double* c_dv; int* c_de;
-    double* dval[2]; int* dexp[2]; uint32_t* dstamp[2];
-    uint32_t* firstpos; uint32_t* d_seen;
+    double* dval[2]; int* dexp[2]; uint8_t* dstamp[2];   // Del round values of the last two rounds ; stamp = round + 1 (entries are rebuilt every row)
+    uint32_t* firstpos; uint8_t* d_seen;
     uint32_t *ch_key, *ch_val;
     // lists
     uint32_t* top_id;                    // [MAX_ACTIVE]
@@ -41,10 +41,8 @@ struct SS {  // shared-memory view of one job
     uint16_t* dlist;                     // [cap] slots in d insertion order
     uint32_t* scan;                      // [cap + 1] scratch
     // ranking scratch
-    int* k_T; unsigned long long* k_mant;
-    // expansion scratch: hash cell and ordered prefix of every candidate
-    uint32_t ccap; unsigned short* ccell; uint32_t* cpre;
-    uint32_t* wt; uint32_t tog, ecall;   // block_prefix scratch [2][32] + call parities
+    int* k_T; unsigned long long* k_mant;   // ranking keys (alias the Del round buffers, which are dead between rows)
+    uint32_t* wt; uint32_t tog, ecall;   // block_prefix scratch [2][8] + call parities
 };
 
 __device__ __forceinline__ uint32_t sp_hash(uint32_t id, int shift) { return (id * 2654435761u) >> shift; }
@@ -72,18 +70,21 @@ __device__ __forceinline__ uint32_t sp_cell(uint32_t* key, uint32_t hmask, int h
 
 // Ordered exclusive prefix of one small value per thread over the block (thread order) ; *total = block sum.
 // One barrier: warp shuffles + per-warp totals in shared memory (double-buffered, so back-to-back calls need no
-// second barrier).  All threads must call.  Two 16-bit counters may be packed into v.
+// second barrier).  All threads must call.  Two 16-bit counters may be packed into v.  At most 8 warps.
 __device__ __forceinline__ uint32_t block_prefix(SS& S, uint32_t v, uint32_t* total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    uint32_t* wt = S.wt + 32 * (S.tog & 1);
+    uint32_t* wt = S.wt + 8 * (S.tog & 1);
     S.tog++;
     if (lane == 31) wt[w] = x;
     __syncthreads();
+    const uint4 a = *(const uint4*)wt, b = *(const uint4*)(wt + 4);   // totals of absent warps stay 0
+    const uint32_t t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t base = 0, tot = 0;
-    for (int k = 0; k < nw; k++) { uint32_t t = wt[k]; base += k < w ? t : 0u; tot += t; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { base += k < w ? t[k] : 0u; tot += t[k]; }
     *total = tot;
     return base + x - v;
 }
@@ -111,10 +112,12 @@ __device__ __forceinline__ XF block_xsum(XF a) {  // deterministic block reducti
 // Unique, first-occurrence-ordered expansion of `src` (node ids) over an adjacency CSR (active_nodes.rs:15-56).
 // and_us: the sources themselves come first.  with_nbrs: append their neighbours (in CSR = newest-edge-first order).
 // Nodes without a current-row entry get one appended (zeroed).  Output: out_id/out_slot, *n_out (<= max_out).
-// Returns false if the entry table would overflow `cap`.
-//   phase 0  candidate list = [sources] ++ neighbours of source 0, 1, ... (ordered scatter through a block prefix)
+// Returns false if the entry table would overflow `cap` (or a node has more than 16 neighbours).
+// The candidate list [sources] ++ neighbours of source 0, 1, ... is never materialised: the thread of source q owns
+// candidate q and the candidates base(q) .. base(q) + deg(q), base = ordered block prefix of the degrees.
 //   phase 1  every candidate finds / inserts its hash cell and min-reduces its position into it
-//   phase 2  a candidate is kept iff it holds the first position of its id ; ordered compaction by a second prefix
+//   phase 2  a candidate is kept iff it holds the first position of its id ; ordered compaction by a second prefix,
+//            sources first, then neighbours
 __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t* off, const uint32_t* nbr, bool and_us, bool with_nbrs,
                           uint32_t* out_id, uint16_t* out_slot, int max_out, uint32_t* n_ent_io, int* n_out) {
     __shared__ uint32_t s_flags[2][2];   // [call parity][0: overflow, 1: new entries not emitted]
@@ -126,65 +129,101 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
     S.ecall++;
     for (uint32_t e = tid; e < n_ent0; e += B) S.firstpos[e] = SP_ABSENT;
     if (tid == 0) { fl[0] = 0; fl[1] = 0; }
-    uint32_t* cid = S.cpre;   // candidate ids
-    uint32_t C = and_us ? (uint32_t)n_src : 0u;
-    if (and_us) for (int q = tid; q < n_src; q += B) if ((uint32_t)q < S.ccap) cid[q] = src[q];
-    if (with_nbrs) {
-        for (int q0 = 0; q0 < n_src; q0 += B) {
-            const int q = q0 + tid;
-            uint32_t o0 = 0, cnt = 0;
-            if (q < n_src) { const uint32_t id = src[q]; o0 = off[id]; cnt = off[id + 1] - o0; }
-            uint32_t tot;
-            const uint32_t pre = C + block_prefix(S, cnt, &tot);
-            for (uint32_t k = 0; k < cnt; k++) if (pre + k < S.ccap) cid[pre + k] = nbr[o0 + k];
-            C += tot;
-        }
-    }
-    __syncthreads();
-    if (C > S.ccap) { *n_out = 0; return false; }
-    for (uint32_t p = tid; p < C; p += B) {
-        const uint32_t id = cid[p];
+    const uint32_t n_self = and_us ? (uint32_t)n_src : 0u;
+    auto note = [&](uint32_t id, uint32_t p) {   // phase 1 for one candidate
         const uint32_t cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
-        S.ccell[p] = (unsigned short)cell;
         const uint32_t v = S.ch_val[cell];
         if (v < SP_TENT) atomicMin(&S.firstpos[v], p);
         else atomicMin(&S.ch_val[cell], SP_TENT | p);
+    };
+    if (!with_nbrs) __syncthreads();   // (the prefix below is the barrier otherwise) firstpos reset before the min-reductions
+    uint32_t C = n_self;
+    for (int q0 = 0; q0 < n_src; q0 += B) {
+        const int q = q0 + tid;
+        uint32_t id = 0, o0 = 0, cnt = 0;
+        if (q < n_src) { id = src[q]; if (with_nbrs) { o0 = off[id]; cnt = off[id + 1] - o0; } }
+        if (with_nbrs) {
+            uint32_t tot;
+            const uint32_t base = C + block_prefix(S, cnt, &tot);
+            C += tot;
+            if (q < n_src) {
+                if (cnt > 16) { fl[0] = 1; cnt = 0; }
+                S.scan[q] = base | (cnt << 20);
+                for (uint32_t k = 0; k < cnt; k++) note(nbr[o0 + k], base + k);
+            }
+        }
+        if (and_us && q < n_src) note(id, (uint32_t)q);
     }
     __syncthreads();
-    uint32_t run = 0;   // kept count in the low half, new-entry count in the high half
-    for (uint32_t p0 = 0; p0 < C; p0 += B) {
-        const uint32_t p = p0 + tid;
-        uint32_t f = 0, cell = 0, v = 0;
-        if (p < C) {
-            cell = S.ccell[p]; v = S.ch_val[cell];
-            if (v < SP_TENT) f = (S.firstpos[v] == p) ? 1u : 0u;
-            else if (v == (SP_TENT | p)) f = 0x10001u;
+    // kept / new flag of candidate p with id `id` : bit 0 kept, bit 16 new entry
+    auto flag_of = [&](uint32_t id, uint32_t p, uint32_t* cell_out, uint32_t* v_out) -> uint32_t {
+        uint32_t h = sp_hash(id, S.hshift);
+        while (S.ch_key[h] != id + 1) h = (h + 1) & S.hmask;   // inserted in phase 1
+        const uint32_t v = S.ch_val[h];
+        *cell_out = h; *v_out = v;
+        if (v < SP_TENT) return (S.firstpos[v] == p) ? 1u : 0u;
+        return v == (SP_TENT | p) ? 0x10001u : 0u;
+    };
+    auto emit = [&](uint32_t id, uint32_t p, uint32_t f, uint32_t excl, uint32_t cell, uint32_t v) {
+        const bool isnew = f >> 16;
+        const uint32_t oi = excl & 0xffffu, ni = excl >> 16;
+        const uint32_t slot = isnew ? n_ent0 + ni : v;
+        const bool em = (int)oi < max_out;
+        if (em) {
+            if (slot >= S.cap) fl[0] = 1;
+            else {
+                if (isnew) {
+                    S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
+                    S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
+                }
+                out_id[oi] = id; out_slot[oi] = (unsigned short)slot;
+            }
         }
-        uint32_t tot;
-        const uint32_t excl = run + block_prefix(S, f, &tot);   // (barrier: every tentative value of this chunk has been read)
-        if (f) {
-            const bool isnew = f >> 16;
-            const uint32_t oi = excl & 0xffffu, ni = excl >> 16;
-            const uint32_t slot = isnew ? n_ent0 + ni : v;
-            const bool emit = (int)oi < max_out;
-            if (emit) {
-                if (slot >= S.cap) fl[0] = 1;
-                else {
-                    const uint32_t id = S.ch_key[cell] - 1;
-                    if (isnew) {
-                        S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
-                        S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
-                    }
-                    out_id[oi] = id; out_slot[oi] = (unsigned short)slot;
+        if (isnew) {
+            S.ch_val[cell] = (em && slot < S.cap) ? slot : SP_ABSENT;
+            if (!em) atomicAdd(&fl[1], 1u);
+        }
+    };
+    uint32_t run = 0;   // kept count in the low half, new-entry count in the high half
+    if (and_us) {
+        for (int q0 = 0; q0 < n_src; q0 += B) {
+            const int q = q0 + tid;
+            uint32_t id = 0, f = 0, cell = 0, v = 0;
+            if (q < n_src) { id = src[q]; f = flag_of(id, (uint32_t)q, &cell, &v); }
+            uint32_t tot;
+            const uint32_t excl = run + block_prefix(S, f, &tot);   // (barrier: every tentative value of this chunk has been read)
+            if (f) emit(id, (uint32_t)q, f, excl, cell, v);
+            run += tot;
+            if (with_nbrs || q0 + B < n_src) __syncthreads();   // later candidates must see the slots published by this chunk
+        }
+    }
+    if (with_nbrs) {
+        for (int q0 = 0; q0 < n_src; q0 += B) {
+            const int q = q0 + tid;
+            uint32_t o0 = 0, base = 0, cnt = 0, mask = 0, mine = 0;
+            if (q < n_src) {
+                const uint32_t sc = S.scan[q];
+                base = sc & 0xfffffu; cnt = sc >> 20; o0 = off[src[q]];
+                for (uint32_t k = 0; k < cnt; k++) {
+                    uint32_t cell, v;
+                    const uint32_t f = flag_of(nbr[o0 + k], base + k, &cell, &v);
+                    if (f) { mask |= (f >> 16 ? 3u : 1u) << (2 * k); mine += f; }
                 }
             }
-            if (isnew) {
-                S.ch_val[cell] = (emit && slot < S.cap) ? slot : SP_ABSENT;
-                if (!emit) atomicAdd(&fl[1], 1u);
+            uint32_t tot;
+            uint32_t excl = run + block_prefix(S, mine, &tot);
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t b2 = (mask >> (2 * k)) & 3u;
+                if (!b2) continue;
+                const uint32_t id = nbr[o0 + k], f = b2 == 3u ? 0x10001u : 1u;
+                uint32_t cell, v;
+                flag_of(id, base + k, &cell, &v);   // (cell and slot again ; the value is not published yet: only this thread does)
+                emit(id, base + k, f, excl, cell, v);
+                excl += f;
             }
+            run += tot;
+            if (q0 + B < n_src) __syncthreads();
         }
-        run += tot;
-        if (p0 + B < C) __syncthreads();   // later chunks must see the slots published by this one
     }
     __syncthreads();
     const uint32_t kept_tot = run & 0xffffu, new_tot = run >> 16;
@@ -267,22 +306,22 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     S.p_m = (double*)take(8 * cap); S.p_i = (double*)take(8 * cap); S.p_d = (double*)take(8 * cap);
     S.c_m = (double*)take(8 * cap); S.c_i = (double*)take(8 * cap); S.c_dv = (double*)take(8 * cap);
     S.dval[0] = (double*)take(8 * cap); S.dval[1] = (double*)take(8 * cap);
-    S.k_mant = (unsigned long long*)take(8 * cap);
+    S.k_mant = (unsigned long long*)S.dval[0];
     S.p_id = (uint32_t*)take(4 * cap); S.p_ex = (int*)take(4 * cap);
     S.c_id = (uint32_t*)take(4 * cap); S.c_mie = (int*)take(4 * cap); S.c_de = (int*)take(4 * cap);
     S.dexp[0] = (int*)take(4 * cap); S.dexp[1] = (int*)take(4 * cap);
-    S.dstamp[0] = (uint32_t*)take(4 * cap); S.dstamp[1] = (uint32_t*)take(4 * cap);
-    S.firstpos = (uint32_t*)take(4 * cap); S.d_seen = (uint32_t*)take(4 * cap);
-    S.k_T = (int*)take(4 * cap);
+    S.k_T = S.dexp[0];
+    S.firstpos = (uint32_t*)take(4 * cap);
     S.scan = (uint32_t*)take(4 * (cap + 1));
     S.ph_key = (uint32_t*)take(4 * hcap); S.ph_val = (uint32_t*)take(4 * hcap);
     S.ch_key = (uint32_t*)take(4 * hcap); S.ch_val = (uint32_t*)take(4 * hcap);
-    S.top_id = (uint32_t*)take(4 * MAX_ACTIVE);
+    S.top_id = (uint32_t*)take(4 * (cap < MAX_ACTIVE ? cap : MAX_ACTIVE));
     S.la_id[0] = (uint32_t*)take(4 * cap); S.la_id[1] = (uint32_t*)take(4 * cap); S.act_id = (uint32_t*)take(4 * cap);
     S.la_slot[0] = (uint16_t*)take(2 * cap); S.la_slot[1] = (uint16_t*)take(2 * cap); S.act_slot = (uint16_t*)take(2 * cap);
     S.dlist = (uint16_t*)take(2 * cap);
-    S.ccap = 4 * cap; S.ccell = (unsigned short*)take(2 * (size_t)S.ccap); S.cpre = (uint32_t*)take(4 * ((size_t)S.ccap + 1));
-    S.wt = (uint32_t*)take(4 * 64); S.tog = 0; S.ecall = 0;
+    S.dstamp[0] = (uint8_t*)take(cap); S.dstamp[1] = (uint8_t*)take(cap); S.d_seen = (uint8_t*)take(cap);
+    S.wt = (uint32_t*)take(4 * 16); S.tog = 0; S.ecall = 0;
+    if (threadIdx.x < 16) S.wt[threadIdx.x] = 0;
 
     __shared__ XF s_mb, s_ib;          // begin scalars of the previous row (forward) / ib of the next row (backward)
     __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
@@ -381,7 +420,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         }
         if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
         const uint32_t n_mi = (uint32_t)n_act;
-        const uint32_t stamp0 = s * 8 + 1;
+        const uint32_t stamp0 = 1;   // Del stamps: round t writes t + 1
         uint32_t n_d = 0;
 
         if (fwd) {
@@ -419,8 +458,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                     for (int a = tid; a < n_l; a += B) { l_id[a] = S.act_id[a]; l_slot[a] = S.act_slot[a]; }
                     __syncthreads();
                 }
-                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint32_t* st = S.dstamp[t & 1];
-                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint32_t* stp = S.dstamp[(t & 1) ^ 1];
+                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint8_t* st = S.dstamp[t & 1];
+                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint8_t* stp = S.dstamp[(t & 1) ^ 1];
                 for (int a0 = 0; a0 < n_l; a0 += B) {
                     const int a = a0 + tid;
                     uint32_t sl = 0, fresh = 0;
@@ -436,7 +475,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                             else if (stp[ps] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[ps], dep[ps]));
                         }
                         if (t == 0) acc = xadd(acc, xmul(ib_cur, lp.p_ID * init[id]));
-                        dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
+                        dv[sl] = acc.v; de[sl] = acc.e; st[sl] = (uint8_t)(stamp0 + t);
                         XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
                         S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
                         fresh = S.d_seen[sl] ? 0u : 1u;
@@ -472,8 +511,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                     if (!ok) break;
                     l_id = S.la_id[t & 1]; l_slot = S.la_slot[t & 1]; n_l = nn;
                 }
-                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint32_t* st = S.dstamp[t & 1];
-                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint32_t* stp = S.dstamp[(t & 1) ^ 1];
+                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint8_t* st = S.dstamp[t & 1];
+                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint8_t* stp = S.dstamp[(t & 1) ^ 1];
                 for (int a0 = 0; a0 < n_l; a0 += B) {
                     const int a = a0 + tid;
                     uint32_t sl = 0, fresh = 0;
@@ -498,7 +537,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                             prev_get(S, PA, id, &pm, &pi, &pd, &pe);
                             acc = xadd(acc, xf(lp.p_DI * lp.p_random * pi, pe));
                         }
-                        dv[sl] = acc.v; de[sl] = acc.e; st[sl] = stamp0 + t;
+                        dv[sl] = acc.v; de[sl] = acc.e; st[sl] = (uint8_t)(stamp0 + t);
                         XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
                         S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
                         fresh = S.d_seen[sl] ? 0u : 1u;
@@ -605,15 +644,13 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
 static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) {
     auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t s = 0;
-    s += 9 * r16(8 * (size_t)cap);
-    s += 12 * r16(4 * (size_t)cap);
-    s += r16(4 * ((size_t)cap + 1));
-    s += 4 * r16(4 * (size_t)hcap);
-    s += r16(4 * MAX_ACTIVE);
-    s += 3 * r16(4 * (size_t)cap);
-    s += 4 * r16(2 * (size_t)cap);
-    s += r16(2 * 4 * (size_t)cap) + r16(4 * (4 * (size_t)cap + 1));
-    s += 4 * 64;
+    s += 8 * r16(8 * (size_t)cap);                       // p_m p_i p_d c_m c_i c_dv dval[2]
+    s += 8 * r16(4 * (size_t)cap);                       // p_id p_ex c_id c_mie c_de dexp[2] firstpos
+    s += r16(4 * ((size_t)cap + 1));                     // scan
+    s += 4 * r16(4 * (size_t)hcap);                      // two hash tables
+    s += r16(4 * (size_t)(cap < MAX_ACTIVE ? cap : MAX_ACTIVE));
+    s += 3 * r16(4 * (size_t)cap) + 4 * r16(2 * (size_t)cap);   // id lists, slot lists, dlist
+    s += 3 * r16((size_t)cap) + 64;                      // stamps, d_seen, prefix scratch
     return s;
 }
 
@@ -621,6 +658,22 @@ int sparse_configure(dbgphmm_model* m) {
     (void)m;
     CUDA_TRY(cudaFuncSetAttribute(k_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return DBGPHMM_OK;
+}
+
+// threads per job: the rows hold 40-130 entries and every phase is a short dependent chain, so two warps do as well as
+// four and let more jobs stay resident
+static int sparse_threads(uint32_t cap) { return cap <= 64 ? 32 : (cap <= 256 ? 64 : 256); }
+
+uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
+    uint32_t hcap = 1;
+    while (hcap < 2 * cap) hcap <<= 1;
+    int per_sm = 0;
+    cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sparse, sparse_threads(cap), sparse_smem_bytes(cap, hcap)) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    return (uint32_t)per_sm * (uint32_t)m->n_sm;
 }
 
 int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap) {
@@ -631,10 +684,10 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
     if (smem > 200 * 1024) { dbg_set_error("sparse_run: capacity too large for shared memory"); return DBGPHMM_ERR_INVALID; }
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
-    int threads = cap <= 64 ? 32 : (cap <= 256 ? 128 : 256);
+    int threads = sparse_threads(cap);
     if (const char* e = getenv("DBGPHMM_SPARSE_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) threads = t; }
-    {   // leave the rest of the unified L1/shared array to L1: the CSR walks of a job re-read the same few lines every row
-        int carve = (int)((smem * 4 + 8192) * 100 / (228 * 1024)) + 1;
+    {   // the kernel is latency-bound: as many resident jobs per SM as shared memory allows
+        int carve = 100;
         if (const char* e = getenv("DBGPHMM_SPARSE_CARVEOUT")) carve = atoi(e);
         if (carve < 10) carve = 10; if (carve > 100) carve = 100;
         cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, carve);

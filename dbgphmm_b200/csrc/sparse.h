@@ -55,5 +55,7 @@ struct SparseIO {
 };
 
 int sparse_configure(dbgphmm_model* m);
+// jobs that are resident at once with entry capacity `cap` (one wave): batches are cut to multiples of it
+uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap);
 // cap: entry capacity per job in shared memory (256 normal, 832 big); threads per CTA chosen from cap
 int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap);
