@@ -247,23 +247,58 @@ __device__ int sp_top_of_prev(SS& S, uint32_t n_prev, uint32_t K, bool by_ratio,
     __shared__ double s_L0;
     __shared__ uint32_t s_cnt;
     const int tid = threadIdx.x, B = blockDim.x;
-    for (uint32_t e = tid; e < n_prev; e += B) sp_key(S, e, &S.k_T[e], &S.k_mant[e]);
+    // Keys: (T, mantissa) of the merged value.  When every T lies within +-1000 binades of entry 0 (practically always)
+    // the pair packs into one 64-bit integer and a comparison is one instruction pair ; otherwise the generic path.
+    const int Tref = S.p_ex[0];
+    uint32_t* bad = S.wt + 16;   // zero on entry (reset below after use)
+    for (uint32_t e = tid; e < n_prev; e += B) {
+        int T; unsigned long long mant;
+        sp_key(S, e, &T, &mant);
+        S.k_T[e] = T;
+        unsigned long long key = 0;
+        if (T != XF_ZERO_E) {
+            const int rel = T - Tref + 1024;
+            if (rel < 1 || rel > 2046) *bad = 1;
+            key = ((unsigned long long)(unsigned)rel << 52) | mant;
+        }
+        S.k_mant[e] = key;
+    }
     if (tid == 0) { s_cnt = 0; s_L0 = -INFINITY; }
     __syncthreads();
+    const bool generic = *bad != 0;
     const uint32_t KK = K < n_prev ? K : n_prev;
-    for (uint32_t e = tid; e < n_prev; e += B) {
-        int T = S.k_T[e]; unsigned long long mt = S.k_mant[e];
-        uint32_t rank = 0;
-        for (uint32_t f = 0; f < n_prev; f++) {
-            int Tf = S.k_T[f]; unsigned long long mf = S.k_mant[f];
-            bool gt = (Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)));
-            rank += gt ? 1u : 0u;
+    if (!generic) {
+        for (uint32_t e = tid; e < n_prev; e += B) {
+            const unsigned long long ke = S.k_mant[e];
+            uint32_t rank = 0;
+#pragma unroll 4
+            for (uint32_t f = 0; f < n_prev; f++) {
+                const unsigned long long kf = S.k_mant[f];
+                rank += (kf > ke || (kf == ke && f < e)) ? 1u : 0u;
+            }
+            if (rank < KK) out_id[rank] = S.p_id[e];
+            S.scan[e] = rank;  // remember for the ratio filter
+            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
         }
-        if (rank < KK) out_id[rank] = S.p_id[e];
-        S.scan[e] = rank;  // remember for the ratio filter
-        if (rank == 0) s_L0 = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
+    } else {
+        // (a row mixing packed and unpacked keys cannot be ranked by k_mant alone: recompute the mantissas)
+        for (uint32_t e = tid; e < n_prev; e += B) { int T; unsigned long long mant; sp_key(S, e, &T, &mant); S.k_mant[e] = mant; }
+        __syncthreads();
+        for (uint32_t e = tid; e < n_prev; e += B) {
+            int T = S.k_T[e]; unsigned long long mt = S.k_mant[e];
+            uint32_t rank = 0;
+            for (uint32_t f = 0; f < n_prev; f++) {
+                int Tf = S.k_T[f]; unsigned long long mf = S.k_mant[f];
+                bool gt = (Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)));
+                rank += gt ? 1u : 0u;
+            }
+            if (rank < KK) out_id[rank] = S.p_id[e];
+            S.scan[e] = rank;
+            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
+        }
     }
     __syncthreads();
+    if (tid == 0) *bad = 0;
     if (!by_ratio) return (int)KK;
     for (uint32_t e = tid; e < n_prev; e += B) {
         if (S.scan[e] < KK) {
@@ -320,8 +355,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     S.la_slot[0] = (uint16_t*)take(2 * cap); S.la_slot[1] = (uint16_t*)take(2 * cap); S.act_slot = (uint16_t*)take(2 * cap);
     S.dlist = (uint16_t*)take(2 * cap);
     S.dstamp[0] = (uint8_t*)take(cap); S.dstamp[1] = (uint8_t*)take(cap); S.d_seen = (uint8_t*)take(cap);
-    S.wt = (uint32_t*)take(4 * 16); S.tog = 0; S.ecall = 0;
-    if (threadIdx.x < 16) S.wt[threadIdx.x] = 0;
+    S.wt = (uint32_t*)take(4 * 20); S.tog = 0; S.ecall = 0;   // [2][8] warp totals + flags
+    if (threadIdx.x < 20) S.wt[threadIdx.x] = 0;
 
     __shared__ XF s_mb, s_ib;          // begin scalars of the previous row (forward) / ib of the next row (backward)
     __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
@@ -650,7 +685,7 @@ static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) {
     s += 4 * r16(4 * (size_t)hcap);                      // two hash tables
     s += r16(4 * (size_t)(cap < MAX_ACTIVE ? cap : MAX_ACTIVE));
     s += 3 * r16(4 * (size_t)cap) + 4 * r16(2 * (size_t)cap);   // id lists, slot lists, dlist
-    s += 3 * r16((size_t)cap) + 64;                      // stamps, d_seen, prefix scratch
+    s += 3 * r16((size_t)cap) + 80;                      // stamps, d_seen, prefix scratch
     return s;
 }
 
