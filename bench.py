@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads of the CPU baseline sample (0 = auto)")
     ap.add_argument("--cpu-read-len", type=int, default=8, help="bases kept per read in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end passes (profiling runs under ncu only; the line then has e2e.value = null)")
     return ap.parse_args()
 
 
@@ -215,14 +216,14 @@ def main():
     value = float(c.item()) / (float(t.item()) * 1e-3) / 1e9
     # end to end
     e_cells, e_ms = 0, 0.0
-    for i in range(1 + min(args.steps, 2)):
+    for i in range(0 if args.no_e2e else 1 + min(args.steps, 2)):
         cc, ms, _ = step_e2e()
         if i > 0:
             e_cells += cc; e_ms += ms
     te = torch.tensor([e_ms], dtype=torch.float64, device="cuda"); ce = torch.tensor([float(e_cells)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce)
-    e2e_val = float(ce.item()) / (float(te.item()) * 1e-3) / 1e9
+    e2e_val = float(ce.item()) / (float(te.item()) * 1e-3) / 1e9 if te.item() > 0 else None
     out = None
     if rank == 0:
         peaks = {}
@@ -232,8 +233,17 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (k_cells * ALGO_BYTES_PER_CELL / (k_ms * 1e-3) / 1e9) if k_ms > 0 else 0.0
+        # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this command
+        # (profiles/r1_dense_reg_dram.json, tools/ncu_summary.py); scaled per cell when the launch shape differs
+        traffic = None
+        try:
+            caps = json.load(open(os.path.join(ROOT, "profiles", "r1_dense_reg_dram.json")))
+            per_cell = sum(c["dram_bytes_per_cell"] for c in caps) / len(caps)
+            traffic = per_cell * (k_cells / max(k_launch, 1))
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "k_dense_reg<FWD>/<BWD> (+ exact worklist kernel, same timed interval)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
+                "traffic": traffic, "traffic_source": "profiles/r1_dense_reg_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell x cells per launch)", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
                 "avg_launch_ms": k_ms / max(k_launch, 1), "launches": k_launch, "cells_per_launch": k_cells / max(k_launch, 1),
                 "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "kernel_share_of_step": k_ms / max(tot_ms, 1e-9)}
         out = {"metric": "PHMM forward-backward GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
