@@ -169,7 +169,7 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
     std::vector<uint32_t> todo(n);
     for (uint32_t i = 0; i < n; i++) todo[i] = i;
     uint32_t caps[3] = {small_cap, 256, 832};
-    if (const char* e = getenv("DBGPHMM_SPARSE_CAP")) { int c0 = atoi(e); if (c0 >= 32 && c0 <= 832) caps[0] = (uint32_t)c0; }
+    if (const char* e = getenv("DBGPHMM_SPARSE_CAP")) { int c0 = atoi(e); if (c0 >= 32 && c0 <= 832) caps[0] = ((uint32_t)c0 + 15u) & ~15u; }
     for (int pass = 0; pass < 3 && !todo.empty(); pass++) {
         if (pass > 0 && caps[pass] <= caps[pass - 1]) continue;
         std::vector<SJob> cur(todo.size());

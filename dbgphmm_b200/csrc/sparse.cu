@@ -23,27 +23,49 @@ struct SGraph {
     const uint32_t* pos_of;
 };
 
-struct SS {  // shared-memory view of one job
-    uint32_t cap, hmask;
+// Shared-memory view of one job.  Every array sits at a fixed multiple of `cap` bytes from `base`, so the view is five
+// registers and an array address is one multiply-add (a struct of ~35 pointers ends up in local memory as soon as it is
+// passed by reference, and every access becomes a long-scoreboard local load).  cap must be a multiple of 16.
+struct SS {
+    unsigned char* base;
+    uint32_t cap, hcap, hmask;
     int hshift;
+    uint32_t htog;          // which of the two hash tables belongs to the current row
+    uint32_t tog, ecall;    // block_prefix / sp_expand call parities
+#define SS_ARR(type, name, off_in_caps) __device__ __forceinline__ type* name() const { return (type*)(base + (size_t)(off_in_caps) * cap); }
     // previous row (packed cells)
-    uint32_t* p_id; double *p_m, *p_i, *p_d; int* p_ex;
-    uint32_t *ph_key, *ph_val;
+    SS_ARR(double, p_m, 0) SS_ARR(double, p_i, 8) SS_ARR(double, p_d, 16)
     // current row under construction
-    uint32_t* c_id; double *c_m, *c_i; int* c_mie; double* c_dv; int* c_de;
-    double* dval[2]; int* dexp[2]; uint8_t* dstamp[2];   // Del round values of the last two rounds ; stamp = round + 1 (entries are rebuilt every row)
-    uint32_t* firstpos; uint8_t* d_seen;
-    uint32_t *ch_key, *ch_val;
-    // lists
-    uint32_t* top_id;                    // [MAX_ACTIVE]
-    uint32_t* la_id[2]; uint16_t* la_slot[2];  // ping-pong node lists (ids + slots), [cap] each
-    uint32_t* act_id; uint16_t* act_slot;      // the step's `nodes` (m/i entries)
-    uint16_t* dlist;                     // [cap] slots in d insertion order
-    uint32_t* scan;                      // [cap + 1] scratch
-    // ranking scratch
-    int* k_T; unsigned long long* k_mant;   // ranking keys (alias the Del round buffers, which are dead between rows)
-    uint32_t* wt; uint32_t tog, ecall;   // block_prefix scratch [2][8] + call parities
+    SS_ARR(double, c_m, 24) SS_ARR(double, c_i, 32) SS_ARR(double, c_dv, 40)
+    // Del values of the last two rounds ; stamp = round + 1 (entries are rebuilt every row)
+    __device__ __forceinline__ double* dval(int k) const { return (double*)(base + (size_t)(48 + 8 * k) * cap); }
+    SS_ARR(uint32_t, p_id, 64) SS_ARR(int, p_ex, 68)
+    SS_ARR(uint32_t, c_id, 72) SS_ARR(int, c_mie, 76) SS_ARR(int, c_de, 80)
+    __device__ __forceinline__ int* dexp(int k) const { return (int*)(base + (size_t)(84 + 4 * k) * cap); }
+    SS_ARR(uint32_t, firstpos, 92)
+    // ping-pong node lists (ids + slots) and the step's `nodes` (m/i entries)
+    __device__ __forceinline__ uint32_t* la_id(int k) const { return (uint32_t*)(base + (size_t)(96 + 4 * k) * cap); }
+    SS_ARR(uint32_t, act_id, 104)
+    SS_ARR(uint32_t, top_id, 108)
+    __device__ __forceinline__ uint16_t* la_slot(int k) const { return (uint16_t*)(base + (size_t)(112 + 2 * k) * cap); }
+    SS_ARR(uint16_t, act_slot, 116)
+    SS_ARR(uint16_t, dlist, 118)         // slots in d insertion order
+    __device__ __forceinline__ uint8_t* dstamp(int k) const { return (uint8_t*)(base + (size_t)(120 + k) * cap); }
+    SS_ARR(uint8_t, d_seen, 122)
+    SS_ARR(uint32_t, scan, 123)          // [cap + 4] scratch
+    // ranking keys alias the Del round buffers, which are dead between rows
+    __device__ __forceinline__ int* k_T() const { return dexp(0); }
+    __device__ __forceinline__ unsigned long long* k_mant() const { return (unsigned long long*)dval(0); }
+    // after the cap-proportional part (127 cap + 16 bytes): block_prefix scratch [2][8] + flags, then the two hash tables
+    __device__ __forceinline__ uint32_t* wt() const { return (uint32_t*)(base + (size_t)127 * cap + 16); }
+    __device__ __forceinline__ uint32_t* htab(uint32_t which) const { return (uint32_t*)(base + (size_t)127 * cap + 16 + 96) + (size_t)which * 2 * hcap; }
+    __device__ __forceinline__ uint32_t* ch_key() const { return htab(htog); }
+    __device__ __forceinline__ uint32_t* ch_val() const { return htab(htog) + hcap; }
+    __device__ __forceinline__ uint32_t* ph_key() const { return htab(htog ^ 1u); }
+    __device__ __forceinline__ uint32_t* ph_val() const { return htab(htog ^ 1u) + hcap; }
+#undef SS_ARR
 };
+#define SS_BYTES(cap, hcap) ((size_t)127 * (cap) + 16 + 96 + (size_t)16 * (hcap))
 
 __device__ __forceinline__ uint32_t sp_hash(uint32_t id, int shift) { return (id * 2654435761u) >> shift; }
 __device__ __forceinline__ int sp_find(const uint32_t* key, const uint32_t* val, uint32_t hmask, int hshift, uint32_t id) {
@@ -76,7 +98,7 @@ __device__ __forceinline__ uint32_t block_prefix(SS& S, uint32_t v, uint32_t* to
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    uint32_t* wt = S.wt + 8 * (S.tog & 1);
+    uint32_t* wt = S.wt() + 8 * (S.tog & 1);
     S.tog++;
     if (lane == 31) wt[w] = x;
     __syncthreads();
@@ -127,14 +149,14 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
     if (cap_limited) max_out = (int)S.cap;
     uint32_t* fl = s_flags[S.ecall & 1];
     S.ecall++;
-    for (uint32_t e = tid; e < n_ent0; e += B) S.firstpos[e] = SP_ABSENT;
+    for (uint32_t e = tid; e < n_ent0; e += B) S.firstpos()[e] = SP_ABSENT;
     if (tid == 0) { fl[0] = 0; fl[1] = 0; }
     const uint32_t n_self = and_us ? (uint32_t)n_src : 0u;
     auto note = [&](uint32_t id, uint32_t p) {   // phase 1 for one candidate
-        const uint32_t cell = sp_cell(S.ch_key, S.hmask, S.hshift, id);
-        const uint32_t v = S.ch_val[cell];
-        if (v < SP_TENT) atomicMin(&S.firstpos[v], p);
-        else atomicMin(&S.ch_val[cell], SP_TENT | p);
+        const uint32_t cell = sp_cell(S.ch_key(), S.hmask, S.hshift, id);
+        const uint32_t v = S.ch_val()[cell];
+        if (v < SP_TENT) atomicMin(&S.firstpos()[v], p);
+        else atomicMin(&S.ch_val()[cell], SP_TENT | p);
     };
     if (!with_nbrs) __syncthreads();   // (the prefix below is the barrier otherwise) firstpos reset before the min-reductions
     uint32_t C = n_self;
@@ -148,7 +170,7 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
             C += tot;
             if (q < n_src) {
                 if (cnt > 16) { fl[0] = 1; cnt = 0; }
-                S.scan[q] = base | (cnt << 20);
+                S.scan()[q] = base | (cnt << 20);
                 for (uint32_t k = 0; k < cnt; k++) note(nbr[o0 + k], base + k);
             }
         }
@@ -158,10 +180,10 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
     // kept / new flag of candidate p with id `id` : bit 0 kept, bit 16 new entry
     auto flag_of = [&](uint32_t id, uint32_t p, uint32_t* cell_out, uint32_t* v_out) -> uint32_t {
         uint32_t h = sp_hash(id, S.hshift);
-        while (S.ch_key[h] != id + 1) h = (h + 1) & S.hmask;   // inserted in phase 1
-        const uint32_t v = S.ch_val[h];
+        while (S.ch_key()[h] != id + 1) h = (h + 1) & S.hmask;   // inserted in phase 1
+        const uint32_t v = S.ch_val()[h];
         *cell_out = h; *v_out = v;
-        if (v < SP_TENT) return (S.firstpos[v] == p) ? 1u : 0u;
+        if (v < SP_TENT) return (S.firstpos()[v] == p) ? 1u : 0u;
         return v == (SP_TENT | p) ? 0x10001u : 0u;
     };
     auto emit = [&](uint32_t id, uint32_t p, uint32_t f, uint32_t excl, uint32_t cell, uint32_t v) {
@@ -173,14 +195,14 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
             if (slot >= S.cap) fl[0] = 1;
             else {
                 if (isnew) {
-                    S.c_id[slot] = id; S.c_m[slot] = 0.0; S.c_i[slot] = 0.0; S.c_mie[slot] = 0; S.c_dv[slot] = 0.0; S.c_de[slot] = XF_ZERO_E;
-                    S.dstamp[0][slot] = 0; S.dstamp[1][slot] = 0; S.d_seen[slot] = 0; S.firstpos[slot] = p;
+                    S.c_id()[slot] = id; S.c_m()[slot] = 0.0; S.c_i()[slot] = 0.0; S.c_mie()[slot] = 0; S.c_dv()[slot] = 0.0; S.c_de()[slot] = XF_ZERO_E;
+                    S.dstamp(0)[slot] = 0; S.dstamp(1)[slot] = 0; S.d_seen()[slot] = 0; S.firstpos()[slot] = p;
                 }
                 out_id[oi] = id; out_slot[oi] = (unsigned short)slot;
             }
         }
         if (isnew) {
-            S.ch_val[cell] = (em && slot < S.cap) ? slot : SP_ABSENT;
+            S.ch_val()[cell] = (em && slot < S.cap) ? slot : SP_ABSENT;
             if (!em) atomicAdd(&fl[1], 1u);
         }
     };
@@ -202,7 +224,7 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
             const int q = q0 + tid;
             uint32_t o0 = 0, base = 0, cnt = 0, mask = 0, mine = 0;
             if (q < n_src) {
-                const uint32_t sc = S.scan[q];
+                const uint32_t sc = S.scan()[q];
                 base = sc & 0xfffffu; cnt = sc >> 20; o0 = off[src[q]];
                 for (uint32_t k = 0; k < cnt; k++) {
                     uint32_t cell, v;
@@ -234,10 +256,10 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
 
 // merged value key of packed entry e of the previous row
 __device__ __forceinline__ void sp_key(const SS& S, uint32_t e, int* T, unsigned long long* mant) {
-    double v = S.p_m[e] + S.p_i[e] + S.p_d[e];
+    double v = S.p_m()[e] + S.p_i()[e] + S.p_d()[e];
     if (v == 0.0) { *T = XF_ZERO_E; *mant = 0; return; }
     long long b = __double_as_longlong(v);
-    *T = S.p_ex[e] + (int)((b >> 52) & 0x7ff) - 1023;
+    *T = S.p_ex()[e] + (int)((b >> 52) & 0x7ff) - 1023;
     *mant = (unsigned long long)b & 0xfffffffffffffull;
 }
 
@@ -249,19 +271,19 @@ __device__ int sp_top_of_prev(SS& S, uint32_t n_prev, uint32_t K, bool by_ratio,
     const int tid = threadIdx.x, B = blockDim.x;
     // Keys: (T, mantissa) of the merged value.  When every T lies within +-1000 binades of entry 0 (practically always)
     // the pair packs into one 64-bit integer and a comparison is one instruction pair ; otherwise the generic path.
-    const int Tref = S.p_ex[0];
-    uint32_t* bad = S.wt + 16;   // zero on entry (reset below after use)
+    const int Tref = S.p_ex()[0];
+    uint32_t* bad = S.wt() + 16;   // zero on entry (reset below after use)
     for (uint32_t e = tid; e < n_prev; e += B) {
         int T; unsigned long long mant;
         sp_key(S, e, &T, &mant);
-        S.k_T[e] = T;
+        S.k_T()[e] = T;
         unsigned long long key = 0;
         if (T != XF_ZERO_E) {
             const int rel = T - Tref + 1024;
             if (rel < 1 || rel > 2046) *bad = 1;
             key = ((unsigned long long)(unsigned)rel << 52) | mant;
         }
-        S.k_mant[e] = key;
+        S.k_mant()[e] = key;
     }
     if (tid == 0) { s_cnt = 0; s_L0 = -INFINITY; }
     __syncthreads();
@@ -269,40 +291,40 @@ __device__ int sp_top_of_prev(SS& S, uint32_t n_prev, uint32_t K, bool by_ratio,
     const uint32_t KK = K < n_prev ? K : n_prev;
     if (!generic) {
         for (uint32_t e = tid; e < n_prev; e += B) {
-            const unsigned long long ke = S.k_mant[e];
+            const unsigned long long ke = S.k_mant()[e];
             uint32_t rank = 0;
 #pragma unroll 4
             for (uint32_t f = 0; f < n_prev; f++) {
-                const unsigned long long kf = S.k_mant[f];
+                const unsigned long long kf = S.k_mant()[f];
                 rank += (kf > ke || (kf == ke && f < e)) ? 1u : 0u;
             }
-            if (rank < KK) out_id[rank] = S.p_id[e];
-            S.scan[e] = rank;  // remember for the ratio filter
-            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
+            if (rank < KK) out_id[rank] = S.p_id()[e];
+            S.scan()[e] = rank;  // remember for the ratio filter
+            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m()[e] + S.p_i()[e] + S.p_d()[e], S.p_ex()[e]));
         }
     } else {
         // (a row mixing packed and unpacked keys cannot be ranked by k_mant alone: recompute the mantissas)
-        for (uint32_t e = tid; e < n_prev; e += B) { int T; unsigned long long mant; sp_key(S, e, &T, &mant); S.k_mant[e] = mant; }
+        for (uint32_t e = tid; e < n_prev; e += B) { int T; unsigned long long mant; sp_key(S, e, &T, &mant); S.k_mant()[e] = mant; }
         __syncthreads();
         for (uint32_t e = tid; e < n_prev; e += B) {
-            int T = S.k_T[e]; unsigned long long mt = S.k_mant[e];
+            int T = S.k_T()[e]; unsigned long long mt = S.k_mant()[e];
             uint32_t rank = 0;
             for (uint32_t f = 0; f < n_prev; f++) {
-                int Tf = S.k_T[f]; unsigned long long mf = S.k_mant[f];
+                int Tf = S.k_T()[f]; unsigned long long mf = S.k_mant()[f];
                 bool gt = (Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)));
                 rank += gt ? 1u : 0u;
             }
-            if (rank < KK) out_id[rank] = S.p_id[e];
-            S.scan[e] = rank;
-            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
+            if (rank < KK) out_id[rank] = S.p_id()[e];
+            S.scan()[e] = rank;
+            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m()[e] + S.p_i()[e] + S.p_d()[e], S.p_ex()[e]));
         }
     }
     __syncthreads();
     if (tid == 0) *bad = 0;
     if (!by_ratio) return (int)KK;
     for (uint32_t e = tid; e < n_prev; e += B) {
-        if (S.scan[e] < KK) {
-            double L = xlog(xf(S.p_m[e] + S.p_i[e] + S.p_d[e], S.p_ex[e]));
+        if (S.scan()[e] < KK) {
+            double L = xlog(xf(S.p_m()[e] + S.p_i()[e] + S.p_d()[e], S.p_ex()[e]));
             if (s_L0 - L < ratio) atomicAdd(&s_cnt, 1u);
         }
     }
@@ -319,8 +341,8 @@ struct PrevAcc {  // accessor of the row before the current one
 };
 __device__ __forceinline__ void prev_get(const SS& S, const PrevAcc& P, uint32_t id, double* m, double* i, double* d, int* ex) {
     if (P.kind == 0) {
-        int sl = sp_find(S.ph_key, S.ph_val, S.hmask, S.hshift, id);
-        if (sl < 0) { *m = *i = *d = 0.0; *ex = 0; } else { *m = S.p_m[sl]; *i = S.p_i[sl]; *d = S.p_d[sl]; *ex = S.p_ex[sl]; }
+        int sl = sp_find(S.ph_key(), S.ph_val(), S.hmask, S.hshift, id);
+        if (sl < 0) { *m = *i = *d = 0.0; *ex = 0; } else { *m = S.p_m()[sl]; *i = S.p_i()[sl]; *d = S.p_d()[sl]; *ex = S.p_ex()[sl]; }
     } else if (P.kind == 1) { *m = P.gm[id]; *i = P.gi[id]; *d = P.gd[id]; *ex = P.ge[id]; }
     else if (P.kind == 2) { *m = *i = *d = P.p_end; *ex = 0; }
     else { *m = *i = *d = 0.0; *ex = 0; }
@@ -333,30 +355,11 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     if (jb.active_idx >= 0 && !io.active[jb.active_idx]) return;
     if (jb.n_rows == 0) return;
     const int tid = threadIdx.x, B = blockDim.x;
-    // ---- carve shared memory
+    // ---- shared-memory view
     SS S;
-    S.cap = cap; S.hmask = hcap - 1; S.hshift = 32 - (31 - __clz(hcap));
-    unsigned char* q = sp_smem;
-    auto take = [&](size_t bytes) { unsigned char* r = q; q += (bytes + 15) & ~(size_t)15; return r; };
-    S.p_m = (double*)take(8 * cap); S.p_i = (double*)take(8 * cap); S.p_d = (double*)take(8 * cap);
-    S.c_m = (double*)take(8 * cap); S.c_i = (double*)take(8 * cap); S.c_dv = (double*)take(8 * cap);
-    S.dval[0] = (double*)take(8 * cap); S.dval[1] = (double*)take(8 * cap);
-    S.k_mant = (unsigned long long*)S.dval[0];
-    S.p_id = (uint32_t*)take(4 * cap); S.p_ex = (int*)take(4 * cap);
-    S.c_id = (uint32_t*)take(4 * cap); S.c_mie = (int*)take(4 * cap); S.c_de = (int*)take(4 * cap);
-    S.dexp[0] = (int*)take(4 * cap); S.dexp[1] = (int*)take(4 * cap);
-    S.k_T = S.dexp[0];
-    S.firstpos = (uint32_t*)take(4 * cap);
-    S.scan = (uint32_t*)take(4 * (cap + 1));
-    S.ph_key = (uint32_t*)take(4 * hcap); S.ph_val = (uint32_t*)take(4 * hcap);
-    S.ch_key = (uint32_t*)take(4 * hcap); S.ch_val = (uint32_t*)take(4 * hcap);
-    S.top_id = (uint32_t*)take(4 * (cap < MAX_ACTIVE ? cap : MAX_ACTIVE));
-    S.la_id[0] = (uint32_t*)take(4 * cap); S.la_id[1] = (uint32_t*)take(4 * cap); S.act_id = (uint32_t*)take(4 * cap);
-    S.la_slot[0] = (uint16_t*)take(2 * cap); S.la_slot[1] = (uint16_t*)take(2 * cap); S.act_slot = (uint16_t*)take(2 * cap);
-    S.dlist = (uint16_t*)take(2 * cap);
-    S.dstamp[0] = (uint8_t*)take(cap); S.dstamp[1] = (uint8_t*)take(cap); S.d_seen = (uint8_t*)take(cap);
-    S.wt = (uint32_t*)take(4 * 20); S.tog = 0; S.ecall = 0;   // [2][8] warp totals + flags
-    if (threadIdx.x < 20) S.wt[threadIdx.x] = 0;
+    S.base = sp_smem; S.cap = cap; S.hcap = hcap; S.hmask = hcap - 1; S.hshift = 32 - (31 - __clz(hcap));
+    S.htog = 0; S.tog = 0; S.ecall = 0;
+    if (threadIdx.x < 24) S.wt()[threadIdx.x] = 0;
 
     __shared__ XF s_mb, s_ib;          // begin scalars of the previous row (forward) / ib of the next row (backward)
     __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
@@ -397,16 +400,16 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         if (jb.mode == SP_TOPN || jb.mode == SP_RATIO) {
             if (s == 0) {
                 n_top = (int)io.top_cnt[jb.top0];
-                for (int t = tid; t < n_top; t += B) S.top_id[t] = io.top_ids[(size_t)jb.top0 * MAX_ACTIVE + t];
+                for (int t = tid; t < n_top; t += B) S.top_id()[t] = io.top_ids[(size_t)jb.top0 * MAX_ACTIVE + t];
             } else {
                 n_top = sp_top_of_prev(S, n_prev, jb.mode == SP_RATIO ? MAX_ACTIVE : lp.n_active_nodes, jb.mode == SP_RATIO,
-                                       lp.active_node_max_ratio, S.top_id);
+                                       lp.active_node_max_ratio, S.top_id());
             }
         } else if (jb.mode == SP_MAPPING) {
             uint64_t a = io.map_row_off[jb.map_row0 + row], b = io.map_row_off[jb.map_row0 + row + 1];
             n_top = (int)(b - a);
             if (n_top > MAX_ACTIVE) n_top = MAX_ACTIVE;
-            for (int t = tid; t < n_top; t += B) S.top_id[t] = io.map_nodes[a + t];
+            for (int t = tid; t < n_top; t += B) S.top_id()[t] = io.map_nodes[a + t];
         } else {  // SP_BYFWD: filled_nodes() of forward row (row-1): top-|m entries| of its merged vector
             const RowDesc fr = io.fdesc[jb.fdesc0 + row - 1];
             const char* pay = io.farena + fr.off;
@@ -417,19 +420,19 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 // stage into the *current* arrays (not yet in use) and rank there
                 for (uint32_t e = tid; e < fr.n_ent; e += B) {
                     double v = fm[e] + fi[e] + fd[e];
-                    if (v == 0.0) { S.k_T[e] = XF_ZERO_E; S.k_mant[e] = 0; }
-                    else { long long bb = __double_as_longlong(v); S.k_T[e] = fex[e] + (int)((bb >> 52) & 0x7ff) - 1023; S.k_mant[e] = (unsigned long long)bb & 0xfffffffffffffull; }
-                    S.c_id[e] = fid[e];
+                    if (v == 0.0) { S.k_T()[e] = XF_ZERO_E; S.k_mant()[e] = 0; }
+                    else { long long bb = __double_as_longlong(v); S.k_T()[e] = fex[e] + (int)((bb >> 52) & 0x7ff) - 1023; S.k_mant()[e] = (unsigned long long)bb & 0xfffffffffffffull; }
+                    S.c_id()[e] = fid[e];
                 }
                 __syncthreads();
                 for (uint32_t e = tid; e < fr.n_ent; e += B) {
-                    int T = S.k_T[e]; unsigned long long mt = S.k_mant[e];
+                    int T = S.k_T()[e]; unsigned long long mt = S.k_mant()[e];
                     uint32_t rank = 0;
                     for (uint32_t f = 0; f < fr.n_ent; f++) {
-                        int Tf = S.k_T[f]; unsigned long long mf = S.k_mant[f];
+                        int Tf = S.k_T()[f]; unsigned long long mf = S.k_mant()[f];
                         rank += ((Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)))) ? 1u : 0u;
                     }
-                    if (rank < fr.n_mi) S.top_id[rank] = S.c_id[e];
+                    if (rank < fr.n_mi) S.top_id()[rank] = S.c_id()[e];
                 }
                 n_top = (int)fr.n_mi;
             }
@@ -440,7 +443,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
 
         // ---------------- 2. reset the current row
         uint32_t n_ent = 0;
-        for (uint32_t h = tid; h < hcap; h += B) { S.ch_key[h] = 0; S.ch_val[h] = SP_ABSENT; }
+        for (uint32_t h = tid; h < hcap; h += B) { S.ch_key()[h] = 0; S.ch_val()[h] = SP_ABSENT; }
         __syncthreads();
 
         // ---------------- 3. the step's `nodes` (they hold m, i)
@@ -448,10 +451,10 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         bool ok = true;
         if (fwd) {
             // forward sparse: nodes = to_childs_and_us(top) (forward.rs:148) ; mapping: nodes = mapping.nodes(i)
-            ok = sp_expand(S, S.top_id, n_top, G.chi_off, G.chi_node, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
+            ok = sp_expand(S, S.top_id(), n_top, G.chi_off, G.chi_node, true, adaptive, S.act_id(), S.act_slot(), MAX_ACTIVE, &n_ent, &n_act);
         } else {
             // backward sparse: M/I over to_parents_and_us(nodes) (backward.rs:243-259) ; non-adaptive: nodes themselves
-            ok = sp_expand(S, S.top_id, n_top, G.par_off, G.par_node, true, adaptive, S.act_id, S.act_slot, MAX_ACTIVE, &n_ent, &n_act);
+            ok = sp_expand(S, S.top_id(), n_top, G.par_off, G.par_node, true, adaptive, S.act_id(), S.act_slot(), MAX_ACTIVE, &n_ent, &n_act);
         }
         if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
         const uint32_t n_mi = (uint32_t)n_act;
@@ -463,7 +466,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             const XF fb0 = xadd(xmul(s_mb, lp.p_MM), xmul(s_ib, lp.p_IM));
             const XF ib_cur = xmul(xadd(xmul(s_mb, lp.p_MI), xmul(s_ib, lp.p_II)), lp.p_random);
             for (uint32_t a = tid; a < n_mi; a += B) {
-                uint32_t id = S.act_id[a], sl = S.act_slot[a];
+                uint32_t id = S.act_id()[a], sl = S.act_slot()[a];
                 XF acc = xf_zero();
                 for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
                     double pm, pi, pd; int pe;
@@ -476,25 +479,25 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 prev_get(S, PA, id, &pm, &pi, &pd, &pe);
                 XF i = xf(lp.p_random * (lp.p_MI * pm + lp.p_II * pi + lp.p_DI * pd), pe);
                 int Em = xexp(m), Ei = xexp(i), Ec = Em > Ei ? Em : Ei;
-                if (Ec == XF_ZERO_E) { S.c_m[sl] = 0.0; S.c_i[sl] = 0.0; S.c_mie[sl] = 0; }
-                else { S.c_m[sl] = m.v == 0.0 ? 0.0 : m.v * pow2i(m.e - Ec); S.c_i[sl] = i.v == 0.0 ? 0.0 : i.v * pow2i(i.e - Ec); S.c_mie[sl] = Ec; }
+                if (Ec == XF_ZERO_E) { S.c_m()[sl] = 0.0; S.c_i()[sl] = 0.0; S.c_mie()[sl] = 0; }
+                else { S.c_m()[sl] = m.v == 0.0 ? 0.0 : m.v * pow2i(m.e - Ec); S.c_i()[sl] = i.v == 0.0 ? 0.0 : i.v * pow2i(i.e - Ec); S.c_mie()[sl] = Ec; }
             }
             __syncthreads();
             // ---------------- 5f. fd: fd0 + 4 x fdt (forward.rs:423-466)
-            const uint32_t* src_id = S.act_id; int n_src = n_act;
+            const uint32_t* src_id = S.act_id(); int n_src = n_act;
             for (int t = 0; t < N_DEL_ROUNDS; t++) {
-                uint32_t* l_id = S.la_id[t & 1]; uint16_t* l_slot = S.la_slot[t & 1];
+                uint32_t* l_id = S.la_id(t & 1); uint16_t* l_slot = S.la_slot(t & 1);
                 int n_l = 0;
                 if (adaptive) {
                     ok = sp_expand(S, src_id, n_src, G.chi_off, G.chi_node, false, true, l_id, l_slot, MAX_ACTIVE, &n_ent, &n_l);
                     if (!ok) break;
                 } else {
                     n_l = n_act;
-                    for (int a = tid; a < n_l; a += B) { l_id[a] = S.act_id[a]; l_slot[a] = S.act_slot[a]; }
+                    for (int a = tid; a < n_l; a += B) { l_id[a] = S.act_id()[a]; l_slot[a] = S.act_slot()[a]; }
                     __syncthreads();
                 }
-                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint8_t* st = S.dstamp[t & 1];
-                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint8_t* stp = S.dstamp[(t & 1) ^ 1];
+                double* dv = S.dval(t & 1); int* de = S.dexp(t & 1); uint8_t* st = S.dstamp(t & 1);
+                const double* dvp = S.dval((t & 1) ^ 1); const int* dep = S.dexp((t & 1) ^ 1); const uint8_t* stp = S.dstamp((t & 1) ^ 1);
                 for (int a0 = 0; a0 < n_l; a0 += B) {
                     const int a = a0 + tid;
                     uint32_t sl = 0, fresh = 0;
@@ -503,22 +506,22 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                         sl = l_slot[a];
                         XF acc = xf_zero();
                         for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
-                            int ps = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, G.par_node[e]);
+                            int ps = sp_find(S.ch_key(), S.ch_val(), S.hmask, S.hshift, G.par_node[e]);
                             if (ps < 0) continue;
                             double tr = trans[G.par_eid[e]];
-                            if (t == 0) { if ((uint32_t)ps < n_mi) acc = xadd(acc, xf(tr * (lp.p_MD * S.c_m[ps] + lp.p_ID * S.c_i[ps]), S.c_mie[ps])); }
+                            if (t == 0) { if ((uint32_t)ps < n_mi) acc = xadd(acc, xf(tr * (lp.p_MD * S.c_m()[ps] + lp.p_ID * S.c_i()[ps]), S.c_mie()[ps])); }
                             else if (stp[ps] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[ps], dep[ps]));
                         }
                         if (t == 0) acc = xadd(acc, xmul(ib_cur, lp.p_ID * init[id]));
                         dv[sl] = acc.v; de[sl] = acc.e; st[sl] = (uint8_t)(stamp0 + t);
-                        XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
-                        S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
-                        fresh = S.d_seen[sl] ? 0u : 1u;
+                        XF tot = xadd(xf(S.c_dv()[sl], S.c_de()[sl]), acc);
+                        S.c_dv()[sl] = tot.v; S.c_de()[sl] = tot.e;
+                        fresh = S.d_seen()[sl] ? 0u : 1u;
                     }
                     // d insertion order: first time a slot receives a Del value
                     uint32_t n_new;
                     const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
-                    if (fresh) { if (o < cap) S.dlist[o] = (uint16_t)sl; S.d_seen[sl] = 1; }
+                    if (fresh) { if (o < cap) S.dlist()[o] = (uint16_t)sl; S.d_seen()[sl] = 1; }
                     n_d += n_new;
                 }
                 __syncthreads();
@@ -528,26 +531,26 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             // ---------------- 6f. fe over nodes (forward.rs:554-558), begin scalars
             XF part = xf_zero();
             for (uint32_t a = tid; a < n_mi; a += B) {
-                uint32_t sl = S.act_slot[a];
-                part = xadd(part, xadd(xf(S.c_m[sl] + S.c_i[sl], S.c_mie[sl]), xf(S.c_dv[sl], S.c_de[sl])));
+                uint32_t sl = S.act_slot()[a];
+                part = xadd(part, xadd(xf(S.c_m()[sl] + S.c_i()[sl], S.c_mie()[sl]), xf(S.c_dv()[sl], S.c_de()[sl])));
             }
             XF esum = block_xsum(part);
             last_scalar = xnorm(xmul(esum, lp.p_end));
             if (tid == 0) { s_mb = xf_zero(); s_ib = xnorm(ib_cur); }
         } else {
             // ---------------- 4b. bd: bd0 + 4 x bdt over iterated to_parents_and_us (backward.rs:299-343)
-            const uint32_t* src_id = S.act_id; int n_src = n_act;
+            const uint32_t* src_id = S.act_id(); int n_src = n_act;
             for (int t = 0; t < N_DEL_ROUNDS; t++) {
                 const uint32_t* l_id; const uint16_t* l_slot; int n_l;
-                if (t == 0 || !adaptive) { l_id = S.act_id; l_slot = S.act_slot; n_l = n_act; }  // A0 == to_parents_and_us(nodes)
+                if (t == 0 || !adaptive) { l_id = S.act_id(); l_slot = S.act_slot(); n_l = n_act; }  // A0 == to_parents_and_us(nodes)
                 else {
                     int nn = 0;
-                    ok = sp_expand(S, src_id, n_src, G.par_off, G.par_node, true, true, S.la_id[t & 1], S.la_slot[t & 1], MAX_ACTIVE, &n_ent, &nn);
+                    ok = sp_expand(S, src_id, n_src, G.par_off, G.par_node, true, true, S.la_id(t & 1), S.la_slot(t & 1), MAX_ACTIVE, &n_ent, &nn);
                     if (!ok) break;
-                    l_id = S.la_id[t & 1]; l_slot = S.la_slot[t & 1]; n_l = nn;
+                    l_id = S.la_id(t & 1); l_slot = S.la_slot(t & 1); n_l = nn;
                 }
-                double* dv = S.dval[t & 1]; int* de = S.dexp[t & 1]; uint8_t* st = S.dstamp[t & 1];
-                const double* dvp = S.dval[(t & 1) ^ 1]; const int* dep = S.dexp[(t & 1) ^ 1]; const uint8_t* stp = S.dstamp[(t & 1) ^ 1];
+                double* dv = S.dval(t & 1); int* de = S.dexp(t & 1); uint8_t* st = S.dstamp(t & 1);
+                const double* dvp = S.dval((t & 1) ^ 1); const int* dep = S.dexp((t & 1) ^ 1); const uint8_t* stp = S.dstamp((t & 1) ^ 1);
                 for (int a0 = 0; a0 < n_l; a0 += B) {
                     const int a = a0 + tid;
                     uint32_t sl = 0, fresh = 0;
@@ -563,7 +566,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                                 prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
                                 acc = xadd(acc, xf(tr * lp.p_DM * (G.emission[ch] == x ? lp.p_match : lp.p_mismatch) * pm, pe));
                             } else {
-                                int cs = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, ch);
+                                int cs = sp_find(S.ch_key(), S.ch_val(), S.hmask, S.hshift, ch);
                                 if (cs >= 0 && stp[cs] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[cs], dep[cs]));
                             }
                         }
@@ -573,13 +576,13 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                             acc = xadd(acc, xf(lp.p_DI * lp.p_random * pi, pe));
                         }
                         dv[sl] = acc.v; de[sl] = acc.e; st[sl] = (uint8_t)(stamp0 + t);
-                        XF tot = xadd(xf(S.c_dv[sl], S.c_de[sl]), acc);
-                        S.c_dv[sl] = tot.v; S.c_de[sl] = tot.e;
-                        fresh = S.d_seen[sl] ? 0u : 1u;
+                        XF tot = xadd(xf(S.c_dv()[sl], S.c_de()[sl]), acc);
+                        S.c_dv()[sl] = tot.v; S.c_de()[sl] = tot.e;
+                        fresh = S.d_seen()[sl] ? 0u : 1u;
                     }
                     uint32_t n_new;
                     const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
-                    if (fresh) { if (o < cap) S.dlist[o] = (uint16_t)sl; S.d_seen[sl] = 1; }
+                    if (fresh) { if (o < cap) S.dlist()[o] = (uint16_t)sl; S.d_seen()[sl] = 1; }
                     n_d += n_new;
                 }
                 __syncthreads();
@@ -589,7 +592,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             // ---------------- 5b. bm, bi over nodes ; bmb, bib sums (backward.rs:423-555)
             XF pmb = xf_zero(), pib = xf_zero();
             for (uint32_t a = tid; a < n_mi; a += B) {
-                uint32_t id = S.act_id[a], sl = S.act_slot[a];
+                uint32_t id = S.act_id()[a], sl = S.act_slot()[a];
                 XF am = xf_zero(), ai = xf_zero();
                 for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) {
                     uint32_t ch = G.chi_node[e];
@@ -597,8 +600,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                     double pm, pi, pd; int pe;
                     prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
                     XF tm = xf(tr * (G.emission[ch] == x ? lp.p_match : lp.p_mismatch) * pm, pe);
-                    int cs = sp_find(S.ch_key, S.ch_val, S.hmask, S.hshift, ch);
-                    XF td = cs >= 0 ? xf(tr * S.c_dv[cs], S.c_de[cs]) : xf_zero();
+                    int cs = sp_find(S.ch_key(), S.ch_val(), S.hmask, S.hshift, ch);
+                    XF td = cs >= 0 ? xf(tr * S.c_dv()[cs], S.c_de()[cs]) : xf_zero();
                     am = xadd(am, xadd(xmul(tm, lp.p_MM), xmul(td, lp.p_MD)));
                     ai = xadd(ai, xadd(xmul(tm, lp.p_IM), xmul(td, lp.p_ID)));
                 }
@@ -607,11 +610,11 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 am = xadd(am, xf(lp.p_MI * lp.p_random * pi, pe));
                 ai = xadd(ai, xf(lp.p_II * lp.p_random * pi, pe));
                 int Em = xexp(am), Ei = xexp(ai), Ec = Em > Ei ? Em : Ei;
-                if (Ec == XF_ZERO_E) { S.c_m[sl] = 0.0; S.c_i[sl] = 0.0; S.c_mie[sl] = 0; }
-                else { S.c_m[sl] = am.v == 0.0 ? 0.0 : am.v * pow2i(am.e - Ec); S.c_i[sl] = ai.v == 0.0 ? 0.0 : ai.v * pow2i(ai.e - Ec); S.c_mie[sl] = Ec; }
+                if (Ec == XF_ZERO_E) { S.c_m()[sl] = 0.0; S.c_i()[sl] = 0.0; S.c_mie()[sl] = 0; }
+                else { S.c_m()[sl] = am.v == 0.0 ? 0.0 : am.v * pow2i(am.e - Ec); S.c_i()[sl] = ai.v == 0.0 ? 0.0 : ai.v * pow2i(ai.e - Ec); S.c_mie()[sl] = Ec; }
                 // begin sums: init_l * (p_XM e_l(x) m''[l] + p_XD d[l])
                 XF um = xf((G.emission[id] == x ? lp.p_match : lp.p_mismatch) * pm, pe);
-                XF ud = xf(S.c_dv[sl], S.c_de[sl]);
+                XF ud = xf(S.c_dv()[sl], S.c_de()[sl]);
                 double in = init[id];
                 pmb = xadd(pmb, xmul(xadd(xmul(um, lp.p_MM), xmul(ud, lp.p_MD)), in));
                 pib = xadd(pib, xmul(xadd(xmul(um, lp.p_IM), xmul(ud, lp.p_ID)), in));
@@ -630,10 +633,10 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
 
         // ---------------- 7. pack the row into the "previous" arrays, swap hash tables
         for (uint32_t e = tid; e < n_ent; e += B) {
-            Cell cl = cell_pack(xf(S.c_m[e], S.c_mie[e]), xf(S.c_i[e], S.c_mie[e]), xf(S.c_dv[e], S.c_de[e]));
-            S.p_id[e] = S.c_id[e]; S.p_m[e] = cl.m; S.p_i[e] = cl.i; S.p_d[e] = cl.d; S.p_ex[e] = cl.e;
+            Cell cl = cell_pack(xf(S.c_m()[e], S.c_mie()[e]), xf(S.c_i()[e], S.c_mie()[e]), xf(S.c_dv()[e], S.c_de()[e]));
+            S.p_id()[e] = S.c_id()[e]; S.p_m()[e] = cl.m; S.p_i()[e] = cl.i; S.p_d()[e] = cl.d; S.p_ex()[e] = cl.e;
         }
-        { uint32_t* t1 = S.ph_key; S.ph_key = S.ch_key; S.ch_key = t1; uint32_t* t2 = S.ph_val; S.ph_val = S.ch_val; S.ch_val = t2; }
+        S.htog ^= 1u;
         n_prev = n_ent;
         if (tid == 0) s_cells += n_mi;
         __syncthreads();
@@ -655,8 +658,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             char* pay = io.arena + off;
             double* om = (double*)pay; double* oi = om + n_ent; double* od = oi + n_ent;
             uint32_t* oid = (uint32_t*)(od + n_ent); int* oex = (int*)(oid + n_ent); uint16_t* odl = (uint16_t*)(oex + n_ent);
-            for (uint32_t e = tid; e < n_ent; e += B) { om[e] = S.p_m[e]; oi[e] = S.p_i[e]; od[e] = S.p_d[e]; oid[e] = S.p_id[e]; oex[e] = S.p_ex[e]; }
-            for (uint32_t e = tid; e < n_d; e += B) odl[e] = S.dlist[e];
+            for (uint32_t e = tid; e < n_ent; e += B) { om[e] = S.p_m()[e]; oi[e] = S.p_i()[e]; od[e] = S.p_d()[e]; oid[e] = S.p_id()[e]; oex[e] = S.p_ex()[e]; }
+            for (uint32_t e = tid; e < n_d; e += B) odl[e] = S.dlist()[e];
             if (tid == 0) {
                 RowDesc r;
                 r.kind = ROW_SPARSE; r.n_ent = n_ent; r.n_mi = n_mi; r.n_d = n_d; r.off = off;
@@ -676,18 +679,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     }
 }
 
-static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) {
-    auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t s = 0;
-    s += 8 * r16(8 * (size_t)cap);                       // p_m p_i p_d c_m c_i c_dv dval[2]
-    s += 8 * r16(4 * (size_t)cap);                       // p_id p_ex c_id c_mie c_de dexp[2] firstpos
-    s += r16(4 * ((size_t)cap + 1));                     // scan
-    s += 4 * r16(4 * (size_t)hcap);                      // two hash tables
-    s += r16(4 * (size_t)(cap < MAX_ACTIVE ? cap : MAX_ACTIVE));
-    s += 3 * r16(4 * (size_t)cap) + 4 * r16(2 * (size_t)cap);   // id lists, slot lists, dlist
-    s += 3 * r16((size_t)cap) + 80;                      // stamps, d_seen, prefix scratch
-    return s;
-}
+static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) { return SS_BYTES(cap, hcap); }
 
 int sparse_configure(dbgphmm_model* m) {
     (void)m;
