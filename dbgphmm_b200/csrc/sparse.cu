@@ -486,15 +486,12 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             // ---------------- 5f. fd: fd0 + 4 x fdt (forward.rs:423-466)
             const uint32_t* src_id = S.act_id(); int n_src = n_act;
             for (int t = 0; t < N_DEL_ROUNDS; t++) {
-                uint32_t* l_id = S.la_id(t & 1); uint16_t* l_slot = S.la_slot(t & 1);
-                int n_l = 0;
+                const uint32_t* l_id = S.act_id(); const uint16_t* l_slot = S.act_slot();   // non-adaptive: every round runs over `nodes`
+                int n_l = n_act;
                 if (adaptive) {
-                    ok = sp_expand(S, src_id, n_src, G.chi_off, G.chi_node, false, true, l_id, l_slot, MAX_ACTIVE, &n_ent, &n_l);
+                    ok = sp_expand(S, src_id, n_src, G.chi_off, G.chi_node, false, true, S.la_id(t & 1), S.la_slot(t & 1), MAX_ACTIVE, &n_ent, &n_l);
                     if (!ok) break;
-                } else {
-                    n_l = n_act;
-                    for (int a = tid; a < n_l; a += B) { l_id[a] = S.act_id()[a]; l_slot[a] = S.act_slot()[a]; }
-                    __syncthreads();
+                    l_id = S.la_id(t & 1); l_slot = S.la_slot(t & 1);
                 }
                 double* dv = S.dval(t & 1); int* de = S.dexp(t & 1); uint8_t* st = S.dstamp(t & 1);
                 const double* dvp = S.dval((t & 1) ^ 1); const int* dep = S.dexp((t & 1) ^ 1); const uint8_t* stp = S.dstamp((t & 1) ^ 1);
@@ -518,12 +515,15 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                         S.c_dv()[sl] = tot.v; S.c_de()[sl] = tot.e;
                         fresh = S.d_seen()[sl] ? 0u : 1u;
                     }
-                    // d insertion order: first time a slot receives a Del value
-                    uint32_t n_new;
-                    const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
-                    if (fresh) { if (o < cap) S.dlist()[o] = (uint16_t)sl; S.d_seen()[sl] = 1; }
-                    n_d += n_new;
+                    // d insertion order: first time a slot receives a Del value (non-adaptive: round 0, in list order)
+                    if (adaptive) {
+                        uint32_t n_new;
+                        const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
+                        if (fresh) { if (o < cap) S.dlist()[o] = (uint16_t)sl; S.d_seen()[sl] = 1; }
+                        n_d += n_new;
+                    } else if (t == 0 && a < n_l) S.dlist()[a] = (uint16_t)sl;
                 }
+                if (!adaptive && t == 0) n_d = (uint32_t)n_l;
                 __syncthreads();
                 src_id = l_id; n_src = n_l;
             }
@@ -580,11 +580,14 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                         S.c_dv()[sl] = tot.v; S.c_de()[sl] = tot.e;
                         fresh = S.d_seen()[sl] ? 0u : 1u;
                     }
-                    uint32_t n_new;
-                    const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
-                    if (fresh) { if (o < cap) S.dlist()[o] = (uint16_t)sl; S.d_seen()[sl] = 1; }
-                    n_d += n_new;
+                    if (adaptive) {
+                        uint32_t n_new;
+                        const uint32_t o = n_d + block_prefix(S, fresh, &n_new);
+                        if (fresh) { if (o < cap) S.dlist()[o] = (uint16_t)sl; S.d_seen()[sl] = 1; }
+                        n_d += n_new;
+                    } else if (t == 0 && a < n_l) S.dlist()[a] = (uint16_t)sl;
                 }
+                if (!adaptive && t == 0) n_d = (uint32_t)n_l;
                 __syncthreads();
                 src_id = l_id; n_src = n_l;
             }
