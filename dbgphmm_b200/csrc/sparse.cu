@@ -263,65 +263,69 @@ __device__ __forceinline__ void sp_key(const SS& S, uint32_t e, int* T, unsigned
     *mant = (unsigned long long)b & 0xfffffffffffffull;
 }
 
+// Ranking keys.  (T, 52-bit mantissa) of a merged value ; zero value: T == XF_ZERO_E.  When every T lies within +-1000 binades of
+// Tref (practically always) the pair packs into one 64-bit integer and a comparison is one instruction pair ; `bad` is raised
+// otherwise and the ranking falls back to the two-word comparison (the mantissa is the low 52 bits either way).
+__device__ __forceinline__ unsigned long long sp_pack(int T, unsigned long long mant, int Tref, uint32_t* bad) {
+    if (T == XF_ZERO_E) return 0;
+    const int rel = T - Tref + 1024;
+    if (rel < 1 || rel > 2046) *bad = 1;
+    return ((unsigned long long)(unsigned)rel << 52) | mant;
+}
+// Rank n keys (k_T, k_mant packed by sp_pack) in descending order, ties by position (UNPINNED in the reference):
+// out_id[rank] = ids[e] for rank < KK and scan[e] = rank.  Caller: barrier before (keys written) ; ends with a barrier.
+__device__ void sp_rank(SS& S, uint32_t n, uint32_t KK, const uint32_t* ids, uint32_t* out_id) {
+    const int tid = threadIdx.x, B = blockDim.x;
+    uint32_t* bad = S.wt() + 16;   // zero between rankings (reset below after use)
+    if (!*bad) {
+        for (uint32_t e = tid; e < n; e += B) {
+            const unsigned long long ke = S.k_mant()[e];
+            uint32_t rank = 0;
+#pragma unroll 4
+            for (uint32_t f = 0; f < n; f++) {
+                const unsigned long long kf = S.k_mant()[f];
+                rank += (kf > ke || (kf == ke && f < e)) ? 1u : 0u;
+            }
+            if (rank < KK) out_id[rank] = ids[e];
+            S.scan()[e] = rank;
+        }
+    } else {
+        const unsigned long long M52 = 0xfffffffffffffull;
+        for (uint32_t e = tid; e < n; e += B) {
+            const int T = S.k_T()[e]; const unsigned long long mt = T == XF_ZERO_E ? 0ull : (S.k_mant()[e] & M52);
+            uint32_t rank = 0;
+            for (uint32_t f = 0; f < n; f++) {
+                const int Tf = S.k_T()[f]; const unsigned long long mf = Tf == XF_ZERO_E ? 0ull : (S.k_mant()[f] & M52);
+                rank += ((Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)))) ? 1u : 0u;
+            }
+            if (rank < KK) out_id[rank] = ids[e];
+            S.scan()[e] = rank;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) *bad = 0;
+}
+
 // top-K ids of the previous (packed) row in descending merged value, ties by entry position (UNPINNED in the
 // reference); by_ratio keeps the prefix with ln v0 - ln v < ratio of the top-400 list (table.rs:134-149).
 __device__ int sp_top_of_prev(SS& S, uint32_t n_prev, uint32_t K, bool by_ratio, double ratio, uint32_t* out_id) {
     __shared__ double s_L0;
     __shared__ uint32_t s_cnt;
     const int tid = threadIdx.x, B = blockDim.x;
-    // Keys: (T, mantissa) of the merged value.  When every T lies within +-1000 binades of entry 0 (practically always)
-    // the pair packs into one 64-bit integer and a comparison is one instruction pair ; otherwise the generic path.
     const int Tref = S.p_ex()[0];
-    uint32_t* bad = S.wt() + 16;   // zero on entry (reset below after use)
     for (uint32_t e = tid; e < n_prev; e += B) {
         int T; unsigned long long mant;
         sp_key(S, e, &T, &mant);
-        S.k_T()[e] = T;
-        unsigned long long key = 0;
-        if (T != XF_ZERO_E) {
-            const int rel = T - Tref + 1024;
-            if (rel < 1 || rel > 2046) *bad = 1;
-            key = ((unsigned long long)(unsigned)rel << 52) | mant;
-        }
-        S.k_mant()[e] = key;
+        S.k_T()[e] = T; S.k_mant()[e] = sp_pack(T, mant, Tref, S.wt() + 16);
     }
     if (tid == 0) { s_cnt = 0; s_L0 = -INFINITY; }
     __syncthreads();
-    const bool generic = *bad != 0;
     const uint32_t KK = K < n_prev ? K : n_prev;
-    if (!generic) {
-        for (uint32_t e = tid; e < n_prev; e += B) {
-            const unsigned long long ke = S.k_mant()[e];
-            uint32_t rank = 0;
-#pragma unroll 4
-            for (uint32_t f = 0; f < n_prev; f++) {
-                const unsigned long long kf = S.k_mant()[f];
-                rank += (kf > ke || (kf == ke && f < e)) ? 1u : 0u;
-            }
-            if (rank < KK) out_id[rank] = S.p_id()[e];
-            S.scan()[e] = rank;  // remember for the ratio filter
-            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m()[e] + S.p_i()[e] + S.p_d()[e], S.p_ex()[e]));
-        }
-    } else {
-        // (a row mixing packed and unpacked keys cannot be ranked by k_mant alone: recompute the mantissas)
-        for (uint32_t e = tid; e < n_prev; e += B) { int T; unsigned long long mant; sp_key(S, e, &T, &mant); S.k_mant()[e] = mant; }
-        __syncthreads();
-        for (uint32_t e = tid; e < n_prev; e += B) {
-            int T = S.k_T()[e]; unsigned long long mt = S.k_mant()[e];
-            uint32_t rank = 0;
-            for (uint32_t f = 0; f < n_prev; f++) {
-                int Tf = S.k_T()[f]; unsigned long long mf = S.k_mant()[f];
-                bool gt = (Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)));
-                rank += gt ? 1u : 0u;
-            }
-            if (rank < KK) out_id[rank] = S.p_id()[e];
-            S.scan()[e] = rank;
-            if (by_ratio && rank == 0) s_L0 = xlog(xf(S.p_m()[e] + S.p_i()[e] + S.p_d()[e], S.p_ex()[e]));
-        }
-    }
-    __syncthreads();
-    if (tid == 0) *bad = 0;
+    sp_rank(S, n_prev, KK, S.p_id(), out_id);
     if (!by_ratio) return (int)KK;
+    for (uint32_t e = tid; e < n_prev; e += B)
+        if (S.scan()[e] == 0) s_L0 = xlog(xf(S.p_m()[e] + S.p_i()[e] + S.p_d()[e], S.p_ex()[e]));
+    __syncthreads();
     for (uint32_t e = tid; e < n_prev; e += B) {
         if (S.scan()[e] < KK) {
             double L = xlog(xf(S.p_m()[e] + S.p_i()[e] + S.p_d()[e], S.p_ex()[e]));
@@ -418,22 +422,16 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             if (fr.n_ent > cap) { if (tid == 0) s_fail = SJ_NEED_BIG; }
             else {
                 // stage into the *current* arrays (not yet in use) and rank there
+                const int Tref = fr.n_ent ? fex[0] : 0;
                 for (uint32_t e = tid; e < fr.n_ent; e += B) {
-                    double v = fm[e] + fi[e] + fd[e];
-                    if (v == 0.0) { S.k_T()[e] = XF_ZERO_E; S.k_mant()[e] = 0; }
-                    else { long long bb = __double_as_longlong(v); S.k_T()[e] = fex[e] + (int)((bb >> 52) & 0x7ff) - 1023; S.k_mant()[e] = (unsigned long long)bb & 0xfffffffffffffull; }
+                    const double v = fm[e] + fi[e] + fd[e];
+                    int T = XF_ZERO_E; unsigned long long mant = 0;
+                    if (v != 0.0) { const long long bb = __double_as_longlong(v); T = fex[e] + (int)((bb >> 52) & 0x7ff) - 1023; mant = (unsigned long long)bb & 0xfffffffffffffull; }
+                    S.k_T()[e] = T; S.k_mant()[e] = sp_pack(T, mant, Tref, S.wt() + 16);
                     S.c_id()[e] = fid[e];
                 }
                 __syncthreads();
-                for (uint32_t e = tid; e < fr.n_ent; e += B) {
-                    int T = S.k_T()[e]; unsigned long long mt = S.k_mant()[e];
-                    uint32_t rank = 0;
-                    for (uint32_t f = 0; f < fr.n_ent; f++) {
-                        int Tf = S.k_T()[f]; unsigned long long mf = S.k_mant()[f];
-                        rank += ((Tf > T) || (Tf == T && (mf > mt || (mf == mt && f < e)))) ? 1u : 0u;
-                    }
-                    if (rank < fr.n_mi) S.top_id()[rank] = S.c_id()[e];
-                }
+                sp_rank(S, fr.n_ent, fr.n_mi, S.c_id(), S.top_id());
                 n_top = (int)fr.n_mi;
             }
         }
