@@ -281,6 +281,23 @@ extern "C" int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables*
     CUDA_TRY(cudaMemcpy(freqs, b_f.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
     return DBGPHMM_OK;
 }
+extern "C" int dbgphmm_output_edge_and_init_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* edge_freqs,
+                                                  double* init_freqs) {
+    ST_TRY(check_pair(m, fwd, bwd));
+    if (!edge_freqs || !init_freqs) { dbg_set_error("to_edge_and_init_freqs: null output"); return DBGPHMM_ERR_INVALID; }
+    if (fwd->bases != bwd->bases) { dbg_set_error("to_edge_and_init_freqs: the two tables come from different reads (freq.rs:281-282)"); return DBGPHMM_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    DevBuf b_e, b_i;
+    ST_TRY(b_e.alloc(sizeof(double) * std::max<uint32_t>(m->E, 1))); ST_TRY(b_i.alloc(sizeof(double) * m->N));
+    CUDA_TRY(cudaMemsetAsync(b_e.p, 0, sizeof(double) * std::max<uint32_t>(m->E, 1), m->stream));
+    CUDA_TRY(cudaMemsetAsync(b_i.p, 0, sizeof(double) * m->N, m->stream));
+    std::vector<HJob> jobs(1);
+    jobs[0] = HJob{0, 0, 0, (uint32_t)fwd->desc.size(), 0};
+    ST_TRY(run_products_edge_freqs(m, jobs, fwd->store, bwd->store, fwd->d_bases, b_e.as<double>(), b_i.as<double>()));
+    if (m->E) CUDA_TRY(cudaMemcpy(edge_freqs, b_e.p, sizeof(double) * m->E, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(init_freqs, b_i.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
+    return DBGPHMM_OK;
+}
 extern "C" int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, int by_ratio, uint32_t n_active,
                                       double ratio, dbgphmm_mappings** out) {
     ST_TRY(check_pair(m, fwd, bwd));

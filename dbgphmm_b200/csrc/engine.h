@@ -122,6 +122,8 @@ int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const
 int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir);
 // sum over rows of F (x) B / P into d_freqs (device, ORIGINAL node order, added to); status ZERO_PROB if some P == 0
 int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, double* d_freqs);
+int run_products_edge_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, const uint8_t* d_bases,
+                            double* d_edge, double* d_init);
 // per-base top nodes of the emit probabilities (hint.rs:124-142) appended to `out` (host Mappings, ORIGINAL ids)
 int run_products_mapping(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, int by_ratio,
                          uint32_t n_active, double ratio, dbgphmm_mappings* out);

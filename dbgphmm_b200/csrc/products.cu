@@ -78,6 +78,108 @@ __global__ void k_prod_rows_freq(ProdCtx C, double* __restrict__ freq, int* __re
     }
 }
 
+// ---- edge and init frequencies (PHMMOutput::to_edge_and_init_freqs, freq.rs:276-298 over to_trans_and_init_probs :332-389)
+// Merged index t = 0..n (one CTA each): F = forward merged(t) (t == 0: f_init), B2 = backward merged(t + 1) (used when t < n),
+// B1 = backward merged(t).  Per edge (k -> l):
+//   to Match:  a_kl e_l(x[t]) B2.m[l] (p_MM F.m[k] + p_IM F.i[k] + p_DM F.d[k]) / P        (t < n)
+//   to Del:    a_kl           B1.d[l] (p_MD F.m[k] + p_ID F.i[k] + p_DD F.d[k]) / P
+// and per node v the Begin -> v transitions with (F.mb, F.ib) and init_v in place of (F.m, F.i) and a_kl.  The two kinds of terms
+// are accumulated separately (the reference sums the six terms of one (t, e) in log space first; the difference is rounding).
+// Each pair of rows is walked from its sparser side: entries of a sparse backward row and their parents, else entries of the
+// forward row (sparse, or all N nodes) and their children.
+struct EdgeCtx {
+    const uint32_t *par_off, *par_node, *par_eid, *chi_off, *chi_node, *chi_eid;
+    const uint8_t* emission;
+    const double *init, *trans;
+    const uint8_t* bases;      // the read of job j starts at base_off[j]
+    const uint64_t* base_off;
+    LinParams lp;
+};
+__device__ __forceinline__ void edge_add(double* acc, double v, int e, const XF& P) {
+    if (v > 0.0) { const double w = (v / P.v) * pow2i(e - P.e); if (w > 0.0) atomicAdd(acc, w); }
+}
+// one (forward row, backward row) pair ; to_m selects the Match terms (backward m, emission) or the Del terms (backward d)
+__device__ void edge_pair(const ProdCtx& C, const EdgeCtx& G, const RowView& F, bool f_is_init, XF fmb, XF fib, const RowView& B, bool to_m, uint8_t x,
+                          const XF& P, const uint32_t* f_ids, const uint32_t* b_ids, double* edge, double* init) {
+    const LinParams& lp = G.lp;
+    const double cm = to_m ? lp.p_MM : lp.p_MD, ci = to_m ? lp.p_IM : lp.p_ID, cd = to_m ? lp.p_DM : lp.p_DD;
+    auto bval = [&](uint32_t l, double* v, int* e) {   // backward factor of node l
+        double m, i, d; int ex;
+        row_at(B, b_ids, l, C.p_end, &m, &i, &d, &ex);
+        *v = to_m ? m * (G.emission[l] == x ? lp.p_match : lp.p_mismatch) : d; *e = ex;
+    };
+    // ---- Begin -> v
+    {
+        const XF bsc = xadd(xmul(fmb, cm), xmul(fib, ci));
+        if (bsc.v != 0.0) {
+            if (B.kind == ROW_SPARSE) {
+                for (uint32_t q = threadIdx.x; q < B.n_ent; q += blockDim.x) {
+                    const uint32_t v = B.id[q];
+                    const double b = to_m ? B.m[q] * (G.emission[v] == x ? lp.p_match : lp.p_mismatch) : B.d[q];
+                    edge_add(&init[C.orig_of[v]], bsc.v * G.init[v] * b, bsc.e + B.ex[q], P);
+                }
+            } else {
+                for (uint32_t v = threadIdx.x; v < C.N; v += blockDim.x) {
+                    double b; int be; bval(v, &b, &be);
+                    edge_add(&init[C.orig_of[v]], bsc.v * G.init[v] * b, bsc.e + be, P);
+                }
+            }
+        }
+    }
+    if (f_is_init) return;   // f_init has m = i = d = 0
+    // ---- k -> l
+    if (B.kind == ROW_SPARSE) {
+        for (uint32_t q = threadIdx.x; q < B.n_ent; q += blockDim.x) {
+            const uint32_t l = B.id[q];
+            const double b = to_m ? B.m[q] * (G.emission[l] == x ? lp.p_match : lp.p_mismatch) : B.d[q];
+            if (b == 0.0) continue;
+            for (uint32_t a = G.par_off[l]; a < G.par_off[l + 1]; a++) {
+                double m, i, d; int fe;
+                row_at(F, f_ids, G.par_node[a], 0.0, &m, &i, &d, &fe);
+                edge_add(&edge[G.par_eid[a]], G.trans[G.par_eid[a]] * b * (cm * m + ci * i + cd * d), fe + B.ex[q], P);
+            }
+        }
+    } else {
+        const uint32_t nf = F.kind == ROW_SPARSE ? F.n_ent : C.N;
+        for (uint32_t q = threadIdx.x; q < nf; q += blockDim.x) {
+            const uint32_t k = F.kind == ROW_SPARSE ? F.id[q] : q;
+            const double f = cm * F.m[q] + ci * F.i[q] + cd * F.d[q];
+            if (f == 0.0) continue;
+            for (uint32_t a = G.chi_off[k]; a < G.chi_off[k + 1]; a++) {
+                double b; int be; bval(G.chi_node[a], &b, &be);
+                edge_add(&edge[G.chi_eid[a]], G.trans[G.chi_eid[a]] * b * f, F.ex[q] + be, P);
+            }
+        }
+    }
+}
+__global__ void k_prod_edge_freq(ProdCtx C, EdgeCtx G, double* __restrict__ edge, double* __restrict__ init, int* __restrict__ err) {
+    const uint32_t j = blockIdx.y, t = blockIdx.x, n = C.len[j];
+    if (t > n) return;
+    const XF P = C.P[j];
+    if (P.v == 0.0) { if (threadIdx.x == 0) *err = 1; return; }
+    RowDesc fr, b1, b2;
+    const bool f_is_init = t == 0;
+    if (f_is_init) { fr.kind = ROW_SPARSE; fr.n_ent = 0; fr.n_mi = 0; fr.n_d = 0; fr.off = 0; fr.mb = xf(1.0, 0); fr.ib = xf_zero(); }
+    else fr = C.fdesc[C.fdesc0[j] + t - 1];
+    auto brow = [&](uint32_t r) { RowDesc d; if (r >= n) { d.kind = 3; d.n_ent = 0; d.n_mi = 0; d.n_d = 0; d.off = 0; } else d = C.bdesc[C.bdesc0[j] + r]; return d; };
+    b1 = brow(t); b2 = brow(t + 1);
+    if ((fr.kind == ROW_DENSE && !C.f_dense_ok) || ((b1.kind == ROW_DENSE || b2.kind == ROW_DENSE) && !C.b_dense_ok)) { if (threadIdx.x == 0) *err = 2; return; }
+    const RowView F = view_row(fr, C.farena, C.fpool, C.fslab_bytes, C.fNp);
+    const RowView B1 = view_row(b1, C.barena, C.bpool, C.bslab_bytes, C.bNp);
+    const RowView B2 = view_row(b2, C.barena, C.bpool, C.bslab_bytes, C.bNp);
+    __shared__ uint32_t f_ids[PROD_MAXE], b_ids[PROD_MAXE];
+    if (F.kind == ROW_SPARSE) for (uint32_t e = threadIdx.x; e < F.n_ent && e < PROD_MAXE; e += blockDim.x) f_ids[e] = F.id[e];
+    if (t < n) {
+        if (B2.kind == ROW_SPARSE) for (uint32_t e = threadIdx.x; e < B2.n_ent && e < PROD_MAXE; e += blockDim.x) b_ids[e] = B2.id[e];
+        __syncthreads();
+        edge_pair(C, G, F, f_is_init, fr.mb, fr.ib, B2, true, G.bases[G.base_off[j] + t], P, f_ids, b_ids, edge, init);
+        __syncthreads();
+    }
+    if (B1.kind == ROW_SPARSE) for (uint32_t e = threadIdx.x; e < B1.n_ent && e < PROD_MAXE; e += blockDim.x) b_ids[e] = B1.id[e];
+    __syncthreads();
+    edge_pair(C, G, F, f_is_init, fr.mb, fr.ib, B1, false, 0, P, f_ids, b_ids, edge, init);
+}
+
 struct DensePair { uint64_t fslab; uint64_t bslab; int b_init; uint32_t job; };
 __global__ void k_prod_dense_freq(ProdCtx C, const DensePair* __restrict__ pairs, double* __restrict__ freq, int* __restrict__ err) {
     const DensePair pr = pairs[blockIdx.y];
@@ -306,6 +408,34 @@ int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const Ro
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     if (err) { dbg_set_error("P(read) == 0: emit probabilities are NaN in the reference (table.rs:500-505)"); return DBGPHMM_ERR_ZERO_PROB; }
+    return DBGPHMM_OK;
+}
+
+// d_edge[E] (original EdgeIndex order) and d_init[N] (original node order) are accumulated into.  Both directions must have kept
+// all their rows (the store strategy).
+int run_products_edge_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, const uint8_t* d_bases,
+                            double* d_edge, double* d_init) {
+    cudaStream_t st = m->stream;
+    EvTimer tm(st, &g_times.product_ms);
+    const uint32_t J = (uint32_t)jobs.size();
+    if (J == 0) return DBGPHMM_OK;
+    ProdBufs pb; ProdCtx C;
+    ST_TRY(make_ctx(m, F, B, pb, &C));
+    std::vector<uint64_t> boff(J);
+    uint32_t maxlen = 0;
+    for (uint32_t j = 0; j < J; j++) { boff[j] = jobs[j].base_off; maxlen = std::max(maxlen, F.len[j]); }
+    DevBuf b_boff;
+    ST_TRY(dev_upload(b_boff, boff, st));
+    EdgeCtx G{m->d_par_off, m->d_par_node, m->d_par_eid, m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_emission,
+              m->d_init + (size_t)jobs[0].x * m->N, m->d_trans + (size_t)jobs[0].x * m->E, d_bases, b_boff.as<uint64_t>(), m->lin};
+    dim3 g(maxlen + 1, J);
+    k_prod_edge_freq<<<g, 128, 0, st>>>(C, G, d_edge, d_init, pb.err.as<int>()); COUNT_LAUNCH();
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, pb.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    if (err == 1) { dbg_set_error("P(read) == 0: transition probabilities are NaN in the reference (freq.rs:346)"); return DBGPHMM_ERR_ZERO_PROB; }
+    if (err) { dbg_set_error("edge frequencies need the stored rows of both directions"); return DBGPHMM_ERR_INVALID; }
     return DBGPHMM_OK;
 }
 

@@ -106,6 +106,16 @@ def mock_linear():
     return genome_graph_to_seq_graph([(b"ATTCGATCGT", 1)])
 
 
+def mock_crossing(has_edge_copy_number):
+    """graph/mocks.rs:44-62 : a(x2), b(x2) -> c(x2), d(x2) crossing; sequences as asserted in mocks.rs:78-85."""
+    nodes = [(b"TGCTCTGGCG", 2), (b"ATTAGGAGCA", 2), (b"GCTGATAGGG", 2), (b"CGAAGATGAG", 2)]
+    if has_edge_copy_number:
+        edges = [(0, 2, 2), (1, 2, 0), (0, 3, 0), (1, 3, 2)]
+    else:
+        edges = [(0, 2, None), (1, 2, None), (0, 3, None), (1, 3, None)]
+    return genome_graph_to_seq_graph(nodes, edges)
+
+
 def multidbg_to_seq_graph(full_is_terminal, full_edges):
     """MultiDbg::to_seq_graph -> to_node_centric_graph(add_terminal=false)  (multi_dbg.rs:1370-1390,1551-1604).
 

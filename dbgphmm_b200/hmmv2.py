@@ -46,7 +46,7 @@ SYMBOLS = [
     "dbgphmm_mappings_sizes", "dbgphmm_mappings_export", "dbgphmm_mappings_to_node_freqs",
     "dbgphmm_forward", "dbgphmm_backward", "dbgphmm_tables_destroy", "dbgphmm_tables_len", "dbgphmm_tables_full_prob",
     "dbgphmm_tables_row_info", "dbgphmm_tables_row_export", "dbgphmm_tables_row_top_nodes",
-    "dbgphmm_output_node_freqs", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
+    "dbgphmm_output_node_freqs", "dbgphmm_output_edge_and_init_freqs", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
     "dbgphmm_run_node_freqs_dev", "dbgphmm_generate_mappings", "dbgphmm_launch_count", "dbgphmm_last_timing",
     "dbgphmm_reads_to_device", "dbgphmm_last_dense_kernel",
 ]
@@ -94,6 +94,7 @@ def lib():
     L.dbgphmm_tables_row_export.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.dbgphmm_tables_row_top_nodes.argtypes = [vp, i64, ci, u32, dbl, vp, C.POINTER(u32)]
     L.dbgphmm_output_node_freqs.argtypes = [vp, vp, vp, vp]
+    L.dbgphmm_output_edge_and_init_freqs.argtypes = [vp, vp, vp, vp, vp]
     L.dbgphmm_output_mapping.argtypes = [vp, vp, vp, ci, u32, dbl, C.POINTER(vp)]
     L.dbgphmm_to_full_prob_reads.argtypes = [vp, vp, vp, ci, vp, vp]
     L.dbgphmm_run_node_freqs.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
@@ -338,6 +339,17 @@ class PHMMOutput:
         f = np.empty(self._model.n_nodes)
         _check(lib().dbgphmm_output_node_freqs(self._model._h, self.forward._h, self.backward._h, _p(f)))
         return f
+
+    def to_edge_and_init_freqs(self):
+        """PHMMOutput::to_edge_and_init_freqs (freq.rs:276-298): (edge_freqs[n_edges] in EdgeIndex order, init_freqs[n_nodes]).
+        The reference takes (phmm, emissions) again; the tables here remember both."""
+        ef = np.empty(len(self._model.src)); nf = np.empty(self._model.n_nodes)
+        _check(lib().dbgphmm_output_edge_and_init_freqs(self._model._h, self.forward._h, self.backward._h, _p(ef), _p(nf)))
+        return ef, nf
+
+    def to_edge_freqs(self):
+        """freq.rs:302-309."""
+        return self.to_edge_and_init_freqs()[0]
 
     def _mapping(self, by_ratio, n_active, ratio):
         h = C.c_void_p()

@@ -136,6 +136,10 @@ int dbgphmm_tables_row_top_nodes(const dbgphmm_tables* t, int64_t row, int by_ra
 /* ---- PHMMOutput of one read (table.rs:450-517, freq.rs:198-255, hint.rs:120-142) ---------------------- */
 /* to_node_freqs (freq.rs:245-255): freqs[n_nodes] */
 int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* freqs);
+/* to_edge_and_init_freqs (freq.rs:276-298, over to_trans_and_init_probs :332-389): edge_freqs[n_edges] in EdgeIndex order,
+ * init_freqs[n_nodes] (the Begin -> node transitions).  to_edge_freqs (freq.rs:302-309) is the first output. */
+int dbgphmm_output_edge_and_init_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* edge_freqs,
+                                       double* init_freqs);
 /* to_mapping(n_active) (by_ratio = 0) / to_mapping_by_score_ratio(ratio): a 1-read Mappings handle */
 int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, int by_ratio,
                            uint32_t n_active, double ratio, dbgphmm_mappings** out);

@@ -749,6 +749,50 @@ int orc_output_node_freqs(const Tables* f, const Tables* b, double* freqs) {
     return 0;
     ORC_CATCH(1)
 }
+// PHMMOutput::to_edge_and_init_freqs (freq.rs:276-298) over to_trans_and_init_probs (freq.rs:332-389) for one read:
+// edge[e] = sum_{i=0..n} (mm + md + im + id + dm + dd of edge e at i).to_value(), init[v] likewise for the Begin -> v transitions.
+int orc_output_edge_init_freqs(const Model* mdl, const Tables* f, const Tables* b, const uint8_t* x, uint64_t n, double* edge, double* init) {
+    ORC_TRY
+    const Params& pa = mdl->param;
+    const size_t E = mdl->esrc.size(), N = mdl->n_nodes;
+    if (n != f->n_emissions() || n != b->n_emissions()) throw std::runtime_error("emissions / tables length mismatch (freq.rs:281-282)");
+    std::fill(edge, edge + E, 0.0); std::fill(init, init + N, 0.0);
+    const double p = f->full_prob();
+    for (size_t i = 0; i <= n; i++) {
+        const Table& fi0 = f->table_merged(i);
+        const Table& bi2 = b->table_merged(i + 1);
+        const Table& bi1 = b->table_merged(i);
+        for (size_t e = 0; e < E; e++) {
+            const uint32_t k = mdl->esrc[e], l = mdl->edst[e];
+            const double pt = mdl->etrans[e];
+            double mm = NEG_INF, im = NEG_INF, dm = NEG_INF;   // TransProb::zero()
+            if (i < n) {
+                const double pe = mdl->p_match_emit(l, x[i]);
+                mm = pdiv(pmul(pmul(pmul(pmul(fi0.m.get(k), pt), pa.p_MM), pe), bi2.m.get(l)), p);
+                im = pdiv(pmul(pmul(pmul(pmul(fi0.i.get(k), pt), pa.p_IM), pe), bi2.m.get(l)), p);
+                dm = pdiv(pmul(pmul(pmul(pmul(fi0.d.get(k), pt), pa.p_DM), pe), bi2.m.get(l)), p);
+            }
+            const double md = pdiv(pmul(pmul(pmul(fi0.m.get(k), pt), pa.p_MD), bi1.d.get(l)), p);
+            const double id = pdiv(pmul(pmul(pmul(fi0.i.get(k), pt), pa.p_ID), bi1.d.get(l)), p);
+            const double dd = pdiv(pmul(pmul(pmul(fi0.d.get(k), pt), pa.p_DD), bi1.d.get(l)), p);
+            edge[e] += std::exp(padd(padd(padd(padd(padd(mm, md), im), id), dm), dd));   // trans_table.rs:40-42
+        }
+        for (size_t v = 0; v < N; v++) {
+            const double pi_ = mdl->init[v];
+            double mm = NEG_INF, im = NEG_INF;
+            if (i < n) {
+                const double pe = mdl->p_match_emit((uint32_t)v, x[i]);
+                mm = pdiv(pmul(pmul(pmul(pmul(fi0.mb, pi_), pa.p_MM), pe), bi2.m.get((uint32_t)v)), p);
+                im = pdiv(pmul(pmul(pmul(pmul(fi0.ib, pi_), pa.p_IM), pe), bi2.m.get((uint32_t)v)), p);
+            }
+            const double md = pdiv(pmul(pmul(pmul(fi0.mb, pi_), pa.p_MD), bi1.d.get((uint32_t)v)), p);
+            const double id = pdiv(pmul(pmul(pmul(fi0.ib, pi_), pa.p_ID), bi1.d.get((uint32_t)v)), p);
+            init[v] += std::exp(padd(padd(padd(padd(padd(mm, md), im), id), NEG_INF), NEG_INF));
+        }
+    }
+    return 0;
+    ORC_CATCH(1)
+}
 // PHMMOutput::to_mapping / to_mapping_by_score_ratio (hint.rs:124-142) for one read.
 // Two-call protocol: row_counts[n] always written; nodes/probs written if non-null.
 int orc_output_mapping(const Tables* f, const Tables* b, int by_ratio, uint64_t n_active, double ratio,

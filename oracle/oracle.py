@@ -65,6 +65,7 @@ def lib():
         L.orc_tables_row_top_nodes.argtypes = [vp, i64, cint, u64, dbl, vp]; L.orc_tables_row_top_nodes.restype = u64
         L.orc_output_node_freqs.argtypes = [vp, vp, vp]; L.orc_output_node_freqs.restype = cint
         L.orc_output_mapping.argtypes = [vp, vp, cint, u64, dbl, vp, vp, vp]; L.orc_output_mapping.restype = cint
+        L.orc_output_edge_init_freqs.argtypes = [vp, vp, vp, vp, u64, vp, vp]; L.orc_output_edge_init_freqs.restype = cint
         L.orc_full_prob_reads.argtypes = [vp, u64, vp, vp, vp, vp, vp, cint, vp, cint]; L.orc_full_prob_reads.restype = dbl
         L.orc_run_node_freqs.argtypes = [vp, u64, vp, vp, cint, cint, vp, vp, vp, vp, vp, vp, cint]; L.orc_run_node_freqs.restype = cint
         L.orc_count_cells.argtypes = [vp, vp, u64, cint, cint, cint]; L.orc_count_cells.restype = u64
@@ -403,6 +404,17 @@ class PHMMOutput:
         if lib().orc_output_node_freqs(self.forward._h, self.backward._h, _p(fr)):
             raise RuntimeError(_err())
         return fr
+
+    def to_edge_and_init_freqs(self, phmm, emissions):
+        """freq.rs:276-298: (edge_freqs[E], init_freqs[N]) of one read."""
+        x = _bases(emissions)
+        ef = np.empty(len(phmm.src)); nf = np.empty(phmm.n_nodes)
+        if lib().orc_output_edge_init_freqs(phmm._h, self.forward._h, self.backward._h, _p(x), len(x), _p(ef), _p(nf)):
+            raise RuntimeError(_err())
+        return ef, nf
+
+    def to_edge_freqs(self, phmm, emissions):
+        return self.to_edge_and_init_freqs(phmm, emissions)[0]
 
     def _mapping(self, by_ratio, n_active, ratio):
         n = len(self.forward)

@@ -301,3 +301,46 @@ def test_read_shorter_than_warmup_and_single_base(H):
         gf, of = g.forward_sparse(read, True), o.forward_sparse(read, True)
         assert_tables_match(gf, of, sg.n_nodes, "fwd ratio")
         assert_tables_match(g.backward_by_forward(read, gf), o.backward_by_forward(read, of), sg.n_nodes, "bwd by fwd")
+
+
+# ---------------------------------------------------------------- edge / init frequencies (freq.rs:276-389)
+def test_edge_freqs_reference_kat_on_mock_crossing(H):
+    """graph/seq_graph.rs:440-504 asserted on the GPU results, plus the oracle on every edge."""
+    ra, rb = b"ATTAGGAGCA", b"ATTAGGAGCAGCTGATAGGG"
+    for flag in (False, True):
+        sg = graphs.mock_crossing(flag)
+        g, o = both(sg, oracle_params(0.01))
+        for r in (ra, rb):
+            gef, gnf = g.run(r).to_edge_and_init_freqs()
+            oef, onf = o.run(r).to_edge_and_init_freqs(o, r)
+            assert np.allclose(gef, oef, rtol=REL_TOL, atol=1e-14), np.abs(gef - oef).max()
+            assert np.allclose(gnf, onf, rtol=REL_TOL, atol=1e-14)
+        ef = g.run(rb).to_edge_freqs()
+        if not flag:
+            assert ef[36] < 0.0001 and ef[37] > 0.9 and ef[38] < 0.0001 and ef[39] < 0.0001
+        else:
+            assert ef[37] == 0.0 and ef[38] == 0.0
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse", "sparse_adaptive", "with_mapping"])
+def test_edge_and_init_freqs_all_row_kinds(H, mode):
+    """dense x dense, dense x sparse, sparse x sparse and b_init pairs of rows, against the oracle."""
+    w = _dbg_case(11, n_reads=3, k=12, p_err=0.004)
+    par = oracle_params(0.002, n_warmup=8, warmup_threshold=30)
+    g, o = both(w.graph, par, "non_zero")
+    for read in w.reads[:3]:
+        read = read[:60]
+        if mode == "dense":
+            go, oo = g.run(read), o.run(read)
+        elif mode == "sparse":
+            go, oo = g.run_sparse(read), o.run_sparse(read)
+        elif mode == "sparse_adaptive":
+            go, oo = g.run_sparse_adaptive(read, False), o.run_sparse_adaptive(read, False)
+        else:
+            om = o.generate_mappings(O.Reads([read]), None, False)
+            gm = H.Mappings(om.read_off, om.row_off, om.nodes, om.probs)
+            go, oo = g.run_with_mapping(read, gm, 0), o.run_with_mapping(read, om[0])
+        gef, gnf = go.to_edge_and_init_freqs()
+        oef, onf = oo.to_edge_and_init_freqs(o, read)
+        assert np.allclose(gef, oef, rtol=REL_TOL, atol=1e-13), (mode, np.abs(gef - oef).max())
+        assert np.allclose(gnf, onf, rtol=REL_TOL, atol=1e-13), (mode, np.abs(gnf - onf).max())

@@ -140,3 +140,30 @@ def test_seqgraph_copy_numbers_to_probs_match_oracle():
                 assert np.array_equal(np.isneginf(x), np.isneginf(y))
                 fin = ~np.isneginf(y)
                 assert np.allclose(x[fin], y[fin], rtol=0, atol=1e-15)
+
+
+def test_seq_graph_edge_copy_num_kat_edge_freqs():
+    """graph/seq_graph.rs:440-504 (seq_graph_edge_copy_num): full probabilities on mock_crossing with and without edge copy
+    numbers and PHMMOutput::to_edge_freqs (freq.rs:276-315) on the junction edges 36..39."""
+    from dbgphmm_b200 import graphs
+    ra, rb = b"ATTAGGAGCA", b"ATTAGGAGCAGCTGATAGGG"
+    outs = {}
+    for flag in (False, True):
+        sg = graphs.mock_crossing(flag)
+        li, lt = sg.to_probs("normal")
+        m = O.PHMMModel(sg.src, sg.dst, sg.base, li, lt, O.params_uniform(0.01))   # PHMMParams::default() (params.rs:126-128)
+        outs[flag] = (m, m.run(ra), m.run(rb))
+    (g1, o1a, o1b), (g2, o2a, o2b) = outs[False], outs[True]
+    for o in (o1a, o1b, o2a, o2b):
+        assert abs(o.to_full_prob_forward() - o.to_full_prob_backward()) < 0.1
+    assert abs(o1a.to_full_prob_forward() - o2a.to_full_prob_forward()) < 0.1
+    assert o1b.to_full_prob_forward() > -17.0
+    assert o2b.to_full_prob_forward() < -39.0
+    ef1 = o1b.to_edge_freqs(g1, rb)
+    assert len(ef1) == 40
+    assert ef1[36] < 0.0001 and ef1[37] > 0.9 and ef1[38] < 0.0001 and ef1[39] < 0.0001
+    ef2 = o2b.to_edge_freqs(g2, rb)
+    assert ef2[37] == 0.0 and ef2[38] == 0.0
+    # every path leaves Begin exactly once (up to the Begin -> Ins mass)
+    _, nf = o1b.to_edge_and_init_freqs(g1, rb)
+    assert abs(nf.sum() - 1.0) < 1e-2
