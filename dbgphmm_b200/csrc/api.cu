@@ -298,6 +298,26 @@ extern "C" int dbgphmm_output_edge_and_init_freqs(dbgphmm_model* m, const dbgphm
     CUDA_TRY(cudaMemcpy(init_freqs, b_i.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
     return DBGPHMM_OK;
 }
+// q_score_exact (q.rs:66-96): init = sum_v A(Begin, v) ln p_init(v), trans = sum_(v,w) A(v, w) ln p_trans(v, w) over emittable nodes
+// (emission != 'n'); the prior term is always zero.  Host-side: two dot products over the model's parameters of candidate x.
+extern "C" int dbgphmm_q_score_exact(const dbgphmm_model* m, uint32_t x, const double* edge_freqs, const double* init_freqs, double out[3]) {
+    if (!m || !edge_freqs || !init_freqs || !out) { dbg_set_error("q_score_exact: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::vector<double> li(m->N), lt(std::max<uint32_t>(m->E, 1));
+    ST_TRY(dbgphmm_model_get_probs(m, x, li.data(), lt.data()));
+    double init = 0.0, trans = 0.0;
+    for (uint32_t v = 0; v < m->N; v++) {   // original node ids
+        if (m->emission[m->pos_of[v]] == 'n') continue;
+        if (!std::isfinite(li[v])) { dbg_set_error("q_score_exact: init_prob is not finite (q.rs:79 asserts)"); return DBGPHMM_ERR_INVALID; }
+        init += init_freqs[v] * li[v];
+    }
+    for (uint32_t e = 0; e < m->E; e++) {
+        if (m->emission[m->pos_of[m->e_src[e]]] == 'n' || m->emission[m->pos_of[m->e_dst[e]]] == 'n') continue;
+        if (!std::isfinite(lt[e])) { dbg_set_error("q_score_exact: trans_prob is not finite (q.rs:88 asserts)"); return DBGPHMM_ERR_INVALID; }
+        trans += edge_freqs[e] * lt[e];
+    }
+    out[0] = init; out[1] = trans; out[2] = 0.0;
+    return DBGPHMM_OK;
+}
 extern "C" int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, int by_ratio, uint32_t n_active,
                                       double ratio, dbgphmm_mappings** out) {
     ST_TRY(check_pair(m, fwd, bwd));
@@ -374,6 +394,36 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
         }
     std::vector<double> per(all.size());
     int st = DBGPHMM_OK;
+    // Mapping-restricted scoring of several candidates: one CTA per (read, 8 candidates) shares the index work of every row
+    // (mapx.cu); groups it cannot take (rows of more than 64 nodes, ...) go through the general path below.
+    std::vector<uint8_t> done(all.size(), 0);
+    if (mappings && X > 1 && !getenv("DBGPHMM_NO_MAPX")) {
+        std::vector<MapxGroup> groups;
+        for (uint64_t r = 0; r < R; r++)
+            for (uint32_t x0 = 0; x0 < X; x0 += 8)
+                groups.push_back(MapxGroup{reads->off[r], (uint32_t)(reads->off[r + 1] - reads->off[r]), mappings->read_off[r], x0, std::min<uint32_t>(8, X - x0),
+                                           (uint32_t)((size_t)x0 * R + r)});
+        std::vector<XF> fin(all.size(), xf_zero());
+        std::vector<uint8_t> failed;
+        st = run_mapx(m, groups, reads->d_bases, dmap, (uint32_t)R, fin.data(), failed, nullptr);
+        if (st != DBGPHMM_OK) { dmap.release(); return st; }
+        for (size_t g = 0; g < groups.size(); g++) {
+            if (failed[g]) continue;
+            for (uint32_t k = 0; k < groups[g].nx; k++) { const size_t idx = groups[g].out0 + (size_t)k * R; per[idx] = xlog(fin[idx]); done[idx] = 1; }
+        }
+        std::vector<HJob> rest; std::vector<uint64_t> rbytes; std::vector<size_t> ridx;
+        for (size_t i = 0; i < all.size(); i++) if (!done[i]) { rest.push_back(all[i]); rbytes.push_back(bytes[i]); ridx.push_back(i); }
+        for (auto& bt : plan_batches(rbytes, m->mem_budget, 1u << 20, sparse_wave_jobs(m, 256))) {
+            std::vector<HJob> jobs(rest.begin() + bt.first, rest.begin() + bt.second);
+            RowStore F;
+            PhaseOpts so; so.keep_rows = false; so.store_sparse = false;
+            st = run_forward(m, jobs, reads->d_bases, kind, so, &dmap, &F);
+            if (st == DBGPHMM_OK) for (size_t i = 0; i < jobs.size(); i++) per[ridx[bt.first + i]] = xlog(F.h_final[i]);
+            F.release();
+            if (st != DBGPHMM_OK) break;
+        }
+        all.clear(); bytes.clear();
+    }
     for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535, sparse_wave_jobs(m, 256))) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         RowStore F;

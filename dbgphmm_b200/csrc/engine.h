@@ -121,6 +121,10 @@ int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const
                           const StepProducts& sp);
 int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir);
 // sum over rows of F (x) B / P into d_freqs (device, ORIGINAL node order, added to); status ZERO_PROB if some P == 0
+// mapx.cu: forward_with_mapping_score_only for groups of candidates X of one read
+struct MapxGroup { uint64_t base_off; uint32_t len; uint64_t map_row0; uint32_t x0, nx, out0; };
+int run_mapx(dbgphmm_model* m, const std::vector<MapxGroup>& groups, const uint8_t* d_bases, const DevMappings& dmap, uint32_t out_stride,
+             XF* h_final, std::vector<uint8_t>& failed, uint64_t* cells_out);
 int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, double* d_freqs);
 int run_products_edge_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, const uint8_t* d_bases,
                             double* d_edge, double* d_init);

@@ -46,7 +46,7 @@ SYMBOLS = [
     "dbgphmm_mappings_sizes", "dbgphmm_mappings_export", "dbgphmm_mappings_to_node_freqs",
     "dbgphmm_forward", "dbgphmm_backward", "dbgphmm_tables_destroy", "dbgphmm_tables_len", "dbgphmm_tables_full_prob",
     "dbgphmm_tables_row_info", "dbgphmm_tables_row_export", "dbgphmm_tables_row_top_nodes",
-    "dbgphmm_output_node_freqs", "dbgphmm_output_edge_and_init_freqs", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
+    "dbgphmm_output_node_freqs", "dbgphmm_output_edge_and_init_freqs", "dbgphmm_q_score_exact", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
     "dbgphmm_run_node_freqs_dev", "dbgphmm_generate_mappings", "dbgphmm_launch_count", "dbgphmm_last_timing",
     "dbgphmm_reads_to_device", "dbgphmm_last_dense_kernel",
 ]
@@ -95,6 +95,7 @@ def lib():
     L.dbgphmm_tables_row_top_nodes.argtypes = [vp, i64, ci, u32, dbl, vp, C.POINTER(u32)]
     L.dbgphmm_output_node_freqs.argtypes = [vp, vp, vp, vp]
     L.dbgphmm_output_edge_and_init_freqs.argtypes = [vp, vp, vp, vp, vp]
+    L.dbgphmm_q_score_exact.argtypes = [vp, u32, vp, vp, vp]
     L.dbgphmm_output_mapping.argtypes = [vp, vp, vp, ci, u32, dbl, C.POINTER(vp)]
     L.dbgphmm_to_full_prob_reads.argtypes = [vp, vp, vp, ci, vp, vp]
     L.dbgphmm_run_node_freqs.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
@@ -468,6 +469,13 @@ class PHMMModel:
 
     def run_with_mapping(self, x, mappings, read_index=0):
         return PHMMOutput(self, self.forward_with_mapping(x, mappings, read_index), self.backward_with_mapping(x, mappings, read_index))
+
+    def q_score_exact(self, edge_freqs, init_freqs, x=0):
+        """q.rs:66-96 -> (init, trans, prior); QScore::total() is their sum."""
+        ef = np.ascontiguousarray(edge_freqs, np.float64); nf = np.ascontiguousarray(init_freqs, np.float64)
+        out = np.zeros(3)
+        _check(lib().dbgphmm_q_score_exact(self._h, x, _p(ef), _p(nf), _p(out)))
+        return tuple(out)
 
     # ---- bulk calls (freq.rs:87-192, hint.rs:193-220)
     def to_full_prob_reads(self, reads, mappings=None, use_max_ratio=True):

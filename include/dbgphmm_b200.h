@@ -140,6 +140,8 @@ int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const
  * init_freqs[n_nodes] (the Begin -> node transitions).  to_edge_freqs (freq.rs:302-309) is the first output. */
 int dbgphmm_output_edge_and_init_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* edge_freqs,
                                        double* init_freqs);
+/* q_score_exact (q.rs:66-96) for candidate x: out = {init, trans, prior (always 0)}; QScore::total = their sum */
+int dbgphmm_q_score_exact(const dbgphmm_model* m, uint32_t x, const double* edge_freqs, const double* init_freqs, double out[3]);
 /* to_mapping(n_active) (by_ratio = 0) / to_mapping_by_score_ratio(ratio): a 1-read Mappings handle */
 int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, int by_ratio,
                            uint32_t n_active, double ratio, dbgphmm_mappings** out);

@@ -339,6 +339,16 @@ class PHMMModel:
     def run_with_mapping(self, x, mapping):
         return PHMMOutput(self.forward_with_mapping(x, mapping), self.backward_with_mapping(x, mapping))
 
+    def q_score_exact(self, edge_freqs, init_freqs):
+        """q.rs:66-96 -> (init, trans, prior) over emittable nodes (emission != 'n')."""
+        emit = self.emission != ord("n")
+        if not (np.isfinite(self.log_init[emit]).all()):
+            raise RuntimeError("init_prob is not finite (q.rs:79 asserts)")
+        keep = emit[self.src] & emit[self.dst]
+        if not np.isfinite(self.log_trans[keep]).all():
+            raise RuntimeError("trans_prob is not finite (q.rs:88 asserts)")
+        return (float((np.asarray(init_freqs)[emit] * self.log_init[emit]).sum()), float((np.asarray(edge_freqs)[keep] * self.log_trans[keep]).sum()), 0.0)
+
     # ---- bulk (freq.rs:175-192, hint.rs:193-220)
     def to_full_prob_reads(self, reads, mappings=None, use_max_ratio=True, n_threads=1):
         per = np.empty(len(reads))

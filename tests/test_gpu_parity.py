@@ -344,3 +344,5 @@ def test_edge_and_init_freqs_all_row_kinds(H, mode):
         oef, onf = oo.to_edge_and_init_freqs(o, read)
         assert np.allclose(gef, oef, rtol=REL_TOL, atol=1e-13), (mode, np.abs(gef - oef).max())
         assert np.allclose(gnf, onf, rtol=REL_TOL, atol=1e-13), (mode, np.abs(gnf - onf).max())
+        gq, oq = g.q_score_exact(gef, gnf), o.q_score_exact(oef, onf)   # q.rs:66-96
+        assert np.allclose(gq, oq, rtol=1e-9, atol=1e-12), (gq, oq)
