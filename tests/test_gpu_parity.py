@@ -346,3 +346,41 @@ def test_edge_and_init_freqs_all_row_kinds(H, mode):
         assert np.allclose(gnf, onf, rtol=REL_TOL, atol=1e-13), (mode, np.abs(gnf - onf).max())
         gq, oq = g.q_score_exact(gef, gnf), o.q_score_exact(oef, onf)   # q.rs:66-96
         assert np.allclose(gq, oq, rtol=1e-9, atol=1e-12), (gq, oq)
+
+
+def test_batched_candidates_wide_and_duplicated_mapping_rows(H, monkeypatch):
+    """Mapping rows the 8-candidates-per-CTA kernel does not take (more than 64 nodes, a duplicated node) fall back to the
+    general sparse kernel: both routes must agree with the oracle and with each other."""
+    w = _dbg_case(13, n_reads=3, k=14, p_err=0.003)
+    sg = w.graph
+    par = oracle_params(0.001, n_warmup=w.k, warmup_threshold=30)
+    g, o = both(sg, par, "non_zero")
+    reads = [r[:80] for r in w.reads]
+    base = o.generate_mappings(O.Reads(reads), None, False)
+    rng = np.random.default_rng(4)
+    read_off, row_off, nodes = [0], [0], []
+    for r in range(len(reads)):
+        for i in range(len(reads[r])):
+            a, b = int(base.row_off[int(base.read_off[r]) + i]), int(base.row_off[int(base.read_off[r]) + i + 1])
+            row = list(base.nodes[a:b])
+            if r == 0 and i % 7 == 3:      # wide rows: 70 - 90 distinct nodes
+                extra = [int(v) for v in rng.permutation(sg.n_nodes)[:90] if int(v) not in row]
+                row = row + extra[:rng.integers(70, 90) - len(row)]
+            if r == 1 and i % 5 == 2:      # a duplicated node (first occurrence wins, active_nodes.rs:15-56 style)
+                row = row + [row[0]]
+            nodes += row; row_off.append(len(nodes))
+        read_off.append(len(row_off) - 1)
+    probs = np.zeros(len(nodes))
+    om = O.Mappings(np.array(read_off, np.uint64), np.array(row_off, np.uint64), np.array(nodes, np.uint32), probs)
+    gm = H.Mappings(om.read_off, om.row_off, om.nodes, om.probs)
+    X = np.stack([sg.node_copy_num, sg.node_copy_num + (rng.random(sg.n_nodes) < 0.05), sg.node_copy_num + 1])
+    g.set_copy_nums_batch(X, "normal")
+    tot, per = g.to_full_prob_reads(H.Reads(reads), gm)
+    monkeypatch.setenv("DBGPHMM_NO_MAPX", "1")
+    tot1, per1 = g.to_full_prob_reads(H.Reads(reads), gm)
+    assert np.allclose(per, per1, rtol=1e-12, atol=0)
+    for x in range(len(X)):
+        li, lt = sg.to_probs("normal", X[x])
+        o.set_probs(li, lt)
+        s, p = o.to_full_prob_reads(O.Reads(reads), om)
+        assert close_log(per[x], p).all(), (x, per[x], p)
