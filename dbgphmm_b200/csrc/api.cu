@@ -413,7 +413,7 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
         }
         std::vector<HJob> rest; std::vector<uint64_t> rbytes; std::vector<size_t> ridx;
         for (size_t i = 0; i < all.size(); i++) if (!done[i]) { rest.push_back(all[i]); rbytes.push_back(bytes[i]); ridx.push_back(i); }
-        for (auto& bt : plan_batches(rbytes, m->mem_budget, 1u << 20, sparse_wave_jobs(m, 256))) {
+        for (auto& bt : plan_batches(rbytes, m->mem_budget, 1u << 20, sparse_wave_jobs(m, sparse_default_cap()))) {
             std::vector<HJob> jobs(rest.begin() + bt.first, rest.begin() + bt.second);
             RowStore F;
             PhaseOpts so; so.keep_rows = false; so.store_sparse = false;
@@ -424,7 +424,7 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
         }
         all.clear(); bytes.clear();
     }
-    for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535, sparse_wave_jobs(m, 256))) {
+    for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535, sparse_wave_jobs(m, sparse_default_cap()))) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         RowStore F;
         PhaseOpts so; so.keep_rows = false; so.store_sparse = false;
@@ -456,7 +456,8 @@ static uint64_t job_bytes_keep(const dbgphmm_model* m, int fk, int bk, uint64_t 
     const uint64_t slab = dense_slab_bytes(m->N), W = m->params.n_warmup;
     uint64_t fd = fk == DBGPHMM_FWD_DENSE ? len : (fk == DBGPHMM_FWD_MAPPING ? 0 : std::min(len, W));
     uint64_t bd = bk == DBGPHMM_BWD_DENSE ? len : (bk == DBGPHMM_BWD_SPARSE ? std::min(len, W) : (bk == DBGPHMM_BWD_BY_FORWARD ? std::min(len, W) + 2 : 0));
-    uint64_t per_row = (uint64_t)m->params.n_active_nodes * 3 * 34 + 256 + 2 * sizeof(RowDesc);
+    const bool ratio = fk == DBGPHMM_FWD_SPARSE_RATIO;
+    const uint64_t per_row = (ratio ? 2048 : (uint64_t)m->params.n_active_nodes * 48 + 256) + 2 * sizeof(RowDesc);   // (arena_estimate, engine.cu)
     return (fd + bd) * slab + 2 * len * per_row + ((uint64_t)1 << 20);
 }
 
@@ -494,10 +495,10 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
     if (const char* e = getenv("DBGPHMM_STRATEGY")) { if (!strcmp(e, "stream")) stream = can_stream; else if (!strcmp(e, "store")) stream = false; }
     if (stream) {
         const uint64_t slab = dense_slab_bytes(m->N);
-        const uint64_t per_row = (uint64_t)m->params.n_active_nodes * 3 * 34 + 256 + 3 * sizeof(RowDesc);
+        const uint64_t per_row = (uint64_t)m->params.n_active_nodes * 48 + 256 + 3 * sizeof(RowDesc);   // (arena_estimate, engine.cu)
         for (uint64_t r = 0; r < R; r++) bytes[r] = 2 * slab + 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20);
     }
-    for (auto& bt : plan_batches(bytes, m->mem_budget, 65535, mode == DBGPHMM_RUN_DENSE ? 0 : sparse_wave_jobs(m, 256))) {
+    for (auto& bt : plan_batches(bytes, m->mem_budget, 65535, mode == DBGPHMM_RUN_DENSE ? 0 : sparse_wave_jobs(m, sparse_default_cap()))) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         HostTrace tr_b("batch");
         RowStore F, B;

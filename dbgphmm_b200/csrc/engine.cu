@@ -154,8 +154,9 @@ static int alloc_arena(SparseArena& a, uint64_t bytes, cudaStream_t st) {
     return DBGPHMM_OK;
 }
 
+#define ST_ARENA_FULL (-100)
 // Run a set of sparse jobs, re-running the ones that overflowed the small shared-memory capacity with the big one.
-static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io, RowStore* store, uint32_t small_cap) {
+static int run_sparse_jobs_once(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io, RowStore* store, uint32_t small_cap) {
     if (sj.empty()) return DBGPHMM_OK;
     cudaStream_t st = m->stream;
     const uint32_t n = (uint32_t)sj.size();
@@ -169,13 +170,28 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
     std::vector<uint32_t> todo(n);
     for (uint32_t i = 0; i < n; i++) todo[i] = i;
     uint32_t caps[3] = {small_cap, 256, 832};
-    if (const char* e = getenv("DBGPHMM_SPARSE_CAP")) { int c0 = atoi(e); if (c0 >= 32 && c0 <= 832) caps[0] = ((uint32_t)c0 + 15u) & ~15u; }
+    // first pass: jobs whose rows outgrow small_cap are carried on by a concurrent rescue launch (sparse.cu) instead of a re-run
+    const uint32_t rescue_cap = sparse_rescue_cap(small_cap);
+    DevBuf b_ctl, b_items, b_hand, b_rows;
+    if (rescue_cap) {
+        ST_TRY(b_ctl.alloc(sizeof(uint32_t) * 4)); ST_TRY(b_items.alloc(sizeof(uint32_t) * n)); ST_TRY(b_hand.alloc(sizeof(SHandoff) * n));
+        ST_TRY(b_rows.alloc((size_t)32 * small_cap * n));
+        CUDA_TRY(cudaMemsetAsync(b_ctl.p, 0, sizeof(uint32_t) * 4, st));
+        CUDA_TRY(cudaMemsetAsync(b_items.p, 0xff, sizeof(uint32_t) * n, st));
+        io.rq_ctl = b_ctl.as<uint32_t>(); io.rq_items = b_items.as<uint32_t>(); io.rq_hand = b_hand.as<SHandoff>(); io.rq_rows = b_rows.as<char>();
+    }
     for (int pass = 0; pass < 3 && !todo.empty(); pass++) {
-        if (pass > 0 && caps[pass] <= caps[pass - 1]) continue;
+        if (pass > 0 && (caps[pass] <= caps[pass - 1] || (pass == 1 && rescue_cap >= caps[1]))) continue;   // (the rescue launch was pass 1)
         std::vector<SJob> cur(todo.size());
         for (size_t i = 0; i < todo.size(); i++) cur[i] = sj[todo[i]];
         CUDA_TRY(cudaMemcpyAsync(b_jobs.p, cur.data(), sizeof(SJob) * cur.size(), cudaMemcpyHostToDevice, st));
-        ST_TRY(sparse_run(m, b_jobs.as<SJob>(), (uint32_t)cur.size(), io, caps[pass]));
+        ST_TRY(sparse_run(m, b_jobs.as<SJob>(), (uint32_t)cur.size(), io, caps[pass], pass == 0 ? rescue_cap : 0));
+        if (pass == 0 && rescue_cap && getenv("DBGPHMM_TRACE")) {
+            uint32_t ctl[4];
+            CUDA_TRY(cudaMemcpyAsync(ctl, b_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            fprintf(stderr, "[dbgphmm] sparse pass 0 (cap %u): %u of %zu jobs carried on by the rescue launch (cap %u)\n", caps[0], ctl[0], cur.size(), rescue_cap);
+        }
         CUDA_TRY(cudaMemcpyAsync(status.data(), io.status, sizeof(int) * cur.size(), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(fin.data(), io.final_scalar, sizeof(XF) * cur.size(), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(cells.data(), io.cells, sizeof(unsigned long long) * cur.size(), cudaMemcpyDeviceToHost, st));
@@ -185,19 +201,55 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
             if (status[i] == SJ_OK) {
                 store->h_final[cur[i].out_idx] = fin[i];
                 store->cells += cells[i];
-            } else if (status[i] == SJ_NEED_BIG && pass < 2) next.push_back(todo[i]);
-            else if (status[i] == SJ_OOM) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
+            } else if (status[i] == SJ_NEED_BIG && pass < 2) {
+                // (on failure the kernel reports where it stopped instead of the cell count: step << 32 | site << 16 | entries)
+                if (next.size() < 8 && getenv("DBGPHMM_TRACE"))
+                    fprintf(stderr, "[dbgphmm]   job %u (dir %d, %u rows) stopped at step %llu, site %llu, %llu entries\n", todo[i], (int)cur[i].dir, cur[i].n_rows,
+                            cells[i] >> 32, (cells[i] >> 16) & 0xffff, cells[i] & 0xffff);
+                next.push_back(todo[i]);
+            }
+            else if (status[i] == SJ_OOM) return ST_ARENA_FULL;
             else { dbg_set_error("a sparse row exceeded MAX_ACTIVE_NODES entries (the reference panics: insufficient capacity)"); return DBGPHMM_ERR_CAPACITY; }
         }
+        if (!next.empty() && getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] sparse pass %d (cap %u): %zu of %zu jobs need a larger capacity\n", pass, caps[pass], next.size(), cur.size());
         todo.swap(next);
+    }
+    if (getenv("DBGPHMM_TRACE") && io.arena_cursor) {
+        unsigned long long cur = 0; uint64_t rows = 0;
+        CUDA_TRY(cudaMemcpy(&cur, io.arena_cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+        for (auto& j : sj) rows += j.n_rows;
+        fprintf(stderr, "[dbgphmm] sparse arena: %.1f MB used of %.1f MB (%.0f B per row over %llu rows)\n", cur / 1e6, io.arena_bytes / 1e6, rows ? (double)cur / rows : 0.0,
+                (unsigned long long)rows);
     }
     return DBGPHMM_OK;
 }
 
-static uint64_t arena_estimate(uint64_t n_rows, uint32_t n_active, bool ratio) {
-    uint64_t per_row = ratio ? 2048 : (uint64_t)n_active * 3 * 34 + 256;
-    uint64_t b = n_rows * per_row + (uint64_t)8 * SPARSE_PAGE_BYTES;
+// Bytes of sparse rows: the arena is sized for typical rows (top-n rows of n_active = 40 hold ~50 entries = ~1.7 KB on the C3
+// workload ; this allows 48 B x n_active + 256) and the phase is repeated once with the bound below if a batch outgrows it.
+uint64_t arena_estimate(uint64_t n_rows, uint32_t n_active, bool ratio) {
+    uint64_t per_row = ratio ? 2048 : (uint64_t)n_active * 48 + 256;
+    uint64_t b = n_rows * per_row + (uint64_t)64 * SPARSE_PAGE_BYTES;
     return (b + 255) & ~(uint64_t)255;
+}
+static uint64_t arena_upper(uint64_t n_rows, uint32_t n_active, bool ratio) {
+    uint64_t per_row = ratio ? (uint64_t)MAX_ACTIVE * 34 + 64 : (uint64_t)n_active * 7 * 34 + 256;   // nodes + children + 5 Del rounds of new children
+    uint64_t b = n_rows * per_row + (uint64_t)64 * SPARSE_PAGE_BYTES;
+    return (b + 255) & ~(uint64_t)255;
+}
+static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io, RowStore* store, uint32_t small_cap, uint64_t upper_bytes) {
+    const uint64_t cells0 = store->cells;
+    int st = run_sparse_jobs_once(m, sj, io, store, small_cap);
+    if (st != ST_ARENA_FULL) return st;
+    if (io.arena_bytes >= upper_bytes) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
+    if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] sparse arena of %.1f MB exhausted: repeating the phase with %.1f MB\n", io.arena_bytes / 1e6, upper_bytes / 1e6);
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    cache_free(store->arena.base); cache_free(store->arena.cursor); store->arena = SparseArena();
+    ST_TRY(alloc_arena(store->arena, upper_bytes, m->stream));
+    io.arena = store->arena.base; io.arena_bytes = store->arena.bytes; io.arena_cursor = store->arena.cursor;
+    store->cells = cells0;
+    st = run_sparse_jobs_once(m, sj, io, store, small_cap);
+    if (st == ST_ARENA_FULL) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
+    return st;
 }
 
 // ================================================================================================ forward
@@ -317,7 +369,8 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
         io.map_row_off = dmap ? dmap->row_off : nullptr; io.map_nodes = dmap ? dmap->nodes : nullptr;
         io.pool = out->pool.base; io.slab_bytes = out->pool.slab_bytes; io.Np = out->pool.Np;
         io.arena = out->arena.base; io.arena_bytes = out->arena.bytes; io.arena_cursor = out->arena.cursor; io.active = nullptr;
-        ST_TRY(run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_FWD_MAPPING ? 64 : 256));
+        ST_TRY(run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_FWD_MAPPING ? 64 : sparse_default_cap(),
+                               store_sparse ? arena_upper(sparse_rows, m->params.n_active_nodes, kind == DBGPHMM_FWD_SPARSE_RATIO) : 0));
     }
     if (!keep_rows) { cache_free(out->pool.base); out->pool.base = nullptr; }  // ping-pong slabs are dead now
     // final e of jobs whose last row is dense
@@ -431,7 +484,8 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
         io.map_row_off = dmap ? dmap->row_off : nullptr; io.map_nodes = dmap ? dmap->nodes : nullptr;
         io.pool = out->pool.base; io.slab_bytes = out->pool.slab_bytes; io.Np = out->pool.Np;
         io.arena = out->arena.base; io.arena_bytes = out->arena.bytes; io.arena_cursor = out->arena.cursor; io.active = nullptr;
-        return run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_BWD_MAPPING ? 64 : 256);
+        return run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_BWD_MAPPING ? 64 : sparse_default_cap(),
+                               arena_upper(sparse_rows, m->params.n_active_nodes, kind == DBGPHMM_BWD_BY_FORWARD));
     };
 
     if (!sparse_first) {

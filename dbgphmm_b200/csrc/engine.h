@@ -131,3 +131,6 @@ int run_products_edge_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, con
 // per-base top nodes of the emit probabilities (hint.rs:124-142) appended to `out` (host Mappings, ORIGINAL ids)
 int run_products_mapping(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, int by_ratio,
                          uint32_t n_active, double ratio, dbgphmm_mappings* out);
+
+// device bytes reserved for n_rows stored sparse rows (typical size ; the sparse phase is repeated with the upper bound if exceeded)
+uint64_t arena_estimate(uint64_t n_rows, uint32_t n_active, bool ratio);

@@ -410,6 +410,9 @@ void model_free(dbgphmm_model* m) {
     free_plan(m->fwd); free_plan(m->bwd);
     cache_trim();
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->stream_aux) cudaStreamDestroy(m->stream_aux);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
 }
 
@@ -508,13 +511,16 @@ extern "C" int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const ui
     dbgphmm_model* m = new dbgphmm_model();
     m->device = device; m->params = *params; m->lin = to_lin(*params);
     int st = DBGPHMM_OK;
-    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { dbg_set_error("stream create failed"); st = DBGPHMM_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream_aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        dbg_set_error("stream create failed"); st = DBGPHMM_ERR_CUDA;
+    }
     if (st == DBGPHMM_OK) st = model_build_graph(m, n_nodes, n_edges, edge_src, edge_dst, emission);
     if (st == DBGPHMM_OK) st = model_upload_probs(m, log_init, log_trans);
     if (st == DBGPHMM_OK) {
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
-        m->mem_budget = mem_budget_bytes ? mem_budget_bytes : (uint64_t)(fr * 0.8);
+        m->mem_budget = mem_budget_bytes ? mem_budget_bytes : (uint64_t)(fr * 0.88);
         st = dense_configure(m);
         if (st == DBGPHMM_OK) st = sparse_configure(m);
     }

@@ -67,6 +67,8 @@ struct dbgphmm_model {
     uint64_t mem_budget = 0;
     int n_sm = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_aux = nullptr;            // rescue launch of the sparse kernel (sparse.cu)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // host copies (relabelled ids unless noted)
     std::vector<uint32_t> pos_of;   // [N] original id -> relabelled

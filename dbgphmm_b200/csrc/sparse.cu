@@ -354,10 +354,13 @@ __device__ __forceinline__ void prev_get(const SS& S, const PrevAcc& P, uint32_t
 
 extern __shared__ __align__(16) unsigned char sp_smem[];
 
-__global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, SparseIO io, uint32_t cap, uint32_t hcap) {
-    const SJob jb = jobs[blockIdx.x];
-    if (jb.active_idx >= 0 && !io.active[jb.active_idx]) return;
-    if (jb.n_rows == 0) return;
+// role 0, no rescue queue: CTA b runs job b ; a job whose row outgrows the launch's entry capacity reports SJ_NEED_BIG.
+// role 0 with a rescue queue: persistent CTAs take jobs off a counter ; a job whose row outgrows the capacity hands its previous
+// row over to the queue and the CTA moves on.  role 1: persistent CTAs of a second launch with the next capacity, running
+// beside the primary one, take such jobs from the queue and carry them on from the row that did not fit.  (Re-running a failed
+// job in a later pass would cost a whole extra job latency: the kernel is latency-bound, one straggler costs as much as a wave.
+// Launch order primary, rescue: neither waits for the other to start, so the pair also completes when kernels are serialised.)
+__global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, SparseIO io, uint32_t cap, uint32_t hcap, int role) {
     const int tid = threadIdx.x, B = blockDim.x;
     // ---- shared-memory view
     SS S;
@@ -369,12 +372,56 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
     __shared__ int s_fail;
     __shared__ unsigned long long s_cells;
+    __shared__ unsigned long long s_info;   // where a job stopped: step << 32 | site << 16 | entries
+    __shared__ uint32_t s_job;
+  for (;;) {
+    uint32_t job_idx = blockIdx.x, s_begin = 0;
+    if (role == 0 && io.rq_ctl) {   // persistent primary CTAs: next job of the launch
+        if (tid == 0) s_job = atomicAdd(io.rq_ctl + 3, 1u);
+        __syncthreads();
+        job_idx = s_job;
+        __syncthreads();
+        if (job_idx >= io.rq_n_jobs) {
+            if (tid == 0) { __threadfence(); atomicAdd(io.rq_ctl + 2, 1u); }
+            return;
+        }
+    }
+    if (role == 1) {   // take the next handed-over job, or leave once every primary CTA is gone and the queue is empty
+        if (tid == 0) {
+            volatile uint32_t* ctl = io.rq_ctl;
+            uint32_t got = SP_ABSENT;
+            for (;;) {
+                const uint32_t done = ctl[2];   // (read before the counters: a push always precedes its CTA's done mark)
+                __threadfence();
+                const uint32_t pushed = ctl[0], popped = ctl[1];
+                if (popped < pushed) { if (atomicCAS(io.rq_ctl + 1, popped, popped + 1) == popped) { got = popped; break; } }
+                else if (done == io.rq_n_primary) break;
+                else __nanosleep(2000);
+            }
+            if (got != SP_ABSENT) {
+                volatile uint32_t* it = io.rq_items + got;
+                uint32_t j;
+                while ((j = *it) == SP_ABSENT) __nanosleep(200);
+                __threadfence();
+                got = j;
+            }
+            s_job = got;
+        }
+        __syncthreads();
+        job_idx = s_job;
+        __syncthreads();
+        if (job_idx == SP_ABSENT) return;
+    }
+    const SJob jb = jobs[job_idx];
+    const bool skip = (jb.active_idx >= 0 && !io.active[jb.active_idx]) || jb.n_rows == 0;
     const double* init = G.init + (size_t)jb.x * G.N;
     const double* trans = G.trans + (size_t)jb.x * G.E;
     const bool fwd = jb.dir == 0;
     const bool adaptive = (jb.mode == SP_TOPN || jb.mode == SP_RATIO);
+    uint32_t n_prev = 0;   // packed entries of the previous row (sparse prev only)
+    XF last_scalar = xf_zero();
     if (tid == 0) {
-        s_page_left = 0; s_page_off = 0; s_fail = SJ_OK; s_cells = 0;
+        s_page_left = 0; s_page_off = 0; s_fail = SJ_OK; s_cells = 0; s_info = 0;
         if (fwd) {
             if (jb.row_begin == 0) { s_mb = xf(1.0, 0); s_ib = xf_zero(); }
             else { s_mb = io.desc[jb.desc0 + jb.row_begin - 1].mb; s_ib = io.desc[jb.desc0 + jb.row_begin - 1].ib; }
@@ -383,11 +430,27 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             s_ib = (jb.row_begin == (int)jb.len - 1) ? xf_zero() : io.desc[jb.desc0 + jb.row_begin + 1].ib;
         }
     }
-    uint32_t n_prev = 0;   // packed entries of the previous row (sparse prev only)
-    XF last_scalar = xf_zero();
+    if (role == 1) {   // resume: the row before step s_begin as the primary CTA left it
+        SHandoff h;
+        {   // (written by another SM: read through L2)
+            const uint4* hp = (const uint4*)(io.rq_hand + job_idx); uint4* hq = (uint4*)&h;
+#pragma unroll
+            for (int k = 0; k < (int)(sizeof(SHandoff) / 16); k++) hq[k] = __ldcg(hp + k);
+        }
+        s_begin = h.step; n_prev = h.n_prev; last_scalar = h.last_scalar;
+        __syncthreads();
+        if (tid == 0 && s_begin > 0) { s_mb = h.mb; s_ib = h.ib; s_cells = h.cells; }
+        const char* hr = io.rq_rows + (size_t)job_idx * 32 * io.rq_cap;
+        const double* hm = (const double*)hr; const double* hi = hm + io.rq_cap; const double* hd = hi + io.rq_cap;
+        const uint32_t* hid = (const uint32_t*)(hd + io.rq_cap); const int* hex = (const int*)(hid + io.rq_cap);
+        for (uint32_t h2 = tid; h2 < hcap; h2 += B) { S.ph_key()[h2] = 0; S.ph_val()[h2] = SP_ABSENT; }
+        for (uint32_t e = tid; e < n_prev; e += B) { S.p_m()[e] = __ldcg(hm + e); S.p_i()[e] = __ldcg(hi + e); S.p_d()[e] = __ldcg(hd + e); S.p_id()[e] = __ldcg(hid + e); S.p_ex()[e] = __ldcg(hex + e); }
+        __syncthreads();
+        for (uint32_t e = tid; e < n_prev; e += B) S.ph_val()[sp_cell(S.ph_key(), S.hmask, S.hshift, S.p_id()[e])] = e;
+    }
     __syncthreads();
 
-    for (uint32_t s = 0; s < jb.n_rows; s++) {
+    for (uint32_t s = s_begin; s < jb.n_rows && !skip; s++) {
         const int row = fwd ? jb.row_begin + (int)s : jb.row_begin - (int)s;
         const uint8_t x = io.bases[jb.base_off + row];
         PrevAcc PA;
@@ -437,7 +500,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         }
         if (n_top > (int)cap && tid == 0) s_fail = SJ_NEED_BIG;   // list scratch is sized by cap
         __syncthreads();
-        if (s_fail) break;
+        if (s_fail) { if (tid == 0) s_info = ((unsigned long long)s << 32) | 1u << 16 | (unsigned)n_top; break; }
 
         // ---------------- 2. reset the current row
         uint32_t n_ent = 0;
@@ -454,7 +517,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             // backward sparse: M/I over to_parents_and_us(nodes) (backward.rs:243-259) ; non-adaptive: nodes themselves
             ok = sp_expand(S, S.top_id(), n_top, G.par_off, G.par_node, true, adaptive, S.act_id(), S.act_slot(), MAX_ACTIVE, &n_ent, &n_act);
         }
-        if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
+        if (!ok) { if (tid == 0) { s_fail = SJ_NEED_BIG; s_info = ((unsigned long long)s << 32) | 2u << 16 | n_ent; } __syncthreads(); break; }
         const uint32_t n_mi = (uint32_t)n_act;
         const uint32_t stamp0 = 1;   // Del stamps: round t writes t + 1
         uint32_t n_d = 0;
@@ -525,7 +588,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 __syncthreads();
                 src_id = l_id; n_src = n_l;
             }
-            if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
+            if (!ok) { if (tid == 0) { s_fail = SJ_NEED_BIG; s_info = ((unsigned long long)s << 32) | 3u << 16 | n_ent; } __syncthreads(); break; }
             // ---------------- 6f. fe over nodes (forward.rs:554-558), begin scalars
             XF part = xf_zero();
             for (uint32_t a = tid; a < n_mi; a += B) {
@@ -589,7 +652,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 __syncthreads();
                 src_id = l_id; n_src = n_l;
             }
-            if (!ok) { if (tid == 0) s_fail = SJ_NEED_BIG; __syncthreads(); break; }
+            if (!ok) { if (tid == 0) { s_fail = SJ_NEED_BIG; s_info = ((unsigned long long)s << 32) | 4u << 16 | n_ent; } __syncthreads(); break; }
             // ---------------- 5b. bm, bi over nodes ; bmb, bib sums (backward.rs:423-555)
             XF pmb = xf_zero(), pib = xf_zero();
             for (uint32_t a = tid; a < n_mi; a += B) {
@@ -673,11 +736,32 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        io.status[blockIdx.x] = s_fail;
-        io.final_scalar[blockIdx.x] = last_scalar;
-        io.cells[blockIdx.x] = s_cells;
+    const bool hand_over = role == 0 && io.rq_ctl && s_fail == SJ_NEED_BIG && n_prev <= io.rq_cap;
+    if (hand_over) {   // previous row + scalars to the rescue queue
+        char* hr = io.rq_rows + (size_t)job_idx * 32 * io.rq_cap;
+        double* hm = (double*)hr; double* hi = hm + io.rq_cap; double* hd = hi + io.rq_cap;
+        uint32_t* hid = (uint32_t*)(hd + io.rq_cap); int* hex = (int*)(hid + io.rq_cap);
+        for (uint32_t e = tid; e < n_prev; e += B) { hm[e] = S.p_m()[e]; hi[e] = S.p_i()[e]; hd[e] = S.p_d()[e]; hid[e] = S.p_id()[e]; hex[e] = S.p_ex()[e]; }
+        if (tid == 0) {
+            SHandoff h;
+            h.step = (uint32_t)(s_info >> 32); h.n_prev = n_prev; h.mb = s_mb; h.ib = s_ib; h.cells = s_cells; h.last_scalar = last_scalar;
+            io.rq_hand[job_idx] = h;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t slot = atomicAdd(io.rq_ctl, 1u);
+            __threadfence();
+            *(volatile uint32_t*)(io.rq_items + slot) = job_idx;
+        }
+    } else if (tid == 0) {
+        io.status[job_idx] = s_fail;
+        io.final_scalar[job_idx] = last_scalar;
+        io.cells[job_idx] = s_fail == SJ_NEED_BIG ? s_info : s_cells;
     }
+    if (role == 0 && !io.rq_ctl) return;
+    __syncthreads();
+  }
 }
 
 static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) { return SS_BYTES(cap, hcap); }
@@ -692,36 +776,74 @@ int sparse_configure(dbgphmm_model* m) {
 // four and let more jobs stay resident
 static int sparse_threads(uint32_t cap) { return cap <= 64 ? 32 : (cap <= 256 ? 64 : 256); }
 
-uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
+uint32_t sparse_default_cap() {
+    if (const char* e = getenv("DBGPHMM_SPARSE_CAP")) { int c0 = atoi(e); if (c0 >= 32 && c0 <= 832) return ((uint32_t)c0 + 15u) & ~15u; }
+    return 128;   // rows of a top-n (n_active_nodes = 40) job hold 50-110 entries ; the rescue launch takes the exceptions
+}
+
+uint32_t sparse_rescue_cap(uint32_t cap) {
+    if (const char* e = getenv("DBGPHMM_SPARSE_RESCUE")) { if (e[0] == '0') return 0; }
+    return cap < 256 ? 256 : 0;
+}
+
+static uint32_t hcap_of(uint32_t cap) {
     uint32_t hcap = 1;
     while (hcap < 2 * cap) hcap <<= 1;
+    return hcap;
+}
+
+// jobs resident at once: as many primary CTAs per SM as shared memory allows beside one rescue CTA
+uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
+    const uint32_t rcap = sparse_rescue_cap(cap);
     int per_sm = 0;
     cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sparse, sparse_threads(cap), sparse_smem_bytes(cap, hcap)) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sparse, sparse_threads(cap), sparse_smem_bytes(cap, hcap_of(cap))) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
+    }
+    if (rcap) {
+        const size_t sm_bytes = 227 * 1024, one = sparse_smem_bytes(cap, hcap_of(cap)) + 1024, big = sparse_smem_bytes(rcap, hcap_of(rcap)) + 1024;
+        const int fit = (int)((sm_bytes - big) / one);
+        if (fit >= 1 && fit < per_sm) per_sm = fit;
     }
     return (uint32_t)per_sm * (uint32_t)m->n_sm;
 }
 
-int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap) {
-    if (n_jobs == 0) return DBGPHMM_OK;
-    uint32_t hcap = 1;
-    while (hcap < 2 * cap) hcap <<= 1;
-    size_t smem = sparse_smem_bytes(cap, hcap);
+static int sparse_launch(dbgphmm_model* m, cudaStream_t st, uint32_t grid, const SGraph& G, const SJob* d_jobs, const SparseIO& io, uint32_t cap, int role) {
+    const uint32_t hcap = hcap_of(cap);
+    const size_t smem = sparse_smem_bytes(cap, hcap);
     if (smem > 200 * 1024) { dbg_set_error("sparse_run: capacity too large for shared memory"); return DBGPHMM_ERR_INVALID; }
-    SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
-             m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
     int threads = sparse_threads(cap);
     if (const char* e = getenv("DBGPHMM_SPARSE_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) threads = t; }
+    k_sparse<<<grid, threads, smem, st>>>(G, m->lin, d_jobs, io, cap, hcap, role);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}
+
+int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io_in, uint32_t cap, uint32_t rescue_cap) {
+    if (n_jobs == 0) return DBGPHMM_OK;
+    SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
+             m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
     {   // the kernel is latency-bound: as many resident jobs per SM as shared memory allows
         int carve = 100;
         if (const char* e = getenv("DBGPHMM_SPARSE_CARVEOUT")) carve = atoi(e);
         if (carve < 10) carve = 10; if (carve > 100) carve = 100;
         cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
-    k_sparse<<<n_jobs, threads, smem, m->stream>>>(G, m->lin, d_jobs, io, cap, hcap);
-    COUNT_LAUNCH();
-    CUDA_TRY(cudaGetLastError());
+    SparseIO io = io_in;
+    if (!rescue_cap || !io.rq_ctl) {
+        io.rq_ctl = nullptr;
+        return sparse_launch(m, m->stream, n_jobs, G, d_jobs, io, cap, 0);
+    }
+    // primary: as many persistent CTAs as stay resident beside one rescue CTA per SM ; rescue CTAs idle until a job is handed over
+    const uint32_t grid = std::min<uint32_t>(n_jobs, sparse_wave_jobs(m, cap));
+    io.rq_cap = cap; io.rq_n_primary = grid; io.rq_n_jobs = n_jobs;
+    CUDA_TRY(cudaEventRecord(m->ev_fork, m->stream));
+    CUDA_TRY(cudaStreamWaitEvent(m->stream_aux, m->ev_fork, 0));
+    ST_TRY(sparse_launch(m, m->stream, grid, G, d_jobs, io, cap, 0));
+    ST_TRY(sparse_launch(m, m->stream_aux, std::min<uint32_t>(n_jobs, (uint32_t)m->n_sm), G, d_jobs, io, rescue_cap, 1));
+    CUDA_TRY(cudaEventRecord(m->ev_join, m->stream_aux));
+    CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     return DBGPHMM_OK;
 }

@@ -30,6 +30,14 @@ struct SJob {
     uint32_t out_idx;     // job index in the caller's batch
 };
 
+// State a job hands over when a row outgrows its launch's entry capacity: the job carries on from `step` in a CTA of the
+// concurrently running rescue launch (larger capacity).  The previous row itself goes to rq_rows.
+struct alignas(16) SHandoff {
+    uint32_t step, n_prev;
+    unsigned long long cells;
+    XF mb, ib, last_scalar;
+};
+
 struct SparseArena {
     char* base = nullptr;
     uint64_t bytes = 0;
@@ -52,10 +60,24 @@ struct SparseIO {
     XF* final_scalar;          // per job: forward -> e of the last row ; backward -> mb of row 0
     unsigned long long* cells; // per job: sum over rows of |nodes| (GCUPS numerator)
     const int* active;
+    // rescue queue (nullptr: a job that needs more capacity reports SJ_NEED_BIG and is re-run by the caller)
+    uint32_t* rq_ctl;          // [0] jobs pushed, [1] jobs taken, [2] primary CTAs that have left, [3] next job of the primary launch
+    uint32_t* rq_items;        // [n_jobs] pushed job indices, 0xffffffff until published
+    SHandoff* rq_hand;         // [n_jobs]
+    char* rq_rows;             // [n_jobs][32 * rq_cap] previous row: m, i, d, id, ex
+    uint32_t rq_cap;           // entry capacity of the primary launch
+    uint32_t rq_n_primary;     // CTAs of the primary launch
+    uint32_t rq_n_jobs;        // jobs of the primary launch
 };
 
 int sparse_configure(dbgphmm_model* m);
+// entry capacity of the first pass over top-n / ratio / by-forward jobs (DBGPHMM_SPARSE_CAP overrides it)
+uint32_t sparse_default_cap();
 // jobs that are resident at once with entry capacity `cap` (one wave): batches are cut to multiples of it
 uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap);
-// cap: entry capacity per job in shared memory (256 normal, 832 big); threads per CTA chosen from cap
-int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap);
+// cap: entry capacity per job in shared memory; threads per CTA chosen from cap.  rescue_cap > cap: a second launch of
+// persistent CTAs with that capacity runs beside the primary one (auxiliary stream) and carries on the jobs whose rows
+// outgrow `cap` (io.rq_* must be set up by the caller); 0: no rescue launch.
+int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap, uint32_t rescue_cap = 0);
+// capacity of the rescue launch that accompanies a primary launch of capacity `cap` (0: none)
+uint32_t sparse_rescue_cap(uint32_t cap);
