@@ -294,8 +294,12 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     ST_TRY(dev_upload(b_active, h_active, st));
     ST_TRY(dev_upload(b_nd, nd_max, st));
     ST_TRY(dev_upload(b_len, out->len, st));
-    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * m->fwd.n_chunks));
-    DevBuf b_wl;
+    // two rows per launch when nothing reads the intermediate rows (ping-pong slabs, no per-row products, fixed warm-up)
+    bool paired = !keep_rows && !opt.step && (kind == DBGPHMM_FWD_SPARSE || kind == DBGPHMM_FWD_DENSE) && steps >= 2 && dense_can_pair(m);
+    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * std::max<size_t>(m->fwd.n_chunks, paired ? 2 * (size_t)dense_pair_tiles(m) : 0)));
+    DevBuf b_wl, b_redo;
+    ST_TRY(b_redo.alloc(sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(b_redo.p, 0, sizeof(int), st));
     ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * m->fwd.n_chunks + 1)));
     ST_TRY(b_top_ids.alloc(sizeof(uint32_t) * (size_t)J * MAX_ACTIVE));
     ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
@@ -303,12 +307,26 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     const int* d_active = kind == DBGPHMM_FWD_SPARSE_RATIO ? b_active.as<int>() : nullptr;
     std::vector<SelectReq> reqs(J);
     ST_TRY(b_reqs.alloc(sizeof(SelectReq) * J));
-    auto slab_of_h = [&](uint32_t j, uint32_t s) { return dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    auto slab_of_h = [&](uint32_t j, uint32_t s) { return paired ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
     delete tr_setup;
     {
         HostTrace t("  fwd dense phase");
         EvTimer tm(st, &g_times.dense_ms);
-        for (uint32_t s = 0; s < steps; s++) {
+        if (paired) {
+            for (uint32_t s = 0; s < steps; s += 2) {
+                uint64_t live = 0;
+                for (uint32_t j = 0; j < J; j++) live += (s < nd_max[j]) + (s + 1 < nd_max[j]);
+                ST_TRY(dense_forward_pair(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, b_part.as<XF>(), b_redo.as<int>(), live * N, s + 1 < steps));
+            }
+            int redo = 0;
+            CUDA_TRY(cudaMemcpyAsync(&redo, b_redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (redo) {   // some tile's exponent range does not fit a two-row frame: single-row steps from the start
+                if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] forward dense phase repeated with single-row steps\n");
+                paired = false;
+            }
+        }
+        for (uint32_t s = 0; s < steps && !paired; s++) {
             uint64_t live = 0;  // jobs that (may) compute row s: the algorithmic cells of this launch
             for (uint32_t j = 0; j < J; j++) live += s < nd_max[j];
             ST_TRY(dense_forward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));

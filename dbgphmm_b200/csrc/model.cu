@@ -75,8 +75,11 @@ static int upload(T** dptr, const std::vector<T>& h) {
 
 // ------------------------------------------------------------------ dense tiling plan
 // up_off/up_node/up_eid: CSR of the upstream direction (parents for forward, children for backward).
+// hops: depth of the upstream closure.  HALO_HOPS serves every single-row kernel ; 2 * HALO_HOPS is the register-stencil layout
+// of the two-rows-per-launch kernel (dense.cu: k_dense_fwd2), whose tiles carry the dependency cone of two rows.
 static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_off, const std::vector<uint32_t>& up_node,
-                      const std::vector<uint32_t>& up_eid) {
+                      const std::vector<uint32_t>& up_eid, int hops = HALO_HOPS) {
+    const bool single = hops == HALO_HOPS;
     std::vector<uint32_t> chunk_start, loc_base, loc_node, nle, le_off, le_eid, fp_eid, fx_off, fx_eid;
     std::vector<uint16_t> le_idx, fp_idx, fx_idx;
     std::vector<uint32_t> rl_node, rl_eid, rx_off, rx_eid;
@@ -84,7 +87,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
     std::vector<uint8_t> rl_flag;
     std::vector<uint32_t> rpos(N, 0xffffffffu);  // node -> position in the register layout of the current tile
     std::vector<uint32_t> stamp(N, 0xffffffffu), lidx(N, 0);
-    std::vector<uint32_t> local, depth_cnt(8);
+    std::vector<uint32_t> local, depth_cnt(std::max(8, hops + 2));
     uint32_t start = 0, cidx = 0, max_local = 0;
     chunk_start.push_back(0);
     loc_base.push_back(0);
@@ -111,7 +114,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
             const bool descending = n_next > n_prev;
             std::vector<uint32_t> head;
             uint32_t v = descending ? local[size - 1] : local[0];
-            for (int h = 0; h < HALO_HOPS; h++) {   // chain of first upstream neighbours above the tile head, deepest first
+            for (int h = 0; h < hops; h++) {   // chain of first upstream neighbours above the tile head, deepest first
                 if (up_off[v + 1] == up_off[v]) break;
                 uint32_t u = up_node[up_off[v]];
                 if (!in_tile(u) || lidx[u] < size || placed[lidx[u]]) break;
@@ -163,7 +166,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
             depth_cnt[0] = size;
             size_t fb = 0, fe = local.size();
             bool ok = true;
-            for (int h = 1; h <= HALO_HOPS && ok; h++) {
+            for (int h = 1; h <= hops && ok; h++) {
                 for (size_t q = fb; q < fe; q++) {
                     uint32_t v = local[q];
                     for (uint32_t a = up_off[v]; a < up_off[v + 1]; a++) {
@@ -177,7 +180,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
                 }
                 fb = fe; fe = local.size();
             }
-            if (ok) {  // the tile's edge list must fit as well
+            if (ok && single) {  // the tile's edge list must fit as well (exact kernel)
                 size_t n_edges_local = 0, n_need = 0;
                 for (int h = 0; h < HALO_HOPS; h++) n_need += depth_cnt[h];
                 for (size_t q = 0; q < n_need && q < local.size(); q++) n_edges_local += up_off[local[q] + 1] - up_off[local[q]];
@@ -198,7 +201,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
         uint32_t cum = 0;
         for (int h = 0; h < 8; h++) { cum += (h <= HALO_HOPS ? depth_cnt[h] : 0); nle.push_back(cum); }
         uint32_t n_need_edges = nle[nle.size() - 8 + (HALO_HOPS - 1)];  // depth <= 5 gather from upstream
-        for (size_t j = 0; j < local.size(); j++) {
+        for (size_t j = 0; single && j < local.size(); j++) {
             uint32_t v = local[j];
             loc_node.push_back(v);
             le_off.push_back((uint32_t)le_idx.size());
@@ -213,8 +216,10 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
             }
             fp_idx.push_back(p0); fp_eid.push_back(e0);
         }
-        le_off.push_back((uint32_t)le_idx.size());  // sentinel of this chunk
-        fx_off.push_back((uint32_t)fx_idx.size());
+        if (single) {
+            le_off.push_back((uint32_t)le_idx.size());  // sentinel of this chunk
+            fx_off.push_back((uint32_t)fx_idx.size());
+        }
         // ---- register-stencil layout of this tile (positions computed by build_layout inside the sizing loop)
         {
             for (size_t q = 0; q < lay.size(); q++) if (lay[q] != 0xffffffffu) rpos[lay[q]] = (uint32_t)q;
@@ -258,7 +263,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
     }
     P.n_chunks = cidx;
     P.max_local = max_local;
-    if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] plan: %u tiles for %u nodes (%.1f core nodes per tile, capacity %d)\n", cidx, N, (double)N / cidx, DENSE_CORE);
+    if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] plan (%d hops): %u tiles for %u nodes (%.1f core nodes per tile, capacity %d)\n", hops, cidx, N, (double)N / cidx, DENSE_CORE);
     P.h_chunk_start = chunk_start;
     ST_TRY(upload(&P.chunk_start, chunk_start));
     ST_TRY(upload(&P.loc_base, loc_base));
@@ -346,6 +351,12 @@ int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* 
     ST_TRY(upload(&m->d_chi_off, m->chi_off)); ST_TRY(upload(&m->d_chi_node, m->chi_node)); ST_TRY(upload(&m->d_chi_eid, m->chi_eid));
     ST_TRY(build_plan(m->fwd, N, m->par_off, m->par_node, m->par_eid));
     ST_TRY(build_plan(m->bwd, N, m->chi_off, m->chi_node, m->chi_eid));
+    {   // layout of the two-rows-per-launch forward kernel ; a graph too branchy for 12-hop tiles simply goes without it
+        const char* e = getenv("DBGPHMM_DENSE_FUSE");
+        if (!(e && e[0] == '0')) {
+            if (build_plan(m->fwd2, N, m->par_off, m->par_node, m->par_eid, 2 * HALO_HOPS) != DBGPHMM_OK) free_plan(m->fwd2);
+        }
+    }
     return DBGPHMM_OK;
 }
 
@@ -407,7 +418,7 @@ void model_free(dbgphmm_model* m) {
     cudaFree(m->d_par_off); cudaFree(m->d_par_node); cudaFree(m->d_par_eid);
     cudaFree(m->d_chi_off); cudaFree(m->d_chi_node); cudaFree(m->d_chi_eid);
     cudaFree(m->d_init); cudaFree(m->d_trans);
-    free_plan(m->fwd); free_plan(m->bwd);
+    free_plan(m->fwd); free_plan(m->bwd); free_plan(m->fwd2);
     cache_trim();
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->stream_aux) cudaStreamDestroy(m->stream_aux);

@@ -86,6 +86,7 @@ struct dbgphmm_model {
     double* d_init = nullptr;   // [n_batch][N] linear, relabelled node order
     double* d_trans = nullptr;  // [n_batch][E] linear, original EdgeIndex order
     DevPlan fwd, bwd;
+    DevPlan fwd2;   // forward tiles with a 2 x HALO_HOPS halo (two rows per launch) ; n_chunks == 0: not available
     // Recompute support for the stream strategy: for every forward tile the tiles that intersect the upstream closure of
     // its nodes within HALO_HOPS * n_warmup hops (the dependency cone of n_warmup dense rows), built lazily.
     uint32_t roi_warmup = 0;

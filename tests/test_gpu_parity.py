@@ -240,6 +240,31 @@ def test_stream_strategy_matches_store_and_oracle(H, monkeypatch):
     assert np.allclose(res["store"][0], res["stream"][0], rtol=1e-12, atol=1e-15)
 
 
+def test_two_rows_per_launch_forward_kernel_and_its_fallback(H, monkeypatch):
+    """Stream strategy: the forward warm-up runs two rows per launch (k_dense_fwd2) and must reproduce the single-row steps bit for
+    bit; a two-row frame that is too narrow (forced here) makes the phase fall back to single-row steps with the same result."""
+    w = _dbg_case(11, n_reads=5)
+    par = oracle_params(0.003, n_warmup=w.k)
+    g, o = both(w.graph, par)
+    of, olf, olb = o.run_node_freqs(O.Reads(w.reads), "sparse", True, None)
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
+    res = {}
+    for tag, span2 in (("pair", None), ("fallback", "1")):
+        if span2 is None:
+            monkeypatch.delenv("DBGPHMM_DENSE_SPAN2", raising=False)
+        else:
+            monkeypatch.setenv("DBGPHMM_DENSE_SPAN2", span2)
+        res[tag] = g.run_node_freqs(H.Reads(w.reads), "sparse", True, None)
+        gf, glf, glb, cells = res[tag]
+        assert close_log(glf, olf).all() and close_log(glb, olb).all()
+        assert np.allclose(gf, of, rtol=REL_TOL, atol=1e-12)
+    assert np.array_equal(res["pair"][1], res["fallback"][1]) and res["pair"][3] == res["fallback"][3]
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "store")
+    monkeypatch.delenv("DBGPHMM_DENSE_SPAN2", raising=False)
+    st = g.run_node_freqs(H.Reads(w.reads), "sparse", True, None)
+    assert np.array_equal(res["pair"][1], st[1])
+
+
 def test_full_prob_reads_batched_over_candidates(H):
     """to_full_prob_reads for a batch of candidate copy-number vectors X (posterior.rs:504-515)."""
     w = _dbg_case(8, n_reads=5, k=16, p_err=0.003)
