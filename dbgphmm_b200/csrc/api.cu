@@ -514,9 +514,13 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
             if (st == DBGPHMM_OK && cudaMemsetAsync(b_err.p, 0, sizeof(int), m->stream) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
             PhaseOpts pf; pf.keep_rows = false; pf.store_sparse = true;
             if (st == DBGPHMM_OK) st = run_forward(m, jobs, reads->d_bases, fk, pf, nullptr, &F);                    // F: sparse rows stored
+            // B dense x F sparse: on the fly after every dense backward step, or (when the two-rows-per-launch kernels are available,
+            // which never write the intermediate rows) by a recompute pass inside the dependency cone like the forward one below
+            const bool b_recompute = dense_can_pair(m);
             StepProducts spb; spb.other = &F; spb.P = F.d_final; spb.d_freqs = d_freqs; spb.d_err = b_err.as<int>();
-            PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = &spb;
-            if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);               // B dense x F sparse on the fly
+            PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = b_recompute ? nullptr : &spb;
+            if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);
+            if (st == DBGPHMM_OK && b_recompute) st = run_backward_recompute(m, jobs, reads->d_bases, F, B, spb);
             if (st == DBGPHMM_OK) st = run_products_freqs(m, jobs, F, B, d_freqs);                                    // sparse x sparse, F sparse x b_init
             StepProducts spf; spf.other = &B; spf.P = F.d_final; spf.d_freqs = d_freqs; spf.d_err = b_err.as<int>();
             if (st == DBGPHMM_OK) st = run_forward_recompute(m, jobs, reads->d_bases, F, B, spf);                    // F dense (cone only) x B sparse

@@ -359,7 +359,7 @@ k_dense_bwd(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs
 }
 
 __global__ void k_dense_bwd_finish(LinParams lp, const DJob* __restrict__ jobs, uint32_t s, RowDesc* __restrict__ desc,
-                                   const int* __restrict__ active, const XF* __restrict__ partials, uint32_t n_chunks) {
+                                   const int* __restrict__ active, const XF* __restrict__ partials, uint32_t n_chunks, int pair_slabs = 0) {
     const DJob jb = jobs[blockIdx.x];
     if (s >= jb.n_steps) return;
     if (jb.active_idx >= 0 && !active[jb.active_idx]) return;
@@ -378,7 +378,7 @@ __global__ void k_dense_bwd_finish(LinParams lp, const DJob* __restrict__ jobs, 
         XF ibn = (row == (int)jb.len - 1) ? xf_zero() : desc[jb.desc0 + row + 1].ib;  // b_init: ib = 0
         RowDesc r;
         r.kind = ROW_DENSE; r.n_ent = 0; r.n_mi = 0; r.n_d = 0;
-        r.off = jb.slab0 + (jb.slab_mod ? (s % jb.slab_mod) : s);
+        r.off = pair_slabs ? jb.slab0 + ((s >> 1) & 1) : jb.slab0 + (jb.slab_mod ? (s % jb.slab_mod) : s);
         r.mb = xnorm(xadd(ta, xmul(ibn, lp.p_MI * lp.p_random)));
         r.ib = xnorm(xadd(tb, xmul(ibn, lp.p_II * lp.p_random)));
         r.e = xf_zero();
@@ -1076,7 +1076,6 @@ k_dense_reg(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jst
 template <bool FWD>
 __global__ void k_dense_prep2(LinParams lp, const DJob* __restrict__ jobs, uint32_t n_jobs, uint32_t s, const uint8_t* __restrict__ bases,
                               const RowDesc* __restrict__ desc, char* __restrict__ pool, uint64_t slab_bytes, JStep* __restrict__ out) {
-    static_assert(FWD, "forward only");
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     const DJob jb = jobs[j];
@@ -1084,23 +1083,27 @@ __global__ void k_dense_prep2(LinParams lp, const DJob* __restrict__ jobs, uint3
     a.prev_ptr = 0; a.out_ptr = 0; a.fb0 = xf_zero(); a.ib_cur = xf_zero(); a.valid = 0; a.x = 0; a.pk = 0; a.base = 0;
     b = a;
     if (s < jb.n_steps) {
-        const int row = jb.first_row + (int)s;
+        const int row = FWD ? jb.first_row + (int)s : jb.first_row - (int)s;
         const uint32_t p = s >> 1;
         a.valid = 1; a.x = (int)jb.x; a.base = bases[jb.base_off + row];
         a.pk = (s == 0) ? jb.prev0_kind : PREV_SLAB;
         a.prev_ptr = (unsigned long long)(pool + (s == 0 ? jb.prev0_slab : jb.slab0 + ((p - 1) & 1)) * slab_bytes);
         a.out_ptr = (unsigned long long)(pool + (jb.slab0 + (p & 1)) * slab_bytes);
-        XF mbp, ibp;
-        if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
-        else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
-        a.ib_cur = xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random);
-        a.fb0 = xadd(xmul(mbp, lp.p_MM), xmul(ibp, lp.p_IM));
+        if (FWD) {
+            XF mbp, ibp;
+            if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
+            else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
+            a.ib_cur = xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random);
+            a.fb0 = xadd(xmul(mbp, lp.p_MM), xmul(ibp, lp.p_IM));
+        }
         if (s + 1 < jb.n_steps) {
-            // begin scalars of row s as k_dense_fwd_finish will write them: mb = 0, ib = xnorm(ib_cur)
-            const XF ibs = xnorm(a.ib_cur);
-            b.valid = 1; b.x = a.x; b.base = bases[jb.base_off + row + 1]; b.pk = PREV_SLAB; b.prev_ptr = 0; b.out_ptr = a.out_ptr;
-            b.ib_cur = xmul(xmul(ibs, lp.p_II), lp.p_random);
-            b.fb0 = xmul(ibs, lp.p_IM);
+            b.valid = 1; b.x = a.x; b.base = bases[jb.base_off + (FWD ? row + 1 : row - 1)]; b.pk = PREV_SLAB; b.prev_ptr = 0; b.out_ptr = a.out_ptr;
+            if (FWD) {
+                // begin scalars of row s as k_dense_fwd_finish will write them: mb = 0, ib = xnorm(ib_cur)
+                const XF ibs = xnorm(a.ib_cur);
+                b.ib_cur = xmul(xmul(ibs, lp.p_II), lp.p_random);
+                b.fb0 = xmul(ibs, lp.p_IM);
+            }
         }
     }
     out[j] = a;
@@ -1356,6 +1359,238 @@ k_dense_fwd2(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ js
     }
 }
 
+
+// k_dense_bwd2: two backward rows (r, r - 1) per launch, the mirror of k_dense_fwd2 on the tiles of DevPlan bwd2.
+__global__ void __launch_bounds__(WT_WARPS * 32, WT_MIN_CTAS)
+k_dense_bwd2(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ jstep, uint32_t n_jobs, uint32_t Np,
+             XF* __restrict__ partials, uint32_t n_tiles, int span2, int* __restrict__ redo, uint32_t jpc) {
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c = blockIdx.x * WT_WARPS + warp;
+    if (c >= n_tiles) return;
+    double* sa = (double*)(rs_raw + (size_t)warp * RS2_SMEM_PER_WARP);
+    double* sb = sa + DENSE_LMAX; double* sc = sb + DENSE_LMAX; int* se = (int*)(sc + DENSE_LMAX);
+    double* rm = (double*)(se + DENSE_LMAX); double* ri = rm + DENSE_LMAX; double* rd = ri + DENSE_LMAX; int* re = (int*)(rd + DENSE_LMAX);
+    JStep* sj = (JStep*)(re + DENSE_LMAX);           // [3 job slots][2 rows]
+    double* sinit = (double*)(sj + 6);
+    uint32_t* sion = (uint32_t*)(sinit + DENSE_LMAX);
+    (void)rd;
+    const uint32_t tbase = c * DENSE_LMAX;
+    const uint32_t g0 = P.chunk_start[c], ncore = P.chunk_start[c + 1] - g0;
+    unsigned int emc = 0, cmask = 0, srcm = 0;
+#pragma unroll
+    for (int q = 0; q < RS_PER_LANE; q++) {
+        const uint32_t nd = P.rl_node[tbase + 32 * q + lane];
+        sion[32 * q + lane] = nd;
+        cmask |= (nd - g0 < ncore ? 1u : 0u) << (8 + q);
+        if (nd != 0xffffffffu) cmask |= 1u << (16 + q);
+    }
+#pragma unroll
+    for (int k = 0; k < RS_PER_LANE; k++) {
+        const uint32_t nd = P.rl_node[tbase + RS_PER_LANE * lane + k];
+        unsigned int code = 4;
+        if (nd != 0xffffffffu) { unsigned char ch = G.emission[nd]; code = ch == 'n' ? 4 : ((ch >> 1) & 3); }
+        emc |= code << (3 * k);
+        cmask |= (nd - g0 < ncore ? 1u : 0u) << k;
+        srcm |= (unsigned int)((P.rl_flag[tbase + RS_PER_LANE * lane + k] >> 2) & 1) << k;
+    }
+    const bool tile_plain = !__any_sync(0xffffffffu, (srcm & ((1u << (RS_PER_LANE - 1)) - 1)) != 0);
+    const int pp0 = P.rl_par[tbase + RS_PER_LANE * lane];
+    int xp = pp0; uint32_t xe = 0xffffffffu; double xt = 0.0; bool ext0 = false;
+    if (P.rl_flag[tbase + RS_PER_LANE * lane] & 2) {
+        const size_t xi = (size_t)c * (DENSE_LMAX + 1) + RS_PER_LANE * lane;
+        const uint32_t a0 = P.rx_off[xi], a1 = P.rx_off[xi + 1];
+        if (a1 - a0 == 1) { xp = P.rx_idx[a0]; xe = P.rx_eid[a0]; } else ext0 = true;
+    }
+    const bool tile_has_x = __any_sync(0xffffffffu, xe != 0xffffffffu);
+    const bool tile_has_xx = __any_sync(0xffffffffu, ext0);
+    double tr[RS_PER_LANE];
+#pragma unroll
+    for (int k = 0; k < RS_PER_LANE; k++) tr[k] = 0.0;
+    int staged_x = -1;
+    const double* trans = G.trans;
+    const uint32_t job0 = blockIdx.y * jpc;
+    const uint32_t n_here = job0 < n_jobs ? min(jpc, n_jobs - job0) : 0u;
+    const size_t prow = (size_t)n_jobs * n_tiles * 2;   // partials of the second row
+    auto fetch_js = [&](uint32_t jj, int slot) {
+        if (lane < 4) cp_async16((char*)&sj[2 * slot] + 16 * lane, (const char*)&jstep[job0 + jj] + 16 * lane);
+        else if (lane < 8) cp_async16((char*)&sj[2 * slot + 1] + 16 * (lane - 4), (const char*)&jstep[n_jobs + job0 + jj] + 16 * (lane - 4));
+    };
+    auto fetch_rows = [&](const JStep& js) {
+        if (!js.valid || js.pk != PREV_SLAB) return;
+        const double* gm = (const double*)js.prev_ptr; const double* gi = gm + Np; const int* ge = (const int*)(gi + 2 * (size_t)Np);
+#pragma unroll
+        for (int q = 0; q < RS_PER_LANE; q++) {
+            if ((cmask >> (16 + q)) & 1) {
+                const int pos = 32 * q + lane; const uint32_t g = sion[pos];
+                cp_async8(&rm[pos], &gm[g]); cp_async8(&ri[pos], &gi[g]); cp_async4(&re[pos], &ge[g]);
+            }
+        }
+    };
+    if (n_here == 0) return;
+#pragma unroll
+    for (int q = 0; q < RS_PER_LANE; q++) { const int pos = 32 * q + lane; rm[pos] = 0.0; ri[pos] = 0.0; re[pos] = 0; }
+    fetch_js(0, 0);
+    if (n_here > 1) fetch_js(1, 1);
+    cp_async_wait_all();
+    __syncwarp();
+    fetch_rows(sj[0]);
+    for (uint32_t jj = 0; jj < n_here; jj++) {
+        const uint32_t job_idx = job0 + jj;
+        const int slot = jj % 3;
+        cp_async_wait_all();
+        __syncwarp();
+        auto prefetch_next = [&]() {
+            __syncwarp();
+            if (jj + 1 < n_here) fetch_rows(sj[2 * ((jj + 1) % 3)]);
+            if (jj + 2 < n_here) fetch_js(jj + 2, (jj + 2) % 3);
+        };
+        const JStep* js0 = &sj[2 * slot];
+        const JStep* js1 = js0 + 1;
+        const int valid = js0->valid, valid2 = js1->valid, hx = js0->x, pk = js0->pk;
+        if (!valid) { prefetch_next(); continue; }
+        if (hx != staged_x) {
+            const double* init = G.init + (size_t)hx * G.N;
+            trans = G.trans + (size_t)hx * G.E;
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) {
+                const uint32_t nd = P.rl_node[tbase + RS_PER_LANE * lane + k], ed = P.rl_eid[tbase + RS_PER_LANE * lane + k];
+                sinit[32 * k + lane] = nd == 0xffffffffu ? 0.0 : init[nd];
+                tr[k] = ed == 0xffffffffu ? 0.0 : trans[ed];
+            }
+            xt = xe == 0xffffffffu ? 0.0 : trans[xe];
+            staged_x = hx;
+        }
+        if (pk != PREV_SLAB) {
+            const double v0 = pk == PREV_B_INIT ? lp.p_end : 0.0;
+#pragma unroll
+            for (int q = 0; q < RS_PER_LANE; q++)
+                if ((cmask >> (16 + q)) & 1) { const int pos = 32 * q + lane; rm[pos] = v0; ri[pos] = v0; re[pos] = 0; }
+            __syncwarp();
+        }
+        double pm[RS_PER_LANE], pi[RS_PER_LANE]; int pe[RS_PER_LANE];
+        int elo = EXP_NONE_LO_, ehi = EXP_NONE_HI_;
+#pragma unroll
+        for (int k = 0; k < RS_PER_LANE; k++) {
+            const int pos = RS_PER_LANE * lane + k;
+            pm[k] = rm[pos]; pi[k] = ri[pos]; pe[k] = re[pos];
+            if (pm[k] + pi[k] != 0.0) { elo = pe[k] < elo ? pe[k] : elo; ehi = pe[k] > ehi ? pe[k] : ehi; }
+        }
+        elo = __reduce_min_sync(0xffffffffu, elo); ehi = __reduce_max_sync(0xffffffffu, ehi);
+        const unsigned long long out_ptr = js0->out_ptr;
+        double* om = (double*)out_ptr; double* oi = om + Np; double* od = oi + Np; int* oe = (int*)(od + Np);
+        if (ehi == EXP_NONE_HI_) {  // nothing but zeros flows into this tile: both rows are zero here
+            prefetch_next();
+            for (uint32_t j = lane; j < ncore; j += 32) { om[g0 + j] = 0.0; oi[g0 + j] = 0.0; od[g0 + j] = 0.0; oe[g0 + j] = 0; }
+            if (lane < 2) { partials[((size_t)job_idx * n_tiles + c) * 2 + lane] = xf_zero(); if (valid2) partials[prow + ((size_t)job_idx * n_tiles + c) * 2 + lane] = xf_zero(); }
+            continue;
+        }
+        if (ehi - elo > span2) {
+            prefetch_next();
+            if (lane == 0) *redo = 1;
+            continue;
+        }
+        const int Eref = ehi;
+#pragma unroll
+        for (int k = 0; k < RS_PER_LANE; k++) { const double sc_ = pow2i(pe[k] - Eref); pm[k] *= sc_; pi[k] *= sc_; }
+        prefetch_next();
+        double cm[RS_PER_LANE], ci[RS_PER_LANE], dacc[RS_PER_LANE], dcur[RS_PER_LANE];
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            const unsigned int x = ((pass ? js1 : js0)->base >> 1) & 3;
+            // next-base row: pm := e_l(x) m''[l]  (every use of m'' is multiplied by the emission of that node)
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) pm[k] *= (((emc >> (3 * k)) & 7) == x ? lp.p_match : lp.p_mismatch);
+            RS_STAGE(sa, pm);
+            __syncwarp();
+            // bd0 (backward.rs:354-377)
+            {
+                double x0 = 0.0;
+                if (tile_has_x) x0 = xt * lp.p_DM * sa[xp];
+                if (tile_has_xx && ext0) x0 += RS_EXTRAS0(sa, sa, sa, lp.p_DM, 0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    double acc = tr[k] * lp.p_DM * RS_UP(pm, sa, k);
+                    if (k == 0) acc += x0;
+                    acc += lp.p_DI * lp.p_random * pi[k];
+                    dcur[k] = acc; dacc[k] = acc;
+                }
+            }
+            RS_STAGE(sc, dcur);
+            __syncwarp();
+            // bdt x 4 (backward.rs:387-404): copies alternate between sc and sb (sa keeps e m'' for bm / bi)
+#pragma unroll
+            for (int t = 1; t < N_DEL_ROUNDS; t++) {
+                double* prevbuf = (t & 1) ? sc : sb; double* curbuf = (t & 1) ? sb : sc;
+                double x0 = 0.0;
+                if (tile_has_x) x0 = xt * lp.p_DD * prevbuf[xp];
+                if (tile_has_xx && ext0) x0 += RS_EXTRAS0(prevbuf, prevbuf, prevbuf, lp.p_DD, 0.0, 0.0);
+#pragma unroll
+                for (int k = RS_PER_LANE - 1; k >= 0; k--) {
+                    double v = tr[k] * lp.p_DD * RS_UP(dcur, prevbuf, k);
+                    if (k == 0) v += x0;
+                    dcur[k] = v; dacc[k] += v;
+                }
+                if (t < N_DEL_ROUNDS - 1) RS_STAGE(curbuf, dcur);
+                __syncwarp();
+            }
+            // d of the source positions into sc, then bm / bi (backward.rs:423-483)
+            RS_STAGE(sc, dacc);
+            __syncwarp();
+            {
+                double xm = 0.0, xi_ = 0.0;
+                if (tile_has_x) { xm = xt * (lp.p_MM * sa[xp] + lp.p_MD * sc[xp]); xi_ = xt * (lp.p_IM * sa[xp] + lp.p_ID * sc[xp]); }
+                if (tile_has_xx && ext0) {
+                    xm += RS_EXTRAS0(sa, sc, sc, lp.p_MM, lp.p_MD, 0.0);
+                    xi_ += RS_EXTRAS0(sa, sc, sc, lp.p_IM, lp.p_ID, 0.0);
+                }
+#pragma unroll
+                for (int k = 0; k < RS_PER_LANE; k++) {
+                    const double um = RS_UP(pm, sa, k), ud = RS_UP(dacc, sc, k);
+                    double am = tr[k] * (lp.p_MM * um + lp.p_MD * ud), ai = tr[k] * (lp.p_IM * um + lp.p_ID * ud);
+                    if (k == 0) { am += xm; ai += xi_; }
+                    cm[k] = am + lp.p_MI * lp.p_random * pi[k];
+                    ci[k] = ai + lp.p_II * lp.p_random * pi[k];
+                }
+            }
+            // begin sums of this row over the core: init_l (p_XM e_l(x) m''[l] + p_XD d[l])  (backward.rs:499-555)
+            double part = 0.0, part2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++)
+                if ((cmask >> k) & 1) { const double in = sinit[32 * k + lane]; part += (pm[k] * lp.p_MM + dacc[k] * lp.p_MD) * in; part2 += (pm[k] * lp.p_IM + dacc[k] * lp.p_ID) * in; }
+            for (int o = 16; o; o >>= 1) { part += __shfl_down_sync(0xffffffffu, part, o); part2 += __shfl_down_sync(0xffffffffu, part2, o); }
+            if (lane == 0) {
+                XF* pp = partials + (pass ? prow : 0) + ((size_t)job_idx * n_tiles + c) * 2;
+                pp[0] = xf(part, Eref); pp[1] = xf(part2, Eref);
+            }
+            __syncwarp();   // sa / sc have been read by every lane
+            if (pass == 1 || !valid2) break;
+#pragma unroll
+            for (int k = 0; k < RS_PER_LANE; k++) { pm[k] = cm[k]; pi[k] = ci[k]; }
+        }
+        // ---- pack the owned cells, stage position-indexed, store the core coalesced
+#pragma unroll
+        for (int k = 0; k < RS_PER_LANE; k++) {
+            const int pos = RS_PER_LANE * lane + k;
+            const double m = cm[k], i = ci[k], d = dacc[k];
+            const double mx = fmax(m, fmax(i, d));
+            int qx = 0; double scl = 0.0;
+            if (mx != 0.0) { qx = ilogb_pos(mx); scl = pow2i(-qx); }
+            sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = mx != 0.0 ? Eref + qx : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < RS_PER_LANE; q++) {
+            const int pos = 32 * q + lane;
+            if ((cmask >> (8 + q)) & 1) {
+                const uint32_t g = sion[pos];
+                om[g] = sa[pos]; oi[g] = sb[pos]; od[g] = sc[pos]; oe[g] = se[pos];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ top-k selection
 // Key of a cell: (T, mantissa, ~original id) with merged value v = (m+i+d) * 2^ex = mant * 2^T, mant in [1,2).
 // Exact ordering of the linear values; ties -> lower ORIGINAL node index first (the dense SparseVec iterates in
@@ -1557,6 +1792,7 @@ int dense_configure(dbgphmm_model* m) {
     CUDA_TRY(cudaFuncSetAttribute(k_dense_reg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_reg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, RS2_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_dense_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, RS2_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SELECT_SMEM_BYTES));
@@ -1618,8 +1854,42 @@ static int fast_span2(const LinParams& lp) {
     if (const char* f = getenv("DBGPHMM_DENSE_SPAN2")) { int v = atoi(f); if (v > 0 && v < span) return v; }   // tests: force the fallback
     return span < 64 ? -1 : (span > 900 ? 900 : span);
 }
-bool dense_can_pair(const dbgphmm_model* m) { return m->fwd2.n_chunks > 0 && use_reg_kernel() && fast_span2(m->lin) > 0; }
-uint32_t dense_pair_tiles(const dbgphmm_model* m) { return m->fwd2.n_chunks; }
+bool dense_can_pair(const dbgphmm_model* m) { return m->fwd2.n_chunks > 0 && m->bwd2.n_chunks > 0 && use_reg_kernel() && fast_span2(m->lin) > 0; }
+uint32_t dense_pair_tiles(const dbgphmm_model* m, int dir) { return dir == 0 ? m->fwd2.n_chunks : m->bwd2.n_chunks; }
+
+// backward rows first_row - s and first_row - s - 1 of every job in one launch ; d_partials holds [2][n_jobs][bwd2.n_chunks][2]
+int dense_backward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, const uint8_t* d_bases,
+                        RowDesc* d_desc, XF* d_partials, int* d_redo, uint64_t pair_cells, bool second) {
+    const uint32_t nt = m->bwd2.n_chunks;
+    const uint32_t jpc = fast_jobs_per_cta(m, nt, n_jobs);
+    dim3 grid((nt + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
+    ST_TRY(ensure_jstep(m, 2 * n_jobs));
+    k_dense_prep2<false><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+    COUNT_LAUNCH();
+    launch_timer_begin(m->stream);
+    k_dense_bwd2<<<grid, WT_WARPS * 32, RS2_SMEM_BYTES, m->stream>>>(plan_view(m->bwd2), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+                                                                      d_partials, nt, fast_span2(m->lin), d_redo, jpc);
+    launch_timer_end(m->stream, pair_cells);
+    COUNT_LAUNCH();
+    k_dense_bwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, nullptr, d_partials, nt, 1);
+    COUNT_LAUNCH();
+    if (second) {
+        k_dense_bwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s + 1, d_desc, nullptr, d_partials + (size_t)n_jobs * nt * 2, nt, 1);
+        COUNT_LAUNCH();
+    }
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}
+
+// backward step restricted to the (job, tile) pairs of a prebuilt worklist (recompute pass of the stream strategy), no row reduction
+int dense_backward_step_list(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t s, const uint8_t* d_bases, XF* d_partials,
+                             const unsigned long long* d_worklist) {
+    k_dense_bwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, nullptr,
+                                                                             pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks, d_worklist);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
+}
 
 // forward rows s and s + 1 of every job in one launch (see k_dense_fwd2) ; d_partials holds [2][n_jobs][fwd2.n_chunks]
 int dense_forward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, const uint8_t* d_bases,

@@ -60,9 +60,13 @@ int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
 // Pair p = s / 2 reads slab0 + ((p - 1) & 1) and writes slab0 + (p & 1).  *d_redo is raised if some tile's exponent range does
 // not fit the two-row frame: the caller then repeats the phase with single-row steps.  second: some job has a row s + 1.
 bool dense_can_pair(const dbgphmm_model* m);
-uint32_t dense_pair_tiles(const dbgphmm_model* m);
+uint32_t dense_pair_tiles(const dbgphmm_model* m, int dir);
 int dense_forward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, const uint8_t* d_bases,
                        RowDesc* d_desc, XF* d_partials, int* d_redo, uint64_t pair_cells, bool second);
+int dense_backward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, const uint8_t* d_bases,
+                        RowDesc* d_desc, XF* d_partials, int* d_redo, uint64_t pair_cells, bool second);
+int dense_backward_step_list(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t s, const uint8_t* d_bases, XF* d_partials,
+                             const unsigned long long* d_worklist);
 
 // forward step restricted to the (job, tile) pairs of a prebuilt worklist (recompute pass of the stream strategy);
 // no row reduction: the rows' scalars are taken from the descriptors written by the first pass.

@@ -296,7 +296,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     ST_TRY(dev_upload(b_len, out->len, st));
     // two rows per launch when nothing reads the intermediate rows (ping-pong slabs, no per-row products, fixed warm-up)
     bool paired = !keep_rows && !opt.step && (kind == DBGPHMM_FWD_SPARSE || kind == DBGPHMM_FWD_DENSE) && steps >= 2 && dense_can_pair(m);
-    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * std::max<size_t>(m->fwd.n_chunks, paired ? 2 * (size_t)dense_pair_tiles(m) : 0)));
+    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * std::max<size_t>(m->fwd.n_chunks, paired ? 2 * (size_t)dense_pair_tiles(m, 0) : 0)));
     DevBuf b_wl, b_redo;
     ST_TRY(b_redo.alloc(sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(b_redo.p, 0, sizeof(int), st));
@@ -451,18 +451,36 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     DevBuf b_dj, b_len, b_part, b_top_ids, b_top_cnt, b_reqs;
     ST_TRY(dev_upload(b_dj, dj, st));
     ST_TRY(dev_upload(b_len, out->len, st));
-    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * m->bwd.n_chunks));
-    DevBuf b_wl;
+    // two rows per launch when nothing reads the intermediate rows (see run_forward)
+    bool paired = !keep_rows && !opt.step && kind == DBGPHMM_BWD_SPARSE && steps >= 2 && dense_can_pair(m);
+    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * std::max<size_t>(m->bwd.n_chunks, paired ? 2 * (size_t)dense_pair_tiles(m, 1) : 0)));
+    DevBuf b_wl, b_redo;
+    ST_TRY(b_redo.alloc(sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(b_redo.p, 0, sizeof(int), st));
     ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * m->bwd.n_chunks + 1)));
     ST_TRY(b_top_ids.alloc(sizeof(uint32_t) * (size_t)J * MAX_ACTIVE));
     ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
     CUDA_TRY(cudaMemsetAsync(b_top_cnt.p, 0, sizeof(uint32_t) * J, st));
-    auto slab_of_h = [&](uint32_t j, uint32_t s) { return dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    auto slab_of_h = [&](uint32_t j, uint32_t s) { return paired ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
 
     auto dense_phase = [&]() -> int {
         HostTrace t("  bwd dense phase");
         EvTimer tm(st, &g_times.dense_ms);
-        for (uint32_t s = 0; s < steps; s++) {
+        if (paired) {
+            for (uint32_t s = 0; s < steps; s += 2) {
+                uint64_t live = 0;
+                for (uint32_t j = 0; j < J; j++) live += (s < out->nd[j]) + (s + 1 < out->nd[j]);
+                ST_TRY(dense_backward_pair(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, b_part.as<XF>(), b_redo.as<int>(), live * N, s + 1 < steps));
+            }
+            int redo = 0;
+            CUDA_TRY(cudaMemcpyAsync(&redo, b_redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (redo) {
+                if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] backward dense phase repeated with single-row steps\n");
+                paired = false;
+            }
+        }
+        for (uint32_t s = 0; s < steps && !paired; s++) {
             uint64_t live = 0;
             for (uint32_t j = 0; j < J; j++) live += s < out->nd[j];
             ST_TRY(dense_backward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));
@@ -573,6 +591,66 @@ __global__ void k_roi_compact(uint32_t n_jobs, uint32_t n_tiles, const unsigned 
             unsigned long long w = atomicAdd(worklist, 1ull);
             worklist[1 + w] = ((unsigned long long)(i / n_tiles) << 32) | (unsigned long long)(i % n_tiles);
         }
+}
+
+// mark the backward tiles whose rows [n - W, n - 1] are needed at the nodes of the sparse forward rows they pair with
+__global__ void k_roi_mark_b(uint32_t W, const RowDesc* __restrict__ fdesc, const uint64_t* __restrict__ fdesc0, const uint32_t* __restrict__ len,
+                             const char* __restrict__ farena, const uint32_t* __restrict__ tile_of, const uint32_t* __restrict__ roi_off,
+                             const uint32_t* __restrict__ roi_tile, uint32_t n_tiles, unsigned char* __restrict__ mark) {
+    const uint32_t j = blockIdx.y, s = blockIdx.x;   // backward row n - 1 - s pairs with forward row n - 2 - s
+    const uint32_t n = len[j];
+    if (s >= W || s + 2 > n) return;
+    const RowDesc r = fdesc[fdesc0[j] + (n - 2 - s)];
+    if (r.kind != ROW_SPARSE) return;
+    const uint32_t* id = (const uint32_t*)(farena + r.off + 24ull * r.n_ent);
+    for (uint32_t e = threadIdx.x; e < r.n_ent; e += blockDim.x) {
+        uint32_t tl = tile_of[id[e]];
+        for (uint32_t a = roi_off[tl]; a < roi_off[tl + 1]; a++) mark[(size_t)j * n_tiles + roi_tile[a]] = 1;
+    }
+}
+
+// Stream strategy, backward warm-up rows x sparse forward rows: the dense backward rows are recomputed inside the dependency cone of
+// the forward rows' node sets and multiplied on the fly (mirror of run_forward_recompute ; lets the main backward pass run two rows
+// per launch without ever writing the intermediate rows).
+int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
+                           const StepProducts& sp) {
+    HostTrace tr("run_backward_recompute");
+    cudaStream_t st = m->stream;
+    const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup, T = m->bwd.n_chunks;
+    ST_TRY(model_ensure_roi(m));
+    EvTimer tm(st, &g_times.dense_ms);
+    std::vector<DJob> dj(J);
+    for (uint32_t j = 0; j < J; j++) {
+        DJob& d = dj[j];
+        d.x = jobs[j].x; d.len = jobs[j].len; d.base_off = jobs[j].base_off; d.n_steps = std::min<uint32_t>(jobs[j].len, W); d.first_row = (int32_t)jobs[j].len - 1;
+        d.prev0_kind = PREV_B_INIT; d.prev0_slab = 0; d.slab0 = 2ull * j; d.slab_mod = 2; d.desc0 = B.desc0[j]; d.active_idx = -1;
+    }
+    DensePool pool;
+    pool.Np = (N + 1) & ~1u; pool.slab_bytes = dense_slab_bytes(N); pool.n_slabs = 2ull * J;
+    DevBuf b_pool, b_dj, b_len, b_mark, b_wl, b_part;
+    ST_TRY(b_pool.alloc(pool.slab_bytes * pool.n_slabs)); pool.base = b_pool.as<char>();
+    ST_TRY(dev_upload(b_dj, dj, st)); ST_TRY(dev_upload(b_len, F.len, st));
+    ST_TRY(b_mark.alloc((size_t)J * T));
+    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * T + 1)));
+    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * T));
+    CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)J * T, st));
+    CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * pool.n_slabs, st));   // cells outside the cone read as zero
+    {
+        dim3 g(W, J);
+        k_roi_mark_b<<<g, 128, 0, st>>>(W, F.d_desc, F.d_desc0, b_len.as<uint32_t>(), F.arena.base, m->d_tile_of_b, m->d_roi_off_b, m->d_roi_tile_b, T,
+                                        b_mark.as<unsigned char>());
+        COUNT_LAUNCH();
+        k_roi_compact<<<4 * m->n_sm, 256, 0, st>>>(J, T, b_mark.as<unsigned char>(), b_wl.as<unsigned long long>());
+        COUNT_LAUNCH();
+    }
+    for (uint32_t s = 0; s < W; s++) {
+        ST_TRY(dense_backward_step_list(m, pool, b_dj.as<DJob>(), s, d_bases, b_part.as<XF>(), b_wl.as<unsigned long long>()));
+        ST_TRY(step_products(m, sp, pool, b_dj.as<DJob>(), J, s, 1));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
 }
 
 int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,

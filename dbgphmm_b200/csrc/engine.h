@@ -119,6 +119,8 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
 // (forward dense row, backward sparse row) products there.  F supplies the row scalars of the first pass.
 int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
                           const StepProducts& sp);
+int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
+                          const StepProducts& sp);
 int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir);
 // sum over rows of F (x) B / P into d_freqs (device, ORIGINAL node order, added to); status ZERO_PROB if some P == 0
 // mapx.cu: forward_with_mapping_score_only for groups of candidates X of one read

@@ -355,6 +355,7 @@ int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* 
         const char* e = getenv("DBGPHMM_DENSE_FUSE");
         if (!(e && e[0] == '0')) {
             if (build_plan(m->fwd2, N, m->par_off, m->par_node, m->par_eid, 2 * HALO_HOPS) != DBGPHMM_OK) free_plan(m->fwd2);
+            if (build_plan(m->bwd2, N, m->chi_off, m->chi_node, m->chi_eid, 2 * HALO_HOPS) != DBGPHMM_OK) free_plan(m->bwd2);
         }
     }
     return DBGPHMM_OK;
@@ -375,16 +376,11 @@ int model_upload_probs(dbgphmm_model* m, const double* log_init, const double* l
     return DBGPHMM_OK;
 }
 
-int model_ensure_roi(dbgphmm_model* m) {
-    const uint32_t W = m->params.n_warmup;
-    if (m->d_roi_off && m->roi_warmup == W) return DBGPHMM_OK;
-    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of);
-    m->d_roi_off = m->d_roi_tile = m->d_tile_of = nullptr;
-    const std::vector<uint32_t>& cs = m->fwd.h_chunk_start;
-    const uint32_t T = m->fwd.n_chunks, N = m->N;
+// tiles that intersect the closure of each tile's nodes over `hops` upstream hops (up_* = parents: forward tiles ; children: backward)
+static int build_roi(const std::vector<uint32_t>& cs, uint32_t T, uint32_t N, uint32_t hops, const std::vector<uint32_t>& up_off,
+                     const std::vector<uint32_t>& up_node, uint32_t** d_off, uint32_t** d_tile, uint32_t** d_tile_of) {
     std::vector<uint32_t> tile_of(N);
     for (uint32_t t = 0; t < T; t++) for (uint32_t v = cs[t]; v < cs[t + 1]; v++) tile_of[v] = t;
-    const uint32_t hops = HALO_HOPS * W;
     std::vector<uint32_t> roi_off(1, 0), roi_tile, stamp(N, 0xffffffffu), tstamp(T, 0xffffffffu), frontier, next;
     for (uint32_t t = 0; t < T; t++) {
         frontier.clear();
@@ -393,8 +389,8 @@ int model_ensure_roi(dbgphmm_model* m) {
         for (uint32_t h = 0; h < hops && !frontier.empty(); h++) {
             next.clear();
             for (uint32_t v : frontier)
-                for (uint32_t a = m->par_off[v]; a < m->par_off[v + 1]; a++) {
-                    uint32_t u = m->par_node[a];
+                for (uint32_t a = up_off[v]; a < up_off[v + 1]; a++) {
+                    uint32_t u = up_node[a];
                     if (stamp[u] != t) {
                         stamp[u] = t; next.push_back(u);
                         uint32_t tu = tile_of[u];
@@ -405,7 +401,18 @@ int model_ensure_roi(dbgphmm_model* m) {
         }
         roi_off.push_back((uint32_t)roi_tile.size());
     }
-    ST_TRY(upload(&m->d_roi_off, roi_off)); ST_TRY(upload(&m->d_roi_tile, roi_tile)); ST_TRY(upload(&m->d_tile_of, tile_of));
+    ST_TRY(upload(d_off, roi_off)); ST_TRY(upload(d_tile, roi_tile)); ST_TRY(upload(d_tile_of, tile_of));
+    return DBGPHMM_OK;
+}
+
+int model_ensure_roi(dbgphmm_model* m) {
+    const uint32_t W = m->params.n_warmup;
+    if (m->d_roi_off && m->roi_warmup == W) return DBGPHMM_OK;
+    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of);
+    cudaFree(m->d_roi_off_b); cudaFree(m->d_roi_tile_b); cudaFree(m->d_tile_of_b);
+    m->d_roi_off = m->d_roi_tile = m->d_tile_of = m->d_roi_off_b = m->d_roi_tile_b = m->d_tile_of_b = nullptr;
+    ST_TRY(build_roi(m->fwd.h_chunk_start, m->fwd.n_chunks, m->N, HALO_HOPS * W, m->par_off, m->par_node, &m->d_roi_off, &m->d_roi_tile, &m->d_tile_of));
+    ST_TRY(build_roi(m->bwd.h_chunk_start, m->bwd.n_chunks, m->N, HALO_HOPS * W, m->chi_off, m->chi_node, &m->d_roi_off_b, &m->d_roi_tile_b, &m->d_tile_of_b));
     m->roi_warmup = W;
     return DBGPHMM_OK;
 }
@@ -414,11 +421,12 @@ void model_free(dbgphmm_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of); cudaFree(m->d_jstep);
+    cudaFree(m->d_roi_off_b); cudaFree(m->d_roi_tile_b); cudaFree(m->d_tile_of_b);
     cudaFree(m->d_pos_of); cudaFree(m->d_orig_of); cudaFree(m->d_emission);
     cudaFree(m->d_par_off); cudaFree(m->d_par_node); cudaFree(m->d_par_eid);
     cudaFree(m->d_chi_off); cudaFree(m->d_chi_node); cudaFree(m->d_chi_eid);
     cudaFree(m->d_init); cudaFree(m->d_trans);
-    free_plan(m->fwd); free_plan(m->bwd); free_plan(m->fwd2);
+    free_plan(m->fwd); free_plan(m->bwd); free_plan(m->fwd2); free_plan(m->bwd2);
     cache_trim();
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->stream_aux) cudaStreamDestroy(m->stream_aux);

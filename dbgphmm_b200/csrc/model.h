@@ -86,11 +86,12 @@ struct dbgphmm_model {
     double* d_init = nullptr;   // [n_batch][N] linear, relabelled node order
     double* d_trans = nullptr;  // [n_batch][E] linear, original EdgeIndex order
     DevPlan fwd, bwd;
-    DevPlan fwd2;   // forward tiles with a 2 x HALO_HOPS halo (two rows per launch) ; n_chunks == 0: not available
+    DevPlan fwd2, bwd2;   // tiles with a 2 x HALO_HOPS halo (two rows per launch) ; n_chunks == 0: not available
     // Recompute support for the stream strategy: for every forward tile the tiles that intersect the upstream closure of
     // its nodes within HALO_HOPS * n_warmup hops (the dependency cone of n_warmup dense rows), built lazily.
     uint32_t roi_warmup = 0;
     uint32_t *d_roi_off = nullptr, *d_roi_tile = nullptr, *d_tile_of = nullptr;
+    uint32_t *d_roi_off_b = nullptr, *d_roi_tile_b = nullptr, *d_tile_of_b = nullptr;   // the same for backward tiles (downstream closure)
     void* d_jstep = nullptr; uint32_t jstep_cap = 0;   // per-(job, step) scalars of the dense fast kernel (dense.cu: JStep)
 };
 int model_ensure_roi(dbgphmm_model* m);
