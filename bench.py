@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-gpu", type=int, default=740, help="reads per GPU per step (740 = 148 SMs x 5 resident sparse jobs: one wave)")
+    ap.add_argument("--reads-per-gpu", type=int, default=1184, help="reads per GPU per step (1184 = 148 SMs x 8 resident sparse jobs: one wave)")
     ap.add_argument("--genome-len", type=int, default=1_000_000)
     ap.add_argument("--read-len", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=40)
@@ -234,16 +234,16 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (k_cells * ALGO_BYTES_PER_CELL / (k_ms * 1e-3) / 1e9) if k_ms > 0 else 0.0
         # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this command
-        # (profiles/r1_dense_reg_dram.json, tools/ncu_summary.py); scaled per cell when the launch shape differs
+        # (profiles/r1_dense_pair_dram.json, tools/ncu_summary.py); scaled per cell when the launch shape differs
         traffic = None
         try:
-            caps = json.load(open(os.path.join(ROOT, "profiles", "r1_dense_reg_dram.json")))
+            caps = json.load(open(os.path.join(ROOT, "profiles", "r1_dense_pair_dram.json")))
             per_cell = sum(c["dram_bytes_per_cell"] for c in caps) / len(caps)
             traffic = per_cell * (k_cells / max(k_launch, 1))
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "k_dense_reg<FWD>/<BWD> (+ exact worklist kernel, same timed interval)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1_dense_reg_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell x cells per launch)", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
+        roof = {"bound": "hbm", "kernel": "k_dense_fwd2 / k_dense_bwd2 (two DP rows per launch)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": "profiles/r1_dense_pair_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell x cells per launch)", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
                 "avg_launch_ms": k_ms / max(k_launch, 1), "launches": k_launch, "cells_per_launch": k_cells / max(k_launch, 1),
                 "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "kernel_share_of_step": k_ms / max(tot_ms, 1e-9)}
         out = {"metric": "PHMM forward-backward GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

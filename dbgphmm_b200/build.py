@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdbgphmm_b200.so")
-SOURCES = ["model.cu", "dense.cu", "sparse.cu", "mapx.cu", "engine.cu", "products.cu", "api.cu"]
+SOURCES = ["model.cu", "dense.cu", "sparse.cu", "mapx.cu", "engine.cu", "products.cu", "api.cu", "formats.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [_nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lcudart", "-lz"]
         subprocess.check_call(cmd, env=env)
     return LIB
 

@@ -1,0 +1,395 @@
+// formats.cu — DBG and MAP text formats of the reference, host side only (no kernels): the data formats either side of the
+// hot path.  A .dbg written by a dbgphmm run becomes the node-centric PHMM graph + copy numbers the device
+// path consumes; candidate copy-number vectors X over COMPACT edges (what the posterior sampler of multi_dbg/posterior.rs
+// proposes) expand to the per-k-mer copy numbers dbgphmm_model_set_copy_nums_batch takes; Mappings round-trip through .map.
+//   DBG  : MultiDbg::to_dbg_writer / from_dbg_reader          multi_dbg/output.rs:155-345   (README.md "DBG")
+//   MAP  : MultiDbg::to_map_writer / from_map_reader_raw      multi_dbg/output.rs:455-623
+//   graph: MultiDbg::to_node_centric_graph(add_terminal=false) multi_dbg.rs:1551-1604 via to_seq_graph :1370-1390
+//   X    : MultiDbg::set_copy_nums                             multi_dbg.rs:1041-1052
+// gzip (.dbg.gz / .dbz / .map.gz / .mpz, output.rs:135-139,473-477) goes through zlib.
+#include <zlib.h>
+#include <charconv>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "model.h"
+#include "../../include/dbgphmm_b200.h"
+
+#define NULL_BASE 'n'   // common.rs:21
+
+struct dbgphmm_dbg {
+    uint32_t k = 0;
+    std::vector<std::string> km1mer;                 // compact node -> (k-1)-mer ; node ids == full-graph ids of the same nodes
+    struct CEdge { uint32_t s, t; std::string kmer; uint32_t copy_num; std::vector<uint32_t> full; };
+    std::vector<CEdge> edges;                        // compact edges in EdgeIndex order
+    // full graph (from_dbg_reader, output.rs:255-300): compact nodes first, then one new node per interior base of every compact edge
+    uint32_t n_nodes_full = 0;
+    std::vector<uint8_t> full_terminal;              // per full node
+    std::vector<uint32_t> fsrc, fdst, fcompact;      // per full edge (== PHMM node): endpoints, owning compact edge
+    std::vector<uint8_t> fbase;
+    // node-centric PHMM edges in the reference's insertion order
+    std::vector<uint32_t> psrc, pdst;
+};
+
+static bool ends_with(const std::string& s, const char* suf) {
+    size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+static bool is_gz_path(const std::string& p) { return ends_with(p, ".gz") || ends_with(p, ".dbz") || ends_with(p, ".mpz"); }
+
+static int read_file(const char* path, std::string* out) {
+    out->clear();
+    gzFile f = gzopen(path, "rb");   // transparently reads plain files as well
+    if (!f) { dbg_set_error(std::string("cannot open ") + path); return DBGPHMM_ERR_INVALID; }
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(f, buf, sizeof(buf))) > 0) out->append(buf, (size_t)n);
+    gzclose(f);
+    if (n < 0) { dbg_set_error(std::string("read error in ") + path); return DBGPHMM_ERR_INVALID; }
+    return DBGPHMM_OK;
+}
+static int write_file(const char* path, const std::string& text) {
+    if (is_gz_path(path)) {
+        gzFile f = gzopen(path, "wb");
+        if (!f) { dbg_set_error(std::string("cannot create ") + path); return DBGPHMM_ERR_INVALID; }
+        size_t off = 0;
+        while (off < text.size()) {
+            int n = gzwrite(f, text.data() + off, (unsigned)std::min<size_t>(text.size() - off, 1u << 30));
+            if (n <= 0) { gzclose(f); dbg_set_error(std::string("write error in ") + path); return DBGPHMM_ERR_INVALID; }
+            off += (size_t)n;
+        }
+        gzclose(f);
+        return DBGPHMM_OK;
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) { dbg_set_error(std::string("cannot create ") + path); return DBGPHMM_ERR_INVALID; }
+    size_t w = fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+    if (w != text.size()) { dbg_set_error(std::string("write error in ") + path); return DBGPHMM_ERR_INVALID; }
+    return DBGPHMM_OK;
+}
+
+// whitespace-separated fields of one line (split_whitespace, output.rs:211,216,...)
+static void split_ws(const std::string& line, std::vector<std::string>* out) {
+    out->clear();
+    size_t i = 0, n = line.size();
+    while (i < n) {
+        while (i < n && isspace((unsigned char)line[i])) i++;
+        size_t j = i;
+        while (j < n && !isspace((unsigned char)line[j])) j++;
+        if (j > i) out->push_back(line.substr(i, j - i));
+        i = j;
+    }
+}
+static bool parse_u32(const std::string& s, uint32_t* v) {
+    if (s.empty()) return false;
+    char* e = nullptr;
+    unsigned long long x = strtoull(s.c_str(), &e, 10);
+    if (*e || x > 0xffffffffull) return false;
+    *v = (uint32_t)x;
+    return true;
+}
+
+static int dbg_finish(dbgphmm_dbg* d) {
+    const uint32_t nc = (uint32_t)d->km1mer.size();
+    uint64_t n_bases = 0;
+    for (auto& e : d->edges) n_bases += e.full.size();
+    if (n_bases >= 0xffffffffull) { dbg_set_error("dbg: too many k-mers"); return DBGPHMM_ERR_INVALID; }
+    d->full_terminal.clear();
+    for (auto& s : d->km1mer) {
+        bool term = true;
+        for (char c : s) term = term && c == NULL_BASE;
+        d->full_terminal.push_back(term ? 1 : 0);
+    }
+    const uint32_t NE = (uint32_t)n_bases;
+    d->fsrc.assign(NE, 0xffffffffu); d->fdst.assign(NE, 0); d->fbase.assign(NE, 0); d->fcompact.assign(NE, 0);
+    uint32_t next_node = nc;
+    for (uint32_t ce = 0; ce < d->edges.size(); ce++) {
+        auto& e = d->edges[ce];
+        if (e.s >= nc || e.t >= nc) { dbg_set_error("dbg: edge endpoint is not a node"); return DBGPHMM_ERR_INVALID; }
+        const size_t n = e.full.size();
+        const std::string seq = e.kmer.substr(d->k - 1);
+        uint32_t prev = e.s;
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t fe = e.full[i];
+            if (fe >= NE || d->fsrc[fe] != 0xffffffffu) { dbg_set_error("dbg: index of edge in full is wrong"); return DBGPHMM_ERR_INVALID; }
+            const uint32_t v = prev;
+            uint32_t w;
+            if (i == n - 1) w = e.t; else { w = next_node++; d->full_terminal.push_back(0); }
+            d->fsrc[fe] = v; d->fdst[fe] = w; d->fbase[fe] = (uint8_t)seq[i]; d->fcompact[fe] = ce;
+            prev = w;
+        }
+    }
+    d->n_nodes_full = next_node;
+    // node-centric graph: PHMM node = full edge ; for every non-terminal full node in index order, parents x children nested,
+    // each adjacency list newest-edge-first (petgraph 0.6 ; edges were added in index order, output.rs:297-301)
+    std::vector<std::vector<uint32_t>> in_e(d->n_nodes_full), out_e(d->n_nodes_full);
+    for (uint32_t fe = NE; fe-- > 0;) { out_e[d->fsrc[fe]].push_back(fe); in_e[d->fdst[fe]].push_back(fe); }
+    d->psrc.clear(); d->pdst.clear();
+    for (uint32_t v = 0; v < d->n_nodes_full; v++) {
+        if (d->full_terminal[v]) continue;
+        for (uint32_t e1 : in_e[v]) for (uint32_t e2 : out_e[v]) { d->psrc.push_back(e1); d->pdst.push_back(e2); }
+    }
+    return DBGPHMM_OK;
+}
+
+extern "C" int dbgphmm_dbg_from_text(const char* text, uint64_t len, dbgphmm_dbg** out) {
+    if (!text || !out) { dbg_set_error("dbg_from_text: bad argument"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_dbg* d = new dbgphmm_dbg();
+    std::vector<std::string> f;
+    bool have_k = false;
+    size_t pos = 0;
+    int st = DBGPHMM_OK;
+    while (pos < len && st == DBGPHMM_OK) {
+        size_t eol = pos;
+        while (eol < len && text[eol] != '\n') eol++;
+        std::string line(text + pos, eol - pos);
+        pos = eol + 1;
+        if (line.empty()) continue;   // (the reference unwraps chars().nth(0) and panics on an empty line ; tolerated here)
+        const char c0 = line[0];
+        if (c0 == 'K') {
+            split_ws(line, &f);
+            if (f.size() < 2 || !parse_u32(f[1], &d->k) || d->k < 2) { dbg_set_error("dbg: bad K line"); st = DBGPHMM_ERR_INVALID; }
+            have_k = true;
+        } else if (c0 == 'N') {
+            split_ws(line, &f);
+            uint32_t id;
+            if (f.size() < 3 || !parse_u32(f[1], &id)) { dbg_set_error("dbg: bad N line"); st = DBGPHMM_ERR_INVALID; break; }
+            if (id != d->km1mer.size()) { dbg_set_error("dbg: node is not sorted"); st = DBGPHMM_ERR_INVALID; break; }
+            d->km1mer.push_back(f[2]);
+        } else if (c0 == 'E') {
+            if (!have_k) { dbg_set_error("dbg: E line before K"); st = DBGPHMM_ERR_INVALID; break; }
+            split_ws(line, &f);
+            dbgphmm_dbg::CEdge e;
+            uint32_t id;
+            if (f.size() < 7 || !parse_u32(f[1], &id) || !parse_u32(f[2], &e.s) || !parse_u32(f[3], &e.t) || !parse_u32(f[5], &e.copy_num)) {
+                dbg_set_error("dbg: bad E line"); st = DBGPHMM_ERR_INVALID; break;
+            }
+            if (id != d->edges.size()) { dbg_set_error("dbg: edge is not sorted"); st = DBGPHMM_ERR_INVALID; break; }
+            e.kmer = f[4];
+            size_t p = 0;
+            const std::string& lst = f[6];
+            while (p <= lst.size()) {
+                size_t q = lst.find(',', p);
+                if (q == std::string::npos) q = lst.size();
+                uint32_t v;
+                if (!parse_u32(lst.substr(p, q - p), &v)) { dbg_set_error("dbg: bad edge id list"); st = DBGPHMM_ERR_INVALID; break; }
+                e.full.push_back(v);
+                p = q + 1;
+            }
+            if (st != DBGPHMM_OK) break;
+            if (e.kmer.size() < d->k || e.kmer.size() - (d->k - 1) != e.full.size()) {
+                dbg_set_error("dbg: length of seq and edges_in_full is different"); st = DBGPHMM_ERR_INVALID; break;
+            }
+            d->edges.push_back(std::move(e));
+        }   // '#' and anything else: ignored (output.rs:250-251)
+    }
+    if (st == DBGPHMM_OK && !have_k) { dbg_set_error("dbg: no K section"); st = DBGPHMM_ERR_INVALID; }
+    if (st == DBGPHMM_OK) st = dbg_finish(d);
+    if (st != DBGPHMM_OK) { delete d; return st; }
+    *out = d;
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_dbg_from_file(const char* path, dbgphmm_dbg** out) {
+    if (!path || !out) { dbg_set_error("dbg_from_file: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::string text;
+    ST_TRY(read_file(path, &text));
+    return dbgphmm_dbg_from_text(text.data(), text.size(), out);
+}
+extern "C" void dbgphmm_dbg_destroy(dbgphmm_dbg* d) { delete d; }
+
+extern "C" int dbgphmm_dbg_sizes(const dbgphmm_dbg* d, uint32_t sizes[6]) {
+    if (!d || !sizes) { dbg_set_error("dbg_sizes: bad argument"); return DBGPHMM_ERR_INVALID; }
+    sizes[0] = d->k; sizes[1] = d->n_nodes_full; sizes[2] = (uint32_t)d->fsrc.size(); sizes[3] = (uint32_t)d->km1mer.size();
+    sizes[4] = (uint32_t)d->edges.size(); sizes[5] = (uint32_t)d->psrc.size();
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_dbg_phmm_graph(const dbgphmm_dbg* d, uint32_t* edge_src, uint32_t* edge_dst, uint8_t* emission, uint32_t* copy_nums,
+                                      uint32_t* compact_edge_of) {
+    if (!d) { dbg_set_error("dbg_phmm_graph: bad argument"); return DBGPHMM_ERR_INVALID; }
+    if (edge_src) memcpy(edge_src, d->psrc.data(), 4 * d->psrc.size());
+    if (edge_dst) memcpy(edge_dst, d->pdst.data(), 4 * d->pdst.size());
+    if (emission) memcpy(emission, d->fbase.data(), d->fbase.size());
+    if (copy_nums) for (size_t e = 0; e < d->fcompact.size(); e++) copy_nums[e] = d->edges[d->fcompact[e]].copy_num;
+    if (compact_edge_of) memcpy(compact_edge_of, d->fcompact.data(), 4 * d->fcompact.size());
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_dbg_get_copy_nums(const dbgphmm_dbg* d, uint32_t* compact_copy_nums) {
+    if (!d || !compact_copy_nums) { dbg_set_error("dbg_get_copy_nums: bad argument"); return DBGPHMM_ERR_INVALID; }
+    for (size_t e = 0; e < d->edges.size(); e++) compact_copy_nums[e] = d->edges[e].copy_num;
+    return DBGPHMM_OK;
+}
+// MultiDbg::is_copy_nums_valid (multi_dbg.rs:1008-1014): copy numbers in == out at every node (interior nodes of a compact edge
+// are balanced by construction, so the compact nodes decide)
+static bool copy_nums_valid(const dbgphmm_dbg* d, const uint32_t* x) {
+    std::vector<long long> bal(d->km1mer.size(), 0);
+    for (size_t e = 0; e < d->edges.size(); e++) { bal[d->edges[e].t] += x[e]; bal[d->edges[e].s] -= x[e]; }
+    for (long long b : bal) if (b != 0) return false;
+    return true;
+}
+extern "C" int dbgphmm_dbg_set_copy_nums(dbgphmm_dbg* d, const uint32_t* compact_copy_nums) {
+    if (!d || !compact_copy_nums) { dbg_set_error("dbg_set_copy_nums: bad argument"); return DBGPHMM_ERR_INVALID; }
+    if (!copy_nums_valid(d, compact_copy_nums)) { dbg_set_error("invalid new copy_nums"); return DBGPHMM_ERR_INVALID; }   // multi_dbg.rs:1051
+    for (size_t e = 0; e < d->edges.size(); e++) d->edges[e].copy_num = compact_copy_nums[e];
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_dbg_expand_copy_nums(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, uint32_t* full) {
+    if (!d || !compact || !full) { dbg_set_error("dbg_expand_copy_nums: bad argument"); return DBGPHMM_ERR_INVALID; }
+    const size_t Ec = d->edges.size(), N = d->fcompact.size();
+    for (uint32_t b = 0; b < n_batch; b++)
+        for (size_t e = 0; e < N; e++) full[(size_t)b * N + e] = compact[(size_t)b * Ec + d->fcompact[e]];
+    return DBGPHMM_OK;
+}
+
+static int copy_out(const std::string& s, char* buf, uint64_t cap, uint64_t* needed) {
+    if (needed) *needed = s.size();
+    if (buf && cap >= s.size()) memcpy(buf, s.data(), s.size());
+    else if (buf) { dbg_set_error("output buffer too small"); return DBGPHMM_ERR_INVALID; }
+    return DBGPHMM_OK;
+}
+static std::string dbg_text(const dbgphmm_dbg* d) {
+    std::string s;
+    s += "# dbgphmm_b200\n";   // (the reference writes its git hash and degree statistics here ; readers skip '#' lines)
+    s += "K\t" + std::to_string(d->k) + "\n";
+    for (size_t v = 0; v < d->km1mer.size(); v++) s += "N\t" + std::to_string(v) + "\t" + d->km1mer[v] + "\n";
+    for (size_t e = 0; e < d->edges.size(); e++) {
+        const auto& ce = d->edges[e];
+        s += "E\t" + std::to_string(e) + "\t" + std::to_string(ce.s) + "\t" + std::to_string(ce.t) + "\t" + ce.kmer + "\t" + std::to_string(ce.copy_num) + "\t";
+        for (size_t i = 0; i < ce.full.size(); i++) { if (i) s += ","; s += std::to_string(ce.full[i]); }
+        s += "\n";
+    }
+    return s;
+}
+extern "C" int dbgphmm_dbg_to_text(const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed) {
+    if (!d) { dbg_set_error("dbg_to_text: bad argument"); return DBGPHMM_ERR_INVALID; }
+    return copy_out(dbg_text(d), buf, cap, needed);
+}
+extern "C" int dbgphmm_dbg_to_file(const dbgphmm_dbg* d, const char* path) {
+    if (!d || !path) { dbg_set_error("dbg_to_file: bad argument"); return DBGPHMM_ERR_INVALID; }
+    return write_file(path, dbg_text(d));
+}
+
+// MultiDbg::to_phmm / to_non_zero_phmm / to_uniform_phmm (multi_dbg.rs:1391-1409): n_warmup := k, probabilities from the copy numbers
+extern "C" int dbgphmm_dbg_to_model(const dbgphmm_dbg* d, const dbgphmm_params* params, int mode, int device, uint64_t mem_budget_bytes, dbgphmm_model** out) {
+    if (!d || !params || !out || mode < 0 || mode > 2) { dbg_set_error("dbg_to_model: bad argument"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_params p = *params;
+    p.n_warmup = d->k;
+    const size_t N = d->fsrc.size(), E = d->psrc.size();
+    std::vector<double> li(N, 0.0), lt(E, 0.0);   // placeholders ; replaced by the copy-number derivation below
+    dbgphmm_model* m = nullptr;
+    ST_TRY(dbgphmm_model_create((uint32_t)N, (uint32_t)E, d->psrc.data(), d->pdst.data(), d->fbase.data(), li.data(), lt.data(), &p, device, mem_budget_bytes, &m));
+    std::vector<uint32_t> cn(N);
+    for (size_t e = 0; e < N; e++) cn[e] = d->edges[d->fcompact[e]].copy_num;
+    int st = dbgphmm_model_set_copy_nums_batch(m, 1, cn.data(), mode);
+    if (st != DBGPHMM_OK) { dbgphmm_model_destroy(m); return st; }
+    *out = m;
+    return DBGPHMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MAP
+// f64 as Rust's `{}` prints it: shortest digits that round-trip, never in exponent notation ; -inf / inf / NaN by name
+static void append_f64(std::string& s, double v) {
+    if (v != v) { s += "NaN"; return; }
+    if (v == INFINITY) { s += "inf"; return; }
+    if (v == -INFINITY) { s += "-inf"; return; }
+    char buf[800];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
+    s.append(buf, r.ptr);
+}
+static bool parse_f64(const std::string& t, double* v) {
+    if (t == "-inf") { *v = -INFINITY; return true; }
+    if (t == "inf") { *v = INFINITY; return true; }
+    if (t == "NaN") { *v = NAN; return true; }
+    char* e = nullptr;
+    *v = strtod(t.c_str(), &e);
+    return !t.empty() && *e == 0;
+}
+
+extern "C" int dbgphmm_mappings_from_map_text(const char* text, uint64_t len, dbgphmm_mappings** out) {
+    if (!text || !out) { dbg_set_error("mappings_from_map_text: bad argument"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_mappings* mp = new dbgphmm_mappings();
+    mp->read_off.push_back(0); mp->row_off.push_back(0);
+    std::vector<std::string> f;
+    uint64_t n_reads = 0, rows_in_read = 0;
+    size_t pos = 0;
+    auto fail = [&](const char* msg) { dbg_set_error(msg); delete mp; return DBGPHMM_ERR_INVALID; };
+    while (pos < len) {
+        size_t eol = pos;
+        while (eol < len && text[eol] != '\n') eol++;
+        std::string line(text + pos, eol - pos);
+        pos = eol + 1;
+        if (line.empty() || line[0] == '#') continue;
+        split_ws(line, &f);
+        uint32_t i, j;
+        if (f.size() < 3 || !parse_u32(f[0], &i) || !parse_u32(f[1], &j)) return fail("map: bad line");
+        // rows arrive read by read, base by base (the reference asserts ret.len() == i + 1 and ret[i].len() == j + 1, output.rs:551-552)
+        if (i == n_reads) { if (n_reads) mp->read_off.push_back(mp->row_off.size() - 1); n_reads++; rows_in_read = 0; }
+        if (i + 1 != n_reads || j != rows_in_read) return fail("map: rows are not in (read, position) order");
+        rows_in_read++;
+        if (f.size() >= 4) {
+            const std::string& lst = f[3];
+            size_t p = 0;
+            while (p <= lst.size()) {
+                size_t q = lst.find(',', p);
+                if (q == std::string::npos) q = lst.size();
+                const std::string item = lst.substr(p, q - p);
+                const size_t c = item.find(':');
+                uint32_t node; double lp;
+                if (c == std::string::npos || !parse_u32(item.substr(0, c), &node) || !parse_f64(item.substr(c + 1), &lp)) return fail("map: bad node:prob item");
+                mp->nodes.push_back(node); mp->logp.push_back(lp);
+                p = q + 1;
+            }
+        }
+        mp->row_off.push_back(mp->nodes.size());
+    }
+    mp->read_off.push_back(mp->row_off.size() - 1);
+    if (n_reads == 0) mp->read_off.assign(1, 0);
+    *out = mp;
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_mappings_from_map_file(const char* path, dbgphmm_mappings** out) {
+    if (!path || !out) { dbg_set_error("mappings_from_map_file: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::string text;
+    ST_TRY(read_file(path, &text));
+    return dbgphmm_mappings_from_map_text(text.data(), text.size(), out);
+}
+static int map_text(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, std::string* out) {
+    if (mp->read_off.size() != reads->n_reads + 1) { dbg_set_error("mappings / reads count mismatch"); return DBGPHMM_ERR_INVALID; }
+    std::string& s = *out;
+    s += "# dbgphmm_b200\n";
+    if (d) s += "# k=" + std::to_string(d->k) + " n_edges_full=" + std::to_string(d->fsrc.size()) + " n_edges_compact=" + std::to_string(d->edges.size()) + "\n";
+    s += "# read\tpos\tbase\tnodes_and_probs\n";
+    for (uint64_t i = 0; i < reads->n_reads; i++) {
+        const uint64_t n = reads->off[i + 1] - reads->off[i];
+        if (mp->read_off[i + 1] - mp->read_off[i] != n) { dbg_set_error("mapping length differs from read length"); return DBGPHMM_ERR_INVALID; }
+        s += "# i=" + std::to_string(i) + "\n";
+        for (uint64_t j = 0; j < n; j++) {
+            const uint64_t row = mp->read_off[i] + j;
+            s += std::to_string(i) + "\t" + std::to_string(j) + "\t";
+            s += (char)reads->bases[reads->off[i] + j];
+            s += "\t";
+            for (uint64_t e = mp->row_off[row]; e < mp->row_off[row + 1]; e++) {
+                if (e > mp->row_off[row]) s += ",";
+                s += std::to_string(mp->nodes[e]) + ":";
+                append_f64(s, mp->logp[e]);
+            }
+            s += "\n";
+        }
+    }
+    return DBGPHMM_OK;
+}
+extern "C" int dbgphmm_mappings_to_map_text(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed) {
+    if (!mp || !reads) { dbg_set_error("mappings_to_map_text: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::string s;
+    ST_TRY(map_text(mp, reads, d, &s));
+    return copy_out(s, buf, cap, needed);
+}
+extern "C" int dbgphmm_mappings_to_map_file(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, const char* path) {
+    if (!mp || !reads || !path) { dbg_set_error("mappings_to_map_file: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::string s;
+    ST_TRY(map_text(mp, reads, d, &s));
+    return write_file(path, s);
+}

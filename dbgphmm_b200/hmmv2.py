@@ -49,6 +49,10 @@ SYMBOLS = [
     "dbgphmm_output_node_freqs", "dbgphmm_output_edge_and_init_freqs", "dbgphmm_q_score_exact", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
     "dbgphmm_run_node_freqs_dev", "dbgphmm_generate_mappings", "dbgphmm_launch_count", "dbgphmm_last_timing",
     "dbgphmm_reads_to_device", "dbgphmm_last_dense_kernel",
+    "dbgphmm_dbg_from_text", "dbgphmm_dbg_from_file", "dbgphmm_dbg_destroy", "dbgphmm_dbg_sizes", "dbgphmm_dbg_phmm_graph",
+    "dbgphmm_dbg_get_copy_nums", "dbgphmm_dbg_set_copy_nums", "dbgphmm_dbg_expand_copy_nums", "dbgphmm_dbg_to_text", "dbgphmm_dbg_to_file",
+    "dbgphmm_dbg_to_model", "dbgphmm_mappings_from_map_text", "dbgphmm_mappings_from_map_file", "dbgphmm_mappings_to_map_text",
+    "dbgphmm_mappings_to_map_file",
 ]
 
 _lib = None
@@ -104,6 +108,21 @@ def lib():
     L.dbgphmm_launch_count.argtypes = [ci]; L.dbgphmm_launch_count.restype = u64
     L.dbgphmm_last_timing.argtypes = [vp, C.POINTER(u64)]
     L.dbgphmm_last_dense_kernel.argtypes = [C.POINTER(dbl), C.POINTER(u64), C.POINTER(u64)]
+    L.dbgphmm_dbg_from_text.argtypes = [C.c_char_p, u64, C.POINTER(vp)]
+    L.dbgphmm_dbg_from_file.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.dbgphmm_dbg_destroy.argtypes = [vp]
+    L.dbgphmm_dbg_sizes.argtypes = [vp, vp]
+    L.dbgphmm_dbg_phmm_graph.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.dbgphmm_dbg_get_copy_nums.argtypes = [vp, vp]
+    L.dbgphmm_dbg_set_copy_nums.argtypes = [vp, vp]
+    L.dbgphmm_dbg_expand_copy_nums.argtypes = [vp, u32, vp, vp]
+    L.dbgphmm_dbg_to_text.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.dbgphmm_dbg_to_file.argtypes = [vp, C.c_char_p]
+    L.dbgphmm_dbg_to_model.argtypes = [vp, PP, ci, ci, u64, C.POINTER(vp)]
+    L.dbgphmm_mappings_from_map_text.argtypes = [C.c_char_p, u64, C.POINTER(vp)]
+    L.dbgphmm_mappings_from_map_file.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.dbgphmm_mappings_to_map_text.argtypes = [vp, vp, vp, vp, u64, C.POINTER(u64)]
+    L.dbgphmm_mappings_to_map_file.argtypes = [vp, vp, vp, C.c_char_p]
     for s in SYMBOLS:
         getattr(L, s)  # fail loudly if the library does not export a declared symbol
     _lib = L
@@ -247,6 +266,34 @@ class Mappings:
         ps = [self.probs[int(self.row_off[i]):int(self.row_off[i + 1])] for i in range(a, b)]
         return Mapping(ns, ps)
 
+    @staticmethod
+    def from_map_str(text):
+        """MultiDbg::from_map_str (multi_dbg/output.rs:589-591)."""
+        b = text.encode() if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        _check(lib().dbgphmm_mappings_from_map_text(b, len(b), C.byref(h)))
+        return Mappings._from_handle(h)
+
+    @staticmethod
+    def from_map_file(path):
+        """MultiDbg::from_map_file_raw (multi_dbg/output.rs:612-623); .map.gz / .mpz are gzip."""
+        h = C.c_void_p()
+        _check(lib().dbgphmm_mappings_from_map_file(os.fsencode(path), C.byref(h)))
+        return Mappings._from_handle(h)
+
+    def to_map_string(self, reads, dbg=None):
+        """MultiDbg::to_map_string (multi_dbg/output.rs:485-489)."""
+        need = C.c_uint64()
+        dh = dbg._h if dbg is not None else None
+        _check(lib().dbgphmm_mappings_to_map_text(self._h, reads._h, dh, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(max(1, need.value))
+        _check(lib().dbgphmm_mappings_to_map_text(self._h, reads._h, dh, buf, need.value, C.byref(need)))
+        return buf.raw[:need.value].decode()
+
+    def to_map_file(self, path, reads, dbg=None):
+        """MultiDbg::to_map_file (multi_dbg/output.rs:461-472)."""
+        _check(lib().dbgphmm_mappings_to_map_file(self._h, reads._h, dbg._h if dbg is not None else None, os.fsencode(path)))
+
     def to_node_freqs(self, n_nodes):
         """Mappings::to_node_freqs (hint.rs:161-171) == MultiDbg::mappings_to_freqs (multi_dbg/draft.rs:201-212)."""
         f = np.zeros(n_nodes)
@@ -367,6 +414,100 @@ class PHMMOutput:
 FWD_DENSE, FWD_SPARSE, FWD_SPARSE_RATIO, FWD_MAPPING = range(4)
 BWD_DENSE, BWD_SPARSE, BWD_MAPPING, BWD_BY_FORWARD = range(4)
 RUN_MODES = {"dense": 0, "sparse": 1, "sparse_adaptive": 2, "with_mapping": 3}
+
+
+class MultiDbg:
+    """The part of MultiDbg (multi_dbg.rs:170-186) a DBG file carries: compact edges with their k-mers, copy numbers and
+    full-graph edge ids.  Host only (no GPU needed) except to_phmm*."""
+
+    def __init__(self, handle):
+        self._h = handle
+        sz = (C.c_uint32 * 6)()
+        _check(lib().dbgphmm_dbg_sizes(handle, sz))
+        self._k, self.n_nodes_full, self.n_edges_full, self.n_nodes_compact, self.n_edges_compact, self.n_phmm_edges = [int(x) for x in sz]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dbgphmm_dbg_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def from_dbg_str(text):
+        """MultiDbg::from_dbg_str (multi_dbg/output.rs:340-342)."""
+        b = text.encode() if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        _check(lib().dbgphmm_dbg_from_text(b, len(b), C.byref(h)))
+        return MultiDbg(h)
+
+    @staticmethod
+    def from_dbg_file(path):
+        """MultiDbg::from_dbg_file (multi_dbg/output.rs:346-357); .dbg.gz / .dbz are gzip."""
+        h = C.c_void_p()
+        _check(lib().dbgphmm_dbg_from_file(os.fsencode(path), C.byref(h)))
+        return MultiDbg(h)
+
+    def k(self):
+        return self._k
+
+    def to_dbg_string(self):
+        """MultiDbg::to_dbg_string (multi_dbg/output.rs:129-133)."""
+        need = C.c_uint64()
+        _check(lib().dbgphmm_dbg_to_text(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(max(1, need.value))
+        _check(lib().dbgphmm_dbg_to_text(self._h, buf, need.value, C.byref(need)))
+        return buf.raw[:need.value].decode()
+
+    def to_dbg_file(self, path):
+        _check(lib().dbgphmm_dbg_to_file(self._h, os.fsencode(path)))
+
+    def phmm_graph(self):
+        """to_seq_graph (multi_dbg.rs:1370-1390): (edge_src, edge_dst, emission, node copy numbers, compact edge of each PHMM node)."""
+        src = np.zeros(self.n_phmm_edges, np.uint32); dst = np.zeros(self.n_phmm_edges, np.uint32)
+        em = np.zeros(self.n_edges_full, np.uint8); cn = np.zeros(self.n_edges_full, np.uint32); ce = np.zeros(self.n_edges_full, np.uint32)
+        _check(lib().dbgphmm_dbg_phmm_graph(self._h, _p(src), _p(dst), _p(em), _p(cn), _p(ce)))
+        return src, dst, em, cn, ce
+
+    def get_copy_nums(self):
+        x = np.zeros(self.n_edges_compact, np.uint32)
+        _check(lib().dbgphmm_dbg_get_copy_nums(self._h, _p(x)))
+        return x
+
+    def set_copy_nums(self, copy_nums):
+        x = np.ascontiguousarray(copy_nums, np.uint32)
+        if x.shape != (self.n_edges_compact,):
+            raise DbgphmmError(ERR_INVALID, "copy_nums must have one entry per compact edge")
+        _check(lib().dbgphmm_dbg_set_copy_nums(self._h, _p(x)))
+
+    def expand_copy_nums(self, candidates):
+        """[B][n_edges_compact] candidate copy numbers -> [B][n_edges_full] for PHMMModel.set_copy_nums_batch."""
+        x = np.ascontiguousarray(np.atleast_2d(candidates), np.uint32)
+        if x.shape[1] != self.n_edges_compact:
+            raise DbgphmmError(ERR_INVALID, "candidates must be [B][n_edges_compact]")
+        out = np.zeros((x.shape[0], self.n_edges_full), np.uint32)
+        _check(lib().dbgphmm_dbg_expand_copy_nums(self._h, x.shape[0], _p(x), _p(out)))
+        return out
+
+    def _to_phmm(self, param, mode, device, mem_budget_bytes):
+        src, dst, em, cn, _ = self.phmm_graph()
+        h = C.c_void_p()
+        _check(lib().dbgphmm_dbg_to_model(self._h, C.byref(param), mode, device, mem_budget_bytes, C.byref(h)))
+        m = PHMMModel.__new__(PHMMModel)
+        m.src, m.dst, m.emission = src, dst, em
+        m.param = param.copy(); m.param.n_warmup = self._k
+        m.n_nodes = self.n_edges_full; m.device = device; m._h = h
+        return m
+
+    def to_phmm(self, param, device=0, mem_budget_bytes=0):
+        """MultiDbg::to_phmm (multi_dbg.rs:1394-1397)."""
+        return self._to_phmm(param, 0, device, mem_budget_bytes)
+
+    def to_non_zero_phmm(self, param, device=0, mem_budget_bytes=0):
+        """MultiDbg::to_non_zero_phmm (multi_dbg.rs:1406-1409)."""
+        return self._to_phmm(param, 1, device, mem_budget_bytes)
+
+    def to_uniform_phmm(self, param, device=0, mem_budget_bytes=0):
+        """MultiDbg::to_uniform_phmm (multi_dbg.rs:1400-1403)."""
+        return self._to_phmm(param, 2, device, mem_budget_bytes)
 
 
 class PHMMModel:

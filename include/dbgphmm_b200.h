@@ -179,6 +179,42 @@ int dbgphmm_run_node_freqs_dev(dbgphmm_model* m, const dbgphmm_reads* reads, int
 int dbgphmm_generate_mappings(dbgphmm_model* m, const dbgphmm_reads* reads, const dbgphmm_mappings* mappings,
                               int use_max_ratio, dbgphmm_mappings** out);
 
+/* ---- file formats either side of the path (host only, no GPU needed) ------------------------------------ */
+typedef struct dbgphmm_dbg dbgphmm_dbg;           /* MultiDbg as a DBG file describes it  multi_dbg.rs:170-186 */
+/* DBG text (K / N / E lines): MultiDbg::from_dbg_reader / from_dbg_file (multi_dbg/output.rs:203-345); a path ending in
+ * .gz / .dbz is gzip (output.rs:135-139).  Errors where the reference asserts (unsorted ids, seq / edge-list length). */
+int dbgphmm_dbg_from_text(const char* text, uint64_t len, dbgphmm_dbg** out);
+int dbgphmm_dbg_from_file(const char* path, dbgphmm_dbg** out);
+void dbgphmm_dbg_destroy(dbgphmm_dbg* d);
+/* sizes = {k, n_nodes_full, n_edges_full (= PHMM nodes), n_nodes_compact, n_edges_compact, n PHMM edges} */
+int dbgphmm_dbg_sizes(const dbgphmm_dbg* d, uint32_t sizes[6]);
+/* MultiDbg::to_seq_graph -> to_node_centric_graph(add_terminal = false) (multi_dbg.rs:1370-1390,1551-1604): PHMM node id =
+ * full-graph edge id; edge_src/edge_dst[n PHMM edges] in the reference's insertion order; emission, copy_nums and
+ * compact_edge_of are [n_edges_full].  Any output may be NULL. */
+int dbgphmm_dbg_phmm_graph(const dbgphmm_dbg* d, uint32_t* edge_src, uint32_t* edge_dst, uint8_t* emission, uint32_t* copy_nums,
+                           uint32_t* compact_edge_of);
+/* MultiDbg::get_copy_nums / set_copy_nums (multi_dbg.rs:1041-1066): one copy number per COMPACT edge; set fails like the
+ * reference's assert when the numbers do not balance at every node (is_copy_nums_valid, multi_dbg.rs:1008-1014). */
+int dbgphmm_dbg_get_copy_nums(const dbgphmm_dbg* d, uint32_t* compact_copy_nums);
+int dbgphmm_dbg_set_copy_nums(dbgphmm_dbg* d, const uint32_t* compact_copy_nums);
+/* Candidate copy-number vectors over compact edges [n_batch][n_edges_compact] (what sample_posterior_once proposes,
+ * multi_dbg/posterior.rs:470-515) -> per-k-mer copy numbers [n_batch][n_edges_full] for dbgphmm_model_set_copy_nums_batch. */
+int dbgphmm_dbg_expand_copy_nums(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, uint32_t* full);
+/* MultiDbg::to_dbg_writer / to_dbg_file (output.rs:140-199).  Text calls: buf may be NULL to query *needed. */
+int dbgphmm_dbg_to_text(const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed);
+int dbgphmm_dbg_to_file(const dbgphmm_dbg* d, const char* path);
+/* MultiDbg::to_phmm (mode 0) / to_non_zero_phmm (1) / to_uniform_phmm (2) (multi_dbg.rs:1391-1409): n_warmup := k. */
+int dbgphmm_dbg_to_model(const dbgphmm_dbg* d, const dbgphmm_params* params, int mode, int device, uint64_t mem_budget_bytes,
+                         dbgphmm_model** out);
+/* MAP text (read, pos, base, node:lnP,...): MultiDbg::from_map_reader_raw / to_map_writer (output.rs:455-623); .gz / .mpz
+ * is gzip.  Log probabilities are printed like Rust's `{}` (shortest round-trip digits, no exponent, "-inf"). d (nullable)
+ * only feeds the header comment. */
+int dbgphmm_mappings_from_map_text(const char* text, uint64_t len, dbgphmm_mappings** out);
+int dbgphmm_mappings_from_map_file(const char* path, dbgphmm_mappings** out);
+int dbgphmm_mappings_to_map_text(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, char* buf, uint64_t cap,
+                                 uint64_t* needed);
+int dbgphmm_mappings_to_map_file(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, const char* path);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
 uint64_t dbgphmm_launch_count(int reset);

@@ -1,0 +1,138 @@
+"""DBG / MAP text formats (multi_dbg/output.rs:155-345, 455-623): host-only entry points of the C ABI, no GPU needed.
+
+Pinned on the reference's own fixtures: the DBG example of README.md:174-191 is toy::repeat (multi_dbg/toy.rs:260-305), whose
+node-centric graph tests/ already hold as graphs.toy_repeat(); the dump/load round trip mirrors output.rs:831-857 (dumpload,
+dbg_gz_compressed) and the MAP round trip output.rs:880-905 (map)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from dbgphmm_b200 import graphs, hmmv2 as H
+
+README_DBG = """# #: comment
+# K section: k of DBG
+K\t4
+# N section: node = (k-1)-mer
+#\tid\tsequence of k-1-mer
+N\t0\tnnn
+N\t1\tCAG
+# E section: edge = simple path of k-mers
+E\t0\t1\t0\tCAGGAAnnn\t1\t9,10,11,12,13,14
+E\t1\t1\t1\tCAGCAG\t3\t6,7,8
+E\t2\t0\t1\tnnnTCCCAG\t1\t0,1,2,3,4,5
+"""
+
+
+def test_readme_dbg_is_toy_repeat():
+    d = H.MultiDbg.from_dbg_str(README_DBG)
+    assert (d.k(), d.n_nodes_compact, d.n_edges_compact, d.n_edges_full) == (4, 2, 3, 15)
+    src, dst, em, cn, ce = d.phmm_graph()
+    sg, k = graphs.toy_repeat()
+    assert k == 4
+    assert bytes(em) == bytes(sg.base) and list(cn) == list(sg.node_copy_num)
+    # same PHMM edge set; the node-centric edges are grouped by the (k-1)-mer they pass through, whose numbering differs
+    # between the hand-written toy (14 named nodes) and from_dbg_reader (compact nodes first), so compare per target node
+    assert sorted(zip(src.tolist(), dst.tolist())) == sorted(zip(sg.src.tolist(), sg.dst.tolist()))
+    for v in range(sg.n_nodes):   # parent order of every node (it fixes the fold order of the parent sums)
+        assert [s for s, t in zip(src, dst) if t == v] == [s for s, t in zip(sg.src, sg.dst) if t == v]
+    assert list(ce) == [2] * 6 + [1] * 3 + [0] * 6
+    assert list(d.get_copy_nums()) == [1, 3, 1]
+
+
+def test_dbg_dump_load_round_trip(tmp_path):
+    d = H.MultiDbg.from_dbg_str(README_DBG)
+    s = d.to_dbg_string()
+    d1 = H.MultiDbg.from_dbg_str(s)
+    assert d1.to_dbg_string() == s
+    body = [ln for ln in s.splitlines() if not ln.startswith("#")]
+    assert body == [ln for ln in README_DBG.splitlines() if ln and not ln.startswith("#")]
+    for name in ("hoge.dbg", "repeat.dbg.gz", "repeat.dbz"):
+        path = tmp_path / name
+        d.to_dbg_file(path)
+        raw = open(path, "rb").read()
+        assert (raw[:2] == b"\x1f\x8b") == (not name.endswith(".dbg"))
+        d2 = H.MultiDbg.from_dbg_file(path)
+        assert d2.to_dbg_string() == s
+        for a, b in zip(d.phmm_graph(), d2.phmm_graph()):
+            assert np.array_equal(a, b)
+
+
+def test_copy_numbers_over_compact_edges():
+    d = H.MultiDbg.from_dbg_str(README_DBG)
+    X = np.array([[1, 3, 1], [1, 0, 1], [2, 5, 2]], np.uint32)
+    full = d.expand_copy_nums(X)
+    assert full.shape == (3, 15)
+    _, _, _, _, ce = d.phmm_graph()
+    assert np.array_equal(full, X[:, ce])
+    d.set_copy_nums([1, 7, 1])
+    assert list(d.get_copy_nums()) == [1, 7, 1] and "CAGCAG\t7\t" in d.to_dbg_string()
+    with pytest.raises(H.DbgphmmError):   # flow in != flow out at a node (multi_dbg.rs:1051 asserts)
+        d.set_copy_nums([1, 3, 2])
+
+
+@pytest.mark.parametrize("bad", ["N\t0\tnnn\n", "K\t4\nN\t1\tnnn\n", "K\t4\nN\t0\tnnn\nE\t0\t0\t0\tnnnA\t1\t0,1\n",
+                                 "K\t4\nN\t0\tnnn\nE\t1\t0\t0\tnnnA\t1\t0\n", "K\t4\nN\t0\tnnn\nE\t0\t0\t0\tnnnAC\t1\t0,0\n"])
+def test_dbg_reader_rejects_what_the_reference_asserts(bad):
+    with pytest.raises(H.DbgphmmError):
+        H.MultiDbg.from_dbg_str(bad)
+
+
+def test_map_round_trip(tmp_path):
+    reads = H.Reads([b"GATCC", b"TAT"])
+    vals = [0.0, -1e-7, -0.1, -2.302585092994046, -13.815510557964274, -1234.5678901234567, -np.inf, -5e-324]
+    rows = [[(3, vals[0]), (2, vals[1]), (4, vals[2])], [(4, vals[3])], [(5, vals[4]), (6, vals[5])], [(6, vals[6])], [(7, vals[7]), (8, -1.0)],
+            [(0, -0.5)], [(1, -0.25), (2, -3.0)], [(9, -0.125)]]
+    mp = H.Mappings.from_list([H.Mapping([[n for n, _ in r] for r in rows[:5]], [[p for _, p in r] for r in rows[:5]]),
+                               H.Mapping([[n for n, _ in r] for r in rows[5:]], [[p for _, p in r] for r in rows[5:]])])
+    d = H.MultiDbg.from_dbg_str(README_DBG)
+    s = mp.to_map_string(reads, d)
+    lines = s.splitlines()
+    assert "# k=4 n_edges_full=15 n_edges_compact=3" in lines and "# read\tpos\tbase\tnodes_and_probs" in lines and "# i=1" in lines
+    body = [ln for ln in lines if not ln.startswith("#")]
+    # Rust's `{}` for f64: shortest round-trip digits, never an exponent (output.rs:516)
+    assert body[0] == "0\t0\tG\t3:0,2:-0.0000001,4:-0.1"
+    assert body[1] == "0\t1\tA\t4:-2.302585092994046"
+    assert body[3] == "0\t3\tC\t6:-inf"
+    assert body[5] == "1\t0\tT\t0:-0.5"
+    assert "e" not in body[4].split("\t")[3]
+    mp2 = H.Mappings.from_map_str(s)
+    assert np.array_equal(mp2.read_off, mp.read_off) and np.array_equal(mp2.row_off, mp.row_off)
+    assert np.array_equal(mp2.nodes, mp.nodes) and np.array_equal(mp2.probs, mp.probs)   # bit-exact round trip
+    for name in ("a.map", "a.map.gz", "a.mpz"):
+        path = tmp_path / name
+        mp.to_map_file(path, reads, d)
+        if name != "a.map":
+            assert gzip.open(path, "rt").read() == s
+        mp3 = H.Mappings.from_map_file(path)
+        assert np.array_equal(mp3.nodes, mp.nodes) and np.array_equal(mp3.probs, mp.probs)
+    with pytest.raises(H.DbgphmmError):
+        H.Mappings.from_map_str("0\t1\tA\t3:-0.5\n")   # first row of a read must be position 0 (output.rs:551-552)
+    with pytest.raises(H.DbgphmmError):
+        mp.to_map_string(H.Reads([b"GATCC"]), d)
+
+
+@pytest.mark.gpu
+def test_dbg_file_to_phmm_scores_like_the_hand_built_model():
+    from oracle import oracle as O
+    d = H.MultiDbg.from_dbg_str(README_DBG)
+    sg, k = graphs.toy_repeat()
+    par = H.params_uniform(0.01)
+    g = d.to_non_zero_phmm(par)
+    li, lt = sg.to_probs("non_zero")
+    op = O.params_uniform(0.01); op.n_warmup = k
+    o = O.PHMMModel(sg.src, sg.dst, sg.base, li, lt, op)
+    reads = [b"TCCCAGCAGCAGCAGGAA", b"CCAGCAGG"]
+    tot, per = g.to_full_prob_reads(H.Reads(reads), None, False)
+    s, p = o.to_full_prob_reads(O.Reads(reads), None, False)
+    assert np.allclose(per[0], p, rtol=1e-9, atol=0)
+    # a batch of candidates over compact edges
+    X = np.array([[1, 3, 1], [1, 2, 1], [1, 6, 1]], np.uint32)
+    g.set_copy_nums_batch(d.expand_copy_nums(X), "normal")
+    tot, per = g.to_full_prob_reads(H.Reads(reads), None, False)
+    for b in range(3):
+        li, lt = sg.to_probs("normal", d.expand_copy_nums(X[b])[0])
+        o.set_probs(li, lt)
+        s, p = o.to_full_prob_reads(O.Reads(reads), None, False)
+        assert np.allclose(per[b], p, rtol=1e-9, atol=0)
