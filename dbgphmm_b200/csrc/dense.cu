@@ -1341,10 +1341,12 @@ k_dense_fwd2(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ js
         for (int k = 0; k < RS_PER_LANE; k++) {
             const int pos = RS_PER_LANE * lane + k;
             const double m = cm[k], i = ci[k], d = dacc[k];
-            const double mx = fmax(m, fmax(i, d));
+            // exponent of the largest state: the values are non-negative, so the largest high word carries it
+            const int hx = max(__double2hiint(m), max(__double2hiint(i), __double2hiint(d)));
+            const bool nz = m + i + d != 0.0;
             int qx = 0; double scl = 0.0;
-            if (mx != 0.0) { qx = ilogb_pos(mx); scl = pow2i(-qx); }
-            sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = mx != 0.0 ? Eref + qx : 0;
+            if (nz) { qx = (hx >> 20) - 1023; scl = pow2i(-qx); }
+            sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = nz ? Eref + qx : 0;
         }
         __syncwarp();
 #pragma unroll
@@ -1573,10 +1575,12 @@ k_dense_bwd2(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ js
         for (int k = 0; k < RS_PER_LANE; k++) {
             const int pos = RS_PER_LANE * lane + k;
             const double m = cm[k], i = ci[k], d = dacc[k];
-            const double mx = fmax(m, fmax(i, d));
+            // exponent of the largest state: the values are non-negative, so the largest high word carries it
+            const int hx = max(__double2hiint(m), max(__double2hiint(i), __double2hiint(d)));
+            const bool nz = m + i + d != 0.0;
             int qx = 0; double scl = 0.0;
-            if (mx != 0.0) { qx = ilogb_pos(mx); scl = pow2i(-qx); }
-            sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = mx != 0.0 ? Eref + qx : 0;
+            if (nz) { qx = (hx >> 20) - 1023; scl = pow2i(-qx); }
+            sa[pos] = m * scl; sb[pos] = i * scl; sc[pos] = d * scl; se[pos] = nz ? Eref + qx : 0;
         }
         __syncwarp();
 #pragma unroll

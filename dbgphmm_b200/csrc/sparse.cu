@@ -102,6 +102,11 @@ __device__ __forceinline__ uint32_t block_prefix(SS& S, uint32_t v, uint32_t* to
     S.tog++;
     if (lane == 31) wt[w] = x;
     __syncthreads();
+    if (blockDim.x <= 64) {   // one or two warps (the common launch shapes): no loop over warp totals
+        const uint2 a = *(const uint2*)wt;   // (the total of an absent warp stays 0)
+        *total = a.x + a.y;
+        return (w ? a.x : 0u) + x - v;
+    }
     const uint4 a = *(const uint4*)wt, b = *(const uint4*)(wt + 4);   // totals of absent warps stay 0
     const uint32_t t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t base = 0, tot = 0;
