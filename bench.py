@@ -152,7 +152,15 @@ def main():
     import torch.distributed as dist
     from dbgphmm_b200 import hmmv2 as H
     from dbgphmm_b200.dist import allreduce_results
-    torch.cuda.set_device(local)
+    for attempt in range(5):   # a context of a process that has just exited may still be tearing down (exclusive-process boxes)
+        try:
+            torch.cuda.set_device(local)
+            torch.zeros(1, device="cuda")
+            break
+        except RuntimeError:
+            if attempt == 4:
+                raise
+            time.sleep(2.0)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     R = args.reads_per_gpu

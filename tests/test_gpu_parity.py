@@ -240,6 +240,38 @@ def test_stream_strategy_matches_store_and_oracle(H, monkeypatch):
     assert np.allclose(res["store"][0], res["stream"][0], rtol=1e-12, atol=1e-15)
 
 
+@pytest.mark.parametrize("cap", ["48", "80"])
+def test_sparse_jobs_that_outgrow_their_tables_are_carried_on_by_the_rescue_launch(H, monkeypatch, cap):
+    """A small entry capacity makes most sparse jobs hand their previous row over to the rescue launch, many of them in the middle of
+    a read; results, active sets and cell counts must not depend on where (or whether) that happens."""
+    w = _dbg_case(13, glen=900, n_reads=6, read_len=300)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(w.graph, par)
+    of, olf, olb = o.run_node_freqs(O.Reads(w.reads), "sparse", True, None)
+    res = {}
+    for tag, env in (("default", {}), ("small", {"DBGPHMM_SPARSE_CAP": cap}), ("rerun", {"DBGPHMM_SPARSE_CAP": cap, "DBGPHMM_SPARSE_RESCUE": "0"})):
+        for k in ("DBGPHMM_SPARSE_CAP", "DBGPHMM_SPARSE_RESCUE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for strat in ("store", "stream"):
+            monkeypatch.setenv("DBGPHMM_STRATEGY", strat)
+            gf, glf, glb, cells = g.run_node_freqs(H.Reads(w.reads), "sparse", True, None)
+            assert close_log(glf, olf).all() and close_log(glb, olb).all(), (tag, strat)
+            assert np.allclose(gf, of, rtol=REL_TOL, atol=1e-12), (tag, strat)
+            res[tag, strat] = (glf, glb, cells)
+        t, u = g.forward_sparse(w.reads[0], False), o.forward_sparse(w.reads[0], False)
+        tb, ub = g.backward_sparse(w.reads[0]), o.backward_sparse(w.reads[0])
+        for a, b in ((t, u), (tb, ub)):
+            for r in range(len(b)):
+                ra, rb = a.row(r), b.row(r)
+                assert ra.is_dense == rb.is_dense
+                if not rb.is_dense:
+                    assert list(ra.ids) == list(rb.ids), (tag, r)
+    for key, v in res.items():
+        assert np.array_equal(v[0], res["default", "store"][0]) and np.array_equal(v[1], res["default", "store"][1]) and v[2] == res["default", "store"][2], key
+
+
 def test_two_rows_per_launch_forward_kernel_and_its_fallback(H, monkeypatch):
     """Stream strategy: the forward warm-up runs two rows per launch (k_dense_fwd2) and must reproduce the single-row steps bit for
     bit; a two-row frame that is too narrow (forced here) makes the phase fall back to single-row steps with the same result."""
