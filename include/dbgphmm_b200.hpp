@@ -118,4 +118,60 @@ private:
     uint32_t n_nodes_;
 };
 
+// The part of MultiDbg a DBG file carries (multi_dbg.rs:170-186, multi_dbg/output.rs:155-345); host only.
+class MultiDbg {
+public:
+    static std::unique_ptr<MultiDbg> from_dbg_str(const std::string& s) {   // output.rs:340
+        dbgphmm_dbg* h = nullptr;
+        check(dbgphmm_dbg_from_text(s.data(), s.size(), &h));
+        return std::unique_ptr<MultiDbg>(new MultiDbg(h));
+    }
+    static std::unique_ptr<MultiDbg> from_dbg_file(const std::string& path) {   // output.rs:346 (.dbg, .dbg.gz, .dbz)
+        dbgphmm_dbg* h = nullptr;
+        check(dbgphmm_dbg_from_file(path.c_str(), &h));
+        return std::unique_ptr<MultiDbg>(new MultiDbg(h));
+    }
+    ~MultiDbg() { dbgphmm_dbg_destroy(h_); }
+    MultiDbg(const MultiDbg&) = delete; MultiDbg& operator=(const MultiDbg&) = delete;
+    uint32_t k() const { return sz_[0]; }
+    uint32_t n_edges_full() const { return sz_[2]; }
+    uint32_t n_edges_compact() const { return sz_[4]; }
+    std::string to_dbg_string() const {   // output.rs:129
+        uint64_t need = 0;
+        check(dbgphmm_dbg_to_text(h_, nullptr, 0, &need));
+        std::string s(need, '\0');
+        check(dbgphmm_dbg_to_text(h_, &s[0], need, &need));
+        return s;
+    }
+    void to_dbg_file(const std::string& path) const { check(dbgphmm_dbg_to_file(h_, path.c_str())); }
+    std::vector<uint32_t> get_copy_nums() const {   // multi_dbg.rs:1056
+        std::vector<uint32_t> x(sz_[4]);
+        check(dbgphmm_dbg_get_copy_nums(h_, x.data()));
+        return x;
+    }
+    void set_copy_nums(const std::vector<uint32_t>& x) {   // multi_dbg.rs:1041 (fails where the reference asserts)
+        if (x.size() != sz_[4]) throw Error(DBGPHMM_ERR_INVALID);
+        check(dbgphmm_dbg_set_copy_nums(h_, x.data()));
+    }
+    // candidates over compact edges [n_batch][n_edges_compact] -> per-k-mer copy numbers [n_batch][n_edges_full]
+    std::vector<uint32_t> expand_copy_nums(uint32_t n_batch, const std::vector<uint32_t>& compact) const {
+        if (compact.size() != (size_t)n_batch * sz_[4]) throw Error(DBGPHMM_ERR_INVALID);
+        std::vector<uint32_t> full((size_t)n_batch * sz_[2]);
+        check(dbgphmm_dbg_expand_copy_nums(h_, n_batch, compact.data(), full.data()));
+        return full;
+    }
+    // to_phmm (mode 0) / to_non_zero_phmm (1) / to_uniform_phmm (2): multi_dbg.rs:1391-1409 ; the caller owns the handle
+    dbgphmm_model* to_phmm_handle(const PHMMParams& param, int mode = 0, int device = 0, uint64_t mem_budget = 0) const {
+        dbgphmm_model* m = nullptr;
+        check(dbgphmm_dbg_to_model(h_, &param, mode, device, mem_budget, &m));
+        return m;
+    }
+    dbgphmm_dbg* handle() const { return h_; }
+
+private:
+    explicit MultiDbg(dbgphmm_dbg* h) : h_(h) { check(dbgphmm_dbg_sizes(h_, sz_)); }
+    dbgphmm_dbg* h_;
+    uint32_t sz_[6];
+};
+
 }  // namespace dbgphmm

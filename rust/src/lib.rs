@@ -17,6 +17,7 @@ pub struct dbgphmm_params {
 #[repr(C)] pub struct dbgphmm_model { _p: [u8; 0] }
 #[repr(C)] pub struct dbgphmm_reads { _p: [u8; 0] }
 #[repr(C)] pub struct dbgphmm_mappings { _p: [u8; 0] }
+#[repr(C)] pub struct dbgphmm_dbg { _p: [u8; 0] }
 
 extern "C" {
     pub fn dbgphmm_last_error() -> *const c_char;
@@ -35,6 +36,15 @@ extern "C" {
     pub fn dbgphmm_run_node_freqs(m: *mut dbgphmm_model, reads: *const dbgphmm_reads, mode: c_int, use_max_ratio: c_int,
                                   mappings: *const dbgphmm_mappings, node_freqs: *mut f64, logp_fwd: *mut f64, logp_bwd: *mut f64,
                                   cells: *mut u64) -> c_int;
+    // file formats either side of the path (multi_dbg/output.rs:155-345, 455-623) and compact-edge copy numbers (multi_dbg.rs:1041-1066)
+    pub fn dbgphmm_dbg_from_file(path: *const c_char, out: *mut *mut dbgphmm_dbg) -> c_int;
+    pub fn dbgphmm_dbg_destroy(d: *mut dbgphmm_dbg);
+    pub fn dbgphmm_dbg_sizes(d: *const dbgphmm_dbg, sizes: *mut u32) -> c_int;
+    pub fn dbgphmm_dbg_expand_copy_nums(d: *const dbgphmm_dbg, n_batch: u32, compact: *const u32, full: *mut u32) -> c_int;
+    pub fn dbgphmm_dbg_to_model(d: *const dbgphmm_dbg, params: *const dbgphmm_params, mode: c_int, device: c_int, mem_budget_bytes: u64,
+                                out: *mut *mut dbgphmm_model) -> c_int;
+    pub fn dbgphmm_mappings_from_map_file(path: *const c_char, out: *mut *mut dbgphmm_mappings) -> c_int;
+    pub fn dbgphmm_mappings_to_map_file(mp: *const dbgphmm_mappings, reads: *const dbgphmm_reads, d: *const dbgphmm_dbg, path: *const c_char) -> c_int;
     pub fn dbgphmm_generate_mappings(m: *mut dbgphmm_model, reads: *const dbgphmm_reads, mappings: *const dbgphmm_mappings,
                                      use_max_ratio: c_int, out: *mut *mut dbgphmm_mappings) -> c_int;
 }

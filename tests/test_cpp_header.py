@@ -10,7 +10,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_cpp_mirror_compiles_and_links(tmp_path):
     B.build()
     src = tmp_path / "t.cpp"
-    src.write_text('#include "dbgphmm_b200.hpp"\nint main() { auto p = dbgphmm::uniform(0.01); return p.n_max_gaps == 4 && p.n_active_nodes == 40 ? 0 : 1; }\n')
+    src.write_text(r'''#include "dbgphmm_b200.hpp"
+int main() {
+    auto p = dbgphmm::uniform(0.01);
+    if (!(p.n_max_gaps == 4 && p.n_active_nodes == 40)) return 1;
+    // README.md:174-191 (toy::repeat) through the host-only format entry points
+    auto d = dbgphmm::MultiDbg::from_dbg_str("K\t4\nN\t0\tnnn\nN\t1\tCAG\nE\t0\t1\t0\tCAGGAAnnn\t1\t9,10,11,12,13,14\n"
+                                            "E\t1\t1\t1\tCAGCAG\t3\t6,7,8\nE\t2\t0\t1\tnnnTCCCAG\t1\t0,1,2,3,4,5\n");
+    if (d->k() != 4 || d->n_edges_full() != 15 || d->n_edges_compact() != 3) return 2;
+    auto full = d->expand_copy_nums(1, {1, 2, 1});
+    if (full.size() != 15 || full[6] != 2 || full[0] != 1 || full[14] != 1) return 3;
+    auto d2 = dbgphmm::MultiDbg::from_dbg_str(d->to_dbg_string());
+    if (d2->to_dbg_string() != d->to_dbg_string()) return 4;
+    try { d->set_copy_nums({1, 3, 2}); return 5; } catch (const dbgphmm::Error&) {}
+    return 0;
+}
+''')
     exe = tmp_path / "t"
     libdir = os.path.join(ROOT, "dbgphmm_b200", "lib")
     env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
