@@ -498,14 +498,25 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
         const uint64_t per_row = (uint64_t)m->params.n_active_nodes * 48 + 256 + 3 * sizeof(RowDesc);   // (arena_estimate, engine.cu)
         for (uint64_t r = 0; r < R; r++) bytes[r] = 2 * slab + 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20);
     }
-    for (auto& bt : plan_batches(bytes, m->mem_budget, 65535, mode == DBGPHMM_RUN_DENSE ? 0 : sparse_wave_jobs(m, sparse_default_cap()))) {
+    // Batches in read order.  A batch that runs out of device memory before anything of it has been accumulated (the estimates
+    // above are for typical rows) is split in two and tried again.
+    std::vector<std::pair<size_t, size_t>> work;
+    {
+        auto planned = plan_batches(bytes, m->mem_budget, 65535, mode == DBGPHMM_RUN_DENSE ? 0 : sparse_wave_jobs(m, sparse_default_cap()));
+        work.assign(planned.rbegin(), planned.rend());   // (a stack: the first batch on top)
+    }
+    while (!work.empty()) {
+        const std::pair<size_t, size_t> bt = work.back();
+        work.pop_back();
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         HostTrace tr_b("batch");
         RowStore F, B;
+        bool accumulated = false;   // something of this batch has reached d_freqs / map_out
         if (!stream) {
             PhaseOpts po;
             st = run_forward(m, jobs, reads->d_bases, fk, po, with_map ? &dmap : nullptr, &F);
             if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, po, with_map ? &dmap : nullptr, &F, &B);
+            if (st == DBGPHMM_OK) accumulated = true;
             if (st == DBGPHMM_OK && d_freqs) st = run_products_freqs(m, jobs, F, B, d_freqs);
             if (st == DBGPHMM_OK && map_out) st = run_products_mapping(m, jobs, F, B, map_by_ratio, m->params.n_active_nodes, m->params.active_node_max_ratio, map_out);
         } else {
@@ -520,6 +531,7 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
             StepProducts spb; spb.other = &F; spb.P = F.d_final; spb.d_freqs = d_freqs; spb.d_err = b_err.as<int>();
             PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = b_recompute ? nullptr : &spb;
             if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);
+            if (st == DBGPHMM_OK || !b_recompute) accumulated = true;
             if (st == DBGPHMM_OK && b_recompute) st = run_backward_recompute(m, jobs, reads->d_bases, F, B, spb);
             if (st == DBGPHMM_OK) st = run_products_freqs(m, jobs, F, B, d_freqs);                                    // sparse x sparse, F sparse x b_init
             StepProducts spf; spf.other = &B; spf.P = F.d_final; spf.d_freqs = d_freqs; spf.d_err = b_err.as<int>();
@@ -536,6 +548,16 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
             if (cells) { cells[0] += F.cells; cells[1] += B.cells; }
         }
         { HostTrace tr_r("release"); F.release(); B.release(); }
+        if (st == DBGPHMM_ERR_OOM && !accumulated && jobs.size() > 1) {
+            if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] batch of %zu reads ran out of device memory: splitting it\n", jobs.size());
+            CUDA_TRY(cudaStreamSynchronize(m->stream));
+            cache_trim();
+            const size_t mid = bt.first + jobs.size() / 2;
+            work.push_back({mid, bt.second});
+            work.push_back({bt.first, mid});
+            st = DBGPHMM_OK;
+            continue;
+        }
         if (st != DBGPHMM_OK) break;
     }
     dmap.release();

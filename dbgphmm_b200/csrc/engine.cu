@@ -145,6 +145,7 @@ static int alloc_pool(DensePool& pool, uint32_t N, uint64_t n_slabs) {
     return DBGPHMM_OK;
 }
 static int alloc_arena(SparseArena& a, uint64_t bytes, cudaStream_t st) {
+    if (const char* e = getenv("DBGPHMM_ARENA_MAX_BYTES")) { const uint64_t cap = strtoull(e, nullptr, 10); if (cap >= 256 && bytes > cap) bytes = cap; }   // tests: force the batch split
     a.bytes = bytes;
     a.base = (char*)cache_alloc(bytes ? bytes : 256);
     if (!a.base) { dbg_set_error("out of device memory for sparse rows"); return DBGPHMM_ERR_OOM; }
@@ -240,7 +241,7 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
     const uint64_t cells0 = store->cells;
     int st = run_sparse_jobs_once(m, sj, io, store, small_cap);
     if (st != ST_ARENA_FULL) return st;
-    if (io.arena_bytes >= upper_bytes) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
+    if (io.arena_bytes >= upper_bytes || getenv("DBGPHMM_ARENA_MAX_BYTES")) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
     if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] sparse arena of %.1f MB exhausted: repeating the phase with %.1f MB\n", io.arena_bytes / 1e6, upper_bytes / 1e6);
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     cache_free(store->arena.base); cache_free(store->arena.cursor); store->arena = SparseArena();

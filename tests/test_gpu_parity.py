@@ -272,6 +272,25 @@ def test_sparse_jobs_that_outgrow_their_tables_are_carried_on_by_the_rescue_laun
         assert np.array_equal(v[0], res["default", "store"][0]) and np.array_equal(v[1], res["default", "store"][1]) and v[2] == res["default", "store"][2], key
 
 
+@pytest.mark.parametrize("strat", ["store", "stream"])
+def test_batch_that_runs_out_of_device_memory_is_split(H, monkeypatch, strat):
+    """The sparse-row arenas are sized for typical rows; a batch that outgrows what it can get (forced here by capping the arena)
+    is split in two and tried again, with the same results as the unsplit batch."""
+    w = _dbg_case(17, glen=900, n_reads=7, read_len=300)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g = gpu_model(w.graph, par)
+    monkeypatch.setenv("DBGPHMM_STRATEGY", strat)
+    ref = g.run_node_freqs(H.Reads(w.reads), "sparse", True, None)
+    monkeypatch.setenv("DBGPHMM_ARENA_MAX_BYTES", str(3 * 256 * 1024))   # three 256 KB pages: at most three jobs per direction
+    got = g.run_node_freqs(H.Reads(w.reads), "sparse", True, None)
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]) and got[3] == ref[3]
+    assert np.allclose(got[0], ref[0], rtol=1e-12, atol=1e-15)
+    monkeypatch.setenv("DBGPHMM_ARENA_MAX_BYTES", "4096")                 # not even one read fits: the error surfaces
+    with pytest.raises(H.DbgphmmError) as ei:
+        g.run_node_freqs(H.Reads(w.reads), "sparse", True, None)
+    assert ei.value.status == H.ERR_OOM
+
+
 def test_two_rows_per_launch_forward_kernel_and_its_fallback(H, monkeypatch):
     """Stream strategy: the forward warm-up runs two rows per launch (k_dense_fwd2) and must reproduce the single-row steps bit for
     bit; a two-row frame that is too narrow (forced here) makes the phase fall back to single-row steps with the same result."""
