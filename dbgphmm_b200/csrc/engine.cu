@@ -161,6 +161,7 @@ static int run_sparse_jobs_once(dbgphmm_model* m, std::vector<SJob>& sj, SparseI
     if (sj.empty()) return DBGPHMM_OK;
     cudaStream_t st = m->stream;
     const uint32_t n = (uint32_t)sj.size();
+    for (const SJob& j : sj) if (j.dir != sj[0].dir) { dbg_set_error("internal: sparse jobs of one launch must share their direction"); return DBGPHMM_ERR_INVALID; }
     DevBuf b_jobs, b_status, b_final, b_cells;
     ST_TRY(dev_upload(b_jobs, sj, st));
     ST_TRY(b_status.alloc(sizeof(int) * n)); ST_TRY(b_final.alloc(sizeof(XF) * n)); ST_TRY(b_cells.alloc(sizeof(unsigned long long) * n));
@@ -186,7 +187,7 @@ static int run_sparse_jobs_once(dbgphmm_model* m, std::vector<SJob>& sj, SparseI
         std::vector<SJob> cur(todo.size());
         for (size_t i = 0; i < todo.size(); i++) cur[i] = sj[todo[i]];
         CUDA_TRY(cudaMemcpyAsync(b_jobs.p, cur.data(), sizeof(SJob) * cur.size(), cudaMemcpyHostToDevice, st));
-        ST_TRY(sparse_run(m, b_jobs.as<SJob>(), (uint32_t)cur.size(), io, caps[pass], pass == 0 ? rescue_cap : 0));
+        ST_TRY(sparse_run(m, b_jobs.as<SJob>(), (uint32_t)cur.size(), io, caps[pass], sj[0].dir, pass == 0 ? rescue_cap : 0));
         if (pass == 0 && rescue_cap && getenv("DBGPHMM_TRACE")) {
             uint32_t ctl[4];
             CUDA_TRY(cudaMemcpyAsync(ctl, b_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, st));

@@ -365,6 +365,9 @@ extern __shared__ __align__(16) unsigned char sp_smem[];
 // beside the primary one, take such jobs from the queue and carry them on from the row that did not fit.  (Re-running a failed
 // job in a later pass would cost a whole extra job latency: the kernel is latency-bound, one straggler costs as much as a wave.
 // Launch order primary, rescue: neither waits for the other to start, so the pair also completes when kernels are serialised.)
+// DIR: 0 every job of the launch runs forward, 1 backward (the launches of a phase are uniform ; a specialised kernel is half the
+// code of the generic one, and the kernel is sensitive to instruction-cache misses: 16 warps per SM wander through > 100 KB of it).
+template <int DIR>
 __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, SparseIO io, uint32_t cap, uint32_t hcap, int role) {
     const int tid = threadIdx.x, B = blockDim.x;
     // ---- shared-memory view
@@ -421,7 +424,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     const bool skip = (jb.active_idx >= 0 && !io.active[jb.active_idx]) || jb.n_rows == 0;
     const double* init = G.init + (size_t)jb.x * G.N;
     const double* trans = G.trans + (size_t)jb.x * G.E;
-    const bool fwd = jb.dir == 0;
+    constexpr bool fwd = DIR == 0;
     const bool adaptive = (jb.mode == SP_TOPN || jb.mode == SP_RATIO);
     uint32_t n_prev = 0;   // packed entries of the previous row (sparse prev only)
     XF last_scalar = xf_zero();
@@ -773,7 +776,8 @@ static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) { return SS_BYTES(c
 
 int sparse_configure(dbgphmm_model* m) {
     (void)m;
-    CUDA_TRY(cudaFuncSetAttribute(k_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_sparse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_sparse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return DBGPHMM_OK;
 }
 
@@ -801,8 +805,9 @@ static uint32_t hcap_of(uint32_t cap) {
 uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
     const uint32_t rcap = sparse_rescue_cap(cap);
     int per_sm = 0;
-    cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sparse, sparse_threads(cap), sparse_smem_bytes(cap, hcap_of(cap))) != cudaSuccess || per_sm < 1) {
+    cudaFuncSetAttribute(k_sparse<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_sparse<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sparse<1>, sparse_threads(cap), sparse_smem_bytes(cap, hcap_of(cap))) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }
@@ -814,19 +819,20 @@ uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
     return (uint32_t)per_sm * (uint32_t)m->n_sm;
 }
 
-static int sparse_launch(dbgphmm_model* m, cudaStream_t st, uint32_t grid, const SGraph& G, const SJob* d_jobs, const SparseIO& io, uint32_t cap, int role) {
+static int sparse_launch(dbgphmm_model* m, cudaStream_t st, uint32_t grid, const SGraph& G, const SJob* d_jobs, const SparseIO& io, uint32_t cap, int role, int dir) {
     const uint32_t hcap = hcap_of(cap);
     const size_t smem = sparse_smem_bytes(cap, hcap);
     if (smem > 200 * 1024) { dbg_set_error("sparse_run: capacity too large for shared memory"); return DBGPHMM_ERR_INVALID; }
     int threads = sparse_threads(cap);
     if (const char* e = getenv("DBGPHMM_SPARSE_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) threads = t; }
-    k_sparse<<<grid, threads, smem, st>>>(G, m->lin, d_jobs, io, cap, hcap, role);
+    if (dir == 0) k_sparse<0><<<grid, threads, smem, st>>>(G, m->lin, d_jobs, io, cap, hcap, role);
+    else k_sparse<1><<<grid, threads, smem, st>>>(G, m->lin, d_jobs, io, cap, hcap, role);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;
 }
 
-int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io_in, uint32_t cap, uint32_t rescue_cap) {
+int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io_in, uint32_t cap, int dir, uint32_t rescue_cap) {
     if (n_jobs == 0) return DBGPHMM_OK;
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
@@ -834,20 +840,21 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
         int carve = 100;
         if (const char* e = getenv("DBGPHMM_SPARSE_CARVEOUT")) carve = atoi(e);
         if (carve < 10) carve = 10; if (carve > 100) carve = 100;
-        cudaFuncSetAttribute(k_sparse, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_sparse<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_sparse<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
     SparseIO io = io_in;
     if (!rescue_cap || !io.rq_ctl) {
         io.rq_ctl = nullptr;
-        return sparse_launch(m, m->stream, n_jobs, G, d_jobs, io, cap, 0);
+        return sparse_launch(m, m->stream, n_jobs, G, d_jobs, io, cap, 0, dir);
     }
     // primary: as many persistent CTAs as stay resident beside one rescue CTA per SM ; rescue CTAs idle until a job is handed over
     const uint32_t grid = std::min<uint32_t>(n_jobs, sparse_wave_jobs(m, cap));
     io.rq_cap = cap; io.rq_n_primary = grid; io.rq_n_jobs = n_jobs;
     CUDA_TRY(cudaEventRecord(m->ev_fork, m->stream));
     CUDA_TRY(cudaStreamWaitEvent(m->stream_aux, m->ev_fork, 0));
-    ST_TRY(sparse_launch(m, m->stream, grid, G, d_jobs, io, cap, 0));
-    ST_TRY(sparse_launch(m, m->stream_aux, std::min<uint32_t>(n_jobs, (uint32_t)m->n_sm), G, d_jobs, io, rescue_cap, 1));
+    ST_TRY(sparse_launch(m, m->stream, grid, G, d_jobs, io, cap, 0, dir));
+    ST_TRY(sparse_launch(m, m->stream_aux, std::min<uint32_t>(n_jobs, (uint32_t)m->n_sm), G, d_jobs, io, rescue_cap, 1, dir));
     CUDA_TRY(cudaEventRecord(m->ev_join, m->stream_aux));
     CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     return DBGPHMM_OK;

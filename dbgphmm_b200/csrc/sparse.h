@@ -78,6 +78,7 @@ uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap);
 // cap: entry capacity per job in shared memory; threads per CTA chosen from cap.  rescue_cap > cap: a second launch of
 // persistent CTAs with that capacity runs beside the primary one (auxiliary stream) and carries on the jobs whose rows
 // outgrow `cap` (io.rq_* must be set up by the caller); 0: no rescue launch.
-int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap, uint32_t rescue_cap = 0);
+// dir: SJob::dir of every job of the launch (0 forward, 1 backward)
+int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap, int dir, uint32_t rescue_cap = 0);
 // capacity of the rescue launch that accompanies a primary launch of capacity `cap` (0: none)
 uint32_t sparse_rescue_cap(uint32_t cap);
