@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 #include "engine.h"
 
 static const double LN2 = 0.693147180559945309417232121458;
@@ -74,6 +75,54 @@ extern "C" int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32
         if (mp->nodes[i] >= n_nodes) { dbg_set_error("mapping node id out of range"); return DBGPHMM_ERR_INVALID; }
         freqs[mp->nodes[i]] += std::exp(mp->logp[i]);
     }
+    return DBGPHMM_OK;
+}
+
+// Prob + Prob of the reference (prob.rs:181-197): the larger term first, then x + ln_1p(exp(y - x)), with its special cases
+static double host_log_add(double a, double b) {
+    const double x = a >= b ? a : b, y = a >= b ? b : a;
+    if (y == -INFINITY) return x;
+    if (x == y) return x + LN2;
+    return x + std::log1p(std::exp(y - x));
+}
+extern "C" int dbgphmm_mappings_map_nodes(const dbgphmm_mappings* mp, uint32_t n_nodes_before, const uint64_t* map_off, const uint32_t* map_to,
+                                          dbgphmm_mappings** out) {
+    if (!mp || !map_off || !out) { dbg_set_error("mappings_map_nodes: bad argument"); return DBGPHMM_ERR_INVALID; }
+    for (uint32_t v = 0; v < n_nodes_before; v++)
+        if (map_off[v + 1] < map_off[v]) { dbg_set_error("mappings_map_nodes: map_off is not non-decreasing"); return DBGPHMM_ERR_INVALID; }
+    // hint.rs:66-88 — per base: every (node, p) spreads p / |node_map(node)| over its images, images that coincide are
+    // added (Prob +), the row is re-sorted by probability, descending, and cut to MAX_ACTIVE_NODES.  The reference collects
+    // the images in a HashMap, so the order among EQUAL probabilities is unspecified there; here: first appearance first.
+    dbgphmm_mappings* o = new dbgphmm_mappings();
+    o->read_off = mp->read_off;
+    o->row_off.assign(1, 0);
+    std::vector<std::pair<uint32_t, double>> acc;   // (image, ln p) in order of first appearance
+    std::unordered_map<uint32_t, uint32_t> where;
+    std::vector<uint32_t> order;
+    const size_t n_rows = mp->row_off.size() - 1;
+    for (size_t r = 0; r < n_rows; r++) {
+        acc.clear(); where.clear();
+        for (uint64_t i = mp->row_off[r]; i < mp->row_off[r + 1]; i++) {
+            const uint32_t v = mp->nodes[i];
+            if (v >= n_nodes_before) { delete o; dbg_set_error("mappings_map_nodes: node id out of range of the node map"); return DBGPHMM_ERR_INVALID; }
+            const uint64_t a = map_off[v], b = map_off[v + 1];
+            if (a == b) continue;
+            if (!map_to) { delete o; dbg_set_error("mappings_map_nodes: bad argument"); return DBGPHMM_ERR_INVALID; }
+            const double share = mp->logp[i] - std::log((double)(b - a));   // Prob / usize (prob.rs:271-279)
+            for (uint64_t j = a; j < b; j++) {
+                auto it = where.find(map_to[j]);
+                if (it == where.end()) { where.emplace(map_to[j], (uint32_t)acc.size()); acc.emplace_back(map_to[j], host_log_add(-INFINITY, share)); }
+                else acc[it->second].second = host_log_add(acc[it->second].second, share);
+            }
+        }
+        order.resize(acc.size());
+        for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return acc[x].second > acc[y].second; });
+        const size_t keep = std::min<size_t>(order.size(), DBGPHMM_MAX_ACTIVE_NODES);
+        for (size_t i = 0; i < keep; i++) { o->nodes.push_back(acc[order[i]].first); o->logp.push_back(acc[order[i]].second); }
+        o->row_off.push_back(o->nodes.size());
+    }
+    *out = o;
     return DBGPHMM_OK;
 }
 

@@ -43,7 +43,7 @@ SYMBOLS = [
     "dbgphmm_model_create", "dbgphmm_model_destroy", "dbgphmm_model_set_params", "dbgphmm_model_set_probs",
     "dbgphmm_model_set_copy_nums_batch", "dbgphmm_model_get_probs", "dbgphmm_model_n_nodes", "dbgphmm_model_n_batch",
     "dbgphmm_reads_create", "dbgphmm_reads_destroy", "dbgphmm_mappings_create", "dbgphmm_mappings_destroy",
-    "dbgphmm_mappings_sizes", "dbgphmm_mappings_export", "dbgphmm_mappings_to_node_freqs",
+    "dbgphmm_mappings_sizes", "dbgphmm_mappings_export", "dbgphmm_mappings_to_node_freqs", "dbgphmm_mappings_map_nodes",
     "dbgphmm_forward", "dbgphmm_backward", "dbgphmm_tables_destroy", "dbgphmm_tables_len", "dbgphmm_tables_full_prob",
     "dbgphmm_tables_row_info", "dbgphmm_tables_row_export", "dbgphmm_tables_row_top_nodes",
     "dbgphmm_output_node_freqs", "dbgphmm_output_edge_and_init_freqs", "dbgphmm_q_score_exact", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
@@ -89,6 +89,7 @@ def lib():
     L.dbgphmm_mappings_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.dbgphmm_mappings_export.argtypes = [vp, vp, vp, vp, vp]
     L.dbgphmm_mappings_to_node_freqs.argtypes = [vp, u32, vp]
+    L.dbgphmm_mappings_map_nodes.argtypes = [vp, u32, vp, vp, C.POINTER(vp)]
     L.dbgphmm_forward.argtypes = [vp, vp, u64, ci, vp, u64, C.POINTER(vp)]
     L.dbgphmm_backward.argtypes = [vp, vp, u64, ci, vp, u64, vp, C.POINTER(vp)]
     L.dbgphmm_tables_destroy.argtypes = [vp]
@@ -299,6 +300,23 @@ class Mappings:
         f = np.zeros(n_nodes)
         _check(lib().dbgphmm_mappings_to_node_freqs(self._h, n_nodes, _p(f)))
         return f
+
+    def map_nodes(self, node_map, n_nodes_before=None):
+        """Mapping::map_nodes (hint.rs:66-88) applied to every read.  node_map: callable node -> list of nodes (as in the
+        reference), or a (map_off, map_to) CSR pair over the old node ids."""
+        if callable(node_map):
+            if n_nodes_before is None:
+                n_nodes_before = int(self.nodes.max()) + 1 if len(self.nodes) else 0
+            off = np.zeros(n_nodes_before + 1, np.uint64); to = []
+            for v in range(n_nodes_before):
+                to.extend(int(w) for w in node_map(v)); off[v + 1] = len(to)
+            to = np.asarray(to, np.uint32)
+        else:
+            off = np.ascontiguousarray(node_map[0], np.uint64); to = np.ascontiguousarray(node_map[1], np.uint32)
+            n_nodes_before = len(off) - 1
+        h = C.c_void_p()
+        _check(lib().dbgphmm_mappings_map_nodes(self._h, n_nodes_before, _p(off), _p(to), C.byref(h)))
+        return Mappings._from_handle(h)
 
 
 class Row:

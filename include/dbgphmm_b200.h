@@ -99,6 +99,15 @@ int dbgphmm_mappings_export(const dbgphmm_mappings* mp, uint64_t* read_off, uint
 /* Mappings::to_node_freqs (hint.rs:161-171) == MultiDbg::mappings_to_freqs (multi_dbg/draft.rs:201-212) */
 int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32_t n_nodes, double* freqs);
 
+/* Mapping::map_nodes (hint.rs:66-88) for every read of the handle: node v of the old graph corresponds to
+ * map_to[map_off[v] .. map_off[v+1]) in the new one (possibly none).  Each (v, p) of a base spreads p / |images| over its images,
+ * coinciding images are added (Prob +, prob.rs:181-197), the base's list is re-sorted by probability, descending, and cut to
+ * DBGPHMM_MAX_ACTIVE_NODES.  This is the step that carries a hint over a graph change: MultiDbg::hint_kp1_from_hint_k
+ * (multi_dbg.rs:1325-1334: v -> the k+1 edges entering node v) and PurgeEdgeMap::update_mapping (multi_dbg.rs:1783-1791: v -> the
+ * surviving edge, or nothing).  Order among equal probabilities: first appearance (the reference's HashMap order is unspecified). */
+int dbgphmm_mappings_map_nodes(const dbgphmm_mappings* mp, uint32_t n_nodes_before, const uint64_t* map_off, const uint32_t* map_to,
+                               dbgphmm_mappings** out);
+
 /* ---- PHMMTables of one read (forward.rs / backward.rs drivers) ---------------------------------------- */
 enum {
     DBGPHMM_FWD_DENSE = 0,        /* forward               forward.rs:24  */

@@ -44,6 +44,15 @@ public:
     std::vector<double> to_node_freqs(uint32_t n_nodes) const {  // hint.rs:161
         std::vector<double> f(n_nodes); check(dbgphmm_mappings_to_node_freqs(h_, n_nodes, f.data())); return f;
     }
+    // Mapping::map_nodes (hint.rs:66-88) over every read; node_map[v] = the nodes v turns into (may be empty)
+    Mappings map_nodes(const std::vector<std::vector<uint32_t>>& node_map) const {
+        std::vector<uint64_t> off(1, 0); std::vector<uint32_t> to;
+        for (auto& ws : node_map) { to.insert(to.end(), ws.begin(), ws.end()); off.push_back(to.size()); }
+        dbgphmm_mappings* o = nullptr;
+        check(dbgphmm_mappings_map_nodes(h_, (uint32_t)node_map.size(), off.data(), to.data(), &o));
+        return Mappings(o);
+    }
+    Mappings(Mappings&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
 private:
     dbgphmm_mappings* h_;
 };

@@ -31,6 +31,8 @@ extern "C" {
     pub fn dbgphmm_mappings_create(n_reads: u64, read_off: *const u64, row_off: *const u64, nodes: *const u32, logp: *const f64,
                                    out: *mut *mut dbgphmm_mappings) -> c_int;
     pub fn dbgphmm_mappings_destroy(m: *mut dbgphmm_mappings);
+    pub fn dbgphmm_mappings_map_nodes(mp: *const dbgphmm_mappings, n_nodes_before: u32, map_off: *const u64, map_to: *const u32,
+                                      out: *mut *mut dbgphmm_mappings) -> c_int;
     pub fn dbgphmm_to_full_prob_reads(m: *mut dbgphmm_model, reads: *const dbgphmm_reads, mappings: *const dbgphmm_mappings,
                                       use_max_ratio: c_int, out_logp: *mut f64, out_logp_per_read: *mut f64) -> c_int;
     pub fn dbgphmm_run_node_freqs(m: *mut dbgphmm_model, reads: *const dbgphmm_reads, mode: c_int, use_max_ratio: c_int,

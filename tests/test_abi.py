@@ -53,6 +53,29 @@ def test_mappings_roundtrip_and_freqs(lib):
     assert np.allclose(f, [0, 0.75, 0.25, 1.0, 0])
 
 
+def test_mapping_node_convert(lib):
+    """hint.rs:234-270 (mapping_node_convert): case 1 is the reference's exact assertion; case 2 (printed only there) and the
+    dropped-node case of PurgeEdgeMap::update_mapping (multi_dbg.rs:1783-1791) follow from map_nodes' definition (hint.rs:66-88)."""
+    lg = np.log
+    m = H.Mappings.from_list([H.Mapping([[0, 1], [2, 3]], [[lg(0.6), lg(0.4)], [lg(0.9), lg(0.1)]])])
+    m1 = m.map_nodes(lambda v: [v + 1], 4)
+    assert [list(x) for x in m1[0].nodes] == [[1, 2], [3, 4]]
+    assert [list(x) for x in m1[0].probs] == [[lg(0.6), lg(0.4)], [lg(0.9), lg(0.1)]]   # p / 1 is exact: assert_eq in the reference
+    m2 = m.map_nodes(lambda v: [v, v + 1], 4)
+    assert [list(x) for x in m2[0].nodes] == [[1, 0, 2], [3, 2, 4]]
+    assert np.allclose(np.exp(np.concatenate(m2[0].probs)), [0.5, 0.3, 0.2, 0.5, 0.45, 0.05], rtol=1e-14)
+    m3 = m.map_nodes(lambda v: [] if v in (0, 3) else [7], 4)
+    assert [list(x) for x in m3[0].nodes] == [[7], [7]]
+    assert np.allclose(np.exp(np.concatenate(m3[0].probs)), [0.4, 0.9], rtol=1e-14)
+    # several reads keep their row structure; more images than MAX_ACTIVE_NODES are cut to the 400 most probable
+    two = H.Mappings.from_list([H.Mapping([[0]], [[0.0]]), H.Mapping([[1], [0, 1]], [[0.0], [lg(0.5), lg(0.5)]])])
+    wide = two.map_nodes(lambda v: list(range(100 + 500 * v, 600 + 500 * v)), 2)
+    assert wide.n_reads() == 2 and len(wide[0]) == 1 and len(wide[1]) == 2
+    assert [len(x) for x in wide[1].nodes] == [400, 400] and list(wide[1].nodes[0][:3]) == [600, 601, 602]
+    with pytest.raises(H.DbgphmmError):
+        m.map_nodes(lambda v: [v], 2)   # node 2 / 3 outside the node map
+
+
 def test_no_gpu_means_loud_failure(lib):
     if H.device_count() > 0:
         pytest.skip("a GPU is present")
