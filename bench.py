@@ -43,6 +43,15 @@ def parse():
     return ap.parse_args()
 
 
+def workload_tag(args):
+    """BASELINE.json configs[2] (C3, the bench default) / one GPU's shard of configs[4] (C5: 5 Mbp haplotypes, 20 kbp reads)."""
+    if (args.genome_len, args.read_len, args.k) == (1_000_000, 10_000, 40):
+        return "C3"
+    if (args.genome_len, args.read_len, args.k) == (5_000_000, 20_000, 40):
+        return "C5 (one GPU's read shard)"
+    return "custom"
+
+
 def make_inputs(args, rank, n_reads):
     """Same graph on every rank (seed 0); rank-specific reads.  C3: 1 Mbp diploid, 1 % het, 10 kbp HiFi reads, k = 40."""
     from dbgphmm_b200 import graphs, synth
@@ -143,7 +152,7 @@ def main():
         print(json.dumps({"metric": "PHMM forward-backward GCUPS", "value": v, "unit": "GCUPS", "impl": "reference", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": f"C3: {args.genome_len} bp diploid 1% het, {args.read_len} bp HiFi reads p=0.001, k={args.k}, run_sparse + node freqs",
+                          "config": {"workload": f"{workload_tag(args)}: {args.genome_len} bp diploid 1% het, {args.read_len} bp HiFi reads p=0.001, k={args.k}, run_sparse + node freqs",
                                      "n_nodes": int(g.n_nodes), "reads_per_step": n_sample},
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
@@ -257,7 +266,7 @@ def main():
         out = {"metric": "PHMM forward-backward GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "reads_per_s": world * R / (ms_step * 1e-3),
-               "config": {"workload": f"C3: {args.genome_len} bp diploid 1% het, {args.read_len} bp HiFi reads p=0.001, k={args.k}, run_sparse + node freqs",
+               "config": {"workload": f"{workload_tag(args)}: {args.genome_len} bp diploid 1% het, {args.read_len} bp HiFi reads p=0.001, k={args.k}, run_sparse + node freqs",
                           "n_nodes": int(N), "reads_per_gpu_per_step": R, "n_active_nodes": 40, "n_warmup": args.k,
                           "l2": "DP rows of one step exceed L2 (each dense row is 28 B x N, hundreds of rows in flight)"},
                "roofline": roof,

@@ -349,6 +349,15 @@ int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* 
     ST_TRY(upload(&m->d_pos_of, m->pos_of)); ST_TRY(upload(&m->d_orig_of, m->orig_of)); ST_TRY(upload(&m->d_emission, m->emission));
     ST_TRY(upload(&m->d_par_off, m->par_off)); ST_TRY(upload(&m->d_par_node, m->par_node)); ST_TRY(upload(&m->d_par_eid, m->par_eid));
     ST_TRY(upload(&m->d_chi_off, m->chi_off)); ST_TRY(upload(&m->d_chi_node, m->chi_node)); ST_TRY(upload(&m->d_chi_eid, m->chi_eid));
+    {
+        std::vector<uint4> pr(N), cr(N);
+        for (uint32_t p = 0; p < N; p++) {
+            const uint32_t po = m->par_off[p], pc = m->par_off[p + 1] - po, co = m->chi_off[p], cc = m->chi_off[p + 1] - co;
+            pr[p] = make_uint4(po, pc, pc ? m->par_node[po] : 0u, pc ? m->par_eid[po] : 0u);
+            cr[p] = make_uint4(co, cc, cc ? m->chi_node[co] : 0u, cc ? m->chi_eid[co] : 0u);
+        }
+        ST_TRY(upload(&m->d_par_rec, pr)); ST_TRY(upload(&m->d_chi_rec, cr));
+    }
     ST_TRY(build_plan(m->fwd, N, m->par_off, m->par_node, m->par_eid));
     ST_TRY(build_plan(m->bwd, N, m->chi_off, m->chi_node, m->chi_eid));
     {   // layout of the two-rows-per-launch forward kernel ; a graph too branchy for 12-hop tiles simply goes without it
@@ -425,6 +434,7 @@ void model_free(dbgphmm_model* m) {
     cudaFree(m->d_pos_of); cudaFree(m->d_orig_of); cudaFree(m->d_emission);
     cudaFree(m->d_par_off); cudaFree(m->d_par_node); cudaFree(m->d_par_eid);
     cudaFree(m->d_chi_off); cudaFree(m->d_chi_node); cudaFree(m->d_chi_eid);
+    cudaFree(m->d_par_rec); cudaFree(m->d_chi_rec);
     cudaFree(m->d_init); cudaFree(m->d_trans);
     free_plan(m->fwd); free_plan(m->bwd); free_plan(m->fwd2); free_plan(m->bwd2);
     cache_trim();

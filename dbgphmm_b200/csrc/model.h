@@ -83,6 +83,9 @@ struct dbgphmm_model {
     uint8_t* d_emission = nullptr;
     uint32_t *d_par_off = nullptr, *d_par_node = nullptr, *d_par_eid = nullptr;
     uint32_t *d_chi_off = nullptr, *d_chi_node = nullptr, *d_chi_eid = nullptr;
+    // per node {first CSR slot, degree, first neighbour, its edge id}: one 16-byte load answers the common degree-1 case of the
+    // latency-bound sparse kernel (CSR offset -> neighbour -> edge id is a chain of dependent L2 loads otherwise)
+    uint4 *d_par_rec = nullptr, *d_chi_rec = nullptr;
     double* d_init = nullptr;   // [n_batch][N] linear, relabelled node order
     double* d_trans = nullptr;  // [n_batch][E] linear, original EdgeIndex order
     DevPlan fwd, bwd;

@@ -21,6 +21,7 @@ struct SGraph {
     const double *init, *trans;
     const uint32_t *par_off, *par_node, *par_eid, *chi_off, *chi_node, *chi_eid;
     const uint32_t* pos_of;
+    const uint4 *par_rec, *chi_rec;   // {CSR offset, degree, first neighbour, its edge id} per node (model.h)
 };
 
 // Shared-memory view of one job.  Every array sits at a fixed multiple of `cap` bytes from `base`, so the view is five
@@ -95,9 +96,15 @@ __device__ __forceinline__ uint32_t sp_cell(uint32_t* key, uint32_t hmask, int h
 // second barrier).  All threads must call.  Two 16-bit counters may be packed into v.  At most 8 warps.
 __device__ __forceinline__ uint32_t block_prefix(SS& S, uint32_t v, uint32_t* total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t x = v;
+    uint32_t x = v;   // becomes the inclusive prefix within the warp
+    if (__all_sync(0xffffffffu, (v & 0xfffefffeu) == 0u)) {   // at most one per 16-bit counter (chains: degree 1): two ballots, no shuffle chain
+        const uint32_t b0 = __ballot_sync(0xffffffffu, v & 1u), b1 = __ballot_sync(0xffffffffu, v >> 16);
+        const uint32_t le = 0xffffffffu >> (31 - lane);
+        x = (uint32_t)__popc(b0 & le) | ((uint32_t)__popc(b1 & le) << 16);
+    } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    }
     uint32_t* wt = S.wt() + 8 * (S.tog & 1);
     S.tog++;
     if (lane == 31) wt[w] = x;
@@ -145,7 +152,7 @@ __device__ __forceinline__ XF block_xsum(XF a) {  // deterministic block reducti
 //   phase 1  every candidate finds / inserts its hash cell and min-reduces its position into it
 //   phase 2  a candidate is kept iff it holds the first position of its id ; ordered compaction by a second prefix,
 //            sources first, then neighbours
-__device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t* off, const uint32_t* nbr, bool and_us, bool with_nbrs,
+__device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint4* rec, const uint32_t* nbr, bool and_us, bool with_nbrs,
                           uint32_t* out_id, uint16_t* out_slot, int max_out, uint32_t* n_ent_io, int* n_out) {
     __shared__ uint32_t s_flags[2][2];   // [call parity][0: overflow, 1: new entries not emitted]
     const int tid = threadIdx.x, B = blockDim.x;
@@ -157,37 +164,47 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
     for (uint32_t e = tid; e < n_ent0; e += B) S.firstpos()[e] = SP_ABSENT;
     if (tid == 0) { fl[0] = 0; fl[1] = 0; }
     const uint32_t n_self = and_us ? (uint32_t)n_src : 0u;
-    auto note = [&](uint32_t id, uint32_t p) {   // phase 1 for one candidate
+    auto note = [&](uint32_t id, uint32_t p) -> uint32_t {   // phase 1 for one candidate ; returns its hash cell
         const uint32_t cell = sp_cell(S.ch_key(), S.hmask, S.hshift, id);
         const uint32_t v = S.ch_val()[cell];
         if (v < SP_TENT) atomicMin(&S.firstpos()[v], p);
         else atomicMin(&S.ch_val()[cell], SP_TENT | p);
+        return cell;
     };
     if (!with_nbrs) __syncthreads();   // (the prefix below is the barrier otherwise) firstpos reset before the min-reductions
     uint32_t C = n_self;
     for (int q0 = 0; q0 < n_src; q0 += B) {
         const int q = q0 + tid;
-        uint32_t id = 0, o0 = 0, cnt = 0;
-        if (q < n_src) { id = src[q]; if (with_nbrs) { o0 = off[id]; cnt = off[id + 1] - o0; } }
+        uint32_t id = 0, cnt = 0;
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (q < n_src) { id = src[q]; if (with_nbrs) { r = __ldg(rec + id); cnt = r.y; } }
         if (with_nbrs) {
+            const bool too_many = cnt > 16;
+            if (too_many) cnt = 0;
             uint32_t tot;
             const uint32_t base = C + block_prefix(S, cnt, &tot);
             C += tot;
             if (q < n_src) {
-                if (cnt > 16) { fl[0] = 1; cnt = 0; }
-                S.scan()[q] = base | (cnt << 20);
-                for (uint32_t k = 0; k < cnt; k++) note(nbr[o0 + k], base + k);
+                if (too_many) fl[0] = 1;
+                uint32_t cell0 = 0;
+                for (uint32_t k = 0; k < cnt; k++) { const uint32_t c = note(k ? nbr[r.x + k] : r.z, base + k); if (k == 0) cell0 = c; }
+                // position of the first candidate (< 8192: at most 400 + 16 x 400), degree, and the hash cell of the first neighbour
+                // (phase 2 does not probe for it again)
+                S.scan()[q] = base | (cnt << 13) | (cell0 << 18);
             }
         }
         if (and_us && q < n_src) note(id, (uint32_t)q);
     }
     __syncthreads();
     // kept / new flag of candidate p with id `id` : bit 0 kept, bit 16 new entry
-    auto flag_of = [&](uint32_t id, uint32_t p, uint32_t* cell_out, uint32_t* v_out) -> uint32_t {
+    auto cell_of = [&](uint32_t id) -> uint32_t {
         uint32_t h = sp_hash(id, S.hshift);
         while (S.ch_key()[h] != id + 1) h = (h + 1) & S.hmask;   // inserted in phase 1
-        const uint32_t v = S.ch_val()[h];
-        *cell_out = h; *v_out = v;
+        return h;
+    };
+    auto flag_at = [&](uint32_t cell, uint32_t p, uint32_t* v_out) -> uint32_t {
+        const uint32_t v = S.ch_val()[cell];
+        *v_out = v;
         if (v < SP_TENT) return (S.firstpos()[v] == p) ? 1u : 0u;
         return v == (SP_TENT | p) ? 0x10001u : 0u;
     };
@@ -216,7 +233,7 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
         for (int q0 = 0; q0 < n_src; q0 += B) {
             const int q = q0 + tid;
             uint32_t id = 0, f = 0, cell = 0, v = 0;
-            if (q < n_src) { id = src[q]; f = flag_of(id, (uint32_t)q, &cell, &v); }
+            if (q < n_src) { id = src[q]; cell = cell_of(id); f = flag_at(cell, (uint32_t)q, &v); }
             uint32_t tot;
             const uint32_t excl = run + block_prefix(S, f, &tot);   // (barrier: every tentative value of this chunk has been read)
             if (f) emit(id, (uint32_t)q, f, excl, cell, v);
@@ -227,13 +244,15 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
     if (with_nbrs) {
         for (int q0 = 0; q0 < n_src; q0 += B) {
             const int q = q0 + tid;
-            uint32_t o0 = 0, base = 0, cnt = 0, mask = 0, mine = 0;
+            uint32_t base = 0, cnt = 0, cell0 = 0, mask = 0, mine = 0;
+            uint4 r = make_uint4(0u, 0u, 0u, 0u);
             if (q < n_src) {
                 const uint32_t sc = S.scan()[q];
-                base = sc & 0xfffffu; cnt = sc >> 20; o0 = off[src[q]];
+                base = sc & 0x1fffu; cnt = (sc >> 13) & 31u; cell0 = sc >> 18;
+                if (cnt) r = __ldg(rec + src[q]);
                 for (uint32_t k = 0; k < cnt; k++) {
-                    uint32_t cell, v;
-                    const uint32_t f = flag_of(nbr[o0 + k], base + k, &cell, &v);
+                    uint32_t v;
+                    const uint32_t f = flag_at(k ? cell_of(nbr[r.x + k]) : cell0, base + k, &v);
                     if (f) { mask |= (f >> 16 ? 3u : 1u) << (2 * k); mine += f; }
                 }
             }
@@ -242,9 +261,9 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint32_t*
             for (uint32_t k = 0; k < cnt; k++) {
                 const uint32_t b2 = (mask >> (2 * k)) & 3u;
                 if (!b2) continue;
-                const uint32_t id = nbr[o0 + k], f = b2 == 3u ? 0x10001u : 1u;
-                uint32_t cell, v;
-                flag_of(id, base + k, &cell, &v);   // (cell and slot again ; the value is not published yet: only this thread does)
+                const uint32_t id = k ? nbr[r.x + k] : r.z, f = b2 == 3u ? 0x10001u : 1u;
+                const uint32_t cell = k ? cell_of(id) : cell0;
+                const uint32_t v = S.ch_val()[cell];   // (the slot again ; the value is not published yet: only this thread does)
                 emit(id, base + k, f, excl, cell, v);
                 excl += f;
             }
@@ -283,14 +302,18 @@ __device__ void sp_rank(SS& S, uint32_t n, uint32_t KK, const uint32_t* ids, uin
     const int tid = threadIdx.x, B = blockDim.x;
     uint32_t* bad = S.wt() + 16;   // zero between rankings (reset below after use)
     if (!*bad) {
+        // f precedes e iff kf > ke, or kf == ke and f < e: that is kf + (f < e) > ke (keys stay below 2^63) ; two keys per load
+        const ulonglong2* k2 = (const ulonglong2*)S.k_mant();   // (16-byte aligned: cap is a multiple of 16)
         for (uint32_t e = tid; e < n; e += B) {
             const unsigned long long ke = S.k_mant()[e];
             uint32_t rank = 0;
-#pragma unroll 4
-            for (uint32_t f = 0; f < n; f++) {
-                const unsigned long long kf = S.k_mant()[f];
-                rank += (kf > ke || (kf == ke && f < e)) ? 1u : 0u;
+#pragma unroll 2
+            for (uint32_t f = 0; f + 1 < n; f += 2) {
+                const ulonglong2 kf = k2[f >> 1];
+                rank += (kf.x + (f < e ? 1ull : 0ull) > ke) ? 1u : 0u;
+                rank += (kf.y + (f + 1 < e ? 1ull : 0ull) > ke) ? 1u : 0u;
             }
+            if (n & 1u) rank += (S.k_mant()[n - 1] + (n - 1 < e ? 1ull : 0ull) > ke) ? 1u : 0u;
             if (rank < KK) out_id[rank] = ids[e];
             S.scan()[e] = rank;
         }
@@ -512,7 +535,11 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
 
         // ---------------- 2. reset the current row
         uint32_t n_ent = 0;
-        for (uint32_t h = tid; h < hcap; h += B) { S.ch_key()[h] = 0; S.ch_val()[h] = SP_ABSENT; }
+        {   // (16-byte stores: the tables are 16-byte aligned and hcap is a power of two >= 64)
+            uint4* hk = (uint4*)S.ch_key(); uint4* hv = (uint4*)S.ch_val();
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u), ab = make_uint4(SP_ABSENT, SP_ABSENT, SP_ABSENT, SP_ABSENT);
+            for (uint32_t h = tid; h < hcap / 4; h += B) { hk[h] = z; hv[h] = ab; }
+        }
         __syncthreads();
 
         // ---------------- 3. the step's `nodes` (they hold m, i)
@@ -520,10 +547,10 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         bool ok = true;
         if (fwd) {
             // forward sparse: nodes = to_childs_and_us(top) (forward.rs:148) ; mapping: nodes = mapping.nodes(i)
-            ok = sp_expand(S, S.top_id(), n_top, G.chi_off, G.chi_node, true, adaptive, S.act_id(), S.act_slot(), MAX_ACTIVE, &n_ent, &n_act);
+            ok = sp_expand(S, S.top_id(), n_top, G.chi_rec, G.chi_node, true, adaptive, S.act_id(), S.act_slot(), MAX_ACTIVE, &n_ent, &n_act);
         } else {
             // backward sparse: M/I over to_parents_and_us(nodes) (backward.rs:243-259) ; non-adaptive: nodes themselves
-            ok = sp_expand(S, S.top_id(), n_top, G.par_off, G.par_node, true, adaptive, S.act_id(), S.act_slot(), MAX_ACTIVE, &n_ent, &n_act);
+            ok = sp_expand(S, S.top_id(), n_top, G.par_rec, G.par_node, true, adaptive, S.act_id(), S.act_slot(), MAX_ACTIVE, &n_ent, &n_act);
         }
         if (!ok) { if (tid == 0) { s_fail = SJ_NEED_BIG; s_info = ((unsigned long long)s << 32) | 2u << 16 | n_ent; } __syncthreads(); break; }
         const uint32_t n_mi = (uint32_t)n_act;
@@ -537,10 +564,13 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             for (uint32_t a = tid; a < n_mi; a += B) {
                 uint32_t id = S.act_id()[a], sl = S.act_slot()[a];
                 XF acc = xf_zero();
-                for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
+                const uint4 r = __ldg(G.par_rec + id);
+                for (uint32_t k = 0; k < r.y; k++) {
+                    const uint32_t pn = k ? G.par_node[r.x + k] : r.z, eid = k ? G.par_eid[r.x + k] : r.w;
+                    const double tr = trans[eid];
                     double pm, pi, pd; int pe;
-                    prev_get(S, PA, G.par_node[e], &pm, &pi, &pd, &pe);
-                    acc = xadd(acc, xf(trans[G.par_eid[e]] * (lp.p_MM * pm + lp.p_IM * pi + lp.p_DM * pd), pe));
+                    prev_get(S, PA, pn, &pm, &pi, &pd, &pe);
+                    acc = xadd(acc, xf(tr * (lp.p_MM * pm + lp.p_IM * pi + lp.p_DM * pd), pe));
                 }
                 acc = xadd(acc, xmul(fb0, init[id]));
                 XF m = xmul(acc, G.emission[id] == x ? lp.p_match : lp.p_mismatch);
@@ -558,7 +588,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 const uint32_t* l_id = S.act_id(); const uint16_t* l_slot = S.act_slot();   // non-adaptive: every round runs over `nodes`
                 int n_l = n_act;
                 if (adaptive) {
-                    ok = sp_expand(S, src_id, n_src, G.chi_off, G.chi_node, false, true, S.la_id(t & 1), S.la_slot(t & 1), MAX_ACTIVE, &n_ent, &n_l);
+                    ok = sp_expand(S, src_id, n_src, G.chi_rec, G.chi_node, false, true, S.la_id(t & 1), S.la_slot(t & 1), MAX_ACTIVE, &n_ent, &n_l);
                     if (!ok) break;
                     l_id = S.la_id(t & 1); l_slot = S.la_slot(t & 1);
                 }
@@ -571,10 +601,12 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                         const uint32_t id = l_id[a];
                         sl = l_slot[a];
                         XF acc = xf_zero();
-                        for (uint32_t e = G.par_off[id]; e < G.par_off[id + 1]; e++) {
-                            int ps = sp_find(S.ch_key(), S.ch_val(), S.hmask, S.hshift, G.par_node[e]);
+                        const uint4 r = __ldg(G.par_rec + id);
+                        for (uint32_t k = 0; k < r.y; k++) {
+                            const uint32_t pn = k ? G.par_node[r.x + k] : r.z, eid = k ? G.par_eid[r.x + k] : r.w;
+                            const double tr = trans[eid];   // (issued before the hash probe: its latency overlaps it)
+                            int ps = sp_find(S.ch_key(), S.ch_val(), S.hmask, S.hshift, pn);
                             if (ps < 0) continue;
-                            double tr = trans[G.par_eid[e]];
                             if (t == 0) { if ((uint32_t)ps < n_mi) acc = xadd(acc, xf(tr * (lp.p_MD * S.c_m()[ps] + lp.p_ID * S.c_i()[ps]), S.c_mie()[ps])); }
                             else if (stp[ps] == stamp0 + t - 1) acc = xadd(acc, xf(tr * lp.p_DD * dvp[ps], dep[ps]));
                         }
@@ -614,7 +646,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 if (t == 0 || !adaptive) { l_id = S.act_id(); l_slot = S.act_slot(); n_l = n_act; }  // A0 == to_parents_and_us(nodes)
                 else {
                     int nn = 0;
-                    ok = sp_expand(S, src_id, n_src, G.par_off, G.par_node, true, true, S.la_id(t & 1), S.la_slot(t & 1), MAX_ACTIVE, &n_ent, &nn);
+                    ok = sp_expand(S, src_id, n_src, G.par_rec, G.par_node, true, true, S.la_id(t & 1), S.la_slot(t & 1), MAX_ACTIVE, &n_ent, &nn);
                     if (!ok) break;
                     l_id = S.la_id(t & 1); l_slot = S.la_slot(t & 1); n_l = nn;
                 }
@@ -627,9 +659,10 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                         const uint32_t id = l_id[a];
                         sl = l_slot[a];
                         XF acc = xf_zero();
-                        for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) {
-                            uint32_t ch = G.chi_node[e];
-                            double tr = trans[G.chi_eid[e]];
+                        const uint4 r = __ldg(G.chi_rec + id);
+                        for (uint32_t k = 0; k < r.y; k++) {
+                            const uint32_t ch = k ? G.chi_node[r.x + k] : r.z, eid = k ? G.chi_eid[r.x + k] : r.w;
+                            const double tr = trans[eid];
                             if (t == 0) {
                                 double pm, pi, pd; int pe;
                                 prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
@@ -666,9 +699,10 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
             for (uint32_t a = tid; a < n_mi; a += B) {
                 uint32_t id = S.act_id()[a], sl = S.act_slot()[a];
                 XF am = xf_zero(), ai = xf_zero();
-                for (uint32_t e = G.chi_off[id]; e < G.chi_off[id + 1]; e++) {
-                    uint32_t ch = G.chi_node[e];
-                    double tr = trans[G.chi_eid[e]];
+                const uint4 r = __ldg(G.chi_rec + id);
+                for (uint32_t k = 0; k < r.y; k++) {
+                    const uint32_t ch = k ? G.chi_node[r.x + k] : r.z, eid = k ? G.chi_eid[r.x + k] : r.w;
+                    const double tr = trans[eid];
                     double pm, pi, pd; int pe;
                     prev_get(S, PA, ch, &pm, &pi, &pd, &pe);
                     XF tm = xf(tr * (G.emission[ch] == x ? lp.p_match : lp.p_mismatch) * pm, pe);
@@ -835,7 +869,7 @@ static int sparse_launch(dbgphmm_model* m, cudaStream_t st, uint32_t grid, const
 int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io_in, uint32_t cap, int dir, uint32_t rescue_cap) {
     if (n_jobs == 0) return DBGPHMM_OK;
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
-             m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of};
+             m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of, m->d_par_rec, m->d_chi_rec};
     {   // the kernel is latency-bound: as many resident jobs per SM as shared memory allows
         int carve = 100;
         if (const char* e = getenv("DBGPHMM_SPARSE_CARVEOUT")) carve = atoi(e);
