@@ -1628,10 +1628,52 @@ __device__ __forceinline__ int skey_digit(const SKey& k, int lvl, int Ttop) {
     return (int)(k.inv_id & 0x3ff);
 }
 
+// Pre-filter of the selection on large rows.  One streaming pass (k_select_tilemax) leaves the largest merged value of every run of
+// SEL_TILE consecutive cells ; the selection kernel then finds a threshold tau that at least k of those tile maxima reach -- every
+// one of them is a cell, so the k-th largest cell is >= tau -- and looks only into the tiles whose maximum reaches it (about k of
+// N / SEL_TILE) instead of sweeping the row three or more times.  Order-preserving 64-bit image of (T, mant) relative to the row
+// maximum Ttop: zero and everything more than 2046 binades below map to 0 (if tau ends up 0 the full algorithm takes over).
+#define SEL_TILE 512
+struct TileKey { unsigned long long mant; int T; int pad; };
+__device__ __forceinline__ unsigned long long skey_pack(int T, unsigned long long mant, int Ttop) {
+    if (T == XF_ZERO_E) return 0ull;
+    const long long rel = (long long)Ttop - T;
+    if (rel < 0 || rel > 2046) return 0ull;
+    return ((unsigned long long)(2047 - rel) << 52) | mant;
+}
+__global__ void __launch_bounds__(256)
+k_select_tilemax(const SelectReq* __restrict__ reqs, const int* __restrict__ active, const char* __restrict__ pool, uint64_t slab_bytes,
+                 uint32_t Np, uint32_t N, uint32_t n_tiles, TileKey* __restrict__ tiles) {
+    const SelectReq rq = reqs[blockIdx.y];
+    if (rq.active_idx >= 0 && !active[rq.active_idx]) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const char* sl = pool + rq.slab * slab_bytes;
+    const double* gm = (const double*)sl; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
+    int T = XF_ZERO_E; unsigned long long mant = 0;
+    const uint32_t g0 = t * SEL_TILE;
+#pragma unroll 4
+    for (int j = 0; j < SEL_TILE / 32; j++) {
+        const uint32_t g = g0 + 32 * j + lane;
+        if (g < N) {
+            const SKey k = cell_key(gm[g], gi[g], gd[g], ge[g], 0);
+            if (k.T > T || (k.T == T && k.mant > mant)) { T = k.T; mant = k.mant; }
+        }
+    }
+    const int Tm = __reduce_max_sync(0xffffffffu, T);
+    const unsigned hi = T == Tm ? (unsigned)(mant >> 32) : 0u;
+    const unsigned hm = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo = (T == Tm && hi == hm) ? (unsigned)mant : 0u;
+    const unsigned lm = __reduce_max_sync(0xffffffffu, lo);
+    if (lane == 0) { TileKey k; k.mant = ((unsigned long long)hm << 32) | lm; k.T = Tm; k.pad = 0; tiles[(size_t)blockIdx.y * n_tiles + t] = k; }
+}
+
 #define SELECT_SMEM_BYTES (SELECT_CAP * (8 + 4 + 4 + 4))
 __global__ void __launch_bounds__(SELECT_THREADS, 1)
 k_dense_select(GraphView G, const SelectReq* __restrict__ reqs, const int* __restrict__ active, const char* __restrict__ pool,
-               uint64_t slab_bytes, uint32_t Np, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_cnt) {
+               uint64_t slab_bytes, uint32_t Np, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_cnt,
+               const TileKey* __restrict__ tiles, uint32_t n_tiles) {
     const SelectReq rq = reqs[blockIdx.x];
     if (rq.active_idx >= 0 && !active[rq.active_idx]) return;
     const char* sl = pool + rq.slab * slab_bytes;
@@ -1650,9 +1692,74 @@ k_dense_select(GraphView G, const SelectReq* __restrict__ reqs, const int* __res
     __shared__ unsigned int s_need, s_ncand, s_done, s_shift;
     __shared__ double s_L0;
     const uint32_t K = rq.k < N ? rq.k : N;
+    bool have = false;   // the candidate arrays hold a superset of the top K (tile pre-filter)
+    if (tiles) {
+        const TileKey* tk = tiles + (size_t)blockIdx.x * n_tiles;
+        __shared__ unsigned long long s_tau;
+        int tmax = XF_ZERO_E;
+        for (uint32_t t = tid; t < n_tiles; t += SELECT_THREADS) { const int T = tk[t].T; tmax = T > tmax ? T : tmax; }
+        tmax = __reduce_max_sync(0xffffffffu, tmax);
+        if ((tid & 31) == 0) sh_T[tid >> 5] = tmax;
+        for (int b = tid; b < SEL_BINS; b += SELECT_THREADS) hist[b] = 0;
+        __syncthreads();
+        tmax = sh_T[0];
+        for (int w = 1; w < SELECT_THREADS / 32; w++) tmax = sh_T[w] > tmax ? sh_T[w] : tmax;
+        const int Tt = tmax;
+        // two radix levels over the tile maxima: exponent digit, then the top 11 mantissa bits
+        for (uint32_t t = tid; t < n_tiles; t += SELECT_THREADS) atomicAdd(&hist[(int)(skey_pack(tk[t].T, tk[t].mant, Tt) >> 52)], 1u);
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int cum = 0;
+            int b = SEL_BINS - 1;
+            for (; b > 0; b--) { if (cum + hist[b] >= K) break; cum += hist[b]; }
+            prefix[0] = b; s_need = K - cum;
+        }
+        __syncthreads();
+        const int b0 = prefix[0];
+        for (int b = tid; b < SEL_BINS; b += SELECT_THREADS) hist[b] = 0;
+        __syncthreads();
+        if (b0 > 0)
+            for (uint32_t t = tid; t < n_tiles; t += SELECT_THREADS) {
+                const unsigned long long pk = skey_pack(tk[t].T, tk[t].mant, Tt);
+                if ((int)(pk >> 52) == b0) atomicAdd(&hist[(int)((pk >> 41) & 0x7ff)], 1u);
+            }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int need = s_need, cum = 0;
+            int b = SEL_BINS - 1;
+            for (; b > 0; b--) { if (cum + hist[b] >= need) break; cum += hist[b]; }
+            s_tau = b0 > 0 ? (((unsigned long long)b0 << 52) | ((unsigned long long)b << 41)) : 0ull;
+            s_ncand = 0;
+        }
+        __syncthreads();
+        const unsigned long long tau = s_tau;
+        if (tau) {
+            for (uint32_t tb = (uint32_t)(tid >> 5) * 32; tb < n_tiles; tb += SELECT_THREADS) {   // a warp takes 32 tiles at a time
+                const uint32_t t = tb + (tid & 31);
+                unsigned int mask = __ballot_sync(0xffffffffu, t < n_tiles && skey_pack(tk[t < n_tiles ? t : 0].T, tk[t < n_tiles ? t : 0].mant, Tt) >= tau);
+                while (mask) {
+                    const uint32_t g0 = (tb + (uint32_t)(__ffs(mask) - 1)) * SEL_TILE;
+                    mask &= mask - 1;
+                    for (int j = 0; j < SEL_TILE / 32; j++) {
+                        const uint32_t g = g0 + 32 * j + (tid & 31);
+                        if (g >= N) break;
+                        const SKey k = cell_key(gm[g], gi[g], gd[g], ge[g], G.orig_of[g]);
+                        if (skey_pack(k.T, k.mant, Tt) >= tau) {
+                            const unsigned int slot = atomicAdd(&s_ncand, 1u);
+                            if (slot < SELECT_CAP) { c_mant[slot] = k.mant; c_T[slot] = k.T; c_inv[slot] = k.inv_id; c_node[slot] = g; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            have = s_ncand >= K && s_ncand <= SELECT_CAP;   // (at least K by construction ; more than fit: the full algorithm below)
+        }
+        __syncthreads();
+    }
+    int nlev = 0;
+    if (!have) {
     if (tid == 0) { s_need = K; s_ncand = 0; s_Ttop = 0x7fffffff; }
     __syncthreads();
-    int nlev = 0;
     // ---- level 0: exponent window [Ttop-2046, Ttop]; shift the window down while fewer than `need` cells are in it
     for (;;) {
         const int Tcap = s_Ttop;  // only cells with T <= Tcap (strictly below the previous window) remain
@@ -1736,6 +1843,7 @@ k_dense_select(GraphView G, const SelectReq* __restrict__ reqs, const int* __res
         }
     }
     __syncthreads();
+    }   // !have
     const unsigned int nc = s_ncand < SELECT_CAP ? s_ncand : SELECT_CAP;
     // ---- rank by counting (nc <= SELECT_CAP), emit in descending order
     for (unsigned int a = tid; a < nc; a += SELECT_THREADS) {
@@ -1961,7 +2069,19 @@ int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
 int dense_select(dbgphmm_model* m, const DensePool& pool, const SelectReq* d_reqs, uint32_t n_reqs, const int* d_active,
                  uint32_t* d_out_ids, uint32_t* d_out_cnt) {
     if (n_reqs == 0) return DBGPHMM_OK;
-    k_dense_select<<<n_reqs, SELECT_THREADS, SELECT_SMEM_BYTES, m->stream>>>(graph_view(m), d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, d_out_ids, d_out_cnt);
+    // rows of >= 64 K cells: tile maxima first (one streaming pass), the selection then reads ~k tiles instead of the row
+    const uint32_t n_tiles = (m->N + SEL_TILE - 1) / SEL_TILE;
+    bool pre = m->N >= (1u << 16);
+    if (const char* e = getenv("DBGPHMM_SELECT_TILES")) pre = e[0] == '1';
+    DevBuf b_tiles;
+    if (pre && b_tiles.alloc(sizeof(TileKey) * (size_t)n_reqs * n_tiles) != DBGPHMM_OK) pre = false;   // (no scratch left: the full sweep needs none)
+    if (pre) {
+        k_select_tilemax<<<dim3((n_tiles + 7) / 8, n_reqs), 256, 0, m->stream>>>(d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, m->N, n_tiles, b_tiles.as<TileKey>());
+        COUNT_LAUNCH();
+        CUDA_TRY(cudaGetLastError());
+    }
+    k_dense_select<<<n_reqs, SELECT_THREADS, SELECT_SMEM_BYTES, m->stream>>>(graph_view(m), d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, d_out_ids, d_out_cnt,
+                                                                            pre ? b_tiles.as<TileKey>() : nullptr, n_tiles);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;

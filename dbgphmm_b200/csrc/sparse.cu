@@ -421,13 +421,17 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         if (tid == 0) {
             volatile uint32_t* ctl = io.rq_ctl;
             uint32_t got = SP_ABSENT;
+            // No fence while waiting: a gpu-scope fence invalidates the whole L1 of the SM (CCTL.IVALL), and this CTA shares its SM
+            // with the primary CTAs, whose graph reads live there.  The counters are read with volatile (L1-bypassing) loads ; the
+            // one decision that needs ordering -- leaving -- fences once: a push always precedes its CTA's done mark, so the counters
+            // read after "every primary CTA is gone" + fence are final.
             for (;;) {
-                const uint32_t done = ctl[2];   // (read before the counters: a push always precedes its CTA's done mark)
-                __threadfence();
                 const uint32_t pushed = ctl[0], popped = ctl[1];
                 if (popped < pushed) { if (atomicCAS(io.rq_ctl + 1, popped, popped + 1) == popped) { got = popped; break; } }
-                else if (done == io.rq_n_primary) break;
-                else __nanosleep(2000);
+                else if (ctl[2] == io.rq_n_primary) {
+                    __threadfence();
+                    if (ctl[1] >= ctl[0]) break;
+                } else __nanosleep(2000);
             }
             if (got != SP_ABSENT) {
                 volatile uint32_t* it = io.rq_items + got;

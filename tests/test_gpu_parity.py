@@ -141,6 +141,33 @@ def test_sparse_ratio_and_by_forward(H, seed):
         assert_tables_match(g.backward_by_forward(read, gf), o.backward_by_forward(read, of), w.graph.n_nodes, "bwd_by_fwd")
 
 
+@pytest.mark.parametrize("n_active", [10, 40])
+def test_dense_selection_through_the_tile_prefilter(H, monkeypatch, n_active):
+    """Top-n of a dense row via tile maxima (dense.cu: k_select_tilemax + the pre-filter of k_dense_select, the default on rows of
+    >= 64 K cells) must pick exactly what the full radix sweep and the oracle pick.  ~90 tiles here: n_active = 40 leaves few spare
+    tiles; the ratio selection (k = 400 > number of tiles) cannot use the pre-filter and must fall through to the full sweep."""
+    w = _dbg_case(11, glen=30000, k=16, het=0.01, p_err=0.003, read_len=120, n_reads=2)
+    assert w.graph.n_nodes > 40 * 512
+    par = oracle_params(0.003, n_warmup=w.k, n_active=n_active, warmup_threshold=30)
+    g, o = both(w.graph, par)
+    read = w.reads[0]
+    of, ob = o.forward_sparse(read, False), o.backward_sparse(read)
+    before = H.launch_count()
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DBGPHMM_SELECT_TILES", flag)
+        gf = g.forward_sparse(read, False)
+        assert_tables_match(gf, of, w.graph.n_nodes, f"fwd_sparse tiles={flag}")
+        assert_tables_match(g.backward_sparse(read), ob, w.graph.n_nodes, f"bwd_sparse tiles={flag}")
+        for r in (0, w.k // 2, w.k - 1):
+            merged = of.row(r).merged(w.graph.n_nodes)
+            for k in (1, n_active):
+                a, b = gf.top_nodes(r, k), of.top_nodes(r, k)
+                assert same_up_to_ties(a, b, merged[b]), (flag, r, k, list(a), list(b))
+            a, b = gf.top_nodes_by_score_ratio(r, 30.0), of.top_nodes_by_score_ratio(r, 30.0)
+            assert same_up_to_ties(a, b, merged[b]), (flag, r, list(a), list(b))
+    assert H.launch_count() > before
+
+
 def test_top_nodes_of_rows(H):
     w = _dbg_case(2)
     par = oracle_params(0.01, n_warmup=w.k)
