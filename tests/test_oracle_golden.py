@@ -167,3 +167,22 @@ def test_seq_graph_edge_copy_num_kat_edge_freqs():
     # every path leaves Begin exactly once (up to the Begin -> Ins mass)
     _, nf = o1b.to_edge_and_init_freqs(g1, rb)
     assert abs(nf.sum() - 1.0) < 1e-2
+
+
+@pytest.mark.parametrize("flag", [True, False])
+def test_hmm_crossing_edge_on_off(flag):
+    """hmmv2/common.rs:381-417 (hmm_crossing_edge_on / _off): mock_crossing -> to_seq_graph -> to_phmm has 40 nodes and 40 edges;
+    with edge copy numbers the transitions 9 -> 20 and 19 -> 30 are 1 and the crossing ones are zero, without them all four are
+    1/2 (seq_graph.rs:180-211).  Checked on the product-side builder and on the oracle's restatement."""
+    from dbgphmm_b200 import graphs
+    sg = graphs.mock_crossing(flag)
+    assert sg.n_nodes == 40 and sg.n_edges == 40
+    for which, (li, lt) in (("graphs", sg.to_probs("normal")), ("oracle", O.seqgraph_to_phmm(sg.src, sg.dst, sg.base, sg.node_copy_num, sg.edge_copy_num, 0))):
+        t = {(int(s), int(d)): float(p) for s, d, p in zip(sg.src, sg.dst, lt)}
+        assert sorted(d for (s, d) in t if s == 9) == [20, 30] and sorted(s for (s, d) in t if d == 20) == [9, 19], which
+        if flag:
+            assert abs(t[(9, 20)]) < 1e-12 and abs(t[(19, 30)]) < 1e-12, which
+            assert t[(9, 30)] == -np.inf and t[(19, 20)] == -np.inf, which
+        else:
+            for e in ((9, 20), (9, 30), (19, 20), (19, 30)):
+                assert abs(t[e] - np.log(0.5)) < 1e-12, (which, e)
