@@ -4,12 +4,16 @@
 // backward drivers: backward.rs:24-53 (dense), :59-93 (mapping), :101-142 (by forward), :146-185 (sparse)
 #include <algorithm>
 #include <cstring>
+#include <mutex>
+#include <thread>
 #include "engine.h"
 
-EngineTimes g_times;
+// Host-side state shared by every handle of the process: the instrumentation is per host thread, the block cache is guarded by a
+// mutex, so different handles may be driven from different threads (one thread per handle at a time, see dbgphmm_b200.h).
+thread_local EngineTimes g_times;
 
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_free, g_ev_busy;
-static std::vector<uint64_t> g_ev_cells;
+static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_free, g_ev_busy;
+static thread_local std::vector<uint64_t> g_ev_cells;
 void launch_timer_begin(cudaStream_t st) {
     std::pair<cudaEvent_t, cudaEvent_t> p;
     if (!g_ev_free.empty()) { p = g_ev_free.back(); g_ev_free.pop_back(); }
@@ -32,34 +36,48 @@ void launch_timer_flush() {
     g_ev_busy.clear(); g_ev_cells.clear();
 }
 
-struct CacheBlock { void* p; size_t bytes; int device; bool used; };
+// Device-memory block cache shared by the handles of the process.  Blocks are returned while the work that used them may still
+// be in flight on the owner's stream (stream order protects the next user on that stream), so a block freed by one host thread is
+// handed to another thread only after a device-wide synchronisation.
+struct CacheBlock { void* p; size_t bytes; int device; bool used; std::thread::id owner; };
 static std::vector<CacheBlock> g_cache;
+static std::recursive_mutex g_cache_mu;
 void* cache_alloc(size_t bytes) {
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
     if (bytes < 256) bytes = 256;
     if (bytes < (1u << 20)) { size_t c = 256; while (c < bytes) c <<= 1; bytes = c; }  // small blocks in power-of-two classes
     int dev = 0; cudaGetDevice(&dev);
-    int best = -1;
-    for (size_t i = 0; i < g_cache.size(); i++) {
-        const CacheBlock& b = g_cache[i];
-        if (!b.used && b.device == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 + (1 << 20))
-            if (best < 0 || b.bytes < g_cache[best].bytes) best = (int)i;
+    const std::thread::id me = std::this_thread::get_id();
+    for (int any_owner = 0; any_owner < 2; any_owner++) {
+        int best = -1;
+        for (size_t i = 0; i < g_cache.size(); i++) {
+            const CacheBlock& b = g_cache[i];
+            if (!b.used && b.device == dev && (any_owner || b.owner == me) && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 + (1 << 20))
+                if (best < 0 || b.bytes < g_cache[best].bytes) best = (int)i;
+        }
+        if (best >= 0) {
+            if (g_cache[best].owner != me) { cudaDeviceSynchronize(); g_cache[best].owner = me; }
+            g_cache[best].used = true;
+            return g_cache[best].p;
+        }
     }
-    if (best >= 0) { g_cache[best].used = true; return g_cache[best].p; }
     void* p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
         cudaGetLastError();
         cache_trim();
         if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
-    g_cache.push_back(CacheBlock{p, bytes, dev, true});
+    g_cache.push_back(CacheBlock{p, bytes, dev, true, me});
     return p;
 }
 void cache_free(void* p) {
     if (!p) return;
-    for (auto& b : g_cache) if (b.p == p) { b.used = false; return; }
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
+    for (auto& b : g_cache) if (b.p == p) { b.used = false; b.owner = std::this_thread::get_id(); return; }
     cudaFree(p);
 }
 void cache_trim() {
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
     int dev = 0; cudaGetDevice(&dev);
     std::vector<CacheBlock> keep;
     for (auto& b : g_cache) {

@@ -93,7 +93,7 @@ struct EngineTimes {
 void launch_timer_begin(cudaStream_t st);
 void launch_timer_end(cudaStream_t st, uint64_t cells);
 void launch_timer_flush();
-extern EngineTimes g_times;
+extern thread_local EngineTimes g_times;   // timings of the last bulk call made by this host thread
 
 // Products taken on the fly, right after a dense row has been computed, against the OTHER direction's stored sparse
 // row (forward row r pairs with backward row r+1, table.rs:500-505).  Lets the dense rows live in two ping-pong slabs.

@@ -13,14 +13,12 @@
 #include "engine.h"
 
 static thread_local std::string g_error;
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 void dbg_set_error(const std::string& s) { g_error = s; }
 
 extern "C" const char* dbgphmm_last_error(void) { return g_error.c_str(); }
 extern "C" uint64_t dbgphmm_launch_count(int reset) {
-    uint64_t c = g_launch_count;
-    if (reset) g_launch_count = 0;
-    return c;
+    return reset ? g_launch_count.exchange(0) : g_launch_count.load();
 }
 extern "C" int dbgphmm_device_count(void) {
     int n = 0;

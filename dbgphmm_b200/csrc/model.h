@@ -1,5 +1,6 @@
 // model.h — host-side structures of the device graph (internal; the public surface is include/dbgphmm_b200.h)
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -22,8 +23,8 @@ void dbg_set_error(const std::string& s);
         if (_s != DBGPHMM_OK) return _s; \
     } while (0)
 
-extern unsigned long long g_launch_count;
-#define COUNT_LAUNCH() (++g_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;
+#define COUNT_LAUNCH() (g_launch_count.fetch_add(1, std::memory_order_relaxed))
 
 // Tiling plan of the dense DP for one direction.  A chunk is a run of consecutive (relabelled) nodes; its
 // local set adds every node within HALO_HOPS hops upstream (forward: ancestors, backward: descendants), sorted

@@ -14,7 +14,9 @@
  *     which fixes the parent/child iteration order (graph/iterators.rs:104-155).
  *   - host pointers in, host pointers out, unless the name ends in _dev.
  *   - handles are immutable after creation except where stated; a handle may be used from one host
- *     thread at a time.  All GPU work of a call is finished when it returns.
+ *     thread at a time, different handles from different threads (the device-memory cache shared by the
+ *     handles of a process is locked; dbgphmm_last_timing / dbgphmm_last_dense_kernel report the calling
+ *     thread's last bulk call).  All GPU work of a call is finished when it returns.
  *   - there is NO CPU fallback: every call fails with DBGPHMM_ERR_CUDA if no sm_100-class device exists.
  */
 #ifndef DBGPHMM_B200_H

@@ -11,6 +11,7 @@ def test_cpp_mirror_compiles_and_links(tmp_path):
     B.build()
     src = tmp_path / "t.cpp"
     src.write_text(r'''#include "dbgphmm_b200.hpp"
+#include <cmath>
 int main() {
     auto p = dbgphmm::uniform(0.01);
     if (!(p.n_max_gaps == 4 && p.n_active_nodes == 40)) return 1;
@@ -23,6 +24,21 @@ int main() {
     auto d2 = dbgphmm::MultiDbg::from_dbg_str(d->to_dbg_string());
     if (d2->to_dbg_string() != d->to_dbg_string()) return 4;
     try { d->set_copy_nums({1, 3, 2}); return 5; } catch (const dbgphmm::Error&) {}
+    // Mapping::map_nodes (hint.rs:234-270, case 1: v -> [v + 1]) through the mirror
+    {
+        const uint64_t read_off[2] = {0, 2}, row_off[3] = {0, 2, 4};
+        const uint32_t nodes[4] = {0, 1, 2, 3};
+        const double logp[4] = {std::log(0.6), std::log(0.4), std::log(0.9), std::log(0.1)};
+        dbgphmm_mappings* h = nullptr;
+        if (dbgphmm_mappings_create(1, read_off, row_off, nodes, logp, &h) != DBGPHMM_OK) return 6;
+        dbgphmm::Mappings mp(h);
+        dbgphmm::Mappings m1 = mp.map_nodes({{1}, {2}, {3}, {4}});
+        uint64_t nr = 0, nrow = 0, nent = 0;
+        if (dbgphmm_mappings_sizes(m1.handle(), &nr, &nrow, &nent) != DBGPHMM_OK || nr != 1 || nrow != 2 || nent != 4) return 7;
+        uint64_t ro[2], rw[3]; uint32_t nd[4]; double lp[4];
+        if (dbgphmm_mappings_export(m1.handle(), ro, rw, nd, lp) != DBGPHMM_OK) return 8;
+        if (!(nd[0] == 1 && nd[1] == 2 && nd[2] == 3 && nd[3] == 4 && lp[0] == logp[0] && lp[3] == logp[3])) return 9;
+    }
     return 0;
 }
 ''')

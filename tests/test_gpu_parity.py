@@ -9,7 +9,7 @@ import pytest
 from dbgphmm_b200 import graphs, synth
 from oracle import oracle as O
 from tests.common import (REL_TOL, assert_rows_match, assert_tables_match, close_log, gpu_model, kat, oracle_model,
-                          oracle_params, random_linear_graph, row_order_exact, same_up_to_ties)
+                          oracle_params, random_linear_graph, row_order_exact, same_up_to_ties, to_gpu_params)
 
 pytestmark = pytest.mark.gpu
 K = kat()
@@ -166,6 +166,78 @@ def test_dense_selection_through_the_tile_prefilter(H, monkeypatch, n_active):
             a, b = gf.top_nodes_by_score_ratio(r, 30.0), of.top_nodes_by_score_ratio(r, 30.0)
             assert same_up_to_ties(a, b, merged[b]), (flag, r, list(a), list(b))
     assert H.launch_count() > before
+
+
+def test_two_handles_driven_from_two_host_threads(H):
+    """The reference's model is Sync and shared by rayon threads; here a handle belongs to one host thread at a time, but different
+    handles may run concurrently (include/dbgphmm_b200.h): the device-memory cache they share must not hand a block of one
+    thread's in-flight work to the other."""
+    import threading
+    w = _dbg_case(5, glen=2000, k=16, read_len=200, n_reads=6)
+    par = oracle_params(0.01, n_warmup=w.k)
+    models = [gpu_model(w.graph, par) for _ in range(2)]
+    reads = [H.Reads(w.reads) for _ in range(2)]
+    ref = models[0].run_node_freqs(reads[0], "sparse")
+    out, err = [None, None], []
+
+    def work(i):
+        try:
+            for mode in ("sparse", "dense", "sparse"):
+                r = models[i].run_node_freqs(reads[i], mode)
+                if mode == "sparse":
+                    out[i] = r
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not err, err
+    for o in out:
+        assert np.allclose(o[0], ref[0], rtol=1e-12, atol=1e-15)
+        assert np.array_equal(o[1], ref[1]) and np.array_equal(o[2], ref[2])
+
+
+def _table_diff(a, b, n_nodes):
+    """PHMMTable::diff (table.rs:183-191): sum of |pa - pb| over m, i, d and the three scalars, in linear space."""
+    def dense(r):
+        if r.is_dense:
+            return np.exp(r.m), np.exp(r.i), np.exp(r.d)
+        m = np.zeros(n_nodes); i = np.zeros(n_nodes); d = np.zeros(n_nodes)
+        m[r.ids] = np.exp(r.m); i[r.ids] = np.exp(r.i); d[r.ids_d] = np.exp(r.d)
+        return m, i, d
+    x, y = dense(a), dense(b)
+    t = sum(np.abs(u - v).sum() for u, v in zip(x, y))
+    return t + sum(abs(np.exp(u) - np.exp(v)) for u, v in ((a.mb, b.mb), (a.ib, b.ib), (a.e, b.e)))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_dense_and_sparse_tables_sweep_of_the_reference(H, seed):
+    """tests/hmm.rs:141-214 (hmmv2_forward_dense_and_sparse / hmmv2_backward_dense_and_sparse, #[ignore]d there for their run time):
+    1000-node random linear PHMM, 100-base reads, (n_warmup, n_active_nodes) in [(10,10), (20,10), (40,10), (40,40), (40,80)]:
+    the sparse tables equal the dense ones exactly inside the warm-up and differ by < 1e-6 at the far end."""
+    sg, seq = random_linear_graph(1000, 2)
+    rng = np.random.default_rng(seed)
+    start = int(rng.integers(0, 900))
+    read = bytearray(seq[start:start + 100])
+    for pos in rng.integers(0, 100, 2):   # a couple of substitutions, like a sampled read at p = 0.01
+        read[pos] = b"ACGT"[(b"ACGT".index(read[pos]) + 1) % 4]
+    read = bytes(read)
+    g = gpu_model(sg, oracle_params(0.01))
+    fd, bd = g.forward(read), g.backward(read)
+    n = len(read)
+    for n_warmup, n_active in [(10, 10), (20, 10), (40, 10), (40, 40), (40, 80)]:
+        g.set_params(to_gpu_params(oracle_params(0.01, n_warmup=n_warmup, n_active=n_active)))
+        fs, bs = g.forward_sparse(read, False), g.backward_sparse(read)
+        for i in range(n):
+            if i < n_warmup:
+                assert fs.row(i).is_dense and _table_diff(fd.row(i), fs.row(i), sg.n_nodes) == 0.0, (n_warmup, n_active, i)
+            if n - i < n_warmup:
+                assert bs.row(i).is_dense and _table_diff(bd.row(i), bs.row(i), sg.n_nodes) == 0.0, (n_warmup, n_active, i)
+        assert _table_diff(fd.row(n - 1), fs.row(n - 1), sg.n_nodes) < 1e-6, (n_warmup, n_active)
+        assert _table_diff(bd.row(0), bs.row(0), sg.n_nodes) < 1e-6, (n_warmup, n_active)
 
 
 def test_top_nodes_of_rows(H):
