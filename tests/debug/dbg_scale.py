@@ -1,5 +1,6 @@
+"""Ad-hoc check of the fast dense kernels against the exact one on a scaled C3 graph (test infrastructure)."""
 import os, sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dbgphmm_b200 import hmmv2 as H
 from dbgphmm_b200 import synth
 from tests.common import gpu_model, oracle_params

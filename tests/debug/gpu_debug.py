@@ -1,6 +1,6 @@
-"""Ad-hoc GPU-vs-oracle diagnostics (prints the first divergence in detail)."""
+"""Ad-hoc GPU-vs-oracle diagnostics (prints the first divergence in detail).  Test infrastructure: lives under tests/ because it uses the oracle."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from dbgphmm_b200 import hmmv2 as H, synth, graphs
 from oracle import oracle as O
