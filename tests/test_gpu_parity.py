@@ -240,6 +240,35 @@ def test_dense_and_sparse_tables_sweep_of_the_reference(H, seed):
         assert _table_diff(bd.row(0), bs.row(0), sg.n_nodes) < 1e-6, (n_warmup, n_active)
 
 
+def test_cuda_matches_the_committed_oracle_fixture(H):
+    """tests/golden/oracle_c2_small.json (written by tests/golden/make_oracle_fixture.py from the CPU oracle): ln P(R|X) and node
+    frequencies within 1e-9 relative (north_star), active-node sets of the stored rows identical."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_fixture", os.path.join(here, "golden", "make_oracle_fixture.py"))
+    fx = importlib.util.module_from_spec(spec); spec.loader.exec_module(fx)
+    with open(os.path.join(here, "golden", "oracle_c2_small.json")) as fh:
+        gold = json.load(fh)
+    w, par, _ = fx.build()
+    assert w.graph.n_nodes == gold["n_nodes"] and [len(r) for r in w.reads] == gold["read_lens"]
+    g = gpu_model(w.graph, par)
+    fr, lf, lb, cells = g.run_node_freqs(H.Reads(w.reads), "sparse")
+    assert np.allclose(lf, gold["logp_forward"], rtol=REL_TOL, atol=0) and np.allclose(lb, gold["logp_backward"], rtol=REL_TOL, atol=0)
+    assert abs(fr.sum() - gold["node_freq_sum"]) <= REL_TOL * gold["node_freq_sum"]
+    for i, v in gold["node_freq_top"]:
+        assert abs(fr[i] - v) <= REL_TOL * max(1.0, abs(v)), (i, fr[i], v)
+    for ri in (0, 1):
+        f, b = g.forward_sparse(w.reads[ri], False), g.backward_sparse(w.reads[ri])
+        for x in (x for x in gold["rows"] if x["read"] == ri):
+            fr_, br_ = f.row(x["row"]), b.row(x["bwd_row"])
+            assert fr_.is_dense == x["fwd_is_dense"] and br_.is_dense == x["bwd_is_dense"]
+            assert sorted(int(v) for v in fr_.ids) == x["fwd_ids"] and sorted(int(v) for v in fr_.ids_d) == x["fwd_ids_d"], (ri, x["row"])
+            assert sorted(int(v) for v in br_.ids) == x["bwd_ids"] and sorted(int(v) for v in br_.ids_d) == x["bwd_ids_d"], (ri, x["bwd_row"])
+            assert abs(fr_.e - x["fwd_e"]) <= REL_TOL * abs(x["fwd_e"]) and abs(br_.mb - x["bwd_mb"]) <= REL_TOL * abs(x["bwd_mb"])
+
+
 def test_top_nodes_of_rows(H):
     w = _dbg_case(2)
     par = oracle_params(0.01, n_warmup=w.k)

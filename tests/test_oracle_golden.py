@@ -186,3 +186,38 @@ def test_hmm_crossing_edge_on_off(flag):
         else:
             for e in ((9, 20), (9, 30), (19, 20), (19, 30)):
                 assert abs(t[e] - np.log(0.5)) < 1e-12, (which, e)
+
+
+def _load_fixture_module():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_oracle_fixture.py")
+    spec = importlib.util.spec_from_file_location("make_oracle_fixture", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_oracle_reproduces_its_committed_fixture():
+    """tests/golden/oracle_c2_small.json (scaled-down C2: sparse mode, n_active_nodes = 40, n_warmup = k) is what the GPU parity
+    test compares against as well; here the oracle must still produce it (index sets exactly, values to 1e-12)."""
+    import json
+    import os
+    fx = _load_fixture_module()
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_c2_small.json")) as fh:
+        gold = json.load(fh)
+    w, par, o = fx.build()
+    assert w.graph.n_nodes == gold["n_nodes"] and w.graph.n_edges == gold["n_edges"] and [len(r) for r in w.reads] == gold["read_lens"]
+    fr, lf, lb = o.run_node_freqs(O.Reads(w.reads), "sparse")
+    assert np.allclose(lf, gold["logp_forward"], rtol=1e-12, atol=0) and np.allclose(lb, gold["logp_backward"], rtol=1e-12, atol=0)
+    assert abs(fr.sum() - gold["node_freq_sum"]) < 1e-9 * gold["node_freq_sum"]
+    for i, v in gold["node_freq_top"]:
+        assert abs(fr[i] - v) <= 1e-12 * max(1.0, abs(v))
+    for ri in (0, 1):
+        f, b = o.forward_sparse(w.reads[ri], False), o.backward_sparse(w.reads[ri])
+        for g in (g for g in gold["rows"] if g["read"] == ri):
+            fr_, br_ = f.row(g["row"]), b.row(g["bwd_row"])
+            assert fr_.is_dense == g["fwd_is_dense"] and br_.is_dense == g["bwd_is_dense"]
+            assert sorted(int(x) for x in fr_.ids) == g["fwd_ids"] and sorted(int(x) for x in fr_.ids_d) == g["fwd_ids_d"]
+            assert sorted(int(x) for x in br_.ids) == g["bwd_ids"] and sorted(int(x) for x in br_.ids_d) == g["bwd_ids_d"]
+            assert abs(fr_.e - g["fwd_e"]) <= 1e-12 * abs(g["fwd_e"]) and abs(br_.mb - g["bwd_mb"]) <= 1e-12 * abs(g["bwd_mb"])
