@@ -48,12 +48,15 @@ __device__ __forceinline__ void row_at(const RowView& v, const uint32_t* sh_ids,
     *m = *i = *d = 0.0; *ex = 0;
 }
 
-// ---- node frequencies, rows where at least one side is sparse
+// ---- node frequencies, rows where at least one side is sparse.  One WARP per merged row (a sparse row holds ~50 entries), four
+// rows per CTA: a CTA per row spent most of the launch on CTA scheduling (10^7 CTAs of one busy warp each on the C3 workload).
+#define PROD_ROWS_PER_CTA 4
 __global__ void k_prod_rows_freq(ProdCtx C, double* __restrict__ freq, int* __restrict__ err) {
-    const uint32_t j = blockIdx.y, r = blockIdx.x;
-    if (r >= C.len[j]) return;
+    const uint32_t j = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * PROD_ROWS_PER_CTA + w;
+    if (r >= C.len[j]) return;   // (whole warps leave ; no block-wide barrier below)
     const XF P = C.P[j];
-    if (P.v == 0.0) { if (threadIdx.x == 0) *err = 1; return; }
+    if (P.v == 0.0) { if (lane == 0) *err = 1; return; }
     const RowDesc fr = C.fdesc[C.fdesc0[j] + r];
     RowDesc br;
     if (r + 1 < C.len[j]) br = C.bdesc[C.bdesc0[j] + r + 1]; else { br.kind = 3; br.n_ent = 0; br.n_mi = 0; br.n_d = 0; br.off = 0; }
@@ -61,19 +64,20 @@ __global__ void k_prod_rows_freq(ProdCtx C, double* __restrict__ freq, int* __re
     if ((fr.kind == ROW_DENSE && !C.f_dense_ok) || (br.kind == ROW_DENSE && !C.b_dense_ok)) return;  // taken by step_products
     const RowView F = view_row(fr, C.farena, C.fpool, C.fslab_bytes, C.fNp);
     const RowView B = view_row(br, C.barena, C.bpool, C.bslab_bytes, C.bNp);
-    __shared__ uint32_t sh_ids[PROD_MAXE];
+    __shared__ uint32_t sh_all[PROD_ROWS_PER_CTA][PROD_MAXE];
+    uint32_t* sh_ids = sh_all[w];
     const RowView& it = (fr.kind == ROW_SPARSE) ? F : B;      // iterate the sparse operand (lhs if both sparse)
     const RowView& other = (fr.kind == ROW_SPARSE) ? B : F;
-    if (other.kind == ROW_SPARSE) for (uint32_t e = threadIdx.x; e < other.n_ent && e < PROD_MAXE; e += blockDim.x) sh_ids[e] = other.id[e];
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < it.n_ent; e += blockDim.x) {
+    if (other.kind == ROW_SPARSE) for (uint32_t e = lane; e < other.n_ent && e < PROD_MAXE; e += 32) sh_ids[e] = other.id[e];
+    __syncwarp();
+    for (uint32_t e = lane; e < it.n_ent; e += 32) {
         uint32_t id = it.id[e];
         double m2, i2, d2; int e2;
         row_at(other, sh_ids, id, C.p_end, &m2, &i2, &d2, &e2);
         double v = it.m[e] * m2 + it.i[e] * i2 + it.d[e] * d2;
         if (v > 0.0) {
-            double w = (v / P.v) * pow2i(it.ex[e] + e2 - P.e);
-            if (w > 0.0) atomicAdd(&freq[C.orig_of[id]], w);
+            double w2 = (v / P.v) * pow2i(it.ex[e] + e2 - P.e);
+            if (w2 > 0.0) atomicAdd(&freq[C.orig_of[id]], w2);
         }
     }
 }
@@ -389,8 +393,8 @@ int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const Ro
     uint32_t maxlen = 0;
     for (uint32_t j = 0; j < J; j++) maxlen = std::max(maxlen, F.len[j]);
     if (maxlen) {
-        dim3 g(maxlen, J);
-        k_prod_rows_freq<<<g, 128, 0, st>>>(C, d_freqs, pb.err.as<int>()); COUNT_LAUNCH();
+        dim3 g((maxlen + PROD_ROWS_PER_CTA - 1) / PROD_ROWS_PER_CTA, J);
+        k_prod_rows_freq<<<g, 32 * PROD_ROWS_PER_CTA, 0, st>>>(C, d_freqs, pb.err.as<int>()); COUNT_LAUNCH();
     }
     std::vector<DensePair> pairs;
     std::vector<uint64_t> dummy;
