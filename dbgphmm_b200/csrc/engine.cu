@@ -272,6 +272,33 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
     return st;
 }
 
+// Stream strategy, top-n jobs: the cells of the last dense row that the first sparse row can read are gathered into a small per-job
+// list right after the top-n selection, so that the ping-pong slabs are dead before the sparse phase starts (groundwork for running
+// the dense warm-up in groups that share one pool of slabs).  Off unless DBGPHMM_GATHER=1.
+static bool gather_enabled() { const char* e = getenv("DBGPHMM_GATHER"); return e && e[0] == '1'; }
+struct GatherBufs {
+    DevBuf cells, cnt, slabs, ovf;
+    uint32_t cap = 0;
+    bool on = false;
+};
+static int gather_prev0(dbgphmm_model* m, int dir, const std::vector<uint64_t>& slab_of_job, const uint32_t* d_top_ids, const uint32_t* d_top_cnt,
+                        const DensePool& pool, GatherBufs* g) {
+    cudaStream_t st = m->stream;
+    const uint32_t J = (uint32_t)slab_of_job.size();
+    g->cap = sparse_gather_cap(m, m->params.n_active_nodes);
+    ST_TRY(g->cells.alloc((size_t)J * 32 * g->cap)); ST_TRY(g->cnt.alloc(sizeof(uint32_t) * J)); ST_TRY(g->ovf.alloc(sizeof(int)));
+    ST_TRY(dev_upload(g->slabs, slab_of_job, st));
+    CUDA_TRY(cudaMemsetAsync(g->ovf.p, 0, sizeof(int), st));
+    ST_TRY(sparse_gather_prev0(m, dir, J, d_top_ids, d_top_cnt, g->slabs.as<uint64_t>(), pool.base, pool.slab_bytes, pool.Np, g->cap, g->cells.as<char>(),
+                               g->cnt.as<uint32_t>(), g->ovf.as<int>()));
+    int ovf = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ovf, g->ovf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ovf) { dbg_set_error("internal: gathered row outgrew its bound"); return DBGPHMM_ERR_INVALID; }
+    g->on = true;
+    return DBGPHMM_OK;
+}
+
 // ================================================================================================ forward
 int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,
                 const DevMappings* dmap, RowStore* out) {
@@ -328,6 +355,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     std::vector<SelectReq> reqs(J);
     ST_TRY(b_reqs.alloc(sizeof(SelectReq) * J));
     auto slab_of_h = [&](uint32_t j, uint32_t s) { return paired ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    GatherBufs gat;
     delete tr_setup;
     {
         HostTrace t("  fwd dense phase");
@@ -377,6 +405,12 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
             CUDA_TRY(cudaMemcpyAsync(b_reqs.p, reqs.data(), sizeof(SelectReq) * nr, cudaMemcpyHostToDevice, st));
             ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), nr, nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
             CUDA_TRY(cudaStreamSynchronize(st));
+            if (!keep_rows && gather_enabled()) {
+                std::vector<uint64_t> gs(J, ~0ull);
+                for (uint32_t j = 0; j < J; j++) if (jobs[j].len > out->nd[j] && out->nd[j] > 0) gs[j] = slab_of_h(j, out->nd[j] - 1);
+                ST_TRY(gather_prev0(m, 0, gs, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>(), out->pool, &gat));
+                cache_free(out->pool.base); out->pool.base = nullptr;   // the ping-pong slabs are dead already
+            }
         }
     }
     for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
@@ -391,7 +425,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
         s.x = jobs[j].x; s.len = n; s.base_off = jobs[j].base_off; s.dir = 0;
         s.mode = kind == DBGPHMM_FWD_SPARSE ? SP_TOPN : (kind == DBGPHMM_FWD_SPARSE_RATIO ? SP_RATIO : SP_MAPPING);
         s.row_begin = (int32_t)nd; s.n_rows = n - nd;
-        s.prev0_kind = nd == 0 ? SPREV_F_INIT : SPREV_DENSE;
+        s.prev0_kind = nd == 0 ? SPREV_F_INIT : (gat.on ? SPREV_GATHER : SPREV_DENSE);
         s.prev0_slab = nd == 0 ? 0 : slab_of_h(j, nd - 1);
         s.top0 = j; s.desc0 = out->desc0[j]; s.fdesc0 = 0; s.map_row0 = jobs[j].map_row0;
         s.store = store_sparse ? 1 : 0; s.active_idx = -1; s.out_idx = j;
@@ -406,6 +440,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
         io.top_ids = b_top_ids.as<uint32_t>(); io.top_cnt = b_top_cnt.as<uint32_t>();
         io.map_row_off = dmap ? dmap->row_off : nullptr; io.map_nodes = dmap ? dmap->nodes : nullptr;
         io.pool = out->pool.base; io.slab_bytes = out->pool.slab_bytes; io.Np = out->pool.Np;
+        io.gather = gat.cells.as<char>(); io.gather_cap = gat.cap; io.gather_cnt = gat.cnt.as<uint32_t>();
         io.arena = out->arena.base; io.arena_bytes = out->arena.bytes; io.arena_cursor = out->arena.cursor; io.active = nullptr;
         ST_TRY(run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_FWD_MAPPING ? 64 : sparse_default_cap(),
                                store_sparse ? arena_upper(sparse_rows, m->params.n_active_nodes, kind == DBGPHMM_FWD_SPARSE_RATIO) : 0));
@@ -482,6 +517,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
     CUDA_TRY(cudaMemsetAsync(b_top_cnt.p, 0, sizeof(uint32_t) * J, st));
     auto slab_of_h = [&](uint32_t j, uint32_t s) { return paired ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    GatherBufs gat;
 
     auto dense_phase = [&]() -> int {
         HostTrace t("  bwd dense phase");
@@ -524,7 +560,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
             s.store = 1; s.active_idx = -1; s.out_idx = j; s.top0 = j;
             if (kind == DBGPHMM_BWD_SPARSE) {
                 if (lo <= 0) continue;  // all rows dense
-                s.mode = SP_TOPN; s.row_begin = lo - 1; s.n_rows = (uint32_t)lo; s.prev0_kind = SPREV_DENSE; s.prev0_slab = slab_of_h(j, out->nd[j] - 1);
+                s.mode = SP_TOPN; s.row_begin = lo - 1; s.n_rows = (uint32_t)lo; s.prev0_kind = gat.on ? SPREV_GATHER : SPREV_DENSE; s.prev0_slab = slab_of_h(j, out->nd[j] - 1);
             } else if (kind == DBGPHMM_BWD_MAPPING) {
                 s.mode = SP_MAPPING; s.row_begin = n - 1; s.n_rows = (uint32_t)n; s.prev0_kind = SPREV_B_INIT;
             } else if (kind == DBGPHMM_BWD_BY_FORWARD) {
@@ -539,6 +575,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
         io.top_ids = b_top_ids.as<uint32_t>(); io.top_cnt = b_top_cnt.as<uint32_t>();
         io.map_row_off = dmap ? dmap->row_off : nullptr; io.map_nodes = dmap ? dmap->nodes : nullptr;
         io.pool = out->pool.base; io.slab_bytes = out->pool.slab_bytes; io.Np = out->pool.Np;
+        io.gather = gat.cells.as<char>(); io.gather_cap = gat.cap; io.gather_cnt = gat.cnt.as<uint32_t>();
         io.arena = out->arena.base; io.arena_bytes = out->arena.bytes; io.arena_cursor = out->arena.cursor; io.active = nullptr;
         return run_sparse_jobs(m, sj, io, out, kind == DBGPHMM_BWD_MAPPING ? 64 : sparse_default_cap(),
                                arena_upper(sparse_rows, m->params.n_active_nodes, kind == DBGPHMM_BWD_BY_FORWARD));
@@ -552,6 +589,12 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
                 if (out->bdense_lo[j] > 0) { SelectReq r{}; r.slab = slab_of_h(j, out->nd[j] - 1); r.k = m->params.n_active_nodes; r.by_ratio = 0; r.active_idx = -1; r.out = j; reqs.push_back(r); }
             ST_TRY(dev_upload(b_reqs, reqs, st));
             ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), (uint32_t)reqs.size(), nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
+            if (!keep_rows && gather_enabled()) {
+                std::vector<uint64_t> gs(J, ~0ull);
+                for (uint32_t j = 0; j < J; j++) if (out->bdense_lo[j] > 0) gs[j] = slab_of_h(j, out->nd[j] - 1);
+                ST_TRY(gather_prev0(m, 1, gs, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>(), out->pool, &gat));
+                cache_free(out->pool.base); out->pool.base = nullptr;   // the ping-pong slabs are dead already
+            }
         }
         ST_TRY(sparse_phase());
     } else {

@@ -351,6 +351,7 @@ int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* 
         std::vector<uint4> pr(N), cr(N);
         for (uint32_t p = 0; p < N; p++) {
             const uint32_t po = m->par_off[p], pc = m->par_off[p + 1] - po, co = m->chi_off[p], cc = m->chi_off[p + 1] - co;
+            m->max_deg = std::max(m->max_deg, std::max(pc, cc));
             pr[p] = make_uint4(po, pc, pc ? m->par_node[po] : 0u, pc ? m->par_eid[po] : 0u);
             cr[p] = make_uint4(co, cc, cc ? m->chi_node[co] : 0u, cc ? m->chi_eid[co] : 0u);
         }

@@ -87,6 +87,7 @@ struct dbgphmm_model {
     // per node {first CSR slot, degree, first neighbour, its edge id}: one 16-byte load answers the common degree-1 case of the
     // latency-bound sparse kernel (CSR offset -> neighbour -> edge id is a chain of dependent L2 loads otherwise)
     uint4 *d_par_rec = nullptr, *d_chi_rec = nullptr;
+    uint32_t max_deg = 0;       // largest in- or out-degree of a node
     double* d_init = nullptr;   // [n_batch][N] linear, relabelled node order
     double* d_trans = nullptr;  // [n_batch][E] linear, original EdgeIndex order
     DevPlan fwd, bwd;

@@ -367,8 +367,9 @@ __device__ int sp_top_of_prev(SS& S, uint32_t n_prev, uint32_t K, bool by_ratio,
 }
 
 struct PrevAcc {  // accessor of the row before the current one
-    int kind;     // 0 sparse (shared memory), 1 dense slab, 2 B-init, 3 F-init
+    int kind;     // 0 sparse (shared memory), 1 dense slab, 2 B-init, 3 F-init, 4 gathered cells of a dense row
     const double *gm, *gi, *gd; const int* ge;
+    const uint32_t* gid; uint32_t gn;   // kind 4: ids of the gathered cells (unsorted, duplicates allowed) and their number
     double p_end;
 };
 __device__ __forceinline__ void prev_get(const SS& S, const PrevAcc& P, uint32_t id, double* m, double* i, double* d, int* ex) {
@@ -377,6 +378,11 @@ __device__ __forceinline__ void prev_get(const SS& S, const PrevAcc& P, uint32_t
         if (sl < 0) { *m = *i = *d = 0.0; *ex = 0; } else { *m = S.p_m()[sl]; *i = S.p_i()[sl]; *d = S.p_d()[sl]; *ex = S.p_ex()[sl]; }
     } else if (P.kind == 1) { *m = P.gm[id]; *i = P.gi[id]; *d = P.gd[id]; *ex = P.ge[id]; }
     else if (P.kind == 2) { *m = *i = *d = P.p_end; *ex = 0; }
+    else if (P.kind == 4) {   // linear search: this is one row per job, and the list holds every cell that row can ask for
+        *m = *i = *d = 0.0; *ex = 0;
+        for (uint32_t e = 0; e < P.gn; e++)
+            if (P.gid[e] == id) { *m = P.gm[e]; *i = P.gi[e]; *d = P.gd[e]; *ex = P.ge[e]; break; }
+    }
     else { *m = *i = *d = 0.0; *ex = 0; }
 }
 
@@ -489,8 +495,15 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         const int row = fwd ? jb.row_begin + (int)s : jb.row_begin - (int)s;
         const uint8_t x = io.bases[jb.base_off + row];
         PrevAcc PA;
-        PA.p_end = lp.p_end; PA.gm = PA.gi = PA.gd = nullptr; PA.ge = nullptr;
+        PA.p_end = lp.p_end; PA.gm = PA.gi = PA.gd = nullptr; PA.ge = nullptr; PA.gid = nullptr; PA.gn = 0;
         if (s > 0) PA.kind = 0;
+        else if (jb.prev0_kind == SPREV_GATHER) {
+            PA.kind = 4;
+            const char* gl = io.gather + (size_t)jb.top0 * 32 * io.gather_cap;
+            PA.gm = (const double*)gl; PA.gi = PA.gm + io.gather_cap; PA.gd = PA.gi + io.gather_cap;
+            PA.gid = (const uint32_t*)(PA.gd + io.gather_cap); PA.ge = (const int*)(PA.gid + io.gather_cap);
+            PA.gn = io.gather_cnt[jb.top0];
+        }
         else if (jb.prev0_kind == SPREV_DENSE) {
             PA.kind = 1;
             const char* sl = io.pool + jb.prev0_slab * io.slab_bytes;
@@ -808,6 +821,60 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     if (role == 0 && !io.rq_ctl) return;
     __syncthreads();
   }
+}
+
+// ---- gather of the cells of the last dense row that step 0 of a top-n job can read (sparse.h)
+__global__ void k_gather_prev0(SGraph G, int dir, const uint32_t* __restrict__ top_ids, const uint32_t* __restrict__ top_cnt, const uint64_t* __restrict__ slabs,
+                               const char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np, uint32_t cap, char* __restrict__ out,
+                               uint32_t* __restrict__ out_cnt, int* __restrict__ overflow) {
+    const uint32_t j = blockIdx.x;
+    if (slabs[j] == ~0ull) { if (threadIdx.x == 0) out_cnt[j] = 0; return; }
+    const char* sl = pool + slabs[j] * slab_bytes;
+    const double* gm = (const double*)sl; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
+    char* o = out + (size_t)j * 32 * cap;
+    double* om = (double*)o; double* oi = om + cap; double* od = oi + cap; uint32_t* oid = (uint32_t*)(od + cap); int* oex = (int*)(oid + cap);
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    auto emit = [&](uint32_t g) {
+        const uint32_t k = atomicAdd(&s_n, 1u);
+        if (k < cap) { oid[k] = g; om[k] = gm[g]; oi[k] = gi[g]; od[k] = gd[g]; oex[k] = ge[g]; }
+    };
+    // forward step 0 reads nodes = top + children(top) and their parents (fm, fi) ; backward step 0 reads A0 = top + parents(top) and
+    // their children (bd0, bm, bi).  `near` is the direction of the node list, `far` the direction of the reads.
+    const uint4* near_rec = dir == 0 ? G.chi_rec : G.par_rec; const uint32_t* near_node = dir == 0 ? G.chi_node : G.par_node;
+    const uint4* far_rec = dir == 0 ? G.par_rec : G.chi_rec;  const uint32_t* far_node = dir == 0 ? G.par_node : G.chi_node;
+    const uint32_t n_top = top_cnt[j];
+    for (uint32_t t = threadIdx.x; t < n_top; t += blockDim.x) {
+        const uint32_t id = top_ids[(size_t)j * MAX_ACTIVE + t];
+        emit(id);
+        const uint4 rf = far_rec[id];
+        for (uint32_t a = 0; a < rf.y; a++) emit(a ? far_node[rf.x + a] : rf.z);
+        const uint4 rn = near_rec[id];
+        for (uint32_t a = 0; a < rn.y; a++) {
+            const uint32_t c = a ? near_node[rn.x + a] : rn.z;
+            emit(c);
+            const uint4 rc = far_rec[c];
+            for (uint32_t b = 0; b < rc.y; b++) emit(b ? far_node[rc.x + b] : rc.z);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { out_cnt[j] = s_n < cap ? s_n : cap; if (s_n > cap) *overflow = 1; }
+}
+uint32_t sparse_gather_cap(const dbgphmm_model* m, uint32_t k) {
+    const uint64_t D = m->max_deg;
+    const uint64_t c = (uint64_t)k * (1 + 2 * D + D * D);
+    return (uint32_t)((std::min<uint64_t>(c, 1u << 24) + 1) & ~1ull);
+}
+int sparse_gather_prev0(dbgphmm_model* m, int dir, uint32_t n_slots, const uint32_t* d_top_ids, const uint32_t* d_top_cnt, const uint64_t* d_slabs,
+                        const char* pool, uint64_t slab_bytes, uint32_t Np, uint32_t cap, char* d_out, uint32_t* d_out_cnt, int* d_overflow) {
+    if (n_slots == 0) return DBGPHMM_OK;
+    SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
+             m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of, m->d_par_rec, m->d_chi_rec};
+    k_gather_prev0<<<n_slots, 64, 0, m->stream>>>(G, dir, d_top_ids, d_top_cnt, d_slabs, pool, slab_bytes, Np, cap, d_out, d_out_cnt, d_overflow);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return DBGPHMM_OK;
 }
 
 static size_t sparse_smem_bytes(uint32_t cap, uint32_t hcap) { return SS_BYTES(cap, hcap); }

@@ -8,7 +8,8 @@ enum {  // node-list source of a sparse step
     SP_MAPPING = 2,  // mapping.nodes(i), non-adaptive                                (forward.rs:71, backward.rs:84)
     SP_BYFWD = 3     // filled_nodes() of forward row i-1, non-adaptive (backward)    (backward.rs:128-133)
 };
-enum { SPREV_F_INIT = 0, SPREV_B_INIT = 1, SPREV_DENSE = 2 };
+enum { SPREV_F_INIT = 0, SPREV_B_INIT = 1, SPREV_DENSE = 2,
+       SPREV_GATHER = 3 };   // the cells of the last dense row that step 0 can read, gathered into a per-job list (sparse_gather_prev0)
 enum { SJ_OK = 0, SJ_NEED_BIG = 1, SJ_CAPACITY = 2, SJ_OOM = 3 };
 
 struct SJob {
@@ -55,6 +56,7 @@ struct SparseIO {
     const uint64_t* map_row_off;  // mapping CSR (device): row -> entries
     const uint32_t* map_nodes;    // relabelled node ids
     const char* pool; uint64_t slab_bytes; uint32_t Np;  // dense pool (SPREV_DENSE)
+    const char* gather; uint32_t gather_cap; const uint32_t* gather_cnt;   // SPREV_GATHER: per request slot m, i, d [cap] f64, id, ex [cap] 32-bit ; entries in use
     char* arena; uint64_t arena_bytes; unsigned long long* arena_cursor;
     int* status;               // per job SJ_*
     XF* final_scalar;          // per job: forward -> e of the last row ; backward -> mb of row 0
@@ -80,5 +82,12 @@ uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap);
 // outgrow `cap` (io.rq_* must be set up by the caller); 0: no rescue launch.
 // dir: SJob::dir of every job of the launch (0 forward, 1 backward)
 int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap, int dir, uint32_t rescue_cap = 0);
+// Gather, for every request slot j with slabs[j] != ~0, the cells of dense row slabs[j] that step 0 of a top-n job started from
+// top_ids[j] can read (forward: top, children(top) and the parents of both ; backward: top, parents(top) and the children of
+// both) into out + j * 32 * cap.  cap must be sparse_gather_cap(m, k) for lists of at most k ids.  *d_overflow is raised if a list
+// outgrows cap (cannot happen for that cap).  With these lists the dense slabs are not needed during the sparse phase.
+uint32_t sparse_gather_cap(const dbgphmm_model* m, uint32_t k);
+int sparse_gather_prev0(dbgphmm_model* m, int dir, uint32_t n_slots, const uint32_t* d_top_ids, const uint32_t* d_top_cnt, const uint64_t* d_slabs,
+                        const char* pool, uint64_t slab_bytes, uint32_t Np, uint32_t cap, char* d_out, uint32_t* d_out_cnt, int* d_overflow);
 // capacity of the rescue launch that accompanies a primary launch of capacity `cap` (0: none)
 uint32_t sparse_rescue_cap(uint32_t cap);

@@ -269,6 +269,25 @@ def test_cuda_matches_the_committed_oracle_fixture(H):
             assert abs(fr_.e - x["fwd_e"]) <= REL_TOL * abs(x["fwd_e"]) and abs(br_.mb - x["bwd_mb"]) <= REL_TOL * abs(x["bwd_mb"])
 
 
+def test_gathered_first_sparse_row_inputs_match_the_dense_slab(H, monkeypatch):
+    """DBGPHMM_GATHER=1 (engine.cu: gather_prev0): the first sparse row of a top-n job reads the last dense row through a per-job
+    list of gathered cells instead of the slab, which is released before the sparse phase.  Same active sets, hence the very same
+    numbers, as the default path (and as the oracle, through the other tests of the stream strategy)."""
+    w = _dbg_case(9, glen=4000, k=16, het=0.02, read_len=300, n_reads=6)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g = gpu_model(w.graph, par)
+    reads = H.Reads(w.reads)
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
+    a = g.run_node_freqs(reads, "sparse")
+    monkeypatch.setenv("DBGPHMM_GATHER", "1")
+    b = g.run_node_freqs(reads, "sparse")
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-15)
+    of, olf, olb = oracle_model(w.graph, par).run_node_freqs(O.Reads(w.reads), "sparse")
+    assert np.allclose(b[1], olf, rtol=REL_TOL, atol=0) and np.allclose(b[2], olb, rtol=REL_TOL, atol=0)
+    assert np.allclose(b[0], of, rtol=REL_TOL, atol=1e-12)
+
+
 def test_top_nodes_of_rows(H):
     w = _dbg_case(2)
     par = oracle_params(0.01, n_warmup=w.k)
