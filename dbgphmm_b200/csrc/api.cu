@@ -542,16 +542,27 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
     for (uint64_t r = 0; r < R; r++) { store_total += bytes[r]; if (all[r].len < 2 * W + 2) can_stream = false; }
     bool stream = can_stream && store_total > m->mem_budget;
     if (const char* e = getenv("DBGPHMM_STRATEGY")) { if (!strcmp(e, "stream")) stream = can_stream; else if (!strcmp(e, "store")) stream = false; }
+    // DBGPHMM_DENSE_GROUP=G (stream strategy): the dense warm-up and the recompute passes run in groups of G jobs that share one pool
+    // of 2 G slabs (engine.cu), so a batch is sized by its sparse rows and can fill the sparse kernel's waves on large graphs
+    uint32_t group = 0;
+    uint64_t plan_budget = m->mem_budget;
     if (stream) {
+        if (const char* e = getenv("DBGPHMM_DENSE_GROUP")) { const int g = atoi(e); if (g > 0) group = (uint32_t)g; }
         const uint64_t slab = dense_slab_bytes(m->N);
         const uint64_t per_row = (uint64_t)m->params.n_active_nodes * 48 + 256 + 3 * sizeof(RowDesc);   // (arena_estimate, engine.cu)
-        for (uint64_t r = 0; r < R; r++) bytes[r] = 2 * slab + 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20);
+        const uint64_t dense_part = group ? (uint64_t)32 * sparse_gather_cap(m, m->params.n_active_nodes) + 64 * (uint64_t)m->fwd.n_chunks : 2 * slab;
+        for (uint64_t r = 0; r < R; r++) bytes[r] = dense_part + 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20);
+        if (group) {
+            const uint64_t pool = 2 * (uint64_t)group * slab;
+            if (pool + (plan_budget >> 3) > plan_budget) { dbg_set_error("DBGPHMM_DENSE_GROUP: the group's slabs do not fit the memory budget"); return DBGPHMM_ERR_OOM; }
+            plan_budget -= pool;
+        }
     }
     // Batches in read order.  A batch that runs out of device memory before anything of it has been accumulated (the estimates
     // above are for typical rows) is split in two and tried again.
     std::vector<std::pair<size_t, size_t>> work;
     {
-        auto planned = plan_batches(bytes, m->mem_budget, 65535, mode == DBGPHMM_RUN_DENSE ? 0 : sparse_wave_jobs(m, sparse_default_cap()));
+        auto planned = plan_batches(bytes, plan_budget, 65535, mode == DBGPHMM_RUN_DENSE ? 0 : sparse_wave_jobs(m, sparse_default_cap()));
         work.assign(planned.rbegin(), planned.rend());   // (a stack: the first batch on top)
     }
     while (!work.empty()) {
@@ -572,19 +583,19 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
             DevBuf b_err;
             st = b_err.alloc(sizeof(int));
             if (st == DBGPHMM_OK && cudaMemsetAsync(b_err.p, 0, sizeof(int), m->stream) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
-            PhaseOpts pf; pf.keep_rows = false; pf.store_sparse = true;
+            PhaseOpts pf; pf.keep_rows = false; pf.store_sparse = true; pf.group = group;
             if (st == DBGPHMM_OK) st = run_forward(m, jobs, reads->d_bases, fk, pf, nullptr, &F);                    // F: sparse rows stored
             // B dense x F sparse: on the fly after every dense backward step, or (when the two-rows-per-launch kernels are available,
             // which never write the intermediate rows) by a recompute pass inside the dependency cone like the forward one below
             const bool b_recompute = dense_can_pair(m);
             StepProducts spb; spb.other = &F; spb.P = F.d_final; spb.d_freqs = d_freqs; spb.d_err = b_err.as<int>();
-            PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = b_recompute ? nullptr : &spb;
+            PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = b_recompute ? nullptr : &spb; pb.group = group;
             if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);
             if (st == DBGPHMM_OK || !b_recompute) accumulated = true;
-            if (st == DBGPHMM_OK && b_recompute) st = run_backward_recompute(m, jobs, reads->d_bases, F, B, spb);
+            if (st == DBGPHMM_OK && b_recompute) st = run_backward_recompute(m, jobs, reads->d_bases, F, B, spb, group);
             if (st == DBGPHMM_OK) st = run_products_freqs(m, jobs, F, B, d_freqs);                                    // sparse x sparse, F sparse x b_init
             StepProducts spf; spf.other = &B; spf.P = F.d_final; spf.d_freqs = d_freqs; spf.d_err = b_err.as<int>();
-            if (st == DBGPHMM_OK) st = run_forward_recompute(m, jobs, reads->d_bases, F, B, spf);                    // F dense (cone only) x B sparse
+            if (st == DBGPHMM_OK) st = run_forward_recompute(m, jobs, reads->d_bases, F, B, spf, group);                    // F dense (cone only) x B sparse
             int err = 0;
             if (st == DBGPHMM_OK && cudaMemcpy(&err, b_err.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
             if (st == DBGPHMM_OK && err) { dbg_set_error("P(read) == 0: emit probabilities are NaN in the reference (table.rs:500-505)"); st = DBGPHMM_ERR_ZERO_PROB; }

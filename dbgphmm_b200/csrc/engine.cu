@@ -273,29 +273,34 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
 }
 
 // Stream strategy, top-n jobs: the cells of the last dense row that the first sparse row can read are gathered into a small per-job
-// list right after the top-n selection, so that the ping-pong slabs are dead before the sparse phase starts (groundwork for running
-// the dense warm-up in groups that share one pool of slabs).  Off unless DBGPHMM_GATHER=1.
+// list right after the top-n selection, so that the ping-pong slabs are dead before the sparse phase starts -- and the dense warm-up
+// can run in GROUPS of jobs that share one pool of slabs (PhaseOpts::group), which decouples the number of jobs of the sparse phase
+// from the 2 x 28 B x N a job's slabs take.  Gathering alone: DBGPHMM_GATHER=1 ; groups: DBGPHMM_DENSE_GROUP.
 static bool gather_enabled() { const char* e = getenv("DBGPHMM_GATHER"); return e && e[0] == '1'; }
 struct GatherBufs {
     DevBuf cells, cnt, slabs, ovf;
     uint32_t cap = 0;
     bool on = false;
 };
-static int gather_prev0(dbgphmm_model* m, int dir, const std::vector<uint64_t>& slab_of_job, const uint32_t* d_top_ids, const uint32_t* d_top_cnt,
+static int gather_init(dbgphmm_model* m, uint32_t J, GatherBufs* g) {
+    g->cap = sparse_gather_cap(m, m->params.n_active_nodes);
+    ST_TRY(g->cells.alloc((size_t)J * 32 * g->cap)); ST_TRY(g->cnt.alloc(sizeof(uint32_t) * std::max<uint32_t>(J, 1))); ST_TRY(g->ovf.alloc(sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(g->cnt.p, 0, sizeof(uint32_t) * std::max<uint32_t>(J, 1), m->stream));
+    CUDA_TRY(cudaMemsetAsync(g->ovf.p, 0, sizeof(int), m->stream));
+    g->on = true;
+    return DBGPHMM_OK;
+}
+// slab_of_job[i]: the last dense row of job g0 + i (~0: none)
+static int gather_group(dbgphmm_model* m, int dir, uint32_t g0, const std::vector<uint64_t>& slab_of_job, const uint32_t* d_top_ids, const uint32_t* d_top_cnt,
                         const DensePool& pool, GatherBufs* g) {
     cudaStream_t st = m->stream;
-    const uint32_t J = (uint32_t)slab_of_job.size();
-    g->cap = sparse_gather_cap(m, m->params.n_active_nodes);
-    ST_TRY(g->cells.alloc((size_t)J * 32 * g->cap)); ST_TRY(g->cnt.alloc(sizeof(uint32_t) * J)); ST_TRY(g->ovf.alloc(sizeof(int)));
     ST_TRY(dev_upload(g->slabs, slab_of_job, st));
-    CUDA_TRY(cudaMemsetAsync(g->ovf.p, 0, sizeof(int), st));
-    ST_TRY(sparse_gather_prev0(m, dir, J, d_top_ids, d_top_cnt, g->slabs.as<uint64_t>(), pool.base, pool.slab_bytes, pool.Np, g->cap, g->cells.as<char>(),
-                               g->cnt.as<uint32_t>(), g->ovf.as<int>()));
+    ST_TRY(sparse_gather_prev0(m, dir, g0, (uint32_t)slab_of_job.size(), d_top_ids, d_top_cnt, g->slabs.as<uint64_t>(), pool.base, pool.slab_bytes, pool.Np, g->cap,
+                               g->cells.as<char>(), g->cnt.as<uint32_t>(), g->ovf.as<int>()));
     int ovf = 0;
     CUDA_TRY(cudaMemcpyAsync(&ovf, g->ovf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // (also: the group's slabs may be overwritten by the next group from here on)
     if (ovf) { dbg_set_error("internal: gathered row outgrew its bound"); return DBGPHMM_ERR_INVALID; }
-    g->on = true;
     return DBGPHMM_OK;
 }
 
@@ -319,17 +324,23 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     if (!out->d_final || !out->d_desc0) { dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
     CUDA_TRY(cudaMemcpyAsync(out->d_desc0, out->desc0.data(), sizeof(uint64_t) * J, cudaMemcpyHostToDevice, st));
     // ---- dense phase layout
+    // top-n jobs whose dense rows are not kept: the first sparse row reads gathered cells, and the warm-up may run in groups of G jobs
+    // that share one pool of slabs (slab indices are then relative to the group)
+    const bool use_gather = kind == DBGPHMM_FWD_SPARSE && !keep_rows && !opt.dense_only && !opt.step && (gather_enabled() || opt.group > 0);
+    const uint32_t G = (use_gather && opt.group > 0 && opt.group < J) ? opt.group : std::max<uint32_t>(J, 1);
     std::vector<uint32_t> nd_max(J);
     std::vector<DJob> dj(J);
-    uint64_t n_slabs = 0; uint32_t steps = 0;
+    uint64_t n_slabs = 0, slab_cur = 0; uint32_t steps = 0;
     for (uint32_t j = 0; j < J; j++) {
         uint32_t n = jobs[j].len;
+        if (j % G == 0) slab_cur = 0;
         nd_max[j] = kind == DBGPHMM_FWD_DENSE ? n : (kind == DBGPHMM_FWD_MAPPING ? 0 : std::min(n, W));
         DJob& d = dj[j];
         d.x = jobs[j].x; d.len = n; d.base_off = jobs[j].base_off; d.n_steps = nd_max[j]; d.first_row = 0;
-        d.prev0_kind = PREV_F_INIT; d.prev0_slab = 0; d.slab0 = n_slabs; d.slab_mod = keep_rows ? 0 : 2; d.desc0 = out->desc0[j];
+        d.prev0_kind = PREV_F_INIT; d.prev0_slab = 0; d.slab0 = slab_cur; d.slab_mod = keep_rows ? 0 : 2; d.desc0 = out->desc0[j];
         d.active_idx = kind == DBGPHMM_FWD_SPARSE_RATIO ? (int32_t)j : -1;
-        n_slabs += keep_rows ? nd_max[j] : std::min<uint32_t>(nd_max[j], 2);
+        slab_cur += keep_rows ? nd_max[j] : std::min<uint32_t>(nd_max[j], 2);
+        n_slabs = std::max(n_slabs, slab_cur);
         steps = std::max(steps, nd_max[j]);
     }
     out->slab0.resize(J);
@@ -342,8 +353,9 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     ST_TRY(dev_upload(b_nd, nd_max, st));
     ST_TRY(dev_upload(b_len, out->len, st));
     // two rows per launch when nothing reads the intermediate rows (ping-pong slabs, no per-row products, fixed warm-up)
-    bool paired = !keep_rows && !opt.step && (kind == DBGPHMM_FWD_SPARSE || kind == DBGPHMM_FWD_DENSE) && steps >= 2 && dense_can_pair(m);
-    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * std::max<size_t>(m->fwd.n_chunks, paired ? 2 * (size_t)dense_pair_tiles(m, 0) : 0)));
+    const bool can_pair = !keep_rows && !opt.step && (kind == DBGPHMM_FWD_SPARSE || kind == DBGPHMM_FWD_DENSE) && steps >= 2 && dense_can_pair(m);
+    std::vector<uint8_t> job_paired(J, 0);   // the job's rows went through the two-rows-per-launch kernel (decides where its last row lies)
+    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * std::max<size_t>(m->fwd.n_chunks, can_pair ? 2 * (size_t)dense_pair_tiles(m, 0) : 0)));
     DevBuf b_wl, b_redo;
     ST_TRY(b_redo.alloc(sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(b_redo.p, 0, sizeof(int), st));
@@ -354,64 +366,75 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     const int* d_active = kind == DBGPHMM_FWD_SPARSE_RATIO ? b_active.as<int>() : nullptr;
     std::vector<SelectReq> reqs(J);
     ST_TRY(b_reqs.alloc(sizeof(SelectReq) * J));
-    auto slab_of_h = [&](uint32_t j, uint32_t s) { return paired ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    auto slab_of_h = [&](uint32_t j, uint32_t s) { return job_paired[j] ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
     GatherBufs gat;
+    if (use_gather) ST_TRY(gather_init(m, J, &gat));
     delete tr_setup;
     {
         HostTrace t("  fwd dense phase");
         EvTimer tm(st, &g_times.dense_ms);
-        if (paired) {
-            for (uint32_t s = 0; s < steps; s += 2) {
-                uint64_t live = 0;
-                for (uint32_t j = 0; j < J; j++) live += (s < nd_max[j]) + (s + 1 < nd_max[j]);
-                ST_TRY(dense_forward_pair(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, b_part.as<XF>(), b_redo.as<int>(), live * N, s + 1 < steps));
+        if (kind != DBGPHMM_FWD_SPARSE_RATIO) out->nd = nd_max;
+        for (uint32_t g0 = 0; g0 < J; g0 += G) {
+            const uint32_t g1 = std::min(J, g0 + G), Jg = g1 - g0;
+            const DJob* d_gj = b_dj.as<DJob>() + g0;
+            uint32_t gsteps = 0;
+            for (uint32_t j = g0; j < g1; j++) gsteps = std::max(gsteps, nd_max[j]);
+            bool paired = can_pair && gsteps >= 2;
+            if (paired) {
+                for (uint32_t s = 0; s < gsteps; s += 2) {
+                    uint64_t live = 0;
+                    for (uint32_t j = g0; j < g1; j++) live += (s < nd_max[j]) + (s + 1 < nd_max[j]);
+                    ST_TRY(dense_forward_pair(m, out->pool, d_gj, Jg, s, d_bases, out->d_desc, b_part.as<XF>(), b_redo.as<int>(), live * N, s + 1 < gsteps));
+                }
+                int redo = 0;
+                CUDA_TRY(cudaMemcpyAsync(&redo, b_redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (redo) {   // some tile's exponent range does not fit a two-row frame: single-row steps from the start
+                    if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] forward dense phase repeated with single-row steps\n");
+                    paired = false;
+                    CUDA_TRY(cudaMemsetAsync(b_redo.p, 0, sizeof(int), st));
+                }
             }
-            int redo = 0;
-            CUDA_TRY(cudaMemcpyAsync(&redo, b_redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            if (redo) {   // some tile's exponent range does not fit a two-row frame: single-row steps from the start
-                if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] forward dense phase repeated with single-row steps\n");
-                paired = false;
+            for (uint32_t j = g0; j < g1; j++) job_paired[j] = paired ? 1 : 0;
+            for (uint32_t s = 0; s < gsteps && !paired; s++) {
+                uint64_t live = 0;  // jobs that (may) compute row s: the algorithmic cells of this launch
+                for (uint32_t j = g0; j < g1; j++) live += s < nd_max[j];
+                ST_TRY(dense_forward_step(m, out->pool, d_gj, Jg, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));
+                if (opt.step) ST_TRY(step_products(m, *opt.step, out->pool, d_gj, Jg, s, 0, g0));
+                if (kind == DBGPHMM_FWD_SPARSE_RATIO) {   // (never grouped: g0 == 0, g1 == J)
+                    // top_nodes_by_score_ratio of row s for every job still dense (forward.rs:112-116)
+                    uint32_t nr = 0;
+                    for (uint32_t j = 0; j < J; j++)
+                        if (s < nd_max[j]) { SelectReq& r = reqs[nr++]; r.slab = slab_of_h(j, s); r.k = MAX_ACTIVE; r.by_ratio = 1; r.ratio = m->params.active_node_max_ratio; r.active_idx = (int32_t)j; r.out = j; }
+                    CUDA_TRY(cudaMemcpyAsync(b_reqs.p, reqs.data(), sizeof(SelectReq) * nr, cudaMemcpyHostToDevice, st));
+                    ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), nr, d_active, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
+                    k_ratio_decide<<<(J + 127) / 128, 128, 0, st>>>(J, s, W, m->params.warmup_threshold, b_len.as<uint32_t>(), b_top_cnt.as<uint32_t>(),
+                                                                     b_active.as<int>(), b_nd.as<uint32_t>());
+                    COUNT_LAUNCH();
+                    CUDA_TRY(cudaStreamSynchronize(st));  // reqs is reused next step
+                }
             }
-        }
-        for (uint32_t s = 0; s < steps && !paired; s++) {
-            uint64_t live = 0;  // jobs that (may) compute row s: the algorithmic cells of this launch
-            for (uint32_t j = 0; j < J; j++) live += s < nd_max[j];
-            ST_TRY(dense_forward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, d_active, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));
-            if (opt.step) ST_TRY(step_products(m, *opt.step, out->pool, b_dj.as<DJob>(), J, s, 0));
-            if (kind == DBGPHMM_FWD_SPARSE_RATIO) {
-                // top_nodes_by_score_ratio of row s for every job still dense (forward.rs:112-116)
+            if (kind == DBGPHMM_FWD_SPARSE && !opt.dense_only) {  // top_nodes(n_active) of the last dense row (forward.rs:115)
                 uint32_t nr = 0;
-                for (uint32_t j = 0; j < J; j++)
-                    if (s < nd_max[j]) { SelectReq& r = reqs[nr++]; r.slab = slab_of_h(j, s); r.k = MAX_ACTIVE; r.by_ratio = 1; r.ratio = m->params.active_node_max_ratio; r.active_idx = (int32_t)j; r.out = j; }
+                for (uint32_t j = g0; j < g1; j++)
+                    if (jobs[j].len > out->nd[j]) { SelectReq& r = reqs[nr++]; r.slab = slab_of_h(j, out->nd[j] - 1); r.k = m->params.n_active_nodes; r.by_ratio = 0; r.ratio = 0; r.active_idx = -1; r.out = j; }
                 CUDA_TRY(cudaMemcpyAsync(b_reqs.p, reqs.data(), sizeof(SelectReq) * nr, cudaMemcpyHostToDevice, st));
-                ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), nr, d_active, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
-                k_ratio_decide<<<(J + 127) / 128, 128, 0, st>>>(J, s, W, m->params.warmup_threshold, b_len.as<uint32_t>(), b_top_cnt.as<uint32_t>(),
-                                                                 b_active.as<int>(), b_nd.as<uint32_t>());
-                COUNT_LAUNCH();
-                CUDA_TRY(cudaStreamSynchronize(st));  // reqs is reused next step
+                ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), nr, nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
+                CUDA_TRY(cudaStreamSynchronize(st));   // (reqs is reused by the next group)
+                if (use_gather) {
+                    std::vector<uint64_t> gs(Jg, ~0ull);
+                    for (uint32_t j = g0; j < g1; j++) if (jobs[j].len > out->nd[j] && out->nd[j] > 0) gs[j - g0] = slab_of_h(j, out->nd[j] - 1);
+                    ST_TRY(gather_group(m, 0, g0, gs, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>(), out->pool, &gat));
+                }
             }
         }
         launch_timer_flush();
         if (kind == DBGPHMM_FWD_SPARSE_RATIO) {
             CUDA_TRY(cudaMemcpyAsync(out->nd.data(), b_nd.p, sizeof(uint32_t) * J, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-        } else out->nd = nd_max;
-        if (opt.dense_only) { HostTrace t2("  fwd dense_only tail"); CUDA_TRY(cudaStreamSynchronize(st)); cache_free(out->pool.base); out->pool.base = nullptr; return DBGPHMM_OK; }
-        if (kind == DBGPHMM_FWD_SPARSE) {  // top_nodes(n_active) of the last dense row (forward.rs:115)
-            uint32_t nr = 0;
-            for (uint32_t j = 0; j < J; j++)
-                if (jobs[j].len > out->nd[j]) { SelectReq& r = reqs[nr++]; r.slab = slab_of_h(j, out->nd[j] - 1); r.k = m->params.n_active_nodes; r.by_ratio = 0; r.ratio = 0; r.active_idx = -1; r.out = j; }
-            CUDA_TRY(cudaMemcpyAsync(b_reqs.p, reqs.data(), sizeof(SelectReq) * nr, cudaMemcpyHostToDevice, st));
-            ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), nr, nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            if (!keep_rows && gather_enabled()) {
-                std::vector<uint64_t> gs(J, ~0ull);
-                for (uint32_t j = 0; j < J; j++) if (jobs[j].len > out->nd[j] && out->nd[j] > 0) gs[j] = slab_of_h(j, out->nd[j] - 1);
-                ST_TRY(gather_prev0(m, 0, gs, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>(), out->pool, &gat));
-                cache_free(out->pool.base); out->pool.base = nullptr;   // the ping-pong slabs are dead already
-            }
         }
+        if (opt.dense_only) { HostTrace t2("  fwd dense_only tail"); CUDA_TRY(cudaStreamSynchronize(st)); cache_free(out->pool.base); out->pool.base = nullptr; return DBGPHMM_OK; }
+        if (use_gather) { cache_free(out->pool.base); out->pool.base = nullptr; }   // the ping-pong slabs are dead already
     }
     for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
     // ---- sparse phase
@@ -479,11 +502,15 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     CUDA_TRY(cudaMemcpyAsync(out->d_desc0, out->desc0.data(), sizeof(uint64_t) * J, cudaMemcpyHostToDevice, st));
     // dense rows of job j: [lo, hi]; they are computed from hi down to lo
     std::vector<DJob> dj(J);
-    uint64_t n_slabs = 0; uint32_t steps = 0;
+    uint64_t n_slabs = 0, slab_cur = 0; uint32_t steps = 0;
     const bool sparse_first = kind == DBGPHMM_BWD_BY_FORWARD;
+    // (see run_forward) top-n jobs whose dense rows are not kept: gathered first-row inputs, warm-up in groups of G jobs
+    const bool use_gather = kind == DBGPHMM_BWD_SPARSE && !keep_rows && !opt.step && (gather_enabled() || opt.group > 0);
+    const uint32_t G = (use_gather && opt.group > 0 && opt.group < J) ? opt.group : std::max<uint32_t>(J, 1);
     for (uint32_t j = 0; j < J; j++) {
         int n = (int)jobs[j].len;
         int lo = -1, hi = -1;
+        if (j % G == 0) slab_cur = 0;
         if (n > 0) {
             if (kind == DBGPHMM_BWD_DENSE) { lo = 0; hi = n - 1; }
             else if (kind == DBGPHMM_BWD_SPARSE) { hi = n - 1; lo = std::max(0, n - (int)W); }
@@ -494,10 +521,11 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
         out->nd[j] = nd;
         DJob& d = dj[j];
         d.x = jobs[j].x; d.len = n; d.base_off = jobs[j].base_off; d.n_steps = nd; d.first_row = hi;
-        d.prev0_kind = PREV_B_INIT; d.prev0_slab = 0; d.slab0 = n_slabs; d.slab_mod = keep_rows ? 0 : 2; d.desc0 = out->desc0[j]; d.active_idx = -1;
+        d.prev0_kind = PREV_B_INIT; d.prev0_slab = 0; d.slab0 = slab_cur; d.slab_mod = keep_rows ? 0 : 2; d.desc0 = out->desc0[j]; d.active_idx = -1;
         uint64_t need = keep_rows ? nd : std::min<uint32_t>(nd, 2);
-        if (sparse_first && nd > 0 && hi < n - 1) { d.prev0_kind = PREV_SLAB; d.prev0_slab = n_slabs + need; need += 1; }  // scattered sparse row hi+1
-        n_slabs += need;
+        if (sparse_first && nd > 0 && hi < n - 1) { d.prev0_kind = PREV_SLAB; d.prev0_slab = slab_cur + need; need += 1; }  // scattered sparse row hi+1
+        slab_cur += need;
+        n_slabs = std::max(n_slabs, slab_cur);
         steps = std::max(steps, nd);
     }
     out->slab0.resize(J);
@@ -507,8 +535,9 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     ST_TRY(dev_upload(b_dj, dj, st));
     ST_TRY(dev_upload(b_len, out->len, st));
     // two rows per launch when nothing reads the intermediate rows (see run_forward)
-    bool paired = !keep_rows && !opt.step && kind == DBGPHMM_BWD_SPARSE && steps >= 2 && dense_can_pair(m);
-    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * std::max<size_t>(m->bwd.n_chunks, paired ? 2 * (size_t)dense_pair_tiles(m, 1) : 0)));
+    const bool can_pair = !keep_rows && !opt.step && kind == DBGPHMM_BWD_SPARSE && steps >= 2 && dense_can_pair(m);
+    std::vector<uint8_t> job_paired(J, 0);
+    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * std::max<size_t>(m->bwd.n_chunks, can_pair ? 2 * (size_t)dense_pair_tiles(m, 1) : 0)));
     DevBuf b_wl, b_redo;
     ST_TRY(b_redo.alloc(sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(b_redo.p, 0, sizeof(int), st));
@@ -516,17 +545,23 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     ST_TRY(b_top_ids.alloc(sizeof(uint32_t) * (size_t)J * MAX_ACTIVE));
     ST_TRY(b_top_cnt.alloc(sizeof(uint32_t) * J));
     CUDA_TRY(cudaMemsetAsync(b_top_cnt.p, 0, sizeof(uint32_t) * J, st));
-    auto slab_of_h = [&](uint32_t j, uint32_t s) { return paired ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
+    auto slab_of_h = [&](uint32_t j, uint32_t s) { return job_paired[j] ? dj[j].slab0 + ((s >> 1) & 1) : dj[j].slab0 + (dj[j].slab_mod ? (s % dj[j].slab_mod) : s); };
     GatherBufs gat;
+    if (use_gather) ST_TRY(gather_init(m, J, &gat));
 
-    auto dense_phase = [&]() -> int {
+    auto dense_phase = [&](uint32_t g0, uint32_t g1) -> int {   // the dense rows of jobs g0 .. g1 - 1
         HostTrace t("  bwd dense phase");
         EvTimer tm(st, &g_times.dense_ms);
+        const uint32_t Jg = g1 - g0;
+        const DJob* d_gj = b_dj.as<DJob>() + g0;
+        uint32_t gsteps = 0;
+        for (uint32_t j = g0; j < g1; j++) gsteps = std::max(gsteps, out->nd[j]);
+        bool paired = can_pair && gsteps >= 2;
         if (paired) {
-            for (uint32_t s = 0; s < steps; s += 2) {
+            for (uint32_t s = 0; s < gsteps; s += 2) {
                 uint64_t live = 0;
-                for (uint32_t j = 0; j < J; j++) live += (s < out->nd[j]) + (s + 1 < out->nd[j]);
-                ST_TRY(dense_backward_pair(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, b_part.as<XF>(), b_redo.as<int>(), live * N, s + 1 < steps));
+                for (uint32_t j = g0; j < g1; j++) live += (s < out->nd[j]) + (s + 1 < out->nd[j]);
+                ST_TRY(dense_backward_pair(m, out->pool, d_gj, Jg, s, d_bases, out->d_desc, b_part.as<XF>(), b_redo.as<int>(), live * N, s + 1 < gsteps));
             }
             int redo = 0;
             CUDA_TRY(cudaMemcpyAsync(&redo, b_redo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -534,16 +569,18 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
             if (redo) {
                 if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] backward dense phase repeated with single-row steps\n");
                 paired = false;
+                CUDA_TRY(cudaMemsetAsync(b_redo.p, 0, sizeof(int), st));
             }
         }
-        for (uint32_t s = 0; s < steps && !paired; s++) {
+        for (uint32_t j = g0; j < g1; j++) job_paired[j] = paired ? 1 : 0;
+        for (uint32_t s = 0; s < gsteps && !paired; s++) {
             uint64_t live = 0;
-            for (uint32_t j = 0; j < J; j++) live += s < out->nd[j];
-            ST_TRY(dense_backward_step(m, out->pool, b_dj.as<DJob>(), J, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));
-            if (opt.step) ST_TRY(step_products(m, *opt.step, out->pool, b_dj.as<DJob>(), J, s, 1));
+            for (uint32_t j = g0; j < g1; j++) live += s < out->nd[j];
+            ST_TRY(dense_backward_step(m, out->pool, d_gj, Jg, s, d_bases, out->d_desc, nullptr, b_part.as<XF>(), b_wl.as<unsigned long long>(), live * N));
+            if (opt.step) ST_TRY(step_products(m, *opt.step, out->pool, d_gj, Jg, s, 1, g0));
         }
         launch_timer_flush();
-        for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
+        for (uint32_t j = g0; j < g1; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
         return DBGPHMM_OK;
     };
     auto sparse_phase = [&]() -> int {
@@ -582,20 +619,23 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     };
 
     if (!sparse_first) {
-        ST_TRY(dense_phase());
-        if (kind == DBGPHMM_BWD_SPARSE) {  // top_nodes(n_active) of the last dense row (backward.rs:174)
-            std::vector<SelectReq> reqs;
-            for (uint32_t j = 0; j < J; j++)
-                if (out->bdense_lo[j] > 0) { SelectReq r{}; r.slab = slab_of_h(j, out->nd[j] - 1); r.k = m->params.n_active_nodes; r.by_ratio = 0; r.active_idx = -1; r.out = j; reqs.push_back(r); }
-            ST_TRY(dev_upload(b_reqs, reqs, st));
-            ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), (uint32_t)reqs.size(), nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
-            if (!keep_rows && gather_enabled()) {
-                std::vector<uint64_t> gs(J, ~0ull);
-                for (uint32_t j = 0; j < J; j++) if (out->bdense_lo[j] > 0) gs[j] = slab_of_h(j, out->nd[j] - 1);
-                ST_TRY(gather_prev0(m, 1, gs, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>(), out->pool, &gat));
-                cache_free(out->pool.base); out->pool.base = nullptr;   // the ping-pong slabs are dead already
+        for (uint32_t g0 = 0; g0 < J; g0 += G) {
+            const uint32_t g1 = std::min(J, g0 + G);
+            ST_TRY(dense_phase(g0, g1));
+            if (kind == DBGPHMM_BWD_SPARSE) {  // top_nodes(n_active) of the last dense row (backward.rs:174)
+                std::vector<SelectReq> reqs;
+                for (uint32_t j = g0; j < g1; j++)
+                    if (out->bdense_lo[j] > 0) { SelectReq r{}; r.slab = slab_of_h(j, out->nd[j] - 1); r.k = m->params.n_active_nodes; r.by_ratio = 0; r.active_idx = -1; r.out = j; reqs.push_back(r); }
+                ST_TRY(dev_upload(b_reqs, reqs, st));
+                ST_TRY(dense_select(m, out->pool, b_reqs.as<SelectReq>(), (uint32_t)reqs.size(), nullptr, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>()));
+                if (use_gather) {
+                    std::vector<uint64_t> gs(g1 - g0, ~0ull);
+                    for (uint32_t j = g0; j < g1; j++) if (out->bdense_lo[j] > 0) gs[j - g0] = slab_of_h(j, out->nd[j] - 1);
+                    ST_TRY(gather_group(m, 1, g0, gs, b_top_ids.as<uint32_t>(), b_top_cnt.as<uint32_t>(), out->pool, &gat));
+                }
             }
         }
+        if (use_gather) { cache_free(out->pool.base); out->pool.base = nullptr; }   // the ping-pong slabs are dead already
         ST_TRY(sparse_phase());
     } else {
         ST_TRY(sparse_phase());
@@ -615,7 +655,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
             COUNT_LAUNCH();
             CUDA_TRY(cudaStreamSynchronize(st));
         }
-        ST_TRY(dense_phase());
+        ST_TRY(dense_phase(0, J));
     }
     if (!keep_rows) { cache_free(out->pool.base); out->pool.base = nullptr; }
     // final mb: row 0 is dense whenever dense rows reach row 0
@@ -676,40 +716,44 @@ __global__ void k_roi_mark_b(uint32_t W, const RowDesc* __restrict__ fdesc, cons
 // the forward rows' node sets and multiplied on the fly (mirror of run_forward_recompute ; lets the main backward pass run two rows
 // per launch without ever writing the intermediate rows).
 int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
-                           const StepProducts& sp) {
+                           const StepProducts& sp, uint32_t group) {
     HostTrace tr("run_backward_recompute");
     cudaStream_t st = m->stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup, T = m->bwd.n_chunks;
     ST_TRY(model_ensure_roi(m));
     EvTimer tm(st, &g_times.dense_ms);
+    const uint32_t G = (group > 0 && group < J) ? group : std::max<uint32_t>(J, 1);   // jobs per pool of slabs
     std::vector<DJob> dj(J);
     for (uint32_t j = 0; j < J; j++) {
         DJob& d = dj[j];
         d.x = jobs[j].x; d.len = jobs[j].len; d.base_off = jobs[j].base_off; d.n_steps = std::min<uint32_t>(jobs[j].len, W); d.first_row = (int32_t)jobs[j].len - 1;
-        d.prev0_kind = PREV_B_INIT; d.prev0_slab = 0; d.slab0 = 2ull * j; d.slab_mod = 2; d.desc0 = B.desc0[j]; d.active_idx = -1;
+        d.prev0_kind = PREV_B_INIT; d.prev0_slab = 0; d.slab0 = 2ull * (j % G); d.slab_mod = 2; d.desc0 = B.desc0[j]; d.active_idx = -1;
     }
     DensePool pool;
-    pool.Np = (N + 1) & ~1u; pool.slab_bytes = dense_slab_bytes(N); pool.n_slabs = 2ull * J;
+    pool.Np = (N + 1) & ~1u; pool.slab_bytes = dense_slab_bytes(N); pool.n_slabs = 2ull * std::min(G, J);
     DevBuf b_pool, b_dj, b_len, b_mark, b_wl, b_part;
-    ST_TRY(b_pool.alloc(pool.slab_bytes * pool.n_slabs)); pool.base = b_pool.as<char>();
+    ST_TRY(b_pool.alloc(pool.slab_bytes * std::max<uint64_t>(pool.n_slabs, 1))); pool.base = b_pool.as<char>();
     ST_TRY(dev_upload(b_dj, dj, st)); ST_TRY(dev_upload(b_len, F.len, st));
-    ST_TRY(b_mark.alloc((size_t)J * T));
-    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * T + 1)));
-    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)J * T));
-    CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)J * T, st));
-    CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
-    CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * pool.n_slabs, st));   // cells outside the cone read as zero
-    {
-        dim3 g(W, J);
-        k_roi_mark_b<<<g, 128, 0, st>>>(W, F.d_desc, F.d_desc0, b_len.as<uint32_t>(), F.arena.base, m->d_tile_of_b, m->d_roi_off_b, m->d_roi_tile_b, T,
-                                        b_mark.as<unsigned char>());
-        COUNT_LAUNCH();
-        k_roi_compact<<<4 * m->n_sm, 256, 0, st>>>(J, T, b_mark.as<unsigned char>(), b_wl.as<unsigned long long>());
-        COUNT_LAUNCH();
-    }
-    for (uint32_t s = 0; s < W; s++) {
-        ST_TRY(dense_backward_step_list(m, pool, b_dj.as<DJob>(), s, d_bases, b_part.as<XF>(), b_wl.as<unsigned long long>()));
-        ST_TRY(step_products(m, sp, pool, b_dj.as<DJob>(), J, s, 1));
+    ST_TRY(b_mark.alloc((size_t)std::min(G, J) * T + 1));
+    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)std::min(G, J) * T + 1)));
+    ST_TRY(b_part.alloc(sizeof(XF) * 2 * (size_t)std::min(G, J) * T + 16));
+    for (uint32_t g0 = 0; g0 < J; g0 += G) {
+        const uint32_t Jg = std::min(J, g0 + G) - g0;
+        CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)Jg * T, st));
+        CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * 2ull * Jg, st));   // cells outside the cone read as zero
+        {
+            dim3 g(W, Jg);
+            k_roi_mark_b<<<g, 128, 0, st>>>(W, F.d_desc, F.d_desc0 + g0, b_len.as<uint32_t>() + g0, F.arena.base, m->d_tile_of_b, m->d_roi_off_b, m->d_roi_tile_b, T,
+                                            b_mark.as<unsigned char>());
+            COUNT_LAUNCH();
+            k_roi_compact<<<4 * m->n_sm, 256, 0, st>>>(Jg, T, b_mark.as<unsigned char>(), b_wl.as<unsigned long long>());
+            COUNT_LAUNCH();
+        }
+        for (uint32_t s = 0; s < W; s++) {
+            ST_TRY(dense_backward_step_list(m, pool, b_dj.as<DJob>() + g0, s, d_bases, b_part.as<XF>(), b_wl.as<unsigned long long>()));
+            ST_TRY(step_products(m, sp, pool, b_dj.as<DJob>() + g0, Jg, s, 1, g0));
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -717,40 +761,44 @@ int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, cons
 }
 
 int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
-                          const StepProducts& sp) {
+                          const StepProducts& sp, uint32_t group) {
     HostTrace tr("run_forward_recompute");
     cudaStream_t st = m->stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup, T = m->fwd.n_chunks;
     ST_TRY(model_ensure_roi(m));
     EvTimer tm(st, &g_times.dense_ms);
+    const uint32_t G = (group > 0 && group < J) ? group : std::max<uint32_t>(J, 1);   // jobs per pool of slabs
     std::vector<DJob> dj(J);
     for (uint32_t j = 0; j < J; j++) {
         DJob& d = dj[j];
         d.x = jobs[j].x; d.len = jobs[j].len; d.base_off = jobs[j].base_off; d.n_steps = std::min<uint32_t>(jobs[j].len, W); d.first_row = 0;
-        d.prev0_kind = PREV_F_INIT; d.prev0_slab = 0; d.slab0 = 2ull * j; d.slab_mod = 2; d.desc0 = F.desc0[j]; d.active_idx = -1;
+        d.prev0_kind = PREV_F_INIT; d.prev0_slab = 0; d.slab0 = 2ull * (j % G); d.slab_mod = 2; d.desc0 = F.desc0[j]; d.active_idx = -1;
     }
     DensePool pool;
-    pool.Np = (N + 1) & ~1u; pool.slab_bytes = dense_slab_bytes(N); pool.n_slabs = 2ull * J;
+    pool.Np = (N + 1) & ~1u; pool.slab_bytes = dense_slab_bytes(N); pool.n_slabs = 2ull * std::min(G, J);
     DevBuf b_pool, b_dj, b_len, b_mark, b_wl, b_part;
-    ST_TRY(b_pool.alloc(pool.slab_bytes * pool.n_slabs)); pool.base = b_pool.as<char>();
+    ST_TRY(b_pool.alloc(pool.slab_bytes * std::max<uint64_t>(pool.n_slabs, 1))); pool.base = b_pool.as<char>();
     ST_TRY(dev_upload(b_dj, dj, st)); ST_TRY(dev_upload(b_len, F.len, st));
-    ST_TRY(b_mark.alloc((size_t)J * T));
-    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)J * T + 1)));
-    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)J * T));
-    CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)J * T, st));
-    CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
-    CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * pool.n_slabs, st));   // cells outside the cone read as zero
-    {
-        dim3 g(W, J);
-        k_roi_mark<<<g, 128, 0, st>>>(W, B.d_desc, B.d_desc0, b_len.as<uint32_t>(), B.arena.base, m->d_tile_of, m->d_roi_off, m->d_roi_tile, T,
-                                      b_mark.as<unsigned char>());
-        COUNT_LAUNCH();
-        k_roi_compact<<<4 * m->n_sm, 256, 0, st>>>(J, T, b_mark.as<unsigned char>(), b_wl.as<unsigned long long>());
-        COUNT_LAUNCH();
-    }
-    for (uint32_t s = 0; s < W; s++) {
-        ST_TRY(dense_forward_step_list(m, pool, b_dj.as<DJob>(), s, d_bases, F.d_desc, b_part.as<XF>(), b_wl.as<unsigned long long>()));
-        ST_TRY(step_products(m, sp, pool, b_dj.as<DJob>(), J, s, 0));
+    ST_TRY(b_mark.alloc((size_t)std::min(G, J) * T + 1));
+    ST_TRY(b_wl.alloc(sizeof(unsigned long long) * ((size_t)std::min(G, J) * T + 1)));
+    ST_TRY(b_part.alloc(sizeof(XF) * (size_t)std::min(G, J) * T + 16));
+    for (uint32_t g0 = 0; g0 < J; g0 += G) {
+        const uint32_t Jg = std::min(J, g0 + G) - g0;
+        CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)Jg * T, st));
+        CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * 2ull * Jg, st));   // cells outside the cone read as zero
+        {
+            dim3 g(W, Jg);
+            k_roi_mark<<<g, 128, 0, st>>>(W, B.d_desc, B.d_desc0 + g0, b_len.as<uint32_t>() + g0, B.arena.base, m->d_tile_of, m->d_roi_off, m->d_roi_tile, T,
+                                          b_mark.as<unsigned char>());
+            COUNT_LAUNCH();
+            k_roi_compact<<<4 * m->n_sm, 256, 0, st>>>(Jg, T, b_mark.as<unsigned char>(), b_wl.as<unsigned long long>());
+            COUNT_LAUNCH();
+        }
+        for (uint32_t s = 0; s < W; s++) {
+            ST_TRY(dense_forward_step_list(m, pool, b_dj.as<DJob>() + g0, s, d_bases, F.d_desc, b_part.as<XF>(), b_wl.as<unsigned long long>()));
+            ST_TRY(step_products(m, sp, pool, b_dj.as<DJob>() + g0, Jg, s, 0, g0));
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());

@@ -107,6 +107,7 @@ struct PhaseOpts {
     bool keep_rows = true;      // dense rows kept (true) or ping-pong (false)
     bool store_sparse = true;   // sparse rows written to the arena
     bool dense_only = false;    // forward: stop after the dense rows (recompute pass)
+    uint32_t group = 0;         // top-n jobs without kept rows: dense warm-up in groups of this many jobs sharing one pool of slabs (0: one group)
     const StepProducts* step = nullptr;
 };
 
@@ -117,11 +118,13 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
                  const DevMappings* dmap, const RowStore* fwd, RowStore* out);
 // Recompute the forward warm-up rows only inside the dependency cone of the backward rows' sparse node sets and take the
 // (forward dense row, backward sparse row) products there.  F supplies the row scalars of the first pass.
+// group: jobs per pool of slabs (0: all of them at once)
 int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
-                          const StepProducts& sp);
+                          const StepProducts& sp, uint32_t group = 0);
 int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
-                          const StepProducts& sp);
-int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir);
+                          const StepProducts& sp, uint32_t group = 0);
+// d_jobs[0 .. n_jobs) are the jobs job0 .. job0 + n_jobs - 1 of the batch (sp's per-job arrays are indexed by batch position)
+int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir, uint32_t job0 = 0);
 // sum over rows of F (x) B / P into d_freqs (device, ORIGINAL node order, added to); status ZERO_PROB if some P == 0
 // mapx.cu: forward_with_mapping_score_only for groups of candidates X of one read
 struct MapxGroup { uint64_t base_off; uint32_t len; uint64_t map_row0; uint32_t x0, nx, out0; };

@@ -341,10 +341,10 @@ __global__ void k_prod_step(const DJob* __restrict__ jobs, uint32_t s, int dir, 
         }
     }
 }
-int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir) {
+int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir, uint32_t job0) {
     if (!sp.other->d_desc0) { dbg_set_error("step_products: the other direction has no device row index"); return DBGPHMM_ERR_INVALID; }
-    k_prod_step<<<n_jobs, 128, 0, m->stream>>>(d_jobs, s, dir, pool.base, pool.slab_bytes, pool.Np, sp.other->d_desc, sp.other->d_desc0,
-                                               sp.other->arena.base, sp.P, m->d_orig_of, sp.d_freqs, sp.d_err);
+    k_prod_step<<<n_jobs, 128, 0, m->stream>>>(d_jobs, s, dir, pool.base, pool.slab_bytes, pool.Np, sp.other->d_desc, sp.other->d_desc0 + job0,
+                                               sp.other->arena.base, sp.P + job0, m->d_orig_of, sp.d_freqs, sp.d_err);
     COUNT_LAUNCH();
     return DBGPHMM_OK;
 }

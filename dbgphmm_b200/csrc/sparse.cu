@@ -824,12 +824,12 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
 }
 
 // ---- gather of the cells of the last dense row that step 0 of a top-n job can read (sparse.h)
-__global__ void k_gather_prev0(SGraph G, int dir, const uint32_t* __restrict__ top_ids, const uint32_t* __restrict__ top_cnt, const uint64_t* __restrict__ slabs,
-                               const char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np, uint32_t cap, char* __restrict__ out,
-                               uint32_t* __restrict__ out_cnt, int* __restrict__ overflow) {
-    const uint32_t j = blockIdx.x;
-    if (slabs[j] == ~0ull) { if (threadIdx.x == 0) out_cnt[j] = 0; return; }
-    const char* sl = pool + slabs[j] * slab_bytes;
+__global__ void k_gather_prev0(SGraph G, int dir, uint32_t slot0, const uint32_t* __restrict__ top_ids, const uint32_t* __restrict__ top_cnt,
+                               const uint64_t* __restrict__ slabs, const char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np, uint32_t cap,
+                               char* __restrict__ out, uint32_t* __restrict__ out_cnt, int* __restrict__ overflow) {
+    const uint32_t j = slot0 + blockIdx.x;
+    if (slabs[blockIdx.x] == ~0ull) return;
+    const char* sl = pool + slabs[blockIdx.x] * slab_bytes;
     const double* gm = (const double*)sl; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
     char* o = out + (size_t)j * 32 * cap;
     double* om = (double*)o; double* oi = om + cap; double* od = oi + cap; uint32_t* oid = (uint32_t*)(od + cap); int* oex = (int*)(oid + cap);
@@ -866,12 +866,12 @@ uint32_t sparse_gather_cap(const dbgphmm_model* m, uint32_t k) {
     const uint64_t c = (uint64_t)k * (1 + 2 * D + D * D);
     return (uint32_t)((std::min<uint64_t>(c, 1u << 24) + 1) & ~1ull);
 }
-int sparse_gather_prev0(dbgphmm_model* m, int dir, uint32_t n_slots, const uint32_t* d_top_ids, const uint32_t* d_top_cnt, const uint64_t* d_slabs,
+int sparse_gather_prev0(dbgphmm_model* m, int dir, uint32_t slot0, uint32_t n, const uint32_t* d_top_ids, const uint32_t* d_top_cnt, const uint64_t* d_slabs,
                         const char* pool, uint64_t slab_bytes, uint32_t Np, uint32_t cap, char* d_out, uint32_t* d_out_cnt, int* d_overflow) {
-    if (n_slots == 0) return DBGPHMM_OK;
+    if (n == 0) return DBGPHMM_OK;
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of, m->d_par_rec, m->d_chi_rec};
-    k_gather_prev0<<<n_slots, 64, 0, m->stream>>>(G, dir, d_top_ids, d_top_cnt, d_slabs, pool, slab_bytes, Np, cap, d_out, d_out_cnt, d_overflow);
+    k_gather_prev0<<<n, 64, 0, m->stream>>>(G, dir, slot0, d_top_ids, d_top_cnt, d_slabs, pool, slab_bytes, Np, cap, d_out, d_out_cnt, d_overflow);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;

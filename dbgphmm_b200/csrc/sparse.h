@@ -82,12 +82,13 @@ uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap);
 // outgrow `cap` (io.rq_* must be set up by the caller); 0: no rescue launch.
 // dir: SJob::dir of every job of the launch (0 forward, 1 backward)
 int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const SparseIO& io, uint32_t cap, int dir, uint32_t rescue_cap = 0);
-// Gather, for every request slot j with slabs[j] != ~0, the cells of dense row slabs[j] that step 0 of a top-n job started from
-// top_ids[j] can read (forward: top, children(top) and the parents of both ; backward: top, parents(top) and the children of
-// both) into out + j * 32 * cap.  cap must be sparse_gather_cap(m, k) for lists of at most k ids.  *d_overflow is raised if a list
-// outgrows cap (cannot happen for that cap).  With these lists the dense slabs are not needed during the sparse phase.
+// Gather, for the request slots j = slot0 .. slot0 + n - 1 with slabs[j - slot0] != ~0, the cells of dense row slabs[j - slot0] that
+// step 0 of a top-n job started from top_ids[j] can read (forward: top, children(top) and the parents of both ; backward: top,
+// parents(top) and the children of both) into out + j * 32 * cap, their number into out_cnt[j] (other slots are left alone).  cap must
+// be sparse_gather_cap(m, k) for lists of at most k ids.  *d_overflow is raised if a list outgrows cap (cannot happen for that cap).
+// With these lists the dense slabs are not needed during the sparse phase.
 uint32_t sparse_gather_cap(const dbgphmm_model* m, uint32_t k);
-int sparse_gather_prev0(dbgphmm_model* m, int dir, uint32_t n_slots, const uint32_t* d_top_ids, const uint32_t* d_top_cnt, const uint64_t* d_slabs,
+int sparse_gather_prev0(dbgphmm_model* m, int dir, uint32_t slot0, uint32_t n, const uint32_t* d_top_ids, const uint32_t* d_top_cnt, const uint64_t* d_slabs,
                         const char* pool, uint64_t slab_bytes, uint32_t Np, uint32_t cap, char* d_out, uint32_t* d_out_cnt, int* d_overflow);
 // capacity of the rescue launch that accompanies a primary launch of capacity `cap` (0: none)
 uint32_t sparse_rescue_cap(uint32_t cap);

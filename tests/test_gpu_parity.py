@@ -288,6 +288,26 @@ def test_gathered_first_sparse_row_inputs_match_the_dense_slab(H, monkeypatch):
     assert np.allclose(b[0], of, rtol=REL_TOL, atol=1e-12)
 
 
+@pytest.mark.parametrize("group", [1, 2, 4])
+def test_dense_warmup_in_groups_sharing_one_pool_of_slabs(H, monkeypatch, group):
+    """DBGPHMM_DENSE_GROUP=G (stream strategy): the dense warm-up rows, the top-n selection, the gather of the first sparse row's inputs
+    and both recompute passes run over groups of G reads that reuse one pool of 2 G slabs.  Nothing about the arithmetic changes, so
+    ln P is identical to the ungrouped run, node frequencies agree to rounding of the atomics, and both match the oracle."""
+    w = _dbg_case(13, glen=4000, k=16, het=0.02, read_len=300, n_reads=7)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g = gpu_model(w.graph, par)
+    reads = H.Reads(w.reads)
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
+    a = g.run_node_freqs(reads, "sparse")
+    monkeypatch.setenv("DBGPHMM_DENSE_GROUP", str(group))
+    b = g.run_node_freqs(reads, "sparse")
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-15)
+    of, olf, olb = oracle_model(w.graph, par).run_node_freqs(O.Reads(w.reads), "sparse")
+    assert np.allclose(b[1], olf, rtol=REL_TOL, atol=0) and np.allclose(b[2], olb, rtol=REL_TOL, atol=0)
+    assert np.allclose(b[0], of, rtol=REL_TOL, atol=1e-12)
+
+
 def test_top_nodes_of_rows(H):
     w = _dbg_case(2)
     par = oracle_params(0.01, n_warmup=w.k)
