@@ -84,3 +84,45 @@ def test_no_gpu_means_loud_failure(lib):
     with pytest.raises(H.DbgphmmError) as ei:
         H.PHMMModel(sg.src, sg.dst, sg.base, li, lt, H.params_uniform(0.01))
     assert ei.value.status == H.ERR_CUDA
+
+
+def test_rust_shim_stays_in_step_with_the_header_and_the_build():
+    """rust/ is source only (no cargo/rustc here): check what can be checked without compiling it -- its `extern "C"`
+    block binds exactly the functions include/dbgphmm_b200.h declares, each with the same number of arguments, the params struct has the
+    header's fields in the header's order, and build.rs compiles the same sources with the same link libraries as
+    dbgphmm_b200/build.py."""
+    hdr = open(os.path.join(ROOT, "include", "dbgphmm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    rs = open(os.path.join(ROOT, "rust", "src", "lib.rs")).read()
+    rs_nc = re.sub(r"//[^\n]*", "", rs)
+
+    def n_args(arglist):
+        a = arglist.strip()
+        return 0 if a in ("", "void") else a.count(",") + 1
+
+    c_decl = {m.group(1): n_args(m.group(2)) for m in re.finditer(r"\b(dbgphmm_[a-z_0-9]+)\s*\(([^)]*)\)\s*;", hdr)}
+    ext = re.search(r'extern "C" \{(.*?)\n\}', rs_nc, flags=re.S).group(1)
+    r_decl = {m.group(1): n_args(m.group(2)) for m in re.finditer(r"pub fn (dbgphmm_[a-z_0-9]+)\s*\(([^)]*)\)", ext)}
+    assert set(r_decl) == set(c_decl) == set(H.SYMBOLS), set(r_decl) ^ set(c_decl)
+    for name, n in r_decl.items():
+        assert n == c_decl[name], f"{name}: {n} arguments in the Rust binding, {c_decl[name]} in the header"
+
+    c_struct = re.search(r"typedef struct dbgphmm_params\s*\{(.*?)\}", hdr, flags=re.S)
+    if c_struct is None:
+        c_struct = re.search(r"struct dbgphmm_params\s*\{(.*?)\}", hdr, flags=re.S)
+    c_fields = []
+    for stmt in c_struct.group(1).split(";"):
+        toks = stmt.replace(",", " ").split()
+        if len(toks) >= 2:
+            c_fields += [t.lower() for t in toks[1:]]
+    r_struct = re.search(r"pub struct dbgphmm_params \{(.*?)\n\}", rs_nc, flags=re.S).group(1)
+    r_fields = re.findall(r"pub ([a-z_0-9]+):", r_struct)
+    assert r_fields == c_fields, (r_fields, c_fields)
+    assert [n.lower() for n, _ in H.Params._fields_] == c_fields
+
+    brs = open(os.path.join(ROOT, "rust", "build.rs")).read()
+    srcs = re.search(r"let srcs = \[(.*?)\];", brs).group(1)
+    assert re.findall(r'"([a-z_]+\.cu)"', srcs) == B.SOURCES
+    for flag in ("arch=compute_100a,code=sm_100a", "-lineinfo", "-lcudart", "-lz"):
+        assert flag in brs, flag
