@@ -386,6 +386,56 @@ class PHMMTables:
         return out[:n.value].copy()
 
 
+def _dense_states(row, n_nodes):
+    """(m, i, d) of a Row as dense ln arrays; entries a sparse row does not store are the SparseVec default, ln 0."""
+    if row.is_dense:
+        return row.m, row.i, row.d
+    m = np.full(n_nodes, -np.inf); i = np.full(n_nodes, -np.inf); d = np.full(n_nodes, -np.inf)
+    m[row.ids] = row.m; i[row.ids] = row.i; d[row.ids_d] = row.d
+    return m, i, d
+
+
+def table_merged(tables, is_forward, merged_index):
+    """PHMMTables::table_merged (table.rs:414-434), 0 <= merged_index <= n: Forward[0] and Backward[n] are the init tables."""
+    n = len(tables)
+    if is_forward:
+        return tables.row(-1 if merged_index == 0 else merged_index - 1)
+    return tables.row(-1 if merged_index >= n else merged_index)
+
+
+def emit_probs(forward, backward, merged_index):
+    """PHMMOutput::to_emit_probs (table.rs:500-505): (F[i] * B[i]) / P(x) with P from the forward tables, as a dense Row of
+    natural logs.  Host-side composition over exported rows (inspection / tests; the bulk products run on the device).  A state
+    one side does not store is that side's default (zero), so the product is zero there -- the values of the reference's
+    SparseVec product, in dense storage.  `forward` / `backward`: anything with row(i), len() and full_prob()."""
+    p = forward.full_prob()
+    if np.isneginf(p):
+        raise DbgphmmError(4, "P(read) == 0: to_emit_probs would be NaN (table.rs:500-505)")
+    n_nodes = forward.n_nodes
+    f = table_merged(forward, True, merged_index); b = table_merged(backward, False, merged_index)
+    r = Row()
+    r.is_dense = True; r.ids = r.ids_d = None
+    (fm, fi, fd), (bm, bi, bd) = _dense_states(f, n_nodes), _dense_states(b, n_nodes)
+    r.m, r.i, r.d = fm + bm - p, fi + bi - p, fd + bd - p
+    r.mb, r.ib, r.e = float(f.mb + b.mb - p), float(f.ib + b.ib - p), float(f.e + b.e - p)
+    return r
+
+
+def state_probs(forward, backward):
+    """PHMMOutput::to_state_probs (freq.rs:237-239): the emit probs of merged index 0..n added up (Prob +, prob.rs:181-197)."""
+    acc = None
+    for i in range(len(forward) + 1):
+        t = emit_probs(forward, backward, i)
+        if acc is None:
+            acc = t
+            continue
+        with np.errstate(invalid="ignore"):
+            for name in ("m", "i", "d"):
+                setattr(acc, name, np.logaddexp(getattr(acc, name), getattr(t, name)))
+            acc.mb, acc.ib, acc.e = (float(np.logaddexp(a, b)) for a, b in ((acc.mb, t.mb), (acc.ib, t.ib), (acc.e, t.e)))
+    return acc
+
+
 class PHMMOutput:
     """PHMMOutput (table.rs:450-517)."""
 
@@ -400,6 +450,18 @@ class PHMMOutput:
 
     def to_full_prob_backward(self):
         return self.backward.full_prob()
+
+    def to_emit_probs(self, merged_index):
+        """table.rs:500-505, a dense Row (host-side composition over exported rows, see emit_probs)."""
+        return emit_probs(self.forward, self.backward, merged_index)
+
+    def iter_emit_probs(self):
+        """freq.rs:226-229: merged index 0..=n."""
+        return (self.to_emit_probs(i) for i in range(self.n_emissions() + 1))
+
+    def to_state_probs(self):
+        """freq.rs:237-239.  to_node_freqs() is exp(merged m + i + d) of this table, computed on the device."""
+        return state_probs(self.forward, self.backward)
 
     def to_node_freqs(self):
         f = np.empty(self._model.n_nodes)
@@ -652,6 +714,39 @@ class PHMMModel:
         _check(lib().dbgphmm_run_node_freqs(self._h, reads._h, RUN_MODES[mode], int(use_max_ratio),
                                             mappings._h if mappings is not None else None, _p(fr), _p(lf), _p(lb), _p(cells)))
         return fr, lf, lb, (int(cells[0]), int(cells[1]))
+
+    # ---- the remaining whole-read-set methods of freq.rs, each one bulk call (reads: Reads or a list of sequences)
+    @staticmethod
+    def _reads(seqs):
+        return seqs if isinstance(seqs, Reads) else Reads(list(seqs))
+
+    def to_node_freqs(self, seqs):
+        """PHMMModel::to_node_freqs (freq.rs:87-102): dense forward + backward per read, node frequencies summed over reads."""
+        return self.run_node_freqs(self._reads(seqs), "dense")[0]
+
+    def to_full_prob(self, seqs):
+        """to_full_prob / to_full_prob_parallel (freq.rs:105-135): ln of the product over reads of the dense forward P(read);
+        the sum is taken in read order (rayon's order is unspecified)."""
+        return float(self.run_node_freqs(self._reads(seqs), "dense", want_freqs=False)[1].sum())
+
+    to_full_prob_parallel = to_full_prob
+
+    def to_full_prob_sparse(self, seqs, use_max_ratio):
+        """freq.rs:138-150: product of forward_sparse(read, use_max_ratio).full_prob() (parameter set 0)."""
+        return float(self.to_full_prob_reads(self._reads(seqs), None, use_max_ratio)[0][0])
+
+    def to_full_prob_sparse_backward(self, seqs):
+        """freq.rs:153-164: product of backward_sparse(read).full_prob()."""
+        return float(self.run_node_freqs(self._reads(seqs), "sparse", want_freqs=False)[2].sum())
+
+    def forward_sparse_score_only(self, x, use_max_ratio):
+        """forward.rs:158-206: forward_sparse keeping one row; returns ln P (parameter set 0)."""
+        return float(self.to_full_prob_reads(Reads([x]), None, use_max_ratio)[1][0, 0])
+
+    def forward_with_mapping_score_only(self, x, mappings, read_index=0):
+        """forward.rs:79-89 with the mapping of read `read_index` of `mappings`."""
+        one = Mappings.from_list([mappings[read_index]])
+        return float(self.to_full_prob_reads(Reads([x]), one, False)[1][0, 0])
 
     def run_node_freqs_dev(self, reads, mode, node_freqs_ptr, use_max_ratio=True, mappings=None, logp_fwd_ptr=None, logp_bwd_ptr=None):
         """Device-pointer variant: node_freqs_ptr (f64[N] on this model's device) is accumulated into."""

@@ -627,3 +627,43 @@ def test_batched_candidates_wide_and_duplicated_mapping_rows(H, monkeypatch):
         o.set_probs(li, lt)
         s, p = o.to_full_prob_reads(O.Reads(reads), om)
         assert close_log(per[x], p).all(), (x, per[x], p)
+
+
+def test_reference_surface_compositions(H):
+    """The rest of the reference's method surface, which the Python mirror composes on the host from the same C-ABI
+    calls: PHMMOutput::{to_emit_probs, to_state_probs} (table.rs:500-505, freq.rs:226-239) over exported device rows, and
+    PHMMModel::{to_node_freqs, to_full_prob(_parallel), to_full_prob_sparse(_backward), forward_*_score_only} (freq.rs:87-165,
+    forward.rs:79-89,158-206) as one bulk call each.  Against the oracle doing it the reference's way, read by read
+    (tests/test_surface_host.py runs the same compositions over the oracle on the CPU)."""
+    w = _dbg_case(8, n_reads=5, k=16, p_err=0.003)
+    par = oracle_params(0.001, n_warmup=w.k, warmup_threshold=30)
+    g, o = both(w.graph, par, "non_zero")
+    seqs = w.reads
+    N = w.graph.n_nodes
+    for go, oo in ((g.run(seqs[0]), o.run(seqs[0])), (g.run_sparse(seqs[0]), o.run_sparse(seqs[0]))):
+        sp = go.to_state_probs()
+        freqs = np.exp(sp.merged(N))
+        assert np.allclose(freqs, go.to_node_freqs(), rtol=1e-9, atol=1e-12)      # the device's own product kernels
+        assert np.allclose(freqs, oo.to_node_freqs(), rtol=1e-9, atol=1e-12)      # the oracle
+        n = go.n_emissions()
+        t = go.to_emit_probs(n // 2)
+        f, b, p = oo.forward.row(n // 2 - 1), oo.backward.row(n // 2), oo.forward.full_prob()
+        want = H._dense_states(f, N)[0] + H._dense_states(b, N)[0] - p
+        big = want > -600.0     # (below that a state may have been flushed beside a much larger state of the same cell, tests/common.py)
+        assert close_log(t.m[big], want[big]).all() and (t.m[~big] < -590.0).all()
+        assert sum(1 for _ in go.iter_emit_probs()) == n + 1
+    want = sum(o.run(x).to_node_freqs() for x in seqs)
+    assert np.allclose(g.to_node_freqs(seqs), want, rtol=1e-9, atol=1e-12)
+    want = sum(o.forward(x).full_prob() for x in seqs)
+    assert close_log(g.to_full_prob(seqs), want).all() and close_log(g.to_full_prob_parallel(H.Reads(seqs)), want).all()
+    for ratio in (False, True):
+        want = sum(o.forward_sparse(x, ratio).full_prob() for x in seqs)
+        assert close_log(g.to_full_prob_sparse(seqs, ratio), want).all()
+        assert close_log(g.forward_sparse_score_only(seqs[1], ratio), o.forward_sparse(seqs[1], ratio).full_prob()).all()
+    want = sum(o.backward_sparse(x).full_prob() for x in seqs)
+    assert close_log(g.to_full_prob_sparse_backward(seqs), want).all()
+    om = o.generate_mappings(O.Reads(seqs), None, True)
+    hm = H.Mappings(om.read_off, om.row_off, om.nodes, om.probs)
+    for r in (0, 3):
+        want = o.forward_with_mapping(seqs[r], om[r]).full_prob()
+        assert close_log(g.forward_with_mapping_score_only(seqs[r], hm, r), want).all()
