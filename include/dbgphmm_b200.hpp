@@ -7,6 +7,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 #include "dbgphmm_b200.h"
 
@@ -23,24 +24,74 @@ inline PHMMParams uniform(double p) { PHMMParams q; dbgphmm_params_uniform(p, &q
 
 class Reads {  // ReadCollection (common/collection.rs:131)
 public:
-    explicit Reads(const std::vector<std::string>& seqs) {
+    explicit Reads(const std::vector<std::string>& seqs) : n_(seqs.size()) {
         std::vector<uint64_t> off(1, 0); std::string all;
         for (auto& s : seqs) { all += s; off.push_back(all.size()); }
         check(dbgphmm_reads_create(seqs.size(), off.data(), (const uint8_t*)all.data(), &h_));
     }
     ~Reads() { dbgphmm_reads_destroy(h_); }
     Reads(const Reads&) = delete; Reads& operator=(const Reads&) = delete;
+    uint64_t len() const { return n_; }
     dbgphmm_reads* handle() const { return h_; }
 private:
     dbgphmm_reads* h_ = nullptr;
+    uint64_t n_;
 };
+
+// Mapping (hint.rs:27-30) of one read, copied to the host: per base the candidate nodes and their ln probabilities
+struct Mapping {
+    std::vector<std::vector<uint32_t>> nodes;
+    std::vector<std::vector<double>> probs;
+};
+
+class MultiDbg;
 
 class Mappings {  // hint.rs:150-152
 public:
     explicit Mappings(dbgphmm_mappings* h) : h_(h) {}
-    ~Mappings() { dbgphmm_mappings_destroy(h_); }
+    explicit Mappings(const std::vector<Mapping>& maps) {
+        std::vector<uint64_t> read_off(1, 0), row_off(1, 0); std::vector<uint32_t> nodes; std::vector<double> logp;
+        for (auto& m : maps) {
+            if (m.nodes.size() != m.probs.size()) throw Error(DBGPHMM_ERR_INVALID);
+            for (size_t i = 0; i < m.nodes.size(); i++) {
+                if (m.nodes[i].size() != m.probs[i].size()) throw Error(DBGPHMM_ERR_INVALID);
+                nodes.insert(nodes.end(), m.nodes[i].begin(), m.nodes[i].end());
+                logp.insert(logp.end(), m.probs[i].begin(), m.probs[i].end());
+                row_off.push_back(nodes.size());
+            }
+            read_off.push_back(row_off.size() - 1);
+        }
+        check(dbgphmm_mappings_create(maps.size(), read_off.data(), row_off.data(), nodes.data(), logp.data(), &h_));
+    }
+    static Mappings from_map_file(const std::string& path) {   // MultiDbg::from_map_file_raw, multi_dbg/output.rs:604-623 (.map, .gz, .mpz)
+        dbgphmm_mappings* h = nullptr;
+        check(dbgphmm_mappings_from_map_file(path.c_str(), &h));
+        return Mappings(h);
+    }
+    static Mappings from_map_str(const std::string& text) {    // output.rs:589-591
+        dbgphmm_mappings* h = nullptr;
+        check(dbgphmm_mappings_from_map_text(text.data(), text.size(), &h));
+        return Mappings(h);
+    }
+    ~Mappings() { if (h_) dbgphmm_mappings_destroy(h_); }
     Mappings(const Mappings&) = delete; Mappings& operator=(const Mappings&) = delete;
+    Mappings(Mappings&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
     dbgphmm_mappings* handle() const { return h_; }
+    uint64_t n_reads() const { uint64_t n = 0; check(dbgphmm_mappings_sizes(h_, &n, nullptr, nullptr)); return n; }
+    // `mappings[r]`
+    Mapping at(uint64_t r) const {
+        uint64_t nr = 0, nrow = 0, nent = 0;
+        check(dbgphmm_mappings_sizes(h_, &nr, &nrow, &nent));
+        if (r >= nr) throw Error(DBGPHMM_ERR_INVALID);
+        std::vector<uint64_t> ro(nr + 1), rw(nrow + 1); std::vector<uint32_t> nd(nent); std::vector<double> lp(nent);
+        check(dbgphmm_mappings_export(h_, ro.data(), rw.data(), nd.data(), lp.data()));
+        Mapping m;
+        for (uint64_t i = ro[r]; i < ro[r + 1]; i++) {
+            m.nodes.emplace_back(nd.begin() + rw[i], nd.begin() + rw[i + 1]);
+            m.probs.emplace_back(lp.begin() + rw[i], lp.begin() + rw[i + 1]);
+        }
+        return m;
+    }
     std::vector<double> to_node_freqs(uint32_t n_nodes) const {  // hint.rs:161
         std::vector<double> f(n_nodes); check(dbgphmm_mappings_to_node_freqs(h_, n_nodes, f.data())); return f;
     }
@@ -52,36 +103,117 @@ public:
         check(dbgphmm_mappings_map_nodes(h_, (uint32_t)node_map.size(), off.data(), to.data(), &o));
         return Mappings(o);
     }
-    Mappings(Mappings&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    // MultiDbg::to_map_file (output.rs:455-527); dbg (nullable) only feeds the header comment
+    inline void to_map_file(const std::string& path, const Reads& reads, const MultiDbg* dbg = nullptr) const;
 private:
-    dbgphmm_mappings* h_;
+    dbgphmm_mappings* h_ = nullptr;
 };
 
-class PHMMTables {  // table.rs:365-435
+// PHMMTable (table.rs:42-73) copied to the host, natural logs.  Dense: m, i, d hold all N nodes and ids / ids_d are empty.
+// Sparse: (ids[j], m[j], i[j]) and (ids_d[j], d[j]) in the insertion order of the reference's SparseVec.
+struct PHMMTable {
+    bool is_dense = true;
+    std::vector<uint32_t> ids, ids_d;
+    std::vector<double> m, i, d;
+    double mb = 0, ib = 0, e = 0;
+};
+
+class PHMMTables {  // table.rs:365-435, resident on the device
 public:
     explicit PHMMTables(dbgphmm_tables* h) : h_(h) {}
     ~PHMMTables() { dbgphmm_tables_destroy(h_); }
     PHMMTables(const PHMMTables&) = delete; PHMMTables& operator=(const PHMMTables&) = delete;
     uint64_t n_emissions() const { return dbgphmm_tables_len(h_); }
     double full_prob() const { double v; check(dbgphmm_tables_full_prob(h_, &v)); return v; }   // table.rs:395
+    // tables[row]; row = -1 is init_table (table.rs:365-380)
+    PHMMTable table(int64_t row) const {
+        uint64_t info[3]; double sc[3];
+        check(dbgphmm_tables_row_info(h_, row, info, sc));
+        PHMMTable t;
+        t.is_dense = info[0] != 0; t.mb = sc[0]; t.ib = sc[1]; t.e = sc[2];
+        t.m.resize(info[1]); t.i.resize(info[1]); t.d.resize(info[2]);
+        if (!t.is_dense) { t.ids.resize(info[1]); t.ids_d.resize(info[2]); }
+        check(dbgphmm_tables_row_export(h_, row, t.is_dense ? nullptr : t.ids.data(), t.m.data(), t.i.data(),
+                                        t.is_dense ? nullptr : t.ids_d.data(), t.d.data()));
+        return t;
+    }
+    PHMMTable init_table() const { return table(-1); }
+    // PHMMTables::table_merged (table.rs:414-434); the direction is the caller's (Forward[0] / Backward[n] = init_table)
+    PHMMTable table_merged(bool is_forward, uint64_t merged_index) const {
+        if (is_forward) return table(merged_index == 0 ? -1 : (int64_t)merged_index - 1);
+        return table(merged_index >= n_emissions() ? -1 : (int64_t)merged_index);
+    }
+    std::vector<uint32_t> top_nodes(int64_t row, uint32_t k) const { return top(row, 0, k, 0.0); }                        // table.rs:127
+    std::vector<uint32_t> top_nodes_by_score_ratio(int64_t row, double ratio) const { return top(row, 1, 0, ratio); }    // table.rs:134
     dbgphmm_tables* handle() const { return h_; }
 private:
+    std::vector<uint32_t> top(int64_t row, int by_ratio, uint32_t k, double ratio) const {
+        std::vector<uint32_t> out(DBGPHMM_MAX_ACTIVE_NODES); uint32_t n = 0;
+        check(dbgphmm_tables_row_top_nodes(h_, row, by_ratio, k, ratio, out.data(), &n));
+        out.resize(n);
+        return out;
+    }
     dbgphmm_tables* h_;
+};
+
+// PHMMOutput (table.rs:450-517): the forward and backward tables of one read and the products over both
+class PHMMOutput {
+public:
+    PHMMOutput(dbgphmm_model* m, uint32_t n_nodes, uint32_t n_edges, std::unique_ptr<PHMMTables> f, std::unique_ptr<PHMMTables> b)
+        : forward(std::move(f)), backward(std::move(b)), m_(m), n_nodes_(n_nodes), n_edges_(n_edges) {
+        if (forward->n_emissions() != backward->n_emissions()) throw Error(DBGPHMM_ERR_INVALID);   // table.rs:473
+    }
+    std::unique_ptr<PHMMTables> forward, backward;
+    uint64_t n_emissions() const { return forward->n_emissions(); }
+    double to_full_prob_forward() const { return forward->full_prob(); }     // table.rs:482
+    double to_full_prob_backward() const { return backward->full_prob(); }   // table.rs:492
+    std::vector<double> to_node_freqs() const {                              // freq.rs:245-255
+        std::vector<double> f(n_nodes_);
+        check(dbgphmm_output_node_freqs(m_, forward->handle(), backward->handle(), f.data()));
+        return f;
+    }
+    // freq.rs:276-298: edge freqs in EdgeIndex order + the Begin -> node freqs
+    std::pair<std::vector<double>, std::vector<double>> to_edge_and_init_freqs() const {
+        std::vector<double> e(n_edges_), i(n_nodes_);
+        check(dbgphmm_output_edge_and_init_freqs(m_, forward->handle(), backward->handle(), e.data(), i.data()));
+        return {std::move(e), std::move(i)};
+    }
+    std::vector<double> to_edge_freqs() const { return to_edge_and_init_freqs().first; }   // freq.rs:302-309
+    Mapping to_mapping(uint32_t n_active_nodes) const { return mapping(0, n_active_nodes, 0.0); }        // hint.rs:124-133
+    Mapping to_mapping_by_score_ratio(double max_ratio) const { return mapping(1, 0, max_ratio); }        // hint.rs:134-142
+private:
+    Mapping mapping(int by_ratio, uint32_t n_active, double ratio) const {
+        dbgphmm_mappings* h = nullptr;
+        check(dbgphmm_output_mapping(m_, forward->handle(), backward->handle(), by_ratio, n_active, ratio, &h));
+        return Mappings(h).at(0);
+    }
+    dbgphmm_model* m_;
+    uint32_t n_nodes_, n_edges_;
 };
 
 class PHMMModel {  // hmmv2/common.rs:61-67
 public:
     PHMMModel(const std::vector<uint32_t>& edge_src, const std::vector<uint32_t>& edge_dst, const std::vector<uint8_t>& emission,
               const std::vector<double>& log_init, const std::vector<double>& log_trans, const PHMMParams& param, int device = 0,
-              uint64_t mem_budget = 0) : n_nodes_((uint32_t)emission.size()) {
-        check(dbgphmm_model_create(n_nodes_, (uint32_t)edge_src.size(), edge_src.data(), edge_dst.data(), emission.data(), log_init.data(),
+              uint64_t mem_budget = 0) : n_nodes_((uint32_t)emission.size()), n_edges_((uint32_t)edge_src.size()) {
+        if (edge_dst.size() != edge_src.size() || log_trans.size() != edge_src.size() || log_init.size() != emission.size()) throw Error(DBGPHMM_ERR_INVALID);
+        check(dbgphmm_model_create(n_nodes_, n_edges_, edge_src.data(), edge_dst.data(), emission.data(), log_init.data(),
                                    log_trans.data(), &param, device, mem_budget, &h_));
     }
+    // adopts a handle made by dbgphmm_dbg_to_model (MultiDbg::to_phmm below)
+    PHMMModel(dbgphmm_model* h, uint32_t n_edges) : h_(h), n_nodes_(dbgphmm_model_n_nodes(h)), n_edges_(n_edges) {}
     ~PHMMModel() { dbgphmm_model_destroy(h_); }
     PHMMModel(const PHMMModel&) = delete; PHMMModel& operator=(const PHMMModel&) = delete;
     uint32_t n_nodes() const { return n_nodes_; }
+    uint32_t n_edges() const { return n_edges_; }
+    void set_params(const PHMMParams& param) { check(dbgphmm_model_set_params(h_, &param)); }
+    void set_probs(const std::vector<double>& log_init, const std::vector<double>& log_trans) {
+        if (log_init.size() != n_nodes_ || log_trans.size() != n_edges_) throw Error(DBGPHMM_ERR_INVALID);
+        check(dbgphmm_model_set_probs(h_, log_init.data(), log_trans.data()));
+    }
     // candidate copy-number assignments X -> parameter sets on the device (seq_graph.rs:160-273)
     void set_copy_nums_batch(uint32_t n_batch, const uint32_t* copy_nums, int mode = 0) { check(dbgphmm_model_set_copy_nums_batch(h_, n_batch, copy_nums, mode)); }
+    uint32_t n_batch() const { return dbgphmm_model_n_batch(h_); }
 
     std::unique_ptr<PHMMTables> forward(const std::string& x) { return fwd(x, DBGPHMM_FWD_DENSE); }                           // forward.rs:24
     std::unique_ptr<PHMMTables> forward_sparse(const std::string& x, bool use_max_ratio) { return fwd(x, use_max_ratio ? DBGPHMM_FWD_SPARSE_RATIO : DBGPHMM_FWD_SPARSE); }  // :93
@@ -91,28 +223,71 @@ public:
     std::unique_ptr<PHMMTables> backward_with_mapping(const std::string& x, const Mappings& m, uint64_t i) { return bwd(x, DBGPHMM_BWD_MAPPING, &m, i); }  // :59
     std::unique_ptr<PHMMTables> backward_by_forward(const std::string& x, const PHMMTables& f) { return bwd(x, DBGPHMM_BWD_BY_FORWARD, nullptr, 0, &f); }  // :101
 
+    // freq.rs:42-76
+    PHMMOutput run(const std::string& x) { return out(forward(x), backward(x)); }
+    PHMMOutput run_sparse(const std::string& x) { return out(forward_sparse(x, false), backward_sparse(x)); }
+    PHMMOutput run_sparse_adaptive(const std::string& x, bool use_max_ratio) {
+        auto f = forward_sparse(x, use_max_ratio);
+        auto b = backward_by_forward(x, *f);
+        return out(std::move(f), std::move(b));
+    }
+    PHMMOutput run_with_mapping(const std::string& x, const Mappings& m, uint64_t i) { return out(forward_with_mapping(x, m, i), backward_with_mapping(x, m, i)); }
+
     // freq.rs:175-192 for every candidate X: returns ln P(R|X) [n_batch]
     std::vector<double> to_full_prob_reads(const Reads& reads, const Mappings* mappings, bool use_max_ratio) {
         std::vector<double> out(dbgphmm_model_n_batch(h_));
         check(dbgphmm_to_full_prob_reads(h_, reads.handle(), mappings ? mappings->handle() : nullptr, use_max_ratio, out.data(), nullptr));
         return out;
     }
-    // run / run_sparse / run_sparse_adaptive / run_with_mapping (freq.rs:42-76) + to_node_freqs (freq.rs:245), summed over reads
+    // run / run_sparse / run_sparse_adaptive / run_with_mapping (freq.rs:42-76) + to_node_freqs (freq.rs:245), summed over reads;
+    // logp_fwd / logp_bwd (nullable) receive to_full_prob_forward / to_full_prob_backward of every read
     std::vector<double> to_node_freqs(const Reads& reads, int run_mode, bool use_max_ratio = true, const Mappings* mappings = nullptr,
-                                      std::vector<double>* logp_fwd = nullptr) {
+                                      std::vector<double>* logp_fwd = nullptr, std::vector<double>* logp_bwd = nullptr) {
         std::vector<double> f(n_nodes_);
-        if (logp_fwd) logp_fwd->resize(0);
-        check(dbgphmm_run_node_freqs(h_, reads.handle(), run_mode, use_max_ratio, mappings ? mappings->handle() : nullptr, f.data(), nullptr, nullptr, nullptr));
+        if (logp_fwd) logp_fwd->resize(reads.len());
+        if (logp_bwd) logp_bwd->resize(reads.len());
+        check(dbgphmm_run_node_freqs(h_, reads.handle(), run_mode, use_max_ratio, mappings ? mappings->handle() : nullptr, f.data(),
+                                     logp_fwd ? logp_fwd->data() : nullptr, logp_bwd ? logp_bwd->data() : nullptr, nullptr));
         return f;
     }
-    std::unique_ptr<Mappings> generate_mappings(const Reads& reads, const Mappings* mappings, bool use_max_ratio) {  // hint.rs:193
+    // PHMMModel::to_node_freqs (freq.rs:87-102): dense forward + backward per read
+    std::vector<double> to_node_freqs(const Reads& reads) { return to_node_freqs(reads, DBGPHMM_RUN_DENSE); }
+    // to_full_prob / to_full_prob_parallel (freq.rs:105-135): ln of the product over reads of the dense forward P(read), in read order
+    double to_full_prob(const Reads& reads) { std::vector<double> lf; to_node_freqs(reads, DBGPHMM_RUN_DENSE, true, nullptr, &lf); return sum(lf); }
+    double to_full_prob_parallel(const Reads& reads) { return to_full_prob(reads); }
+    // freq.rs:138-150 (parameter set 0)
+    double to_full_prob_sparse(const Reads& reads, bool use_max_ratio) { return to_full_prob_reads(reads, nullptr, use_max_ratio)[0]; }
+    // freq.rs:153-164
+    double to_full_prob_sparse_backward(const Reads& reads) {
+        std::vector<double> lb; to_node_freqs(reads, DBGPHMM_RUN_SPARSE, true, nullptr, nullptr, &lb); return sum(lb);
+    }
+    // forward.rs:158-206 / 79-89
+    double forward_sparse_score_only(const std::string& x, bool use_max_ratio) {
+        Reads one(std::vector<std::string>{x});
+        return to_full_prob_reads(one, nullptr, use_max_ratio)[0];
+    }
+    double forward_with_mapping_score_only(const std::string& x, const Mapping& m) {
+        Reads one(std::vector<std::string>{x});
+        Mappings hint(std::vector<Mapping>{m});
+        return to_full_prob_reads(one, &hint, false)[0];
+    }
+    Mappings generate_mappings(const Reads& reads, const Mappings* mappings, bool use_max_ratio) {  // hint.rs:193
         dbgphmm_mappings* out = nullptr;
         check(dbgphmm_generate_mappings(h_, reads.handle(), mappings ? mappings->handle() : nullptr, use_max_ratio, &out));
-        return std::make_unique<Mappings>(out);
+        return Mappings(out);
+    }
+    // q_score_exact (q.rs:66-96) of parameter set x: {init, trans, prior}
+    std::vector<double> q_score_exact(const std::vector<double>& edge_freqs, const std::vector<double>& init_freqs, uint32_t x = 0) const {
+        if (edge_freqs.size() != n_edges_ || init_freqs.size() != n_nodes_) throw Error(DBGPHMM_ERR_INVALID);
+        std::vector<double> q(3);
+        check(dbgphmm_q_score_exact(h_, x, edge_freqs.data(), init_freqs.data(), q.data()));
+        return q;
     }
     dbgphmm_model* handle() const { return h_; }
 
 private:
+    static double sum(const std::vector<double>& v) { double s = 0; for (double x : v) s += x; return s; }
+    PHMMOutput out(std::unique_ptr<PHMMTables> f, std::unique_ptr<PHMMTables> b) { return PHMMOutput(h_, n_nodes_, n_edges_, std::move(f), std::move(b)); }
     std::unique_ptr<PHMMTables> fwd(const std::string& x, int kind, const Mappings* m = nullptr, uint64_t i = 0) {
         dbgphmm_tables* t = nullptr;
         check(dbgphmm_forward(h_, (const uint8_t*)x.data(), x.size(), kind, m ? m->handle() : nullptr, i, &t));
@@ -124,7 +299,7 @@ private:
         return std::make_unique<PHMMTables>(t);
     }
     dbgphmm_model* h_ = nullptr;
-    uint32_t n_nodes_;
+    uint32_t n_nodes_, n_edges_;
 };
 
 // The part of MultiDbg a DBG file carries (multi_dbg.rs:170-186, multi_dbg/output.rs:155-345); host only.
@@ -175,6 +350,10 @@ public:
         check(dbgphmm_dbg_to_model(h_, &param, mode, device, mem_budget, &m));
         return m;
     }
+    // MultiDbg::to_phmm / to_non_zero_phmm / to_uniform_phmm (multi_dbg.rs:1391-1409; n_warmup := k)
+    std::unique_ptr<PHMMModel> to_phmm(const PHMMParams& param, int device = 0) const { return std::make_unique<PHMMModel>(to_phmm_handle(param, 0, device), sz_[5]); }
+    std::unique_ptr<PHMMModel> to_non_zero_phmm(const PHMMParams& param, int device = 0) const { return std::make_unique<PHMMModel>(to_phmm_handle(param, 1, device), sz_[5]); }
+    std::unique_ptr<PHMMModel> to_uniform_phmm(const PHMMParams& param, int device = 0) const { return std::make_unique<PHMMModel>(to_phmm_handle(param, 2, device), sz_[5]); }
     dbgphmm_dbg* handle() const { return h_; }
 
 private:
@@ -182,5 +361,9 @@ private:
     dbgphmm_dbg* h_;
     uint32_t sz_[6];
 };
+
+inline void Mappings::to_map_file(const std::string& path, const Reads& reads, const MultiDbg* dbg) const {
+    check(dbgphmm_mappings_to_map_file(h_, reads.handle(), dbg ? dbg->handle() : nullptr, path.c_str()));
+}
 
 }  // namespace dbgphmm
