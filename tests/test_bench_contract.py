@@ -1,0 +1,39 @@
+"""bench.py's JSON contract on the CPU: the reference arm (`--impl reference` = the oracle port timed on the host cores, the one
+place outside tests/ and smoke() that executes oracle/) prints one line with the keys the driver reads; under a multi-rank launch
+only rank 0 works.  Tiny workload so that it takes a second; the GPU arm is exercised by the driver on a B200."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TINY = ["--genome-len", "20000", "--read-len", "500", "--steps", "2", "--warmup", "1", "--cpu-sample-reads", "2"]
+
+
+def _run(extra_env=None, args=()):
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env.update(extra_env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", *TINY, *args],
+                          capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+
+
+def test_reference_arm_prints_one_contract_line():
+    p = _run()
+    assert p.returncode == 0, p.stderr
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "PHMM forward-backward GCUPS" and d["unit"] == "GCUPS"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    p = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ["--gpus", "2"])
+    assert p.returncode == 0 and p.stdout.strip() == "", (p.stdout, p.stderr)
