@@ -8,7 +8,7 @@
 static const double LN2 = 0.693147180559945309417232121458;
 
 // ------------------------------------------------------------------ reads / mappings handles
-extern "C" int dbgphmm_reads_create(uint64_t n_reads, const uint64_t* offsets, const uint8_t* bases, dbgphmm_reads** out) {
+extern "C" int dbgphmm_reads_create(uint64_t n_reads, const uint64_t* offsets, const uint8_t* bases, dbgphmm_reads** out) try {
     if (!out || !offsets || (n_reads && offsets[n_reads] && !bases)) { dbg_set_error("reads_create: bad argument"); return DBGPHMM_ERR_INVALID; }
     for (uint64_t r = 0; r < n_reads; r++)
         if (offsets[r + 1] < offsets[r]) { dbg_set_error("reads_create: offsets not monotone"); return DBGPHMM_ERR_INVALID; }
@@ -23,13 +23,13 @@ extern "C" int dbgphmm_reads_create(uint64_t n_reads, const uint64_t* offsets, c
     r->bases.assign(bases, bases + total);
     *out = r;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" void dbgphmm_reads_destroy(dbgphmm_reads* r) {
     if (!r) return;
     if (r->d_bases) { cudaSetDevice(r->device); cudaFree(r->d_bases); }
     delete r;
 }
-extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) {
+extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) try {
     if (!m || !r) { dbg_set_error("reads_to_device: bad argument"); return DBGPHMM_ERR_INVALID; }
     if (r->d_bases && r->device == m->device) return DBGPHMM_OK;
     CUDA_TRY(cudaSetDevice(m->device));
@@ -38,10 +38,10 @@ extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) {
     if (!r->bases.empty()) CUDA_TRY(cudaMemcpy(r->d_bases, r->bases.data(), r->bases.size(), cudaMemcpyHostToDevice));
     r->device = m->device;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 extern "C" int dbgphmm_mappings_create(uint64_t n_reads, const uint64_t* read_off, const uint64_t* row_off, const uint32_t* nodes,
-                                       const double* logp, dbgphmm_mappings** out) {
+                                       const double* logp, dbgphmm_mappings** out) try {
     if (!out || !read_off || !row_off) { dbg_set_error("mappings_create: bad argument"); return DBGPHMM_ERR_INVALID; }
     dbgphmm_mappings* mp = new dbgphmm_mappings();
     mp->read_off.assign(read_off, read_off + n_reads + 1);
@@ -51,23 +51,23 @@ extern "C" int dbgphmm_mappings_create(uint64_t n_reads, const uint64_t* read_of
     if (n_ent) { mp->nodes.assign(nodes, nodes + n_ent); if (logp) mp->logp.assign(logp, logp + n_ent); else mp->logp.assign(n_ent, 0.0); }
     *out = mp;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" void dbgphmm_mappings_destroy(dbgphmm_mappings* mp) { delete mp; }
-extern "C" int dbgphmm_mappings_sizes(const dbgphmm_mappings* mp, uint64_t* n_reads, uint64_t* n_rows, uint64_t* n_entries) {
+extern "C" int dbgphmm_mappings_sizes(const dbgphmm_mappings* mp, uint64_t* n_reads, uint64_t* n_rows, uint64_t* n_entries) try {
     if (!mp) { dbg_set_error("mappings_sizes: null"); return DBGPHMM_ERR_INVALID; }
     if (n_reads) *n_reads = mp->read_off.empty() ? 0 : mp->read_off.size() - 1;
     if (n_rows) *n_rows = mp->row_off.empty() ? 0 : mp->row_off.size() - 1;
     if (n_entries) *n_entries = mp->nodes.size();
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_mappings_export(const dbgphmm_mappings* mp, uint64_t* read_off, uint64_t* row_off, uint32_t* nodes, double* logp) {
+} ABI_CATCH
+extern "C" int dbgphmm_mappings_export(const dbgphmm_mappings* mp, uint64_t* read_off, uint64_t* row_off, uint32_t* nodes, double* logp) try {
     if (!mp) { dbg_set_error("mappings_export: null"); return DBGPHMM_ERR_INVALID; }
     std::memcpy(read_off, mp->read_off.data(), 8 * mp->read_off.size());
     std::memcpy(row_off, mp->row_off.data(), 8 * mp->row_off.size());
     if (!mp->nodes.empty()) { std::memcpy(nodes, mp->nodes.data(), 4 * mp->nodes.size()); std::memcpy(logp, mp->logp.data(), 8 * mp->logp.size()); }
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32_t n_nodes, double* freqs) {
+} ABI_CATCH
+extern "C" int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32_t n_nodes, double* freqs) try {
     if (!mp || !freqs) { dbg_set_error("mappings_to_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
     // hint.rs:161-171 — a plain host-side scatter of exp(logp); not on the DP path, no device work involved
     std::fill(freqs, freqs + n_nodes, 0.0);
@@ -76,7 +76,7 @@ extern "C" int dbgphmm_mappings_to_node_freqs(const dbgphmm_mappings* mp, uint32
         freqs[mp->nodes[i]] += std::exp(mp->logp[i]);
     }
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 // Prob + Prob of the reference (prob.rs:181-197): the larger term first, then x + ln_1p(exp(y - x)), with its special cases
 static double host_log_add(double a, double b) {
@@ -86,7 +86,7 @@ static double host_log_add(double a, double b) {
     return x + std::log1p(std::exp(y - x));
 }
 extern "C" int dbgphmm_mappings_map_nodes(const dbgphmm_mappings* mp, uint32_t n_nodes_before, const uint64_t* map_off, const uint32_t* map_to,
-                                          dbgphmm_mappings** out) {
+                                          dbgphmm_mappings** out) try {
     if (!mp || !map_off || !out) { dbg_set_error("mappings_map_nodes: bad argument"); return DBGPHMM_ERR_INVALID; }
     for (uint32_t v = 0; v < n_nodes_before; v++)
         if (map_off[v + 1] < map_off[v]) { dbg_set_error("mappings_map_nodes: map_off is not non-decreasing"); return DBGPHMM_ERR_INVALID; }
@@ -124,7 +124,7 @@ extern "C" int dbgphmm_mappings_map_nodes(const dbgphmm_mappings* mp, uint32_t n
     }
     *out = o;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 // ------------------------------------------------------------------ PHMMTables of one read
 struct dbgphmm_tables {
@@ -170,7 +170,7 @@ static int one_job(dbgphmm_model* m, const uint8_t* bases, uint64_t n, const dbg
 }
 
 extern "C" int dbgphmm_forward(dbgphmm_model* m, const uint8_t* bases, uint64_t n, int kind, const dbgphmm_mappings* mapping,
-                               uint64_t read_index, dbgphmm_tables** out) {
+                               uint64_t read_index, dbgphmm_tables** out) try {
     if (!m || !bases || !out || kind < 0 || kind > 3) { dbg_set_error("forward: bad argument"); return DBGPHMM_ERR_INVALID; }
     dbgphmm_tables* t = new dbgphmm_tables();
     t->dir = 0; t->kind = kind;
@@ -182,9 +182,9 @@ extern "C" int dbgphmm_forward(dbgphmm_model* m, const uint8_t* bases, uint64_t 
     if (st != DBGPHMM_OK) { dbgphmm_tables_destroy(t); return st; }
     *out = t;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" int dbgphmm_backward(dbgphmm_model* m, const uint8_t* bases, uint64_t n, int kind, const dbgphmm_mappings* mapping,
-                                uint64_t read_index, const dbgphmm_tables* fwd, dbgphmm_tables** out) {
+                                uint64_t read_index, const dbgphmm_tables* fwd, dbgphmm_tables** out) try {
     if (!m || !bases || !out || kind < 0 || kind > 3) { dbg_set_error("backward: bad argument"); return DBGPHMM_ERR_INVALID; }
     if (kind == DBGPHMM_BWD_BY_FORWARD && (!fwd || fwd->dir != 0 || fwd->bases.size() != n)) { dbg_set_error("backward_by_forward needs the forward tables of the same read"); return DBGPHMM_ERR_INVALID; }
     dbgphmm_tables* t = new dbgphmm_tables();
@@ -197,14 +197,14 @@ extern "C" int dbgphmm_backward(dbgphmm_model* m, const uint8_t* bases, uint64_t
     if (st != DBGPHMM_OK) { dbgphmm_tables_destroy(t); return st; }
     *out = t;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" uint64_t dbgphmm_tables_len(const dbgphmm_tables* t) { return t ? t->desc.size() : 0; }
-extern "C" int dbgphmm_tables_full_prob(const dbgphmm_tables* t, double* logp) {
+extern "C" int dbgphmm_tables_full_prob(const dbgphmm_tables* t, double* logp) try {
     if (!t || !logp || t->desc.empty()) { dbg_set_error("tables_full_prob: empty tables (table.rs:380-393 panics)"); return DBGPHMM_ERR_INVALID; }
     *logp = t->dir == 0 ? xlog(t->desc.back().e) : xlog(t->desc.front().mb);
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_tables_row_info(const dbgphmm_tables* t, int64_t row, uint64_t info[3], double sc[3]) {
+} ABI_CATCH
+extern "C" int dbgphmm_tables_row_info(const dbgphmm_tables* t, int64_t row, uint64_t info[3], double sc[3]) try {
     if (!t || row < -1 || row >= (int64_t)t->desc.size()) { dbg_set_error("tables_row_info: row out of range"); return DBGPHMM_ERR_INVALID; }
     if (row < 0) {  // init_table: f_init (forward.rs:255-266) / b_init (backward.rs:197-211), both dense
         info[0] = 1; info[1] = t->m->N; info[2] = t->m->N;
@@ -215,7 +215,7 @@ extern "C" int dbgphmm_tables_row_info(const dbgphmm_tables* t, int64_t row, uin
     info[0] = r.kind == ROW_DENSE; info[1] = r.kind == ROW_DENSE ? t->m->N : r.n_mi; info[2] = r.kind == ROW_DENSE ? t->m->N : r.n_d;
     sc[0] = xlog(r.mb); sc[1] = xlog(r.ib); sc[2] = xlog(r.e);
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 static inline double lg(double v, int e) { return v == 0.0 ? -INFINITY : std::log(v) + (double)e * LN2; }
 
 // raw copy of a stored row to the host
@@ -247,7 +247,7 @@ static int fetch_row(const dbgphmm_tables* t, const RowDesc& r, HostRow* h) {
     return DBGPHMM_OK;
 }
 
-extern "C" int dbgphmm_tables_row_export(const dbgphmm_tables* t, int64_t row, uint32_t* ids_mi, double* om, double* oi, uint32_t* ids_d, double* od) {
+extern "C" int dbgphmm_tables_row_export(const dbgphmm_tables* t, int64_t row, uint32_t* ids_mi, double* om, double* oi, uint32_t* ids_d, double* od) try {
     if (!t || row < -1 || row >= (int64_t)t->desc.size()) { dbg_set_error("tables_row_export: row out of range"); return DBGPHMM_ERR_INVALID; }
     const dbgphmm_model* m = t->m;
     if (row < 0) {
@@ -268,9 +268,9 @@ extern "C" int dbgphmm_tables_row_export(const dbgphmm_tables* t, int64_t row, u
         for (uint32_t a = 0; a < r.n_d; a++) { uint32_t e = h.dlist[a]; ids_d[a] = m->orig_of[h.id[e]]; od[a] = lg(h.d[e], h.ex[e]); }
     }
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
-extern "C" int dbgphmm_tables_row_top_nodes(const dbgphmm_tables* t, int64_t row, int by_ratio, uint32_t k, double ratio, uint32_t* out, uint32_t* n_out) {
+extern "C" int dbgphmm_tables_row_top_nodes(const dbgphmm_tables* t, int64_t row, int by_ratio, uint32_t k, double ratio, uint32_t* out, uint32_t* n_out) try {
     if (!t || !out || !n_out || row < 0 || row >= (int64_t)t->desc.size()) { dbg_set_error("tables_row_top_nodes: row out of range"); return DBGPHMM_ERR_INVALID; }
     dbgphmm_model* m = t->m;
     const RowDesc& r = t->desc[row];
@@ -309,7 +309,7 @@ extern "C" int dbgphmm_tables_row_top_nodes(const dbgphmm_tables* t, int64_t row
     }
     *n_out = cnt;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 // ------------------------------------------------------------------ PHMMOutput of one read
 static int check_pair(const dbgphmm_model* m, const dbgphmm_tables* f, const dbgphmm_tables* b) {
@@ -318,7 +318,7 @@ static int check_pair(const dbgphmm_model* m, const dbgphmm_tables* f, const dbg
     }
     return DBGPHMM_OK;
 }
-extern "C" int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* freqs) {
+extern "C" int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* freqs) try {
     ST_TRY(check_pair(m, fwd, bwd));
     CUDA_TRY(cudaSetDevice(m->device));
     DevBuf b_f;
@@ -329,9 +329,9 @@ extern "C" int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables*
     ST_TRY(run_products_freqs(m, jobs, fwd->store, bwd->store, b_f.as<double>()));
     CUDA_TRY(cudaMemcpy(freqs, b_f.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" int dbgphmm_output_edge_and_init_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* edge_freqs,
-                                                  double* init_freqs) {
+                                                  double* init_freqs) try {
     ST_TRY(check_pair(m, fwd, bwd));
     if (!edge_freqs || !init_freqs) { dbg_set_error("to_edge_and_init_freqs: null output"); return DBGPHMM_ERR_INVALID; }
     if (fwd->bases != bwd->bases) { dbg_set_error("to_edge_and_init_freqs: the two tables come from different reads (freq.rs:281-282)"); return DBGPHMM_ERR_INVALID; }
@@ -346,10 +346,10 @@ extern "C" int dbgphmm_output_edge_and_init_freqs(dbgphmm_model* m, const dbgphm
     if (m->E) CUDA_TRY(cudaMemcpy(edge_freqs, b_e.p, sizeof(double) * m->E, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(init_freqs, b_i.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 // q_score_exact (q.rs:66-96): init = sum_v A(Begin, v) ln p_init(v), trans = sum_(v,w) A(v, w) ln p_trans(v, w) over emittable nodes
 // (emission != 'n'); the prior term is always zero.  Host-side: two dot products over the model's parameters of candidate x.
-extern "C" int dbgphmm_q_score_exact(const dbgphmm_model* m, uint32_t x, const double* edge_freqs, const double* init_freqs, double out[3]) {
+extern "C" int dbgphmm_q_score_exact(const dbgphmm_model* m, uint32_t x, const double* edge_freqs, const double* init_freqs, double out[3]) try {
     if (!m || !edge_freqs || !init_freqs || !out) { dbg_set_error("q_score_exact: bad argument"); return DBGPHMM_ERR_INVALID; }
     std::vector<double> li(m->N), lt(std::max<uint32_t>(m->E, 1));
     ST_TRY(dbgphmm_model_get_probs(m, x, li.data(), lt.data()));
@@ -366,9 +366,9 @@ extern "C" int dbgphmm_q_score_exact(const dbgphmm_model* m, uint32_t x, const d
     }
     out[0] = init; out[1] = trans; out[2] = 0.0;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, int by_ratio, uint32_t n_active,
-                                      double ratio, dbgphmm_mappings** out) {
+                                      double ratio, dbgphmm_mappings** out) try {
     ST_TRY(check_pair(m, fwd, bwd));
     CUDA_TRY(cudaSetDevice(m->device));
     std::vector<HJob> jobs(1);
@@ -378,21 +378,21 @@ extern "C" int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fw
     if (st != DBGPHMM_OK) { delete mp; return st; }
     *out = mp;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 // ------------------------------------------------------------------ bulk calls
 static void reset_times() { g_times = EngineTimes(); }
-extern "C" int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells) {
+extern "C" int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells) try {
     ms[0] = g_times.dense_ms; ms[1] = g_times.sparse_ms; ms[2] = g_times.product_ms; ms[3] = g_times.total_ms;
     if (dense_cells) *dense_cells = g_times.dense_cells;
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_last_dense_kernel(double* ms, uint64_t* launches, uint64_t* cells) {
+} ABI_CATCH
+extern "C" int dbgphmm_last_dense_kernel(double* ms, uint64_t* launches, uint64_t* cells) try {
     if (ms) *ms = g_times.dense_kernel_ms;
     if (launches) *launches = g_times.dense_kernel_launches;
     if (cells) *cells = g_times.dense_kernel_cells;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 static int check_reads_mappings(const dbgphmm_reads* reads, const dbgphmm_mappings* mp) {
     if (!mp) return DBGPHMM_OK;
@@ -419,7 +419,7 @@ static std::vector<std::pair<size_t, size_t>> plan_batches(const std::vector<uin
 }
 
 extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads* reads, const dbgphmm_mappings* mappings, int use_max_ratio,
-                                          double* out_logp, double* out_per_read) {
+                                          double* out_logp, double* out_per_read) try {
     if (!m || !reads || !out_logp) { dbg_set_error("to_full_prob_reads: bad argument"); return DBGPHMM_ERR_INVALID; }
     ST_TRY(check_reads_mappings(reads, mappings));
     CUDA_TRY(cudaSetDevice(m->device));
@@ -490,7 +490,7 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
         out_logp[x] = s;
     }
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 static void run_kinds(int mode, int use_max_ratio, int* fk, int* bk) {
     switch (mode) {
@@ -626,7 +626,7 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
 
 extern "C" int dbgphmm_run_node_freqs_dev(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int use_max_ratio,
                                           const dbgphmm_mappings* mappings, double* node_freqs_dev, double* logp_fwd_dev, double* logp_bwd_dev,
-                                          uint64_t cells[2]) {
+                                          uint64_t cells[2]) try {
     if (!m || !reads || mode < 0 || mode > 3) { dbg_set_error("run_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
     std::vector<double> lf(reads->n_reads), lb(reads->n_reads);
@@ -634,9 +634,9 @@ extern "C" int dbgphmm_run_node_freqs_dev(dbgphmm_model* m, const dbgphmm_reads*
     if (logp_fwd_dev && !lf.empty()) CUDA_TRY(cudaMemcpy(logp_fwd_dev, lf.data(), 8 * lf.size(), cudaMemcpyHostToDevice));
     if (logp_bwd_dev && !lb.empty()) CUDA_TRY(cudaMemcpy(logp_bwd_dev, lb.data(), 8 * lb.size(), cudaMemcpyHostToDevice));
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" int dbgphmm_run_node_freqs(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int use_max_ratio, const dbgphmm_mappings* mappings,
-                                      double* node_freqs, double* logp_fwd, double* logp_bwd, uint64_t cells[2]) {
+                                      double* node_freqs, double* logp_fwd, double* logp_bwd, uint64_t cells[2]) try {
     if (!m || !reads || mode < 0 || mode > 3) { dbg_set_error("run_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
     DevBuf b_f;
@@ -644,9 +644,9 @@ extern "C" int dbgphmm_run_node_freqs(dbgphmm_model* m, const dbgphmm_reads* rea
     ST_TRY(run_impl(m, reads, mode, use_max_ratio, mappings, node_freqs ? b_f.as<double>() : nullptr, logp_fwd, logp_bwd, cells, nullptr, 0));
     if (node_freqs) CUDA_TRY(cudaMemcpy(node_freqs, b_f.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" int dbgphmm_generate_mappings(dbgphmm_model* m, const dbgphmm_reads* reads, const dbgphmm_mappings* mappings, int use_max_ratio,
-                                         dbgphmm_mappings** out) {
+                                         dbgphmm_mappings** out) try {
     if (!m || !reads || !out) { dbg_set_error("generate_mappings: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
     dbgphmm_mappings* mp = new dbgphmm_mappings();
@@ -657,4 +657,4 @@ extern "C" int dbgphmm_generate_mappings(dbgphmm_model* m, const dbgphmm_reads* 
     if (st != DBGPHMM_OK) { delete mp; return st; }
     *out = mp;
     return DBGPHMM_OK;
-}
+} ABI_CATCH

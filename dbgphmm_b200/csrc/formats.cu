@@ -61,14 +61,14 @@ static int write_file(const char* path, const std::string& text) {
             if (n <= 0) { gzclose(f); dbg_set_error(std::string("write error in ") + path); return DBGPHMM_ERR_INVALID; }
             off += (size_t)n;
         }
-        gzclose(f);
+        if (gzclose(f) != Z_OK) { dbg_set_error(std::string("write error in ") + path); return DBGPHMM_ERR_INVALID; }   // (the last block is flushed here)
         return DBGPHMM_OK;
     }
     FILE* f = fopen(path, "wb");
     if (!f) { dbg_set_error(std::string("cannot create ") + path); return DBGPHMM_ERR_INVALID; }
     size_t w = fwrite(text.data(), 1, text.size(), f);
-    fclose(f);
-    if (w != text.size()) { dbg_set_error(std::string("write error in ") + path); return DBGPHMM_ERR_INVALID; }
+    const int rc = fclose(f);
+    if (w != text.size() || rc != 0) { dbg_set_error(std::string("write error in ") + path); return DBGPHMM_ERR_INVALID; }
     return DBGPHMM_OK;
 }
 
@@ -136,7 +136,7 @@ static int dbg_finish(dbgphmm_dbg* d) {
     return DBGPHMM_OK;
 }
 
-extern "C" int dbgphmm_dbg_from_text(const char* text, uint64_t len, dbgphmm_dbg** out) {
+extern "C" int dbgphmm_dbg_from_text(const char* text, uint64_t len, dbgphmm_dbg** out) try {
     if (!text || !out) { dbg_set_error("dbg_from_text: bad argument"); return DBGPHMM_ERR_INVALID; }
     dbgphmm_dbg* d = new dbgphmm_dbg();
     std::vector<std::string> f;
@@ -192,23 +192,23 @@ extern "C" int dbgphmm_dbg_from_text(const char* text, uint64_t len, dbgphmm_dbg
     if (st != DBGPHMM_OK) { delete d; return st; }
     *out = d;
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_dbg_from_file(const char* path, dbgphmm_dbg** out) {
+} ABI_CATCH
+extern "C" int dbgphmm_dbg_from_file(const char* path, dbgphmm_dbg** out) try {
     if (!path || !out) { dbg_set_error("dbg_from_file: bad argument"); return DBGPHMM_ERR_INVALID; }
     std::string text;
     ST_TRY(read_file(path, &text));
     return dbgphmm_dbg_from_text(text.data(), text.size(), out);
-}
+} ABI_CATCH
 extern "C" void dbgphmm_dbg_destroy(dbgphmm_dbg* d) { delete d; }
 
-extern "C" int dbgphmm_dbg_sizes(const dbgphmm_dbg* d, uint32_t sizes[6]) {
+extern "C" int dbgphmm_dbg_sizes(const dbgphmm_dbg* d, uint32_t sizes[6]) try {
     if (!d || !sizes) { dbg_set_error("dbg_sizes: bad argument"); return DBGPHMM_ERR_INVALID; }
     sizes[0] = d->k; sizes[1] = d->n_nodes_full; sizes[2] = (uint32_t)d->fsrc.size(); sizes[3] = (uint32_t)d->km1mer.size();
     sizes[4] = (uint32_t)d->edges.size(); sizes[5] = (uint32_t)d->psrc.size();
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" int dbgphmm_dbg_phmm_graph(const dbgphmm_dbg* d, uint32_t* edge_src, uint32_t* edge_dst, uint8_t* emission, uint32_t* copy_nums,
-                                      uint32_t* compact_edge_of) {
+                                      uint32_t* compact_edge_of) try {
     if (!d) { dbg_set_error("dbg_phmm_graph: bad argument"); return DBGPHMM_ERR_INVALID; }
     if (edge_src) memcpy(edge_src, d->psrc.data(), 4 * d->psrc.size());
     if (edge_dst) memcpy(edge_dst, d->pdst.data(), 4 * d->pdst.size());
@@ -216,12 +216,12 @@ extern "C" int dbgphmm_dbg_phmm_graph(const dbgphmm_dbg* d, uint32_t* edge_src, 
     if (copy_nums) for (size_t e = 0; e < d->fcompact.size(); e++) copy_nums[e] = d->edges[d->fcompact[e]].copy_num;
     if (compact_edge_of) memcpy(compact_edge_of, d->fcompact.data(), 4 * d->fcompact.size());
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_dbg_get_copy_nums(const dbgphmm_dbg* d, uint32_t* compact_copy_nums) {
+} ABI_CATCH
+extern "C" int dbgphmm_dbg_get_copy_nums(const dbgphmm_dbg* d, uint32_t* compact_copy_nums) try {
     if (!d || !compact_copy_nums) { dbg_set_error("dbg_get_copy_nums: bad argument"); return DBGPHMM_ERR_INVALID; }
     for (size_t e = 0; e < d->edges.size(); e++) compact_copy_nums[e] = d->edges[e].copy_num;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 // MultiDbg::is_copy_nums_valid (multi_dbg.rs:1008-1014): copy numbers in == out at every node (interior nodes of a compact edge
 // are balanced by construction, so the compact nodes decide)
 static bool copy_nums_valid(const dbgphmm_dbg* d, const uint32_t* x) {
@@ -230,19 +230,19 @@ static bool copy_nums_valid(const dbgphmm_dbg* d, const uint32_t* x) {
     for (long long b : bal) if (b != 0) return false;
     return true;
 }
-extern "C" int dbgphmm_dbg_set_copy_nums(dbgphmm_dbg* d, const uint32_t* compact_copy_nums) {
+extern "C" int dbgphmm_dbg_set_copy_nums(dbgphmm_dbg* d, const uint32_t* compact_copy_nums) try {
     if (!d || !compact_copy_nums) { dbg_set_error("dbg_set_copy_nums: bad argument"); return DBGPHMM_ERR_INVALID; }
     if (!copy_nums_valid(d, compact_copy_nums)) { dbg_set_error("invalid new copy_nums"); return DBGPHMM_ERR_INVALID; }   // multi_dbg.rs:1051
     for (size_t e = 0; e < d->edges.size(); e++) d->edges[e].copy_num = compact_copy_nums[e];
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_dbg_expand_copy_nums(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, uint32_t* full) {
+} ABI_CATCH
+extern "C" int dbgphmm_dbg_expand_copy_nums(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, uint32_t* full) try {
     if (!d || !compact || !full) { dbg_set_error("dbg_expand_copy_nums: bad argument"); return DBGPHMM_ERR_INVALID; }
     const size_t Ec = d->edges.size(), N = d->fcompact.size();
     for (uint32_t b = 0; b < n_batch; b++)
         for (size_t e = 0; e < N; e++) full[(size_t)b * N + e] = compact[(size_t)b * Ec + d->fcompact[e]];
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 static int copy_out(const std::string& s, char* buf, uint64_t cap, uint64_t* needed) {
     if (needed) *needed = s.size();
@@ -263,17 +263,17 @@ static std::string dbg_text(const dbgphmm_dbg* d) {
     }
     return s;
 }
-extern "C" int dbgphmm_dbg_to_text(const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed) {
+extern "C" int dbgphmm_dbg_to_text(const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed) try {
     if (!d) { dbg_set_error("dbg_to_text: bad argument"); return DBGPHMM_ERR_INVALID; }
     return copy_out(dbg_text(d), buf, cap, needed);
-}
-extern "C" int dbgphmm_dbg_to_file(const dbgphmm_dbg* d, const char* path) {
+} ABI_CATCH
+extern "C" int dbgphmm_dbg_to_file(const dbgphmm_dbg* d, const char* path) try {
     if (!d || !path) { dbg_set_error("dbg_to_file: bad argument"); return DBGPHMM_ERR_INVALID; }
     return write_file(path, dbg_text(d));
-}
+} ABI_CATCH
 
 // MultiDbg::to_phmm / to_non_zero_phmm / to_uniform_phmm (multi_dbg.rs:1391-1409): n_warmup := k, probabilities from the copy numbers
-extern "C" int dbgphmm_dbg_to_model(const dbgphmm_dbg* d, const dbgphmm_params* params, int mode, int device, uint64_t mem_budget_bytes, dbgphmm_model** out) {
+extern "C" int dbgphmm_dbg_to_model(const dbgphmm_dbg* d, const dbgphmm_params* params, int mode, int device, uint64_t mem_budget_bytes, dbgphmm_model** out) try {
     if (!d || !params || !out || mode < 0 || mode > 2) { dbg_set_error("dbg_to_model: bad argument"); return DBGPHMM_ERR_INVALID; }
     dbgphmm_params p = *params;
     p.n_warmup = d->k;
@@ -287,7 +287,7 @@ extern "C" int dbgphmm_dbg_to_model(const dbgphmm_dbg* d, const dbgphmm_params* 
     if (st != DBGPHMM_OK) { dbgphmm_model_destroy(m); return st; }
     *out = m;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 // ------------------------------------------------------------------------------------------------ MAP
 // f64 as Rust's `{}` prints it: shortest digits that round-trip, never in exponent notation ; -inf / inf / NaN by name
@@ -308,7 +308,7 @@ static bool parse_f64(const std::string& t, double* v) {
     return !t.empty() && *e == 0;
 }
 
-extern "C" int dbgphmm_mappings_from_map_text(const char* text, uint64_t len, dbgphmm_mappings** out) {
+extern "C" int dbgphmm_mappings_from_map_text(const char* text, uint64_t len, dbgphmm_mappings** out) try {
     if (!text || !out) { dbg_set_error("mappings_from_map_text: bad argument"); return DBGPHMM_ERR_INVALID; }
     dbgphmm_mappings* mp = new dbgphmm_mappings();
     mp->read_off.push_back(0); mp->row_off.push_back(0);
@@ -349,13 +349,13 @@ extern "C" int dbgphmm_mappings_from_map_text(const char* text, uint64_t len, db
     if (n_reads == 0) mp->read_off.assign(1, 0);
     *out = mp;
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_mappings_from_map_file(const char* path, dbgphmm_mappings** out) {
+} ABI_CATCH
+extern "C" int dbgphmm_mappings_from_map_file(const char* path, dbgphmm_mappings** out) try {
     if (!path || !out) { dbg_set_error("mappings_from_map_file: bad argument"); return DBGPHMM_ERR_INVALID; }
     std::string text;
     ST_TRY(read_file(path, &text));
     return dbgphmm_mappings_from_map_text(text.data(), text.size(), out);
-}
+} ABI_CATCH
 static int map_text(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, std::string* out) {
     if (mp->read_off.size() != reads->n_reads + 1) { dbg_set_error("mappings / reads count mismatch"); return DBGPHMM_ERR_INVALID; }
     std::string& s = *out;
@@ -381,15 +381,15 @@ static int map_text(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, cons
     }
     return DBGPHMM_OK;
 }
-extern "C" int dbgphmm_mappings_to_map_text(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed) {
+extern "C" int dbgphmm_mappings_to_map_text(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed) try {
     if (!mp || !reads) { dbg_set_error("mappings_to_map_text: bad argument"); return DBGPHMM_ERR_INVALID; }
     std::string s;
     ST_TRY(map_text(mp, reads, d, &s));
     return copy_out(s, buf, cap, needed);
-}
-extern "C" int dbgphmm_mappings_to_map_file(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, const char* path) {
+} ABI_CATCH
+extern "C" int dbgphmm_mappings_to_map_file(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, const char* path) try {
     if (!mp || !reads || !path) { dbg_set_error("mappings_to_map_file: bad argument"); return DBGPHMM_ERR_INVALID; }
     std::string s;
     ST_TRY(map_text(mp, reads, d, &s));
     return write_file(path, s);
-}
+} ABI_CATCH

@@ -486,7 +486,7 @@ __global__ void k_copy_to_probs(const uint32_t* __restrict__ cn, const uint8_t* 
     }
 }
 
-extern "C" int dbgphmm_model_set_copy_nums_batch(dbgphmm_model* m, uint32_t n_batch, const uint32_t* copy_nums, int mode) {
+extern "C" int dbgphmm_model_set_copy_nums_batch(dbgphmm_model* m, uint32_t n_batch, const uint32_t* copy_nums, int mode) try {
     if (!m || !copy_nums || n_batch == 0 || mode < 0 || mode > 2) { dbg_set_error("set_copy_nums_batch: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
     uint32_t N = m->N, E = m->E;
@@ -507,9 +507,9 @@ extern "C" int dbgphmm_model_set_copy_nums_batch(dbgphmm_model* m, uint32_t n_ba
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     cudaFree(d_cn); cudaFree(d_total);
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
-extern "C" int dbgphmm_model_get_probs(const dbgphmm_model* m, uint32_t x, double* log_init, double* log_trans) {
+extern "C" int dbgphmm_model_get_probs(const dbgphmm_model* m, uint32_t x, double* log_init, double* log_trans) try {
     if (!m || x >= m->n_batch) { dbg_set_error("get_probs: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
     std::vector<double> init(m->N), trans(m->E);
@@ -518,11 +518,11 @@ extern "C" int dbgphmm_model_get_probs(const dbgphmm_model* m, uint32_t x, doubl
     for (uint32_t p = 0; p < m->N; p++) log_init[m->orig_of[p]] = std::log(init[p]);
     for (uint32_t e = 0; e < m->E; e++) log_trans[e] = std::log(trans[e]);
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 
 extern "C" int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const uint32_t* edge_src, const uint32_t* edge_dst,
                                     const uint8_t* emission, const double* log_init, const double* log_trans,
-                                    const dbgphmm_params* params, int device, uint64_t mem_budget_bytes, dbgphmm_model** out) {
+                                    const dbgphmm_params* params, int device, uint64_t mem_budget_bytes, dbgphmm_model** out) try {
     if (!out || !params || !emission || !log_init || (n_edges && (!edge_src || !edge_dst || !log_trans)) || n_nodes == 0) {
         dbg_set_error("model_create: bad argument"); return DBGPHMM_ERR_INVALID;
     }
@@ -555,17 +555,17 @@ extern "C" int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const ui
     if (st != DBGPHMM_OK) { model_free(m); return st; }
     *out = m;
     return DBGPHMM_OK;
-}
+} ABI_CATCH
 extern "C" void dbgphmm_model_destroy(dbgphmm_model* m) { model_free(m); }
-extern "C" int dbgphmm_model_set_params(dbgphmm_model* m, const dbgphmm_params* p) {
+extern "C" int dbgphmm_model_set_params(dbgphmm_model* m, const dbgphmm_params* p) try {
     if (!m || !p || p->n_max_gaps != 4) { dbg_set_error("set_params: bad argument"); return DBGPHMM_ERR_INVALID; }
     m->params = *p; m->lin = to_lin(*p);
     return DBGPHMM_OK;
-}
-extern "C" int dbgphmm_model_set_probs(dbgphmm_model* m, const double* log_init, const double* log_trans) {
+} ABI_CATCH
+extern "C" int dbgphmm_model_set_probs(dbgphmm_model* m, const double* log_init, const double* log_trans) try {
     if (!m || !log_init) { dbg_set_error("set_probs: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
     return model_upload_probs(m, log_init, log_trans);
-}
+} ABI_CATCH
 extern "C" uint32_t dbgphmm_model_n_nodes(const dbgphmm_model* m) { return m ? m->N : 0; }
 extern "C" uint32_t dbgphmm_model_n_batch(const dbgphmm_model* m) { return m ? m->n_batch : 0; }

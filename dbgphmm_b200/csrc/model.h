@@ -2,6 +2,8 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include "common.cuh"
@@ -22,6 +24,13 @@ void dbg_set_error(const std::string& s);
         int _s = (expr);             \
         if (_s != DBGPHMM_OK) return _s; \
     } while (0)
+
+// Every status-returning entry point of the C ABI is a function-try-block closed by this: no C++ exception (host allocation
+// failure inside a std::vector, ...) crosses the boundary into ctypes / Rust / C callers
+#define ABI_CATCH                                                                                                             \
+    catch (const std::bad_alloc&) { dbg_set_error("out of host memory"); return DBGPHMM_ERR_OOM; }                            \
+    catch (const std::exception& e) { dbg_set_error(std::string("C++ exception: ") + e.what()); return DBGPHMM_ERR_INVALID; } \
+    catch (...) { dbg_set_error("unknown C++ exception"); return DBGPHMM_ERR_INVALID; }
 
 extern std::atomic<unsigned long long> g_launch_count;
 #define COUNT_LAUNCH() (g_launch_count.fetch_add(1, std::memory_order_relaxed))

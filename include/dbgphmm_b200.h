@@ -6,7 +6,8 @@
  * re-exposes these under the original method names lives in rust/ (source only).
  *
  * Conventions
- *   - every call returns an int status (0 = DBGPHMM_OK); the reference panics instead (no Result).
+ *   - every call returns an int status (0 = DBGPHMM_OK); the reference panics instead (no Result).  No C++ exception
+ *     crosses the boundary: allocation failures and the like come back as a status as well.
  *     dbgphmm_last_error() returns a thread-local message for the last non-zero status.
  *   - probabilities cross the ABI as natural-log f64, exactly `Prob.0` (prob.rs:13,74-76);
  *     zero probability is -INFINITY.
@@ -36,7 +37,7 @@ extern "C" {
                                    reference's ArrayVec-backed SparseVec panics with "insufficient capacity") */
 #define DBGPHMM_ERR_ZERO_PROB 4 /* P(read) == 0 where the reference would produce NaN and panic in Ord
                                    (table.rs:500-505 with prob.rs:296-300) */
-#define DBGPHMM_ERR_OOM 5       /* device memory budget too small for one read */
+#define DBGPHMM_ERR_OOM 5       /* device memory budget too small for one read, or a host allocation failed */
 
 #define DBGPHMM_MAX_ACTIVE_NODES 400 /* hmmv2/table.rs:22 */
 

@@ -136,3 +136,11 @@ def test_dbg_file_to_phmm_scores_like_the_hand_built_model():
         o.set_probs(li, lt)
         s, p = o.to_full_prob_reads(O.Reads(reads), None, False)
         assert np.allclose(per[b], p, rtol=1e-9, atol=0)
+
+
+def test_no_cpp_exception_crosses_the_c_abi():
+    """Every status-returning entry point is a function-try-block (ABI_CATCH, csrc/model.h).  A second K line that contradicts
+    the E lines already read makes std::string::substr throw inside dbg_finish: the caller gets a status, not std::terminate."""
+    with pytest.raises(H.DbgphmmError) as ei:
+        H.MultiDbg.from_dbg_str("K\t4\nN\t0\tnnn\nE\t0\t0\t0\tnnnA\t1\t0\nK\t10\n")
+    assert ei.value.status == H.ERR_INVALID and "C++ exception" in str(ei.value)
