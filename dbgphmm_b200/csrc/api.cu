@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <unordered_map>
 #include "engine.h"
 
@@ -43,13 +44,21 @@ extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) try {
 extern "C" int dbgphmm_mappings_create(uint64_t n_reads, const uint64_t* read_off, const uint64_t* row_off, const uint32_t* nodes,
                                        const double* logp, dbgphmm_mappings** out) try {
     if (!out || !read_off || !row_off) { dbg_set_error("mappings_create: bad argument"); return DBGPHMM_ERR_INVALID; }
-    dbgphmm_mappings* mp = new dbgphmm_mappings();
+    // the two CSR levels must be well-formed before anything is copied: they are trusted as indices from here on
+    if (read_off[0] != 0) { dbg_set_error("mappings_create: read_off[0] must be 0"); return DBGPHMM_ERR_INVALID; }
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (read_off[r + 1] < read_off[r]) { dbg_set_error("mappings_create: read_off is not non-decreasing"); return DBGPHMM_ERR_INVALID; }
+    const uint64_t n_rows = read_off[n_reads];
+    if (row_off[0] != 0) { dbg_set_error("mappings_create: row_off[0] must be 0"); return DBGPHMM_ERR_INVALID; }
+    for (uint64_t i = 0; i < n_rows; i++)
+        if (row_off[i + 1] < row_off[i]) { dbg_set_error("mappings_create: row_off is not non-decreasing"); return DBGPHMM_ERR_INVALID; }
+    const uint64_t n_ent = row_off[n_rows];
+    if (n_ent && !nodes) { dbg_set_error("mappings_create: nodes is null"); return DBGPHMM_ERR_INVALID; }
+    std::unique_ptr<dbgphmm_mappings> mp(new dbgphmm_mappings());
     mp->read_off.assign(read_off, read_off + n_reads + 1);
-    uint64_t n_rows = read_off[n_reads];
     mp->row_off.assign(row_off, row_off + n_rows + 1);
-    uint64_t n_ent = row_off[n_rows];
     if (n_ent) { mp->nodes.assign(nodes, nodes + n_ent); if (logp) mp->logp.assign(logp, logp + n_ent); else mp->logp.assign(n_ent, 0.0); }
-    *out = mp;
+    *out = mp.release();
     return DBGPHMM_OK;
 } ABI_CATCH
 extern "C" void dbgphmm_mappings_destroy(dbgphmm_mappings* mp) { delete mp; }

@@ -126,3 +126,20 @@ def test_rust_shim_stays_in_step_with_the_header_and_the_build():
     assert re.findall(r'"([a-z_]+\.cu)"', srcs) == B.SOURCES
     for flag in ("arch=compute_100a,code=sm_100a", "-lineinfo", "-lcudart", "-lz"):
         assert flag in brs, flag
+
+
+def test_mappings_create_rejects_malformed_csr(lib):
+    ro = lambda *v: np.array(v, np.uint64)
+    nodes = np.array([1, 2, 3], np.uint32); lp = np.zeros(3)
+    ok = H.Mappings(ro(0, 2), ro(0, 2, 3), nodes, lp)
+    assert ok.n_reads() == 1 and [list(x) for x in ok[0].nodes] == [[1, 2], [3]]
+    for read_off, row_off in ((ro(1, 2), ro(0, 2, 3)),        # read_off[0] != 0
+                              (ro(0, 2, 1), ro(0, 2, 3)),     # read_off decreasing
+                              (ro(0, 2), ro(1, 2, 3)),        # row_off[0] != 0
+                              (ro(0, 2), ro(0, 3, 2))):       # row_off decreasing
+        with pytest.raises(H.DbgphmmError) as ei:
+            H.Mappings(read_off, row_off, nodes, lp)
+        assert ei.value.status == H.ERR_INVALID
+    h = C.c_void_p()
+    st = lib.dbgphmm_mappings_create(1, ro(0, 2).ctypes.data_as(C.c_void_p), ro(0, 2, 3).ctypes.data_as(C.c_void_p), None, None, C.byref(h))
+    assert st == H.ERR_INVALID and b"nodes is null" in lib.dbgphmm_last_error()
