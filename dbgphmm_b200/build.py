@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdbgphmm_b200.so")
-SOURCES = ["model.cu", "dense.cu", "sparse.cu", "mapx.cu", "engine.cu", "products.cu", "api.cu", "formats.cu"]
+SOURCES = ["model.cu", "dense.cu", "sparse.cu", "mapx.cu", "engine.cu", "products.cu", "api.cu", "formats.cu", "score.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 

@@ -244,6 +244,35 @@ extern "C" int dbgphmm_dbg_expand_copy_nums(const dbgphmm_dbg* d, uint32_t n_bat
     return DBGPHMM_OK;
 } ABI_CATCH
 
+// MultiDbg::genome_size (multi_dbg.rs:1018-1028): copies of every k-mer whose last base is not the null base, for the current copy
+// numbers (compact == NULL, n_batch = 1) or for a batch of candidates over compact edges
+extern "C" int dbgphmm_dbg_genome_size(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, uint64_t* out) try {
+    if (!d || !out || (!compact && n_batch != 1)) { dbg_set_error("dbg_genome_size: bad argument"); return DBGPHMM_ERR_INVALID; }
+    const size_t Ec = d->edges.size();
+    std::vector<uint64_t> emitting(Ec, 0);   // non-null bases along each compact edge
+    for (size_t e = 0; e < d->fcompact.size(); e++) if (d->fbase[e] != NULL_BASE) emitting[d->fcompact[e]]++;
+    for (uint32_t b = 0; b < n_batch; b++) {
+        uint64_t g = 0;
+        for (size_t e = 0; e < Ec; e++) g += emitting[e] * (uint64_t)(compact ? compact[(size_t)b * Ec + e] : d->edges[e].copy_num);
+        out[b] = g;
+    }
+    return DBGPHMM_OK;
+} ABI_CATCH
+// MultiDbg::n_euler_circuits (multi_dbg.rs:831-837): ln of the number of Euler circuits of the compact graph with the copy numbers
+// as multiplicities, separate components not allowed.  Candidates must balance at every node, as set_copy_nums asserts.
+extern "C" int dbgphmm_dbg_n_euler_circuits(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, double* out) try {
+    if (!d || !out || (!compact && n_batch != 1)) { dbg_set_error("dbg_n_euler_circuits: bad argument"); return DBGPHMM_ERR_INVALID; }
+    const size_t Ec = d->edges.size();
+    std::vector<uint32_t> s(Ec), t(Ec), w(Ec);
+    for (size_t e = 0; e < Ec; e++) { s[e] = d->edges[e].s; t[e] = d->edges[e].t; }
+    for (uint32_t b = 0; b < n_batch; b++) {
+        for (size_t e = 0; e < Ec; e++) w[e] = compact ? compact[(size_t)b * Ec + e] : d->edges[e].copy_num;
+        if (!copy_nums_valid(d, w.data())) { dbg_set_error("invalid copy_nums (candidate " + std::to_string(b) + ")"); return DBGPHMM_ERR_INVALID; }
+        ST_TRY(dbgphmm_euler_circuit_count((uint32_t)d->km1mer.size(), Ec, s.data(), t.data(), w.data(), 0, &out[b]));
+    }
+    return DBGPHMM_OK;
+} ABI_CATCH
+
 static int copy_out(const std::string& s, char* buf, uint64_t cap, uint64_t* needed) {
     if (needed) *needed = s.size();
     if (buf && cap >= s.size()) memcpy(buf, s.data(), s.size());

@@ -53,6 +53,7 @@ SYMBOLS = [
     "dbgphmm_dbg_get_copy_nums", "dbgphmm_dbg_set_copy_nums", "dbgphmm_dbg_expand_copy_nums", "dbgphmm_dbg_to_text", "dbgphmm_dbg_to_file",
     "dbgphmm_dbg_to_model", "dbgphmm_mappings_from_map_text", "dbgphmm_mappings_from_map_file", "dbgphmm_mappings_to_map_text",
     "dbgphmm_mappings_to_map_file",
+    "dbgphmm_dbg_genome_size", "dbgphmm_dbg_n_euler_circuits", "dbgphmm_euler_circuit_count", "dbgphmm_prior_normal",
 ]
 
 _lib = None
@@ -124,6 +125,10 @@ def lib():
     L.dbgphmm_mappings_from_map_file.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.dbgphmm_mappings_to_map_text.argtypes = [vp, vp, vp, vp, u64, C.POINTER(u64)]
     L.dbgphmm_mappings_to_map_file.argtypes = [vp, vp, vp, C.c_char_p]
+    L.dbgphmm_dbg_genome_size.argtypes = [vp, u32, vp, vp]
+    L.dbgphmm_dbg_n_euler_circuits.argtypes = [vp, u32, vp, vp]
+    L.dbgphmm_euler_circuit_count.argtypes = [u32, u64, vp, vp, vp, ci, C.POINTER(dbl)]
+    L.dbgphmm_prior_normal.argtypes = [dbl, dbl, dbl, C.POINTER(dbl)]
     for s in SYMBOLS:
         getattr(L, s)  # fail loudly if the library does not export a declared symbol
     _lib = L
@@ -496,6 +501,87 @@ BWD_DENSE, BWD_SPARSE, BWD_MAPPING, BWD_BY_FORWARD = range(4)
 RUN_MODES = {"dense": 0, "sparse": 1, "sparse_adaptive": 2, "with_mapping": 3}
 
 
+def _padd(a, b):
+    """Prob + Prob (prob.rs:181-197)."""
+    x, y = (a, b) if a >= b else (b, a)
+    if np.isneginf(y):
+        return x
+    if x == y:
+        return x + float(np.log(2.0))
+    return x + float(np.log1p(np.exp(y - x)))
+
+
+class Score:
+    """Score (multi_dbg/posterior.rs:164-208): natural logs; p() = P(R|X) P(G) #circuits."""
+    __slots__ = ("likelihood", "prior", "genome_size", "n_euler_circuits")
+
+    def __init__(self, likelihood, prior, genome_size, n_euler_circuits):
+        self.likelihood, self.prior, self.genome_size, self.n_euler_circuits = likelihood, prior, genome_size, n_euler_circuits
+
+    def p(self):
+        return self.likelihood + self.prior + self.n_euler_circuits
+
+    def __repr__(self):
+        return f"Score(likelihood={self.likelihood}, prior={self.prior}, genome_size={self.genome_size}, n_euler_circuits={self.n_euler_circuits})"
+
+
+class Posterior:
+    """Posterior (multi_dbg/posterior.rs:82-161): the distinct copy-number vectors seen so far with their scores."""
+
+    def __init__(self):
+        self.samples = []            # (copy_nums tuple, Score) in insertion order
+        self._p = -np.inf
+
+    def contains(self, copy_nums):
+        return self.find(copy_nums) is not None
+
+    def find(self, copy_nums):
+        key = tuple(int(c) for c in copy_nums)
+        for k, sc in self.samples:
+            if k == key:
+                return sc
+        return None
+
+    def add(self, copy_nums, score):
+        """posterior.rs:93-98: a copy-number vector counts once."""
+        if not self.contains(copy_nums):
+            self._p = _padd(self._p, score.p())
+            self.samples.append((tuple(int(c) for c in copy_nums), score))
+
+    def p(self):
+        return self._p
+
+    def max_sample(self):
+        """posterior.rs:113-118 (max_by_key: the LAST of equal maxima, like Iterator::max_by_key)."""
+        best = None
+        for k, sc in self.samples:
+            if best is None or sc.p() >= best[1].p():
+                best = (k, sc)
+        return best
+
+    def max_copy_nums(self):
+        return np.array(self.max_sample()[0], np.uint32)
+
+    def p_edge_x(self, edge, x):
+        """P(X[edge] = x | R) (posterior.rs:141-143 over hist.rs:48-71), natural log."""
+        z, px = -np.inf, -np.inf
+        for k, sc in self.samples:
+            w = sc.p() - self._p
+            z = _padd(z, w)
+            if k[edge] == x:
+                px = _padd(px, w)
+        return px - z if not np.isneginf(px) else -np.inf
+
+
+def euler_circuit_count(n_nodes, edges, allow_multiple_component):
+    """graph/euler.rs:94-123: ln of the number of Euler circuits of a multigraph given as (source, target, multiplicity) triples."""
+    e = np.ascontiguousarray(edges, np.uint32).reshape(-1, 3)
+    s, t, w = (np.ascontiguousarray(e[:, i]) for i in range(3))
+    v = C.c_double()
+    _check(lib().dbgphmm_euler_circuit_count(n_nodes, len(e), _p(s), _p(t), _p(w), int(allow_multiple_component), C.byref(v)))
+    return v.value
+
+
 class MultiDbg:
     """The part of MultiDbg (multi_dbg.rs:170-186) a DBG file carries: compact edges with their k-mers, copy numbers and
     full-graph edge ids.  Host only (no GPU needed) except to_phmm*."""
@@ -566,6 +652,50 @@ class MultiDbg:
         out = np.zeros((x.shape[0], self.n_edges_full), np.uint32)
         _check(lib().dbgphmm_dbg_expand_copy_nums(self._h, x.shape[0], _p(x), _p(out)))
         return out
+
+    # ---- the terms of to_score beside the likelihood (multi_dbg/posterior.rs:225-277)
+    def _candidates(self, candidates):
+        if candidates is None:
+            return None, 1
+        x = np.ascontiguousarray(np.atleast_2d(candidates), np.uint32)
+        if x.shape[1] != self.n_edges_compact:
+            raise DbgphmmError(ERR_INVALID, "candidates must be [B][n_edges_compact]")
+        return x, x.shape[0]
+
+    def genome_size(self, candidates=None):
+        """MultiDbg::genome_size (multi_dbg.rs:1018-1028) of the current copy numbers (an int) or of every candidate ([B])."""
+        x, b = self._candidates(candidates)
+        out = np.zeros(b, np.uint64)
+        _check(lib().dbgphmm_dbg_genome_size(self._h, b, _p(x), _p(out)))
+        return int(out[0]) if candidates is None else out
+
+    def n_euler_circuits(self, candidates=None):
+        """MultiDbg::n_euler_circuits (multi_dbg.rs:831-837): ln of the number of Euler circuits (-inf: none)."""
+        x, b = self._candidates(candidates)
+        out = np.zeros(b, np.float64)
+        _check(lib().dbgphmm_dbg_n_euler_circuits(self._h, b, _p(x), _p(out)))
+        return float(out[0]) if candidates is None else out
+
+    def to_prior(self, genome_size_expected, genome_size_sigma, candidates=None):
+        """MultiDbg::to_prior (posterior.rs:225-231): ln Normal(genome_size; expected, sigma)."""
+        g = np.atleast_1d(self.genome_size(candidates))
+        out = np.zeros(len(g)); v = C.c_double()
+        for i, x in enumerate(g):
+            _check(lib().dbgphmm_prior_normal(float(x), float(genome_size_expected), float(genome_size_sigma), C.byref(v)))
+            out[i] = v.value
+        return float(out[0]) if candidates is None else out
+
+    def to_scores(self, phmm, reads, mappings, candidates, genome_size_expected, genome_size_sigma, mode="normal"):
+        """MultiDbg::to_score (posterior.rs:259-277) for every candidate copy-number vector over compact edges at once: what
+        sample_posterior_once evaluates per neighbour with dbg.clone() + set_copy_nums + to_phmm + to_full_prob_reads
+        (posterior.rs:504-515).  `phmm`: a model of this graph (to_phmm); its parameter sets are replaced by the candidates'.
+        One expansion to k-mer copy numbers, one on-device derivation of (init, trans) for the batch, one batched
+        to_full_prob_reads (use_max_ratio = true like to_likelihood, posterior.rs:247-255), then the host-side terms."""
+        x, b = self._candidates(candidates)
+        phmm.set_copy_nums_batch(self.expand_copy_nums(x), mode)
+        like = phmm.to_full_prob_reads(reads, mappings, True)[0]
+        gs = self.genome_size(x); prior = self.to_prior(genome_size_expected, genome_size_sigma, x); ne = self.n_euler_circuits(x)
+        return [Score(float(like[i]), float(prior[i]), int(gs[i]), float(ne[i])) for i in range(b)]
 
     def _to_phmm(self, param, mode, device, mem_budget_bytes):
         src, dst, em, cn, _ = self.phmm_graph()

@@ -212,6 +212,21 @@ int dbgphmm_dbg_set_copy_nums(dbgphmm_dbg* d, const uint32_t* compact_copy_nums)
 /* Candidate copy-number vectors over compact edges [n_batch][n_edges_compact] (what sample_posterior_once proposes,
  * multi_dbg/posterior.rs:470-515) -> per-k-mer copy numbers [n_batch][n_edges_full] for dbgphmm_model_set_copy_nums_batch. */
 int dbgphmm_dbg_expand_copy_nums(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, uint32_t* full);
+/* The terms of MultiDbg::to_score beside the likelihood (multi_dbg/posterior.rs:225-277), for the current copy numbers (compact ==
+ * NULL, n_batch = 1) or a batch of candidates [n_batch][n_edges_compact]; with dbgphmm_to_full_prob_reads they give
+ * Score::p() = ln P(R|X) + ln P(G) + ln #circuits for every candidate of sample_posterior_once without rebuilding a MultiDbg.
+ *   genome_size      MultiDbg::genome_size (multi_dbg.rs:1018-1028)
+ *   n_euler_circuits MultiDbg::n_euler_circuits (multi_dbg.rs:831-837; BEST theorem, graph/euler.rs:22-123), natural log, -inf = none;
+ *                    candidates must balance at every node (DBGPHMM_ERR_INVALID otherwise, the assert of set_copy_nums) */
+int dbgphmm_dbg_genome_size(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, uint64_t* out);
+int dbgphmm_dbg_n_euler_circuits(const dbgphmm_dbg* d, uint32_t n_batch, const uint32_t* compact, double* out);
+/* euler_circuit_count (graph/euler.rs:94-123) of a multigraph given as an edge list with multiplicities (parallel edges and self
+ * loops allowed): ln of the number of Euler circuits; allow_multiple_component = product over the strongly connected components.
+ * A multigraph that does not balance at some node has no Euler circuit: -inf. */
+int dbgphmm_euler_circuit_count(uint32_t n_nodes, uint64_t n_edges, const uint32_t* edge_src, const uint32_t* edge_dst,
+                                const uint32_t* multiplicity, int allow_multiple_component, double* out_ln_count);
+/* MultiDbg::to_prior (posterior.rs:225-231) = distribution::normal(x, mu, sigma) (distribution.rs:22-25), natural log */
+int dbgphmm_prior_normal(double x, double mu, double sigma, double* out_ln_p);
 /* MultiDbg::to_dbg_writer / to_dbg_file (output.rs:140-199).  Text calls: buf may be NULL to query *needed. */
 int dbgphmm_dbg_to_text(const dbgphmm_dbg* d, char* buf, uint64_t cap, uint64_t* needed);
 int dbgphmm_dbg_to_file(const dbgphmm_dbg* d, const char* path);

@@ -302,6 +302,14 @@ private:
     uint32_t n_nodes_, n_edges_;
 };
 
+// Score (multi_dbg/posterior.rs:164-208), natural logs
+struct Score {
+    double likelihood = 0, prior = 0;
+    uint64_t genome_size = 0;
+    double n_euler_circuits = 0;
+    double p() const { return likelihood + prior + n_euler_circuits; }   // P(R|X) P(G) #circuits
+};
+
 // The part of MultiDbg a DBG file carries (multi_dbg.rs:170-186, multi_dbg/output.rs:155-345); host only.
 class MultiDbg {
 public:
@@ -349,6 +357,37 @@ public:
         dbgphmm_model* m = nullptr;
         check(dbgphmm_dbg_to_model(h_, &param, mode, device, mem_budget, &m));
         return m;
+    }
+    // The terms of to_score beside the likelihood (multi_dbg/posterior.rs:225-277) for the current copy numbers ...
+    uint64_t genome_size() const { uint64_t g = 0; check(dbgphmm_dbg_genome_size(h_, 1, nullptr, &g)); return g; }            // multi_dbg.rs:1018
+    double n_euler_circuits() const { double v = 0; check(dbgphmm_dbg_n_euler_circuits(h_, 1, nullptr, &v)); return v; }        // multi_dbg.rs:831 (ln)
+    double to_prior(uint32_t genome_size_expected, uint32_t genome_size_sigma) const {                                           // posterior.rs:225
+        double v = 0; check(dbgphmm_prior_normal((double)genome_size(), genome_size_expected, genome_size_sigma, &v)); return v;
+    }
+    // ... and for a batch of candidates over compact edges [n_batch][n_edges_compact]
+    std::vector<uint64_t> genome_size(uint32_t n_batch, const std::vector<uint32_t>& compact) const {
+        if (compact.size() != (size_t)n_batch * sz_[4]) throw Error(DBGPHMM_ERR_INVALID);
+        std::vector<uint64_t> g(n_batch); check(dbgphmm_dbg_genome_size(h_, n_batch, compact.data(), g.data())); return g;
+    }
+    std::vector<double> n_euler_circuits(uint32_t n_batch, const std::vector<uint32_t>& compact) const {
+        if (compact.size() != (size_t)n_batch * sz_[4]) throw Error(DBGPHMM_ERR_INVALID);
+        std::vector<double> v(n_batch); check(dbgphmm_dbg_n_euler_circuits(h_, n_batch, compact.data(), v.data())); return v;
+    }
+    // MultiDbg::to_score (posterior.rs:259-277) for every candidate at once: one expansion, one on-device (init, trans) derivation,
+    // one batched to_full_prob_reads on `phmm` (a model of this graph, to_phmm), then the host-side terms
+    std::vector<Score> to_scores(PHMMModel& phmm, const Reads& reads, const Mappings* mappings, uint32_t n_batch, const std::vector<uint32_t>& compact,
+                                 uint32_t genome_size_expected, uint32_t genome_size_sigma, int mode = 0) const {
+        const std::vector<uint32_t> full = expand_copy_nums(n_batch, compact);
+        phmm.set_copy_nums_batch(n_batch, full.data(), mode);
+        const std::vector<double> like = phmm.to_full_prob_reads(reads, mappings, true);
+        const std::vector<uint64_t> gs = genome_size(n_batch, compact);
+        const std::vector<double> ne = n_euler_circuits(n_batch, compact);
+        std::vector<Score> out(n_batch);
+        for (uint32_t b = 0; b < n_batch; b++) {
+            out[b].likelihood = like[b]; out[b].genome_size = gs[b]; out[b].n_euler_circuits = ne[b];
+            check(dbgphmm_prior_normal((double)gs[b], genome_size_expected, genome_size_sigma, &out[b].prior));
+        }
+        return out;
     }
     // MultiDbg::to_phmm / to_non_zero_phmm / to_uniform_phmm (multi_dbg.rs:1391-1409; n_warmup := k)
     std::unique_ptr<PHMMModel> to_phmm(const PHMMParams& param, int device = 0) const { return std::make_unique<PHMMModel>(to_phmm_handle(param, 0, device), sz_[5]); }

@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = root.join("dbgphmm_b200/csrc");
     // the same list and flags as dbgphmm_b200/build.py (tests/test_abi.py keeps the two in step)
-    let srcs = ["model.cu", "dense.cu", "sparse.cu", "mapx.cu", "engine.cu", "products.cu", "api.cu", "formats.cu"];
+    let srcs = ["model.cu", "dense.cu", "sparse.cu", "mapx.cu", "engine.cu", "products.cu", "api.cu", "formats.cu", "score.cu"];
     let mut objs = Vec::new();
     for s in srcs {
         let o = out.join(s.replace(".cu", ".o"));

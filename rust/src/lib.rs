@@ -94,6 +94,11 @@ extern "C" {
     pub fn dbgphmm_dbg_get_copy_nums(d: *const dbgphmm_dbg, compact_copy_nums: *mut u32) -> c_int;
     pub fn dbgphmm_dbg_set_copy_nums(d: *mut dbgphmm_dbg, compact_copy_nums: *const u32) -> c_int;
     pub fn dbgphmm_dbg_expand_copy_nums(d: *const dbgphmm_dbg, n_batch: u32, compact: *const u32, full: *mut u32) -> c_int;
+    pub fn dbgphmm_dbg_genome_size(d: *const dbgphmm_dbg, n_batch: u32, compact: *const u32, out: *mut u64) -> c_int;
+    pub fn dbgphmm_dbg_n_euler_circuits(d: *const dbgphmm_dbg, n_batch: u32, compact: *const u32, out: *mut f64) -> c_int;
+    pub fn dbgphmm_euler_circuit_count(n_nodes: u32, n_edges: u64, edge_src: *const u32, edge_dst: *const u32, multiplicity: *const u32,
+                                       allow_multiple_component: c_int, out_ln_count: *mut f64) -> c_int;
+    pub fn dbgphmm_prior_normal(x: f64, mu: f64, sigma: f64, out_ln_p: *mut f64) -> c_int;
     pub fn dbgphmm_dbg_to_text(d: *const dbgphmm_dbg, buf: *mut c_char, cap: u64, needed: *mut u64) -> c_int;
     pub fn dbgphmm_dbg_to_file(d: *const dbgphmm_dbg, path: *const c_char) -> c_int;
     pub fn dbgphmm_dbg_to_model(d: *const dbgphmm_dbg, params: *const dbgphmm_params, mode: c_int, device: c_int, mem_budget_bytes: u64,

@@ -64,6 +64,13 @@ static int host_only() {
     dbgphmm::Mapping a = m1.at(0);
     CHECK(a.nodes.size() == 2 && a.nodes[0] == std::vector<uint32_t>({1, 2}) && a.nodes[1] == std::vector<uint32_t>({3, 4}), 7);
     CHECK(a.probs[0][0] == m0.probs[0][0] && a.probs[1][1] == m0.probs[1][1], 8);
+    // n_euler_circuits_test_toy (multi_dbg.rs:2320-2328), genome size, prior
+    CHECK(near(std::exp(d->n_euler_circuits()), 1.0, 1e-4), 40);
+    CHECK(d->genome_size() == 18 && near(d->to_prior(18, 3), -0.5 * std::log(2.0 * M_PI * 9.0), 1e-15), 41);
+    auto ne = d->n_euler_circuits(2, {1, 3, 1, 0, 0, 0});
+    CHECK(near(std::exp(ne[0]), 1.0, 1e-4) && std::exp(ne[1]) == 0.0, 42);
+    dbgphmm::Score sc; sc.likelihood = -10; sc.prior = -2; sc.n_euler_circuits = std::log(5.0);
+    CHECK(near(sc.p(), -12 + std::log(5.0), 1e-15), 43);
     auto f = mp.to_node_freqs(5);   // hint.rs:161-171
     CHECK(near(f[0], 0.6, 1e-15) && near(f[2], 0.9, 1e-15) && f[4] == 0.0, 9);
     return 0;
