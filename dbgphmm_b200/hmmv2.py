@@ -697,6 +697,47 @@ class MultiDbg:
         gs = self.genome_size(x); prior = self.to_prior(genome_size_expected, genome_size_sigma, x); ne = self.n_euler_circuits(x)
         return [Score(float(like[i]), float(prior[i]), int(gs[i]), float(ne[i])) for i in range(b)]
 
+    def clone(self):
+        return MultiDbg.from_dbg_str(self.to_dbg_string())
+
+    def sample_posterior_once(self, phmm, reads, mappings, neighbors, posterior, genome_size_expected, genome_size_sigma, mode="normal"):
+        """MultiDbg::sample_posterior_once (posterior.rs:470-600) in its single-move form: score every neighbour the posterior has not
+        seen yet -- all of them in ONE batched to_scores where the reference clones the graph per neighbour under rayon -- add them,
+        and return the best sample (copy_nums tuple, Score) if it is not the current copy-number vector, else None.
+        `neighbors`: copy-number vectors over compact edges, e.g. the output of the reference's neighbour search (not built here)."""
+        todo, seen = [], set()
+        for c in neighbors:
+            key = tuple(int(v) for v in c)
+            if key not in seen and not posterior.contains(key):
+                seen.add(key); todo.append(key)
+        if todo:
+            for key, sc in zip(todo, self.to_scores(phmm, reads, mappings, np.array(todo, np.uint32), genome_size_expected, genome_size_sigma, mode)):
+                posterior.add(key, sc)
+        best = posterior.max_sample()
+        return best if best[0] != tuple(int(v) for v in self.get_copy_nums()) else None
+
+    def sample_posterior(self, phmm, reads, mappings, genome_size_expected, genome_size_sigma, neighbors_fn, max_iter, mode="normal"):
+        """The greedy search of MultiDbg::sample_posterior (posterior.rs:314-420): start from the current copy numbers, score the
+        neighbours, move to the best one, stop at a local optimum or after max_iter moves.  `neighbors_fn(dbg)` returns the candidate
+        sets to try in order (the reference tries rescue, partial and full neighbours, posterior.rs:352-372) for the copy numbers `dbg`
+        currently holds.  `self` is left untouched; returns the Posterior."""
+        post = Posterior()
+        dbg = self.clone()
+        copy_nums = tuple(int(v) for v in dbg.get_copy_nums())
+        post.add(copy_nums, dbg.to_scores(phmm, reads, mappings, np.array([copy_nums], np.uint32), genome_size_expected, genome_size_sigma, mode)[0])
+        n_iter = 0
+        while n_iter < max_iter:
+            dbg.set_copy_nums(np.array(copy_nums, np.uint32))
+            for cand in neighbors_fn(dbg):
+                sample = dbg.sample_posterior_once(phmm, reads, mappings, cand, post, genome_size_expected, genome_size_sigma, mode)
+                if sample is not None:
+                    copy_nums = sample[0]
+                    n_iter += 1
+                    break
+            else:
+                break        # no better neighbour: local optimum
+        return post
+
     def _to_phmm(self, param, mode, device, mem_budget_bytes):
         src, dst, em, cn, _ = self.phmm_graph()
         h = C.c_void_p()

@@ -140,3 +140,57 @@ def test_to_scores_batches_the_candidates_through_one_model_call():
     assert [s.likelihood for s in scores] == [-10.0, -20.0] and [s.genome_size for s in scores] == [30, 36]
     assert abs(math.exp(scores[0].n_euler_circuits) - 5.0) < 1e-4
     assert abs(scores[0].p() - (-10.0 + d.to_prior(28, 5) + math.log(5.0))) < 1e-9
+
+
+def test_sample_posterior_greedy_search_over_the_oracle():
+    """MultiDbg::sample_posterior (posterior.rs:314-420) with a caller-supplied neighbour generator, end to end on toy::repeat with
+    real likelihoods: the model calls are answered by the oracle (the checker standing in for the device, as in
+    tests/test_surface_host.py).  Reads come from the 3-unit genome of the toy; the search starts from 1 unit and walks +-1 steps."""
+    from dbgphmm_b200 import graphs
+    from oracle import oracle as O
+    d = H.MultiDbg.from_dbg_str(README_DBG)
+    sg, k = graphs.toy_repeat()
+    op = O.params_uniform(0.01); op.n_warmup = k
+    li, lt = sg.to_probs("normal")
+    o = O.PHMMModel(sg.src, sg.dst, sg.base, li, lt, op)
+    genome = b"TCCCAGCAGCAGCAGGAA"
+    reads = O.Reads([genome] * 4 + [genome[2:14], genome[5:]])
+    evaluated = []
+
+    class OracleModel:
+        def set_copy_nums_batch(self, full, mode):
+            self.full, self.mode = full, mode
+
+        def to_full_prob_reads(self, rd, mappings, use_max_ratio):
+            out = []
+            for x in self.full:
+                o.set_probs(*sg.to_probs(self.mode, x))
+                out.append(o.to_full_prob_reads(rd, mappings, use_max_ratio)[0])
+                evaluated.append(tuple(int(v) for v in x[6:9]))
+            return np.array(out), None
+
+    def neighbors(dbg):
+        c = dbg.get_copy_nums()
+        up = c.copy(); up[1] += 1
+        out = [up]
+        if c[1] > 0:
+            dn = c.copy(); dn[1] -= 1
+            out.append(dn)
+        return [out]
+
+    d.set_copy_nums(np.array([1, 1, 1], np.uint32))
+    post = d.sample_posterior(OracleModel(), reads, None, 18, 3, neighbors, max_iter=10)
+    assert list(d.get_copy_nums()) == [1, 1, 1]                        # self untouched
+    seen = [s[0] for s in post.samples]
+    assert seen[0] == (1, 1, 1) and len(set(seen)) == len(seen)          # every vector scored once (posterior.rs:93-98, 507-511)
+    assert len(evaluated) == len(seen)
+    best = post.max_sample()
+    assert best[0] == (1, 3, 1), (best, seen)                            # the truth: three units
+    # the walk went 1 -> 2 -> 3, looked at 4 and 2 from there and stopped
+    assert set(seen) == {(1, 1, 1), (1, 2, 1), (1, 0, 1), (1, 3, 1), (1, 4, 1)}
+    for key, sc in post.samples:
+        o.set_probs(*sg.to_probs("normal", d.expand_copy_nums(np.array([key], np.uint32))[0]))
+        want = o.to_full_prob_reads(reads, None, True)[0]
+        assert abs(sc.likelihood - want) < 1e-12 and sc.genome_size == 9 + 3 * key[1]
+    assert abs(post.p() - np.logaddexp.reduce([sc.p() for _, sc in post.samples])) < 1e-9
+    assert post.p_edge_x(1, 3) > post.p_edge_x(1, 2) > post.p_edge_x(1, 0)
