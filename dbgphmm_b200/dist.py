@@ -33,3 +33,21 @@ def allreduce_results(node_freqs, logp_sum, dist=None, device=None):
     if is_np:
         return f_out.cpu().numpy(), l_out.cpu().numpy()
     return f_out, l_out
+
+
+def full_prob_reads_sharded(model, seqs, mappings, dist=None, use_max_ratio=True, device=None, make_reads=None):
+    """ln P(R|X) for every candidate X of `model` (PHMMModel.to_full_prob_reads, freq.rs:175-192) with the reads sharded over the
+    ranks: each rank scores its contiguous shard (with the shard's own mappings) against all candidates, then ONE all-reduce of
+    the [n_batch] per-candidate sums.  `seqs`: the full list of reads, the same on every rank; returns the [n_batch] totals,
+    identical on every rank.  `make_reads`: constructor of the read collection (default hmmv2.Reads)."""
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    lo, hi = shard_bounds(len(seqs), rank, world)
+    if make_reads is None:
+        from .hmmv2 import Reads as make_reads
+    if hi > lo:
+        tot = np.asarray(model.to_full_prob_reads(make_reads(seqs[lo:hi]), mappings.slice(lo, hi) if mappings is not None else None, use_max_ratio)[0], np.float64)
+    else:
+        tot = np.zeros(model.n_batch())      # more ranks than reads: an empty shard contributes ln 1 to every candidate
+    _, out = allreduce_results(np.zeros(0), tot, dist, device)
+    return np.asarray(out)

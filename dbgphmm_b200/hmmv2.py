@@ -272,6 +272,14 @@ class Mappings:
         ps = [self.probs[int(self.row_off[i]):int(self.row_off[i + 1])] for i in range(a, b)]
         return Mapping(ns, ps)
 
+    def slice(self, lo, hi):
+        """The Mappings of reads lo .. hi-1 (a shard of the read set keeps its own mappings)."""
+        if not (0 <= lo <= hi <= self.n_reads()):
+            raise DbgphmmError(ERR_INVALID, "mappings slice out of range")
+        r0, r1 = int(self.read_off[lo]), int(self.read_off[hi])
+        e0, e1 = int(self.row_off[r0]), int(self.row_off[r1])
+        return Mappings(self.read_off[lo:hi + 1] - np.uint64(r0), self.row_off[r0:r1 + 1] - np.uint64(e0), self.nodes[e0:e1], self.probs[e0:e1])
+
     @staticmethod
     def from_map_str(text):
         """MultiDbg::from_map_str (multi_dbg/output.rs:589-591)."""

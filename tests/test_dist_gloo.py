@@ -69,3 +69,73 @@ def test_two_rank_allreduce_matches_single_process(tmp_path):
     assert np.array_equal(f0, f1) and np.array_equal(l0, l1)          # every rank ends with the same result
     assert np.allclose(f0, fr, rtol=1e-12, atol=1e-15)
     assert abs(l0[0] - lf.sum()) < 1e-9 * abs(lf.sum())
+
+
+class _OracleCandidates:
+    """stand-in for hmmv2.PHMMModel with several parameter sets: the oracle scores the shard once per candidate"""
+
+    def __init__(self, w, X, par):
+        from oracle import oracle as O
+        self.O, self.sg, self.X = O, w.graph, X
+        li, lt = w.graph.to_probs("normal", X[0])
+        self.m = O.PHMMModel(w.graph.src, w.graph.dst, w.graph.base, li, lt, par)
+
+    def n_batch(self):
+        return len(self.X)
+
+    def to_full_prob_reads(self, reads, mappings, use_max_ratio):
+        O = self.O
+        om = None if mappings is None else O.Mappings(mappings.read_off, mappings.row_off, mappings.nodes, mappings.probs)
+        tot = []
+        for x in self.X:
+            self.m.set_probs(*self.sg.to_probs("normal", x))
+            tot.append(self.m.to_full_prob_reads(O.Reads([reads[r] for r in range(len(reads))]), om, use_max_ratio)[0])
+        return np.array(tot), None
+
+
+def _case_c4():
+    from dbgphmm_b200 import synth
+    from oracle import oracle as O
+    w = synth.make_workload("t", 500, 12, 4, 120, 0.01, ploidy=2, het=0.02, seed=3, n_reads=5)
+    par = O.params_uniform(0.01); par.n_warmup = w.k
+    rng = np.random.default_rng(1)
+    X = np.stack([w.graph.node_copy_num, w.graph.node_copy_num + (rng.random(w.graph.n_nodes) < 0.05)])
+    return w, par, X
+
+
+def _worker_c4(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dbgphmm_b200 import hmmv2 as H
+    from dbgphmm_b200.dist import full_prob_reads_sharded
+    from oracle import oracle as O
+    w, par, X = _case_c4()
+    model = _OracleCandidates(w, X, par)
+    om = model.m.generate_mappings(O.Reads(w.reads), None, False)
+    maps = H.Mappings(om.read_off, om.row_off, om.nodes, om.probs)          # (host-only handle: no GPU needed)
+    with_maps = full_prob_reads_sharded(model, w.reads, maps, dist)
+    # more ranks than reads: the last rank's shard is empty
+    few = full_prob_reads_sharded(model, w.reads[:2], None, dist, use_max_ratio=False)
+    np.save(os.path.join(out_dir, f"m{rank}.npy"), with_maps); np.save(os.path.join(out_dir, f"e{rank}.npy"), few)
+    dist.destroy_process_group()
+
+
+def test_three_rank_sharded_full_prob_reads_over_candidates(tmp_path):
+    """Batched P(R|X) (BASELINE configs[3]) with the reads sharded over ranks, mappings travelling with their reads, one all-reduce
+    of the per-candidate sums; world_size 3 so that 2 reads leave one rank without work."""
+    world = 3
+    mp.spawn(_worker_c4, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, ROOT)
+    from dbgphmm_b200 import hmmv2 as H
+    from oracle import oracle as O
+    w, par, X = _case_c4()
+    model = _OracleCandidates(w, X, par)
+    om = model.m.generate_mappings(O.Reads(w.reads), None, False)
+    maps = H.Mappings(om.read_off, om.row_off, om.nodes, om.probs)
+    want_m = model.to_full_prob_reads(H.Reads(w.reads), maps, True)[0]
+    want_e = model.to_full_prob_reads(H.Reads(w.reads[:2]), None, False)[0]
+    for r in range(world):
+        assert np.allclose(np.load(tmp_path / f"m{r}.npy"), want_m, rtol=1e-12, atol=0)
+        assert np.allclose(np.load(tmp_path / f"e{r}.npy"), want_e, rtol=1e-12, atol=0)
+    assert want_m[0] != want_m[1]
