@@ -3,6 +3,7 @@
 // panics this throws dbgphmm::Error.  The reference is compiled Rust and no Rust toolchain exists in this image, so this
 // is the compiled-language host layer (see INTEGRATION.md for the Rust shim a maintainer would add).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -310,6 +311,52 @@ struct Score {
     double p() const { return likelihood + prior + n_euler_circuits; }   // P(R|X) P(G) #circuits
 };
 
+// Prob + Prob (prob.rs:181-197)
+inline double prob_add(double a, double b) {
+    const double x = a >= b ? a : b, y = a >= b ? b : a;
+    if (y == -INFINITY) return x;
+    if (x == y) return x + 0.693147180559945309417232121458;
+    return x + std::log1p(std::exp(y - x));
+}
+
+// PosteriorSample / Posterior (multi_dbg/posterior.rs:42-161): the distinct copy-number vectors seen so far with their scores
+struct PosteriorSample {
+    std::vector<uint32_t> copy_nums;
+    Score score;
+};
+class Posterior {
+public:
+    bool contains(const std::vector<uint32_t>& copy_nums) const { return find(copy_nums) != nullptr; }
+    const PosteriorSample* find(const std::vector<uint32_t>& copy_nums) const {
+        for (auto& s : samples_) if (s.copy_nums == copy_nums) return &s;
+        return nullptr;
+    }
+    void add(const PosteriorSample& sample) {                          // posterior.rs:93-98: a vector counts once
+        if (!contains(sample.copy_nums)) { p_ = prob_add(p_, sample.score.p()); samples_.push_back(sample); }
+    }
+    const PosteriorSample& max_sample() const {                        // posterior.rs:113-118 (max_by_key: the last of equal maxima)
+        if (samples_.empty()) throw Error(DBGPHMM_ERR_INVALID);
+        size_t best = 0;
+        for (size_t i = 1; i < samples_.size(); i++) if (samples_[i].score.p() >= samples_[best].score.p()) best = i;
+        return samples_[best];
+    }
+    const std::vector<uint32_t>& max_copy_nums() const { return max_sample().copy_nums; }
+    const std::vector<PosteriorSample>& samples() const { return samples_; }
+    double p() const { return p_; }                                    // ln of the normalisation factor
+    double p_edge_x(size_t edge, uint32_t x) const {                   // ln P(X[edge] = x | R), posterior.rs:141-159 over hist.rs:48-71
+        double z = -INFINITY, px = -INFINITY;
+        for (auto& s : samples_) {
+            const double w = s.score.p() - p_;
+            z = prob_add(z, w);
+            if (s.copy_nums.at(edge) == x) px = prob_add(px, w);
+        }
+        return px == -INFINITY ? -INFINITY : px - z;
+    }
+private:
+    std::vector<PosteriorSample> samples_;
+    double p_ = -INFINITY;
+};
+
 // The part of MultiDbg a DBG file carries (multi_dbg.rs:170-186, multi_dbg/output.rs:155-345); host only.
 class MultiDbg {
 public:
@@ -388,6 +435,54 @@ public:
             check(dbgphmm_prior_normal((double)gs[b], genome_size_expected, genome_size_sigma, &out[b].prior));
         }
         return out;
+    }
+    // MultiDbg::sample_posterior_once (posterior.rs:470-600), single-move form: every neighbour the posterior has not seen yet is
+    // scored in ONE batched to_scores (the reference clones the graph per neighbour under rayon); returns true and the best sample if
+    // it is not the current copy-number vector.  `neighbors`: copy-number vectors over compact edges (the neighbour search of
+    // neighbors.rs is not part of this library).
+    bool sample_posterior_once(PHMMModel& phmm, const Reads& reads, const Mappings* mappings, const std::vector<std::vector<uint32_t>>& neighbors,
+                               Posterior& posterior, uint32_t genome_size_expected, uint32_t genome_size_sigma, PosteriorSample* best, int mode = 0) const {
+        std::vector<std::vector<uint32_t>> todo;
+        for (auto& c : neighbors) {
+            if (c.size() != sz_[4]) throw Error(DBGPHMM_ERR_INVALID);
+            bool dup = posterior.contains(c);
+            for (auto& t : todo) dup = dup || t == c;
+            if (!dup) todo.push_back(c);
+        }
+        if (!todo.empty()) {
+            std::vector<uint32_t> flat;
+            for (auto& c : todo) flat.insert(flat.end(), c.begin(), c.end());
+            const std::vector<Score> sc = to_scores(phmm, reads, mappings, (uint32_t)todo.size(), flat, genome_size_expected, genome_size_sigma, mode);
+            for (size_t i = 0; i < todo.size(); i++) posterior.add(PosteriorSample{todo[i], sc[i]});
+        }
+        const PosteriorSample& top = posterior.max_sample();
+        if (top.copy_nums == get_copy_nums()) return false;
+        if (best) *best = top;
+        return true;
+    }
+    // The greedy search of MultiDbg::sample_posterior (posterior.rs:314-420): from the current copy numbers, score the neighbours, move
+    // to the best one, stop at a local optimum or after max_iter moves.  neighbors_fn(const MultiDbg&) returns the candidate sets to
+    // try in order (std::vector<std::vector<std::vector<uint32_t>>>) for the copy numbers the graph it is given holds.
+    template <class NeighborsFn>
+    Posterior sample_posterior(PHMMModel& phmm, const Reads& reads, const Mappings* mappings, uint32_t genome_size_expected,
+                               uint32_t genome_size_sigma, NeighborsFn neighbors_fn, size_t max_iter, int mode = 0) const {
+        Posterior post;
+        std::unique_ptr<MultiDbg> dbg = from_dbg_str(to_dbg_string());
+        std::vector<uint32_t> copy_nums = dbg->get_copy_nums();
+        post.add(PosteriorSample{copy_nums, dbg->to_scores(phmm, reads, mappings, 1, copy_nums, genome_size_expected, genome_size_sigma, mode)[0]});
+        for (size_t n_iter = 0; n_iter < max_iter;) {
+            dbg->set_copy_nums(copy_nums);
+            bool moved = false;
+            for (auto& cand : neighbors_fn(*dbg)) {
+                PosteriorSample best;
+                if (dbg->sample_posterior_once(phmm, reads, mappings, cand, post, genome_size_expected, genome_size_sigma, &best, mode)) {
+                    copy_nums = best.copy_nums; n_iter++; moved = true;
+                    break;
+                }
+            }
+            if (!moved) break;   // local optimum
+        }
+        return post;
     }
     // MultiDbg::to_phmm / to_non_zero_phmm / to_uniform_phmm (multi_dbg.rs:1391-1409; n_warmup := k)
     std::unique_ptr<PHMMModel> to_phmm(const PHMMParams& param, int device = 0) const { return std::make_unique<PHMMModel>(to_phmm_handle(param, 0, device), sz_[5]); }
