@@ -143,3 +143,22 @@ def test_mappings_create_rejects_malformed_csr(lib):
     h = C.c_void_p()
     st = lib.dbgphmm_mappings_create(1, ro(0, 2).ctypes.data_as(C.c_void_p), ro(0, 2, 3).ctypes.data_as(C.c_void_p), None, None, C.byref(h))
     assert st == H.ERR_INVALID and b"nodes is null" in lib.dbgphmm_last_error()
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as pedantic C99 and a C program links against the library (what cgo / JNI /
+    a Rust `extern "C"` block would bind)."""
+    import subprocess
+    B.build()
+    src = tmp_path / "c.c"
+    src.write_text('#include <stdio.h>\n#include "dbgphmm_b200.h"\n'
+                   'int main(void) { dbgphmm_params p; dbgphmm_params_uniform(0.01, &p); double lp = 1.0;\n'
+                   '  if (dbgphmm_prior_normal(30.0, 28.0, 5.0, &lp) != DBGPHMM_OK || !(lp < 0.0)) return 1;\n'
+                   '  printf("%u %d\\n", p.n_active_nodes, dbgphmm_device_count() >= 0); return p.n_max_gaps == 4 ? 0 : 2; }\n')
+    libdir = os.path.join(ROOT, "dbgphmm_b200", "lib")
+    env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+    exe = tmp_path / "c"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L", libdir, "-ldbgphmm_b200", f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-lcudart", "-o", str(exe)], env=env)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.split()[0] == "40", (out.returncode, out.stdout, out.stderr)
