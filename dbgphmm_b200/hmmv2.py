@@ -336,6 +336,19 @@ class Row:
     """One PHMMTable (table.rs:42-73), natural logs."""
     __slots__ = ("is_dense", "ids", "m", "i", "ids_d", "d", "mb", "ib", "e")
 
+    def n_active_nodes(self):
+        """table.rs:108-110: entries of m (all N for a dense row)."""
+        return len(self.m)
+
+    def diff(self, other, n_nodes):
+        return table_diff(self, other, n_nodes)
+
+    def log_diff(self, other, n_nodes):
+        return table_log_diff(self, other, n_nodes)
+
+    def to_nodevec(self, n_nodes):
+        return self.merged(n_nodes)
+
     def merged(self, n_nodes):
         """PHMMTable::to_nodevec (table.rs:199-211) as a dense ln array (absent = -inf)."""
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -345,6 +358,45 @@ class Row:
             v[self.ids] = np.logaddexp(self.m, self.i)
             v[self.ids_d] = np.logaddexp(v[self.ids_d], self.d)
         return v
+
+
+def table_diff(a, b, n_nodes):
+    """PHMMTable::diff (table.rs:187-195): sum of |p_a - p_b| over the M / I / D states of every node and mb, ib, e -- the measure
+    the reference's own dense-vs-sparse tests use (forward.rs:621-638, tests/hmm.rs:122-214).  a, b: rows with is_dense / ids / m ..."""
+    tot = 0.0
+    with np.errstate(over="ignore"):
+        for x, y in zip(_dense_states(a, n_nodes), _dense_states(b, n_nodes)):
+            tot += float(np.abs(np.exp(x) - np.exp(y)).sum())
+        for name in ("mb", "ib", "e"):
+            tot += abs(float(np.exp(getattr(a, name))) - float(np.exp(getattr(b, name))))
+    return tot
+
+
+def table_log_diff(a, b, n_nodes):
+    """PHMMTable::log_diff (table.rs:174-182) over Prob::log_diff (prob.rs:110-124): sum of |ln p_a - ln p_b|; two zeros differ by 0,
+    a zero and a non-zero by +inf."""
+    def ld(x, y):
+        x = np.atleast_1d(np.asarray(x, np.float64)); y = np.atleast_1d(np.asarray(y, np.float64))
+        zx, zy = np.isneginf(x), np.isneginf(y)
+        with np.errstate(invalid="ignore"):
+            d = np.where(zx & zy, 0.0, np.where(zx | zy, np.inf, np.abs(x - y)))
+        return float(d.sum())
+    tot = sum(ld(x, y) for x, y in zip(_dense_states(a, n_nodes), _dense_states(b, n_nodes)))
+    return tot + sum(ld(getattr(a, name), getattr(b, name)) for name in ("mb", "ib", "e"))
+
+
+class QScore:
+    """QScore (hmmv2/q.rs:14-52): the three terms q_score_exact returns."""
+    __slots__ = ("init", "trans", "prior")
+
+    def __init__(self, init, trans, prior):
+        self.init, self.trans, self.prior = init, trans, prior
+
+    def total(self):
+        return self.init + self.trans + self.prior
+
+    def sub(self, other):
+        return QScore(self.init - other.init, self.trans - other.trans, self.prior - other.prior)
 
 
 class PHMMTables:
@@ -392,6 +444,31 @@ class PHMMTables:
         out = np.empty(MAX_ACTIVE_NODES, np.uint32); n = C.c_uint32()
         _check(lib().dbgphmm_tables_row_top_nodes(self._h, i, 0, k, 0.0, _p(out), C.byref(n)))
         return out[:n.value].copy()
+
+    def table(self, i):
+        return self.row(i)
+
+    def first_table(self):
+        return self.row(0)
+
+    def last_table(self):
+        return self.row(len(self) - 1)
+
+    def filled_nodes(self, i):
+        """PHMMTable::filled_nodes (table.rs:117-123): None for a dense row, else the top-|m entries| of the merged row."""
+        info = np.zeros(3, np.uint64); sc = np.zeros(3, np.float64)
+        _check(lib().dbgphmm_tables_row_info(self._h, i, _p(info), _p(sc)))
+        return None if info[0] else self.top_nodes(i, int(info[1]))
+
+    def top_nodes_with_prob(self, i, k):
+        """table.rs:153-159: [(node, ln merged prob)] of the top k nodes of row i."""
+        v = self.row(i).merged(self.n_nodes)
+        return [(int(n), float(v[n])) for n in self.top_nodes(i, k)]
+
+    def top_nodes_with_prob_by_score_ratio(self, i, ratio):
+        """table.rs:163-169."""
+        v = self.row(i).merged(self.n_nodes)
+        return [(int(n), float(v[n])) for n in self.top_nodes_by_score_ratio(i, ratio)]
 
     def top_nodes_by_score_ratio(self, i, ratio):
         out = np.empty(MAX_ACTIVE_NODES, np.uint32); n = C.c_uint32()

@@ -115,3 +115,30 @@ def test_emit_probs_of_an_impossible_read_fail_like_the_reference():
     assert np.isneginf(f.full_prob())
     with pytest.raises(H.DbgphmmError):
         H.emit_probs(f, b, 1)
+
+
+def test_table_diff_and_log_diff_like_the_reference_tests(case):
+    """PHMMTable::diff / log_diff (table.rs:174-195) as the reference's own tests use them: dense vs sparse rows are identical inside
+    the warm-up (`diff == 0.0`, tests/hmm.rs:155-173) and close after it (forward.rs:621-638 asserts < 1e-9 on its linear mock)."""
+    w, o = case
+    x = w.reads[2]
+    N = o.n_nodes
+    dense, sparse = o.forward(x), o.forward_sparse(x, False)
+    for r in range(len(dense)):
+        a, b = dense.row(r), sparse.row(r)
+        d = H.table_diff(a, b, N)
+        if b.is_dense:
+            assert d == 0.0 and H.table_log_diff(a, b, N) == 0.0
+        else:
+            assert d < 1e-6 and np.isinf(H.table_log_diff(a, b, N))      # absent sparse entries are zeros: ln-diff is infinite
+    assert not sparse.row(len(dense) - 1).is_dense
+    # hand-made rows: |p_a - p_b| summed over states and the three scalars
+    a, b = H.Row(), H.Row()
+    a.is_dense = b.is_dense = False
+    a.ids = np.array([1, 3], np.uint32); a.m = np.log([0.5, 0.25]); a.i = np.log([0.125, 1e-300]); a.ids_d = np.array([3], np.uint32); a.d = np.log([0.0625])
+    b.ids = np.array([3], np.uint32); b.m = np.log([0.25]); b.i = np.array([-np.inf]); b.ids_d = np.zeros(0, np.uint32); b.d = np.zeros(0)
+    a.mb, a.ib, a.e = np.log(0.5), -np.inf, np.log(0.1); b.mb, b.ib, b.e = np.log(0.25), -np.inf, np.log(0.1)
+    assert abs(a.diff(b, 5) - (0.5 + 0.125 + 1e-300 + 0.0625 + 0.25)) < 1e-15
+    assert np.isinf(a.log_diff(b, 5)) and a.log_diff(a, 5) == 0.0 and a.n_active_nodes() == 2
+    q = H.QScore(-1.0, -2.0, 0.0).sub(H.QScore(-0.5, -1.0, 0.0))
+    assert (q.init, q.trans, q.total()) == (-0.5, -1.0, -1.5)
