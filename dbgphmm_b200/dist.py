@@ -51,3 +51,20 @@ def full_prob_reads_sharded(model, seqs, mappings, dist=None, use_max_ratio=True
         tot = np.zeros(model.n_batch())      # more ranks than reads: an empty shard contributes ln 1 to every candidate
     _, out = allreduce_results(np.zeros(0), tot, dist, device)
     return np.asarray(out)
+
+
+def full_prob_candidates_sharded(model, full_copy_nums, reads, mappings, dist=None, use_max_ratio=True, mode="normal", device=None):
+    """The fallback of SURVEY.md 8e for fewer reads than GPUs: shard the CANDIDATES instead.  Every rank derives (init, trans) for
+    its contiguous slice of `full_copy_nums` [B][n_nodes] (PHMMModel.set_copy_nums_batch), scores ALL reads against it and writes
+    its slice of a zeroed [B] vector; ONE all-reduce (a sum with disjoint supports) assembles ln P(R|X) for every candidate on every
+    rank.  `reads` / `mappings`: the whole read set, the same on every rank."""
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    x = np.ascontiguousarray(np.atleast_2d(full_copy_nums), np.uint32)
+    lo, hi = shard_bounds(len(x), rank, world)
+    out = np.zeros(len(x))
+    if hi > lo:
+        model.set_copy_nums_batch(x[lo:hi], mode)
+        out[lo:hi] = np.asarray(model.to_full_prob_reads(reads, mappings, use_max_ratio)[0], np.float64)
+    _, tot = allreduce_results(np.zeros(0), out, dist, device)
+    return np.asarray(tot)

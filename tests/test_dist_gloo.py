@@ -83,6 +83,10 @@ class _OracleCandidates:
     def n_batch(self):
         return len(self.X)
 
+    def set_copy_nums_batch(self, X, mode):
+        assert mode == "normal"
+        self.X = np.asarray(X)
+
     def to_full_prob_reads(self, reads, mappings, use_max_ratio):
         O = self.O
         om = None if mappings is None else O.Mappings(mappings.read_off, mappings.row_off, mappings.nodes, mappings.probs)
@@ -118,6 +122,11 @@ def _worker_c4(rank, world, port, out_dir):
     # more ranks than reads: the last rank's shard is empty
     few = full_prob_reads_sharded(model, w.reads[:2], None, dist, use_max_ratio=False)
     np.save(os.path.join(out_dir, f"m{rank}.npy"), with_maps); np.save(os.path.join(out_dir, f"e{rank}.npy"), few)
+    # the other way round: candidates sharded, every rank scores all reads (4 candidates over 3 ranks: 2 + 1 + 1)
+    from dbgphmm_b200.dist import full_prob_candidates_sharded
+    X4 = np.stack([X[0], X[1], X[0] + 1, X[1] + 1])
+    by_cand = full_prob_candidates_sharded(model, X4, H.Reads(w.reads), maps, dist)
+    np.save(os.path.join(out_dir, f"c{rank}.npy"), by_cand)
     dist.destroy_process_group()
 
 
@@ -139,3 +148,9 @@ def test_three_rank_sharded_full_prob_reads_over_candidates(tmp_path):
         assert np.allclose(np.load(tmp_path / f"m{r}.npy"), want_m, rtol=1e-12, atol=0)
         assert np.allclose(np.load(tmp_path / f"e{r}.npy"), want_e, rtol=1e-12, atol=0)
     assert want_m[0] != want_m[1]
+    X4 = np.stack([X[0], X[1], X[0] + 1, X[1] + 1])
+    model.set_copy_nums_batch(X4, "normal")
+    want_c = model.to_full_prob_reads(H.Reads(w.reads), maps, True)[0]
+    for r in range(world):
+        assert np.allclose(np.load(tmp_path / f"c{r}.npy"), want_c, rtol=1e-12, atol=0)
+    assert len(set(np.round(want_c, 6))) == 4
