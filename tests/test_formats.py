@@ -136,15 +136,6 @@ def test_dbg_file_to_phmm_scores_like_the_hand_built_model():
         o.set_probs(li, lt)
         s, p = o.to_full_prob_reads(O.Reads(reads), None, False)
         assert np.allclose(per[b], p, rtol=1e-9, atol=0)
-    # MultiDbg::to_score of the same candidates in one call (posterior.rs:259-277: to_likelihood uses use_max_ratio = true)
-    scores = d.to_scores(g, H.Reads(reads), None, X, 18, 3)
-    for b in range(3):
-        li, lt = sg.to_probs("normal", d.expand_copy_nums(X[b])[0])
-        o.set_probs(li, lt)
-        s, _ = o.to_full_prob_reads(O.Reads(reads), None, True)
-        assert abs(scores[b].likelihood - s) <= 1e-9 * abs(s)
-        assert scores[b].genome_size == [18, 15, 27][b] and abs(scores[b].n_euler_circuits) < 1e-12
-        assert abs(scores[b].p() - (s - 0.5 * np.log(2 * np.pi * 9.0) - ([18, 15, 27][b] - 18) ** 2 / 18.0)) <= 1e-9 * abs(s)
 
 
 def test_no_cpp_exception_crosses_the_c_abi():
