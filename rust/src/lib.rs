@@ -329,6 +329,83 @@ impl CudaPHMM {
         (q[0], q[1], q[2])
     }
 }
+/// `Score` (multi_dbg/posterior.rs:164-208), natural logs.
+#[derive(Clone, Copy, Debug, PartialEq)]
+pub struct Score { pub likelihood: f64, pub prior: f64, pub genome_size: u64, pub n_euler_circuits: f64 }
+impl Score {
+    /// `P(R|X) P(G) #circuits` (posterior.rs:199-201)
+    pub fn p(&self) -> f64 { self.likelihood + self.prior + self.n_euler_circuits }
+}
+
+/// The part of `MultiDbg` a DBG file carries (multi_dbg.rs:170-186): compact + full graph, copy numbers.  Host only.
+pub struct CudaDbg { h: *mut dbgphmm_dbg, k: usize, n_edges_full: usize, n_edges_compact: usize, n_phmm_edges: usize }
+impl CudaDbg {
+    fn adopt(h: *mut dbgphmm_dbg) -> Self {
+        let mut sz = [0u32; 6];
+        check(unsafe { dbgphmm_dbg_sizes(h, sz.as_mut_ptr()) });
+        CudaDbg { h, k: sz[0] as usize, n_edges_full: sz[2] as usize, n_edges_compact: sz[4] as usize, n_phmm_edges: sz[5] as usize }
+    }
+    /// `MultiDbg::from_dbg_file` (multi_dbg/output.rs:346-357; .dbg, .dbg.gz, .dbz)
+    pub fn from_dbg_file(path: &str) -> Self {
+        let c = std::ffi::CString::new(path).unwrap();
+        let mut h = std::ptr::null_mut();
+        check(unsafe { dbgphmm_dbg_from_file(c.as_ptr(), &mut h) });
+        Self::adopt(h)
+    }
+    pub fn k(&self) -> usize { self.k }
+    pub fn n_edges_full(&self) -> usize { self.n_edges_full }
+    pub fn n_edges_compact(&self) -> usize { self.n_edges_compact }
+    /// `MultiDbg::get_copy_nums` / `set_copy_nums` (multi_dbg.rs:1041-1066; set panics on copy numbers that do not balance)
+    pub fn get_copy_nums(&self) -> Vec<u32> {
+        let mut x = vec![0u32; self.n_edges_compact];
+        check(unsafe { dbgphmm_dbg_get_copy_nums(self.h, x.as_mut_ptr()) });
+        x
+    }
+    pub fn set_copy_nums(&mut self, copy_nums: &[u32]) {
+        assert_eq!(copy_nums.len(), self.n_edges_compact);
+        check(unsafe { dbgphmm_dbg_set_copy_nums(self.h, copy_nums.as_ptr()) });
+    }
+    /// `MultiDbg::genome_size` (multi_dbg.rs:1018-1028)
+    pub fn genome_size(&self) -> u64 {
+        let mut g = 0u64;
+        check(unsafe { dbgphmm_dbg_genome_size(self.h, 1, std::ptr::null(), &mut g) });
+        g
+    }
+    /// `MultiDbg::n_euler_circuits` (multi_dbg.rs:831-837), natural log
+    pub fn n_euler_circuits(&self) -> f64 {
+        let mut v = 0f64;
+        check(unsafe { dbgphmm_dbg_n_euler_circuits(self.h, 1, std::ptr::null(), &mut v) });
+        v
+    }
+    /// `MultiDbg::to_phmm` (multi_dbg.rs:1394-1397; `n_warmup := k`)
+    pub fn to_phmm(&self, param: &dbgphmm_params, device: i32) -> CudaPHMM {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { dbgphmm_dbg_to_model(self.h, param, 0, device, 0, &mut h) });
+        CudaPHMM { h, n_nodes: self.n_edges_full, n_edges: self.n_phmm_edges }
+    }
+    /// `MultiDbg::to_score` (posterior.rs:259-277) for every candidate of `sample_posterior_once` (posterior.rs:504-515) at once:
+    /// `candidates` is `[n_batch][n_edges_compact]`, flattened.  One expansion to k-mer copy numbers, one on-device derivation of
+    /// (init, trans), one batched `to_full_prob_reads` (use_max_ratio = true like `to_likelihood`), then the host-side terms.
+    pub fn to_scores(&self, phmm: &mut CudaPHMM, reads: &CudaReads, mappings: Option<&CudaMappings>, n_batch: usize, candidates: &[u32],
+                     genome_size_expected: u32, genome_size_sigma: u32) -> Vec<Score> {
+        assert_eq!(candidates.len(), n_batch * self.n_edges_compact);
+        let mut full = vec![0u32; n_batch * self.n_edges_full];
+        check(unsafe { dbgphmm_dbg_expand_copy_nums(self.h, n_batch as u32, candidates.as_ptr(), full.as_mut_ptr()) });
+        phmm.set_copy_nums_batch(n_batch, &full, false);
+        let like = phmm.to_full_prob_reads(reads, mappings, true);
+        let (mut gs, mut ne) = (vec![0u64; n_batch], vec![0f64; n_batch]);
+        check(unsafe { dbgphmm_dbg_genome_size(self.h, n_batch as u32, candidates.as_ptr(), gs.as_mut_ptr()) });
+        check(unsafe { dbgphmm_dbg_n_euler_circuits(self.h, n_batch as u32, candidates.as_ptr(), ne.as_mut_ptr()) });
+        (0..n_batch).map(|b| {
+            let mut prior = 0f64;
+            check(unsafe { dbgphmm_prior_normal(gs[b] as f64, genome_size_expected as f64, genome_size_sigma as f64, &mut prior) });
+            Score { likelihood: like[b], prior, genome_size: gs[b], n_euler_circuits: ne[b] }
+        }).collect()
+    }
+}
+impl Drop for CudaDbg { fn drop(&mut self) { unsafe { dbgphmm_dbg_destroy(self.h) } } }
+unsafe impl Send for CudaDbg {}
+
 impl Drop for CudaPHMM { fn drop(&mut self) { unsafe { dbgphmm_model_destroy(self.h) } } }
 // one host thread at a time per handle (header, "Conventions")
 unsafe impl Send for CudaPHMM {}
