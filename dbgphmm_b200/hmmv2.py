@@ -785,27 +785,53 @@ class MultiDbg:
     def clone(self):
         return MultiDbg.from_dbg_str(self.to_dbg_string())
 
-    def sample_posterior_once(self, phmm, reads, mappings, neighbors, posterior, genome_size_expected, genome_size_sigma, mode="normal"):
-        """MultiDbg::sample_posterior_once (posterior.rs:470-600) in its single-move form: score every neighbour the posterior has not
-        seen yet -- all of them in ONE batched to_scores where the reference clones the graph per neighbour under rayon -- add them,
-        and return the best sample (copy_nums tuple, Score) if it is not the current copy-number vector, else None.
-        `neighbors`: copy-number vectors over compact edges, e.g. the output of the reference's neighbour search (not built here)."""
-        todo, seen = [], set()
-        for c in neighbors:
-            key = tuple(int(v) for v in c)
-            if key not in seen and not posterior.contains(key):
-                seen.add(key); todo.append(key)
-        if todo:
-            for key, sc in zip(todo, self.to_scores(phmm, reads, mappings, np.array(todo, np.uint32), genome_size_expected, genome_size_sigma, mode)):
-                posterior.add(key, sc)
+    def sample_posterior_once(self, phmm, reads, mappings, neighbors, posterior, genome_size_expected, genome_size_sigma, mode="normal",
+                              multi_move=False):
+        """MultiDbg::sample_posterior_once (posterior.rs:470-600): score every neighbour the posterior has not seen yet -- all of them
+        in ONE batched to_scores where the reference clones the graph per neighbour under rayon -- add them, and return the best
+        sample (copy_nums tuple, Score) if it is not the current copy-number vector, else None.
+        `neighbors`: copy-number vectors over compact edges, e.g. the output of the reference's neighbour search (not built here).
+        multi_move (posterior.rs:533-588, the mode of rescue-only rounds): the neighbours that improve on the current score are
+        taken best first and accepted while their changes touch disjoint edges (`is_independent_update`, neighbors.rs:493-509; the
+        update cycle of a neighbour is its difference from the current vector); the combined move is scored and added as well."""
+        def score_new(cands):
+            todo, seen = [], set()
+            for c in cands:
+                key = tuple(int(v) for v in c)
+                if key not in seen and not posterior.contains(key):
+                    seen.add(key); todo.append(key)
+            if todo:
+                for key, sc in zip(todo, self.to_scores(phmm, reads, mappings, np.array(todo, np.uint32), genome_size_expected, genome_size_sigma, mode)):
+                    posterior.add(key, sc)
+        score_new(neighbors)
+        current = tuple(int(v) for v in self.get_copy_nums())
+        if multi_move:
+            cur_score = posterior.find(current)
+            if cur_score is None:
+                raise DbgphmmError(ERR_INVALID, "current copy number was not sampled")       # posterior.rs:540 (expect)
+            keys = [tuple(int(v) for v in c) for c in neighbors]
+            # sorted_by_key(score).rev(): descending, later neighbours first among equal scores
+            order = sorted(range(len(keys)), key=lambda i: (posterior.find(keys[i]).p(), i), reverse=True)
+            combined, touched = list(current), set()
+            for i in order:
+                if not posterior.find(keys[i]).p() > cur_score.p():
+                    break                                                                     # neighbours are sorted by score
+                delta = {e: keys[i][e] - current[e] for e in range(len(current)) if keys[i][e] != current[e]}
+                if touched.isdisjoint(delta):
+                    for e, dv in delta.items():
+                        combined[e] += dv
+                    touched.update(delta)
+            score_new([combined])
         best = posterior.max_sample()
-        return best if best[0] != tuple(int(v) for v in self.get_copy_nums()) else None
+        return best if best[0] != current else None
 
-    def sample_posterior(self, phmm, reads, mappings, genome_size_expected, genome_size_sigma, neighbors_fn, max_iter, mode="normal"):
+    def sample_posterior(self, phmm, reads, mappings, genome_size_expected, genome_size_sigma, neighbors_fn, max_iter, mode="normal",
+                         multi_move=False):
         """The greedy search of MultiDbg::sample_posterior (posterior.rs:314-420): start from the current copy numbers, score the
         neighbours, move to the best one, stop at a local optimum or after max_iter moves.  `neighbors_fn(dbg)` returns the candidate
         sets to try in order (the reference tries rescue, partial and full neighbours, posterior.rs:352-372) for the copy numbers `dbg`
-        currently holds.  `self` is left untouched; returns the Posterior."""
+        currently holds; multi_move as in sample_posterior_once (the reference switches it on for rescue-only rounds, posterior.rs:391).
+        `self` is left untouched; returns the Posterior."""
         post = Posterior()
         dbg = self.clone()
         copy_nums = tuple(int(v) for v in dbg.get_copy_nums())
@@ -814,7 +840,7 @@ class MultiDbg:
         while n_iter < max_iter:
             dbg.set_copy_nums(np.array(copy_nums, np.uint32))
             for cand in neighbors_fn(dbg):
-                sample = dbg.sample_posterior_once(phmm, reads, mappings, cand, post, genome_size_expected, genome_size_sigma, mode)
+                sample = dbg.sample_posterior_once(phmm, reads, mappings, cand, post, genome_size_expected, genome_size_sigma, mode, multi_move)
                 if sample is not None:
                     copy_nums = sample[0]
                     n_iter += 1

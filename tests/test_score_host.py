@@ -194,3 +194,81 @@ def test_sample_posterior_greedy_search_over_the_oracle():
         assert abs(sc.likelihood - want) < 1e-12 and sc.genome_size == 9 + 3 * key[1]
     assert abs(post.p() - np.logaddexp.reduce([sc.p() for _, sc in post.samples])) < 1e-9
     assert post.p_edge_x(1, 3) > post.p_edge_x(1, 2) > post.p_edge_x(1, 0)
+
+
+def _dbg_text_of_genome(genome, k):
+    """DBG text (multi_dbg/output.rs:155-199) of one linear genome with n-padded ends: (k-1)-mer nodes, k-mer edges with their
+    multiplicity as copy number, compact edges = maximal simple paths between nodes that branch (or the all-n terminal)."""
+    s = "n" * (k - 1) + genome + "n" * (k - 1)
+    kmers = {}
+    for j in range(len(s) - k + 1):
+        kmers[s[j:j + k]] = kmers.get(s[j:j + k], 0) + 1
+    out_e, in_e = {}, {}
+    for km in kmers:
+        out_e.setdefault(km[:-1], []).append(km); in_e.setdefault(km[1:], []).append(km)
+    nodes = sorted(set(out_e) | set(in_e))
+    is_compact = lambda v: v == "n" * (k - 1) or len(out_e.get(v, [])) != 1 or len(in_e.get(v, [])) != 1
+    cnodes = [v for v in nodes if is_compact(v)]
+    cid = {v: i for i, v in enumerate(cnodes)}
+    full_id = {km: i for i, km in enumerate(sorted(kmers))}
+    lines = [f"K\t{k}"] + [f"N\t{i}\t{v}" for i, v in enumerate(cnodes)]
+    eid = 0
+    for v in cnodes:
+        for km in sorted(out_e.get(v, [])):
+            path, seq, w = [km], km, km[1:]
+            while not is_compact(w):
+                km2 = out_e[w][0]
+                path.append(km2); seq += km2[-1]; w = km2[1:]
+            assert len({kmers[x] for x in path}) == 1
+            lines.append(f"E\t{eid}\t{cid[v]}\t{cid[w]}\t{seq}\t{kmers[km]}\t" + ",".join(str(full_id[x]) for x in path))
+            eid += 1
+    return "\n".join(lines) + "\n"
+
+
+def test_multi_move_accepts_independent_improvements_at_once():
+    """posterior.rs:533-588 (the mode of rescue-only rounds): two tandem repeats, both under-counted; the +1 moves on the two repeat
+    edges both improve the score and touch different edges, so they are accepted together and the combined vector is scored in the
+    same round; a third neighbour that shares an edge with an accepted one is left out.  Likelihoods from the oracle."""
+    from dbgphmm_b200 import graphs
+    from oracle import oracle as O
+    k = 4
+    genome = "TCC" + "CAG" * 3 + "GAATACT" + "TGA" * 3 + "CCGT"
+    d = H.MultiDbg.from_dbg_str(_dbg_text_of_genome(genome, k))
+    src, dst, em, cn, ce = d.phmm_graph()
+    truth = d.get_copy_nums()
+    loops = [e for e in range(d.n_edges_compact) if truth[e] == 2]        # the two self-loop edges CAG -> CAG and TGA -> TGA
+    assert len(loops) == 2 and d.genome_size() == len(genome)
+    op = O.params_uniform(0.01); op.n_warmup = k
+    li, lt = graphs.copy_nums_to_probs(src, dst, em, cn, None, "normal")
+    o = O.PHMMModel(src, dst, em, li, lt, op)
+    reads = O.Reads([genome.encode()] * 5)
+
+    class OracleModel:
+        def set_copy_nums_batch(self, full, mode):
+            self.full, self.mode = full, mode
+
+        def to_full_prob_reads(self, rd, mappings, use_max_ratio):
+            out = []
+            for x in self.full:
+                o.set_probs(*graphs.copy_nums_to_probs(src, dst, em, x, None, self.mode))
+                out.append(o.to_full_prob_reads(rd, mappings, use_max_ratio)[0])
+            return np.array(out), None
+
+    start = truth.copy(); start[loops] = 1
+    d.set_copy_nums(start)
+    up = lambda *es: np.array([start[e] + (1 if e in es else 0) for e in range(len(start))], np.uint32)
+    both_plus_a_again = up(loops[0]); both_plus_a_again[loops[0]] += 1          # +2 on loop A: shares the edge with the +1 move
+    neighbors = [up(loops[0]), up(loops[1]), both_plus_a_again]
+    post = H.Posterior()
+    post.add(start, d.to_scores(OracleModel(), reads, None, [start], len(genome), 3)[0])
+    best = d.sample_posterior_once(OracleModel(), reads, None, neighbors, post, len(genome), 3, multi_move=True)
+    seen = [s[0] for s in post.samples]
+    assert tuple(truth) in seen and len(seen) == 5                             # start, 3 neighbours, the combined move
+    assert best is not None and best[0] == tuple(int(v) for v in truth)        # both repeats fixed in one round
+    # without multi-move the same round only gets as far as the better single move
+    post1 = H.Posterior()
+    post1.add(start, d.to_scores(OracleModel(), reads, None, [start], len(genome), 3)[0])
+    best1 = d.sample_posterior_once(OracleModel(), reads, None, neighbors, post1, len(genome), 3)
+    assert tuple(truth) not in [s[0] for s in post1.samples] and best1[0] in (tuple(up(loops[0])), tuple(up(loops[1])))
+    with pytest.raises(H.DbgphmmError):                                        # "current copy number was not sampled"
+        d.sample_posterior_once(OracleModel(), reads, None, neighbors, H.Posterior(), len(genome), 3, multi_move=True)
