@@ -68,3 +68,19 @@ def full_prob_candidates_sharded(model, full_copy_nums, reads, mappings, dist=No
         out[lo:hi] = np.asarray(model.to_full_prob_reads(reads, mappings, use_max_ratio)[0], np.float64)
     _, tot = allreduce_results(np.zeros(0), out, dist, device)
     return np.asarray(tot)
+
+
+def mappings_to_freqs_sharded(model, seqs, dist=None, use_max_ratio=True, device=None, make_reads=None):
+    """MultiDbg::generate_mappings + mappings_to_freqs (posterior.rs:609-630, draft.rs:201-212) with the reads sharded over the ranks:
+    every rank maps its own shard (the mappings stay with their reads: no collective), and the per-node frequencies
+    `Mappings::to_node_freqs` (hint.rs:161-171) are summed with ONE all-reduce.  Returns (node_freqs [N] identical on every rank,
+    this rank's Mappings, (lo, hi) = the reads they belong to)."""
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    lo, hi = shard_bounds(len(seqs), rank, world)
+    if make_reads is None:
+        from .hmmv2 import Reads as make_reads
+    mine = model.generate_mappings(make_reads(seqs[lo:hi]), None, use_max_ratio) if hi > lo else None
+    f = np.asarray(mine.to_node_freqs(model.n_nodes), np.float64) if mine is not None else np.zeros(model.n_nodes)
+    f_all, _ = allreduce_results(f, np.zeros(1), dist, device)
+    return np.asarray(f_all), mine, (lo, hi)

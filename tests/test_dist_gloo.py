@@ -127,6 +127,12 @@ def _worker_c4(rank, world, port, out_dir):
     X4 = np.stack([X[0], X[1], X[0] + 1, X[1] + 1])
     by_cand = full_prob_candidates_sharded(model, X4, H.Reads(w.reads), maps, dist)
     np.save(os.path.join(out_dir, f"c{rank}.npy"), by_cand)
+    # mapping generation: per-read output stays on its rank, only the [N] node frequencies are summed
+    from dbgphmm_b200.dist import mappings_to_freqs_sharded
+    o2 = O.PHMMModel(w.graph.src, w.graph.dst, w.graph.base, *w.graph.to_probs("uniform"), par)
+    f_all, mine, (lo, hi) = mappings_to_freqs_sharded(o2, w.reads, dist, use_max_ratio=False, make_reads=O.Reads)
+    assert mine.n_reads() == hi - lo
+    np.save(os.path.join(out_dir, f"q{rank}.npy"), f_all)
     dist.destroy_process_group()
 
 
@@ -154,3 +160,8 @@ def test_three_rank_sharded_full_prob_reads_over_candidates(tmp_path):
     for r in range(world):
         assert np.allclose(np.load(tmp_path / f"c{r}.npy"), want_c, rtol=1e-12, atol=0)
     assert len(set(np.round(want_c, 6))) == 4
+    o2 = O.PHMMModel(w.graph.src, w.graph.dst, w.graph.base, *w.graph.to_probs("uniform"), par)
+    want_f = o2.generate_mappings(O.Reads(w.reads), None, False).to_node_freqs(o2.n_nodes)
+    for r in range(world):
+        assert np.allclose(np.load(tmp_path / f"q{r}.npy"), want_f, rtol=1e-12, atol=1e-15)
+    assert abs(want_f.sum() - sum(len(x) for x in w.reads)) < 0.02 * want_f.sum()      # about one node per base (top-n lists drop the tail)
