@@ -69,10 +69,10 @@ def test_cpp_sample_posterior_walks_to_the_true_copy_number(tmp_path):
     assert rc == 0 and "posterior search ok" in out, (rc, out)
 
 
-def test_c3_full_size_properties(monkeypatch):
+@pytest.fixture(scope="module")
+def c3_full():
     """BASELINE.json configs[2] at its FULL size (1 Mbp diploid, 1 % het, k = 40: N = 1.33 M nodes, 10 kbp reads; the graph bench.py
-    measures), a handful of reads: size-independent properties instead of the oracle (one full read costs ~100 CPU-seconds there).
-    The same assertions hold against the oracle at 50 kbp in tests/test_gpu_configs.py::test_c3_scaled_diploid_stream_strategy_properties."""
+    measures) and a handful of reads."""
     from dbgphmm_b200 import synth
     h0 = synth.random_genome(1_000_000, 0)
     h1 = synth.mutate_substitutions(h0, 0.01, 1)
@@ -81,16 +81,16 @@ def test_c3_full_size_properties(monkeypatch):
     assert len(reads) == 6 and sg.n_nodes > 1_300_000
     par = H.params_uniform(0.001); par.n_warmup = 40
     li, lt = sg.to_probs("normal")
-    g = H.PHMMModel(sg.src, sg.dst, sg.base, li, lt, par)
-    res = {}
-    for strat in ("stream", "store"):
-        monkeypatch.setenv("DBGPHMM_STRATEGY", strat)
-        res[strat] = g.run_node_freqs(H.Reads(reads), "sparse")
-    fs, lfs, lbs, cs = res["stream"]
-    ft, lft, lbt, ct = res["store"]
-    # the strategy (which rows are kept, two rows per launch or one) does not change the result
-    assert cs == ct and np.allclose(lfs, lft, rtol=1e-12, atol=0) and np.allclose(lbs, lbt, rtol=1e-12, atol=0)
-    assert np.allclose(fs, ft, rtol=1e-9, atol=1e-12)
+    return sg, reads, H.PHMMModel(sg.src, sg.dst, sg.base, li, lt, par)
+
+
+def test_c3_full_size_properties(c3_full, monkeypatch):
+    """Size-independent properties instead of the oracle (one full read costs ~100 CPU-seconds there), on the path bench.py times
+    (stream strategy).  The same bounds hold against the oracle at 50 kbp in
+    tests/test_gpu_configs.py::test_c3_scaled_diploid_stream_strategy_properties."""
+    sg, reads, g = c3_full
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
+    fs, lfs, lbs, cs = g.run_node_freqs(H.Reads(reads), "sparse")
     # cells: 2 x 40 dense warm-up rows of N nodes per read dominate (SURVEY 8d)
     assert cs[0] > 6 * 40 * sg.n_nodes and cs[1] > 6 * 40 * sg.n_nodes
     n_bases = sum(len(r) for r in reads)
@@ -98,9 +98,22 @@ def test_c3_full_size_properties(monkeypatch):
     assert abs(fs.sum() / n_bases - 1.0) < 5e-3              # every base is emitted by exactly one Match / Ins state (+ ~0.1 % silent Del mass)
     assert np.allclose(lfs, lbs, rtol=1e-3)                  # forward and backward totals differ only by the bounded Del chain
     # reads are independent: a batch is the sum of its parts, whatever the batching
-    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
     fa, lfa, _, _ = g.run_node_freqs(H.Reads(reads[:2]), "sparse")
     fb, lfb, _, _ = g.run_node_freqs(H.Reads(reads[2:]), "sparse")
     assert np.allclose(fa + fb, fs, rtol=1e-9, atol=1e-12) and np.allclose(np.concatenate([lfa, lfb]), lfs, rtol=1e-12, atol=0)
     # the expected frequencies follow the reads: the nodes a read passes through carry it
     assert (fs > 0.5).sum() > 0.9 * n_bases / 2 and fs.max() < len(reads) + 0.5
+
+
+def test_c3_full_size_strategy_independence(c3_full, monkeypatch):
+    """Which rows are kept (store: every dense row of the batch, single-row kernels; stream: two ping-pong slabs per read, two rows
+    per launch, products by cone recompute) does not change the result -- at full size."""
+    sg, reads, g = c3_full
+    res = {}
+    for strat in ("stream", "store"):
+        monkeypatch.setenv("DBGPHMM_STRATEGY", strat)
+        res[strat] = g.run_node_freqs(H.Reads(reads[:3]), "sparse")
+    fs, lfs, lbs, cs = res["stream"]
+    ft, lft, lbt, ct = res["store"]
+    assert cs == ct and np.allclose(lfs, lft, rtol=1e-12, atol=0) and np.allclose(lbs, lbt, rtol=1e-12, atol=0)
+    assert np.allclose(fs, ft, rtol=1e-9, atol=1e-12)
