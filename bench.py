@@ -40,6 +40,10 @@ def parse():
     ap.add_argument("--cpu-read-len", type=int, default=8, help="bases kept per read in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end passes (profiling runs under ncu only; the line then has e2e.value = null)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling passes over the 4,000-read C3 dataset")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra workload lines (C4 batched P(R|X)); they only run at N = 1")
+    ap.add_argument("--coverage", type=float, default=20.0, help="read coverage of the strong-scaling dataset (C3: 20x)")
+    ap.add_argument("--cpu-full-reads", type=int, default=0, help="full-length reads added to the CPU baseline sample (~3 CPU-minutes each at C3)")
     return ap.parse_args()
 
 
@@ -100,37 +104,100 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(args, g, li, lt, reads, n_sample):
-    """The reference's CPU algorithm (oracle port, OpenMP over reads like rayon over reads, freq.rs:181-191) on a sample."""
+def host_cores():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm asks OpenMP for an explicit
+    thread count (num_threads clause), so that variable does not apply to it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference(args, g, li, lt, reads, n_sample, gpu_cells_per_step=None):
+    """The reference's CPU algorithm (oracle port, OpenMP over reads like rayon over reads, freq.rs:181-191) on a bounded sample."""
     from oracle import oracle as O
     par = O.params_uniform(0.001)
     par.n_warmup = args.k
     o = O.PHMMModel(g.src, g.dst, g.base, li, lt, par)
-    threads = min(O.max_threads(), n_sample)
-    # Bounded sample: one full 10 kbp read costs ~100 CPU-seconds at N = 1.3 M, so the sample keeps the first
-    # `cpu_read_len` bases of each read.  Every row is then a dense warm-up row (len < n_warmup), i.e. the row type that
-    # makes up > 98 % of the cells of the full workload, at the same N; GCUPS is per cell, so the rate is comparable.
+    threads = min(host_cores(), n_sample)
+    # Bounded sample.  One dense warm-up row of one read costs 2.2 CPU-seconds at N = 1.33 M (one core), a full 10 kbp read has 80 of
+    # them (forward + backward) = ~3 CPU-minutes, so a full-length read does not fit a step of a 25-step run: the sample keeps the
+    # first `cpu_read_len` bases of each read.  Every sampled row is a dense warm-up row (len < n_warmup) at the full N -- the row
+    # type that holds > 99 % of the workload's cells; GCUPS is per cell, so the rate carries over.  (`--cpu-full-reads K` adds K
+    # full-length reads; profiles/ holds one such run.)
     sample = [r[:args.cpu_read_len] for r in reads[:n_sample]]
-    cells = sum(len(r) for r in sample) * 2 * g.n_nodes
+    n_full = min(args.cpu_full_reads, len(reads))
+    sample += [r for r in reads[:n_full]]
+    dense_cells = sum(min(len(r), args.k) for r in sample) * 2 * g.n_nodes
     t0 = time.perf_counter()
     fr, lf, lb = o.run_node_freqs(O.Reads(sample), "sparse", True, None, n_threads=threads, want_freqs=True)
     dt = time.perf_counter() - t0
-    # sparse cells of the same sample (cheap second pass is avoided: count from the GPU-side accounting when available)
-    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
-            "sample": f"{len(sample)} reads of the same workload cut to their first {args.cpu_read_len} bases "
-                      f"(all rows dense warm-up rows over N={g.n_nodes} nodes; run_sparse + to_node_freqs)",
-            "seconds": dt, "logp_fwd": lf.tolist()}
+    cells = dense_cells   # (+ ~50 cells per sparse row of the full-length reads: < 1 %, not counted)
+    out = {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+           "sample": f"{n_sample} reads of the same workload cut to their first {args.cpu_read_len} bases"
+                     + (f" + {n_full} full-length reads" if n_full else "")
+                     + f" (dense warm-up rows over N={g.n_nodes} nodes, forward + backward + node freqs; OpenMP over reads)",
+           "sample_reads": len(sample), "sample_bases_per_read": args.cpu_read_len, "full_length_reads": n_full,
+           "rows_covered": "dense warm-up rows only" if not n_full else "dense warm-up rows + the sparse rows of the full-length reads",
+           "cells_per_s_per_core": cells / dt / threads,
+           "reference_hint_cells_per_s_per_core": 3.8e6,
+           "hint_source": "src/hmmv2/speed.rs:307-310 (dense forward on an Apple M1, the only in-tree figure); this port does log-space f64 with fresh rows per step like the reference",
+           "seconds": dt, "logp_fwd": lf.tolist()}
+    if gpu_cells_per_step:
+        out["sample_fraction"] = cells / gpu_cells_per_step
+    return out
 
 
 def auto_cpu_sample(n_nodes, k):
-    from oracle import oracle as O
-    cores = O.max_threads()
+    cores = host_cores()
     try:
         avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
     except Exception:
         avail = 32 << 30
     per_read = 2 * 16 * n_nodes * 24 * 2.5  # stored dense rows of both directions + temporaries
     return int(max(1, min(cores, avail * 0.5 / per_read)))
+
+
+def workload_text(args):
+    return f"{workload_tag(args)}: {args.genome_len} bp diploid 1% het, {args.read_len} bp HiFi reads p=0.001, k={args.k}, run_sparse + node freqs"
+
+
+def extra_c4(H, local, n_candidates=64, n_reads=200):
+    """BASELINE configs[3] (C4): batched P(R|X) with mappings over candidate copy numbers, through dbgphmm_to_full_prob_reads with
+    HOST buffers (posterior.rs:504-515 over freq.rs:175-192): reads x candidates / s."""
+    from dbgphmm_b200 import graphs, synth
+    hap = synth.tandem_repeat_genome(10_000, 16, 20_000, seed=3, divergence=0.005)
+    hap2 = synth.mutate_substitutions(hap, 0.002, 77)
+    sg, _ = graphs.build_dbg([hap.tobytes(), hap2.tobytes()], 40, seed=9)
+    reads = synth.sample_reads([hap, hap2], 20, 10_000, 0.001, 13)[:n_reads]
+    par = H.params_uniform(0.001); par.n_warmup = 40
+    li, lt = sg.to_probs("non_zero")
+    m = H.PHMMModel(sg.src, sg.dst, sg.base, li, lt, par, device=local)
+    rd = H.Reads(reads)
+    t0 = time.perf_counter()
+    maps = m.generate_mappings(rd, None, False)
+    t_map = time.perf_counter() - t0
+    rng = np.random.default_rng(1)
+    cn = sg.node_copy_num
+    X = np.repeat(cn[None, :], n_candidates, 0).astype(np.uint32)
+    rep = np.where(cn >= 2)[0]
+    for b in range(1, n_candidates):
+        idx = rng.choice(rep, size=min(40, len(rep)), replace=False)
+        X[b, idx] = np.maximum(1, X[b, idx].astype(np.int64) + rng.choice([-1, 1], size=len(idx))).astype(np.uint32)
+    m.set_copy_nums_batch(X, "non_zero")
+    m.to_full_prob_reads(rd, maps)   # warm-up
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r2 = H.Reads(reads)             # host buffers in: the read set is validated and copied inside the timed region
+        tot, per = m.to_full_prob_reads(r2, maps)
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts))
+    cells = float(len(maps.nodes)) * n_candidates
+    return {"workload": "C4: 200 kbp tandem-repeat region (16 x 10 kbp units), 10 kbp reads, to_full_prob_reads with mappings batched over candidates",
+            "n_nodes": int(sg.n_nodes), "reads": len(reads), "candidates": n_candidates, "value": len(reads) * n_candidates / dt, "unit": "reads x candidates / s",
+            "ms_per_call": dt * 1e3, "gcups": cells / dt / 1e9, "generate_mappings_s": t_map, "host_buffers": True,
+            "best_candidate": int(np.argmax(tot))}
 
 
 def main():
@@ -147,20 +214,21 @@ def main():
             if s >= args.warmup:
                 vals.append(r)
         v = float(np.mean([r["value"] for r in vals])); sec = float(np.mean([r["seconds"] for r in vals]))
-        cb = {k: vals[-1][k] for k in ("unit", "cores", "kind", "sample")}
+        cb = {k: val for k, val in vals[-1].items() if k not in ("seconds", "logp_fwd", "value")}
         cb["value"] = v
         print(json.dumps({"metric": "PHMM forward-backward GCUPS", "value": v, "unit": "GCUPS", "impl": "reference", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": f"{workload_tag(args)}: {args.genome_len} bp diploid 1% het, {args.read_len} bp HiFi reads p=0.001, k={args.k}, run_sparse + node freqs",
-                                     "n_nodes": int(g.n_nodes), "reads_per_step": n_sample},
+                          "config": {"workload": workload_text(args), "n_nodes": int(g.n_nodes), "reads_per_step": n_sample,
+                                     "same_config_note": "same graph, parameters, metric and cell definition as the GPU arm; each step is a bounded sample of "
+                                                         "the GPU arm's step (see cpu_baseline.sample) because one full step costs ~60 CPU-hours"},
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
     import torch
     import torch.distributed as dist
     from dbgphmm_b200 import hmmv2 as H
-    from dbgphmm_b200.dist import allreduce_results
+    from dbgphmm_b200 import dist as D
     for attempt in range(5):   # a context of a process that has just exited may still be tearing down (exclusive-process boxes)
         try:
             torch.cuda.set_device(local)
@@ -178,70 +246,110 @@ def main():
     par.n_warmup = args.k  # MultiDbg::to_phmm (multi_dbg.rs:1395)
     model = H.PHMMModel(g.src, g.dst, g.base, li, lt, par, device=local)
     N = g.n_nodes
-    freqs = torch.zeros(N, dtype=torch.float64, device="cuda")
-    logp = torch.zeros(1, dtype=torch.float64, device="cuda")
-    lp_dev = torch.zeros(R, dtype=torch.float64, device="cuda")
-    rd = H.Reads(reads)
-    model.reads_to_device(rd)
-    h2d = int(rd.total_bases() + rd.offsets.nbytes); d2h = int(N * 8 + 2 * R * 8)
+    # ONE device buffer holds what the ranks exchange: [N] node frequencies + the summed ln P(R).  The library accumulates into it,
+    # the all-reduce runs on it in place (no concatenation, no copy).
+    buf, freqs, logp = D.packed_buffer(N, 1, "cuda")
+    verbose = bool(os.environ.get("BENCH_VERBOSE"))
+
+    def note(msg):
+        if verbose:
+            sys.stderr.write(f"[bench rank {rank}] {msg}\n"); sys.stderr.flush()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        """inputs resident in HBM; device outputs; one all-reduce of node freqs + summed ln P."""
-        freqs.zero_()
-        cells = model.run_node_freqs_dev(rd, "sparse", freqs.data_ptr(), logp_fwd_ptr=lp_dev.data_ptr())
+    def step_resident(rd, lp_dev):
+        """inputs resident in HBM; device outputs; one in-place all-reduce of node freqs + summed ln P."""
+        buf.zero_()
+        torch.cuda.current_stream().synchronize()   # the library runs on its own stream: order the zeroing before it
+        cells = model.run_node_freqs_dev(rd, "sparse", freqs.data_ptr(), logp_fwd_ptr=lp_dev.data_ptr())   # returns after its stream has drained
         logp[0] = lp_dev.sum()
-        ms = H.last_timing()[3]
-        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        allreduce_results(freqs, logp, dist if world > 1 else None)   # one NCCL all-reduce of [N] freqs + summed ln P
-        ev1.record(); torch.cuda.synchronize()
-        return sum(cells), ms + ev0.elapsed_time(ev1)
+        D.allreduce_results(freqs, logp, dist if world > 1 else None)   # adjacent views of `buf`: one in-place NCCL all-reduce
+        return sum(cells)
 
+    def timed(rd, lp_dev, n_warm, n_steps, tag):
+        """n_steps passes bracketed by barrier + synchronize, timed with CUDA events around the whole bracket; max over ranks."""
+        for i in range(n_warm):
+            note(f"{tag} warmup {i}")
+            step_resident(rd, lp_dev)
+        barrier()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        H.launch_count(reset=True)
+        ev0.record()
+        cells, lib_ms, k = 0, 0.0, [0.0, 0, 0]
+        for i in range(n_steps):
+            note(f"{tag} step {i}")
+            cells += step_resident(rd, lp_dev)
+            lib_ms += H.last_timing()[3]
+            a, b, c = H.last_dense_kernel(); k[0] += a; k[1] += b; k[2] += c
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms, lib_ms], dtype=torch.float64, device="cuda"); c = torch.tensor([float(cells)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c)
+        return float(c.item()), float(t[0].item()), float(t[1].item()), k, H.launch_count()
+
+    # ---- weak scaling (the headline): every rank processes its own R reads
+    rd = H.Reads(reads)
+    model.reads_to_device(rd)
+    lp_dev = torch.zeros(R, dtype=torch.float64, device="cuda")
+    h2d = int(rd.total_bases() + rd.offsets.nbytes); d2h = int(N * 8 + 2 * R * 8)
+    for i in range(args.warmup):
+        note(f"warmup {i}")
+        step_resident(rd, lp_dev)
+    sampler = ClockSampler(local); sampler.start()
+    tot_cells, tot_ms, lib_ms, (k_ms, k_launch, k_cells), launches = timed(rd, lp_dev, 0, args.steps, "weak")
+    clocks = sampler.stop()
+    ms_step = tot_ms / args.steps
+    value = tot_cells / (tot_ms * 1e-3) / 1e9
+    sum_logp = float(logp.item()); sum_freq = float(freqs.sum().item())
+
+    # ---- strong scaling: the C3 dataset itself (2 Mbp of haplotypes x 20 / 10 kbp = 4,000 reads) sharded over the ranks
+    strong = None
+    if not args.no_strong:
+        from dbgphmm_b200 import synth
+        h0 = synth.random_genome(args.genome_len, 0); h1 = synth.mutate_substitutions(h0, 0.01, 1)
+        total = int(round(2 * args.genome_len * args.coverage / args.read_len))
+        all_reads = synth.sample_reads([h0, h1], args.coverage, args.read_len, 0.001, 4242)[:total]
+        lo, hi = D.shard_bounds(len(all_reads), rank, world)
+        rd_s = H.Reads(all_reads[lo:hi]); model.reads_to_device(rd_s)
+        lp_s = torch.zeros(max(hi - lo, 1), dtype=torch.float64, device="cuda")
+        s_steps = max(1, min(args.steps, 3))
+        s_cells, s_ms, s_lib, _, _ = timed(rd_s, lp_s, 1, s_steps, "strong")
+        strong = {"scaling": "strong", "reads_total": len(all_reads), "reads_per_gpu": hi - lo, "value": s_cells / (s_ms * 1e-3) / 1e9, "unit": "GCUPS",
+                  "ms_per_step": s_ms / s_steps, "reads_per_s": len(all_reads) / (s_ms / s_steps * 1e-3), "steps": s_steps, "warmup": 1,
+                  "sum_logp": float(logp.item()),
+                  "note": "one step = the whole dataset once; the sparse rows are latency-bound per read, so a rank with fewer reads than one resident wave "
+                          "(sparse_wave_jobs) does not run them faster"}
+        del rd_s
+
+    # ---- end to end: host buffers in, host buffers out through the public API (reads handle re-created: validation + H2D inside)
     def step_e2e():
-        """host buffers in, host buffers out through the public API (reads handle re-created: validation + H2D inside)."""
-        t0 = time.perf_counter()
         r2 = H.Reads(reads)
         fr, lf, lb, cells = model.run_node_freqs(r2, "sparse")
         if world > 1:
-            t = torch.from_numpy(fr).cuda(); dist.all_reduce(t); fr = t.cpu().numpy()
+            t = torch.from_numpy(np.concatenate([fr, [lf.sum()]])).cuda(); dist.all_reduce(t); fr = t.cpu().numpy()
         torch.cuda.synchronize()
-        return sum(cells), (time.perf_counter() - t0) * 1e3, float(lf.sum())
+        return sum(cells)
 
-    for _ in range(args.warmup):
-        step_resident()
-    sampler = ClockSampler(local); sampler.start()
-    H.launch_count(reset=True)
-    barrier()
-    tot_cells, tot_ms, k_ms, k_launch, k_cells = 0, 0.0, 0.0, 0, 0
-    for _ in range(args.steps):
-        c, ms = step_resident()
-        tot_cells += c; tot_ms += ms
-        a, b, cc = H.last_dense_kernel(); k_ms += a; k_launch += b; k_cells += cc
-    barrier()
-    launches = H.launch_count()
-    clocks = sampler.stop()
-    # max over ranks of the device time, sum over ranks of the cells
-    t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda"); c = torch.tensor([float(tot_cells)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c)
-    ms_step = float(t.item()) / args.steps
-    value = float(c.item()) / (float(t.item()) * 1e-3) / 1e9
-    # end to end
-    e_cells, e_ms = 0, 0.0
-    for i in range(0 if args.no_e2e else 1 + min(args.steps, 2)):
-        cc, ms, _ = step_e2e()
-        if i > 0:
-            e_cells += cc; e_ms += ms
-    te = torch.tensor([e_ms], dtype=torch.float64, device="cuda"); ce = torch.tensor([float(e_cells)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce)
-    e2e_val = float(ce.item()) / (float(te.item()) * 1e-3) / 1e9 if te.item() > 0 else None
-    out = None
+    e2e_val = None
+    if not args.no_e2e:
+        note("e2e warmup"); step_e2e()
+        n_e = min(args.steps, 3)
+        barrier()
+        t0 = time.perf_counter(); e_cells = 0
+        for i in range(n_e):
+            note(f"e2e {i}")
+            e_cells += step_e2e()
+        barrier()
+        e_ms = (time.perf_counter() - t0) * 1e3
+        te = torch.tensor([e_ms], dtype=torch.float64, device="cuda"); ce = torch.tensor([float(e_cells)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce)
+        e2e_val = float(ce.item()) / (float(te.item()) * 1e-3) / 1e9
     if rank == 0:
         peaks = {}
         try:
@@ -250,35 +358,50 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (k_cells * ALGO_BYTES_PER_CELL / (k_ms * 1e-3) / 1e9) if k_ms > 0 else 0.0
-        # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this command
-        # (profiles/r1_dense_pair_dram.json, tools/ncu_summary.py); scaled per cell when the launch shape differs
-        traffic = None
-        try:
-            caps = json.load(open(os.path.join(ROOT, "profiles", "r1_dense_pair_dram.json")))
-            per_cell = sum(c["dram_bytes_per_cell"] for c in caps) / len(caps)
-            traffic = per_cell * (k_cells / max(k_launch, 1))
-        except Exception:
-            pass
+        # DRAM traffic of the dominant kernel: an ncu counter, so it cannot be read inside an unprofiled run; the figure comes from the
+        # committed `ncu --set full` capture of this command (tools/ncu_summary.py), per cell x the cells of one launch of this run
+        traffic, dram_frac, tsrc = None, None, None
+        for name in ("r2_dense_pair_dram.json", "r1_dense_pair_dram.json"):
+            try:
+                caps = json.load(open(os.path.join(ROOT, "profiles", name)))
+                per_cell = sum(c["dram_bytes_per_cell"] for c in caps) / len(caps)
+                traffic = per_cell * (k_cells / max(k_launch, 1))
+                dram_frac = (per_cell * k_cells / (k_ms * 1e-3) / 1e9) / peak if k_ms > 0 else None
+                tsrc = f"profiles/{name} (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell x cells per launch of this run)"
+                break
+            except Exception:
+                continue
         roof = {"bound": "hbm", "kernel": "k_dense_fwd2 / k_dense_bwd2 (two DP rows per launch)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1_dense_pair_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell x cells per launch)", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
+                "traffic": traffic, "traffic_source": tsrc, "dram_frac": dram_frac,
+                "dram_frac_note": "DRAM bytes actually moved (ncu capture) / launch time measured in this run / peak: the two-row fusion moves less than the algorithmic 48 B per cell",
+                "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
                 "avg_launch_ms": k_ms / max(k_launch, 1), "launches": k_launch, "cells_per_launch": k_cells / max(k_launch, 1),
                 "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "kernel_share_of_step": k_ms / max(tot_ms, 1e-9)}
         out = {"metric": "PHMM forward-backward GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "reads_per_s": world * R / (ms_step * 1e-3),
-               "config": {"workload": f"{workload_tag(args)}: {args.genome_len} bp diploid 1% het, {args.read_len} bp HiFi reads p=0.001, k={args.k}, run_sparse + node freqs",
-                          "n_nodes": int(N), "reads_per_gpu_per_step": R, "n_active_nodes": 40, "n_warmup": args.k,
-                          "l2": "DP rows of one step exceed L2 (each dense row is 28 B x N, hundreds of rows in flight)"},
+               "reads_per_s": world * R / (ms_step * 1e-3), "library_ms_per_step": lib_ms / args.steps,
+               "config": {"workload": workload_text(args), "n_nodes": int(N), "reads_per_gpu_per_step": R, "n_active_nodes": 40, "n_warmup": args.k,
+                          "l2": "DP rows of one step exceed L2 (each dense row is 28 B x N, hundreds of rows in flight)",
+                          "timing": "CUDA events around the bracket of all timed steps (zeroing, library call, ln P reduction, all-reduce), max over ranks"},
                "roofline": roof,
                "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": int(launches), "clocks": clocks}
-        if not args.no_cpu_baseline:
+               "gpu_launches": int(launches), "clocks": clocks, "checksum": {"sum_logp": sum_logp, "sum_node_freqs": sum_freq}}
+        if strong:
+            out["strong"] = strong
+        if world == 1 and not args.no_extras:
+            try:
+                note("extra C4")
+                out["extra"] = [extra_c4(H, local)]
+            except Exception as exc:   # an extra line never takes the headline down, but says why it is missing
+                out["extra"] = [{"workload": "C4", "error": repr(exc)}]
+        if world == 1 and not args.no_cpu_baseline:
             n_sample = args.cpu_sample_reads or auto_cpu_sample(N, args.k)
-            cb = cpu_reference(args, g, li, lt, reads, min(n_sample, len(reads)))
+            cb = cpu_reference(args, g, li, lt, reads, min(n_sample, len(reads)), gpu_cells_per_step=tot_cells / args.steps)
             cb.pop("logp_fwd", None); cb.pop("seconds", None)
             out["cpu_baseline"] = cb
         print(json.dumps(out))
     if world > 1:
+        barrier()
         dist.destroy_process_group()
     return 0
 
@@ -286,13 +409,17 @@ def main():
 if __name__ == "__main__":
     try:
         rc = main()
-    except Exception:
-        # single-process runs get one more attempt after a transient failure (e.g. the device still being released by the
-        # process that ran before this one); a multi-rank job cannot re-enter its rendezvous and fails as it is
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            raise
+    except Exception as exc:
+        # no retry: a failure of the hot path must fail the run.  Say which rank failed and what the library reported.
         import traceback
+        msg = ""
+        try:
+            from dbgphmm_b200 import hmmv2 as _H
+            msg = _H.lib().dbgphmm_last_error().decode()
+        except Exception:
+            pass
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')}] FAILED: {exc!r}; dbgphmm_last_error: {msg!r}\n")
         traceback.print_exc()
-        time.sleep(5.0)
-        rc = main()
+        sys.stderr.flush()
+        sys.exit(1)
     sys.exit(rc)

@@ -173,6 +173,60 @@ static int alloc_arena(SparseArena& a, uint64_t bytes, cudaStream_t st) {
     return DBGPHMM_OK;
 }
 
+// ------------------------------------------------------------------ DBGPHMM_VERIFY=1: structural check of every stored row
+// (debug aid: descriptors are poisoned at allocation, so a row no kernel wrote is reported with its job and row)
+static bool verify_enabled() { static int v = -1; if (v < 0) { const char* e = getenv("DBGPHMM_VERIFY"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
+struct VerifyRec { uint32_t job, row, code; int kind; uint32_t n_ent, n_mi, n_d, bad_id; unsigned long long off; };
+__global__ void k_verify_rows(uint32_t n_jobs, const RowDesc* __restrict__ desc, const uint64_t* __restrict__ desc0, const uint32_t* __restrict__ len,
+                              const uint32_t* __restrict__ row_lo, const uint32_t* __restrict__ row_hi, const char* __restrict__ arena, uint64_t arena_bytes,
+                              uint64_t n_slabs, uint32_t N, uint32_t* __restrict__ n_bad, VerifyRec* __restrict__ recs, uint32_t max_recs) {
+    const uint32_t j = blockIdx.y;
+    const uint32_t lo = row_lo[j], hi = row_hi[j] < len[j] ? row_hi[j] : len[j];
+    for (uint32_t r = lo + blockIdx.x; r < hi; r += gridDim.x) {
+        const RowDesc d = desc[desc0[j] + r];
+        uint32_t code = 0, bad_id = 0;
+        if (d.kind == ROW_DENSE) { if (d.off >= n_slabs && n_slabs) code = 2; }
+        else if (d.kind == ROW_SPARSE) {
+            if (d.n_ent > 832 || d.n_mi > d.n_ent || d.n_d > d.n_ent) code = 3;
+            else if (d.off + sparse_row_bytes(d.n_ent, d.n_d) > arena_bytes || (d.off & 7)) code = 4;
+            else {
+                const uint32_t* id = (const uint32_t*)(arena + d.off + 24ull * d.n_ent);
+                for (uint32_t e = threadIdx.x; e < d.n_ent; e += blockDim.x) if (id[e] >= N) { code = 5; bad_id = id[e]; }
+            }
+        } else code = 1;
+        if (code) {
+            const uint32_t k = atomicAdd(n_bad, 1u);
+            if (k < max_recs) { VerifyRec v; v.job = j; v.row = r; v.code = code; v.kind = d.kind; v.n_ent = d.n_ent; v.n_mi = d.n_mi; v.n_d = d.n_d; v.bad_id = bad_id; v.off = d.off; recs[k] = v; }
+        }
+    }
+}
+// rows [row_lo[j], row_hi[j]) of every job must be well-formed
+static int verify_rows(dbgphmm_model* m, const char* what, const RowStore& S, const std::vector<uint32_t>& row_lo, const std::vector<uint32_t>& row_hi) {
+    cudaStream_t st = m->stream;
+    const uint32_t J = (uint32_t)S.len.size();
+    if (J == 0) return DBGPHMM_OK;
+    DevBuf b_lo, b_hi, b_len, b_n, b_recs;
+    ST_TRY(dev_upload(b_lo, row_lo, st)); ST_TRY(dev_upload(b_hi, row_hi, st)); ST_TRY(dev_upload(b_len, S.len, st));
+    ST_TRY(b_n.alloc(sizeof(uint32_t))); ST_TRY(b_recs.alloc(sizeof(VerifyRec) * 64));
+    CUDA_TRY(cudaMemsetAsync(b_n.p, 0, sizeof(uint32_t), st));
+    k_verify_rows<<<dim3(64, J), 64, 0, st>>>(J, S.d_desc, S.d_desc0, b_len.as<uint32_t>(), b_lo.as<uint32_t>(), b_hi.as<uint32_t>(), S.arena.base, S.arena.bytes,
+                                               S.pool.base ? S.pool.n_slabs : 0, m->N, b_n.as<uint32_t>(), b_recs.as<VerifyRec>(), 64);
+    uint32_t n_bad = 0; std::vector<VerifyRec> recs(64);
+    CUDA_TRY(cudaMemcpyAsync(&n_bad, b_n.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(recs.data(), b_recs.p, sizeof(VerifyRec) * 64, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    if (!n_bad) return DBGPHMM_OK;
+    fprintf(stderr, "[dbgphmm verify] %s: %u malformed rows\n", what, n_bad);
+    for (uint32_t k = 0; k < std::min<uint32_t>(n_bad, 24); k++) {
+        const VerifyRec& v = recs[k];
+        fprintf(stderr, "   job %u (len %u, nd %u) row %u: code %u kind %d n_ent %u n_mi %u n_d %u off %llu bad_id %u\n", v.job, S.len[v.job], S.nd[v.job], v.row, v.code, v.kind,
+                v.n_ent, v.n_mi, v.n_d, v.off, v.bad_id);
+    }
+    dbg_set_error(std::string("DBGPHMM_VERIFY: malformed rows after ") + what);
+    return DBGPHMM_ERR_INVALID;
+}
+
 #define ST_ARENA_FULL (-100)
 // Run a set of sparse jobs, re-running the ones that overflowed the small shared-memory capacity with the big one.
 static int run_sparse_jobs_once(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io, RowStore* store, uint32_t small_cap) {
@@ -184,6 +238,7 @@ static int run_sparse_jobs_once(dbgphmm_model* m, std::vector<SJob>& sj, SparseI
     ST_TRY(dev_upload(b_jobs, sj, st));
     ST_TRY(b_status.alloc(sizeof(int) * n)); ST_TRY(b_final.alloc(sizeof(XF) * n)); ST_TRY(b_cells.alloc(sizeof(unsigned long long) * n));
     io.status = b_status.as<int>(); io.final_scalar = b_final.as<XF>(); io.cells = b_cells.as<unsigned long long>();
+    if (verify_enabled()) CUDA_TRY(cudaMemsetAsync(b_status.p, 0x7f, sizeof(int) * n, st));   // a status no CTA wrote is then not SJ_OK
     std::vector<int> status(n);
     std::vector<XF> fin(n);
     std::vector<unsigned long long> cells(n);
@@ -229,6 +284,13 @@ static int run_sparse_jobs_once(dbgphmm_model* m, std::vector<SJob>& sj, SparseI
                 next.push_back(todo[i]);
             }
             else if (status[i] == SJ_OOM) return ST_ARENA_FULL;
+            else if (status[i] == 0x7f7f7f7f) {
+                uint32_t ctl[4] = {0, 0, 0, 0};
+                if (io.rq_ctl) cudaMemcpy(ctl, io.rq_ctl, sizeof(ctl), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[dbgphmm verify] sparse pass %d: job %u (dir %d, %u rows) was never finished by any CTA ; queue: pushed %u taken %u primaries gone %u next job %u of %zu\n",
+                        pass, todo[i], (int)cur[i].dir, cur[i].n_rows, ctl[0], ctl[1], ctl[2], ctl[3], cur.size());
+                dbg_set_error("DBGPHMM_VERIFY: a sparse job was never finished"); return DBGPHMM_ERR_INVALID;
+            }
             else { dbg_set_error("a sparse row exceeded MAX_ACTIVE_NODES entries (the reference panics: insufficient capacity)"); return DBGPHMM_ERR_CAPACITY; }
         }
         if (!next.empty() && getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] sparse pass %d (cap %u): %zu of %zu jobs need a larger capacity\n", pass, caps[pass], next.size(), cur.size());
@@ -323,6 +385,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     out->d_desc0 = (uint64_t*)cache_alloc(sizeof(uint64_t) * std::max<uint32_t>(J, 1));
     if (!out->d_final || !out->d_desc0) { dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
     CUDA_TRY(cudaMemcpyAsync(out->d_desc0, out->desc0.data(), sizeof(uint64_t) * J, cudaMemcpyHostToDevice, st));
+    if (verify_enabled()) CUDA_TRY(cudaMemsetAsync(out->d_desc, 0xff, sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1), st));
     // ---- dense phase layout
     // top-n jobs whose dense rows are not kept: the first sparse row reads gathered cells, and the warm-up may run in groups of G jobs
     // that share one pool of slabs (slab indices are then relative to the group)
@@ -478,6 +541,11 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     CUDA_TRY(cudaMemcpyAsync(out->h_final.data(), out->d_final, sizeof(XF) * J, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    if (verify_enabled()) {
+        std::vector<uint32_t> lo(J, 0), hi(J);
+        for (uint32_t j = 0; j < J; j++) hi[j] = store_sparse ? jobs[j].len : out->nd[j];
+        ST_TRY(verify_rows(m, "run_forward", *out, lo, hi));
+    }
     return DBGPHMM_OK;
 }
 
@@ -500,6 +568,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     out->d_desc0 = (uint64_t*)cache_alloc(sizeof(uint64_t) * std::max<uint32_t>(J, 1));
     if (!out->d_final || !out->d_desc0) { dbg_set_error("out of device memory"); return DBGPHMM_ERR_OOM; }
     CUDA_TRY(cudaMemcpyAsync(out->d_desc0, out->desc0.data(), sizeof(uint64_t) * J, cudaMemcpyHostToDevice, st));
+    if (verify_enabled()) CUDA_TRY(cudaMemsetAsync(out->d_desc, 0xff, sizeof(RowDesc) * std::max<uint64_t>(tot_rows, 1), st));
     // dense rows of job j: [lo, hi]; they are computed from hi down to lo
     std::vector<DJob> dj(J);
     uint64_t n_slabs = 0, slab_cur = 0; uint32_t steps = 0;
@@ -669,6 +738,11 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     CUDA_TRY(cudaMemcpyAsync(out->h_final.data(), out->d_final, sizeof(XF) * J, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    if (verify_enabled()) {
+        std::vector<uint32_t> lo(J, 0), hi(J);
+        for (uint32_t j = 0; j < J; j++) hi[j] = jobs[j].len;
+        ST_TRY(verify_rows(m, "run_backward", *out, lo, hi));
+    }
     return DBGPHMM_OK;
 }
 

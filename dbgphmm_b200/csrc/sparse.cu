@@ -406,7 +406,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     if (threadIdx.x < 24) S.wt()[threadIdx.x] = 0;
 
     __shared__ XF s_mb, s_ib;          // begin scalars of the previous row (forward) / ib of the next row (backward)
-    __shared__ uint64_t s_page_off; __shared__ uint32_t s_page_left;
+    __shared__ uint64_t s_page_off;   // start of a freshly taken arena page (thread 0 -> block)
     __shared__ int s_fail;
     __shared__ unsigned long long s_cells;
     __shared__ unsigned long long s_info;   // where a job stopped: step << 32 | site << 16 | entries
@@ -460,9 +460,10 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
     constexpr bool fwd = DIR == 0;
     const bool adaptive = (jb.mode == SP_TOPN || jb.mode == SP_RATIO);
     uint32_t n_prev = 0;   // packed entries of the previous row (sparse prev only)
+    uint64_t page_off = 0, page_left = 0;   // arena page this job is filling (block-uniform registers)
     XF last_scalar = xf_zero();
     if (tid == 0) {
-        s_page_left = 0; s_page_off = 0; s_fail = SJ_OK; s_cells = 0; s_info = 0;
+        s_page_off = 0; s_fail = SJ_OK; s_cells = 0; s_info = 0;
         if (fwd) {
             if (jb.row_begin == 0) { s_mb = xf(1.0, 0); s_ib = xf_zero(); }
             else { s_mb = io.desc[jb.desc0 + jb.row_begin - 1].mb; s_ib = io.desc[jb.desc0 + jb.row_begin - 1].ib; }
@@ -515,7 +516,7 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         if (jb.mode == SP_TOPN || jb.mode == SP_RATIO) {
             if (s == 0) {
                 n_top = (int)io.top_cnt[jb.top0];
-                for (int t = tid; t < n_top; t += B) S.top_id()[t] = io.top_ids[(size_t)jb.top0 * MAX_ACTIVE + t];
+                if (n_top <= (int)cap) for (int t = tid; t < n_top; t += B) S.top_id()[t] = io.top_ids[(size_t)jb.top0 * MAX_ACTIVE + t];
             } else {
                 n_top = sp_top_of_prev(S, n_prev, jb.mode == SP_RATIO ? MAX_ACTIVE : lp.n_active_nodes, jb.mode == SP_RATIO,
                                        lp.active_node_max_ratio, S.top_id());
@@ -523,8 +524,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
         } else if (jb.mode == SP_MAPPING) {
             uint64_t a = io.map_row_off[jb.map_row0 + row], b = io.map_row_off[jb.map_row0 + row + 1];
             n_top = (int)(b - a);
-            if (n_top > MAX_ACTIVE) n_top = MAX_ACTIVE;
-            for (int t = tid; t < n_top; t += B) S.top_id()[t] = io.map_nodes[a + t];
+            if (b - a > MAX_ACTIVE) { if (tid == 0) s_fail = SJ_CAPACITY; n_top = 0; }   // (the reference's 400-entry SparseVec panics)
+            if (n_top <= (int)cap) for (int t = tid; t < n_top; t += B) S.top_id()[t] = io.map_nodes[a + t];
         } else {  // SP_BYFWD: filled_nodes() of forward row (row-1): top-|m entries| of its merged vector
             const RowDesc fr = io.fdesc[jb.fdesc0 + row - 1];
             const char* pay = io.farena + fr.off;
@@ -766,18 +767,23 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
 
         // ---------------- 8. store
         if (jb.store) {
-            uint64_t bytes = sparse_row_bytes(n_ent, n_d);
-            if (tid == 0) {
-                if (bytes > s_page_left) {
-                    uint64_t pg = bytes > SPARSE_PAGE_BYTES ? ((bytes + 255) & ~(uint64_t)255) : SPARSE_PAGE_BYTES;
+            // The page cursor lives in registers, identical in every thread (n_ent and n_d are block-uniform): only a fresh page goes
+            // through shared memory, written before the barrier and read after it.  (It used to be a shared variable that thread 0
+            // advanced after writing its part of the row with no barrier in between: a slower warp could read the advanced offset and
+            // write its entries into the next row's place.)
+            const uint64_t bytes = sparse_row_bytes(n_ent, n_d);
+            if (bytes > page_left) {
+                const uint64_t pg = bytes > SPARSE_PAGE_BYTES ? ((bytes + 255) & ~(uint64_t)255) : SPARSE_PAGE_BYTES;
+                if (tid == 0) {
                     unsigned long long o = atomicAdd(io.arena_cursor, (unsigned long long)pg);
                     if (o + pg > io.arena_bytes) s_fail = SJ_OOM;
-                    s_page_off = o; s_page_left = (uint32_t)pg;
+                    s_page_off = o;
                 }
+                __syncthreads();
+                if (s_fail) break;
+                page_off = s_page_off; page_left = pg;
             }
-            __syncthreads();
-            if (s_fail) break;
-            const uint64_t off = s_page_off;
+            const uint64_t off = page_off;
             char* pay = io.arena + off;
             double* om = (double*)pay; double* oi = om + n_ent; double* od = oi + n_ent;
             uint32_t* oid = (uint32_t*)(od + n_ent); int* oex = (int*)(oid + n_ent); uint16_t* odl = (uint16_t*)(oex + n_ent);
@@ -789,8 +795,8 @@ __global__ void k_sparse(SGraph G, LinParams lp, const SJob* __restrict__ jobs, 
                 if (fwd) { r.mb = xf_zero(); r.ib = s_ib; r.e = last_scalar; }
                 else { r.mb = s_mb; r.ib = s_ib; r.e = xf_zero(); }
                 io.desc[jb.desc0 + row] = r;
-                s_page_off = off + bytes; s_page_left -= (uint32_t)bytes;
             }
+            page_off = off + bytes; page_left -= bytes;
             __syncthreads();
         }
     }

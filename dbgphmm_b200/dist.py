@@ -17,22 +17,42 @@ def shard_reads(reads, rank, world):
 
 
 def allreduce_results(node_freqs, logp_sum, dist=None, device=None):
-    """Sum node_freqs [N] and the scalar(s) logp_sum over all ranks in one collective.  Inputs may be numpy arrays or torch
-    tensors (on `device` for NCCL).  Returns (node_freqs, logp_sum) of the same kind as given."""
+    """Sum node_freqs [N] and the scalar(s) logp_sum over all ranks.  numpy inputs: packed into one payload, ONE collective, new arrays
+    are returned.  torch tensors: reduced IN PLACE (the inputs hold the sums afterwards and are returned); when both are views of one
+    buffer -- `packed_buffer` below -- pass the buffer's two views and a single collective over the whole buffer is issued, otherwise
+    the (tiny) logp tensor takes a second collective.  No copy of the [N] vector is made on the torch path."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return node_freqs, logp_sum
     import torch
-    is_np = isinstance(node_freqs, np.ndarray)
-    f = torch.from_numpy(np.ascontiguousarray(node_freqs)) if is_np else node_freqs
-    l = torch.as_tensor(np.atleast_1d(np.asarray(logp_sum, np.float64))) if not torch.is_tensor(logp_sum) else logp_sum
-    if device is not None:
-        f = f.to(device); l = l.to(device)
-    buf = torch.cat([f.reshape(-1).to(torch.float64), l.reshape(-1).to(torch.float64)])  # one payload, one collective
-    dist.all_reduce(buf)
-    f_out, l_out = buf[:f.numel()], buf[f.numel():]
-    if is_np:
-        return f_out.cpu().numpy(), l_out.cpu().numpy()
-    return f_out, l_out
+    if isinstance(node_freqs, np.ndarray) or not torch.is_tensor(node_freqs):
+        f = torch.from_numpy(np.ascontiguousarray(node_freqs, np.float64))
+        l = torch.as_tensor(np.atleast_1d(np.asarray(logp_sum, np.float64)))
+        buf = torch.cat([f.reshape(-1), l.reshape(-1)])      # one payload, one collective
+        if device is not None:
+            buf = buf.to(device)
+        dist.all_reduce(buf)
+        buf = buf.cpu()
+        return buf[:f.numel()].numpy(), buf[f.numel():].numpy()
+    l = logp_sum if torch.is_tensor(logp_sum) else torch.as_tensor(np.atleast_1d(np.asarray(logp_sum, np.float64)), device=node_freqs.device)
+    nf, nl = node_freqs.numel(), l.numel()
+    same = (node_freqs.is_contiguous() and l.is_contiguous() and node_freqs.dtype == l.dtype and node_freqs.device == l.device
+            and node_freqs.untyped_storage().data_ptr() == l.untyped_storage().data_ptr()
+            and l.storage_offset() == node_freqs.storage_offset() + nf)
+    if same:   # adjacent views of one buffer: reduce the buffer itself
+        whole = torch.as_strided(node_freqs, (nf + nl,), (1,), node_freqs.storage_offset())
+        dist.all_reduce(whole)
+    else:
+        dist.all_reduce(node_freqs)
+        dist.all_reduce(l)
+    return node_freqs, l
+
+
+def packed_buffer(n_nodes, n_scalars=1, device=None):
+    """One f64 buffer [n_nodes + n_scalars] and its two views (node_freqs, scalars): what the ranks exchange, laid out so that
+    allreduce_results issues a single in-place collective."""
+    import torch
+    buf = torch.zeros(n_nodes + n_scalars, dtype=torch.float64, device=device)
+    return buf, buf[:n_nodes], buf[n_nodes:]
 
 
 def full_prob_reads_sharded(model, seqs, mappings, dist=None, use_max_ratio=True, device=None, make_reads=None):
