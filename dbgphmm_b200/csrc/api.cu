@@ -471,7 +471,7 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
         }
         std::vector<HJob> rest; std::vector<uint64_t> rbytes; std::vector<size_t> ridx;
         for (size_t i = 0; i < all.size(); i++) if (!done[i]) { rest.push_back(all[i]); rbytes.push_back(bytes[i]); ridx.push_back(i); }
-        for (auto& bt : plan_batches(rbytes, m->mem_budget, 1u << 20, sparse_wave_jobs(m, sparse_default_cap()))) {
+        for (auto& bt : plan_batches(rbytes, model_budget(m), 1u << 20, sparse_wave_jobs(m, sparse_default_cap()))) {
             std::vector<HJob> jobs(rest.begin() + bt.first, rest.begin() + bt.second);
             RowStore F;
             PhaseOpts so; so.keep_rows = false; so.store_sparse = false;
@@ -482,7 +482,7 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
         }
         all.clear(); bytes.clear();
     }
-    for (auto& bt : plan_batches(bytes, m->mem_budget, mappings ? (1u << 20) : 65535, sparse_wave_jobs(m, sparse_default_cap()))) {
+    for (auto& bt : plan_batches(bytes, model_budget(m), mappings ? (1u << 20) : 65535, sparse_wave_jobs(m, sparse_default_cap()))) {
         std::vector<HJob> jobs(all.begin() + bt.first, all.begin() + bt.second);
         RowStore F;
         PhaseOpts so; so.keep_rows = false; so.store_sparse = false;
@@ -549,12 +549,13 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
     bool can_stream = (mode == DBGPHMM_RUN_SPARSE) && !map_out && d_freqs;
     uint64_t store_total = 0;
     for (uint64_t r = 0; r < R; r++) { store_total += bytes[r]; if (all[r].len < 2 * W + 2) can_stream = false; }
-    bool stream = can_stream && store_total > m->mem_budget;
+    const uint64_t budget_now = model_budget(m);
+    bool stream = can_stream && store_total > budget_now;
     if (const char* e = getenv("DBGPHMM_STRATEGY")) { if (!strcmp(e, "stream")) stream = can_stream; else if (!strcmp(e, "store")) stream = false; }
     // DBGPHMM_DENSE_GROUP=G (stream strategy): the dense warm-up and the recompute passes run in groups of G jobs that share one pool
     // of 2 G slabs (engine.cu), so a batch is sized by its sparse rows and can fill the sparse kernel's waves on large graphs
     uint32_t group = 0;
-    uint64_t plan_budget = m->mem_budget;
+    uint64_t plan_budget = budget_now;
     if (stream) {
         if (const char* e = getenv("DBGPHMM_DENSE_GROUP")) { const int g = atoi(e); if (g > 0) group = (uint32_t)g; }
         const uint64_t slab = dense_slab_bytes(m->N);

@@ -76,6 +76,22 @@ void cache_free(void* p) {
     for (auto& b : g_cache) if (b.p == p) { b.used = false; b.owner = std::this_thread::get_id(); return; }
     cudaFree(p);
 }
+uint64_t cache_unused_bytes() {
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
+    int dev = 0; cudaGetDevice(&dev);
+    uint64_t n = 0;
+    for (auto& b : g_cache) if (!b.used && b.device == dev) n += b.bytes;
+    return n;
+}
+// Device memory a bulk call may plan with.  A fixed budget given at model creation is taken as it is; otherwise 88 % of what is free
+// NOW plus what this process holds in unused cache blocks (they are reused or trimmed): other allocations of the process made after
+// the model was created -- torch tensors, NCCL buffers, another handle's rows -- are then accounted for.
+uint64_t model_budget(const dbgphmm_model* m) {
+    if (m->mem_budget_fixed) return m->mem_budget;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return m->mem_budget; }
+    return (uint64_t)(((double)fr + (double)cache_unused_bytes()) * 0.88);
+}
 void cache_trim() {
     std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
     int dev = 0; cudaGetDevice(&dev);
@@ -175,7 +191,7 @@ static int alloc_arena(SparseArena& a, uint64_t bytes, cudaStream_t st) {
 
 // ------------------------------------------------------------------ DBGPHMM_VERIFY=1: structural check of every stored row
 // (debug aid: descriptors are poisoned at allocation, so a row no kernel wrote is reported with its job and row)
-static bool verify_enabled() { static int v = -1; if (v < 0) { const char* e = getenv("DBGPHMM_VERIFY"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
+static bool verify_enabled() { const char* e = getenv("DBGPHMM_VERIFY"); return e && e[0] == '1'; }
 struct VerifyRec { uint32_t job, row, code; int kind; uint32_t n_ent, n_mi, n_d, bad_id; unsigned long long off; };
 __global__ void k_verify_rows(uint32_t n_jobs, const RowDesc* __restrict__ desc, const uint64_t* __restrict__ desc0, const uint32_t* __restrict__ len,
                               const uint32_t* __restrict__ row_lo, const uint32_t* __restrict__ row_hi, const char* __restrict__ arena, uint64_t arena_bytes,

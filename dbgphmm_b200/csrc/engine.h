@@ -43,6 +43,8 @@ struct RowStore {
 void* cache_alloc(size_t bytes);   // nullptr on failure
 void cache_free(void* p);
 void cache_trim();                 // give every unused block back to the driver
+uint64_t cache_unused_bytes();     // bytes of this device held in unused cache blocks
+uint64_t model_budget(const dbgphmm_model* m);   // device bytes a bulk call may plan with, from the memory free at the time of the call
 
 struct DevBuf {  // scoped device allocation
     void* p = nullptr;

@@ -549,6 +549,7 @@ extern "C" int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const ui
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
         m->mem_budget = mem_budget_bytes ? mem_budget_bytes : (uint64_t)(fr * 0.88);
+        m->mem_budget_fixed = mem_budget_bytes != 0;
         st = dense_configure(m);
         if (st == DBGPHMM_OK) st = sparse_configure(m);
     }

@@ -74,7 +74,8 @@ struct dbgphmm_model {
     uint32_t n_batch = 1;
     dbgphmm_params params;  // logs, as given
     LinParams lin;          // linear
-    uint64_t mem_budget = 0;
+    uint64_t mem_budget = 0;        // fixed by the caller, or 88 % of the memory free at creation (fallback only: see model_budget)
+    bool mem_budget_fixed = false;
     int n_sm = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_aux = nullptr;            // rescue launch of the sparse kernel (sparse.cu)

@@ -70,7 +70,8 @@ void dbgphmm_params_uniform(double p, dbgphmm_params* out);
 /* Build the device graph from a node-centric PHMM (common.rs:61-67,202-261).
  * edge_src/edge_dst: EdgeIndex order.  emission: 'A','C','G','T' or 'n' (NULL_BASE, common.rs:21).
  * log_init[n_nodes], log_trans[n_edges]: PNode.init_prob / PEdge.trans_prob as natural logs.
- * device: CUDA ordinal.  mem_budget_bytes: device memory the handle may use for DP rows (0 = 88% of free). */
+ * device: CUDA ordinal.  mem_budget_bytes: device memory the handle may use for DP rows
+ * (0 = 88% of what is free at the time of each bulk call, counting this library's reusable cache blocks). */
 int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const uint32_t* edge_src, const uint32_t* edge_dst,
                          const uint8_t* emission, const double* log_init, const double* log_trans,
                          const dbgphmm_params* params, int device, uint64_t mem_budget_bytes, dbgphmm_model** out);

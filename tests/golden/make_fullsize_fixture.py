@@ -49,7 +49,8 @@ def build_case(name):
 
 
 def boundary_tie(prev_row, n_nodes, k, rel=1e-9):
-    """True if the k-th and (k+1)-th largest merged values of a sparse row tie within rel (the top-k set is then not unique)."""
+    """Bit 0: the k-th and (k+1)-th largest merged values of a sparse row tie within rel on the ln scale (the criterion of
+    tests/common.py::same_up_to_ties); bit 1: they are exactly equal.  The top-k set is then not determined by the values."""
     with np.errstate(divide="ignore", invalid="ignore"):
         idx = np.union1d(prev_row.ids, prev_row.ids_d)
         v = np.full(len(idx), -np.inf)
@@ -58,12 +59,12 @@ def boundary_tie(prev_row, n_nodes, k, rel=1e-9):
         posd = np.searchsorted(idx, prev_row.ids_d)
         v[posd] = np.logaddexp(v[posd], prev_row.d)
     if len(v) <= k:
-        return False
+        return 0
     s = np.sort(v)[::-1]
     a, b = s[k - 1], s[k]
-    if np.isneginf(a) and np.isneginf(b):
-        return True
-    return abs(a - b) <= rel * max(1.0, abs(a))
+    if a == b:
+        return 3
+    return 1 if abs(a - b) <= rel * max(1.0, abs(a)) else 0
 
 
 def one_read(o, read, n_nodes, n_active):
@@ -78,7 +79,7 @@ def one_read(o, read, n_nodes, n_active):
     ties = [0, 0]
     for d, t in enumerate((f, b)):
         dense = np.zeros(n, np.uint8); n_mi = np.zeros(n, np.uint32); n_d = np.zeros(n, np.uint32)
-        h_mi = np.zeros(n, np.uint64); h_d = np.zeros(n, np.uint64); sc = np.zeros(n)
+        h_mi = np.zeros(n, np.uint64); h_d = np.zeros(n, np.uint64); sc = np.zeros(n); tie = np.zeros(n, np.uint8)
         prev = None
         order = range(n) if d == 0 else range(n - 1, -1, -1)   # the order the rows were computed in
         for r in order:
@@ -88,11 +89,12 @@ def one_read(o, read, n_nodes, n_active):
             if not row.is_dense:
                 n_mi[r] = len(row.ids); n_d[r] = len(row.ids_d)
                 h_mi[r] = ids_hash(row.ids); h_d[r] = ids_hash(row.ids_d)
-                if prev is not None and not prev.is_dense and boundary_tie(prev, n_nodes, n_active):
-                    ties[d] += 1
+                if prev is not None and not prev.is_dense:
+                    tie[r] = boundary_tie(prev, n_nodes, n_active)
+                    ties[d] += int(tie[r] != 0)
             prev = row if not row.is_dense else None
         p = "f_" if d == 0 else "b_"
-        out.update({p + "dense": dense, p + "n_mi": n_mi, p + "n_d": n_d, p + "h_mi": h_mi, p + "h_d": h_d, p + "scalar": sc})
+        out.update({p + "dense": dense, p + "n_mi": n_mi, p + "n_d": n_d, p + "h_mi": h_mi, p + "h_d": h_d, p + "scalar": sc, p + "tie": tie})
     out["ties"] = np.array(ties, np.uint32)
     out["seconds"] = time.time() - t0
     return out
