@@ -388,299 +388,12 @@ __global__ void k_dense_bwd_finish(LinParams lp, const DJob* __restrict__ jobs, 
 
 #define EXP_NONE_LO_ 0x3fffffff
 #define EXP_NONE_HI_ (-0x3fffffff)
-// ------------------------------------------------------------------------------------------------ common-frame kernel
-// Fast path of the dense row step, one WARP per tile (DENSE_CORE consecutive nodes + 6-hop halo), no block barriers:
-// every warp stages its tile's adjacency once (registers + a private slice of shared memory) and then walks over the
-// reads of its job group on its own, so load latency of one warp overlaps compute of the others.
-// When every non-zero input of a tile (previous row of the tile and its halo, begin-state terms) lies within `span`
-// binades of the largest one, all of them are brought to ONE exponent E_ref with exact power-of-two scalings and the
-// step runs in plain f64 (no operand can underflow inside the step: `span` leaves room for every factor a row applies).
-// Tiles that do not qualify are appended to the worklist of the exact kernel above.
-struct WarpSmem {
-    double *p0, *pi, *pd, *cm, *ci, *trdd;   // p0: previous m (round A), then d0 (round B onwards)
-    unsigned short* par;
-};
-#define WT_SMEM_PER_WARP (DENSE_LMAX * (6 * 8 + 2))
-#define WT_SMEM_BYTES (WT_WARPS * WT_SMEM_PER_WARP)
-
-// Contribution of the EXTRA upstream edges of local node j (rare: merge nodes): sum trans * (ca a[l] + cb b[l] + cc c[l]).
-// Kept out of line so that the common single-parent path stays small (the kernel is instruction-cache sensitive).
-__device__ __noinline__ double wt_extras(const uint32_t* __restrict__ fx_off, const uint16_t* __restrict__ fx_idx, const uint32_t* __restrict__ fx_eid,
-                                         const double* __restrict__ trans, uint32_t loj, const double* a, const double* b, const double* c,
-                                         double ca, double cb, double cc) {
-    double acc = 0.0;
-    for (uint32_t e = fx_off[loj], ee = fx_off[loj + 1]; e < ee; e++) {
-        int l = fx_idx[e];
-        acc += trans[fx_eid[e]] * (ca * a[l] + cb * b[l] + cc * c[l]);
-    }
-    return acc;
-}
-#define WT_EXTRAS(A, B, C, ca, cb, cc) wt_extras(P.fx_off, P.fx_idx, P.fx_eid, trans, lo + j, (A), (B), (C), (ca), (cb), (cc))
-
-// One warp-synchronous Del round over the tile: cur[j] = sum over upstream edges (l -> j) of trans * p_DD * prev[l]
-// for every local node of depth < `nb`; returns this lane's values in add[] (fdt, forward.rs:510-524; bdt, backward.rs:387-404)
-#define WT_DEL_ROUND(prevbuf, curbuf, nb)                                                                              \
-    _Pragma("unroll") for (int q = 0; q < WT_SLOTS; q++) {                                                             \
-        int j = q * 32 + lane;                                                                                         \
-        if (j < (nb)) {                                                                                                \
-            double v = S.trdd[j] * (prevbuf)[par[q]];                                                                  \
-            if (em[q] & 0x80) v += WT_EXTRAS((prevbuf), (prevbuf), (prevbuf), lp.p_DD, 0.0, 0.0);                      \
-            (curbuf)[j] = v; dacc[q] += v;                                                                             \
-        }                                                                                                              \
-    }                                                                                                                  \
-    __syncwarp();
-
-template <bool FWD>
-__global__ void __launch_bounds__(WT_WARPS * 32, WT_MIN_CTAS)
-k_dense_warp(PlanView P, GraphView G, LinParams lp, const DJob* __restrict__ jobs, uint32_t n_jobs, uint32_t s, const uint8_t* __restrict__ bases,
-             const RowDesc* __restrict__ desc, const int* __restrict__ active, char* __restrict__ pool, uint64_t slab_bytes, uint32_t Np,
-             XF* __restrict__ partials, uint32_t n_tiles, int span, unsigned long long* __restrict__ worklist, uint32_t jpc) {
-    extern __shared__ __align__(16) unsigned char wt_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t c = blockIdx.x * WT_WARPS + warp;
-    if (c >= n_tiles) return;   // no block-wide barrier anywhere in this kernel
-    WarpSmem S;
-    {
-        unsigned char* base = wt_raw + (size_t)warp * WT_SMEM_PER_WARP;
-        S.p0 = (double*)base; S.pi = S.p0 + DENSE_LMAX; S.pd = S.pi + DENSE_LMAX; S.cm = S.pd + DENSE_LMAX; S.ci = S.cm + DENSE_LMAX;
-        S.trdd = S.ci + DENSE_LMAX; S.par = (unsigned short*)(S.trdd + DENSE_LMAX);
-    }
-    const uint32_t lb = P.loc_base[c], lo = lb + c;
-    const uint32_t* nle = P.nle + (size_t)c * 8;
-    const int n0 = nle[0], n1 = nle[1], n4 = nle[4], n5 = nle[5], nL = nle[6];
-    const uint32_t g0 = P.chunk_start[c];
-    const uint32_t x0 = P.fx_off[lo];
-    // ---- tile structure in registers: slot q of this lane is local node j = q * 32 + lane
-    uint32_t node[WT_SLOTS]; int par[WT_SLOTS]; unsigned char em[WT_SLOTS];
-    double tr[WT_SLOTS], init_[WT_SLOTS];
-#pragma unroll
-    for (int q = 0; q < WT_SLOTS; q++) {
-        int j = q * 32 + lane;
-        node[q] = 0; par[q] = j; em[q] = 4; tr[q] = 0.0; init_[q] = 0.0;
-        if (j < nL) {
-            node[q] = P.loc_node[lb + j]; par[q] = P.fp_idx[lb + j];
-            { unsigned char ch = G.emission[node[q]];   // base code in bits 0-2 (A C T G -> 0 1 2 3, n -> 4), flags in bits 6-7
-              em[q] = (unsigned char)((ch == 'n' ? 4 : ((ch >> 1) & 3)) | (P.fx_off[lo + j + 1] > P.fx_off[lo + j] ? 0x80 : 0)); }
-            S.par[j] = (unsigned short)par[q];
-        }
-    }
-    __syncwarp();
-    int staged_x = -1;
-    const double* trans = G.trans;
-    const uint32_t job0 = blockIdx.y * jpc;
-    for (uint32_t jj = 0; jj < jpc; jj++) {
-        const uint32_t job_idx = job0 + jj;
-        if (job_idx >= n_jobs) break;
-        // ---- per-tile scalars: lane 0 prepares them, the warp receives them by shuffle
-        int valid = 0, hx = 0, pk = 0, row = 0; unsigned int xbase = 0;
-        unsigned long long prev_ptr = 0, out_ptr = 0;
-        XF fb0 = xf_zero(), ib_cur = xf_zero();
-        if (lane == 0) {
-            const DJob jb = jobs[job_idx];
-            if (s < jb.n_steps && !(jb.active_idx >= 0 && !active[jb.active_idx])) {
-                valid = 1; hx = (int)jb.x;
-                row = FWD ? jb.first_row + (int)s : jb.first_row - (int)s;
-                xbase = bases[jb.base_off + row];
-                pk = (s == 0) ? jb.prev0_kind : PREV_SLAB;
-                prev_ptr = (unsigned long long)(pool + (s == 0 ? jb.prev0_slab : slab_of(jb, s - 1)) * slab_bytes);
-                out_ptr = (unsigned long long)(pool + slab_of(jb, s) * slab_bytes);
-                if (FWD) {
-                    XF mbp, ibp;
-                    if (row == 0) { mbp = xf(1.0, 0); ibp = xf_zero(); }
-                    else { mbp = desc[jb.desc0 + row - 1].mb; ibp = desc[jb.desc0 + row - 1].ib; }
-                    ib_cur = xmul(xadd(xmul(mbp, lp.p_MI), xmul(ibp, lp.p_II)), lp.p_random);   // fib, forward.rs:541-545
-                    fb0 = xadd(xmul(mbp, lp.p_MM), xmul(ibp, lp.p_IM));                         // begin part of fm
-                }
-            }
-        }
-        valid = __shfl_sync(0xffffffffu, valid, 0);
-        if (!valid) continue;
-        hx = __shfl_sync(0xffffffffu, hx, 0); pk = __shfl_sync(0xffffffffu, pk, 0); xbase = __shfl_sync(0xffffffffu, xbase, 0);
-        prev_ptr = __shfl_sync(0xffffffffu, prev_ptr, 0); out_ptr = __shfl_sync(0xffffffffu, out_ptr, 0);
-        if (FWD) {
-            fb0.v = __shfl_sync(0xffffffffu, fb0.v, 0); fb0.e = __shfl_sync(0xffffffffu, fb0.e, 0);
-            ib_cur.v = __shfl_sync(0xffffffffu, ib_cur.v, 0); ib_cur.e = __shfl_sync(0xffffffffu, ib_cur.e, 0);
-        }
-        const unsigned char x = (unsigned char)((xbase >> 1) & 3);   // base code of the read base
-        if (hx != staged_x) {
-            const double* init = G.init + (size_t)hx * G.N;
-            trans = G.trans + (size_t)hx * G.E;
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) {
-                int j = q * 32 + lane;
-                if (j < nL) { uint32_t e = P.fp_eid[lb + j]; init_[q] = init[node[q]]; tr[q] = e == 0xffffffffu ? 0.0 : trans[e]; S.trdd[j] = tr[q] * lp.p_DD; }
-            }
-            staged_x = hx;
-        }
-        // ---- previous row of the tile: load, exponent range by warp shuffles, scale in registers, stage
-        double vm[WT_SLOTS], vi[WT_SLOTS], vd[WT_SLOTS]; int ve[WT_SLOTS];
-        int elo = EXP_NONE_LO_, ehi = EXP_NONE_HI_;
-        if (pk == PREV_SLAB) {
-            const double* gm = (const double*)prev_ptr; const double* gi = gm + Np; const double* gd = gi + Np; const int* ge = (const int*)(gd + Np);
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) {
-                int j = q * 32 + lane;
-                vm[q] = 0.0; vi[q] = 0.0; vd[q] = 0.0; ve[q] = 0;
-                if (j < nL) { uint32_t g = node[q]; vm[q] = gm[g]; vi[q] = gi[g]; vd[q] = FWD ? gd[g] : 0.0; ve[q] = ge[g]; }
-            }
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++)
-                if (vm[q] + vi[q] + vd[q] != 0.0) { elo = ve[q] < elo ? ve[q] : elo; ehi = ve[q] > ehi ? ve[q] : ehi; }
-        } else {
-            const double v0 = pk == PREV_B_INIT ? lp.p_end : 0.0;
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) { vm[q] = v0; vi[q] = v0; vd[q] = 0.0; ve[q] = 0; }
-            if (v0 != 0.0) { elo = 0; ehi = 0; }
-        }
-        if (FWD) {
-            if (fb0.v != 0.0) { int e = xexp(fb0); elo = e < elo ? e : elo; ehi = e > ehi ? e : ehi; }
-            if (ib_cur.v != 0.0) { int e = xexp(ib_cur); elo = e < elo ? e : elo; ehi = e > ehi ? e : ehi; }
-        }
-        elo = __reduce_min_sync(0xffffffffu, elo); ehi = __reduce_max_sync(0xffffffffu, ehi);
-        double* om = (double*)out_ptr; double* oi = om + Np; double* od = oi + Np; int* oe = (int*)(od + Np);
-        if (ehi == EXP_NONE_HI_) {  // nothing but zeros flows into this tile: the row is zero here
-            for (int j = lane; j < n0; j += 32) { om[g0 + j] = 0.0; oi[g0 + j] = 0.0; od[g0 + j] = 0.0; oe[g0 + j] = 0; }
-            if (lane == 0) {
-                if (FWD) partials[(size_t)job_idx * n_tiles + c] = xf_zero();
-                else { partials[((size_t)job_idx * n_tiles + c) * 2] = xf_zero(); partials[((size_t)job_idx * n_tiles + c) * 2 + 1] = xf_zero(); }
-            }
-            continue;
-        }
-        if (ehi - elo > span) {    // exponent range too wide for one frame: the exact kernel takes this tile
-            if (lane == 0) { unsigned long long w = atomicAdd(worklist, 1ull); worklist[1 + w] = ((unsigned long long)job_idx << 32) | c; }
-            continue;
-        }
-        const int Eref = ehi;
-        __syncwarp();   // the previous tile's shared-memory reads are done
-#pragma unroll
-        for (int q = 0; q < WT_SLOTS; q++) {
-            int j = q * 32 + lane;
-            if (j < nL) {
-                double sc = pow2i(ve[q] - Eref);
-                if (FWD) { vm[q] *= sc; vi[q] *= sc; vd[q] *= sc; S.pd[j] = vd[q]; }
-                else { vm[q] *= sc * ((em[q] & 7) == x ? lp.p_match : lp.p_mismatch); vi[q] *= sc; }   // vm := e_l(x) m''[l]
-                S.p0[j] = vm[q]; S.pi[j] = vi[q];
-            }
-        }
-        __syncwarp();
-        double dacc[WT_SLOTS];
-        if (FWD) {
-            const double fbv = fb0.v == 0.0 ? 0.0 : fb0.v * pow2i(fb0.e - Eref);
-            const double ibv = ib_cur.v == 0.0 ? 0.0 : ib_cur.v * pow2i(ib_cur.e - Eref);
-            // round A: fm, fi  (forward.rs:337-388)
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) {
-                int j = q * 32 + lane;
-                if (j < n5) {
-                    int l = par[q];
-                    double acc = tr[q] * (lp.p_MM * S.p0[l] + lp.p_IM * S.pi[l] + lp.p_DM * S.pd[l]);
-                    if (em[q] & 0x80) acc += WT_EXTRAS(S.p0, S.pi, S.pd, lp.p_MM, lp.p_IM, lp.p_DM);
-                    acc += fbv * init_[q];
-                    S.cm[j] = acc * ((em[q] & 7) == x ? lp.p_match : lp.p_mismatch);
-                    S.ci[j] = lp.p_random * (lp.p_MI * vm[q] + lp.p_II * vi[q] + lp.p_DI * vd[q]);
-                }
-            }
-            __syncwarp();
-            // round B: fd0 (forward.rs:480-501) into p0
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) {
-                int j = q * 32 + lane;
-                if (j < n4) {
-                    int l = par[q];
-                    double acc = tr[q] * (lp.p_MD * S.cm[l] + lp.p_ID * S.ci[l]);
-                    if (em[q] & 0x80) acc += WT_EXTRAS(S.cm, S.ci, S.ci, lp.p_MD, lp.p_ID, 0.0);
-                    acc += ibv * (lp.p_ID * init_[q]);
-                    S.p0[j] = acc;
-                }
-            }
-            __syncwarp();
-            // fd = fd0 + 4 x fdt (forward.rs:423-466): warp-synchronous rounds, ping-pong between p0 and pd
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) { int j = q * 32 + lane; dacc[q] = j < n4 ? S.p0[j] : 0.0; }
-            WT_DEL_ROUND(S.p0, S.pd, nle[3])
-            WT_DEL_ROUND(S.pd, S.p0, nle[2])
-            WT_DEL_ROUND(S.p0, S.pd, nle[1])
-            WT_DEL_ROUND(S.pd, S.p0, nle[0])
-            double part = 0.0;
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) {
-                int j = q * 32 + lane;
-                if (j < n0) {
-                    double d = dacc[q];
-                    double m = S.cm[j], i = S.ci[j];
-                    double mx = fmax(m, fmax(i, d));
-                    if (mx == 0.0) { om[g0 + j] = 0.0; oi[g0 + j] = 0.0; od[g0 + j] = 0.0; oe[g0 + j] = 0; }
-                    else {
-                        int qx = ilogb_pos(mx);
-                        double sc = pow2i(-qx);
-                        om[g0 + j] = m * sc; oi[g0 + j] = i * sc; od[g0 + j] = d * sc; oe[g0 + j] = Eref + qx;
-                        part += m + i + d;
-                    }
-                }
-            }
-            for (int o = 16; o; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-            if (lane == 0) partials[(size_t)job_idx * n_tiles + c] = xf(part, Eref);
-        } else {
-            // p0 holds e_l(x) m''[l]; bd0 (backward.rs:354-377) for depth <= 5 goes to cm
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) {
-                int j = q * 32 + lane;
-                if (j < n5) {
-                    double acc = tr[q] * lp.p_DM * S.p0[par[q]];
-                    if (em[q] & 0x80) acc += WT_EXTRAS(S.p0, S.p0, S.p0, lp.p_DM, 0.0, 0.0);
-                    acc += lp.p_DI * lp.p_random * vi[q];
-                    S.cm[j] = acc;
-                }
-            }
-            __syncwarp();
-            // bd = bd0 + 4 x bdt (backward.rs:299-343): rounds ping-pong between cm and ci; d of depth <= 1 ends in pd
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) { int j = q * 32 + lane; dacc[q] = j < n5 ? S.cm[j] : 0.0; }
-            WT_DEL_ROUND(S.cm, S.ci, nle[4])
-            WT_DEL_ROUND(S.ci, S.cm, nle[3])
-            WT_DEL_ROUND(S.cm, S.ci, nle[2])
-            WT_DEL_ROUND(S.ci, S.cm, nle[1])
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) { int j = q * 32 + lane; if (j < n1) S.pd[j] = dacc[q]; }
-            __syncwarp();
-            double pmb = 0.0, pib = 0.0;
-#pragma unroll
-            for (int q = 0; q < WT_SLOTS; q++) {
-                int j = q * 32 + lane;
-                if (j < n0) {
-                    int l = par[q];
-                    double tm = tr[q] * S.p0[l], td = tr[q] * S.pd[l];
-                    double am = tm * lp.p_MM + td * lp.p_MD, ai = tm * lp.p_IM + td * lp.p_ID;
-                    if (em[q] & 0x80) {
-                        am += WT_EXTRAS(S.p0, S.pd, S.pd, lp.p_MM, lp.p_MD, 0.0);
-                        ai += WT_EXTRAS(S.p0, S.pd, S.pd, lp.p_IM, lp.p_ID, 0.0);
-                    }
-                    am += lp.p_MI * lp.p_random * vi[q];
-                    ai += lp.p_II * lp.p_random * vi[q];
-                    double d = dacc[q];
-                    double mx = fmax(am, fmax(ai, d));
-                    uint32_t g = g0 + j;
-                    if (mx == 0.0) { om[g] = 0.0; oi[g] = 0.0; od[g] = 0.0; oe[g] = 0; }
-                    else {
-                        int qx = ilogb_pos(mx);
-                        double sc = pow2i(-qx);
-                        om[g] = am * sc; oi[g] = ai * sc; od[g] = d * sc; oe[g] = Eref + qx;
-                    }
-                    pmb += (vm[q] * lp.p_MM + d * lp.p_MD) * init_[q];
-                    pib += (vm[q] * lp.p_IM + d * lp.p_ID) * init_[q];
-                }
-            }
-            for (int o = 16; o; o >>= 1) { pmb += __shfl_down_sync(0xffffffffu, pmb, o); pib += __shfl_down_sync(0xffffffffu, pib, o); }
-            if (lane == 0) {
-                partials[((size_t)job_idx * n_tiles + c) * 2] = xf(pmb, Eref);
-                partials[((size_t)job_idx * n_tiles + c) * 2 + 1] = xf(pib, Eref);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ register-stencil kernel
-// Same step as k_dense_warp (one warp per tile, one exponent frame per tile, exact scalings), but every lane OWNS
+// ------------------------------------------------------------------------------------------------ common-frame kernels
+// Fast path of the dense row step, one WARP per tile (DENSE_CORE consecutive nodes + halo), no block barriers.  When every non-zero
+// input of a tile (previous row of the tile and its halo, begin-state terms) lies within `span` binades of the largest one, all of
+// them are brought to ONE exponent E_ref with exact power-of-two scalings and the step runs in plain f64 (no operand can underflow
+// inside the step: `span` leaves room for every factor a row applies).  Tiles that do not qualify go to the exact kernel above.
+// Register-stencil form of that step (one warp per tile, one exponent frame per tile, exact scalings): every lane OWNS
 // RS_PER_LANE consecutive positions of the tile's register layout (model.cu: [chain above the tile head | core | rest of
 // the halo in chains]).  For almost every node the first upstream neighbour is the previous position, i.e. the lane's own
 // previous register or one shuffle from the lane below, so Match/Ins/Del need no shared-memory gathers; nodes whose
@@ -1890,7 +1603,6 @@ static int fast_span(const LinParams& lp) {
 }
 
 // reads handled by one CTA: the tile structure is staged once per CTA, so as many as still leave ~6 waves of CTAs
-static bool use_reg_kernel() { const char* e = getenv("DBGPHMM_DENSE_KERNEL"); return !(e && !strcmp(e, "warp")); }
 static uint32_t fast_jobs_per_cta(const dbgphmm_model* m, uint32_t n_chunks, uint32_t n_jobs) {
     uint32_t target = 8u * 3u * (uint32_t)m->n_sm;
     uint32_t n_ctas = (n_chunks + WT_WARPS - 1) / WT_WARPS;
@@ -1905,8 +1617,6 @@ int dense_configure(dbgphmm_model* m) {
     CUDA_TRY(cudaFuncSetAttribute(k_dense_reg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, RS2_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, RS2_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_dense_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_dense_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_dense_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SELECT_SMEM_BYTES));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, m->device));
@@ -1931,19 +1641,12 @@ int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jo
     CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), m->stream));
     const uint32_t jpc = fast_jobs_per_cta(m, m->fwd.n_chunks, n_jobs);
     dim3 grid((m->fwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
-    if (use_reg_kernel()) {
-        ST_TRY(ensure_jstep(m, n_jobs));
-        k_dense_prep<true><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
-        COUNT_LAUNCH();
-    }
+    ST_TRY(ensure_jstep(m, n_jobs));
+    k_dense_prep<true><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+    COUNT_LAUNCH();
     launch_timer_begin(m->stream);
-    if (use_reg_kernel())
-        k_dense_reg<true><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
-                                                                              d_partials, m->fwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
-    else
-        k_dense_warp<true><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
-                                                                               d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks,
-                                                                               fast_span(m->lin), d_worklist, jpc);
+    k_dense_reg<true><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+                                                                          d_partials, m->fwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
     COUNT_LAUNCH();
     k_dense_fwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
                                                                              d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks, d_worklist);
@@ -1966,7 +1669,7 @@ static int fast_span2(const LinParams& lp) {
     if (const char* f = getenv("DBGPHMM_DENSE_SPAN2")) { int v = atoi(f); if (v > 0 && v < span) return v; }   // tests: force the fallback
     return span < 64 ? -1 : (span > 900 ? 900 : span);
 }
-bool dense_can_pair(const dbgphmm_model* m) { return m->fwd2.n_chunks > 0 && m->bwd2.n_chunks > 0 && use_reg_kernel() && fast_span2(m->lin) > 0; }
+bool dense_can_pair(const dbgphmm_model* m) { return m->fwd2.n_chunks > 0 && m->bwd2.n_chunks > 0 && fast_span2(m->lin) > 0; }
 uint32_t dense_pair_tiles(const dbgphmm_model* m, int dir) { return dir == 0 ? m->fwd2.n_chunks : m->bwd2.n_chunks; }
 
 // backward rows first_row - s and first_row - s - 1 of every job in one launch ; d_partials holds [2][n_jobs][bwd2.n_chunks][2]
@@ -2042,19 +1745,12 @@ int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
     CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), m->stream));
     const uint32_t jpc = fast_jobs_per_cta(m, m->bwd.n_chunks, n_jobs);
     dim3 grid((m->bwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
-    if (use_reg_kernel()) {
-        ST_TRY(ensure_jstep(m, n_jobs));
-        k_dense_prep<false><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
-        COUNT_LAUNCH();
-    }
+    ST_TRY(ensure_jstep(m, n_jobs));
+    k_dense_prep<false><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+    COUNT_LAUNCH();
     launch_timer_begin(m->stream);
-    if (use_reg_kernel())
-        k_dense_reg<false><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
-                                                                               d_partials, m->bwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
-    else
-        k_dense_warp<false><<<grid, WT_WARPS * 32, WT_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, n_jobs, s, d_bases, d_desc,
-                                                                                d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks,
-                                                                                fast_span(m->lin), d_worklist, jpc);
+    k_dense_reg<false><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+                                                                           d_partials, m->bwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
     COUNT_LAUNCH();
     k_dense_bwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_active,
                                                                              pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks, d_worklist);

@@ -360,11 +360,8 @@ int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* 
     ST_TRY(build_plan(m->fwd, N, m->par_off, m->par_node, m->par_eid));
     ST_TRY(build_plan(m->bwd, N, m->chi_off, m->chi_node, m->chi_eid));
     {   // layout of the two-rows-per-launch forward kernel ; a graph too branchy for 12-hop tiles simply goes without it
-        const char* e = getenv("DBGPHMM_DENSE_FUSE");
-        if (!(e && e[0] == '0')) {
-            if (build_plan(m->fwd2, N, m->par_off, m->par_node, m->par_eid, 2 * HALO_HOPS) != DBGPHMM_OK) free_plan(m->fwd2);
-            if (build_plan(m->bwd2, N, m->chi_off, m->chi_node, m->chi_eid, 2 * HALO_HOPS) != DBGPHMM_OK) free_plan(m->bwd2);
-        }
+        if (build_plan(m->fwd2, N, m->par_off, m->par_node, m->par_eid, 2 * HALO_HOPS) != DBGPHMM_OK) free_plan(m->fwd2);
+        if (build_plan(m->bwd2, N, m->chi_off, m->chi_node, m->chi_eid, 2 * HALO_HOPS) != DBGPHMM_OK) free_plan(m->bwd2);
     }
     return DBGPHMM_OK;
 }

@@ -934,8 +934,7 @@ static int sparse_launch(dbgphmm_model* m, cudaStream_t st, uint32_t grid, const
     const uint32_t hcap = hcap_of(cap);
     const size_t smem = sparse_smem_bytes(cap, hcap);
     if (smem > 200 * 1024) { dbg_set_error("sparse_run: capacity too large for shared memory"); return DBGPHMM_ERR_INVALID; }
-    int threads = sparse_threads(cap);
-    if (const char* e = getenv("DBGPHMM_SPARSE_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) threads = t; }
+    const int threads = sparse_threads(cap);
     if (dir == 0) k_sparse<0><<<grid, threads, smem, st>>>(G, m->lin, d_jobs, io, cap, hcap, role);
     else k_sparse<1><<<grid, threads, smem, st>>>(G, m->lin, d_jobs, io, cap, hcap, role);
     COUNT_LAUNCH();
@@ -947,13 +946,9 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
     if (n_jobs == 0) return DBGPHMM_OK;
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of, m->d_par_rec, m->d_chi_rec};
-    {   // the kernel is latency-bound: as many resident jobs per SM as shared memory allows
-        int carve = 100;
-        if (const char* e = getenv("DBGPHMM_SPARSE_CARVEOUT")) carve = atoi(e);
-        if (carve < 10) carve = 10; if (carve > 100) carve = 100;
-        cudaFuncSetAttribute(k_sparse<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(k_sparse<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    }
+    // the kernel is latency-bound: as many resident jobs per SM as shared memory allows
+    cudaFuncSetAttribute(k_sparse<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_sparse<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     SparseIO io = io_in;
     if (!rescue_cap || !io.rq_ctl) {
         io.rq_ctl = nullptr;
