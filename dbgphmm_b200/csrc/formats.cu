@@ -11,7 +11,10 @@
 #include <charconv>
 #include <cstdio>
 #include <cstdlib>
+#include <cctype>
+#include <cmath>
 #include <cstring>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -421,4 +424,306 @@ extern "C" int dbgphmm_mappings_to_map_file(const dbgphmm_mappings* mp, const db
     std::string s;
     ST_TRY(map_text(mp, reads, d, &s));
     return write_file(path, s);
+} ABI_CATCH
+
+// ------------------------------------------------------------------------------------------------ dataset JSON
+// Dataset::to_json_file / from_json_file (e2e.rs:31-52,123-130): serde_json of
+//   { "genome": ["L:ACGT...", ...]                      Genome(Vec<StyledSequence>), Display "{style}:{bases}"  collection.rs:371-379,460-464
+//     "genome_size": usize,
+//     "reads": { "reads": ["ACGT:+:0-12,0-13,I,0-15", ...] }   PositionedReads: "{bases}:{+|-}:{origins}", an origin is
+//                                                               "{hap}-{pos}" or "I"  (collection.rs:711-757, genome_graph.rs:117-151)
+//     "phmm_params": { "p_mismatch": "-6.907755278982137(0.0010)", ..., "n_active_nodes": 40, "active_node_max_ratio": 30.0,
+//                      "n_warmup": 50, "warmup_threshold": 200, "n_max_gaps": 4 } }   Prob Display "{ln p}({p:.4})"  prob.rs:158-169
+// The reads of a dataset are what the hot path consumes (dbgphmm_dataset_reads -> dbgphmm_reads); genome, origins and parameters travel
+// with them so that a dataset written by a dbgphmm run feeds the B200 path and a dataset written here loads in the reference.
+struct dbgphmm_dataset {
+    std::vector<std::string> hap; std::vector<char> style;
+    uint64_t genome_size = 0;
+    std::vector<std::string> read; std::vector<uint8_t> revcomp;
+    std::vector<std::vector<int64_t>> onode; std::vector<std::vector<uint64_t>> opos;   // per base: haplotype (-1 = Ins) and position
+    dbgphmm_params params;
+};
+
+namespace {
+struct JVal {   // just enough JSON for the schema above
+    enum Kind { NUL, BOOL, NUM, STR, ARR, OBJ } kind = NUL;
+    double num = 0; bool b = false; std::string str; std::string raw;
+    std::vector<JVal> arr; std::vector<std::pair<std::string, JVal>> obj;
+    const JVal* get(const char* k) const { for (auto& kv : obj) if (kv.first == k) return &kv.second; return nullptr; }
+};
+struct JParser {
+    const char* p; const char* e; std::string err;
+    void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+    bool fail(const char* m) { if (err.empty()) err = m; return false; }
+    bool str(std::string* out) {
+        if (p >= e || *p != '"') return fail("expected a string");
+        p++; out->clear();
+        while (p < e && *p != '"') {
+            if (*p == '\\') {
+                if (++p >= e) return fail("bad escape");
+                switch (*p) {
+                    case 'n': *out += '\n'; break; case 't': *out += '\t'; break; case 'r': *out += '\r'; break;
+                    case 'b': *out += '\b'; break; case 'f': *out += '\f'; break;
+                    case 'u': { if (e - p < 5) return fail("bad \\u escape"); unsigned c = (unsigned)strtoul(std::string(p + 1, 4).c_str(), nullptr, 16); *out += (char)(c & 0x7f); p += 4; break; }
+                    default: *out += *p;
+                }
+                p++;
+            } else *out += *p++;
+        }
+        if (p >= e) return fail("unterminated string");
+        p++;
+        return true;
+    }
+    bool val(JVal* v, int depth = 0) {
+        if (depth > 32) return fail("nesting too deep");
+        ws();
+        if (p >= e) return fail("unexpected end");
+        if (*p == '{') {
+            v->kind = JVal::OBJ; p++; ws();
+            if (p < e && *p == '}') { p++; return true; }
+            for (;;) {
+                ws(); std::string k; if (!str(&k)) return false;
+                ws(); if (p >= e || *p != ':') return fail("expected ':'"); p++;
+                JVal c; if (!val(&c, depth + 1)) return false;
+                v->obj.emplace_back(std::move(k), std::move(c));
+                ws(); if (p < e && *p == ',') { p++; continue; }
+                if (p < e && *p == '}') { p++; return true; }
+                return fail("expected ',' or '}'");
+            }
+        }
+        if (*p == '[') {
+            v->kind = JVal::ARR; p++; ws();
+            if (p < e && *p == ']') { p++; return true; }
+            for (;;) {
+                JVal c; if (!val(&c, depth + 1)) return false;
+                v->arr.push_back(std::move(c));
+                ws(); if (p < e && *p == ',') { p++; continue; }
+                if (p < e && *p == ']') { p++; return true; }
+                return fail("expected ',' or ']'");
+            }
+        }
+        if (*p == '"') { v->kind = JVal::STR; return str(&v->str); }
+        if (!strncmp(p, "true", std::min<size_t>(4, e - p)) && e - p >= 4) { v->kind = JVal::BOOL; v->b = true; p += 4; return true; }
+        if (!strncmp(p, "false", std::min<size_t>(5, e - p)) && e - p >= 5) { v->kind = JVal::BOOL; v->b = false; p += 5; return true; }
+        if (!strncmp(p, "null", std::min<size_t>(4, e - p)) && e - p >= 4) { v->kind = JVal::NUL; p += 4; return true; }
+        const char* q = p;
+        while (q < e && (isdigit((unsigned char)*q) || *q == '-' || *q == '+' || *q == '.' || *q == 'e' || *q == 'E')) q++;
+        if (q == p) return fail("unexpected character");
+        v->kind = JVal::NUM; v->raw.assign(p, q);
+        char* end = nullptr; v->num = strtod(v->raw.c_str(), &end);
+        if (*end) return fail("bad number");
+        p = q;
+        return true;
+    }
+};
+bool parse_u64(const std::string& s, uint64_t* v) {
+    if (s.empty() || s.size() > 20) return false;
+    for (char c : s) if (!isdigit((unsigned char)c)) return false;
+    *v = strtoull(s.c_str(), nullptr, 10);
+    return true;
+}
+// Prob: "{ln p}({p:.4})" (prob.rs:158-169) ; a bare number is accepted too
+bool parse_prob(const JVal& v, double* out) {
+    if (v.kind == JVal::NUM) { *out = v.num; return true; }
+    if (v.kind != JVal::STR) return false;
+    const size_t par = v.str.find('(');
+    return parse_f64(par == std::string::npos ? v.str : v.str.substr(0, par), out);
+}
+bool json_u64(const JVal* v, uint64_t* out) { return v && v->kind == JVal::NUM && parse_u64(v->raw, out); }
+void json_str(std::string& s, const std::string& t) {
+    s += '"';
+    for (char c : t) { if (c == '"' || c == '\\') s += '\\'; s += c; }
+    s += '"';
+}
+int dataset_parse(const char* text, uint64_t len, dbgphmm_dataset** out) {
+    if (!text || !out) { dbg_set_error("dataset_from_json: bad argument"); return DBGPHMM_ERR_INVALID; }
+    JParser P{text, text + len, ""};
+    JVal root;
+    if (!P.val(&root) || root.kind != JVal::OBJ) { dbg_set_error("dataset JSON: " + (P.err.empty() ? std::string("not an object") : P.err)); return DBGPHMM_ERR_INVALID; }
+    P.ws();
+    if (P.p != P.e) { dbg_set_error("dataset JSON: trailing characters"); return DBGPHMM_ERR_INVALID; }
+    std::unique_ptr<dbgphmm_dataset> d(new dbgphmm_dataset());
+    const JVal* g = root.get("genome");
+    if (!g || g->kind != JVal::ARR) { dbg_set_error("dataset JSON: genome must be an array of styled sequences"); return DBGPHMM_ERR_INVALID; }
+    for (auto& h : g->arr) {
+        if (h.kind != JVal::STR || h.str.size() < 2 || h.str[1] != ':' || !strchr("CLF", h.str[0])) { dbg_set_error("dataset JSON: a styled sequence is \"C|L|F:bases\" (collection.rs:371-391)"); return DBGPHMM_ERR_INVALID; }
+        d->style.push_back(h.str[0]); d->hap.push_back(h.str.substr(2));
+    }
+    if (!json_u64(root.get("genome_size"), &d->genome_size)) { dbg_set_error("dataset JSON: genome_size"); return DBGPHMM_ERR_INVALID; }
+    const JVal* rc = root.get("reads");
+    const JVal* rs = rc && rc->kind == JVal::OBJ ? rc->get("reads") : nullptr;
+    if (!rs || rs->kind != JVal::ARR) { dbg_set_error("dataset JSON: reads.reads must be an array"); return DBGPHMM_ERR_INVALID; }
+    for (auto& r : rs->arr) {
+        if (r.kind != JVal::STR) { dbg_set_error("dataset JSON: a read is a string"); return DBGPHMM_ERR_INVALID; }
+        // PositionedSequence "{bases}:{+|-}:{origins}" ; a plain sequence (Reads, collection.rs:811-819) is accepted without origins
+        const size_t c1 = r.str.find(':');
+        std::string bases = c1 == std::string::npos ? r.str : r.str.substr(0, c1);
+        for (char b : bases) if (b != 'A' && b != 'C' && b != 'G' && b != 'T') { dbg_set_error("dataset JSON: read bases must be uppercase ACGT (collection.rs:236-249)"); return DBGPHMM_ERR_INVALID; }
+        std::vector<int64_t> on; std::vector<uint64_t> op; uint8_t rev = 0;
+        if (c1 != std::string::npos) {
+            const size_t c2 = r.str.find(':', c1 + 1);
+            if (c2 == std::string::npos || c2 != c1 + 2 || (r.str[c1 + 1] != '+' && r.str[c1 + 1] != '-')) { dbg_set_error("dataset JSON: a positioned read is \"bases:+|-:origins\" (collection.rs:732-757)"); return DBGPHMM_ERR_INVALID; }
+            rev = r.str[c1 + 1] == '-';
+            size_t a = c2 + 1;
+            while (a <= r.str.size() && !(a == r.str.size() && bases.empty())) {
+                size_t b = r.str.find(',', a); if (b == std::string::npos) b = r.str.size();
+                const std::string o = r.str.substr(a, b - a);
+                const size_t dash = o.find('-');
+                if (dash == std::string::npos) { on.push_back(-1); op.push_back(0); }   // "I" (anything without a dash parses as Ins, genome_graph.rs:147-149)
+                else {
+                    uint64_t hn, hp;
+                    if (!parse_u64(o.substr(0, dash), &hn) || !parse_u64(o.substr(dash + 1), &hp)) { dbg_set_error("dataset JSON: an origin is \"hap-pos\" or \"I\""); return DBGPHMM_ERR_INVALID; }
+                    on.push_back((int64_t)hn); op.push_back(hp);
+                }
+                if (b == r.str.size()) break;
+                a = b + 1;
+            }
+            if (on.size() != bases.size()) { dbg_set_error("dataset JSON: one origin per base (collection.rs:522 asserts it)"); return DBGPHMM_ERR_INVALID; }
+        } else { on.assign(bases.size(), -1); op.assign(bases.size(), 0); }
+        d->read.push_back(std::move(bases)); d->revcomp.push_back(rev); d->onode.push_back(std::move(on)); d->opos.push_back(std::move(op));
+    }
+    const JVal* pp = root.get("phmm_params");
+    if (!pp || pp->kind != JVal::OBJ) { dbg_set_error("dataset JSON: phmm_params"); return DBGPHMM_ERR_INVALID; }
+    dbgphmm_params& q = d->params;
+    struct { const char* name; double* dst; } probs[] = {
+        {"p_mismatch", &q.p_mismatch}, {"p_match", &q.p_match}, {"p_random", &q.p_random}, {"p_gap_open", &q.p_gap_open}, {"p_gap_ext", &q.p_gap_ext},
+        {"p_end", &q.p_end}, {"p_MM", &q.p_MM}, {"p_IM", &q.p_IM}, {"p_DM", &q.p_DM}, {"p_MI", &q.p_MI}, {"p_II", &q.p_II}, {"p_DI", &q.p_DI},
+        {"p_MD", &q.p_MD}, {"p_ID", &q.p_ID}, {"p_DD", &q.p_DD}};
+    for (auto& f : probs) {
+        const JVal* v = pp->get(f.name);
+        if (!v || !parse_prob(*v, f.dst)) { dbg_set_error(std::string("dataset JSON: phmm_params.") + f.name); return DBGPHMM_ERR_INVALID; }
+    }
+    uint64_t u = 0;
+    if (!json_u64(pp->get("n_active_nodes"), &u)) { dbg_set_error("dataset JSON: phmm_params.n_active_nodes"); return DBGPHMM_ERR_INVALID; } q.n_active_nodes = (uint32_t)u;
+    if (!json_u64(pp->get("n_warmup"), &u)) { dbg_set_error("dataset JSON: phmm_params.n_warmup"); return DBGPHMM_ERR_INVALID; } q.n_warmup = (uint32_t)u;
+    if (!json_u64(pp->get("n_max_gaps"), &u)) { dbg_set_error("dataset JSON: phmm_params.n_max_gaps"); return DBGPHMM_ERR_INVALID; } q.n_max_gaps = (uint32_t)u;
+    q.warmup_threshold = DBGPHMM_MAX_ACTIVE_NODES / 2;   // #[serde(default = "default_warmup_threshold")], params.rs:60-67
+    if (pp->get("warmup_threshold")) { if (!json_u64(pp->get("warmup_threshold"), &u)) { dbg_set_error("dataset JSON: phmm_params.warmup_threshold"); return DBGPHMM_ERR_INVALID; } q.warmup_threshold = (uint32_t)u; }
+    const JVal* ar = pp->get("active_node_max_ratio");
+    if (!ar || ar->kind != JVal::NUM) { dbg_set_error("dataset JSON: phmm_params.active_node_max_ratio"); return DBGPHMM_ERR_INVALID; }
+    q.active_node_max_ratio = ar->num;
+    *out = d.release();
+    return DBGPHMM_OK;
+}
+void append_prob(std::string& s, double lnp) {   // Prob Display: "{}({:.4})" of (ln p, p)
+    s += '"'; append_f64(s, lnp);
+    char buf[64]; snprintf(buf, sizeof(buf), "(%.4f)", std::exp(lnp));
+    s += buf; s += '"';
+}
+void append_json_f64(std::string& s, double v) {   // serde_json: shortest round-trip digits, always with a fraction or exponent
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    std::string t(buf, r.ptr);
+    if (t.find_first_of(".eE") == std::string::npos) t += ".0";
+    s += t;
+}
+std::string dataset_text(const dbgphmm_dataset* d) {
+    std::string s = "{\"genome\":[";
+    for (size_t i = 0; i < d->hap.size(); i++) { if (i) s += ','; json_str(s, std::string(1, d->style[i]) + ":" + d->hap[i]); }
+    s += "],\"genome_size\":" + std::to_string(d->genome_size) + ",\"reads\":{\"reads\":[";
+    for (size_t i = 0; i < d->read.size(); i++) {
+        if (i) s += ',';
+        std::string r = d->read[i] + ":" + (d->revcomp[i] ? "-" : "+") + ":";
+        for (size_t j = 0; j < d->onode[i].size(); j++) {
+            if (j) r += ',';
+            if (d->onode[i][j] < 0) r += 'I'; else r += std::to_string(d->onode[i][j]) + "-" + std::to_string(d->opos[i][j]);
+        }
+        json_str(s, r);
+    }
+    s += "]},\"phmm_params\":{";
+    const dbgphmm_params& q = d->params;
+    const std::pair<const char*, double> probs[] = {{"p_mismatch", q.p_mismatch}, {"p_match", q.p_match}, {"p_random", q.p_random}, {"p_gap_open", q.p_gap_open},
+        {"p_gap_ext", q.p_gap_ext}, {"p_end", q.p_end}, {"p_MM", q.p_MM}, {"p_IM", q.p_IM}, {"p_DM", q.p_DM}, {"p_MI", q.p_MI}, {"p_II", q.p_II}, {"p_DI", q.p_DI},
+        {"p_MD", q.p_MD}, {"p_ID", q.p_ID}, {"p_DD", q.p_DD}};
+    for (auto& f : probs) { s += '"'; s += f.first; s += "\":"; append_prob(s, f.second); s += ','; }
+    s += "\"n_active_nodes\":" + std::to_string(q.n_active_nodes) + ",\"active_node_max_ratio\":";
+    append_json_f64(s, q.active_node_max_ratio);
+    s += ",\"n_warmup\":" + std::to_string(q.n_warmup) + ",\"warmup_threshold\":" + std::to_string(q.warmup_threshold) + ",\"n_max_gaps\":" + std::to_string(q.n_max_gaps) + "}}";
+    return s;
+}
+}  // namespace
+
+extern "C" int dbgphmm_dataset_from_json_text(const char* text, uint64_t len, dbgphmm_dataset** out) try { return dataset_parse(text, len, out); } ABI_CATCH
+extern "C" int dbgphmm_dataset_from_json_file(const char* path, dbgphmm_dataset** out) try {
+    if (!path || !out) { dbg_set_error("dataset_from_json_file: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::string text;
+    ST_TRY(read_file(path, &text));
+    return dataset_parse(text.data(), text.size(), out);
+} ABI_CATCH
+extern "C" void dbgphmm_dataset_destroy(dbgphmm_dataset* d) { delete d; }
+extern "C" int dbgphmm_dataset_create(uint32_t n_haps, const uint64_t* hap_off, const uint8_t* hap_bases, const uint8_t* hap_style, uint64_t genome_size,
+                                      uint64_t n_reads, const uint64_t* read_off, const uint8_t* read_bases, const uint8_t* read_revcomp, const int64_t* origin_hap,
+                                      const uint64_t* origin_pos, const dbgphmm_params* params, dbgphmm_dataset** out) try {
+    if (!out || !params || (n_haps && (!hap_off || !hap_style)) || (n_reads && !read_off)) { dbg_set_error("dataset_create: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::unique_ptr<dbgphmm_dataset> d(new dbgphmm_dataset());
+    for (uint32_t h = 0; h < n_haps; h++) {
+        if (hap_off[h + 1] < hap_off[h] || !strchr("CLF", (char)hap_style[h]) || !hap_style[h]) { dbg_set_error("dataset_create: haplotype offsets / styles ('C', 'L' or 'F')"); return DBGPHMM_ERR_INVALID; }
+        d->hap.emplace_back((const char*)hap_bases + hap_off[h], (const char*)hap_bases + hap_off[h + 1]); d->style.push_back((char)hap_style[h]);
+    }
+    d->genome_size = genome_size;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        if (read_off[r + 1] < read_off[r]) { dbg_set_error("dataset_create: read offsets not monotone"); return DBGPHMM_ERR_INVALID; }
+        const uint64_t a = read_off[r], b = read_off[r + 1];
+        std::string bases((const char*)read_bases + a, (const char*)read_bases + b);
+        for (char c : bases) if (c != 'A' && c != 'C' && c != 'G' && c != 'T') { dbg_set_error("dataset_create: read bases must be uppercase ACGT"); return DBGPHMM_ERR_INVALID; }
+        std::vector<int64_t> on(b - a, -1); std::vector<uint64_t> op(b - a, 0);
+        if (origin_hap && origin_pos) for (uint64_t j = a; j < b; j++) { on[j - a] = origin_hap[j] < 0 ? -1 : origin_hap[j]; op[j - a] = origin_hap[j] < 0 ? 0 : origin_pos[j]; }
+        d->read.push_back(std::move(bases)); d->revcomp.push_back(read_revcomp ? read_revcomp[r] != 0 : 0); d->onode.push_back(std::move(on)); d->opos.push_back(std::move(op));
+    }
+    d->params = *params;
+    *out = d.release();
+    return DBGPHMM_OK;
+} ABI_CATCH
+extern "C" int dbgphmm_dataset_sizes(const dbgphmm_dataset* d, uint64_t sizes[5]) try {
+    if (!d || !sizes) { dbg_set_error("dataset_sizes: bad argument"); return DBGPHMM_ERR_INVALID; }
+    sizes[0] = d->hap.size(); sizes[1] = 0; for (auto& h : d->hap) sizes[1] += h.size();
+    sizes[2] = d->read.size(); sizes[3] = 0; for (auto& r : d->read) sizes[3] += r.size();
+    sizes[4] = d->genome_size;
+    return DBGPHMM_OK;
+} ABI_CATCH
+extern "C" int dbgphmm_dataset_genome(const dbgphmm_dataset* d, uint64_t* hap_off, uint8_t* bases, uint8_t* style) try {
+    if (!d) { dbg_set_error("dataset_genome: bad argument"); return DBGPHMM_ERR_INVALID; }
+    uint64_t o = 0;
+    for (size_t h = 0; h < d->hap.size(); h++) {
+        if (hap_off) hap_off[h] = o;
+        if (bases) memcpy(bases + o, d->hap[h].data(), d->hap[h].size());
+        if (style) style[h] = (uint8_t)d->style[h];
+        o += d->hap[h].size();
+    }
+    if (hap_off) hap_off[d->hap.size()] = o;
+    return DBGPHMM_OK;
+} ABI_CATCH
+extern "C" int dbgphmm_dataset_reads(const dbgphmm_dataset* d, dbgphmm_reads** out) try {
+    if (!d || !out) { dbg_set_error("dataset_reads: bad argument"); return DBGPHMM_ERR_INVALID; }
+    std::vector<uint64_t> off(d->read.size() + 1, 0); std::vector<uint8_t> bases;
+    for (size_t r = 0; r < d->read.size(); r++) { bases.insert(bases.end(), d->read[r].begin(), d->read[r].end()); off[r + 1] = bases.size(); }
+    return dbgphmm_reads_create(d->read.size(), off.data(), bases.empty() ? nullptr : bases.data(), out);
+} ABI_CATCH
+extern "C" int dbgphmm_dataset_read_origins(const dbgphmm_dataset* d, uint64_t* read_off, uint8_t* bases, uint8_t* revcomp, int64_t* origin_hap, uint64_t* origin_pos) try {
+    if (!d) { dbg_set_error("dataset_read_origins: bad argument"); return DBGPHMM_ERR_INVALID; }
+    uint64_t o = 0;
+    for (size_t r = 0; r < d->read.size(); r++) {
+        if (read_off) read_off[r] = o;
+        if (revcomp) revcomp[r] = d->revcomp[r];
+        for (size_t j = 0; j < d->read[r].size(); j++, o++) {
+            if (bases) bases[o] = (uint8_t)d->read[r][j];
+            if (origin_hap) origin_hap[o] = d->onode[r][j];
+            if (origin_pos) origin_pos[o] = d->opos[r][j];
+        }
+    }
+    if (read_off) read_off[d->read.size()] = o;
+    return DBGPHMM_OK;
+} ABI_CATCH
+extern "C" int dbgphmm_dataset_params(const dbgphmm_dataset* d, dbgphmm_params* out) try {
+    if (!d || !out) { dbg_set_error("dataset_params: bad argument"); return DBGPHMM_ERR_INVALID; }
+    *out = d->params;
+    return DBGPHMM_OK;
+} ABI_CATCH
+extern "C" int dbgphmm_dataset_to_json_text(const dbgphmm_dataset* d, char* buf, uint64_t cap, uint64_t* needed) try {
+    if (!d) { dbg_set_error("dataset_to_json_text: bad argument"); return DBGPHMM_ERR_INVALID; }
+    return copy_out(dataset_text(d), buf, cap, needed);
+} ABI_CATCH
+extern "C" int dbgphmm_dataset_to_json_file(const dbgphmm_dataset* d, const char* path) try {
+    if (!d || !path) { dbg_set_error("dataset_to_json_file: bad argument"); return DBGPHMM_ERR_INVALID; }
+    return write_file(path, dataset_text(d));
 } ABI_CATCH

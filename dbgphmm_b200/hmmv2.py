@@ -54,6 +54,9 @@ SYMBOLS = [
     "dbgphmm_dbg_to_model", "dbgphmm_mappings_from_map_text", "dbgphmm_mappings_from_map_file", "dbgphmm_mappings_to_map_text",
     "dbgphmm_mappings_to_map_file",
     "dbgphmm_dbg_genome_size", "dbgphmm_dbg_n_euler_circuits", "dbgphmm_euler_circuit_count", "dbgphmm_prior_normal",
+    "dbgphmm_dataset_from_json_text", "dbgphmm_dataset_from_json_file", "dbgphmm_dataset_create", "dbgphmm_dataset_destroy", "dbgphmm_dataset_sizes",
+    "dbgphmm_dataset_genome", "dbgphmm_dataset_reads", "dbgphmm_dataset_read_origins", "dbgphmm_dataset_params", "dbgphmm_dataset_to_json_text",
+    "dbgphmm_dataset_to_json_file",
 ]
 
 _lib = None
@@ -129,6 +132,17 @@ def lib():
     L.dbgphmm_dbg_n_euler_circuits.argtypes = [vp, u32, vp, vp]
     L.dbgphmm_euler_circuit_count.argtypes = [u32, u64, vp, vp, vp, ci, C.POINTER(dbl)]
     L.dbgphmm_prior_normal.argtypes = [dbl, dbl, dbl, C.POINTER(dbl)]
+    L.dbgphmm_dataset_from_json_text.argtypes = [C.c_char_p, u64, C.POINTER(vp)]
+    L.dbgphmm_dataset_from_json_file.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.dbgphmm_dataset_create.argtypes = [u32, vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, PP, C.POINTER(vp)]
+    L.dbgphmm_dataset_destroy.argtypes = [vp]
+    L.dbgphmm_dataset_sizes.argtypes = [vp, vp]
+    L.dbgphmm_dataset_genome.argtypes = [vp, vp, vp, vp]
+    L.dbgphmm_dataset_reads.argtypes = [vp, C.POINTER(vp)]
+    L.dbgphmm_dataset_read_origins.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.dbgphmm_dataset_params.argtypes = [vp, PP]
+    L.dbgphmm_dataset_to_json_text.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.dbgphmm_dataset_to_json_file.argtypes = [vp, C.c_char_p]
     for s in SYMBOLS:
         getattr(L, s)  # fail loudly if the library does not export a declared symbol
     _lib = L
@@ -665,6 +679,104 @@ def euler_circuit_count(n_nodes, edges, allow_multiple_component):
     v = C.c_double()
     _check(lib().dbgphmm_euler_circuit_count(n_nodes, len(e), _p(s), _p(t), _p(w), int(allow_multiple_component), C.byref(v)))
     return v.value
+
+
+class Dataset:
+    """e2e::Dataset (e2e.rs:31-130): genome, genome_size, positioned reads and the PHMM parameters they were sampled with, in the
+    reference's JSON form.  `reads()` is the ReadCollection the hot path takes."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dbgphmm_dataset_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def from_json_str(text):
+        b = text.encode() if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        _check(lib().dbgphmm_dataset_from_json_text(b, len(b), C.byref(h)))
+        return Dataset(h)
+
+    @staticmethod
+    def from_json_file(path):
+        h = C.c_void_p()
+        _check(lib().dbgphmm_dataset_from_json_file(os.fsencode(path), C.byref(h)))
+        return Dataset(h)
+
+    @staticmethod
+    def new(haplotypes, styles, reads, param, genome_size=None, revcomp=None, origins=None):
+        """haplotypes: sequences; styles: 'C' / 'L' / 'F' per haplotype; reads: sequences; origins: per read a list of (hap, pos) or
+        None for an inserted base (GenomeGraphPos, genome_graph.rs:60-115)."""
+        haps = [_bases(h) for h in haplotypes]
+        hoff = np.zeros(len(haps) + 1, np.uint64); hoff[1:] = np.cumsum([len(h) for h in haps])
+        hb = np.ascontiguousarray(np.concatenate(haps)) if haps else np.zeros(0, np.uint8)
+        st = np.frombuffer("".join(styles).encode(), np.uint8).copy()
+        rs = [_bases(r) for r in reads]
+        roff = np.zeros(len(rs) + 1, np.uint64); roff[1:] = np.cumsum([len(r) for r in rs])
+        rb = np.ascontiguousarray(np.concatenate(rs)) if rs else np.zeros(0, np.uint8)
+        rv = None if revcomp is None else np.ascontiguousarray(revcomp, np.uint8)
+        oh = op = None
+        if origins is not None:
+            oh = np.array([(-1 if o is None else o[0]) for r in origins for o in r], np.int64)
+            op = np.array([(0 if o is None else o[1]) for r in origins for o in r], np.uint64)
+            assert len(oh) == len(rb)
+        gs = int(hoff[-1]) if genome_size is None else int(genome_size)
+        h = C.c_void_p()
+        q = param.copy()
+        _check(lib().dbgphmm_dataset_create(len(haps), _p(hoff), _p(hb), _p(st), gs, len(rs), _p(roff), _p(rb), _p(rv), _p(oh), _p(op), C.byref(q), C.byref(h)))
+        return Dataset(h)
+
+    def _sizes(self):
+        s = np.zeros(5, np.uint64)
+        _check(lib().dbgphmm_dataset_sizes(self._h, _p(s)))
+        return [int(x) for x in s]
+
+    def genome_size(self):
+        return self._sizes()[4]
+
+    def genome(self):
+        """-> list of (style, bases)"""
+        n, nb = self._sizes()[:2]
+        off = np.zeros(n + 1, np.uint64); b = np.zeros(nb, np.uint8); st = np.zeros(n, np.uint8)
+        _check(lib().dbgphmm_dataset_genome(self._h, _p(off), _p(b), _p(st)))
+        return [(chr(st[i]), b[int(off[i]):int(off[i + 1])].tobytes()) for i in range(n)]
+
+    def reads(self):
+        """-> Reads (the sequences; positions are dropped like ReadCollection::to_fasta does)"""
+        _, _, n, nb, _ = self._sizes()
+        off = np.zeros(n + 1, np.uint64); b = np.zeros(nb, np.uint8)
+        _check(lib().dbgphmm_dataset_read_origins(self._h, _p(off), _p(b), None, None, None))
+        return Reads([b[int(off[i]):int(off[i + 1])] for i in range(n)])
+
+    def read_origins(self):
+        """-> (revcomp flags, per read a list of (hap, pos) or None)"""
+        _, _, n, nb, _ = self._sizes()
+        off = np.zeros(n + 1, np.uint64); rv = np.zeros(n, np.uint8); oh = np.zeros(nb, np.int64); op = np.zeros(nb, np.uint64)
+        _check(lib().dbgphmm_dataset_read_origins(self._h, _p(off), None, _p(rv), _p(oh), _p(op)))
+        out = [[None if oh[j] < 0 else (int(oh[j]), int(op[j])) for j in range(int(off[i]), int(off[i + 1]))] for i in range(n)]
+        return [bool(x) for x in rv], out
+
+    def params(self):
+        q = Params()
+        _check(lib().dbgphmm_dataset_params(self._h, C.byref(q)))
+        return q
+
+    def coverage(self):
+        """Dataset::coverage (e2e.rs:72-74): total bases of the reads / genome_size"""
+        return self._sizes()[3] / max(1, self.genome_size())
+
+    def to_json_string(self):
+        need = C.c_uint64(0)
+        _check(lib().dbgphmm_dataset_to_json_text(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(int(need.value))
+        _check(lib().dbgphmm_dataset_to_json_text(self._h, buf, need.value, C.byref(need)))
+        return buf.raw[:need.value].decode()
+
+    def to_json_file(self, path):
+        _check(lib().dbgphmm_dataset_to_json_file(self._h, os.fsencode(path)))
 
 
 class MultiDbg:

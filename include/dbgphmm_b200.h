@@ -243,6 +243,27 @@ int dbgphmm_mappings_to_map_text(const dbgphmm_mappings* mp, const dbgphmm_reads
                                  uint64_t* needed);
 int dbgphmm_mappings_to_map_file(const dbgphmm_mappings* mp, const dbgphmm_reads* reads, const dbgphmm_dbg* d, const char* path);
 
+/* Dataset JSON (Dataset::to_json_file / from_json_file, e2e.rs:31-52,123-130: serde_json of genome, genome_size, positioned reads and the
+ * PHMM parameters they were sampled with).  Styled sequences are "C|L|F:bases" (collection.rs:371-391,460-464), positioned reads
+ * "bases:+|-:origins" with an origin "hap-pos" or "I" (collection.rs:711-757, genome_graph.rs:117-151), probabilities "{ln p}({p:.4})"
+ * (prob.rs:158-169).  A path ending in .gz is gzip.  dataset_reads hands the read set to the hot path. */
+typedef struct dbgphmm_dataset dbgphmm_dataset;
+int dbgphmm_dataset_from_json_text(const char* text, uint64_t len, dbgphmm_dataset** out);
+int dbgphmm_dataset_from_json_file(const char* path, dbgphmm_dataset** out);
+/* hap_style[h] in {'C' circular, 'L' linear, 'F' linear fragment}; read_revcomp, origin_hap (-1 = inserted base), origin_pos may be NULL */
+int dbgphmm_dataset_create(uint32_t n_haps, const uint64_t* hap_off, const uint8_t* hap_bases, const uint8_t* hap_style, uint64_t genome_size,
+                           uint64_t n_reads, const uint64_t* read_off, const uint8_t* read_bases, const uint8_t* read_revcomp, const int64_t* origin_hap,
+                           const uint64_t* origin_pos, const dbgphmm_params* params, dbgphmm_dataset** out);
+void dbgphmm_dataset_destroy(dbgphmm_dataset* d);
+/* sizes = {haplotypes, genome bases, reads, read bases, genome_size field} */
+int dbgphmm_dataset_sizes(const dbgphmm_dataset* d, uint64_t sizes[5]);
+int dbgphmm_dataset_genome(const dbgphmm_dataset* d, uint64_t* hap_off, uint8_t* bases, uint8_t* style);
+int dbgphmm_dataset_reads(const dbgphmm_dataset* d, dbgphmm_reads** out);
+int dbgphmm_dataset_read_origins(const dbgphmm_dataset* d, uint64_t* read_off, uint8_t* bases, uint8_t* revcomp, int64_t* origin_hap, uint64_t* origin_pos);
+int dbgphmm_dataset_params(const dbgphmm_dataset* d, dbgphmm_params* out);
+int dbgphmm_dataset_to_json_text(const dbgphmm_dataset* d, char* buf, uint64_t cap, uint64_t* needed);
+int dbgphmm_dataset_to_json_file(const dbgphmm_dataset* d, const char* path);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
 uint64_t dbgphmm_launch_count(int reset);

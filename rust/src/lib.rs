@@ -22,6 +22,7 @@ pub struct dbgphmm_params {
 #[repr(C)] pub struct dbgphmm_mappings { _p: [u8; 0] }
 #[repr(C)] pub struct dbgphmm_tables { _p: [u8; 0] }
 #[repr(C)] pub struct dbgphmm_dbg { _p: [u8; 0] }
+#[repr(C)] pub struct dbgphmm_dataset { _p: [u8; 0] }
 
 pub const MAX_ACTIVE_NODES: usize = 400; // hmmv2/table.rs:22
 
@@ -108,6 +109,21 @@ extern "C" {
     pub fn dbgphmm_mappings_to_map_text(mp: *const dbgphmm_mappings, reads: *const dbgphmm_reads, d: *const dbgphmm_dbg, buf: *mut c_char,
                                         cap: u64, needed: *mut u64) -> c_int;
     pub fn dbgphmm_mappings_to_map_file(mp: *const dbgphmm_mappings, reads: *const dbgphmm_reads, d: *const dbgphmm_dbg, path: *const c_char) -> c_int;
+    // dataset JSON (Dataset::to_json_file / from_json_file, e2e.rs:123-130)
+    pub fn dbgphmm_dataset_from_json_text(text: *const c_char, len: u64, out: *mut *mut dbgphmm_dataset) -> c_int;
+    pub fn dbgphmm_dataset_from_json_file(path: *const c_char, out: *mut *mut dbgphmm_dataset) -> c_int;
+    pub fn dbgphmm_dataset_create(n_haps: u32, hap_off: *const u64, hap_bases: *const u8, hap_style: *const u8, genome_size: u64,
+                                  n_reads: u64, read_off: *const u64, read_bases: *const u8, read_revcomp: *const u8, origin_hap: *const i64,
+                                  origin_pos: *const u64, params: *const dbgphmm_params, out: *mut *mut dbgphmm_dataset) -> c_int;
+    pub fn dbgphmm_dataset_destroy(d: *mut dbgphmm_dataset);
+    pub fn dbgphmm_dataset_sizes(d: *const dbgphmm_dataset, sizes: *mut u64) -> c_int;
+    pub fn dbgphmm_dataset_genome(d: *const dbgphmm_dataset, hap_off: *mut u64, bases: *mut u8, style: *mut u8) -> c_int;
+    pub fn dbgphmm_dataset_reads(d: *const dbgphmm_dataset, out: *mut *mut dbgphmm_reads) -> c_int;
+    pub fn dbgphmm_dataset_read_origins(d: *const dbgphmm_dataset, read_off: *mut u64, bases: *mut u8, revcomp: *mut u8, origin_hap: *mut i64,
+                                        origin_pos: *mut u64) -> c_int;
+    pub fn dbgphmm_dataset_params(d: *const dbgphmm_dataset, out: *mut dbgphmm_params) -> c_int;
+    pub fn dbgphmm_dataset_to_json_text(d: *const dbgphmm_dataset, buf: *mut c_char, cap: u64, needed: *mut u64) -> c_int;
+    pub fn dbgphmm_dataset_to_json_file(d: *const dbgphmm_dataset, path: *const c_char) -> c_int;
     // instrumentation
     pub fn dbgphmm_launch_count(reset: c_int) -> u64;
     pub fn dbgphmm_last_timing(ms: *mut f64, dense_cells: *mut u64) -> c_int;

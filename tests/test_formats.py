@@ -4,6 +4,7 @@ Pinned on the reference's own fixtures: the DBG example of README.md:174-191 is 
 node-centric graph tests/ already hold as graphs.toy_repeat(); the dump/load round trip mirrors output.rs:831-857 (dumpload,
 dbg_gz_compressed) and the MAP round trip output.rs:880-905 (map)."""
 import gzip
+import json
 import os
 
 import numpy as np
@@ -183,3 +184,72 @@ def test_mutated_dbg_and_map_texts_are_parsed_or_rejected_never_crash():
         except H.DbgphmmError:
             rejected += 1
     assert parsed > 50 and rejected > 50
+
+
+# ---- dataset JSON (Dataset::to_json_file / from_json_file, e2e.rs:123-130)
+def _ref_prob(lnp):
+    """Prob's Display (prob.rs:158-162): '{}({:.4})' of (ln p, p) the way Rust prints f64."""
+    import math
+    if lnp == -math.inf:
+        return "-inf(0.0000)"
+    r = repr(float(lnp))
+    if "e" in r or "E" in r:
+        from decimal import Decimal
+        r = format(Decimal(r), "f")
+    if r.endswith(".0"):
+        r = r[:-2]
+    return f"{r}({math.exp(lnp):.4f})"
+
+
+def test_dataset_json_matches_the_reference_serde_form(tmp_path):
+    from dbgphmm_b200 import hmmv2 as H
+    par = H.params_uniform(0.001)
+    haps = [b"ATCGATTTAGC", b"GGGC"]
+    reads = [b"ATCGT", b"TTAG"]
+    origins = [[(0, 0), (0, 1), (0, 2), None, (0, 3)], [(0, 5), (0, 6), (0, 7), (0, 9)]]   # the fixture of collection.rs:847-861 + one with a deletion
+    d = H.Dataset.new(haps, ["L", "C"], reads, par, revcomp=[1, 0], origins=origins)
+    text = d.to_json_string()
+    doc = json.loads(text)
+    # the literal forms the reference's own tests pin: styled sequences (collection.rs:836-842), positioned reads (:711-725)
+    assert doc["genome"] == ["L:ATCGATTTAGC", "C:GGGC"]
+    assert doc["genome_size"] == 15
+    assert doc["reads"] == {"reads": ["ATCGT:-:0-0,0-1,0-2,I,0-3", "TTAG:+:0-5,0-6,0-7,0-9"]}
+    pp = doc["phmm_params"]
+    assert list(pp) == ["p_mismatch", "p_match", "p_random", "p_gap_open", "p_gap_ext", "p_end", "p_MM", "p_IM", "p_DM", "p_MI", "p_II", "p_DI", "p_MD", "p_ID",
+                        "p_DD", "n_active_nodes", "active_node_max_ratio", "n_warmup", "warmup_threshold", "n_max_gaps"]      # field order of params.rs:16-66
+    for name in list(pp)[:15]:
+        assert pp[name] == _ref_prob(getattr(par, name)), name
+    assert (pp["n_active_nodes"], pp["active_node_max_ratio"], pp["n_warmup"], pp["warmup_threshold"], pp["n_max_gaps"]) == (40, 30.0, 50, 200, 4)
+    assert '"active_node_max_ratio":30.0' in text       # serde_json prints an f64 with its fraction
+    # round trip through text and through a gzip file
+    for e in (H.Dataset.from_json_str(text), None):
+        if e is None:
+            p = str(tmp_path / "d.json.gz"); d.to_json_file(p); e = H.Dataset.from_json_file(p)
+        assert e.to_json_string() == text
+        assert e.genome() == [("L", haps[0]), ("C", haps[1])] and e.genome_size() == 15
+        assert [bytes(r) for r in [e.reads()[0], e.reads()[1]]] == reads
+        assert e.read_origins() == ([True, False], origins)
+        q = e.params()
+        assert all(getattr(q, n) == getattr(par, n) for n, _ in H.Params._fields_)
+        assert abs(e.coverage() - 9 / 15) < 1e-15
+
+
+def test_dataset_json_reader_accepts_reference_output_and_rejects_malformed_text():
+    from dbgphmm_b200 import hmmv2 as H
+    # as serde_json writes it: no spaces, zero probability as "-inf(0.0000)", warmup_threshold absent in old files (params.rs:60 default)
+    probs = ",".join(f'"{n}":"{v}"' for n, v in [("p_mismatch", "-inf(0.0000)"), ("p_match", "0(1.0000)"), ("p_random", "-1.3862943611198906(0.2500)"),
+                                                   ("p_gap_open", "-inf(0.0000)"), ("p_gap_ext", "-inf(0.0000)"), ("p_end", "-11.512925464970229(0.0000)"),
+                                                   ("p_MM", "-0.000010000050000287824(1.0000)"), ("p_IM", "-1e-5(1.0000)"), ("p_DM", "-0.00001(1.0000)"),
+                                                   ("p_MI", "-inf(0.0000)"), ("p_II", "-inf(0.0000)"), ("p_DI", "-inf(0.0000)"), ("p_MD", "-inf(0.0000)"),
+                                                   ("p_ID", "-inf(0.0000)"), ("p_DD", "-inf(0.0000)")])
+    text = ('{"genome":["L:ACGT"],"genome_size":4,"reads":{"reads":["ACG:+:0-0,0-1,0-2","CG"]},"phmm_params":{' + probs +
+            ',"n_active_nodes":40,"active_node_max_ratio":30.0,"n_warmup":50,"n_max_gaps":4}}')
+    d = H.Dataset.from_json_str(text)
+    q = d.params()
+    assert q.p_mismatch == -np.inf and q.p_match == 0.0 and q.p_MM == -0.000010000050000287824 and q.p_IM == -1e-5 and q.warmup_threshold == 200
+    assert [bytes(d.reads()[i]) for i in range(2)] == [b"ACG", b"CG"]
+    assert d.read_origins()[1][1] == [None, None]      # a plain sequence carries no origins
+    for bad in ['{"genome":["X:ACGT"]', text.replace('"L:ACGT"', '"Q:ACGT"'), text.replace("0-0,0-1,0-2", "0-0,0-1"), text.replace('"ACG:+:', '"AcG:+:'),
+                text.replace('"genome_size":4', '"genome_size":-4'), text[:-1], text + "x", text.replace('"n_warmup":50,', "")]:
+        with pytest.raises(H.DbgphmmError):
+            H.Dataset.from_json_str(bad)

@@ -1,17 +1,18 @@
 #!/bin/bash
-# Round measurement on one B200: bench line, ncu launch list, ncu --set full captures of the dense pair kernels and of k_sparse.
+# Round measurement on one B200: full-size parity test, ncu --set full captures (with source) of the dense pair kernels and of k_sparse.
 # Every ncu pass runs only after the same command has exited 0 without ncu; numbers printed under ncu are never bench values.
 mkdir -p gpurun_out
-set -x
-timeout 900 python bench.py > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err || { tail -5 gpurun_out/bench_1gpu.err; exit 1; }
-cat gpurun_out/bench_1gpu.json
-timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --reads-per-gpu 148 > gpurun_out/b148.log 2>&1 || exit 2
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --reads-per-gpu 148 > gpurun_out/ncu_list.log 2>&1
-timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/b1184.log 2>&1 || exit 3
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_dense_(fwd|bwd)2' -s 18 -c 4 -f -o gpurun_out/dense_pair \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_dense.log 2>&1
-timeout 300 python tools/profile_step.py --reads 1184 --read-len 1500 --reps 1 > gpurun_out/p1500.log 2>&1 || exit 4
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_sparse' -c 2 -f -o gpurun_out/sparse \
-    python tools/profile_step.py --reads 1184 --read-len 1500 --reps 1 > gpurun_out/ncu_sparse.log 2>&1
-ls -la gpurun_out
+B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-strong --no-extras"
+if [ "$1" != "noparity" ]; then
+timeout 1500 python -m pytest tests/test_fullsize_gpu.py -m gpu -x -q -s > gpurun_out/pytest_fullsize.log 2>&1; echo "fullsize rc=$?"; tail -12 gpurun_out/pytest_fullsize.log
+fi
+timeout 300 $B > gpurun_out/b1184.log 2>&1 || { echo "bench failed"; tail -5 gpurun_out/b1184.log; exit 3; }
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_dense_(fwd|bwd)2' -s 18 -c 4 -f -o gpurun_out/dense_pair $B > gpurun_out/ncu_dense.log 2>&1
+echo "ncu dense rc=$?"
+ncu -i gpurun_out/dense_pair.ncu-rep --page source --csv > gpurun_out/src_dense_pair.csv 2>/dev/null
+timeout 300 python tools/profile_step.py --reads 1184 --read-len 1500 --reps 1 > gpurun_out/p1500.log 2>&1 || { echo "profile_step failed"; tail -5 gpurun_out/p1500.log; exit 4; }
+cat gpurun_out/p1500.log | tail -3
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_sparse' -c 4 -f -o gpurun_out/sparse python tools/profile_step.py --reads 1184 --read-len 1500 --reps 1 > gpurun_out/ncu_sparse.log 2>&1
+echo "ncu sparse rc=$?"
+ncu -i gpurun_out/sparse.ncu-rep --page source --csv > gpurun_out/src_sparse.csv 2>/dev/null
+ls -la gpurun_out | tail -20
