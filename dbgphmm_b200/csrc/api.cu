@@ -552,16 +552,42 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
     const uint64_t budget_now = model_budget(m);
     bool stream = can_stream && store_total > budget_now;
     if (const char* e = getenv("DBGPHMM_STRATEGY")) { if (!strcmp(e, "stream")) stream = can_stream; else if (!strcmp(e, "store")) stream = false; }
-    // DBGPHMM_DENSE_GROUP=G (stream strategy): the dense warm-up and the recompute passes run in groups of G jobs that share one pool
-    // of 2 G slabs (engine.cu), so a batch is sized by its sparse rows and can fill the sparse kernel's waves on large graphs
+    // Stream strategy: the dense warm-up and the recompute passes can run in GROUPS of G jobs that share one pool of 2 G slabs
+    // (engine.cu), so that a batch is sized by its sparse rows and fills the sparse kernel's resident wave even when two slabs per read
+    // would not leave room for that many reads (C5: 187 MB slabs -> 296 reads = 2 jobs per SM without groups).  G is chosen here: no
+    // groups when a full wave fits with two slabs per read (C3), else the largest G the budget leaves beside a wave's sparse rows.
+    // DBGPHMM_DENSE_GROUP=G forces a group size (0: never group).
     uint32_t group = 0;
     uint64_t plan_budget = budget_now;
     if (stream) {
-        if (const char* e = getenv("DBGPHMM_DENSE_GROUP")) { const int g = atoi(e); if (g > 0) group = (uint32_t)g; }
         const uint64_t slab = dense_slab_bytes(m->N);
         const uint64_t per_row = (uint64_t)m->params.n_active_nodes * 48 + 256 + 3 * sizeof(RowDesc);   // (arena_estimate, engine.cu)
-        const uint64_t dense_part = group ? (uint64_t)32 * sparse_gather_cap(m, m->params.n_active_nodes) + 64 * (uint64_t)m->fwd.n_chunks : 2 * slab;
-        for (uint64_t r = 0; r < R; r++) bytes[r] = dense_part + 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20);
+        const uint64_t gather_part = (uint64_t)32 * sparse_gather_cap(m, m->params.n_active_nodes) + 64 * (uint64_t)m->fwd.n_chunks;
+        auto rows_bytes = [&](uint64_t r) { return 2 * (uint64_t)all[r].len * per_row + ((uint64_t)1 << 20); };
+        const uint64_t wave = sparse_wave_jobs(m, sparse_default_cap());
+        bool forced = false;
+        if (const char* e = getenv("DBGPHMM_DENSE_GROUP")) { const int g = atoi(e); forced = true; if (g > 0) group = (uint32_t)g; }
+        if (!forced) {
+            const uint64_t target = std::min<uint64_t>(R, wave);
+            uint64_t acc = 0, fit = 0;
+            while (fit < R && acc + 2 * slab + rows_bytes(fit) <= budget_now) { acc += 2 * slab + rows_bytes(fit); fit++; }
+            if (fit < target) {   // two slabs per read do not leave room for a full wave
+                // the largest batch (a wave, half a wave, ...) beyond what fits ungrouped whose sparse rows leave room for a pool of
+                // at least 16 reads' slabs (the dense kernels want a few hundred thousand tiles per launch)
+                for (uint64_t jt = target; jt > fit && !group; jt = jt / 2) {
+                    uint64_t rows = 0;
+                    for (uint64_t r = 0; r < jt; r++) rows += gather_part + rows_bytes(r);
+                    const uint64_t reserve = budget_now >> 4;
+                    if (rows + reserve < budget_now) {
+                        const uint64_t g = (budget_now - rows - reserve) / (2 * slab);
+                        if (g >= 16 || g >= jt) group = (uint32_t)std::min<uint64_t>(g, jt);
+                    }
+                }
+            }
+            if (group && getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] dense warm-up in groups of %u reads (two slabs per read would fit %llu of %llu reads)\n", group, (unsigned long long)fit, (unsigned long long)R);
+        }
+        const uint64_t dense_part = group ? gather_part : 2 * slab;
+        for (uint64_t r = 0; r < R; r++) bytes[r] = dense_part + rows_bytes(r);
         if (group) {
             const uint64_t pool = 2 * (uint64_t)group * slab;
             if (pool + (plan_budget >> 3) > plan_budget) { dbg_set_error("DBGPHMM_DENSE_GROUP: the group's slabs do not fit the memory budget"); return DBGPHMM_ERR_OOM; }

@@ -823,6 +823,11 @@ __global__ void k_dense_prep2(LinParams lp, const DJob* __restrict__ jobs, uint3
     out[n_jobs + j] = b;
 }
 
+#ifdef RS2_UNROLL_PASSES
+#define RS2_PASS_PRAGMA _Pragma("unroll")
+#else
+#define RS2_PASS_PRAGMA _Pragma("unroll 1")
+#endif
 #define RS2_SMEM_PER_WARP (2 * DENSE_LMAX * (3 * 8 + 4) + 6 * 64 + DENSE_LMAX * (8 + 4))
 #define RS2_SMEM_BYTES (WT_WARPS * RS2_SMEM_PER_WARP)
 
@@ -973,7 +978,7 @@ k_dense_fwd2(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ js
         }
         prefetch_next();   // (barrier inside) every lane is done with the raw row: refill it for the next job
         double cm[RS_PER_LANE], ci[RS_PER_LANE], dacc[RS_PER_LANE], dcur[RS_PER_LANE];
-#pragma unroll 1
+RS2_PASS_PRAGMA
         for (int pass = 0; pass < 2; pass++) {
             const JStep* jq = pass ? js1 : js0;
             const XF fb0 = jq->fb0, ib_cur = jq->ib_cur;
@@ -1210,7 +1215,7 @@ k_dense_bwd2(PlanView P, GraphView G, LinParams lp, const JStep* __restrict__ js
         for (int k = 0; k < RS_PER_LANE; k++) { const double sc_ = pow2i(pe[k] - Eref); pm[k] *= sc_; pi[k] *= sc_; }
         prefetch_next();
         double cm[RS_PER_LANE], ci[RS_PER_LANE], dacc[RS_PER_LANE], dcur[RS_PER_LANE];
-#pragma unroll 1
+RS2_PASS_PRAGMA
         for (int pass = 0; pass < 2; pass++) {
             const unsigned int x = ((pass ? js1 : js0)->base >> 1) & 3;
             // next-base row: pm := e_l(x) m''[l]  (every use of m'' is multiplied by the emission of that node)

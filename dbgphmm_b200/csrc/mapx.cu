@@ -51,7 +51,8 @@ __device__ __forceinline__ uint8_t mx_find(const uint32_t* key, const uint8_t* v
     }
 }
 
-__global__ void __launch_bounds__(MX_THREADS)
+// (min 4 CTAs per SM: without a residency hint ptxas settled on 32 registers and spilled 72 bytes ; 72 registers, no spills now)
+__global__ void __launch_bounds__(MX_THREADS, 4)
 k_mapx(const uint32_t* __restrict__ par_off, const uint32_t* __restrict__ par_node, const uint32_t* __restrict__ par_eid,
        const uint8_t* __restrict__ emission, const double* __restrict__ init_t, const double* __restrict__ trans_t, uint32_t n_x,
        LinParams lp, const MJob* __restrict__ jobs, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ map_row_off,

@@ -302,20 +302,29 @@ __device__ void sp_rank(SS& S, uint32_t n, uint32_t KK, const uint32_t* ids, uin
     const int tid = threadIdx.x, B = blockDim.x;
     uint32_t* bad = S.wt() + 16;   // zero between rankings (reset below after use)
     if (!*bad) {
-        // f precedes e iff kf > ke, or kf == ke and f < e: that is kf + (f < e) > ke (keys stay below 2^63) ; two keys per load
-        const ulonglong2* k2 = (const ulonglong2*)S.k_mant();   // (16-byte aligned: cap is a multiple of 16)
-        for (uint32_t e = tid; e < n; e += B) {
-            const unsigned long long ke = S.k_mant()[e];
+        // f precedes e iff kf > ke, or kf == ke and f < e.  Keys stay below 2^63, so as signed integers that is kf > ke - (f < e): a
+        // threshold instead of an addition per key.  Pairs of keys per load ; the pairs wholly below this warp's smallest e compare
+        // against ke - 1, the pairs wholly above its largest e against ke (no per-key choice), only the pairs in between choose.
+        const longlong2* k2 = (const longlong2*)S.k_mant();   // (16-byte aligned: cap is a multiple of 16)
+        const long long* k1 = (const long long*)S.k_mant();
+        const uint32_t np = n >> 1;
+        for (uint32_t e0 = tid & ~31u; e0 < n; e0 += B) {   // (whole warps: the range split below is warp-uniform)
+            const uint32_t e = e0 + (tid & 31u);
+            const bool on = e < n;
+            const long long ke = on ? k1[e] : 0, ke1 = ke - 1;
+            const uint32_t p_lo = min(e0 >> 1, np), p_hi = min((e0 + 32u) >> 1, np);   // pairs [p_lo, p_hi) straddle this warp's entries
             uint32_t rank = 0;
-#pragma unroll 2
-            for (uint32_t f = 0; f + 1 < n; f += 2) {
-                const ulonglong2 kf = k2[f >> 1];
-                rank += (kf.x + (f < e ? 1ull : 0ull) > ke) ? 1u : 0u;
-                rank += (kf.y + (f + 1 < e ? 1ull : 0ull) > ke) ? 1u : 0u;
+            for (uint32_t p2 = 0; p2 < p_lo; p2++) { const longlong2 kf = k2[p2]; rank += (kf.x > ke1) + (kf.y > ke1); }
+            for (uint32_t p2 = p_lo; p2 < p_hi; p2++) {
+                const longlong2 kf = k2[p2];
+                rank += (kf.x > (2 * p2 < e ? ke1 : ke)) + (kf.y > (2 * p2 + 1 < e ? ke1 : ke));
             }
-            if (n & 1u) rank += (S.k_mant()[n - 1] + (n - 1 < e ? 1ull : 0ull) > ke) ? 1u : 0u;
-            if (rank < KK) out_id[rank] = ids[e];
-            S.scan()[e] = rank;
+            for (uint32_t p2 = p_hi; p2 < np; p2++) { const longlong2 kf = k2[p2]; rank += (kf.x > ke) + (kf.y > ke); }
+            if (n & 1u) rank += k1[n - 1] > (n - 1 < e ? ke1 : ke);
+            if (on) {
+                if (rank < KK) out_id[rank] = ids[e];
+                S.scan()[e] = rank;
+            }
         }
     } else {
         const unsigned long long M52 = 0xfffffffffffffull;

@@ -1007,6 +1007,10 @@ class PHMMModel:
             lib().dbgphmm_model_destroy(self._h)
             self._h = None
 
+    def close(self):
+        """Release the device graph and every cached row buffer of this device now (also happens when the object is collected)."""
+        self.__del__()
+
     def n_edges(self):
         return len(self.src)
 

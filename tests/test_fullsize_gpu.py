@@ -111,3 +111,70 @@ def test_c3_fullsize_rows_and_bulk_against_the_oracle_fixture(monkeypatch, capsy
     fr2, lf2, lb2, cells2 = m.run_node_freqs(H.Reads(reads), "sparse")
     assert cells2 == cells and np.array_equal(lf2, lf) and np.array_equal(lb2, lb)
     assert np.allclose(fr2, fr, rtol=1e-11, atol=1e-14)
+
+
+def test_c3_fullsize_two_batches_and_arena_repeat(monkeypatch):
+    """The memory-pressure paths at full N: a budget that holds two reads' rows forces a second batch; an arena sized at a
+    fraction of the estimate is outgrown, the phase is repeated with the worst-case bound; dense groups of one read.  All of them must give
+    the fixture's answers."""
+    from dbgphmm_b200 import hmmv2 as H
+    fx = load("c3")
+    g = build(fx)
+    N = g.n_nodes
+    r0, r1 = (np.asarray(fx[f"r{i}_read"], np.uint8) for i in range(2))
+    reads = [r0, r1, r0]
+    want_lf = [float(fx["r0_logp_fwd"]), float(fx["r1_logp_fwd"]), float(fx["r0_logp_fwd"])]
+    want = np.zeros(N)
+    for i in (0, 1, 0):
+        np.add.at(want, fx[f"r{i}_freq_idx"], fx[f"r{i}_freq_val"])
+    li, lt = g.to_probs("normal")
+    par = H.params_uniform(0.001); par.n_warmup = int(fx["k"][0])
+    slab = ((N + 1) // 2 * 2 * 28 + 255) // 256 * 256
+    per_read = 2 * slab + 2 * 10_000 * (40 * 48 + 256 + 3 * 64) + (1 << 20)
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
+    monkeypatch.setenv("DBGPHMM_VERIFY", "1")
+    for env, budget in (({}, int(2.4 * per_read)), ({"DBGPHMM_ARENA_EST_PCT": "30"}, 0), ({"DBGPHMM_DENSE_GROUP": "1"}, 0)):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = H.PHMMModel(g.src, g.dst, g.base, li, lt, par, mem_budget_bytes=budget)
+        fr, lf, lb, cells = m.run_node_freqs(H.Reads(reads), "sparse")
+        assert all(close(a, b) for a, b in zip(lf, want_lf)), (env, lf, want_lf)
+        assert np.allclose(fr, want, rtol=1e-9, atol=1e-12), (env, np.abs(fr - want).max())
+        m.close()
+        for k in env:
+            monkeypatch.delenv(k)
+
+
+def test_c5_fullsize_read_against_the_oracle_fixture(monkeypatch, capsys):
+    """BASELINE configs[4] graph (5 Mbp diploid, N = 6.66 M) with one full 20 kbp read (31 CPU-minutes in the oracle): active sets of every
+    row through the single-read tables, then the bulk call in the stream strategy with the dense warm-up in GROUPS sharing one pool of
+    slabs (the mode the library chooses by itself on this graph when a batch holds more reads than two slabs each leave room for)."""
+    from dbgphmm_b200 import hmmv2 as H
+    fx = load("c5")
+    g = build(fx)
+    m = model_of(H, g, int(fx["k"][0]))
+    N = g.n_nodes
+    read = np.asarray(fx["r0_read"], np.uint8)
+    n = len(read)
+    f = m.forward_sparse(read, False)
+    assert close(f.full_prob(), float(fx["r0_logp_fwd"]))
+    df, df_t, sf = compare_rows(f, fx, "r0_f_", n, "C5 fwd")
+    del f
+    b = m.backward_sparse(read)
+    assert close(b.full_prob(), float(fx["r0_logp_bwd"]))
+    db, db_t, sb = compare_rows(b, fx, "r0_b_", n, "C5 bwd")
+    del b
+    ties = fx["r0_ties"].tolist()
+    with capsys.disabled():
+        print(f"\nC5 read ({n} rows): active sets differ in {len(df)} forward / {len(db)} backward rows; ties across the top-n boundary in {ties[0]} / {ties[1]} rows")
+    assert not sf and not sb, (sf[:3], sb[:3])
+    assert len(df) == df_t and len(db) == db_t and len(df) <= ties[0] and len(db) <= ties[1], (df[:5], db[:5])
+    want = np.zeros(N)
+    np.add.at(want, fx["r0_freq_idx"], fx["r0_freq_val"])
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
+    monkeypatch.setenv("DBGPHMM_VERIFY", "1")
+    for group in ("2", "0"):     # three copies of the read in groups of two (one full group, one partial) ; then ungrouped
+        monkeypatch.setenv("DBGPHMM_DENSE_GROUP", group)
+        fr, lf, lb, cells = m.run_node_freqs(H.Reads([read, read, read]), "sparse")
+        assert all(close(x, float(fx["r0_logp_fwd"])) for x in lf) and all(close(x, float(fx["r0_logp_bwd"])) for x in lb), group
+        assert np.allclose(fr, 3.0 * want, rtol=1e-9, atol=1e-12), (group, np.abs(fr - 3.0 * want).max())

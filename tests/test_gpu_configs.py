@@ -5,7 +5,7 @@ import pytest
 
 from dbgphmm_b200 import graphs, synth
 from oracle import oracle as O
-from tests.common import REL_TOL, assert_tables_match, close_log, gpu_model, oracle_model, oracle_params
+from tests.common import REL_TOL, assert_tables_match, close_log, gpu_model, oracle_model, oracle_params, same_up_to_ties
 
 pytestmark = pytest.mark.gpu
 
@@ -98,6 +98,61 @@ def test_c4_batched_candidates_on_a_tandem_repeat(H):
         s, p = o.to_full_prob_reads(O.Reads(reads), omaps)
         assert close_log(per[x], p).all(), (x, per[x], p)
         assert close_log(tot[x], s).all()
+
+
+def test_c4_full_size_region_64_candidates(H):
+    """configs[3] at its size: 200 kbp KIR-like region (16 x 10 kbp units, two haplotypes, N ~ 94 k), 10 kbp reads, B = 64 candidate copy-number
+    vectors scored with mappings in one batched call (posterior.rs:504-515) -- the workload of bench.py's C4 line.  The mappings
+    come from the GPU (generate_mappings), are checked against the oracle's on the first reads, and every candidate's per-read
+    ln P(R|X) is compared with the oracle given the same mappings."""
+    import os
+    hap = synth.tandem_repeat_genome(10_000, 16, 20_000, seed=3, divergence=0.005)
+    hap2 = synth.mutate_substitutions(hap, 0.002, 77)
+    sg, _ = graphs.build_dbg([hap.tobytes(), hap2.tobytes()], 40, seed=9)
+    assert sg.n_nodes > 80_000
+    reads = synth.sample_reads([hap, hap2], 20, 10_000, 0.001, 13)[:6]
+    par = oracle_params(0.001, n_warmup=40)
+    g = gpu_model(sg, par, "non_zero")
+    o = oracle_model(sg, par, "non_zero")
+    gmaps = g.generate_mappings(H.Reads(reads), None, False)
+    omaps2 = o.generate_mappings(O.Reads(reads[:2]), None, False, n_threads=2)
+    n2 = int(omaps2.read_off[2])
+    assert np.array_equal(gmaps.row_off[:n2 + 1], omaps2.row_off)
+    # Inside a 16-copy repeat many of a row's 40 nodes carry (nearly) the same probability: the lists must agree as sets of everything
+    # clearly above the row's smallest value, in order up to ties, and in their sorted values.
+    n_reordered = 0
+    for r in range(n2):
+        a, b = int(omaps2.row_off[r]), int(omaps2.row_off[r + 1])
+        gi, gp, oi, op = gmaps.nodes[a:b], gmaps.probs[a:b], omaps2.nodes[a:b], omaps2.probs[a:b]
+        assert np.allclose(np.sort(gp), np.sort(op), rtol=0, atol=1e-7), r
+        if np.array_equal(gi, oi):
+            continue
+        n_reordered += 1
+        if same_up_to_ties(gi, oi, op, rel=1e-8):
+            continue
+        edge = op.min() + 1e-8 * max(1.0, abs(op.min()))
+        assert {int(i) for i, p in zip(gi, gp) if p > edge} == {int(i) for i, p in zip(oi, op) if p > edge}, r
+    print(f"C4 mappings: {n_reordered} of {n2} rows list their (near-)tied nodes in another order than the oracle")
+    omaps = O.Mappings(gmaps.read_off, gmaps.row_off, gmaps.nodes, gmaps.probs)
+    rng = np.random.default_rng(1)
+    B = 64
+    cn = sg.node_copy_num
+    X = np.repeat(cn[None, :], B, 0).astype(np.uint32)
+    rep = np.where(cn >= 2)[0]
+    for b in range(1, B):
+        idx = rng.choice(rep, size=40, replace=False)
+        X[b, idx] = np.maximum(1, X[b, idx].astype(np.int64) + rng.choice([-1, 1], size=len(idx))).astype(np.uint32)
+    g.set_copy_nums_batch(X, "non_zero")
+    tot, per = g.to_full_prob_reads(H.Reads(reads), gmaps)
+    assert tot.shape == (B,) and per.shape == (B, len(reads))
+    threads = max(1, min(8, len(os.sched_getaffinity(0))))
+    for x in range(B):
+        li, lt = sg.to_probs("non_zero", X[x])
+        o.set_probs(li, lt)
+        s, p = o.to_full_prob_reads(O.Reads(reads), omaps, n_threads=threads)
+        assert close_log(per[x], p).all(), (x, per[x], p)
+        assert close_log(tot[x], s).all()
+    assert len(set(np.round(tot, 6))) > B // 2          # the candidates are really different models
 
 
 def test_fast_and_exact_dense_kernels_agree_on_a_large_graph(H, monkeypatch):
