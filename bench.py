@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-gpu", type=int, default=1184, help="reads per GPU per step (1184 = 148 SMs x 8 resident sparse jobs: one wave)")
+    ap.add_argument("--reads-per-gpu", type=int, default=0, help="reads per GPU per step (0 = one resident wave of the sparse kernel: SMs x jobs per SM, PHMMModel.wave_reads)")
     ap.add_argument("--genome-len", type=int, default=1_000_000)
     ap.add_argument("--read-len", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=40)
@@ -56,18 +56,26 @@ def workload_tag(args):
     return "custom"
 
 
+def make_reads(args, rank, n_reads):
+    """Rank-specific reads of the workload's genome (10 kbp HiFi reads for C3)."""
+    from dbgphmm_b200 import synth
+    h0 = synth.random_genome(args.genome_len, 0)
+    h1 = synth.mutate_substitutions(h0, 0.01, 1)
+    cov = n_reads * args.read_len / (2.0 * args.genome_len)
+    reads = synth.sample_reads([h0, h1], cov, args.read_len, 0.001, 1000 + rank)[:n_reads]
+    while len(reads) < n_reads:
+        reads += synth.sample_reads([h0, h1], cov, args.read_len, 0.001, 5000 + rank + len(reads))[:n_reads - len(reads)]
+    return reads
+
+
 def make_inputs(args, rank, n_reads):
     """Same graph on every rank (seed 0); rank-specific reads.  C3: 1 Mbp diploid, 1 % het, 10 kbp HiFi reads, k = 40."""
     from dbgphmm_b200 import graphs, synth
     h0 = synth.random_genome(args.genome_len, 0)
     h1 = synth.mutate_substitutions(h0, 0.01, 1)
     g, _ = graphs.build_dbg([h0.tobytes(), h1.tobytes()], args.k, seed=100)
-    cov = n_reads * args.read_len / (2.0 * args.genome_len)
-    reads = synth.sample_reads([h0, h1], cov, args.read_len, 0.001, 1000 + rank)[:n_reads]
-    while len(reads) < n_reads:
-        reads += synth.sample_reads([h0, h1], cov, args.read_len, 0.001, 5000 + rank + len(reads))[:n_reads - len(reads)]
     li, lt = g.to_probs("normal")
-    return g, li, lt, reads
+    return g, li, lt, make_reads(args, rank, n_reads)
 
 
 class ClockSampler:
@@ -200,18 +208,19 @@ def extra_c4(H, local, n_candidates=64, n_reads=200):
             "best_candidate": int(np.argmax(tot))}
 
 
-def extra_c5(H, local, n_reads=1184):
+def extra_c5(H, local, n_reads=0):
     """One GPU's read shard of BASELINE configs[4] (C5): 5 Mbp diploid (N = 6.66 M), 20 kbp reads, run_sparse + node freqs through
     dbgphmm_run_node_freqs with HOST buffers.  Two dense slabs per read (2 x 187 MB) would leave room for ~350 reads = 2 sparse jobs per
     SM; the library runs the dense warm-up in groups sharing one pool of slabs so that the sparse phase still gets a full resident wave."""
     from dbgphmm_b200 import graphs, synth
     h0 = synth.random_genome(5_000_000, 0); h1 = synth.mutate_substitutions(h0, 0.01, 1)
     g, _ = graphs.build_dbg([h0.tobytes(), h1.tobytes()], 40, seed=100)
-    cov = n_reads * 20_000 / (2.0 * 5_000_000)
-    reads = synth.sample_reads([h0, h1], cov, 20_000, 0.001, 1000)[:n_reads]
     li, lt = g.to_probs("normal")
     par = H.params_uniform(0.001); par.n_warmup = 40
     m = H.PHMMModel(g.src, g.dst, g.base, li, lt, par, device=local)
+    n_reads = n_reads or m.wave_reads()
+    cov = n_reads * 20_000 / (2.0 * 5_000_000)
+    reads = synth.sample_reads([h0, h1], cov, 20_000, 0.001, 1000)[:n_reads]
     m.run_node_freqs(H.Reads(reads), "sparse")    # warm-up
     ts, cells = [], 0
     for _ in range(2):
@@ -266,11 +275,12 @@ def main():
             time.sleep(2.0)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    R = args.reads_per_gpu
-    g, li, lt, reads = make_inputs(args, rank, R)
+    g, li, lt, reads = make_inputs(args, rank, 1)
     par = H.params_uniform(0.001)
     par.n_warmup = args.k  # MultiDbg::to_phmm (multi_dbg.rs:1395)
     model = H.PHMMModel(g.src, g.dst, g.base, li, lt, par, device=local)
+    R = args.reads_per_gpu or model.wave_reads()
+    reads = make_reads(args, rank, R)
     N = g.n_nodes
     # ONE device buffer holds what the ranks exchange: [N] node frequencies + the summed ln P(R).  The library accumulates into it,
     # the all-reduce runs on it in place (no concatenation, no copy).

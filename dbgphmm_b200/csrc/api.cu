@@ -4,6 +4,9 @@
 #include <cstring>
 #include <memory>
 #include <unordered_map>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include "engine.h"
 
 static const double LN2 = 0.693147180559945309417232121458;
@@ -34,6 +37,7 @@ extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) try {
     if (!m || !r) { dbg_set_error("reads_to_device: bad argument"); return DBGPHMM_ERR_INVALID; }
     if (r->d_bases && r->device == m->device) return DBGPHMM_OK;
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     if (r->d_bases) { cudaFree(r->d_bases); r->d_bases = nullptr; }
     CUDA_TRY(cudaMalloc((void**)&r->d_bases, std::max<size_t>(r->bases.size(), 1)));
     if (!r->bases.empty()) CUDA_TRY(cudaMemcpy(r->d_bases, r->bases.data(), r->bases.size(), cudaMemcpyHostToDevice));
@@ -154,6 +158,7 @@ static int tables_finish(dbgphmm_tables* t) {
 extern "C" void dbgphmm_tables_destroy(dbgphmm_tables* t) {
     if (!t) return;
     if (t->device >= 0) cudaSetDevice(t->device);
+    cache_set_stream(nullptr);   // (the model the rows belong to may be gone: no stream to order the reuse behind)
     t->store.release();
     cudaFree(t->d_bases);
     delete t;
@@ -164,6 +169,7 @@ static int one_job(dbgphmm_model* m, const uint8_t* bases, uint64_t n, const dbg
     for (uint64_t i = 0; i < n; i++)
         if (bases[i] != 'A' && bases[i] != 'C' && bases[i] != 'G' && bases[i] != 'T') { dbg_set_error("bases must be uppercase ACGT"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     t->m = m; t->device = m->device; t->bases.assign(bases, bases + n);
     CUDA_TRY(cudaMalloc((void**)&t->d_bases, n));
     CUDA_TRY(cudaMemcpy(t->d_bases, bases, n, cudaMemcpyHostToDevice));
@@ -232,6 +238,7 @@ struct HostRow { std::vector<double> m, i, d; std::vector<int> ex; std::vector<u
 static int fetch_row(const dbgphmm_tables* t, const RowDesc& r, HostRow* h) {
     const dbgphmm_model* m = t->m;
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     if (r.kind == ROW_DENSE) {
         uint32_t N = m->N, Np = t->store.pool.Np;
         const char* sl = t->store.pool.base + r.off * t->store.pool.slab_bytes;
@@ -284,17 +291,18 @@ extern "C" int dbgphmm_tables_row_top_nodes(const dbgphmm_tables* t, int64_t row
     dbgphmm_model* m = t->m;
     const RowDesc& r = t->desc[row];
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     if (r.kind == ROW_DENSE) {  // the device selection kernel used by the forward/backward drivers
         DevBuf b_req, b_ids, b_cnt;
         std::vector<SelectReq> rq(1);
         rq[0].slab = r.off; rq[0].k = by_ratio ? MAX_ACTIVE : std::min<uint32_t>(k, MAX_ACTIVE); rq[0].by_ratio = by_ratio; rq[0].ratio = ratio; rq[0].active_idx = -1; rq[0].out = 0;
-        ST_TRY(dev_upload(b_req, rq, m->stream));
+        ST_TRY(dev_upload(b_req, rq, MSET(m).stream));
         ST_TRY(b_ids.alloc(sizeof(uint32_t) * MAX_ACTIVE)); ST_TRY(b_cnt.alloc(sizeof(uint32_t)));
         ST_TRY(dense_select(m, t->store.pool, b_req.as<SelectReq>(), 1, nullptr, b_ids.as<uint32_t>(), b_cnt.as<uint32_t>()));
         uint32_t cnt = 0; std::vector<uint32_t> ids(MAX_ACTIVE);
-        CUDA_TRY(cudaMemcpyAsync(&cnt, b_cnt.p, 4, cudaMemcpyDeviceToHost, m->stream));
-        CUDA_TRY(cudaMemcpyAsync(ids.data(), b_ids.p, 4 * MAX_ACTIVE, cudaMemcpyDeviceToHost, m->stream));
-        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        CUDA_TRY(cudaMemcpyAsync(&cnt, b_cnt.p, 4, cudaMemcpyDeviceToHost, MSET(m).stream));
+        CUDA_TRY(cudaMemcpyAsync(ids.data(), b_ids.p, 4 * MAX_ACTIVE, cudaMemcpyDeviceToHost, MSET(m).stream));
+        CUDA_TRY(cudaStreamSynchronize(MSET(m).stream));
         for (uint32_t a = 0; a < cnt; a++) out[a] = m->orig_of[ids[a]];
         *n_out = cnt;
         return DBGPHMM_OK;
@@ -330,9 +338,10 @@ static int check_pair(const dbgphmm_model* m, const dbgphmm_tables* f, const dbg
 extern "C" int dbgphmm_output_node_freqs(dbgphmm_model* m, const dbgphmm_tables* fwd, const dbgphmm_tables* bwd, double* freqs) try {
     ST_TRY(check_pair(m, fwd, bwd));
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     DevBuf b_f;
     ST_TRY(b_f.alloc(sizeof(double) * m->N));
-    CUDA_TRY(cudaMemsetAsync(b_f.p, 0, sizeof(double) * m->N, m->stream));
+    CUDA_TRY(cudaMemsetAsync(b_f.p, 0, sizeof(double) * m->N, MSET(m).stream));
     std::vector<HJob> jobs(1);
     jobs[0] = HJob{0, 0, 0, (uint32_t)fwd->desc.size(), 0};
     ST_TRY(run_products_freqs(m, jobs, fwd->store, bwd->store, b_f.as<double>()));
@@ -345,10 +354,11 @@ extern "C" int dbgphmm_output_edge_and_init_freqs(dbgphmm_model* m, const dbgphm
     if (!edge_freqs || !init_freqs) { dbg_set_error("to_edge_and_init_freqs: null output"); return DBGPHMM_ERR_INVALID; }
     if (fwd->bases != bwd->bases) { dbg_set_error("to_edge_and_init_freqs: the two tables come from different reads (freq.rs:281-282)"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     DevBuf b_e, b_i;
     ST_TRY(b_e.alloc(sizeof(double) * std::max<uint32_t>(m->E, 1))); ST_TRY(b_i.alloc(sizeof(double) * m->N));
-    CUDA_TRY(cudaMemsetAsync(b_e.p, 0, sizeof(double) * std::max<uint32_t>(m->E, 1), m->stream));
-    CUDA_TRY(cudaMemsetAsync(b_i.p, 0, sizeof(double) * m->N, m->stream));
+    CUDA_TRY(cudaMemsetAsync(b_e.p, 0, sizeof(double) * std::max<uint32_t>(m->E, 1), MSET(m).stream));
+    CUDA_TRY(cudaMemsetAsync(b_i.p, 0, sizeof(double) * m->N, MSET(m).stream));
     std::vector<HJob> jobs(1);
     jobs[0] = HJob{0, 0, 0, (uint32_t)fwd->desc.size(), 0};
     ST_TRY(run_products_edge_freqs(m, jobs, fwd->store, bwd->store, fwd->d_bases, b_e.as<double>(), b_i.as<double>()));
@@ -380,6 +390,7 @@ extern "C" int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fw
                                       double ratio, dbgphmm_mappings** out) try {
     ST_TRY(check_pair(m, fwd, bwd));
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     std::vector<HJob> jobs(1);
     jobs[0] = HJob{0, 0, 0, (uint32_t)fwd->desc.size(), 0};
     dbgphmm_mappings* mp = new dbgphmm_mappings();
@@ -390,6 +401,11 @@ extern "C" int dbgphmm_output_mapping(dbgphmm_model* m, const dbgphmm_tables* fw
 } ABI_CATCH
 
 // ------------------------------------------------------------------ bulk calls
+extern "C" uint32_t dbgphmm_model_wave_reads(const dbgphmm_model* m) {
+    if (!m) return 0;
+    if (cudaSetDevice(m->device) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return sparse_wave_jobs(const_cast<dbgphmm_model*>(m), sparse_default_cap());
+}
 static void reset_times() { g_times = EngineTimes(); }
 extern "C" int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells) try {
     ms[0] = g_times.dense_ms; ms[1] = g_times.sparse_ms; ms[2] = g_times.product_ms; ms[3] = g_times.total_ms;
@@ -432,9 +448,10 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
     if (!m || !reads || !out_logp) { dbg_set_error("to_full_prob_reads: bad argument"); return DBGPHMM_ERR_INVALID; }
     ST_TRY(check_reads_mappings(reads, mappings));
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     ST_TRY(dbgphmm_reads_to_device(m, const_cast<dbgphmm_reads*>(reads)));
     reset_times();
-    EvTimer total(m->stream, &g_times.total_ms);
+    EvTimer total(MSET(m).stream, &g_times.total_ms);
     const uint64_t R = reads->n_reads; const uint32_t X = m->n_batch;
     const int kind = mappings ? DBGPHMM_FWD_MAPPING : (use_max_ratio ? DBGPHMM_FWD_SPARSE_RATIO : DBGPHMM_FWD_SPARSE);
     DevMappings dmap;
@@ -501,6 +518,11 @@ extern "C" int dbgphmm_to_full_prob_reads(dbgphmm_model* m, const dbgphmm_reads*
     return DBGPHMM_OK;
 } ABI_CATCH
 
+struct Gate {   // one-shot, idempotent
+    std::mutex mu; std::condition_variable cv; bool is_open = false;
+    void open() { { std::lock_guard<std::mutex> lk(mu); is_open = true; } cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return is_open; }); }
+};
 static void run_kinds(int mode, int use_max_ratio, int* fk, int* bk) {
     switch (mode) {
         case DBGPHMM_RUN_DENSE: *fk = DBGPHMM_FWD_DENSE; *bk = DBGPHMM_BWD_DENSE; break;
@@ -525,7 +547,7 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
     if (mode == DBGPHMM_RUN_WITH_MAPPING && !mappings) { dbg_set_error("run_with_mapping needs mappings"); return DBGPHMM_ERR_INVALID; }
     ST_TRY(dbgphmm_reads_to_device(m, const_cast<dbgphmm_reads*>(reads)));
     reset_times();
-    EvTimer total(m->stream, &g_times.total_ms);
+    EvTimer total(MSET(m).stream, &g_times.total_ms);
     int fk, bk;
     run_kinds(mode, use_max_ratio, &fk, &bk);
     const bool with_map = mode == DBGPHMM_RUN_WITH_MAPPING;
@@ -618,15 +640,58 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
         } else {
             DevBuf b_err;
             st = b_err.alloc(sizeof(int));
-            if (st == DBGPHMM_OK && cudaMemsetAsync(b_err.p, 0, sizeof(int), m->stream) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
+            if (st == DBGPHMM_OK && cudaMemsetAsync(b_err.p, 0, sizeof(int), MSET(m).stream) != cudaSuccess) st = DBGPHMM_ERR_CUDA;
             PhaseOpts pf; pf.keep_rows = false; pf.store_sparse = true; pf.group = group;
-            if (st == DBGPHMM_OK) st = run_forward(m, jobs, reads->d_bases, fk, pf, nullptr, &F);                    // F: sparse rows stored
             // B dense x F sparse: on the fly after every dense backward step, or (when the two-rows-per-launch kernels are available,
             // which never write the intermediate rows) by a recompute pass inside the dependency cone like the forward one below
             const bool b_recompute = dense_can_pair(m);
             StepProducts spb; spb.other = &F; spb.P = F.d_final; spb.d_freqs = d_freqs; spb.d_err = b_err.as<int>();
             PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = b_recompute ? nullptr : &spb; pb.group = group;
-            if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);
+            // The two directions do not depend on each other (with the recompute passes), and their sparse phases are latency-bound per
+            // read: a second host thread drives the backward direction on the handle's second stream set.  Order: forward dense rows ->
+            // (first-row inputs gathered, slabs released) -> backward dense rows -> BOTH sparse phases side by side.  With fewer reads
+            // than half a resident wave the two sparse kernels share the SMs and the phase costs one latency instead of two; a full
+            // wave still fills the tail of one kernel with the head of the other.  DBGPHMM_OVERLAP=0: one thread, one phase at a time.
+            bool overlap = b_recompute && fk == DBGPHMM_FWD_SPARSE && bk == DBGPHMM_BWD_SPARSE;
+            if (const char* e = getenv("DBGPHMM_OVERLAP")) overlap = overlap && e[0] != '0';
+            if (st == DBGPHMM_OK && overlap) {
+                Gate f_dense_done, b_dense_done;
+                pf.force_gather = true;
+                pf.after_dense = [&] { f_dense_done.open(); b_dense_done.wait(); };
+                pb.before_dense = [&] { f_dense_done.wait(); };
+                pb.after_dense = [&] { b_dense_done.open(); };
+                int st_b = DBGPHMM_OK; std::string err_b; EngineTimes times_b;
+                std::thread tb([&] {
+                    tl_stream_set = 1;
+                    try {
+                        if (cudaSetDevice(m->device) != cudaSuccess) { dbg_set_error("cudaSetDevice failed in the backward thread"); st_b = DBGPHMM_ERR_CUDA; }
+                        else {
+                            cache_set_stream(MSET(m).stream);
+                            g_times = EngineTimes();
+                            st_b = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, nullptr, &B);
+                        }
+                    } catch (const std::bad_alloc&) { dbg_set_error("out of host memory"); st_b = DBGPHMM_ERR_OOM; }
+                    catch (const std::exception& e) { dbg_set_error(std::string("C++ exception: ") + e.what()); st_b = DBGPHMM_ERR_INVALID; }
+                    if (st_b != DBGPHMM_OK) err_b = dbgphmm_last_error();
+                    b_dense_done.open();          // (whatever happened: nobody waits forever)
+                    times_b = g_times;
+                    launch_timer_release();
+                    cache_set_stream(nullptr);
+                });
+                try { st = run_forward(m, jobs, reads->d_bases, fk, pf, nullptr, &F); }
+                catch (...) { f_dense_done.open(); tb.join(); throw; }
+                f_dense_done.open();
+                tb.join();
+                g_times.dense_ms += times_b.dense_ms; g_times.sparse_ms += times_b.sparse_ms; g_times.dense_cells += times_b.dense_cells;
+                g_times.dense_kernel_ms += times_b.dense_kernel_ms; g_times.dense_kernel_launches += times_b.dense_kernel_launches;
+                g_times.dense_kernel_cells += times_b.dense_kernel_cells;
+                if (st == DBGPHMM_OK && st_b != DBGPHMM_OK) { st = st_b; dbg_set_error(err_b); }
+                spb.P = F.d_final;
+            } else {
+                if (st == DBGPHMM_OK) st = run_forward(m, jobs, reads->d_bases, fk, pf, nullptr, &F);                    // F: sparse rows stored
+                spb.P = F.d_final;    // (allocated by run_forward)
+                if (st == DBGPHMM_OK) st = run_backward(m, jobs, reads->d_bases, bk, pb, nullptr, &F, &B);
+            }
             if (st == DBGPHMM_OK || !b_recompute) accumulated = true;
             if (st == DBGPHMM_OK && b_recompute) st = run_backward_recompute(m, jobs, reads->d_bases, F, B, spb, group);
             if (st == DBGPHMM_OK) st = run_products_freqs(m, jobs, F, B, d_freqs);                                    // sparse x sparse, F sparse x b_init
@@ -646,7 +711,7 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
         { HostTrace tr_r("release"); F.release(); B.release(); }
         if (st == DBGPHMM_ERR_OOM && !accumulated && jobs.size() > 1) {
             if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] batch of %zu reads ran out of device memory: splitting it\n", jobs.size());
-            CUDA_TRY(cudaStreamSynchronize(m->stream));
+            CUDA_TRY(cudaStreamSynchronize(MSET(m).stream));
             cache_trim();
             const size_t mid = bt.first + jobs.size() / 2;
             work.push_back({mid, bt.second});
@@ -665,6 +730,7 @@ extern "C" int dbgphmm_run_node_freqs_dev(dbgphmm_model* m, const dbgphmm_reads*
                                           uint64_t cells[2]) try {
     if (!m || !reads || mode < 0 || mode > 3) { dbg_set_error("run_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     std::vector<double> lf(reads->n_reads), lb(reads->n_reads);
     ST_TRY(run_impl(m, reads, mode, use_max_ratio, mappings, node_freqs_dev, lf.data(), lb.data(), cells, nullptr, 0));
     if (logp_fwd_dev && !lf.empty()) CUDA_TRY(cudaMemcpy(logp_fwd_dev, lf.data(), 8 * lf.size(), cudaMemcpyHostToDevice));
@@ -675,8 +741,9 @@ extern "C" int dbgphmm_run_node_freqs(dbgphmm_model* m, const dbgphmm_reads* rea
                                       double* node_freqs, double* logp_fwd, double* logp_bwd, uint64_t cells[2]) try {
     if (!m || !reads || mode < 0 || mode > 3) { dbg_set_error("run_node_freqs: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     DevBuf b_f;
-    if (node_freqs) { ST_TRY(b_f.alloc(sizeof(double) * m->N)); CUDA_TRY(cudaMemsetAsync(b_f.p, 0, sizeof(double) * m->N, m->stream)); }
+    if (node_freqs) { ST_TRY(b_f.alloc(sizeof(double) * m->N)); CUDA_TRY(cudaMemsetAsync(b_f.p, 0, sizeof(double) * m->N, MSET(m).stream)); }
     ST_TRY(run_impl(m, reads, mode, use_max_ratio, mappings, node_freqs ? b_f.as<double>() : nullptr, logp_fwd, logp_bwd, cells, nullptr, 0));
     if (node_freqs) CUDA_TRY(cudaMemcpy(node_freqs, b_f.p, sizeof(double) * m->N, cudaMemcpyDeviceToHost));
     return DBGPHMM_OK;
@@ -685,6 +752,7 @@ extern "C" int dbgphmm_generate_mappings(dbgphmm_model* m, const dbgphmm_reads* 
                                          dbgphmm_mappings** out) try {
     if (!m || !reads || !out) { dbg_set_error("generate_mappings: bad argument"); return DBGPHMM_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(m->device));
+    cache_set_stream(MSET(m).stream);
     dbgphmm_mappings* mp = new dbgphmm_mappings();
     mp->read_off.push_back(0); mp->row_off.push_back(0);
     // hint.rs:205-217: run_with_mapping if hints exist, else run_sparse_adaptive(use_max_ratio)

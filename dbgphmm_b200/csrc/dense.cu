@@ -1630,12 +1630,12 @@ int dense_configure(dbgphmm_model* m) {
 }
 
 static int ensure_jstep(dbgphmm_model* m, uint32_t n_jobs) {
-    if (n_jobs <= m->jstep_cap) return DBGPHMM_OK;
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
-    cudaFree(m->d_jstep); m->d_jstep = nullptr; m->jstep_cap = 0;
+    if (n_jobs <= MSET(m).jstep_cap) return DBGPHMM_OK;
+    CUDA_TRY(cudaStreamSynchronize(MSET(m).stream));
+    cudaFree(MSET(m).d_jstep); MSET(m).d_jstep = nullptr; MSET(m).jstep_cap = 0;
     const uint32_t cap = std::max<uint32_t>(1024, n_jobs + n_jobs / 2);
-    CUDA_TRY(cudaMalloc(&m->d_jstep, (size_t)cap * sizeof(JStep)));
-    m->jstep_cap = cap;
+    CUDA_TRY(cudaMalloc(&MSET(m).d_jstep, (size_t)cap * sizeof(JStep)));
+    MSET(m).jstep_cap = cap;
     return DBGPHMM_OK;
 }
 
@@ -1643,21 +1643,21 @@ static int ensure_jstep(dbgphmm_model* m, uint32_t n_jobs) {
 int dense_forward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
                        const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, unsigned long long* d_worklist,
                        uint64_t step_cells) {
-    CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), m->stream));
+    CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), MSET(m).stream));
     const uint32_t jpc = fast_jobs_per_cta(m, m->fwd.n_chunks, n_jobs);
     dim3 grid((m->fwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
     ST_TRY(ensure_jstep(m, n_jobs));
-    k_dense_prep<true><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+    k_dense_prep<true><<<(n_jobs + 127) / 128, 128, 0, MSET(m).stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)MSET(m).d_jstep);
     COUNT_LAUNCH();
-    launch_timer_begin(m->stream);
-    k_dense_reg<true><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+    launch_timer_begin(MSET(m).stream);
+    k_dense_reg<true><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->fwd), graph_view(m), m->lin, (const JStep*)MSET(m).d_jstep, n_jobs, pool.Np,
                                                                           d_partials, m->fwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
     COUNT_LAUNCH();
-    k_dense_fwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
+    k_dense_fwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
                                                                              d_active, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks, d_worklist);
-    launch_timer_end(m->stream, step_cells);
+    launch_timer_end(MSET(m).stream, step_cells);
     COUNT_LAUNCH();
-    k_dense_fwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->fwd.n_chunks);
+    k_dense_fwd_finish<<<n_jobs, 256, 0, MSET(m).stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->fwd.n_chunks);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;
@@ -1684,17 +1684,17 @@ int dense_backward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
     const uint32_t jpc = fast_jobs_per_cta(m, nt, n_jobs);
     dim3 grid((nt + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
     ST_TRY(ensure_jstep(m, 2 * n_jobs));
-    k_dense_prep2<false><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+    k_dense_prep2<false><<<(n_jobs + 127) / 128, 128, 0, MSET(m).stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, pool.base, pool.slab_bytes, (JStep*)MSET(m).d_jstep);
     COUNT_LAUNCH();
-    launch_timer_begin(m->stream);
-    k_dense_bwd2<<<grid, WT_WARPS * 32, RS2_SMEM_BYTES, m->stream>>>(plan_view(m->bwd2), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+    launch_timer_begin(MSET(m).stream);
+    k_dense_bwd2<<<grid, WT_WARPS * 32, RS2_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->bwd2), graph_view(m), m->lin, (const JStep*)MSET(m).d_jstep, n_jobs, pool.Np,
                                                                       d_partials, nt, fast_span2(m->lin), d_redo, jpc);
-    launch_timer_end(m->stream, pair_cells);
+    launch_timer_end(MSET(m).stream, pair_cells);
     COUNT_LAUNCH();
-    k_dense_bwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, nullptr, d_partials, nt, 1);
+    k_dense_bwd_finish<<<n_jobs, 256, 0, MSET(m).stream>>>(m->lin, d_jobs, s, d_desc, nullptr, d_partials, nt, 1);
     COUNT_LAUNCH();
     if (second) {
-        k_dense_bwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s + 1, d_desc, nullptr, d_partials + (size_t)n_jobs * nt * 2, nt, 1);
+        k_dense_bwd_finish<<<n_jobs, 256, 0, MSET(m).stream>>>(m->lin, d_jobs, s + 1, d_desc, nullptr, d_partials + (size_t)n_jobs * nt * 2, nt, 1);
         COUNT_LAUNCH();
     }
     CUDA_TRY(cudaGetLastError());
@@ -1704,7 +1704,7 @@ int dense_backward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_j
 // backward step restricted to the (job, tile) pairs of a prebuilt worklist (recompute pass of the stream strategy), no row reduction
 int dense_backward_step_list(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t s, const uint8_t* d_bases, XF* d_partials,
                              const unsigned long long* d_worklist) {
-    k_dense_bwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, nullptr,
+    k_dense_bwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, nullptr,
                                                                              pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks, d_worklist);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
@@ -1718,17 +1718,17 @@ int dense_forward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_jo
     const uint32_t jpc = fast_jobs_per_cta(m, nt, n_jobs);
     dim3 grid((nt + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
     ST_TRY(ensure_jstep(m, 2 * n_jobs));
-    k_dense_prep2<true><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+    k_dense_prep2<true><<<(n_jobs + 127) / 128, 128, 0, MSET(m).stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, pool.base, pool.slab_bytes, (JStep*)MSET(m).d_jstep);
     COUNT_LAUNCH();
-    launch_timer_begin(m->stream);
-    k_dense_fwd2<<<grid, WT_WARPS * 32, RS2_SMEM_BYTES, m->stream>>>(plan_view(m->fwd2), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+    launch_timer_begin(MSET(m).stream);
+    k_dense_fwd2<<<grid, WT_WARPS * 32, RS2_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->fwd2), graph_view(m), m->lin, (const JStep*)MSET(m).d_jstep, n_jobs, pool.Np,
                                                                       d_partials, nt, fast_span2(m->lin), d_redo, jpc);
-    launch_timer_end(m->stream, pair_cells);
+    launch_timer_end(MSET(m).stream, pair_cells);
     COUNT_LAUNCH();
-    k_dense_fwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, nullptr, d_partials, nt, 1);
+    k_dense_fwd_finish<<<n_jobs, 256, 0, MSET(m).stream>>>(m->lin, d_jobs, s, d_desc, nullptr, d_partials, nt, 1);
     COUNT_LAUNCH();
     if (second) {
-        k_dense_fwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s + 1, d_desc, nullptr, d_partials + (size_t)n_jobs * nt, nt, 1);
+        k_dense_fwd_finish<<<n_jobs, 256, 0, MSET(m).stream>>>(m->lin, d_jobs, s + 1, d_desc, nullptr, d_partials + (size_t)n_jobs * nt, nt, 1);
         COUNT_LAUNCH();
     }
     CUDA_TRY(cudaGetLastError());
@@ -1737,7 +1737,7 @@ int dense_forward_pair(dbgphmm_model* m, const DensePool& pool, const DJob* d_jo
 
 int dense_forward_step_list(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t s, const uint8_t* d_bases,
                             const RowDesc* d_desc, XF* d_partials, const unsigned long long* d_worklist) {
-    k_dense_fwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
+    k_dense_fwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->fwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_desc,
                                                                              nullptr, pool.base, pool.slab_bytes, pool.Np, d_partials, m->fwd.n_chunks, d_worklist);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
@@ -1747,21 +1747,21 @@ int dense_forward_step_list(dbgphmm_model* m, const DensePool& pool, const DJob*
 int dense_backward_step(dbgphmm_model* m, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s,
                         const uint8_t* d_bases, RowDesc* d_desc, const int* d_active, XF* d_partials, unsigned long long* d_worklist,
                         uint64_t step_cells) {
-    CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), m->stream));
+    CUDA_TRY(cudaMemsetAsync(d_worklist, 0, sizeof(unsigned long long), MSET(m).stream));
     const uint32_t jpc = fast_jobs_per_cta(m, m->bwd.n_chunks, n_jobs);
     dim3 grid((m->bwd.n_chunks + WT_WARPS - 1) / WT_WARPS, (n_jobs + jpc - 1) / jpc);
     ST_TRY(ensure_jstep(m, n_jobs));
-    k_dense_prep<false><<<(n_jobs + 127) / 128, 128, 0, m->stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)m->d_jstep);
+    k_dense_prep<false><<<(n_jobs + 127) / 128, 128, 0, MSET(m).stream>>>(m->lin, d_jobs, n_jobs, s, d_bases, d_desc, d_active, pool.base, pool.slab_bytes, (JStep*)MSET(m).d_jstep);
     COUNT_LAUNCH();
-    launch_timer_begin(m->stream);
-    k_dense_reg<false><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, (const JStep*)m->d_jstep, n_jobs, pool.Np,
+    launch_timer_begin(MSET(m).stream);
+    k_dense_reg<false><<<grid, WT_WARPS * 32, RS_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->bwd), graph_view(m), m->lin, (const JStep*)MSET(m).d_jstep, n_jobs, pool.Np,
                                                                            d_partials, m->bwd.n_chunks, fast_span(m->lin), d_worklist, jpc);
     COUNT_LAUNCH();
-    k_dense_bwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, m->stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_active,
+    k_dense_bwd<<<16 * m->n_sm, DENSE_THREADS, DENSE_SMEM_BYTES, MSET(m).stream>>>(plan_view(m->bwd), graph_view(m), m->lin, d_jobs, s, d_bases, d_active,
                                                                              pool.base, pool.slab_bytes, pool.Np, d_partials, m->bwd.n_chunks, d_worklist);
-    launch_timer_end(m->stream, step_cells);
+    launch_timer_end(MSET(m).stream, step_cells);
     COUNT_LAUNCH();
-    k_dense_bwd_finish<<<n_jobs, 256, 0, m->stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->bwd.n_chunks);
+    k_dense_bwd_finish<<<n_jobs, 256, 0, MSET(m).stream>>>(m->lin, d_jobs, s, d_desc, d_active, d_partials, m->bwd.n_chunks);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;
@@ -1777,11 +1777,11 @@ int dense_select(dbgphmm_model* m, const DensePool& pool, const SelectReq* d_req
     DevBuf b_tiles;
     if (pre && b_tiles.alloc(sizeof(TileKey) * (size_t)n_reqs * n_tiles) != DBGPHMM_OK) pre = false;   // (no scratch left: the full sweep needs none)
     if (pre) {
-        k_select_tilemax<<<dim3((n_tiles + 7) / 8, n_reqs), 256, 0, m->stream>>>(d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, m->N, n_tiles, b_tiles.as<TileKey>());
+        k_select_tilemax<<<dim3((n_tiles + 7) / 8, n_reqs), 256, 0, MSET(m).stream>>>(d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, m->N, n_tiles, b_tiles.as<TileKey>());
         COUNT_LAUNCH();
         CUDA_TRY(cudaGetLastError());
     }
-    k_dense_select<<<n_reqs, SELECT_THREADS, SELECT_SMEM_BYTES, m->stream>>>(graph_view(m), d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, d_out_ids, d_out_cnt,
+    k_dense_select<<<n_reqs, SELECT_THREADS, SELECT_SMEM_BYTES, MSET(m).stream>>>(graph_view(m), d_reqs, d_active, pool.base, pool.slab_bytes, pool.Np, d_out_ids, d_out_cnt,
                                                                             pre ? b_tiles.as<TileKey>() : nullptr, n_tiles);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());

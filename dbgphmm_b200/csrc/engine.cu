@@ -35,30 +35,44 @@ void launch_timer_flush() {
     }
     g_ev_busy.clear(); g_ev_cells.clear();
 }
+void launch_timer_release() {
+    launch_timer_flush();
+    for (auto& p : g_ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    g_ev_free.clear();
+}
 
-// Device-memory block cache shared by the handles of the process.  Blocks are returned while the work that used them may still
-// be in flight on the owner's stream (stream order protects the next user on that stream), so a block freed by one host thread is
-// handed to another thread only after a device-wide synchronisation.
-struct CacheBlock { void* p; size_t bytes; int device; bool used; std::thread::id owner; };
+// Device-memory block cache shared by the handles of the process, stream-ordered: a block is returned while the work that used it
+// may still be in flight on the stream of the code that frees it (cache_set_stream).  Taking it again on the SAME stream needs
+// nothing (stream order); another stream first waits for an event recorded on the freeing stream at the time of the free, so no
+// device-wide synchronisation is needed when two host threads drive two stream sets of one handle side by side.  Code that frees
+// without a current stream (none of the library's own) falls back to a device synchronisation at the next foreign reuse.
+struct CacheBlock { void* p; size_t bytes; int device; bool used; cudaStream_t owner; cudaEvent_t ev; bool ev_valid; };
 static std::vector<CacheBlock> g_cache;
 static std::recursive_mutex g_cache_mu;
+static thread_local cudaStream_t tl_cache_stream = nullptr;
+void cache_set_stream(cudaStream_t st) { tl_cache_stream = st; }
 void* cache_alloc(size_t bytes) {
     std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
     if (bytes < 256) bytes = 256;
     if (bytes < (1u << 20)) { size_t c = 256; while (c < bytes) c <<= 1; bytes = c; }  // small blocks in power-of-two classes
     int dev = 0; cudaGetDevice(&dev);
-    const std::thread::id me = std::this_thread::get_id();
+    const cudaStream_t me = tl_cache_stream;
     for (int any_owner = 0; any_owner < 2; any_owner++) {
         int best = -1;
         for (size_t i = 0; i < g_cache.size(); i++) {
             const CacheBlock& b = g_cache[i];
-            if (!b.used && b.device == dev && (any_owner || b.owner == me) && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 + (1 << 20))
+            if (!b.used && b.device == dev && (any_owner || (me && b.owner == me)) && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 + (1 << 20))
                 if (best < 0 || b.bytes < g_cache[best].bytes) best = (int)i;
         }
         if (best >= 0) {
-            if (g_cache[best].owner != me) { cudaDeviceSynchronize(); g_cache[best].owner = me; }
-            g_cache[best].used = true;
-            return g_cache[best].p;
+            CacheBlock& b = g_cache[best];
+            if (!me || b.owner != me) {
+                if (b.ev_valid && me) cudaStreamWaitEvent(me, b.ev, 0);
+                else if (b.ev_valid) cudaEventSynchronize(b.ev);
+                else cudaDeviceSynchronize();
+            }
+            b.owner = me; b.used = true;
+            return b.p;
         }
     }
     void* p = nullptr;
@@ -67,13 +81,20 @@ void* cache_alloc(size_t bytes) {
         cache_trim();
         if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
-    g_cache.push_back(CacheBlock{p, bytes, dev, true, me});
+    g_cache.push_back(CacheBlock{p, bytes, dev, true, me, nullptr, false});
     return p;
 }
 void cache_free(void* p) {
     if (!p) return;
     std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
-    for (auto& b : g_cache) if (b.p == p) { b.used = false; b.owner = std::this_thread::get_id(); return; }
+    for (auto& b : g_cache) if (b.p == p) {
+        b.used = false; b.owner = tl_cache_stream; b.ev_valid = false;
+        if (tl_cache_stream) {
+            if (!b.ev && cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); b.ev = nullptr; }
+            if (b.ev && cudaEventRecord(b.ev, tl_cache_stream) == cudaSuccess) b.ev_valid = true; else cudaGetLastError();
+        }
+        return;
+    }
     cudaFree(p);
 }
 uint64_t cache_unused_bytes() {
@@ -97,7 +118,7 @@ void cache_trim() {
     int dev = 0; cudaGetDevice(&dev);
     std::vector<CacheBlock> keep;
     for (auto& b : g_cache) {
-        if (!b.used && b.device == dev) cudaFree(b.p);
+        if (!b.used && b.device == dev) { cudaFree(b.p); if (b.ev) cudaEventDestroy(b.ev); }   // (cudaFree waits for the device)
         else keep.push_back(b);
     }
     g_cache.swap(keep);
@@ -218,7 +239,7 @@ __global__ void k_verify_rows(uint32_t n_jobs, const RowDesc* __restrict__ desc,
 }
 // rows [row_lo[j], row_hi[j]) of every job must be well-formed
 static int verify_rows(dbgphmm_model* m, const char* what, const RowStore& S, const std::vector<uint32_t>& row_lo, const std::vector<uint32_t>& row_hi) {
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     const uint32_t J = (uint32_t)S.len.size();
     if (J == 0) return DBGPHMM_OK;
     DevBuf b_lo, b_hi, b_len, b_n, b_recs;
@@ -247,7 +268,7 @@ static int verify_rows(dbgphmm_model* m, const char* what, const RowStore& S, co
 // Run a set of sparse jobs, re-running the ones that overflowed the small shared-memory capacity with the big one.
 static int run_sparse_jobs_once(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io, RowStore* store, uint32_t small_cap) {
     if (sj.empty()) return DBGPHMM_OK;
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     const uint32_t n = (uint32_t)sj.size();
     for (const SJob& j : sj) if (j.dir != sj[0].dir) { dbg_set_error("internal: sparse jobs of one launch must share their direction"); return DBGPHMM_ERR_INVALID; }
     DevBuf b_jobs, b_status, b_final, b_cells;
@@ -345,9 +366,9 @@ static int run_sparse_jobs(dbgphmm_model* m, std::vector<SJob>& sj, SparseIO io,
     if (st != ST_ARENA_FULL) return st;
     if (io.arena_bytes >= upper_bytes || getenv("DBGPHMM_ARENA_MAX_BYTES")) { dbg_set_error("sparse row arena exhausted"); return DBGPHMM_ERR_OOM; }
     if (getenv("DBGPHMM_TRACE")) fprintf(stderr, "[dbgphmm] sparse arena of %.1f MB exhausted: repeating the phase with %.1f MB\n", io.arena_bytes / 1e6, upper_bytes / 1e6);
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    CUDA_TRY(cudaStreamSynchronize(MSET(m).stream));
     cache_free(store->arena.base); cache_free(store->arena.cursor); store->arena = SparseArena();
-    ST_TRY(alloc_arena(store->arena, upper_bytes, m->stream));
+    ST_TRY(alloc_arena(store->arena, upper_bytes, MSET(m).stream));
     io.arena = store->arena.base; io.arena_bytes = store->arena.bytes; io.arena_cursor = store->arena.cursor;
     store->cells = cells0;
     st = run_sparse_jobs_once(m, sj, io, store, small_cap);
@@ -368,15 +389,15 @@ struct GatherBufs {
 static int gather_init(dbgphmm_model* m, uint32_t J, GatherBufs* g) {
     g->cap = sparse_gather_cap(m, m->params.n_active_nodes);
     ST_TRY(g->cells.alloc((size_t)J * 32 * g->cap)); ST_TRY(g->cnt.alloc(sizeof(uint32_t) * std::max<uint32_t>(J, 1))); ST_TRY(g->ovf.alloc(sizeof(int)));
-    CUDA_TRY(cudaMemsetAsync(g->cnt.p, 0, sizeof(uint32_t) * std::max<uint32_t>(J, 1), m->stream));
-    CUDA_TRY(cudaMemsetAsync(g->ovf.p, 0, sizeof(int), m->stream));
+    CUDA_TRY(cudaMemsetAsync(g->cnt.p, 0, sizeof(uint32_t) * std::max<uint32_t>(J, 1), MSET(m).stream));
+    CUDA_TRY(cudaMemsetAsync(g->ovf.p, 0, sizeof(int), MSET(m).stream));
     g->on = true;
     return DBGPHMM_OK;
 }
 // slab_of_job[i]: the last dense row of job g0 + i (~0: none)
 static int gather_group(dbgphmm_model* m, int dir, uint32_t g0, const std::vector<uint64_t>& slab_of_job, const uint32_t* d_top_ids, const uint32_t* d_top_cnt,
                         const DensePool& pool, GatherBufs* g) {
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     ST_TRY(dev_upload(g->slabs, slab_of_job, st));
     ST_TRY(sparse_gather_prev0(m, dir, g0, (uint32_t)slab_of_job.size(), d_top_ids, d_top_cnt, g->slabs.as<uint64_t>(), pool.base, pool.slab_bytes, pool.Np, g->cap,
                                g->cells.as<char>(), g->cnt.as<uint32_t>(), g->ovf.as<int>()));
@@ -393,7 +414,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     const bool keep_rows = opt.keep_rows, store_sparse = opt.store_sparse;
     HostTrace tr_all("run_forward");
     HostTrace* tr_setup = new HostTrace("  fwd setup");
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup;
     out->dir = 0; out->dense_kept = keep_rows;
     out->desc0.resize(J); out->len.resize(J); out->nd.assign(J, 0); out->h_final.assign(J, xf_zero());
@@ -410,7 +431,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
     // ---- dense phase layout
     // top-n jobs whose dense rows are not kept: the first sparse row reads gathered cells, and the warm-up may run in groups of G jobs
     // that share one pool of slabs (slab indices are then relative to the group)
-    const bool use_gather = kind == DBGPHMM_FWD_SPARSE && !keep_rows && !opt.dense_only && !opt.step && (gather_enabled() || opt.group > 0);
+    const bool use_gather = kind == DBGPHMM_FWD_SPARSE && !keep_rows && !opt.dense_only && !opt.step && (gather_enabled() || opt.group > 0 || opt.force_gather);
     const uint32_t G = (use_gather && opt.group > 0 && opt.group < J) ? opt.group : std::max<uint32_t>(J, 1);
     std::vector<uint32_t> nd_max(J);
     std::vector<DJob> dj(J);
@@ -521,6 +542,7 @@ int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* 
         if (use_gather) { cache_free(out->pool.base); out->pool.base = nullptr; }   // the ping-pong slabs are dead already
     }
     for (uint32_t j = 0; j < J; j++) { out->cells += (uint64_t)out->nd[j] * N; g_times.dense_cells += (uint64_t)out->nd[j] * N; }
+    if (opt.after_dense) opt.after_dense();
     // ---- sparse phase
     std::vector<SJob> sj;
     uint64_t sparse_rows = 0;
@@ -575,7 +597,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
                  const DevMappings* dmap, const RowStore* fwd, RowStore* out) {
     const bool keep_rows = opt.keep_rows;
     HostTrace tr_all("run_backward");
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup;
     out->dir = 1; out->dense_kept = keep_rows;
     out->desc0.resize(J); out->len.resize(J); out->nd.assign(J, 0); out->h_final.assign(J, xf_zero());
@@ -595,7 +617,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     uint64_t n_slabs = 0, slab_cur = 0; uint32_t steps = 0;
     const bool sparse_first = kind == DBGPHMM_BWD_BY_FORWARD;
     // (see run_forward) top-n jobs whose dense rows are not kept: gathered first-row inputs, warm-up in groups of G jobs
-    const bool use_gather = kind == DBGPHMM_BWD_SPARSE && !keep_rows && !opt.step && (gather_enabled() || opt.group > 0);
+    const bool use_gather = kind == DBGPHMM_BWD_SPARSE && !keep_rows && !opt.step && (gather_enabled() || opt.group > 0 || opt.force_gather);
     const uint32_t G = (use_gather && opt.group > 0 && opt.group < J) ? opt.group : std::max<uint32_t>(J, 1);
     for (uint32_t j = 0; j < J; j++) {
         int n = (int)jobs[j].len;
@@ -620,6 +642,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
     }
     out->slab0.resize(J);
     for (uint32_t j = 0; j < J; j++) out->slab0[j] = dj[j].slab0;
+    if (opt.before_dense) opt.before_dense();
     { HostTrace t("  bwd alloc_pool"); ST_TRY(alloc_pool(out->pool, N, n_slabs)); }
     DevBuf b_dj, b_len, b_part, b_top_ids, b_top_cnt, b_reqs;
     ST_TRY(dev_upload(b_dj, dj, st));
@@ -726,6 +749,7 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
             }
         }
         if (use_gather) { cache_free(out->pool.base); out->pool.base = nullptr; }   // the ping-pong slabs are dead already
+        if (opt.after_dense) opt.after_dense();
         ST_TRY(sparse_phase());
     } else {
         ST_TRY(sparse_phase());
@@ -813,7 +837,7 @@ __global__ void k_roi_mark_b(uint32_t W, const RowDesc* __restrict__ fdesc, cons
 int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
                            const StepProducts& sp, uint32_t group) {
     HostTrace tr("run_backward_recompute");
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup, T = m->bwd.n_chunks;
     ST_TRY(model_ensure_roi(m));
     EvTimer tm(st, &g_times.dense_ms);
@@ -858,7 +882,7 @@ int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, cons
 int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, const RowStore& F, const RowStore& B,
                           const StepProducts& sp, uint32_t group) {
     HostTrace tr("run_forward_recompute");
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     const uint32_t J = (uint32_t)jobs.size(), N = m->N, W = m->params.n_warmup, T = m->fwd.n_chunks;
     ST_TRY(model_ensure_roi(m));
     EvTimer tm(st, &g_times.dense_ms);

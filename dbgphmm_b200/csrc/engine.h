@@ -1,5 +1,6 @@
 // engine.h — batch orchestration of the dense / sparse phases, row stores, products (internal).
 #pragma once
+#include <functional>
 #include <vector>
 #include "dense.h"
 #include "sparse.h"
@@ -40,6 +41,7 @@ struct RowStore {
 };
 
 // Caching allocator for the large row buffers (cudaMalloc / cudaFree of tens of GB cost ~100 ms each).
+void cache_set_stream(cudaStream_t st);   // the stream this host thread's allocations are used on / freed behind (stream-ordered reuse)
 void* cache_alloc(size_t bytes);   // nullptr on failure
 void cache_free(void* p);
 void cache_trim();                 // give every unused block back to the driver
@@ -95,6 +97,7 @@ struct EngineTimes {
 void launch_timer_begin(cudaStream_t st);
 void launch_timer_end(cudaStream_t st, uint64_t cells);
 void launch_timer_flush();
+void launch_timer_release();   // destroy this thread's pooled events (helper threads call it before they end)
 extern thread_local EngineTimes g_times;   // timings of the last bulk call made by this host thread
 
 // Products taken on the fly, right after a dense row has been computed, against the OTHER direction's stored sparse
@@ -110,6 +113,10 @@ struct PhaseOpts {
     bool store_sparse = true;   // sparse rows written to the arena
     bool dense_only = false;    // forward: stop after the dense rows (recompute pass)
     uint32_t group = 0;         // top-n jobs without kept rows: dense warm-up in groups of this many jobs sharing one pool of slabs (0: one group)
+    bool force_gather = false;  // top-n jobs without kept rows: the first sparse row reads gathered cells and the slabs are released before the sparse phase
+    // hooks of the two-thread bulk path (api.cu): called before the dense rows' slabs are allocated (backward) / once the dense phase is
+    // over and, with gathered first-row inputs, its slabs have been released -- right before the sparse phase
+    std::function<void()> before_dense, after_dense;
     const StepProducts* step = nullptr;
 };
 

@@ -425,7 +425,7 @@ int model_ensure_roi(dbgphmm_model* m) {
 void model_free(dbgphmm_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of); cudaFree(m->d_jstep);
+    cudaFree(m->d_roi_off); cudaFree(m->d_roi_tile); cudaFree(m->d_tile_of);
     cudaFree(m->d_roi_off_b); cudaFree(m->d_roi_tile_b); cudaFree(m->d_tile_of_b);
     cudaFree(m->d_pos_of); cudaFree(m->d_orig_of); cudaFree(m->d_emission);
     cudaFree(m->d_par_off); cudaFree(m->d_par_node); cudaFree(m->d_par_eid);
@@ -433,13 +433,19 @@ void model_free(dbgphmm_model* m) {
     cudaFree(m->d_par_rec); cudaFree(m->d_chi_rec);
     cudaFree(m->d_init); cudaFree(m->d_trans);
     free_plan(m->fwd); free_plan(m->bwd); free_plan(m->fwd2); free_plan(m->bwd2);
+    cache_set_stream(nullptr);   // (this handle's streams are about to go)
     cache_trim();
-    if (m->stream) cudaStreamDestroy(m->stream);
-    if (m->stream_aux) cudaStreamDestroy(m->stream_aux);
-    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-    if (m->ev_join) cudaEventDestroy(m->ev_join);
+    for (auto& ss : m->ss) {
+        cudaFree(ss.d_jstep);
+        if (ss.stream) cudaStreamDestroy(ss.stream);
+        if (ss.aux) cudaStreamDestroy(ss.aux);
+        if (ss.ev_fork) cudaEventDestroy(ss.ev_fork);
+        if (ss.ev_join) cudaEventDestroy(ss.ev_join);
+    }
     delete m;
 }
+
+thread_local int tl_stream_set = 0;
 
 // ------------------------------------------------------------------ copy numbers -> parameters on the device
 // graph/seq_graph.rs:110-135,160-273 with edge copy numbers None (multi_dbg.rs:1386-1387,1434-1437).
@@ -490,18 +496,18 @@ extern "C" int dbgphmm_model_set_copy_nums_batch(dbgphmm_model* m, uint32_t n_ba
     uint32_t* d_cn = nullptr; unsigned long long* d_total = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_cn, sizeof(uint32_t) * (size_t)n_batch * N));
     CUDA_TRY(cudaMalloc((void**)&d_total, sizeof(unsigned long long) * n_batch));
-    CUDA_TRY(cudaMemcpyAsync(d_cn, copy_nums, sizeof(uint32_t) * (size_t)n_batch * N, cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long) * n_batch, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_cn, copy_nums, sizeof(uint32_t) * (size_t)n_batch * N, cudaMemcpyHostToDevice, MSET(m).stream));
+    CUDA_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long) * n_batch, MSET(m).stream));
     cudaFree(m->d_init); cudaFree(m->d_trans); m->d_init = m->d_trans = nullptr;
     CUDA_TRY(cudaMalloc((void**)&m->d_init, sizeof(double) * (size_t)n_batch * std::max<uint32_t>(N, 1)));
     CUDA_TRY(cudaMalloc((void**)&m->d_trans, sizeof(double) * (size_t)n_batch * std::max<uint32_t>(E, 1)));
     m->n_batch = n_batch;
     dim3 g1(std::min<uint32_t>((N + 255) / 256, 1024), n_batch), g2((N + 255) / 256, n_batch);
-    k_copy_total<<<g1, 256, 0, m->stream>>>(d_cn, m->d_emission, m->d_orig_of, N, mode, d_total); COUNT_LAUNCH();
-    k_copy_to_probs<<<g2, 256, 0, m->stream>>>(d_cn, m->d_emission, m->d_orig_of, m->d_chi_off, m->d_chi_node, m->d_chi_eid, N, E, mode,
+    k_copy_total<<<g1, 256, 0, MSET(m).stream>>>(d_cn, m->d_emission, m->d_orig_of, N, mode, d_total); COUNT_LAUNCH();
+    k_copy_to_probs<<<g2, 256, 0, MSET(m).stream>>>(d_cn, m->d_emission, m->d_orig_of, m->d_chi_off, m->d_chi_node, m->d_chi_eid, N, E, mode,
                                                 d_total, m->d_init, m->d_trans); COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    CUDA_TRY(cudaStreamSynchronize(MSET(m).stream));
     cudaFree(d_cn); cudaFree(d_total);
     return DBGPHMM_OK;
 } ABI_CATCH
@@ -536,10 +542,11 @@ extern "C" int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const ui
     dbgphmm_model* m = new dbgphmm_model();
     m->device = device; m->params = *params; m->lin = to_lin(*params);
     int st = DBGPHMM_OK;
-    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream_aux, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        dbg_set_error("stream create failed"); st = DBGPHMM_ERR_CUDA;
-    }
+    for (auto& ss : m->ss)
+        if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ss.aux, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss.ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ss.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            dbg_set_error("stream create failed"); st = DBGPHMM_ERR_CUDA;
+        }
     if (st == DBGPHMM_OK) st = model_build_graph(m, n_nodes, n_edges, edge_src, edge_dst, emission);
     if (st == DBGPHMM_OK) st = model_upload_probs(m, log_init, log_trans);
     if (st == DBGPHMM_OK) {

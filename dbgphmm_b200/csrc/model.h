@@ -68,6 +68,9 @@ struct DevPlan {
     std::vector<uint32_t> h_chunk_start;
 };
 
+extern thread_local int tl_stream_set;   // which StreamSet of a model this host thread drives (0 unless a bulk call says otherwise)
+#define MSET(m) ((m)->ss[tl_stream_set])
+
 struct dbgphmm_model {
     int device = 0;
     uint32_t N = 0, E = 0;
@@ -77,9 +80,15 @@ struct dbgphmm_model {
     uint64_t mem_budget = 0;        // fixed by the caller, or 88 % of the memory free at creation (fallback only: see model_budget)
     bool mem_budget_fixed = false;
     int n_sm = 148;
-    cudaStream_t stream = nullptr;
-    cudaStream_t stream_aux = nullptr;            // rescue launch of the sparse kernel (sparse.cu)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Two sets of streams / per-launch scratch: a bulk call may drive the forward and the backward direction from two host threads
+    // (api.cu: the sparse phases of both directions then run side by side); every thread works on the set its tl_stream_set names.
+    struct StreamSet {
+        cudaStream_t stream = nullptr;
+        cudaStream_t aux = nullptr;                // rescue launch of the sparse kernel (sparse.cu)
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        void* d_jstep = nullptr; uint32_t jstep_cap = 0;   // per-(job, step) scalars of the dense fast kernel (dense.cu: JStep)
+    };
+    mutable StreamSet ss[2];
 
     // host copies (relabelled ids unless noted)
     std::vector<uint32_t> pos_of;   // [N] original id -> relabelled
@@ -107,7 +116,6 @@ struct dbgphmm_model {
     uint32_t roi_warmup = 0;
     uint32_t *d_roi_off = nullptr, *d_roi_tile = nullptr, *d_tile_of = nullptr;
     uint32_t *d_roi_off_b = nullptr, *d_roi_tile_b = nullptr, *d_tile_of_b = nullptr;   // the same for backward tiles (downstream closure)
-    void* d_jstep = nullptr; uint32_t jstep_cap = 0;   // per-(job, step) scalars of the dense fast kernel (dense.cu: JStep)
 };
 int model_ensure_roi(dbgphmm_model* m);
 

@@ -343,7 +343,7 @@ __global__ void k_prod_step(const DJob* __restrict__ jobs, uint32_t s, int dir, 
 }
 int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& pool, const DJob* d_jobs, uint32_t n_jobs, uint32_t s, int dir, uint32_t job0) {
     if (!sp.other->d_desc0) { dbg_set_error("step_products: the other direction has no device row index"); return DBGPHMM_ERR_INVALID; }
-    k_prod_step<<<n_jobs, 128, 0, m->stream>>>(d_jobs, s, dir, pool.base, pool.slab_bytes, pool.Np, sp.other->d_desc, sp.other->d_desc0 + job0,
+    k_prod_step<<<n_jobs, 128, 0, MSET(m).stream>>>(d_jobs, s, dir, pool.base, pool.slab_bytes, pool.Np, sp.other->d_desc, sp.other->d_desc0 + job0,
                                                sp.other->arena.base, sp.P + job0, m->d_orig_of, sp.d_freqs, sp.d_err);
     COUNT_LAUNCH();
     return DBGPHMM_OK;
@@ -353,7 +353,7 @@ int step_products(dbgphmm_model* m, const StepProducts& sp, const DensePool& poo
 struct ProdBufs { DevBuf fdesc0, bdesc0, len, pairs, err; };
 
 static int make_ctx(dbgphmm_model* m, const RowStore& F, const RowStore& B, ProdBufs& pb, ProdCtx* C) {
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     ST_TRY(dev_upload(pb.fdesc0, F.desc0, st)); ST_TRY(dev_upload(pb.bdesc0, B.desc0, st)); ST_TRY(dev_upload(pb.len, F.len, st));
     ST_TRY(pb.err.alloc(sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(pb.err.p, 0, sizeof(int), st));
@@ -384,7 +384,7 @@ static void dense_pairs(const RowStore& F, const RowStore& B, std::vector<DenseP
 
 int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, double* d_freqs) {
     HostTrace tr("run_products_freqs");
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     EvTimer tm(st, &g_times.product_ms);
     const uint32_t J = (uint32_t)jobs.size();
     if (J == 0) return DBGPHMM_OK;
@@ -419,7 +419,7 @@ int run_products_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const Ro
 // all their rows (the store strategy).
 int run_products_edge_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, const uint8_t* d_bases,
                             double* d_edge, double* d_init) {
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     EvTimer tm(st, &g_times.product_ms);
     const uint32_t J = (uint32_t)jobs.size();
     if (J == 0) return DBGPHMM_OK;
@@ -445,7 +445,7 @@ int run_products_edge_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, con
 
 int run_products_mapping(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, int by_ratio,
                          uint32_t n_active, double ratio, dbgphmm_mappings* out) {
-    cudaStream_t st = m->stream;
+    cudaStream_t st = MSET(m).stream;
     EvTimer tm(st, &g_times.product_ms);
     const uint32_t J = (uint32_t)jobs.size();
     ProdBufs pb; ProdCtx C;

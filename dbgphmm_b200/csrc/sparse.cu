@@ -47,26 +47,27 @@ struct SS {
     // ping-pong node lists (ids + slots) and the step's `nodes` (m/i entries)
     __device__ __forceinline__ uint32_t* la_id(int k) const { return (uint32_t*)(base + (size_t)(96 + 4 * k) * cap); }
     SS_ARR(uint32_t, act_id, 104)
-    SS_ARR(uint32_t, top_id, 108)
-    __device__ __forceinline__ uint16_t* la_slot(int k) const { return (uint16_t*)(base + (size_t)(112 + 2 * k) * cap); }
-    SS_ARR(uint16_t, act_slot, 116)
-    SS_ARR(uint16_t, dlist, 118)         // slots in d insertion order
-    __device__ __forceinline__ uint8_t* dstamp(int k) const { return (uint8_t*)(base + (size_t)(120 + k) * cap); }
-    SS_ARR(uint8_t, d_seen, 122)
-    SS_ARR(uint32_t, scan, 123)          // [cap + 4] scratch
+    // the step's top list is dead once `nodes` has been expanded from it, before Del round 1 first writes la_id(1): same storage
+    __device__ __forceinline__ uint32_t* top_id() const { return la_id(1); }
+    __device__ __forceinline__ uint16_t* la_slot(int k) const { return (uint16_t*)(base + (size_t)(108 + 2 * k) * cap); }
+    SS_ARR(uint16_t, act_slot, 112)
+    SS_ARR(uint16_t, dlist, 114)         // slots in d insertion order
+    __device__ __forceinline__ uint8_t* dstamp(int k) const { return (uint8_t*)(base + (size_t)(116 + k) * cap); }
+    SS_ARR(uint8_t, d_seen, 118)
+    SS_ARR(uint32_t, scan, 119)          // [cap + 4] scratch
     // ranking keys alias the Del round buffers, which are dead between rows
     __device__ __forceinline__ int* k_T() const { return dexp(0); }
     __device__ __forceinline__ unsigned long long* k_mant() const { return (unsigned long long*)dval(0); }
-    // after the cap-proportional part (127 cap + 16 bytes): block_prefix scratch [2][8] + flags, then the two hash tables
-    __device__ __forceinline__ uint32_t* wt() const { return (uint32_t*)(base + (size_t)127 * cap + 16); }
-    __device__ __forceinline__ uint32_t* htab(uint32_t which) const { return (uint32_t*)(base + (size_t)127 * cap + 16 + 96) + (size_t)which * 2 * hcap; }
+    // after the cap-proportional part (123 cap + 16 bytes): block_prefix scratch [2][8] + flags, then the two hash tables
+    __device__ __forceinline__ uint32_t* wt() const { return (uint32_t*)(base + (size_t)123 * cap + 16); }
+    __device__ __forceinline__ uint32_t* htab(uint32_t which) const { return (uint32_t*)(base + (size_t)123 * cap + 16 + 96) + (size_t)which * 2 * hcap; }
     __device__ __forceinline__ uint32_t* ch_key() const { return htab(htog); }
     __device__ __forceinline__ uint32_t* ch_val() const { return htab(htog) + hcap; }
     __device__ __forceinline__ uint32_t* ph_key() const { return htab(htog ^ 1u); }
     __device__ __forceinline__ uint32_t* ph_val() const { return htab(htog ^ 1u) + hcap; }
 #undef SS_ARR
 };
-#define SS_BYTES(cap, hcap) ((size_t)127 * (cap) + 16 + 96 + (size_t)16 * (hcap))
+#define SS_BYTES(cap, hcap) ((size_t)123 * (cap) + 16 + 96 + (size_t)16 * (hcap))
 
 __device__ __forceinline__ uint32_t sp_hash(uint32_t id, int shift) { return (id * 2654435761u) >> shift; }
 __device__ __forceinline__ int sp_find(const uint32_t* key, const uint32_t* val, uint32_t hmask, int hshift, uint32_t id) {
@@ -302,29 +303,21 @@ __device__ void sp_rank(SS& S, uint32_t n, uint32_t KK, const uint32_t* ids, uin
     const int tid = threadIdx.x, B = blockDim.x;
     uint32_t* bad = S.wt() + 16;   // zero between rankings (reset below after use)
     if (!*bad) {
-        // f precedes e iff kf > ke, or kf == ke and f < e.  Keys stay below 2^63, so as signed integers that is kf > ke - (f < e): a
-        // threshold instead of an addition per key.  Pairs of keys per load ; the pairs wholly below this warp's smallest e compare
-        // against ke - 1, the pairs wholly above its largest e against ke (no per-key choice), only the pairs in between choose.
-        const longlong2* k2 = (const longlong2*)S.k_mant();   // (16-byte aligned: cap is a multiple of 16)
-        const long long* k1 = (const long long*)S.k_mant();
-        const uint32_t np = n >> 1;
-        for (uint32_t e0 = tid & ~31u; e0 < n; e0 += B) {   // (whole warps: the range split below is warp-uniform)
-            const uint32_t e = e0 + (tid & 31u);
-            const bool on = e < n;
-            const long long ke = on ? k1[e] : 0, ke1 = ke - 1;
-            const uint32_t p_lo = min(e0 >> 1, np), p_hi = min((e0 + 32u) >> 1, np);   // pairs [p_lo, p_hi) straddle this warp's entries
+        // f precedes e iff kf > ke, or kf == ke and f < e: that is kf + (f < e) > ke (keys stay below 2^63) ; two keys per load
+        // (a variant with thresholds ke - (f < e) and warp-uniform loop ranges measured 5 % slower: three short loops instead of one)
+        const ulonglong2* k2 = (const ulonglong2*)S.k_mant();   // (16-byte aligned: cap is a multiple of 16)
+        for (uint32_t e = tid; e < n; e += B) {
+            const unsigned long long ke = S.k_mant()[e];
             uint32_t rank = 0;
-            for (uint32_t p2 = 0; p2 < p_lo; p2++) { const longlong2 kf = k2[p2]; rank += (kf.x > ke1) + (kf.y > ke1); }
-            for (uint32_t p2 = p_lo; p2 < p_hi; p2++) {
-                const longlong2 kf = k2[p2];
-                rank += (kf.x > (2 * p2 < e ? ke1 : ke)) + (kf.y > (2 * p2 + 1 < e ? ke1 : ke));
+#pragma unroll 2
+            for (uint32_t f = 0; f + 1 < n; f += 2) {
+                const ulonglong2 kf = k2[f >> 1];
+                rank += (kf.x + (f < e ? 1ull : 0ull) > ke) ? 1u : 0u;
+                rank += (kf.y + (f + 1 < e ? 1ull : 0ull) > ke) ? 1u : 0u;
             }
-            for (uint32_t p2 = p_hi; p2 < np; p2++) { const longlong2 kf = k2[p2]; rank += (kf.x > ke) + (kf.y > ke); }
-            if (n & 1u) rank += k1[n - 1] > (n - 1 < e ? ke1 : ke);
-            if (on) {
-                if (rank < KK) out_id[rank] = ids[e];
-                S.scan()[e] = rank;
-            }
+            if (n & 1u) rank += (S.k_mant()[n - 1] + (n - 1 < e ? 1ull : 0ull) > ke) ? 1u : 0u;
+            if (rank < KK) out_id[rank] = ids[e];
+            S.scan()[e] = rank;
         }
     } else {
         const unsigned long long M52 = 0xfffffffffffffull;
@@ -886,7 +879,7 @@ int sparse_gather_prev0(dbgphmm_model* m, int dir, uint32_t slot0, uint32_t n, c
     if (n == 0) return DBGPHMM_OK;
     SGraph G{m->N, m->E, m->d_emission, m->d_init, m->d_trans, m->d_par_off, m->d_par_node, m->d_par_eid,
              m->d_chi_off, m->d_chi_node, m->d_chi_eid, m->d_pos_of, m->d_par_rec, m->d_chi_rec};
-    k_gather_prev0<<<n, 64, 0, m->stream>>>(G, dir, slot0, d_top_ids, d_top_cnt, d_slabs, pool, slab_bytes, Np, cap, d_out, d_out_cnt, d_overflow);
+    k_gather_prev0<<<n, 64, 0, MSET(m).stream>>>(G, dir, slot0, d_top_ids, d_top_cnt, d_slabs, pool, slab_bytes, Np, cap, d_out, d_out_cnt, d_overflow);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return DBGPHMM_OK;
@@ -911,8 +904,11 @@ uint32_t sparse_default_cap() {
 }
 
 uint32_t sparse_rescue_cap(uint32_t cap) {
-    if (const char* e = getenv("DBGPHMM_SPARSE_RESCUE")) { if (e[0] == '0') return 0; }
-    return cap < 256 ? 256 : 0;
+    // 192 entries: with the 128-entry primary tables that leaves shared memory for 9 primary jobs per SM beside one rescue CTA (256 -> 8).
+    // No row of the C3 / C5 workloads outgrows it (a row that does is re-run with 256 / 832 entries: correct, one job latency slower).
+    uint32_t rc = 192;
+    if (const char* e = getenv("DBGPHMM_SPARSE_RESCUE")) { const int v = atoi(e); if (v <= 0) return 0; if (v >= 64 && v <= 832) rc = ((uint32_t)v + 15u) & ~15u; }
+    return cap < rc ? rc : 0;
 }
 
 static uint32_t hcap_of(uint32_t cap) {
@@ -932,8 +928,11 @@ uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
         per_sm = 1;
     }
     if (rcap) {
+        // (DBGPHMM_SPARSE_MARGIN: bytes kept free per SM beside the primary CTAs and the rescue CTA)
+        size_t margin = 4096;
+        if (const char* e = getenv("DBGPHMM_SPARSE_MARGIN")) margin = (size_t)atoi(e);
         const size_t sm_bytes = 227 * 1024, one = sparse_smem_bytes(cap, hcap_of(cap)) + 1024, big = sparse_smem_bytes(rcap, hcap_of(rcap)) + 1024;
-        const int fit = (int)((sm_bytes - big) / one);
+        const int fit = (int)((sm_bytes - big - margin) / one);
         if (fit >= 1 && fit < per_sm) per_sm = fit;
     }
     return (uint32_t)per_sm * (uint32_t)m->n_sm;
@@ -961,16 +960,16 @@ int sparse_run(dbgphmm_model* m, const SJob* d_jobs, uint32_t n_jobs, const Spar
     SparseIO io = io_in;
     if (!rescue_cap || !io.rq_ctl) {
         io.rq_ctl = nullptr;
-        return sparse_launch(m, m->stream, n_jobs, G, d_jobs, io, cap, 0, dir);
+        return sparse_launch(m, MSET(m).stream, n_jobs, G, d_jobs, io, cap, 0, dir);
     }
     // primary: as many persistent CTAs as stay resident beside one rescue CTA per SM ; rescue CTAs idle until a job is handed over
     const uint32_t grid = std::min<uint32_t>(n_jobs, sparse_wave_jobs(m, cap));
     io.rq_cap = cap; io.rq_n_primary = grid; io.rq_n_jobs = n_jobs;
-    CUDA_TRY(cudaEventRecord(m->ev_fork, m->stream));
-    CUDA_TRY(cudaStreamWaitEvent(m->stream_aux, m->ev_fork, 0));
-    ST_TRY(sparse_launch(m, m->stream, grid, G, d_jobs, io, cap, 0, dir));
-    ST_TRY(sparse_launch(m, m->stream_aux, std::min<uint32_t>(n_jobs, (uint32_t)m->n_sm), G, d_jobs, io, rescue_cap, 1, dir));
-    CUDA_TRY(cudaEventRecord(m->ev_join, m->stream_aux));
-    CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+    CUDA_TRY(cudaEventRecord(MSET(m).ev_fork, MSET(m).stream));
+    CUDA_TRY(cudaStreamWaitEvent(MSET(m).aux, MSET(m).ev_fork, 0));
+    ST_TRY(sparse_launch(m, MSET(m).stream, grid, G, d_jobs, io, cap, 0, dir));
+    ST_TRY(sparse_launch(m, MSET(m).aux, std::min<uint32_t>(n_jobs, (uint32_t)m->n_sm), G, d_jobs, io, rescue_cap, 1, dir));
+    CUDA_TRY(cudaEventRecord(MSET(m).ev_join, MSET(m).aux));
+    CUDA_TRY(cudaStreamWaitEvent(MSET(m).stream, MSET(m).ev_join, 0));
     return DBGPHMM_OK;
 }

@@ -48,7 +48,7 @@ SYMBOLS = [
     "dbgphmm_tables_row_info", "dbgphmm_tables_row_export", "dbgphmm_tables_row_top_nodes",
     "dbgphmm_output_node_freqs", "dbgphmm_output_edge_and_init_freqs", "dbgphmm_q_score_exact", "dbgphmm_output_mapping", "dbgphmm_to_full_prob_reads", "dbgphmm_run_node_freqs",
     "dbgphmm_run_node_freqs_dev", "dbgphmm_generate_mappings", "dbgphmm_launch_count", "dbgphmm_last_timing",
-    "dbgphmm_reads_to_device", "dbgphmm_last_dense_kernel",
+    "dbgphmm_reads_to_device", "dbgphmm_last_dense_kernel", "dbgphmm_model_wave_reads",
     "dbgphmm_dbg_from_text", "dbgphmm_dbg_from_file", "dbgphmm_dbg_destroy", "dbgphmm_dbg_sizes", "dbgphmm_dbg_phmm_graph",
     "dbgphmm_dbg_get_copy_nums", "dbgphmm_dbg_set_copy_nums", "dbgphmm_dbg_expand_copy_nums", "dbgphmm_dbg_to_text", "dbgphmm_dbg_to_file",
     "dbgphmm_dbg_to_model", "dbgphmm_mappings_from_map_text", "dbgphmm_mappings_from_map_file", "dbgphmm_mappings_to_map_text",
@@ -88,6 +88,7 @@ def lib():
     L.dbgphmm_reads_create.argtypes = [u64, vp, vp, C.POINTER(vp)]
     L.dbgphmm_reads_destroy.argtypes = [vp]
     L.dbgphmm_reads_to_device.argtypes = [vp, vp]
+    L.dbgphmm_model_wave_reads.argtypes = [vp]; L.dbgphmm_model_wave_reads.restype = u32
     L.dbgphmm_mappings_create.argtypes = [u64, vp, vp, vp, vp, C.POINTER(vp)]
     L.dbgphmm_mappings_destroy.argtypes = [vp]
     L.dbgphmm_mappings_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -1038,6 +1039,10 @@ class PHMMModel:
 
     def n_batch(self):
         return int(lib().dbgphmm_model_n_batch(self._h))
+
+    def wave_reads(self):
+        """Reads whose sparse rows are resident at once (SMs x sparse jobs per SM): the efficient batch quantum of the bulk calls."""
+        return int(lib().dbgphmm_model_wave_reads(self._h))
 
     # ---- forward.rs
     def _fwd(self, x, kind, mappings=None, read_index=0):

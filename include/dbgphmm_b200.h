@@ -273,6 +273,9 @@ int dbgphmm_last_timing(double ms[4], uint64_t* dense_cells);
 /* The dominant kernel (dense forward/backward row step) of the last bulk call: summed launch durations from CUDA
  * events recorded around every launch on the library's stream, number of launches, and the cells they computed. */
 int dbgphmm_last_dense_kernel(double* ms, uint64_t* launches, uint64_t* cells);
+/* Reads whose sparse DP rows are resident on the device at once (SMs x sparse jobs per SM): the sparse rows are latency-bound per read, so
+ * the bulk calls (run_node_freqs, to_full_prob_reads, generate_mappings) are most efficient on read sets that are multiples of it. */
+uint32_t dbgphmm_model_wave_reads(const dbgphmm_model* m);
 /* Upload-free variant for benchmarking: move a reads handle's bases to the device once (idempotent). */
 int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r);
 

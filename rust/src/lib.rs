@@ -128,6 +128,7 @@ extern "C" {
     pub fn dbgphmm_launch_count(reset: c_int) -> u64;
     pub fn dbgphmm_last_timing(ms: *mut f64, dense_cells: *mut u64) -> c_int;
     pub fn dbgphmm_last_dense_kernel(ms: *mut f64, launches: *mut u64, cells: *mut u64) -> c_int;
+    pub fn dbgphmm_model_wave_reads(m: *const dbgphmm_model) -> u32;
     pub fn dbgphmm_reads_to_device(m: *mut dbgphmm_model, r: *mut dbgphmm_reads) -> c_int;
 }
 

