@@ -364,8 +364,11 @@ def main():
 
     # ---- end to end: host buffers in, host buffers out through the public API (reads handle re-created: validation + H2D inside)
     def step_e2e():
+        t0 = time.perf_counter()
         r2 = H.Reads(reads)
+        t1 = time.perf_counter()
         fr, lf, lb, cells = model.run_node_freqs(r2, "sparse")
+        note(f"e2e: reads handle {1e3 * (t1 - t0):.1f} ms, call {1e3 * (time.perf_counter() - t1):.1f} ms (library events: {H.last_timing()[3]:.1f} ms)")
         if world > 1:
             t = torch.from_numpy(np.concatenate([fr, [lf.sum()]])).cuda(); dist.all_reduce(t); fr = t.cpu().numpy()
         torch.cuda.synchronize()

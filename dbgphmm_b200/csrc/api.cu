@@ -649,11 +649,13 @@ static int run_impl(dbgphmm_model* m, const dbgphmm_reads* reads, int mode, int 
             PhaseOpts pb; pb.keep_rows = false; pb.store_sparse = true; pb.step = b_recompute ? nullptr : &spb; pb.group = group;
             // The two directions do not depend on each other (with the recompute passes), and their sparse phases are latency-bound per
             // read: a second host thread drives the backward direction on the handle's second stream set.  Order: forward dense rows ->
-            // (first-row inputs gathered, slabs released) -> backward dense rows -> BOTH sparse phases side by side.  With fewer reads
-            // than half a resident wave the two sparse kernels share the SMs and the phase costs one latency instead of two; a full
-            // wave still fills the tail of one kernel with the head of the other.  DBGPHMM_OVERLAP=0: one thread, one phase at a time.
-            bool overlap = b_recompute && fk == DBGPHMM_FWD_SPARSE && bk == DBGPHMM_BWD_SPARSE;
-            if (const char* e = getenv("DBGPHMM_OVERLAP")) overlap = overlap && e[0] != '0';
+            // (first-row inputs gathered, slabs released) -> backward dense rows -> BOTH sparse phases side by side: with fewer reads
+            // than ~0.4 of a resident wave the CTAs of the four launches (two primary, two rescue) are resident at once and the phases
+            // share their latency (measured per pass: 250 reads 699 -> 597 ms, 500 reads 1041 -> 965 ms).  Larger batches keep one phase
+            // at a time (measured: no gain from 666 reads on, and a rescue launch that finds no shared memory starts its jobs late).
+            // DBGPHMM_OVERLAP=0 never overlaps, =1 always does.
+            bool overlap = b_recompute && fk == DBGPHMM_FWD_SPARSE && bk == DBGPHMM_BWD_SPARSE && sparse_pair_fits(m, sparse_default_cap(), (uint32_t)jobs.size());
+            if (const char* e = getenv("DBGPHMM_OVERLAP")) overlap = b_recompute && fk == DBGPHMM_FWD_SPARSE && bk == DBGPHMM_BWD_SPARSE && e[0] != '0';
             if (st == DBGPHMM_OK && overlap) {
                 Gate f_dense_done, b_dense_done;
                 pf.force_gather = true;

@@ -749,7 +749,14 @@ int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t*
             }
         }
         if (use_gather) { cache_free(out->pool.base); out->pool.base = nullptr; }   // the ping-pong slabs are dead already
-        if (opt.after_dense) opt.after_dense();
+        if (opt.after_dense) {
+            // The dense tail (selection kernels) must be over before the other direction's persistent sparse CTAs take the SMs: they are
+            // configured for maximum shared memory, and a kernel that wants another L1 / shared split waits for an idle SM -- which a
+            // persistent kernel never leaves -- so this direction's sparse launch, queued behind the selection, would start only after the
+            // other direction's phase had finished (measured: the two phases did not overlap at all).
+            CUDA_TRY(cudaStreamSynchronize(st));
+            opt.after_dense();
+        }
         ST_TRY(sparse_phase());
     } else {
         ST_TRY(sparse_phase());

@@ -938,6 +938,17 @@ uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
     return (uint32_t)per_sm * (uint32_t)m->n_sm;
 }
 
+// Both directions' sparse launches (primary + rescue each) resident at once: the two-thread bulk path runs the two sparse phases side by
+// side only then.  With more jobs one direction's rescue CTAs would find no shared memory until primary CTAs of the other direction leave
+// -- persistent ones, i.e. at the end -- and the jobs handed over to them would start a whole job latency late.
+bool sparse_pair_fits(dbgphmm_model* m, uint32_t cap, uint32_t n_jobs) {
+    const uint32_t rcap = sparse_rescue_cap(cap);
+    const size_t sm_bytes = 227 * 1024, one = sparse_smem_bytes(cap, hcap_of(cap)) + 1024, big = rcap ? sparse_smem_bytes(rcap, hcap_of(rcap)) + 1024 : 0;
+    // on average over the SMs: the rescue CTAs are a pool (any of them takes any handed-over job), so it is enough that most are resident
+    const double per_sm = (double)n_jobs / (double)m->n_sm;
+    return 2.0 * per_sm * (double)one + 2.0 * (double)big + 4096.0 <= (double)sm_bytes;
+}
+
 static int sparse_launch(dbgphmm_model* m, cudaStream_t st, uint32_t grid, const SGraph& G, const SJob* d_jobs, const SparseIO& io, uint32_t cap, int role, int dir) {
     const uint32_t hcap = hcap_of(cap);
     const size_t smem = sparse_smem_bytes(cap, hcap);

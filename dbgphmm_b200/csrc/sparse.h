@@ -77,6 +77,8 @@ int sparse_configure(dbgphmm_model* m);
 uint32_t sparse_default_cap();
 // jobs that are resident at once with entry capacity `cap` (one wave): batches are cut to multiples of it
 uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap);
+// n_jobs forward jobs and n_jobs backward jobs (primary + rescue launches of both directions) are resident at once
+bool sparse_pair_fits(dbgphmm_model* m, uint32_t cap, uint32_t n_jobs);
 // cap: entry capacity per job in shared memory; threads per CTA chosen from cap.  rescue_cap > cap: a second launch of
 // persistent CTAs with that capacity runs beside the primary one (auxiliary stream) and carries on the jobs whose rows
 // outgrow `cap` (io.rq_* must be set up by the caller); 0: no rescue launch.

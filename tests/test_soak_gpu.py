@@ -48,3 +48,25 @@ def test_soak_stream_strategy_two_handles(monkeypatch, cap):
             assert np.array_equal(lf, rlf) and np.array_equal(lb, rlb), f"pass {step} handle {h}: ln P changed"
             # the frequencies are accumulated with f64 atomics: the order of the additions is not fixed
             assert np.allclose(fr, rf, rtol=1e-11, atol=1e-13), f"pass {step} handle {h}: node frequencies changed by {np.abs(fr - rf).max()}"
+
+
+def test_two_thread_overlap_equals_one_phase_at_a_time(monkeypatch):
+    """Stream strategy: both sparse phases side by side (second host thread, second stream set) against one phase at a time."""
+    from dbgphmm_b200 import hmmv2 as H
+    monkeypatch.setenv("DBGPHMM_STRATEGY", "stream")
+    monkeypatch.setenv("DBGPHMM_VERIFY", "1")
+    w, reads = _workload(11, 200)
+    li, lt = w.graph.to_probs("normal")
+    par = H.params_uniform(0.001); par.n_warmup = w.k
+    m = H.PHMMModel(w.graph.src, w.graph.dst, w.graph.base, li, lt, par)
+    res = {}
+    for mode in ("0", "1", "0", "1"):
+        monkeypatch.setenv("DBGPHMM_OVERLAP", mode)
+        fr, lf, lb, cells = m.run_node_freqs(H.Reads(reads), "sparse")
+        if mode in res:
+            rf, rlf, rlb, rc = res[mode]
+            assert cells == rc and np.array_equal(lf, rlf) and np.array_equal(lb, rlb)
+        res[mode] = (fr, lf, lb, cells)
+    assert res["0"][3] == res["1"][3]
+    assert np.array_equal(res["0"][1], res["1"][1]) and np.array_equal(res["0"][2], res["1"][2])
+    assert np.allclose(res["0"][0], res["1"][0], rtol=1e-11, atol=1e-13)
