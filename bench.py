@@ -451,6 +451,12 @@ def main():
 
 
 if __name__ == "__main__":
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "--impl" not in " ".join(sys.argv[1:]).replace("--impl ours", ""):
+        try:    # torchrun then writes the failing rank's traceback into its error file (and its summary names it)
+            from torch.distributed.elastic.multiprocessing.errors import record
+            main = record(main)
+        except Exception:
+            pass
     try:
         rc = main()
     except Exception as exc:

@@ -867,7 +867,11 @@ int run_backward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, cons
         const uint32_t Jg = std::min(J, g0 + G) - g0;
         CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)Jg * T, st));
         CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
-        CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * 2ull * Jg, st));   // cells outside the cone read as zero
+        // No zeroing of the slabs (88 GB per pass on C3 in round 1): a cone tile next to the cone's edge does read cells no tile of this
+        // pass wrote, but what it makes of them stays outside the dependency cone of the cells the products read -- the cone is the closure
+        // over HALO_HOPS hops per row and n_warmup rows, and a value travels at most HALO_HOPS hops per row.  DBGPHMM_VERIFY=1 poisons
+        // the slabs with NaN patterns instead, so that any such dependence would surface as NaN frequencies in the tests that set it.
+        if (verify_enabled()) CUDA_TRY(cudaMemsetAsync(pool.base, 0xff, pool.slab_bytes * 2ull * Jg, st));
         {
             dim3 g(W, Jg);
             k_roi_mark_b<<<g, 128, 0, st>>>(W, F.d_desc, F.d_desc0 + g0, b_len.as<uint32_t>() + g0, F.arena.base, m->d_tile_of_b, m->d_roi_off_b, m->d_roi_tile_b, T,
@@ -912,7 +916,11 @@ int run_forward_recompute(dbgphmm_model* m, const std::vector<HJob>& jobs, const
         const uint32_t Jg = std::min(J, g0 + G) - g0;
         CUDA_TRY(cudaMemsetAsync(b_mark.p, 0, (size_t)Jg * T, st));
         CUDA_TRY(cudaMemsetAsync(b_wl.p, 0, sizeof(unsigned long long), st));
-        CUDA_TRY(cudaMemsetAsync(pool.base, 0, pool.slab_bytes * 2ull * Jg, st));   // cells outside the cone read as zero
+        // No zeroing of the slabs (88 GB per pass on C3 in round 1): a cone tile next to the cone's edge does read cells no tile of this
+        // pass wrote, but what it makes of them stays outside the dependency cone of the cells the products read -- the cone is the closure
+        // over HALO_HOPS hops per row and n_warmup rows, and a value travels at most HALO_HOPS hops per row.  DBGPHMM_VERIFY=1 poisons
+        // the slabs with NaN patterns instead, so that any such dependence would surface as NaN frequencies in the tests that set it.
+        if (verify_enabled()) CUDA_TRY(cudaMemsetAsync(pool.base, 0xff, pool.slab_bytes * 2ull * Jg, st));
         {
             dim3 g(W, Jg);
             k_roi_mark<<<g, 128, 0, st>>>(W, B.d_desc, B.d_desc0 + g0, b_len.as<uint32_t>() + g0, B.arena.base, m->d_tile_of, m->d_roi_off, m->d_roi_tile, T,

@@ -39,6 +39,46 @@ private:
     uint64_t n_;
 };
 
+// e2e::Dataset (e2e.rs:31-130): genome, genome_size, positioned reads and the PHMM parameters they were sampled with, in the reference's
+// JSON form (Dataset::to_json_file / from_json_file).  reads() hands the read set to the hot path.
+class Dataset {
+public:
+    explicit Dataset(dbgphmm_dataset* h) : h_(h) {}
+    static Dataset from_json_file(const std::string& path) { dbgphmm_dataset* h = nullptr; check(dbgphmm_dataset_from_json_file(path.c_str(), &h)); return Dataset(h); }
+    static Dataset from_json_str(const std::string& text) { dbgphmm_dataset* h = nullptr; check(dbgphmm_dataset_from_json_text(text.data(), text.size(), &h)); return Dataset(h); }
+    ~Dataset() { if (h_) dbgphmm_dataset_destroy(h_); }
+    Dataset(const Dataset&) = delete; Dataset& operator=(const Dataset&) = delete;
+    Dataset(Dataset&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    uint64_t genome_size() const { uint64_t s[5]; check(dbgphmm_dataset_sizes(h_, s)); return s[4]; }
+    uint64_t n_reads() const { uint64_t s[5]; check(dbgphmm_dataset_sizes(h_, s)); return s[2]; }
+    double coverage() const { uint64_t s[5]; check(dbgphmm_dataset_sizes(h_, s)); return s[4] ? (double)s[3] / (double)s[4] : 0.0; }   // e2e.rs:72-74
+    std::vector<std::string> genome() const {   // "C|L|F:bases" per haplotype (StyledSequence's Display, collection.rs:460-464)
+        uint64_t s[5]; check(dbgphmm_dataset_sizes(h_, s));
+        std::vector<uint64_t> off(s[0] + 1); std::string bases(s[1], ' '); std::string style(s[0], ' ');
+        check(dbgphmm_dataset_genome(h_, off.data(), (uint8_t*)&bases[0], (uint8_t*)&style[0]));
+        std::vector<std::string> out;
+        for (uint64_t i = 0; i < s[0]; i++) out.push_back(std::string(1, style[i]) + ":" + bases.substr(off[i], off[i + 1] - off[i]));
+        return out;
+    }
+    std::vector<std::string> reads() const {
+        uint64_t s[5]; check(dbgphmm_dataset_sizes(h_, s));
+        std::vector<uint64_t> off(s[2] + 1); std::string bases(s[3], ' ');
+        check(dbgphmm_dataset_read_origins(h_, off.data(), (uint8_t*)&bases[0], nullptr, nullptr, nullptr));
+        std::vector<std::string> out;
+        for (uint64_t i = 0; i < s[2]; i++) out.push_back(bases.substr(off[i], off[i + 1] - off[i]));
+        return out;
+    }
+    dbgphmm_params params() const { dbgphmm_params p; check(dbgphmm_dataset_params(h_, &p)); return p; }
+    std::string to_json_string() const {
+        uint64_t need = 0; check(dbgphmm_dataset_to_json_text(h_, nullptr, 0, &need));
+        std::string s(need, ' '); check(dbgphmm_dataset_to_json_text(h_, &s[0], need, &need)); return s;
+    }
+    void to_json_file(const std::string& path) const { check(dbgphmm_dataset_to_json_file(h_, path.c_str())); }
+    dbgphmm_dataset* handle() const { return h_; }
+private:
+    dbgphmm_dataset* h_ = nullptr;
+};
+
 // Mapping (hint.rs:27-30) of one read, copied to the host: per base the candidate nodes and their ln probabilities
 struct Mapping {
     std::vector<std::vector<uint32_t>> nodes;
@@ -215,6 +255,7 @@ public:
     // candidate copy-number assignments X -> parameter sets on the device (seq_graph.rs:160-273)
     void set_copy_nums_batch(uint32_t n_batch, const uint32_t* copy_nums, int mode = 0) { check(dbgphmm_model_set_copy_nums_batch(h_, n_batch, copy_nums, mode)); }
     uint32_t n_batch() const { return dbgphmm_model_n_batch(h_); }
+    uint32_t wave_reads() const { return dbgphmm_model_wave_reads(h_); }   // reads whose sparse rows are resident at once: the efficient batch quantum
 
     std::unique_ptr<PHMMTables> forward(const std::string& x) { return fwd(x, DBGPHMM_FWD_DENSE); }                           // forward.rs:24
     std::unique_ptr<PHMMTables> forward_sparse(const std::string& x, bool use_max_ratio) { return fwd(x, use_max_ratio ? DBGPHMM_FWD_SPARSE_RATIO : DBGPHMM_FWD_SPARSE); }  // :93

@@ -37,3 +37,15 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_exit_without_work():
     p = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ["--gpus", "2"])
     assert p.returncode == 0 and p.stdout.strip() == "", (p.stdout, p.stderr)
+
+
+def test_reference_arm_ignores_torchrun_single_thread_default():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use the host cores (round 1 reported `cores: 1` at N > 1)."""
+    if len(os.sched_getaffinity(0)) < 2:
+        return
+    p = _run({"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, ["--gpus", "2"])
+    assert p.returncode == 0, p.stderr
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["cores"] == 2          # = min(host cores, reads of the sample)
+    for key in ("sample_reads", "sample_bases_per_read", "rows_covered", "cells_per_s_per_core", "reference_hint_cells_per_s_per_core"):
+        assert key in d["cpu_baseline"], key

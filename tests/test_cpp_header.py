@@ -81,6 +81,18 @@ static int host_only() {
     CHECK(near(post.p_edge_x(1, 5), sc.p() - post.p(), 1e-12) && near(post.p_edge_x(0, 1), 0.0, 1e-12) && post.p_edge_x(2, 7) == -INFINITY, 47);
     auto f = mp.to_node_freqs(5);   // hint.rs:161-171
     CHECK(near(f[0], 0.6, 1e-15) && near(f[2], 0.9, 1e-15) && f[4] == 0.0, 9);
+    // Dataset JSON (e2e.rs:123-130): styled sequences and positioned reads in the reference's serde forms (collection.rs:836-861)
+    const std::string dj = "{\"genome\":[\"C:ATCGAT\",\"L:GGGC\"],\"genome_size\":10,\"reads\":{\"reads\":[\"ATCGT:-:0-0,0-1,0-2,I,0-3\"]},"
+        "\"phmm_params\":{\"p_mismatch\":\"-4.605170185988091(0.0100)\",\"p_match\":\"-0.01005033585350145(0.9900)\",\"p_random\":\"-1.3862943611198906(0.2500)\","
+        "\"p_gap_open\":\"-4.605170185988091(0.0100)\",\"p_gap_ext\":\"-4.605170185988091(0.0100)\",\"p_end\":\"-11.512925464970229(0.0000)\","
+        "\"p_MM\":\"-0.02021270866322344(0.9800)\",\"p_IM\":\"-0.02021270866322344(0.9800)\",\"p_DM\":\"-0.02021270866322344(0.9800)\","
+        "\"p_MI\":\"-4.605170185988091(0.0100)\",\"p_II\":\"-4.605170185988091(0.0100)\",\"p_DI\":\"-4.605170185988091(0.0100)\","
+        "\"p_MD\":\"-4.605170185988091(0.0100)\",\"p_ID\":\"-4.605170185988091(0.0100)\",\"p_DD\":\"-4.605170185988091(0.0100)\","
+        "\"n_active_nodes\":40,\"active_node_max_ratio\":30.0,\"n_warmup\":50,\"warmup_threshold\":200,\"n_max_gaps\":4}}";
+    auto ds = dbgphmm::Dataset::from_json_str(dj);
+    CHECK(ds.genome_size() == 10 && ds.n_reads() == 1 && ds.genome() == std::vector<std::string>({"C:ATCGAT", "L:GGGC"}) && ds.reads()[0] == "ATCGT", 48);
+    CHECK(ds.params().n_warmup == 50 && near(ds.params().p_mismatch, std::log(0.01), 1e-15) && near(ds.coverage(), 0.5, 1e-15), 49);
+    CHECK(dbgphmm::Dataset::from_json_str(ds.to_json_string()).to_json_string() == ds.to_json_string(), 50);
     return 0;
 }
 
