@@ -928,9 +928,7 @@ uint32_t sparse_wave_jobs(dbgphmm_model* m, uint32_t cap) {
         per_sm = 1;
     }
     if (rcap) {
-        // (DBGPHMM_SPARSE_MARGIN: bytes kept free per SM beside the primary CTAs and the rescue CTA)
-        size_t margin = 4096;
-        if (const char* e = getenv("DBGPHMM_SPARSE_MARGIN")) margin = (size_t)atoi(e);
+        const size_t margin = 4096;   // bytes kept free per SM beside the primary CTAs and the rescue CTA
         const size_t sm_bytes = 227 * 1024, one = sparse_smem_bytes(cap, hcap_of(cap)) + 1024, big = sparse_smem_bytes(rcap, hcap_of(rcap)) + 1024;
         const int fit = (int)((sm_bytes - big - margin) / one);
         if (fit >= 1 && fit < per_sm) per_sm = fit;
