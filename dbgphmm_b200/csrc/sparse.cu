@@ -72,17 +72,20 @@ struct SS {
 __device__ __forceinline__ uint32_t sp_hash(uint32_t id, int shift) { return (id * 2654435761u) >> shift; }
 __device__ __forceinline__ int sp_find(const uint32_t* key, const uint32_t* val, uint32_t hmask, int hshift, uint32_t id) {
     uint32_t h = sp_hash(id, hshift);
-    for (;;) {
+    for (uint32_t tries = 0; tries <= hmask; tries++) {   // (bounded: a completely full table has no empty cell to stop at)
         uint32_t k = key[h];
         if (k == id + 1) { uint32_t v = val[h]; return v < SP_TENT ? (int)v : -1; }
         if (k == 0) return -1;
         h = (h + 1) & hmask;
     }
+    return -1;
 }
-// returns the cell holding `id`, inserting the key (value untouched = SP_ABSENT) if new
+// returns the cell holding `id`, inserting the key (value untouched = SP_ABSENT) if new ; SP_ABSENT if the table is full (a row on
+// a heavily branching graph can offer more distinct candidates than 2 x cap cells: the caller then reports the row as too large for
+// this capacity instead of probing forever)
 __device__ __forceinline__ uint32_t sp_cell(uint32_t* key, uint32_t hmask, int hshift, uint32_t id) {
     uint32_t h = sp_hash(id, hshift);
-    for (;;) {
+    for (uint32_t tries = 0; tries <= 2 * hmask + 1; tries++) {
         uint32_t k = key[h];
         if (k == id + 1) return h;
         if (k == 0) {
@@ -90,6 +93,7 @@ __device__ __forceinline__ uint32_t sp_cell(uint32_t* key, uint32_t hmask, int h
             if (old == 0u || old == id + 1) return h;
         } else h = (h + 1) & hmask;
     }
+    return SP_ABSENT;
 }
 
 // Ordered exclusive prefix of one small value per thread over the block (thread order) ; *total = block sum.
@@ -167,6 +171,7 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint4* re
     const uint32_t n_self = and_us ? (uint32_t)n_src : 0u;
     auto note = [&](uint32_t id, uint32_t p) -> uint32_t {   // phase 1 for one candidate ; returns its hash cell
         const uint32_t cell = sp_cell(S.ch_key(), S.hmask, S.hshift, id);
+        if (cell == SP_ABSENT) { fl[0] = 1; return 0; }       // hash table full: the row does not fit this capacity
         const uint32_t v = S.ch_val()[cell];
         if (v < SP_TENT) atomicMin(&S.firstpos()[v], p);
         else atomicMin(&S.ch_val()[cell], SP_TENT | p);
@@ -197,10 +202,11 @@ __device__ bool sp_expand(SS& S, const uint32_t* src, int n_src, const uint4* re
         if (and_us && q < n_src) note(id, (uint32_t)q);
     }
     __syncthreads();
+    if (fl[0]) { __syncthreads(); return false; }   // (uniform: some candidate found no hash cell or a node has too many neighbours ; phase 2 would probe for keys that are not there)
     // kept / new flag of candidate p with id `id` : bit 0 kept, bit 16 new entry
     auto cell_of = [&](uint32_t id) -> uint32_t {
         uint32_t h = sp_hash(id, S.hshift);
-        while (S.ch_key()[h] != id + 1) h = (h + 1) & S.hmask;   // inserted in phase 1
+        for (uint32_t tries = 0; tries <= S.hmask && S.ch_key()[h] != id + 1; tries++) h = (h + 1) & S.hmask;   // inserted in phase 1
         return h;
     };
     auto flag_at = [&](uint32_t cell, uint32_t p, uint32_t* v_out) -> uint32_t {
