@@ -162,6 +162,37 @@ impl CudaReads {
 }
 impl Drop for CudaReads { fn drop(&mut self) { unsafe { dbgphmm_reads_destroy(self.h) } } }
 
+/// `e2e::Dataset` (e2e.rs:31-130) in the reference's JSON form (`Dataset::to_json_file` / `from_json_file`): genome, genome size,
+/// positioned reads and the PHMM parameters they were sampled with.  `reads()` is the read set the hot path takes.
+pub struct CudaDataset { h: *mut dbgphmm_dataset }
+impl CudaDataset {
+    pub fn from_json_file(path: &str) -> Self {
+        let c = std::ffi::CString::new(path).unwrap();
+        let mut h = std::ptr::null_mut();
+        check(unsafe { dbgphmm_dataset_from_json_file(c.as_ptr(), &mut h) });
+        CudaDataset { h }
+    }
+    pub fn to_json_file(&self, path: &str) {
+        let c = std::ffi::CString::new(path).unwrap();
+        check(unsafe { dbgphmm_dataset_to_json_file(self.h, c.as_ptr()) });
+    }
+    fn sizes(&self) -> [u64; 5] { let mut s = [0u64; 5]; check(unsafe { dbgphmm_dataset_sizes(self.h, s.as_mut_ptr()) }); s }
+    pub fn genome_size(&self) -> usize { self.sizes()[4] as usize }
+    /// `Dataset::coverage` (e2e.rs:72-74)
+    pub fn coverage(&self) -> f64 { let s = self.sizes(); s[3] as f64 / s[4].max(1) as f64 }
+    pub fn params(&self) -> dbgphmm_params {
+        let mut p = std::mem::MaybeUninit::<dbgphmm_params>::uninit();
+        check(unsafe { dbgphmm_dataset_params(self.h, p.as_mut_ptr()) });
+        unsafe { p.assume_init() }
+    }
+    pub fn reads(&self) -> CudaReads {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { dbgphmm_dataset_reads(self.h, &mut h) });
+        CudaReads { h, n: self.sizes()[2] as usize }
+    }
+}
+impl Drop for CudaDataset { fn drop(&mut self) { unsafe { dbgphmm_dataset_destroy(self.h) } } }
+
 /// `Mappings` (hint.rs:150-152): per read, per base, the candidate nodes and their probabilities (hint.rs:27-30).
 pub struct CudaMappings { h: *mut dbgphmm_mappings }
 impl CudaMappings {
