@@ -30,7 +30,11 @@ extern "C" int dbgphmm_reads_create(uint64_t n_reads, const uint64_t* offsets, c
 } ABI_CATCH
 extern "C" void dbgphmm_reads_destroy(dbgphmm_reads* r) {
     if (!r) return;
-    if (r->d_bases) { cudaSetDevice(r->device); cudaFree(r->d_bases); }
+    if (r->d_bases) {   // (a cache block: no cudaFree in steady state ; no stream to order the reuse behind -> the next user synchronises)
+        cudaSetDevice(r->device);
+        cache_set_stream(nullptr);
+        cache_free(r->d_bases);
+    }
     delete r;
 }
 extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) try {
@@ -38,9 +42,13 @@ extern "C" int dbgphmm_reads_to_device(dbgphmm_model* m, dbgphmm_reads* r) try {
     if (r->d_bases && r->device == m->device) return DBGPHMM_OK;
     CUDA_TRY(cudaSetDevice(m->device));
     cache_set_stream(MSET(m).stream);
-    if (r->d_bases) { cudaFree(r->d_bases); r->d_bases = nullptr; }
-    CUDA_TRY(cudaMalloc((void**)&r->d_bases, std::max<size_t>(r->bases.size(), 1)));
-    if (!r->bases.empty()) CUDA_TRY(cudaMemcpy(r->d_bases, r->bases.data(), r->bases.size(), cudaMemcpyHostToDevice));
+    if (r->d_bases) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(r->device); cache_free(r->d_bases); r->d_bases = nullptr; cudaSetDevice(cur); }
+    r->d_bases = (uint8_t*)cache_alloc(std::max<size_t>(r->bases.size(), 1));   // (from the block cache: a fresh handle per call costs no cudaMalloc / cudaFree)
+    if (!r->d_bases) { dbg_set_error("out of device memory for the reads"); return DBGPHMM_ERR_OOM; }
+    if (!r->bases.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(r->d_bases, r->bases.data(), r->bases.size(), cudaMemcpyHostToDevice, MSET(m).stream));
+        CUDA_TRY(cudaStreamSynchronize(MSET(m).stream));
+    }
     r->device = m->device;
     return DBGPHMM_OK;
 } ABI_CATCH

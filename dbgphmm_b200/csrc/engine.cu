@@ -57,11 +57,17 @@ void* cache_alloc(size_t bytes) {
     if (bytes < (1u << 20)) { size_t c = 256; while (c < bytes) c <<= 1; bytes = c; }  // small blocks in power-of-two classes
     int dev = 0; cudaGetDevice(&dev);
     const cudaStream_t me = tl_cache_stream;
-    for (int any_owner = 0; any_owner < 2; any_owner++) {
+    // best fit within 1.5 x the request, this stream's blocks first ; then, for large requests, up to 4 x: consecutive batches of
+    // different shapes (1332 reads, then the 668 left over) otherwise find nothing that "fits", allocate their own set of blocks, run
+    // out of memory, trim the cache and allocate again -- 400-600 ms of cudaMalloc / cudaFree per change of shape (measured)
+    for (int pass = 0; pass < 3; pass++) {
+        const bool any_owner = pass >= 1;
+        if (pass == 2 && bytes < ((size_t)64 << 20)) break;
+        const size_t limit = pass == 2 ? 4 * bytes : bytes + bytes / 2 + (1 << 20);
         int best = -1;
         for (size_t i = 0; i < g_cache.size(); i++) {
             const CacheBlock& b = g_cache[i];
-            if (!b.used && b.device == dev && (any_owner || (me && b.owner == me)) && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 + (1 << 20))
+            if (!b.used && b.device == dev && (any_owner || (me && b.owner == me)) && b.bytes >= bytes && b.bytes <= limit)
                 if (best < 0 || b.bytes < g_cache[best].bytes) best = (int)i;
         }
         if (best >= 0) {

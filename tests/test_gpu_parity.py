@@ -516,6 +516,48 @@ def test_full_prob_reads_batched_over_candidates(H):
             assert close_log(per2[x], p2).all(), (x, per2[x], p2)
 
 
+def test_mapping_rows_beyond_the_sparsevec_capacity(H):
+    """Mapping rows: up to 400 distinct nodes (the capacity of the reference's SparseVec, table.rs:22) are scored -- through the wide
+    shape of k_mapx for several candidates, through k_sparse for one -- and agree with the oracle; 401 nodes are an error where the
+    reference panics (round 1 silently truncated such a row)."""
+    w = _dbg_case(13, glen=900, n_reads=2, read_len=300)      # (a k-mer graph: candidates change init / trans through node copy numbers alone)
+    sg = w.graph
+    assert sg.n_nodes > 500
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(sg, par)
+    read = w.reads[0][:12]
+    base = o.generate_mappings(O.Reads([read]), None, False)
+    rng = np.random.default_rng(2)
+
+    def maps(width):
+        nodes, row_off = [], [0]
+        for i in range(len(read)):
+            have = [int(v) for v in base.nodes[int(base.row_off[i]):int(base.row_off[i + 1])]]
+            row = have + [int(v) for v in rng.permutation(sg.n_nodes) if int(v) not in have][:width - len(have)]
+            nodes += row; row_off.append(len(nodes))
+        om = O.Mappings(np.array([0, len(read)], np.uint64), np.array(row_off, np.uint64), np.array(nodes, np.uint32), np.zeros(len(nodes)))
+        return om, H.Mappings(om.read_off, om.row_off, om.nodes, om.probs)
+
+    om, gm = maps(400)
+    X = np.stack([sg.node_copy_num, sg.node_copy_num + 1, sg.node_copy_num + (rng.random(sg.n_nodes) < 0.3)])
+    g.set_copy_nums_batch(X, "normal")
+    tot, per = g.to_full_prob_reads(H.Reads([read]), gm)
+    for x in range(len(X)):
+        li, lt = sg.to_probs("normal", X[x])
+        o.set_probs(li, lt)
+        s, p = o.to_full_prob_reads(O.Reads([read]), om)
+        assert close_log(per[x], p).all(), (x, per[x], p)
+    g.set_copy_nums_batch(X[:1], "normal")
+    tot1, per1 = g.to_full_prob_reads(H.Reads([read]), gm)
+    assert per1[0, 0] == per[0, 0]
+    _, gm401 = maps(401)
+    for cand in (X, X[:1]):
+        g.set_copy_nums_batch(cand, "normal")
+        with pytest.raises(H.DbgphmmError) as ei:
+            g.to_full_prob_reads(H.Reads([read]), gm401)
+        assert ei.value.status == H.ERR_CAPACITY
+
+
 def test_capacity_overflow_is_an_error_like_the_reference_panic(H):
     # ratio mode leaving warm-up with > 200 candidates overflows the 400-entry SparseVec (params.rs:37-38)
     w = _dbg_case(0)
