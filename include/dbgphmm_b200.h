@@ -17,7 +17,8 @@
  *   - handles are immutable after creation except where stated; a handle may be used from one host
  *     thread at a time, different handles from different threads (the device-memory cache shared by the
  *     handles of a process is locked; dbgphmm_last_timing / dbgphmm_last_dense_kernel report the calling
- *     thread's last bulk call).  All GPU work of a call is finished when it returns.
+ *     thread's last bulk call).  All GPU work of a call is finished when it returns.  A bulk call may start one helper
+ *     host thread of its own (it drives the backward direction on the handle's second stream set) and joins it before returning.
  *   - there is NO CPU fallback: every call fails with DBGPHMM_ERR_CUDA if no sm_100-class device exists.
  */
 #ifndef DBGPHMM_B200_H
