@@ -73,7 +73,7 @@ extern "C" int dbgphmm_mappings_create(uint64_t n_reads, const uint64_t* read_of
     *out = mp.release();
     return DBGPHMM_OK;
 } ABI_CATCH
-extern "C" void dbgphmm_mappings_destroy(dbgphmm_mappings* mp) { delete mp; }
+extern "C" void dbgphmm_mappings_destroy(dbgphmm_mappings* mp) { if (mp) mappings_release_device(mp); delete mp; }
 extern "C" int dbgphmm_mappings_sizes(const dbgphmm_mappings* mp, uint64_t* n_reads, uint64_t* n_rows, uint64_t* n_entries) try {
     if (!mp) { dbg_set_error("mappings_sizes: null"); return DBGPHMM_ERR_INVALID; }
     if (n_reads) *n_reads = mp->read_off.empty() ? 0 : mp->read_off.size() - 1;

@@ -137,20 +137,36 @@ void RowStore::release() {
     cache_free(arena.base); cache_free(arena.cursor); arena = SparseArena();
     cache_free(d_final); d_final = nullptr;
 }
-void DevMappings::release() { cudaFree(row_off); cudaFree(nodes); row_off = nullptr; nodes = nullptr; }
+void DevMappings::release() { if (owned) { cudaFree(row_off); cudaFree(nodes); } row_off = nullptr; nodes = nullptr; }
 
 int upload_mappings(dbgphmm_model* m, const dbgphmm_mappings* mp, DevMappings* out) {
-    std::vector<uint32_t> nodes(mp->nodes.size());
-    for (size_t i = 0; i < nodes.size(); i++) {
-        if (mp->nodes[i] >= m->N) { dbg_set_error("mapping node id out of range"); return DBGPHMM_ERR_INVALID; }
-        nodes[i] = m->pos_of[mp->nodes[i]];
+    if (!(mp->d_nodes && mp->d_model_serial == m->serial)) {
+        mappings_release_device(mp);
+        std::vector<uint32_t> nodes(mp->nodes.size());
+        for (size_t i = 0; i < nodes.size(); i++) {
+            if (mp->nodes[i] >= m->N) { dbg_set_error("mapping node id out of range"); return DBGPHMM_ERR_INVALID; }
+            nodes[i] = m->pos_of[mp->nodes[i]];
+        }
+        uint64_t* d_off = nullptr; uint32_t* d_nd = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&d_off, sizeof(uint64_t) * std::max<size_t>(mp->row_off.size(), 1)));
+        if (cudaMalloc((void**)&d_nd, sizeof(uint32_t) * std::max<size_t>(nodes.size(), 1)) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(d_off); dbg_set_error("out of device memory for the mappings"); return DBGPHMM_ERR_OOM;
+        }
+        mp->d_row_off = d_off; mp->d_nodes = d_nd; mp->d_model_serial = m->serial; mp->d_device = m->device;
+        CUDA_TRY(cudaMemcpy(d_off, mp->row_off.data(), sizeof(uint64_t) * mp->row_off.size(), cudaMemcpyHostToDevice));
+        if (!nodes.empty()) CUDA_TRY(cudaMemcpy(d_nd, nodes.data(), sizeof(uint32_t) * nodes.size(), cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMalloc((void**)&out->row_off, sizeof(uint64_t) * std::max<size_t>(mp->row_off.size(), 1)));
-    CUDA_TRY(cudaMalloc((void**)&out->nodes, sizeof(uint32_t) * std::max<size_t>(nodes.size(), 1)));
-    CUDA_TRY(cudaMemcpy(out->row_off, mp->row_off.data(), sizeof(uint64_t) * mp->row_off.size(), cudaMemcpyHostToDevice));
-    if (!nodes.empty()) CUDA_TRY(cudaMemcpy(out->nodes, nodes.data(), sizeof(uint32_t) * nodes.size(), cudaMemcpyHostToDevice));
+    out->row_off = mp->d_row_off; out->nodes = mp->d_nodes; out->owned = false;
     out->read_off = mp->read_off;
     return DBGPHMM_OK;
+}
+void mappings_release_device(const dbgphmm_mappings* mp) {
+    if (!mp->d_nodes && !mp->d_row_off) return;
+    int cur = 0; cudaGetDevice(&cur);
+    if (mp->d_device >= 0) cudaSetDevice(mp->d_device);
+    cudaFree(mp->d_row_off); cudaFree(mp->d_nodes);
+    mp->d_row_off = nullptr; mp->d_nodes = nullptr; mp->d_model_serial = 0; mp->d_device = -1;
+    cudaSetDevice(cur);
 }
 
 // ------------------------------------------------------------------ small control kernels

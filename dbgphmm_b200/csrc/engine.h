@@ -17,6 +17,7 @@ struct DevMappings {     // device copy of a Mappings CSR with relabelled node i
     uint64_t* row_off = nullptr;
     uint32_t* nodes = nullptr;
     std::vector<uint64_t> read_off;  // host: first row of each read
+    bool owned = false;              // false: a view of the copy the mappings handle keeps (upload_mappings)
     void release();
 };
 
@@ -120,7 +121,9 @@ struct PhaseOpts {
     const StepProducts* step = nullptr;
 };
 
+// device view of the mappings for model m: the copy the handle keeps (made on first use with this model, reused afterwards)
 int upload_mappings(dbgphmm_model* m, const dbgphmm_mappings* mp, DevMappings* out);
+void mappings_release_device(const dbgphmm_mappings* mp);
 int run_forward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,
                 const DevMappings* dmap, RowStore* out);
 int run_backward(dbgphmm_model* m, const std::vector<HJob>& jobs, const uint8_t* d_bases, int kind, const PhaseOpts& opt,

@@ -540,6 +540,8 @@ extern "C" int dbgphmm_model_create(uint32_t n_nodes, uint32_t n_edges, const ui
     }
     CUDA_TRY(cudaSetDevice(device));
     dbgphmm_model* m = new dbgphmm_model();
+    static std::atomic<uint64_t> next_serial{0};
+    m->serial = ++next_serial;
     m->device = device; m->params = *params; m->lin = to_lin(*params);
     int st = DBGPHMM_OK;
     for (auto& ss : m->ss)

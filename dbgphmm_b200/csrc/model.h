@@ -72,6 +72,7 @@ extern thread_local int tl_stream_set;   // which StreamSet of a model this host
 #define MSET(m) ((m)->ss[tl_stream_set])
 
 struct dbgphmm_model {
+    uint64_t serial = 0;            // unique per created model (keys the device copies other handles keep for it)
     int device = 0;
     uint32_t N = 0, E = 0;
     uint32_t n_batch = 1;
@@ -131,6 +132,13 @@ struct dbgphmm_mappings {
     std::vector<uint64_t> read_off, row_off;
     std::vector<uint32_t> nodes;  // ORIGINAL node ids
     std::vector<double> logp;
+    // Device copy (row offsets + node ids relabelled for ONE model), made by the first bulk call that uses the mappings with that
+    // model and kept: sample_posterior_once scores hundreds of candidate sets against the same mappings (posterior.rs:504-515), and
+    // relabelling + uploading 80 M node ids was a third of a C4 call.  The handle's content never changes after creation.
+    mutable uint64_t* d_row_off = nullptr;
+    mutable uint32_t* d_nodes = nullptr;
+    mutable uint64_t d_model_serial = 0;
+    mutable int d_device = -1;
 };
 
 int model_build_graph(dbgphmm_model* m, uint32_t n_nodes, uint32_t n_edges, const uint32_t* src, const uint32_t* dst,
