@@ -445,6 +445,7 @@ int run_products_edge_freqs(dbgphmm_model* m, const std::vector<HJob>& jobs, con
 
 int run_products_mapping(dbgphmm_model* m, const std::vector<HJob>& jobs, const RowStore& F, const RowStore& B, int by_ratio,
                          uint32_t n_active, double ratio, dbgphmm_mappings* out) {
+    HostTrace tr_all("run_products_mapping");
     cudaStream_t st = MSET(m).stream;
     EvTimer tm(st, &g_times.product_ms);
     const uint32_t J = (uint32_t)jobs.size();
@@ -529,19 +530,42 @@ int run_products_mapping(dbgphmm_model* m, const std::vector<HJob>& jobs, const 
     for (size_t p = 0; p < plin.size(); p++) dense_of[plin[p]] = (int64_t)p;
     if (out->read_off.empty()) out->read_off.push_back(0);
     if (out->row_off.empty()) out->row_off.push_back(0);
-    for (uint32_t j = 0; j < J; j++) {
-        for (uint32_t r = 0; r < F.len[j]; r++) {
-            uint64_t lin = lin0[j] + r;
-            if (dense_of[lin] >= 0) {
-                auto& ns = d_rows_nodes[dense_of[lin]]; auto& ls = d_rows_logp[dense_of[lin]];
-                out->nodes.insert(out->nodes.end(), ns.begin(), ns.end()); out->logp.insert(out->logp.end(), ls.begin(), ls.end());
-            } else {
-                out->nodes.insert(out->nodes.end(), s_nodes.begin() + offsets[lin], s_nodes.begin() + offsets[lin + 1]);
-                out->logp.insert(out->logp.end(), s_logp.begin() + offsets[lin], s_logp.begin() + offsets[lin + 1]);
+    // (the rows of the sparse pass lie in row order in s_nodes / s_logp: runs of them are appended in one piece -- a C4 batch has
+    // 2 M rows of 40 entries, and a vector insert per row was most of the call)
+    {
+        HostTrace tr_asm("  mapping assembly");
+        size_t n_dense_entries = 0;
+        for (auto& ns : d_rows_nodes) n_dense_entries += ns.size();
+        out->nodes.reserve(out->nodes.size() + s_nodes.size() + n_dense_entries);
+        out->logp.reserve(out->logp.size() + s_logp.size() + n_dense_entries);
+        out->row_off.reserve(out->row_off.size() + n_lin);
+        out->read_off.reserve(out->read_off.size() + J);
+        uint64_t run_a = 0, run_b = 0;   // pending run of sparse-pass entries [run_a, run_b)
+        auto flush = [&]() {
+            if (run_b > run_a) {
+                out->nodes.insert(out->nodes.end(), s_nodes.begin() + run_a, s_nodes.begin() + run_b);
+                out->logp.insert(out->logp.end(), s_logp.begin() + run_a, s_logp.begin() + run_b);
             }
-            out->row_off.push_back(out->nodes.size());
+            run_a = run_b;
+        };
+        for (uint32_t j = 0; j < J; j++) {
+            for (uint32_t r = 0; r < F.len[j]; r++) {
+                const uint64_t lin = lin0[j] + r;
+                if (dense_of[lin] >= 0) {
+                    flush();
+                    auto& ns = d_rows_nodes[dense_of[lin]]; auto& ls = d_rows_logp[dense_of[lin]];
+                    out->nodes.insert(out->nodes.end(), ns.begin(), ns.end()); out->logp.insert(out->logp.end(), ls.begin(), ls.end());
+                    run_a = run_b = offsets[lin + 1];
+                    out->row_off.push_back(out->nodes.size());
+                } else {
+                    if (offsets[lin] != run_b) { flush(); run_a = offsets[lin]; }
+                    run_b = offsets[lin + 1];
+                    out->row_off.push_back(out->nodes.size() + (run_b - run_a));
+                }
+            }
+            out->read_off.push_back(out->row_off.size() - 1);
         }
-        out->read_off.push_back(out->row_off.size() - 1);
+        flush();
     }
     return DBGPHMM_OK;
 }
