@@ -14,12 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def ids_hash(ids):
-    h = np.uint64(0xcbf29ce484222325)
-    p = np.uint64(0x100000001b3)
-    with np.errstate(over="ignore"):
-        for b in np.sort(np.asarray(ids, np.uint32)).astype("<u4").tobytes():
-            h = (h ^ np.uint64(b)) * p
-    return h
+    """64-bit FNV-1a over the sorted ids as little-endian u32 (the fixture's h_mi / h_d); Python ints: ~4x faster than numpy scalars"""
+    h = 0xcbf29ce484222325
+    for b in np.sort(np.asarray(ids, np.uint32)).astype("<u4").tobytes():
+        h = ((h ^ b) * 0x100000001b3) & 0xffffffffffffffff
+    return np.uint64(h)
 
 
 def load(name):
