@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--read-len", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=40)
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads of the CPU baseline sample (0 = auto)")
-    ap.add_argument("--cpu-read-len", type=int, default=8, help="bases kept per read in the CPU baseline sample")
+    ap.add_argument("--cpu-read-len", type=int, default=0,
+                    help="bases kept per read in the CPU sample (0 = 8; in the reference arm 4 when steps + warmup > 10, so that the driver's 20 + 5 steps end within a few minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end passes (profiling runs under ncu only; the line then has e2e.value = null)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling passes over the 4,000-read C3 dataset")
@@ -133,6 +134,8 @@ def cpu_reference(args, g, li, lt, reads, n_sample, gpu_cells_per_step=None):
     # first `cpu_read_len` bases of each read.  Every sampled row is a dense warm-up row (len < n_warmup) at the full N -- the row
     # type that holds > 99 % of the workload's cells; GCUPS is per cell, so the rate carries over.  (`--cpu-full-reads K` adds K
     # full-length reads; profiles/ holds one such run.)
+    if not args.cpu_read_len:
+        args.cpu_read_len = 8
     sample = [r[:args.cpu_read_len] for r in reads[:n_sample]]
     n_full = min(args.cpu_full_reads, len(reads))
     sample += [r for r in reads[:n_full]]
@@ -164,6 +167,20 @@ def auto_cpu_sample(n_nodes, k):
         avail = 32 << 30
     per_read = 2 * 16 * n_nodes * 24 * 2.5  # stored dense rows of both directions + temporaries
     return int(max(1, min(cores, avail * 0.5 / per_read)))
+
+
+# reads per GPU per step of the device arm on a B200 when --reads-per-gpu is not given: one resident wave of the sparse kernel,
+# 148 SMs x 9 jobs (dbgphmm_model_wave_reads).  The reference arm states the same figure without touching the device.
+B200_WAVE_READS = 148 * 9
+
+
+def workload_config(args, n_nodes, reads_per_gpu):
+    """`config` of the JSON line: the workload and how it is timed.  Both arms print the same dictionary (the reference arm runs a
+    bounded sample of this workload per step and says so in `cpu_baseline.sample`)."""
+    return {"workload": workload_text(args), "n_nodes": int(n_nodes), "reads_per_gpu_per_step": int(reads_per_gpu), "n_active_nodes": 40, "n_warmup": args.k,
+            "l2": "DP rows of one step exceed L2 (each dense row is 28 B x N on the device, 24 B x N in the CPU arm; hundreds of rows in flight)",
+            "timing": "device arm: CUDA events around the bracket of all timed steps (zeroing, library call, ln P reduction, all-reduce), max over ranks; "
+                      "reference arm (--impl reference): host clock around each step's CPU sample, mean over the timed steps"}
 
 
 def workload_text(args):
@@ -243,6 +260,8 @@ def main():
             return 0
         g, li, lt, reads = make_inputs(args, 0, max(args.cpu_sample_reads, 64))
         n_sample = args.cpu_sample_reads or auto_cpu_sample(g.n_nodes, args.k)
+        if not args.cpu_read_len:
+            args.cpu_read_len = 8 if args.steps + args.warmup <= 10 else 4
         vals = []
         for s in range(args.warmup + args.steps):
             r = cpu_reference(args, g, li, lt, reads, n_sample)
@@ -254,9 +273,7 @@ def main():
         print(json.dumps({"metric": "PHMM forward-backward GCUPS", "value": v, "unit": "GCUPS", "impl": "reference", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": workload_text(args), "n_nodes": int(g.n_nodes), "reads_per_step": n_sample,
-                                     "same_config_note": "same graph, parameters, metric and cell definition as the GPU arm; each step is a bounded sample of "
-                                                         "the GPU arm's step (see cpu_baseline.sample) because one full step costs ~60 CPU-hours"},
+                          "config": workload_config(args, g.n_nodes, args.reads_per_gpu or B200_WAVE_READS),
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -419,9 +436,7 @@ def main():
         out = {"metric": "PHMM forward-backward GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "reads_per_s": world * R / (ms_step * 1e-3), "library_ms_per_step": lib_ms / args.steps,
-               "config": {"workload": workload_text(args), "n_nodes": int(N), "reads_per_gpu_per_step": R, "n_active_nodes": 40, "n_warmup": args.k,
-                          "l2": "DP rows of one step exceed L2 (each dense row is 28 B x N, hundreds of rows in flight)",
-                          "timing": "CUDA events around the bracket of all timed steps (zeroing, library call, ln P reduction, all-reduce), max over ranks"},
+               "config": workload_config(args, N, R),
                "roofline": roof,
                "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": int(launches), "clocks": clocks, "checksum": {"sum_logp": sum_logp, "sum_node_freqs": sum_freq}}

@@ -29,6 +29,18 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the reference arm runs on the device arm's `config`: one builder serves both, key for key
+    sys.path.insert(0, ROOT)
+    import bench
+    old_argv, sys.argv = sys.argv, ["bench.py", "--impl", "reference", *TINY]
+    try:
+        args = bench.parse()
+    finally:
+        sys.argv = old_argv
+    assert list(d["config"]) == ["workload", "n_nodes", "reads_per_gpu_per_step", "n_active_nodes", "n_warmup", "l2", "timing"]
+    assert d["config"]["reads_per_gpu_per_step"] == bench.B200_WAVE_READS == 1332
+    assert d["config"] == bench.workload_config(args, d["config"]["n_nodes"], bench.B200_WAVE_READS)
+    assert d["cpu_baseline"]["sample_bases_per_read"] == 8       # 2 + 1 steps: the longer sample; 4 bases from 11 steps on
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
