@@ -122,23 +122,27 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
             for (uint32_t q = 0; q < size; q++) { order.push_back(local[descending ? size - 1 - q : q]); placed[q] = 1; }
             // remaining halo nodes: chains following "x is the first upstream neighbour of the next", deepest first
             for (size_t q = local.size(); q-- > size;) {   // local is depth-sorted: start from the deepest
-                if (placed[q]) continue;
-                uint32_t x = local[q];
-                for (;;) {   // climb to the top of x's unplaced first-neighbour chain
-                    if (up_off[x + 1] == up_off[x]) break;
-                    uint32_t u = up_node[up_off[x]];
-                    if (!in_tile(u) || placed[lidx[u]]) break;
-                    x = u;
-                }
-                for (;;) {   // walk down: append x, then an unplaced halo node whose first neighbour is x
-                    placed[lidx[x]] = 1; order.push_back(x);
-                    uint32_t nxt = 0xffffffffu;
-                    for (size_t r = size; r < local.size(); r++) {
-                        uint32_t y = local[r];
-                        if (!placed[r] && up_off[y + 1] > up_off[y] && up_node[up_off[y]] == x) { nxt = y; break; }
+                // The walk down from the top of local[q]'s chain may leave through another branch of a fork and never come back to
+                // local[q] (its first neighbour can be shallower than itself when that one has a shorter way to the core): repeat
+                // from local[q] until it is placed -- every pass places at least its top node, and stops climbing at placed nodes.
+                while (!placed[q]) {
+                    uint32_t x = local[q];
+                    for (size_t steps = 0; steps < local.size(); steps++) {   // climb to the top of x's unplaced first-neighbour chain
+                        if (up_off[x + 1] == up_off[x]) break;                // (bounded: a cycle of halo nodes has no top)
+                        uint32_t u = up_node[up_off[x]];
+                        if (!in_tile(u) || placed[lidx[u]]) break;
+                        x = u;
                     }
-                    if (nxt == 0xffffffffu) break;
-                    x = nxt;
+                    for (;;) {   // walk down: append x, then an unplaced halo node whose first neighbour is x
+                        placed[lidx[x]] = 1; order.push_back(x);
+                        uint32_t nxt = 0xffffffffu;
+                        for (size_t r = size; r < local.size(); r++) {
+                            uint32_t y = local[r];
+                            if (!placed[r] && up_off[y + 1] > up_off[y] && up_node[up_off[y]] == x) { nxt = y; break; }
+                        }
+                        if (nxt == 0xffffffffu) break;
+                        x = nxt;
+                    }
                 }
             }
             lay.clear();

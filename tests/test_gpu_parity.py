@@ -120,6 +120,38 @@ def test_dense_multi_chunk_graph(H):
         assert_tables_match(g.backward(read), o.backward(read), w.graph.n_nodes, "bwd")
 
 
+def test_dense_rows_on_a_chain_with_cross_edges(H):
+    """Forks and merges inside the halos, short cycles: the tile planner used to lose a halo node whose first upstream neighbour lies
+    on the other branch of a fork (host-side out-of-bounds write, garbage positions on the device).  Found by the sanitizer run of
+    the host logic (tests/test_host_logic_asan.py); here the rows of such a graph against the oracle."""
+    rng = np.random.default_rng(5)
+    n = 1500
+    src, dst = list(range(n - 1)), list(range(1, n))
+    for _ in range(60):
+        v = int(rng.integers(0, n)); w = int(np.clip(v + rng.integers(-30, 30), 0, n - 1))
+        if (v, w) not in set(zip(src, dst)):
+            src.append(v); dst.append(w)
+    base = rng.choice(np.frombuffer(b"ACGT", np.uint8), n)
+    sg = graphs.SeqGraph(src, dst, base, np.ones(n, np.int64))
+    g, o = both(sg, oracle_params(0.01, n_warmup=20))
+    read = bytes(base[400:440])
+    assert_tables_match(g.forward(read), o.forward(read), n, "fwd")
+    assert_tables_match(g.backward(read), o.backward(read), n, "bwd")
+    gs, os_ = g.run(read), o.run(read)
+    assert close_log(gs.to_full_prob_forward(), os_.to_full_prob_forward()).all()
+    assert np.allclose(gs.to_node_freqs(), os_.to_node_freqs(), rtol=REL_TOL, atol=1e-12)
+
+
+def test_dense_rows_on_a_small_k_graph_with_cycles(H):
+    """k = 8: a branchy de Bruijn graph with cycles of halo nodes (the planner's climb to the top of a chain used to spin on them)."""
+    w = _dbg_case(5, glen=3000, k=8, ploidy=1, het=0.0, read_len=40, n_reads=2)
+    par = oracle_params(0.01, n_warmup=w.k)
+    g, o = both(w.graph, par)
+    for read in w.reads:
+        assert_tables_match(g.forward(read), o.forward(read), w.graph.n_nodes, "fwd")
+        assert_tables_match(g.backward(read), o.backward(read), w.graph.n_nodes, "bwd")
+
+
 @pytest.mark.parametrize("seed,n_active", [(0, 40), (1, 10), (3, 80)])
 def test_sparse_topn_rows_bit_exact_sets(H, seed, n_active):
     w = _dbg_case(seed)
