@@ -114,7 +114,7 @@ extern "C" int dbgphmm_mappings_map_nodes(const dbgphmm_mappings* mp, uint32_t n
     // hint.rs:66-88 — per base: every (node, p) spreads p / |node_map(node)| over its images, images that coincide are
     // added (Prob +), the row is re-sorted by probability, descending, and cut to MAX_ACTIVE_NODES.  The reference collects
     // the images in a HashMap, so the order among EQUAL probabilities is unspecified there; here: first appearance first.
-    dbgphmm_mappings* o = new dbgphmm_mappings();
+    std::unique_ptr<dbgphmm_mappings> o(new dbgphmm_mappings());   // (owned until handed out: an exception below must not leak it)
     o->read_off = mp->read_off;
     o->row_off.assign(1, 0);
     std::vector<std::pair<uint32_t, double>> acc;   // (image, ln p) in order of first appearance
@@ -125,10 +125,10 @@ extern "C" int dbgphmm_mappings_map_nodes(const dbgphmm_mappings* mp, uint32_t n
         acc.clear(); where.clear();
         for (uint64_t i = mp->row_off[r]; i < mp->row_off[r + 1]; i++) {
             const uint32_t v = mp->nodes[i];
-            if (v >= n_nodes_before) { delete o; dbg_set_error("mappings_map_nodes: node id out of range of the node map"); return DBGPHMM_ERR_INVALID; }
+            if (v >= n_nodes_before) { dbg_set_error("mappings_map_nodes: node id out of range of the node map"); return DBGPHMM_ERR_INVALID; }
             const uint64_t a = map_off[v], b = map_off[v + 1];
             if (a == b) continue;
-            if (!map_to) { delete o; dbg_set_error("mappings_map_nodes: bad argument"); return DBGPHMM_ERR_INVALID; }
+            if (!map_to) { dbg_set_error("mappings_map_nodes: bad argument"); return DBGPHMM_ERR_INVALID; }
             const double share = mp->logp[i] - std::log((double)(b - a));   // Prob / usize (prob.rs:271-279)
             for (uint64_t j = a; j < b; j++) {
                 auto it = where.find(map_to[j]);
@@ -143,7 +143,7 @@ extern "C" int dbgphmm_mappings_map_nodes(const dbgphmm_mappings* mp, uint32_t n
         for (size_t i = 0; i < keep; i++) { o->nodes.push_back(acc[order[i]].first); o->logp.push_back(acc[order[i]].second); }
         o->row_off.push_back(o->nodes.size());
     }
-    *out = o;
+    *out = o.release();
     return DBGPHMM_OK;
 } ABI_CATCH
 
