@@ -1607,12 +1607,23 @@ static int fast_span(const LinParams& lp) {
     return span < 64 ? -1 : (span > 900 ? 900 : span);
 }
 
-// reads handled by one CTA: the tile structure is staged once per CTA, so as many as still leave ~6 waves of CTAs
+// reads handled by one CTA: the tile structure is staged once per CTA, so as many as still leave ~12 waves of CTAs -- and among the
+// next few splits the one whose last, partly filled wave costs least: the CTAs of a launch take the same time, so a grid of 12.2
+// waves runs as long as one of 13.  Cost model: ceil(waves) x (jobs per CTA + 3), the 3 standing for the per-CTA staging of the tile.
 static uint32_t fast_jobs_per_cta(const dbgphmm_model* m, uint32_t n_chunks, uint32_t n_jobs) {
-    uint32_t target = 8u * 3u * (uint32_t)m->n_sm;
-    uint32_t n_ctas = (n_chunks + WT_WARPS - 1) / WT_WARPS;
-    uint32_t groups = std::max<uint32_t>(1, std::min<uint32_t>(n_jobs, (target + n_ctas - 1) / n_ctas));
-    return (n_jobs + groups - 1) / groups;
+    const uint32_t target = 8u * 3u * (uint32_t)m->n_sm;
+    const uint32_t n_ctas = (n_chunks + WT_WARPS - 1) / WT_WARPS;
+    const uint32_t resident = (uint32_t)WT_MIN_CTAS * (uint32_t)m->n_sm;
+    const uint32_t g0 = std::max<uint32_t>(1, std::min<uint32_t>(n_jobs, (target + n_ctas - 1) / n_ctas));
+    uint32_t best_jpc = (n_jobs + g0 - 1) / g0;
+    uint64_t best_cost = ~0ull;
+    for (uint32_t g = g0; g <= std::min<uint32_t>(n_jobs, g0 + 5); g++) {
+        const uint32_t jpc = (n_jobs + g - 1) / g, groups = (n_jobs + jpc - 1) / jpc;
+        const uint64_t waves = ((uint64_t)n_ctas * groups + resident - 1) / resident;
+        const uint64_t cost = waves * (jpc + 3);
+        if (cost < best_cost) { best_cost = cost; best_jpc = jpc; }
+    }
+    return best_jpc;
 }
 
 int dense_configure(dbgphmm_model* m) {

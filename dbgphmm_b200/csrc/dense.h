@@ -2,7 +2,7 @@
 #pragma once
 #include "model.h"
 
-#define DENSE_CORE 128      // nodes of a tile (owned by one warp of the common-frame kernel)
+#define DENSE_CORE 152      // most nodes a tile may own (the planner shrinks it until tile + halo + alignment pads fit DENSE_LMAX)
 #define DENSE_LMAX 160      // tile + 6-hop halo capacity
 #define DENSE_PER_LANE (DENSE_LMAX / 32)   // register-stencil kernel: consecutive positions owned by one lane
 #define DENSE_EMAX 256      // local upstream edges of one tile

@@ -196,7 +196,7 @@ static int build_plan(DevPlan& P, uint32_t N, const std::vector<uint32_t>& up_of
             // undo stamps and retry with a smaller chunk
             for (uint32_t v : local) stamp[v] = 0xffffffffu;
             if (size == 1) { dbg_set_error("graph too dense: the 6-hop neighbourhood of one node exceeds the tile capacity"); return DBGPHMM_ERR_INVALID; }
-            size = size > 16 ? size - 8 : std::max<uint32_t>(1, size / 2);
+            size = size > 16 ? size - 4 : std::max<uint32_t>(1, size / 2);
         }
         // emit chunk
         uint32_t base = (uint32_t)loc_node.size();
@@ -303,23 +303,38 @@ int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* 
     for (uint32_t e = E; e-- > 0;) { oe[ofill[src[e]]++] = e; ie[ifill[dst[e]]++] = e; }
     auto indeg = [&](uint32_t v) { return ioff[v + 1] - ioff[v]; };
     auto outdeg = [&](uint32_t v) { return ooff[v + 1] - ooff[v]; };
-    // ---- relabel: depth-first over maximal simple chains so that a node's parent is usually its predecessor
+    // ---- relabel: depth-first over maximal simple chains so that a node's parent is usually its predecessor.  A node with several
+    // parents (the merge below a bubble) waits until all of them are labelled: the branches of a bubble then sit next to each other
+    // in the new order, inside the same tile or two, instead of one branch following the main chain and the others being collected
+    // far away at the end of the traversal -- where every one of them costs the tiles on both sides a 6- or 12-hop halo.
     std::vector<uint32_t> orig_of; orig_of.reserve(N);
     std::vector<uint8_t> visited(N, 0);
+    std::vector<uint32_t> waiting(N);   // parents not labelled yet (self loops do not count)
+    for (uint32_t v = 0; v < N; v++) { uint32_t w = 0; for (uint32_t a = ioff[v]; a < ioff[v + 1]; a++) w += src[ie[a]] != v; waiting[v] = w; }
     auto is_head = [&](uint32_t v) {
         if (indeg(v) != 1) return true;
         uint32_t p = src[ie[ioff[v]]];
         return outdeg(p) != 1 || p == v;
     };
-    std::vector<uint32_t> stack;
+    std::vector<uint32_t> stack, deferred;
+    size_t deferred_head = 0;
     auto run_from = [&](uint32_t s) {
         stack.push_back(s);
-        while (!stack.empty()) {
+        bool force = true;   // the start of a traversal, and a deferred node when nothing else is left (cycles), go in as they are
+        for (;;) {
+            if (stack.empty()) {
+                while (deferred_head < deferred.size() && visited[deferred[deferred_head]]) deferred_head++;
+                if (deferred_head == deferred.size()) break;
+                stack.push_back(deferred[deferred_head++]); force = true;
+            }
             uint32_t v = stack.back(); stack.pop_back();
             if (visited[v]) continue;
+            if (!force && waiting[v] > 0) { deferred.push_back(v); continue; }
+            force = false;
             // walk the chain
             for (;;) {
                 visited[v] = 1; orig_of.push_back(v);
+                for (uint32_t a = ooff[v]; a < ooff[v + 1]; a++) { uint32_t c = dst[oe[a]]; if (c != v && waiting[c] > 0) waiting[c]--; }
                 if (outdeg(v) == 1) {
                     uint32_t c = dst[oe[ooff[v]]];
                     if (!visited[c] && !is_head(c)) { v = c; continue; }
@@ -329,6 +344,7 @@ int model_build_graph(dbgphmm_model* m, uint32_t N, uint32_t E, const uint32_t* 
             // children of the tail, pushed so that the newest-first first child is visited first
             for (uint32_t a = ooff[v + 1]; a-- > ooff[v];) { uint32_t c = dst[oe[a]]; if (!visited[c]) stack.push_back(c); }
         }
+        deferred.clear(); deferred_head = 0;
     };
     for (uint32_t v = 0; v < N; v++) if (!visited[v] && indeg(v) == 0) run_from(v);
     for (uint32_t v = 0; v < N; v++) if (!visited[v] && is_head(v)) run_from(v);

@@ -221,6 +221,7 @@ static int run_cache() {
 }
 
 int main(int argc, char** argv) {
+    if (const char* e = getenv("STUB_DEVICE_BYTES")) stub_device_bytes = strtoull(e, nullptr, 10);   // (default 1 GiB)
     if (argc >= 2 && !strcmp(argv[1], "cache")) return run_cache();
     if (argc >= 3 && !strcmp(argv[1], "plan")) { for (int i = 2; i < argc; i++) if (run_plan(argv[i])) return 1; return 0; }
     fprintf(stderr, "usage: host_logic plan <graph.bin>... | cache\n");
