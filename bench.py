@@ -423,7 +423,8 @@ def main():
                 per_cell = sum(c["dram_bytes_per_cell"] for c in caps) / len(caps)
                 traffic = per_cell * (k_cells / max(k_launch, 1))
                 dram_frac = (per_cell * k_cells / (k_ms * 1e-3) / 1e9) / peak if k_ms > 0 else None
-                tsrc = f"profiles/{name} (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell x cells per launch of this run)"
+                tsrc = (f"profiles/{name} (ncu dram__bytes_read.sum + dram__bytes_write.sum per cell x cells per launch of this run; the capture "
+                        "predates the re-tiling at the end of round 2 -- 12 % fewer tiles, so fewer halo cells are read: an upper bound)")
                 break
             except Exception:
                 continue
