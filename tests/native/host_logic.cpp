@@ -43,7 +43,7 @@ int dense_backward_step_list(dbgphmm_model*, const DensePool&, const DJob*, uint
 struct Stats { uint64_t tiles = 0, positions = 0, core = 0, pads = 0, plain = 0, extras = 0; };
 
 // up = parents (forward plans) or children (backward plans), CSR over relabelled ids
-static Stats check_plan(const dbgphmm_model* m, const DevPlan& P, bool fwd, const char* name) {
+static Stats check_plan(const dbgphmm_model* m, const DevPlan& P, bool fwd, const char* name, int hops) {
     Stats st;
     const uint32_t N = m->N, L = DENSE_LMAX, PL = DENSE_PER_LANE;
     const std::vector<uint32_t>& up_off = fwd ? m->par_off : m->chi_off;
@@ -103,6 +103,27 @@ static Stats check_plan(const dbgphmm_model* m, const DevPlan& P, bool fwd, cons
             if (q % PL) CHECK(!(flag[q] & 3) && (eid[q] == 0xffffffffu || par[q] + 1 == q), "%s tile %u pos %u: a special node off slot 0", name, c, q);
             if (x >= g0 && x < g1) CHECK(n_in_tile == deg, "%s tile %u pos %u: core node %u has %u of %u upstream edges in the tile", name, c, q, x, n_in_tile, deg);
         }
+        {   // the tile holds the whole upstream closure of its core over `hops` hops: a node nearer than that has every upstream edge here
+            std::vector<uint32_t> frontier, next; std::vector<int> depth(L, -1);
+            for (uint32_t x : here) if (x >= g0 && x < g1) { depth[pos_of[x]] = 0; frontier.push_back(x); }
+            for (int h = 0; h < hops; h++) {
+                next.clear();
+                for (uint32_t x : frontier)
+                    for (uint32_t a = up_off[x]; a < up_off[x + 1]; a++) {
+                        const uint32_t u = up_node[a];
+                        CHECK(pos_of[u] >= 0, "%s tile %u: node %u at depth %d lacks its upstream neighbour %u", name, c, x, h, u);
+                        if (depth[pos_of[u]] < 0) { depth[pos_of[u]] = h + 1; next.push_back(u); }
+                    }
+                frontier.swap(next);
+            }
+            for (uint32_t x : here) CHECK(depth[pos_of[x]] >= 0, "%s tile %u: node %u is not within %d upstream hops of the core", name, c, x, hops);
+            // and every edge between two nodes of the tile whose head is nearer than `hops` is in the tables (first neighbour or extra)
+            for (uint32_t x : here) {
+                if (depth[pos_of[x]] >= hops) continue;
+                const uint32_t q = (uint32_t)pos_of[x], deg = up_off[x + 1] - up_off[x];
+                CHECK((eid[q] != 0xffffffffu ? 1u : 0u) + (xo[q + 1] - xo[q]) == deg, "%s tile %u pos %u: %u upstream edges, %u in the tables", name, c, q, deg, (eid[q] != 0xffffffffu ? 1u : 0u) + (xo[q + 1] - xo[q]));
+            }
+        }
         for (uint32_t q = 0; q < L; q++) {
             if (is_source[q]) CHECK(flag[q] & 4, "%s tile %u pos %u: read by another position but not flagged as a source", name, c, q);
             if ((flag[q] & 4) && q % PL != PL - 1) plain = false;
@@ -144,10 +165,10 @@ static int run_plan(const char* path) {
         for (uint32_t a = m->chi_off[q] + 1; a < m->chi_off[q + 1]; a++) CHECK(m->chi_eid[a - 1] > m->chi_eid[a], "children not newest edge first");
     }
     printf("%s: N=%u E=%u max_deg=%u\n", path, N, E, m->max_deg);
-    struct { const DevPlan* P; bool fwd; const char* name; } plans[4] = {{&m->fwd, true, "fwd"}, {&m->bwd, false, "bwd"}, {&m->fwd2, true, "fwd2"}, {&m->bwd2, false, "bwd2"}};
+    struct { const DevPlan* P; bool fwd; const char* name; int hops; } plans[4] = {{&m->fwd, true, "fwd", HALO_HOPS}, {&m->bwd, false, "bwd", HALO_HOPS}, {&m->fwd2, true, "fwd2", 2 * HALO_HOPS}, {&m->bwd2, false, "bwd2", 2 * HALO_HOPS}};
     for (auto& pl : plans) {
         if (!pl.P->n_chunks) { printf("  %-4s not available\n", pl.name); continue; }
-        const Stats s = check_plan(m, *pl.P, pl.fwd, pl.name);
+        const Stats s = check_plan(m, *pl.P, pl.fwd, pl.name, pl.hops);
         printf("  %-4s tiles=%llu core/tile=%.1f occupied=%.3f plain_tiles=%.3f extras/tile=%.2f\n", pl.name, (unsigned long long)s.tiles, (double)s.core / s.tiles,
                (double)s.positions / (s.tiles * DENSE_LMAX), (double)s.plain / s.tiles, (double)s.extras / s.tiles);
     }

@@ -102,3 +102,9 @@ def test_tiling_plans_of_many_graph_shapes(host_logic):
         assert f"{name}.bin: N=" in out, out
     assert "random.bin: rejected (graph too dense" in out
     assert out.count("fwd2 tiles=") >= 6 and "not available" not in out.split("random.bin")[0]
+    # tiling efficiency of the C3-like graph: with the branches of a bubble labelled next to each other a two-row tile owns ~138 of
+    # its 160 positions (122 when every alternative branch was labelled at the end of the traversal)
+    import re
+    dip = out.split("diploid.bin")[1].split(".bin")[0]
+    core = {m.group(1): float(m.group(2)) for m in re.finditer(r"(fwd2|bwd2|fwd|bwd)\s+tiles=\d+ core/tile=([0-9.]+)", dip)}
+    assert core["fwd2"] > 132 and core["bwd2"] > 132 and core["fwd"] > 140 and core["bwd"] > 140, core
