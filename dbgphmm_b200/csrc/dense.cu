@@ -1623,7 +1623,7 @@ static uint32_t fast_jobs_per_cta(const dbgphmm_model* m, uint32_t n_chunks, uin
         const uint64_t cost = waves * (jpc + 3);
         if (cost < best_cost) { best_cost = cost; best_jpc = jpc; }
     }
-    return best_jpc;
+    return std::max<uint32_t>(1, best_jpc);
 }
 
 int dense_configure(dbgphmm_model* m) {
